@@ -1,0 +1,201 @@
+/* mapcaller_b200.h -- C ABI of libmapcaller_b200.so
+ *
+ * B200-native (sm_100a) replacement for MapCaller's read-mapping hot path.  The reference has no
+ * plugin/FFI layer: its de-facto operator interface is the set of `extern` C++ functions and
+ * process-wide globals of reference src/structure.h:197-292.  Every entry
+ * point below names the reference interface it replaces.  Plain pointers and sizes only: no STL,
+ * no exceptions, no torch types.  All functions return 0 on success and a negative code on
+ * failure; mc_last_error() then holds a message.  There is NO CPU fallback: every mc_ctx_* call
+ * fails with MC_ERR_CUDA when no sm_100 device / driver is usable.
+ *
+ * Threading: one mc_ctx per GPU; calls on one ctx must be serialised by the caller (the reference
+ * serialises the same state behind OutputLock/ProfileLock, src/ReadMapping.cpp:537,564).
+ * Ownership: inputs are caller-owned and may be released when the call returns; output pointers
+ * are library-owned pinned host memory, valid until the next mc_map_batch/mc_ctx_destroy on the ctx.
+ */
+#ifndef MAPCALLER_B200_H
+#define MAPCALLER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_OK            0
+#define MC_ERR_ARG      -1
+#define MC_ERR_CUDA     -2
+#define MC_ERR_IO       -3
+#define MC_ERR_OVERFLOW -4
+#define MC_ERR_NCCL     -5
+
+#define MC_CHUNK_READS 200   /* ReadChunkSize, reference src/structure.h:24 */
+#define MC_MAX_OCC      50   /* OCC_Thr, reference src/bwt_search.cpp:3 */
+#define MC_MIN_SEED     16   /* MinSeedLength, reference src/structure.h:23 */
+#define MC_MAX_RLEN   4000   /* longest read accepted (keeps the 16-bit profile counters exact) */
+
+const char *mc_last_error(void);
+const char *mc_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Index: the in-memory image of bwaidx_t / bwt_t (reference src/structure.h:32-72) as loaded by
+ * bwa_idx_load + RestoreReferenceInfo (reference src/bwt_index.cpp:150,232).  On-disk format is the
+ * reference's (.bwt .sa .pac .ann .amb; reference src/BWT_Index/bwtindex.c:53-149, bwt.c:174-196,
+ * bntseq.c:59-91) so an index built by either side loads in the other.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mc_index mc_index;
+
+typedef struct {
+    const uint32_t *bwt;      /* interleaved occ+BWT words, 64-byte blocks (bwt_t::bwt) */
+    uint64_t bwt_size;        /* number of uint32 words (bwt_t::bwt_size) */
+    uint64_t primary;         /* bwt_t::primary */
+    uint64_t L2[5];           /* bwt_t::L2 */
+    uint64_t seq_len;         /* bwt_t::seq_len == 2 * genome_size */
+    const uint64_t *sa;       /* sampled suffix array, sa[0] == (uint64_t)-1 (bwt_t::sa) */
+    uint64_t n_sa;            /* bwt_t::n_sa */
+    int32_t sa_intv;          /* bwt_t::sa_intv (32) */
+    const uint8_t *pac;       /* forward-only 2-bit packed reference (bwaidx_t::pac) */
+    int64_t genome_size;      /* GenomeSize == bntseq_t::l_pac */
+    int32_t n_chrom;          /* iChromsomeNum */
+    const int32_t *chrom_len; /* ChromosomeVec[i].len */
+    const char *const *chrom_name; /* ChromosomeVec[i].name (may be NULL) */
+} mc_index_view;
+
+/* Replaces bwa_idx_build() (reference src/BWT_Index/bwtindex.c:77): builds the FM-index of
+ * fwd + revcomp from 2-bit codes (0..3) of the concatenated contigs. */
+int mc_index_build(const uint8_t *fwd_codes, int64_t genome_size, int32_t n_chrom, const int32_t *chrom_len,
+                   const char *const *chrom_name, int32_t n_threads, mc_index **out);
+/* FASTA front end of the same: N / IUPAC bases are replaced exactly as bntseq.c:144,173 does
+ * (srand48(11), lrand48()&3) and recorded in .amb. */
+int mc_index_build_fasta(const char *fasta_path, int32_t n_threads, mc_index **out);
+/* Replaces bwa_idx_load() + RestoreReferenceInfo(). */
+int mc_index_load(const char *prefix, mc_index **out);
+/* Writes <prefix>.bwt/.sa/.pac/.ann/.amb byte-compatible with the reference's builder. */
+int mc_index_save(const mc_index *idx, const char *prefix);
+/* Wraps arrays the caller already holds (e.g. the reference's own bwaidx_t) without copying. */
+int mc_index_wrap(const mc_index_view *view, mc_index **out);
+int mc_index_get(const mc_index *idx, mc_index_view *view);
+void mc_index_free(mc_index *idx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mapping context: one GPU, one full index replica in HBM, the device-resident pile-up profile and
+ * the sequential state the reference keeps in globals (avgDist, totals; src/ReadMapping.cpp:20-21).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mc_ctx mc_ctx;
+
+typedef struct {
+    int32_t paired;            /* bPairEnd: reads arrive as adjacent mates (mate 1 first) */
+    int32_t alg_ksw2;          /* !NW_ALG: 0 = nw_alignment, 1 = ksw2_alignment (-alg) */
+    int32_t max_pos_diff;      /* MaxPosDiff (-indel), default 30 */
+    int32_t max_clip;          /* MaxClipSize (-maxclip), default 5 */
+    int32_t max_dup;           /* iMaxDuplicate (-dup), default 5, 1..15 */
+    float   max_mismatch_rate; /* MaxMisMatchRate (-maxmm), default 0.05f */
+    int32_t update_profile;    /* bVCFoutput: accumulate the pile-up profile */
+    int32_t want_alignments;   /* bSAMoutput: return per-read candidates/fragments for SamReport */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t shard_rank;        /* multi-GPU: this context's position in file order (0 when single) */
+    int32_t shard_count;       /* multi-GPU: number of shards (1 when single) */
+    int32_t reserved[5];
+} mc_params;
+
+void mc_params_default(mc_params *p);   /* defaults of reference src/main.cpp:159-191 */
+
+int mc_ctx_create(const mc_index *idx, const mc_params *params, mc_ctx **out);
+void mc_ctx_destroy(mc_ctx *ctx);
+
+/* One batch = the NEXT n_reads reads of the library in file order (reference chunk protocol,
+ * src/GetData.cpp:85-99): a multiple of MC_CHUNK_READS except for the last batch of a library. */
+typedef struct {
+    int64_t n_reads;
+    const uint8_t *seq;       /* concatenated ASCII bases as read from FASTA/FASTQ (mate 2 NOT yet reversed) */
+    const int64_t *seq_off;   /* n_reads + 1 offsets into seq */
+} mc_batch_in;
+
+/* AlnSummary_t (reference src/structure.h:135-140) + the slice of candidates of this read */
+typedef struct { int32_t score, sub_score, best_idx, cand_begin, n_cand, rlen; } mc_read_out;
+/* AlnCan_t (reference src/structure.h:125-133); frags only for score > 0 */
+typedef struct { int32_t score, orientation, paired_idx, frag_begin, n_frag, pad; } mc_cand_out;
+/* FragPair_t (reference src/structure.h:113-123); aln1 = aln[aln_off .. +aln_len), aln2 follows at aln_off+aln_cap */
+typedef struct { int64_t gPos; int32_t rPos, rLen, gLen, bSimple, aln_off, aln_len, aln_cap, pad; } mc_frag_out;
+/* CoordinatePair_t of GenCoordinatePair (reference src/ReadMapping.cpp:361-394), one per pair */
+typedef struct { int64_t gPos1, gPos2, dist; } mc_pair_out;
+/* what one 200-read chunk adds to the totals under OutputLock (reference src/ReadMapping.cpp:538) */
+typedef struct { int32_t n_reads, mapped, paired, est_distance; int64_t dist_sum, len_sum; } mc_chunk_out;
+
+typedef struct {
+    int64_t n_reads, n_cands, n_frags, n_aln_bytes, n_pairs, n_chunks;
+    const mc_read_out *reads;      /* n_reads (NULL unless want_alignments) */
+    const mc_cand_out *cands;      /* arena; index through reads[].cand_begin */
+    const mc_frag_out *frags;      /* arena; index through cands[].frag_begin */
+    const uint8_t *aln;            /* arena of alignment strings */
+    const mc_pair_out *pairs;      /* n_pairs (paired mode) */
+    const mc_chunk_out *chunks;    /* n_chunks */
+    int32_t replays;               /* chunks re-run because the avgDist speculation missed (diagnostic) */
+} mc_batch_out;
+
+/* Replaces the body of ReadMapping() (reference src/ReadMapping.cpp:416-646) for one batch:
+ * seeding, clustering, pairing, rescue, gapped fills, scoring, pair statistics and the profile
+ * update, bit-identical to a single reference thread processing the same reads in order. */
+int mc_map_batch(mc_ctx *ctx, const mc_batch_in *in, mc_batch_out *out);
+
+/* Sequential state (reference globals iTotalReadNum, iTotalMappingNum, iTotalPairedNum,
+ * TotalPairedDistance, ReadLengthSum, avgDist; src/ReadMapping.cpp:20-21) */
+typedef struct { int64_t total_reads, total_mapped, total_paired, total_distance, read_length_sum; uint32_t avg_dist; uint32_t pad; } mc_totals;
+int mc_get_totals(const mc_ctx *ctx, mc_totals *out);
+int mc_set_totals(mc_ctx *ctx, const mc_totals *in);
+
+/* ---- profile (reference MappingRecordArr / InsertSeqMap / DeleteSeqMap / BreakPointMap /
+ *      InversionSiteVec / TranslocationSiteVec; src/structure.h:152-163,220-221) --------------- */
+
+/* Packs the device counters of [beg, end) into MappingRecord_t records (16 bytes each: uint64
+ * A:12,C:12,G:12,T:12,multi_hit:12,readCount:4 then uint16 F1,R2,F2,R1), saturating/wrapping as the
+ * reference does. `out` must hold (end-beg)*16 bytes. */
+int mc_profile_read(mc_ctx *ctx, int64_t beg, int64_t end, void *out);
+
+typedef struct { int64_t pos; int32_t kind /* 0 ins, 1 del */, len, count, seq_off; } mc_indel_rec;
+/* Unique (pos, kind, sequence) triples with their uint16-wrapped counts, sorted by (kind,pos,seq). */
+int mc_profile_indels(mc_ctx *ctx, const mc_indel_rec **recs, int64_t *n_recs, const uint8_t **seq_arena);
+typedef struct { int64_t pos; int64_t count; } mc_breakpoint_rec;
+int mc_profile_breakpoints(mc_ctx *ctx, const mc_breakpoint_rec **recs, int64_t *n_recs);
+typedef struct { int64_t gPos, dist; } mc_site_rec;
+/* kind 0 = InversionSiteVec, 1 = TranslocationSiteVec, sorted by gPos as the thread-end merge does */
+int mc_profile_sites(mc_ctx *ctx, int32_t kind, const mc_site_rec **recs, int64_t *n_recs);
+
+/* Multi-GPU: sum the device counters / gather the records of all ranks (NCCL over NVLink) so that
+ * rank 0 holds the whole-library profile.  `nccl_comm` is an ncclComm_t. */
+int mc_profile_allreduce(mc_ctx *ctx, void *nccl_comm);
+
+/* ---- operator-level entry points (per-kernel parity tests and micro-benchmarks) ---------------- */
+
+/* BWT_Search (reference src/bwt_search.cpp:121) for n independent (read, start) queries.
+ * codes: concatenated 0..4 codes, off[n+1]; start[n].  out_len/out_freq[n]; out_loc[n*MC_MAX_OCC]. */
+int mc_bwt_search_batch(mc_ctx *ctx, int64_t n, const uint8_t *codes, const int64_t *off, const int32_t *start,
+                        int32_t *out_len, int32_t *out_freq, uint64_t *out_loc);
+/* nw_alignment / ksw2_alignment (reference src/nw_alignment.cpp:18, src/ksw2_alignment.cpp:250) for n
+ * independent problems.  s1/s2 concatenated ASCII with offsets; out1/out2 receive the gapped strings at
+ * out_off[i] (caller provides out_off[i+1]-out_off[i] >= len1+len2); out_len[i] = aligned length. */
+int mc_align_batch(mc_ctx *ctx, int32_t use_ksw2, int64_t n, const uint8_t *s1, const int64_t *off1, const uint8_t *s2,
+                   const int64_t *off2, const int64_t *out_off, uint8_t *out1, uint8_t *out2, int32_t *out_len);
+
+/* ---- measurement hooks ---------------------------------------------------------------------- */
+typedef struct {
+    double ms_seed, ms_locate, ms_cluster, ms_pair, ms_align, ms_profile, ms_h2d, ms_d2h, ms_total;
+    int64_t seed_blocks;      /* 64-byte occ blocks the reference algorithm touches while extending */
+    int64_t locate_blocks;    /* 64-byte blocks touched by the LF walks of bwt_sa */
+    int64_t sa_reads;         /* 8-byte sampled-SA reads */
+    int64_t dp_cells;         /* sum of m*n over the gapped fills */
+    int64_t dp_tasks;
+    int64_t profile_columns;  /* MappingRecord_t columns touched by the pile-up update */
+    int64_t kernel_launches;
+} mc_stats;
+int mc_get_stats(const mc_ctx *ctx, mc_stats *out);   /* accumulated since create / last reset */
+int mc_reset_stats(mc_ctx *ctx);
+/* Device-resident replay used by bench.py: maps a batch whose reads are already in HBM
+ * (uploaded by mc_stage_batch) and returns nothing to the host but the chunk statistics. */
+int mc_stage_batch(mc_ctx *ctx, const mc_batch_in *in, int32_t slot);
+int mc_map_staged(mc_ctx *ctx, int32_t slot, mc_batch_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPCALLER_B200_H */

@@ -1,0 +1,304 @@
+"""ctypes binding of libmapcaller_b200.so (include/mapcaller_b200.h).
+
+This is plumbing for the tests and bench.py: the product is the C-ABI library.  There is no Python or
+CPU implementation behind these classes; if the shared library (built by __graft_entry__.build()) is
+missing, importing fails loudly, and every mapping call fails with MC_ERR_CUDA on a box without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmapcaller_b200.so")
+
+CHUNK_READS = 200
+
+
+class McError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("paired", C.c_int32), ("alg_ksw2", C.c_int32), ("max_pos_diff", C.c_int32), ("max_clip", C.c_int32),
+                ("max_dup", C.c_int32), ("max_mismatch_rate", C.c_float), ("update_profile", C.c_int32),
+                ("want_alignments", C.c_int32), ("device", C.c_int32), ("shard_rank", C.c_int32),
+                ("shard_count", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class IndexView(C.Structure):
+    _fields_ = [("bwt", C.c_void_p), ("bwt_size", C.c_uint64), ("primary", C.c_uint64), ("L2", C.c_uint64 * 5),
+                ("seq_len", C.c_uint64), ("sa", C.c_void_p), ("n_sa", C.c_uint64), ("sa_intv", C.c_int32),
+                ("pac", C.c_void_p), ("genome_size", C.c_int64), ("n_chrom", C.c_int32), ("chrom_len", C.c_void_p),
+                ("chrom_name", C.c_void_p)]
+
+
+class BatchIn(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("seq", C.c_void_p), ("seq_off", C.c_void_p)]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_cands", C.c_int64), ("n_frags", C.c_int64), ("n_aln_bytes", C.c_int64),
+                ("n_pairs", C.c_int64), ("n_chunks", C.c_int64), ("reads", C.c_void_p), ("cands", C.c_void_p),
+                ("frags", C.c_void_p), ("aln", C.c_void_p), ("pairs", C.c_void_p),
+                ("chunks", C.c_void_p), ("replays", C.c_int32)]
+
+
+class Totals(C.Structure):
+    _fields_ = [("total_reads", C.c_int64), ("total_mapped", C.c_int64), ("total_paired", C.c_int64),
+                ("total_distance", C.c_int64), ("read_length_sum", C.c_int64), ("avg_dist", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile",
+                                           "ms_h2d", "ms_d2h", "ms_total")] + \
+               [(k, C.c_int64) for k in ("seed_blocks", "locate_blocks", "sa_reads", "dp_cells", "dp_tasks",
+                                          "profile_columns", "kernel_launches")]
+
+
+READ_DT = np.dtype([("score", "<i4"), ("sub_score", "<i4"), ("best_idx", "<i4"), ("cand_begin", "<i4"), ("n_cand", "<i4"), ("rlen", "<i4")])
+CAND_DT = np.dtype([("score", "<i4"), ("orientation", "<i4"), ("paired_idx", "<i4"), ("frag_begin", "<i4"), ("n_frag", "<i4"), ("pad", "<i4")])
+FRAG_DT = np.dtype([("gPos", "<i8"), ("rPos", "<i4"), ("rLen", "<i4"), ("gLen", "<i4"), ("bSimple", "<i4"), ("aln_off", "<i4"),
+                    ("aln_len", "<i4"), ("aln_cap", "<i4"), ("pad", "<i4")])
+PAIR_DT = np.dtype([("gPos1", "<i8"), ("gPos2", "<i8"), ("dist", "<i8")])
+CHUNK_DT = np.dtype([("n_reads", "<i4"), ("mapped", "<i4"), ("paired", "<i4"), ("est_distance", "<i4"), ("dist_sum", "<i8"), ("len_sum", "<i8")])
+INDEL_DT = np.dtype([("pos", "<i8"), ("kind", "<i4"), ("len", "<i4"), ("count", "<i4"), ("seq_off", "<i4")])
+PROFILE_DT = np.dtype([("bits", "<u8"), ("F1", "<u2"), ("R2", "<u2"), ("F2", "<u2"), ("R1", "<u2")])
+
+_lib = None
+
+
+def lib():
+    """Loads the C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise McError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first" % _LIB_PATH)
+        L = C.CDLL(_LIB_PATH)
+        L.mc_last_error.restype = C.c_char_p
+        L.mc_version.restype = C.c_char_p
+        L.mc_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.mc_index_build_fasta.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.mc_index_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.mc_index_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.mc_index_wrap.argtypes = [C.POINTER(IndexView), C.POINTER(C.c_void_p)]
+        L.mc_index_get.argtypes = [C.c_void_p, C.POINTER(IndexView)]
+        L.mc_index_free.argtypes = [C.c_void_p]
+        L.mc_params_default.argtypes = [C.POINTER(Params)]
+        L.mc_ctx_create.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.c_void_p)]
+        L.mc_ctx_destroy.argtypes = [C.c_void_p]
+        L.mc_map_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut)]
+        L.mc_stage_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.c_int32]
+        L.mc_map_staged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BatchOut)]
+        L.mc_get_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
+        L.mc_set_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
+        L.mc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.mc_reset_stats.argtypes = [C.c_void_p]
+        L.mc_profile_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        L.mc_profile_indels.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
+        L.mc_profile_breakpoints.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.mc_profile_sites.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise McError("%s failed (%d): %s" % (what, rc, lib().mc_last_error().decode()))
+
+
+def _view(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_uint8 * (count * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+class Index:
+    """mc_index: the reference's bwaidx_t image (reference src/structure.h:32-72)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def build(cls, fwd_codes: np.ndarray, chrom_len=None, chrom_name=None, threads: int = 0) -> "Index":
+        fwd_codes = np.ascontiguousarray(fwd_codes, dtype=np.uint8)
+        h = C.c_void_p()
+        if chrom_len is None:
+            chrom_len = [len(fwd_codes)]
+        lens = np.asarray(chrom_len, dtype=np.int32)
+        names = None
+        if chrom_name is not None:
+            names = (C.c_char_p * len(chrom_name))(*[n.encode() for n in chrom_name])
+        _check(lib().mc_index_build(fwd_codes.ctypes.data, len(fwd_codes), len(lens), lens.ctypes.data, names, threads, C.byref(h)), "mc_index_build")
+        return cls(h)
+
+    @classmethod
+    def build_fasta(cls, path: str, threads: int = 0) -> "Index":
+        h = C.c_void_p()
+        _check(lib().mc_index_build_fasta(path.encode(), threads, C.byref(h)), "mc_index_build_fasta")
+        return cls(h)
+
+    @classmethod
+    def load(cls, prefix: str) -> "Index":
+        h = C.c_void_p()
+        _check(lib().mc_index_load(prefix.encode(), C.byref(h)), "mc_index_load")
+        return cls(h)
+
+    def save(self, prefix: str) -> None:
+        _check(lib().mc_index_save(self._h, prefix.encode()), "mc_index_save")
+
+    def view(self) -> IndexView:
+        v = IndexView()
+        _check(lib().mc_index_get(self._h, C.byref(v)), "mc_index_get")
+        return v
+
+    @property
+    def genome_size(self) -> int:
+        return self.view().genome_size
+
+    def close(self):
+        if self._h:
+            lib().mc_index_free(self._h)
+            self._h = None
+
+
+class Context:
+    """mc_ctx: one GPU's mapping state; map_batch() replaces the body of the reference's ReadMapping()."""
+
+    def __init__(self, index: Index, **kw):
+        p = Params()
+        lib().mc_params_default(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError("unknown parameter %s" % k)
+            setattr(p, k, v)
+        self.params = p
+        self._index = index
+        h = C.c_void_p()
+        _check(lib().mc_ctx_create(index._h, C.byref(p), C.byref(h)), "mc_ctx_create")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib().mc_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @staticmethod
+    def _batch(seq: np.ndarray, off: np.ndarray):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        b = BatchIn(len(off) - 1, seq.ctypes.data, off.ctypes.data)
+        return b, (seq, off)
+
+    def _wrap(self, out: BatchOut, copy: bool):
+        f = (lambda x: x.copy()) if copy else (lambda x: x)
+        return dict(reads=f(_view(out.reads, out.n_reads if out.reads else 0, READ_DT)), cands=f(_view(out.cands, out.n_cands, CAND_DT)),
+                    frags=f(_view(out.frags, out.n_frags, FRAG_DT)), aln=f(_view(out.aln, out.n_aln_bytes, np.dtype("u1"))),
+                    pairs=f(_view(out.pairs, out.n_pairs, PAIR_DT)), chunks=f(_view(out.chunks, out.n_chunks, CHUNK_DT)),
+                    replays=out.replays)
+
+    def map_batch(self, seq: np.ndarray, off: np.ndarray, copy: bool = True):
+        b, keep = self._batch(seq, off)
+        out = BatchOut()
+        _check(lib().mc_map_batch(self._h, C.byref(b), C.byref(out)), "mc_map_batch")
+        return self._wrap(out, copy)
+
+    def stage_batch(self, seq: np.ndarray, off: np.ndarray, slot: int = 0):
+        b, keep = self._batch(seq, off)
+        _check(lib().mc_stage_batch(self._h, C.byref(b), slot), "mc_stage_batch")
+
+    def map_staged(self, slot: int = 0, copy: bool = False):
+        out = BatchOut()
+        _check(lib().mc_map_staged(self._h, slot, C.byref(out)), "mc_map_staged")
+        return self._wrap(out, copy)
+
+    def totals(self) -> dict:
+        t = Totals()
+        _check(lib().mc_get_totals(self._h, C.byref(t)), "mc_get_totals")
+        return {k: getattr(t, k) for k, _ in Totals._fields_ if k != "pad"}
+
+    def set_totals(self, **kw):
+        t = Totals()
+        _check(lib().mc_get_totals(self._h, C.byref(t)), "mc_get_totals")
+        for k, v in kw.items():
+            setattr(t, k, v)
+        _check(lib().mc_set_totals(self._h, C.byref(t)), "mc_set_totals")
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(lib().mc_get_stats(self._h, C.byref(s)), "mc_get_stats")
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def reset_stats(self):
+        _check(lib().mc_reset_stats(self._h), "mc_reset_stats")
+
+    def profile(self, beg: int = 0, end: int | None = None) -> np.ndarray:
+        """MappingRecord_t records (reference src/structure.h:152-163) of [beg, end)."""
+        if end is None:
+            end = self._index.genome_size
+        out = np.zeros(end - beg, dtype=PROFILE_DT)
+        _check(lib().mc_profile_read(self._h, beg, end, out.ctypes.data), "mc_profile_read")
+        return out
+
+    def profile_columns(self, beg: int = 0, end: int | None = None) -> np.ndarray:
+        """int32 [n, 10]: A C G T multi_hit readCount F1 R2 F2 R1 (unpacked MappingRecord_t)."""
+        p = self.profile(beg, end)
+        b = p["bits"]
+        cols = [(b >> np.uint64(s)) & np.uint64(0xFFF) for s in (0, 12, 24, 36, 48)] + [(b >> np.uint64(60)) & np.uint64(0xF)]
+        cols += [p["F1"], p["R2"], p["F2"], p["R1"]]
+        return np.stack([c.astype(np.int32) for c in cols], axis=1)
+
+    def indels(self):
+        """[(pos, seq bytes, count)] for insertions, same for deletions (InsertSeqMap / DeleteSeqMap)."""
+        recs, n, arena = C.c_void_p(), C.c_int64(), C.c_void_p()
+        _check(lib().mc_profile_indels(self._h, C.byref(recs), C.byref(n), C.byref(arena)), "mc_profile_indels")
+        r = _view(recs.value, n.value, INDEL_DT)
+        out = ([], [])
+        for x in r:
+            s = C.string_at(arena.value + int(x["seq_off"]), int(x["len"]))
+            out[int(x["kind"])].append((int(x["pos"]), s, int(x["count"])))
+        return out
+
+    def breakpoints(self):
+        recs, n = C.c_void_p(), C.c_int64()
+        _check(lib().mc_profile_breakpoints(self._h, C.byref(recs), C.byref(n)), "mc_profile_breakpoints")
+        a = _view(recs.value, n.value, np.dtype([("pos", "<i8"), ("count", "<i8")]))
+        return [(int(x["pos"]), int(x["count"])) for x in a]
+
+    def sites(self, kind: int):
+        recs, n = C.c_void_p(), C.c_int64()
+        _check(lib().mc_profile_sites(self._h, kind, C.byref(recs), C.byref(n)), "mc_profile_sites")
+        a = _view(recs.value, n.value, np.dtype([("gPos", "<i8"), ("dist", "<i8")]))
+        return [(int(x["gPos"]), int(x["dist"])) for x in a]
+
+
+def unpack_reads(res: dict):
+    """Batch result -> list of dicts shaped like tests/ref_oracle.parse_reads() output (for comparisons)."""
+    reads, cands, frags, aln = res["reads"], res["cands"], res["frags"], res["aln"]
+    out = []
+    alnb = aln.tobytes()
+    for r in reads:
+        cl = []
+        for c in cands[r["cand_begin"]:r["cand_begin"] + r["n_cand"]]:
+            fl = []
+            if c["score"] > 0:
+                for f in frags[c["frag_begin"]:c["frag_begin"] + c["n_frag"]]:
+                    if f["bSimple"]:
+                        a1 = a2 = b""
+                    else:
+                        o, ln, cp = int(f["aln_off"]), int(f["aln_len"]), int(f["aln_cap"])
+                        a1, a2 = alnb[o:o + ln], alnb[o + cp:o + cp + ln]
+                    fl.append((int(f["bSimple"]), int(f["rPos"]), int(f["gPos"]), int(f["rLen"]), int(f["gLen"]), a1, a2))
+            cl.append(dict(score=int(c["score"]), orientation=int(c["orientation"]) if c["score"] > 0 else -1, paired=int(c["paired_idx"]), frags=fl))
+        out.append(dict(rlen=int(r["rlen"]), score=int(r["score"]), sub_score=int(r["sub_score"]), best=int(r["best_idx"]), cands=cl))
+    return out

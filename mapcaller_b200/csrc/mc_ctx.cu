@@ -1,0 +1,689 @@
+// Mapping context and batch controller (C ABI of include/mapcaller_b200.h).
+//
+// Host side of the pipeline: owns the HBM-resident index replica, the arenas of one batch, the
+// device-resident profile and the sequential state of the reference's thread body
+// (src/ReadMapping.cpp:416-646): avgDist and the running totals.  The 200-read chunk protocol and the
+// avgDist feedback (:538-539) are reproduced exactly by speculation: all chunks of a batch are mapped
+// with the current EstiDistance, each pair reports the interval of EstiDistance values that leave its
+// outcome unchanged, and the host walks the chunk statistics in file order, re-running only the chunks
+// whose true EstiDistance falls outside their interval.
+#include "mc_launch.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+void mc_set_error(const char* fmt, ...);
+
+// ---- memory helpers ---------------------------------------------------------------------------------
+#ifdef MC_HOSTEMU
+#define MC_CHECK(x) do { } while (0)
+static int dev_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : -1; }
+static void dev_free(void* p) { free(p); }
+static int host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : -1; }
+static void host_free(void* p) { free(p); }
+static int dev_h2d(void* d, const void* h, size_t n, mc_stream_t) { memcpy(d, h, n); return 0; }
+static int dev_d2h(void* h, const void* d, size_t n, mc_stream_t) { memcpy(h, d, n); return 0; }
+static int dev_d2d(void* d, const void* s, size_t n, mc_stream_t) { memcpy(d, s, n); return 0; }
+static int dev_zero(void* d, size_t n, mc_stream_t) { memset(d, 0, n); return 0; }
+static int dev_sync(mc_stream_t) { return 0; }
+struct mc_event_t { int x; };
+static void ev_create(mc_event_t*) {}
+static void ev_destroy(mc_event_t*) {}
+static void ev_record(mc_event_t*, mc_stream_t) {}
+static double ev_ms(mc_event_t*, mc_event_t*) { return 0; }
+#else
+static int cuda_fail(cudaError_t e, const char* what)
+{
+	if (e == cudaSuccess) return 0;
+	mc_set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+	return -1;
+}
+static int dev_alloc(void** p, size_t n) { return cuda_fail(cudaMalloc(p, n ? n : 1), "cudaMalloc"); }
+static void dev_free(void* p) { if (p) cudaFree(p); }
+static int host_alloc(void** p, size_t n) { return cuda_fail(cudaMallocHost(p, n ? n : 1), "cudaMallocHost"); }
+static void host_free(void* p) { if (p) cudaFreeHost(p); }
+static int dev_h2d(void* d, const void* h, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "H2D copy") : 0; }
+static int dev_d2h(void* h, const void* d, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "D2H copy") : 0; }
+static int dev_d2d(void* d, const void* sp, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemcpyAsync(d, sp, n, cudaMemcpyDeviceToDevice, s), "D2D copy") : 0; }
+static int dev_zero(void* d, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemsetAsync(d, 0, n, s), "memset") : 0; }
+static int dev_sync(mc_stream_t s)
+{
+	if (cuda_fail(cudaStreamSynchronize(s), "stream synchronize")) return -1;
+	return cuda_fail(cudaGetLastError(), "kernel launch");
+}
+typedef cudaEvent_t mc_event_t;
+static void ev_create(mc_event_t* e) { cudaEventCreate(e); }
+static void ev_destroy(mc_event_t* e) { cudaEventDestroy(*e); }
+static void ev_record(mc_event_t* e, mc_stream_t s) { cudaEventRecord(*e, s); }
+static double ev_ms(mc_event_t* a, mc_event_t* b) { float ms = 0; cudaEventElapsedTime(&ms, *a, *b); return ms; }
+#endif
+
+struct DBuf {
+	void* p = nullptr; size_t cap = 0;
+	int reserve(size_t n) // contents are NOT preserved
+	{
+		if (n <= cap) return 0;
+		dev_free(p); p = nullptr; cap = 0;
+		size_t want = n + n / 4 + 256;
+		if (dev_alloc(&p, want)) return -1;
+		cap = want; return 0;
+	}
+	int grow_keep(size_t n, size_t used, mc_stream_t s)
+	{
+		if (n <= cap) return 0;
+		void* q = nullptr; size_t want = n + n / 2 + 256;
+		if (dev_alloc(&q, want)) return -1;
+		if (used) { if (dev_d2d(q, p, used, s) || dev_sync(s)) return -1; }
+		dev_free(p); p = q; cap = want; return 0;
+	}
+	void release() { dev_free(p); p = nullptr; cap = 0; }
+	template <class T> T* as() const { return (T*)p; }
+};
+struct HBuf {
+	void* p = nullptr; size_t cap = 0;
+	int reserve(size_t n)
+	{
+		if (n <= cap) return 0;
+		host_free(p); p = nullptr; cap = 0;
+		size_t want = n + n / 4 + 256;
+		if (host_alloc(&p, want)) return -1;
+		cap = want; return 0;
+	}
+	void release() { host_free(p); p = nullptr; cap = 0; }
+	template <class T> T* as() const { return (T*)p; }
+};
+
+enum { EV_START, EV_H2D, EV_SEED, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_COUNT };
+
+struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key; mc_u64 pad; };
+struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
+
+struct Staged { DBuf seq, roff, seed_off; int64_t n_reads = 0, n_bytes = 0, n_slots = 0; std::vector<int64_t> h_roff; bool valid = false; };
+
+struct mc_ctx {
+	mc_params prm;
+	mc_stream_t stream;
+	// index replica
+	DBuf d_bwt, d_sa, d_pac, d_chrom_end, d_chrom_id;
+	DevIndex ix;
+	int64_t G;
+	// profile
+	DBuf d_cnt16, d_multi, d_rcount;
+	DBuf d_bp, d_ind, d_ind_seq, d_pbump;
+	int64_t bp_cap = 0, ind_cap = 0, ind_seq_cap = 0;
+	// batch arenas
+	Staged cur; Staged slots[4];
+	DBuf d_slot_freq, d_seeds, d_slot_loc, d_loc_slot, d_pairs, d_npair;
+	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
+	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
+	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
+	DBuf d_keys, d_keys_tmp, d_accept, d_sort;
+	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0; int64_t rescue_cap = 1 << 20;
+	// pinned host staging
+	HBuf h_in_seq, h_in_off, h_seed_off, h_small, h_chunk, h_chunk_lo, h_chunk_hi, h_pairs, h_reads, h_cands, h_frags, h_aln, h_misc;
+	std::vector<mc_read_out> reads_out; std::vector<mc_cand_out> cands_out;
+	std::vector<mc_chunk_out> chunks_final;
+	// sequential state
+	mc_totals tot;
+	bool discord_init = false; int64_t discord_gpos = 0, discord_dist = 0;
+	std::vector<mc_site_rec> inv_sites, tnl_sites;
+	// finalize products
+	std::vector<mc_indel_rec> ind_out; std::vector<uint8_t> ind_seq_out; std::vector<mc_breakpoint_rec> bp_out;
+	// stats
+	mc_stats stats; DevStats dstats_last;
+	mc_event_t ev[EV_COUNT];
+};
+
+static void zero_stats(mc_stats* s) { memset(s, 0, sizeof(*s)); }
+
+extern "C" {
+
+void mc_params_default(mc_params* p)
+{
+	memset(p, 0, sizeof(*p));
+	p->paired = 1; p->alg_ksw2 = 0; p->max_pos_diff = 30; p->max_clip = 5; p->max_dup = 5; p->max_mismatch_rate = 0.05f;
+	p->update_profile = 1; p->want_alignments = 0; p->device = 0; p->shard_rank = 0; p->shard_count = 1;
+}
+
+void mc_ctx_destroy(mc_ctx* c)
+{
+	if (!c) return;
+	DBuf* bufs[] = {&c->d_bwt, &c->d_sa, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_cnt16, &c->d_multi, &c->d_rcount, &c->d_bp, &c->d_ind,
+	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
+	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
+	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort};
+	for (DBuf* b : bufs) b->release();
+	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
+	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
+	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc};
+	for (HBuf* b : hb) b->release();
+	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
+#ifndef MC_HOSTEMU
+	if (c->stream) cudaStreamDestroy(c->stream);
+#endif
+	delete c;
+}
+
+int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
+{
+	if (!idx || !params || !out) { mc_set_error("mc_ctx_create: null argument"); return MC_ERR_ARG; }
+	if (params->max_dup < 1 || params->max_dup > 15 || params->max_pos_diff < 0) { mc_set_error("mc_ctx_create: parameter out of range"); return MC_ERR_ARG; }
+	mc_index_view v;
+	if (mc_index_get(idx, &v)) return MC_ERR_ARG;
+	mc_ctx* c = new mc_ctx();
+	c->prm = *params; memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = 1000; zero_stats(&c->stats);
+#ifndef MC_HOSTEMU
+	int ndev = 0;
+	if (cuda_fail(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev <= params->device)
+	{
+		if (ndev <= params->device && ndev > 0) mc_set_error("mc_ctx_create: CUDA device %d not present (%d visible)", params->device, ndev);
+		delete c; return MC_ERR_CUDA;
+	}
+	if (cuda_fail(cudaSetDevice(params->device), "cudaSetDevice")) { delete c; return MC_ERR_CUDA; }
+	if (cuda_fail(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
+#else
+	c->stream = 0;
+#endif
+	for (int i = 0; i < EV_COUNT; i++) ev_create(&c->ev[i]);
+	const int64_t G = v.genome_size; c->G = G;
+	std::vector<int64_t> ends; std::vector<int32_t> ids;
+	{
+		// PosChrIdMap (reference src/bwt_index.cpp:244-255): forward ends ascending, then reverse-strand ends
+		std::vector<std::pair<int64_t, int32_t> > kv; int64_t tot = 0;
+		for (int i = 0; i < v.n_chrom; i++)
+		{
+			int64_t fwd = tot; tot += v.chrom_len[i]; int64_t rev = 2 * G - tot;
+			kv.push_back(std::make_pair(fwd + v.chrom_len[i] - 1, i)); kv.push_back(std::make_pair(rev + v.chrom_len[i] - 1, i));
+		}
+		std::sort(kv.begin(), kv.end());
+		for (size_t i = 0; i < kv.size(); i++) { ends.push_back(kv[i].first); ids.push_back(kv[i].second); }
+	}
+	const size_t pac_bytes = (size_t)(G / 4 + 1);
+	int bad = 0;
+	bad |= c->d_bwt.reserve(v.bwt_size * 4 + 64) || dev_h2d(c->d_bwt.p, v.bwt, v.bwt_size * 4, c->stream);
+	bad |= c->d_sa.reserve(v.n_sa * 8) || dev_h2d(c->d_sa.p, v.sa, v.n_sa * 8, c->stream);
+	bad |= c->d_pac.reserve(pac_bytes + 16) || dev_h2d(c->d_pac.p, v.pac, pac_bytes, c->stream);
+	bad |= c->d_chrom_end.reserve(ends.size() * 8) || dev_h2d(c->d_chrom_end.p, ends.data(), ends.size() * 8, c->stream);
+	bad |= c->d_chrom_id.reserve(ids.size() * 4) || dev_h2d(c->d_chrom_id.p, ids.data(), ids.size() * 4, c->stream);
+	if (params->update_profile)
+	{
+		bad |= c->d_cnt16.reserve((size_t)G * 16) || dev_zero(c->d_cnt16.p, (size_t)G * 16, c->stream);
+		bad |= c->d_multi.reserve((size_t)G * 4) || dev_zero(c->d_multi.p, (size_t)G * 4, c->stream);
+		bad |= c->d_rcount.reserve((size_t)G) || dev_zero(c->d_rcount.p, (size_t)G, c->stream);
+	}
+	bad |= c->d_pbump.reserve(sizeof(PersistBumps)) || dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream);
+	bad |= c->d_bumps.reserve(sizeof(Bumps)) || c->d_stats.reserve(sizeof(DevStats)) || dev_zero(c->d_stats.p, sizeof(DevStats), c->stream);
+	bad |= c->h_small.reserve(4096);
+	bad |= dev_sync(c->stream);
+	if (bad) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
+	DevIndex& ix = c->ix;
+	ix.bwt = c->d_bwt.as<uint32_t>(); ix.sa = c->d_sa.as<uint64_t>(); ix.pac = c->d_pac.as<uint8_t>();
+	ix.chrom_end = c->d_chrom_end.as<int64_t>(); ix.chrom_id = c->d_chrom_id.as<int32_t>(); ix.n_end = (int32_t)ends.size();
+	ix.primary = v.primary; for (int i = 0; i < 5; i++) ix.L2[i] = v.L2[i]; ix.seq_len = v.seq_len; ix.G = G; ix.twoG = 2 * G;
+	*out = c;
+	return MC_OK;
+}
+
+int mc_get_totals(const mc_ctx* c, mc_totals* out) { if (!c || !out) return MC_ERR_ARG; *out = c->tot; return MC_OK; }
+int mc_set_totals(mc_ctx* c, const mc_totals* in) { if (!c || !in) return MC_ERR_ARG; c->tot = *in; return MC_OK; }
+int mc_get_stats(const mc_ctx* c, mc_stats* out) { if (!c || !out) return MC_ERR_ARG; *out = c->stats; out->kernel_launches = g_launches; return MC_OK; }
+int mc_reset_stats(mc_ctx* c) { if (!c) return MC_ERR_ARG; zero_stats(&c->stats); g_launches = 0; return MC_OK; }
+
+} // extern "C"
+
+// ---- staging ------------------------------------------------------------------------------------------
+static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st)
+{
+	const int64_t n = in->n_reads;
+	if (n < 0 || (n > 0 && (!in->seq || !in->seq_off))) { mc_set_error("mc_map_batch: bad batch"); return MC_ERR_ARG; }
+	if (c->prm.paired && (n & 1)) { mc_set_error("mc_map_batch: paired mode needs an even number of reads"); return MC_ERR_ARG; }
+	if (n >= (1ll << MC_KEY_SHIFT)) { mc_set_error("mc_map_batch: at most %lld reads per batch", (1ll << MC_KEY_SHIFT) - 1); return MC_ERR_ARG; }
+	const int64_t base = n ? in->seq_off[0] : 0, bytes = n ? in->seq_off[n] - base : 0;
+	st.h_roff.resize(n + 1);
+	if (c->h_seed_off.reserve((n + 1) * 8) || c->h_in_off.reserve((n + 1) * 8)) return MC_ERR_CUDA;
+	int64_t* so = c->h_seed_off.as<int64_t>(); int64_t* ro = c->h_in_off.as<int64_t>();
+	int64_t slots = 0;
+	for (int64_t i = 0; i < n; i++)
+	{
+		const int64_t len = in->seq_off[i + 1] - in->seq_off[i];
+		if (len < 0 || len > MC_MAX_RLEN) { mc_set_error("mc_map_batch: read %lld has length %lld (limit %d)", (long long)i, (long long)len, MC_MAX_RLEN); return MC_ERR_ARG; }
+		ro[i] = in->seq_off[i] - base; so[i] = slots; slots += len / 17 + 1;
+	}
+	ro[n] = bytes; so[n] = slots;
+	memcpy(st.h_roff.data(), ro, (n + 1) * 8);
+	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 1) * 8)) return MC_ERR_CUDA;
+	// pageable caller memory goes through the pinned staging buffer so the copy is asynchronous
+	if (c->h_in_seq.reserve(bytes)) return MC_ERR_CUDA;
+	if (bytes) memcpy(c->h_in_seq.p, in->seq + base, bytes);
+	if (dev_h2d(st.seq.p, c->h_in_seq.p, bytes, c->stream) || dev_h2d(st.roff.p, ro, (n + 1) * 8, c->stream) || dev_h2d(st.seed_off.p, so, (n + 1) * 8, c->stream)) return MC_ERR_CUDA;
+	st.n_reads = n; st.n_bytes = bytes; st.n_slots = slots; st.valid = true;
+	return MC_OK;
+}
+
+// ---- the batch controller -----------------------------------------------------------------------------
+static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
+{
+	const mc_stream_t s = c->stream;
+	const int64_t n = st.n_reads;
+	const bool paired = c->prm.paired != 0;
+	const int64_t n_pairs = paired ? n / 2 : 0;
+	const int64_t n_chunks = (n + MC_CHUNK_READS - 1) / MC_CHUNK_READS;
+	memset(out, 0, sizeof(*out));
+	if (n == 0) return MC_OK;
+
+	PipeArgs a; memset(&a, 0, sizeof(a));
+	a.ix = c->ix;
+	a.pr.paired = c->prm.paired; a.pr.alg_ksw2 = c->prm.alg_ksw2; a.pr.max_pos_diff = c->prm.max_pos_diff; a.pr.max_clip = c->prm.max_clip;
+	a.pr.max_dup = c->prm.max_dup; a.pr.update_profile = c->prm.update_profile; a.pr.max_mismatch_rate = c->prm.max_mismatch_rate;
+	a.st = c->d_stats.as<DevStats>(); a.n_reads = n; a.seq = st.seq.as<uint8_t>(); a.roff = st.roff.as<int64_t>(); a.seed_off = st.seed_off.as<int64_t>();
+	a.first_read = c->tot.total_reads;
+	a.n_slots = st.n_slots;
+
+	int bad = 0;
+	bad |= c->d_slot_freq.reserve(st.n_slots * 4) || c->d_seeds.reserve(st.n_slots * sizeof(Seed)) || c->d_slot_loc.reserve((st.n_slots + 1) * 8);
+	bad |= c->d_scan.reserve(device_scan_scratch_bytes(st.n_slots));
+	bad |= c->d_npair.reserve(n * 4) || c->d_ncand0.reserve(n * 4) || c->d_ncand.reserve(n * 4) || c->d_rsum.reserve(n * sizeof(ReadSum));
+	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(n_chunks * sizeof(mc_chunk_out));
+	bad |= c->d_chunk_lo.reserve(n_chunks * 4) || c->d_chunk_hi.reserve(n_chunks * 4);
+	bad |= c->d_pair_flag.reserve((n_pairs + 1) * 4) || c->d_est_lo.reserve((n_pairs + 1) * 4) || c->d_est_hi.reserve((n_pairs + 1) * 4);
+	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4) || c->d_accept.reserve(n + 1);
+	bad |= c->h_chunk.reserve(n_chunks * sizeof(mc_chunk_out)) || c->h_chunk_lo.reserve(n_chunks * 4) || c->h_chunk_hi.reserve(n_chunks * 4);
+	if (bad) return MC_ERR_CUDA;
+	a.slot_freq = c->d_slot_freq.as<uint32_t>(); a.seeds = c->d_seeds.as<Seed>(); a.slot_loc = c->d_slot_loc.as<int64_t>();
+	a.npair = c->d_npair.as<int32_t>(); a.ncand0 = c->d_ncand0.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
+	a.est = c->d_est.as<int32_t>(); a.active = c->d_active.as<uint8_t>(); a.chunk_out = c->d_chunk_out.as<mc_chunk_out>();
+	a.chunk_lo = c->d_chunk_lo.as<int32_t>(); a.chunk_hi = c->d_chunk_hi.as<int32_t>();
+	a.pair_flag = c->d_pair_flag.as<int32_t>(); a.est_lo = c->d_est_lo.as<int32_t>(); a.est_hi = c->d_est_hi.as<int32_t>();
+	a.pair_out = c->d_pair_out.as<mc_pair_out>(); a.rtask = c->d_rtask.as<int32_t>();
+	Bumps* db = c->d_bumps.as<Bumps>();
+	a.pair_bump = &db->pair; a.frag_bump = &db->frag; a.aln_bump = &db->aln; a.task_bump = &db->task; a.dpws_bump = &db->dpws; a.rtask_bump = &db->rtask;
+	a.prof.cnt16 = c->d_cnt16.as<uint32_t>(); a.prof.multi = c->d_multi.as<uint32_t>(); a.prof.rcount = c->d_rcount.as<uint8_t>();
+
+	// ---- seeding ----
+	ev_record(&c->ev[EV_H2D], s);
+	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats), s);
+	if (prep_needed) launch_prep(a, n, s);
+	launch_seed(a, n, s);
+	ev_record(&c->ev[EV_SEED], s);
+	device_scan_u32(a.slot_freq, c->d_slot_loc.as<int64_t>(), st.n_slots, c->d_scan.as<int64_t>(), s);
+	int64_t* h_small = c->h_small.as<int64_t>();
+	bad |= dev_d2h(h_small, c->d_slot_loc.as<int64_t>() + st.n_slots, 8, s) || dev_sync(s);
+	if (bad) return MC_ERR_CUDA;
+	const int64_t n_locs = h_small[0];
+	a.n_locs = n_locs;
+
+	// ---- locate + cluster ----
+	const int64_t cand_total = (paired ? 2 : 1) * n_locs + 1;
+	for (;;) // arenas may have to grow (overflow flag) -> retry from here
+	{
+		const int64_t pair_cap = n_locs + c->rescue_cap;
+		const int64_t frag_cap = (int64_t)(c->frag_factor * (double)(n_locs + 1024)) + n;
+		const int64_t aln_cap = (int64_t)(c->aln_factor * (double)st.n_bytes) + (1 << 20);
+		const int64_t dpws_cap = (int64_t)(c->dpws_factor * (double)st.n_bytes) + (8 << 20);
+		const int64_t task_cap = n + 1024;
+		if (frag_cap >= 0x7fffffffll || aln_cap >= 0x7fffffffll) { mc_set_error("mc_map_batch: batch too large for 32-bit arena offsets; split it"); return MC_ERR_ARG; }
+		bad |= c->d_loc_slot.reserve((n_locs + 1) * 4) || c->d_pairs.reserve(pair_cap * sizeof(SPair));
+		bad |= c->d_cands.reserve(cand_total * sizeof(Cand)) || c->d_cscore.reserve(cand_total * 4) || c->d_cpaired.reserve(cand_total * 4);
+		bad |= c->d_corient.reserve(cand_total * 4) || c->d_cfrag.reserve(cand_total * 4) || c->d_cnfrag.reserve(cand_total * 4) || c->d_ctmp.reserve(cand_total * 4);
+		bad |= c->d_frags.reserve(frag_cap * sizeof(mc_frag_out)) || c->d_aln.reserve(aln_cap) || c->d_tasks.reserve(task_cap * sizeof(DpTask)) || c->d_dpws.reserve(dpws_cap);
+		if (bad) return MC_ERR_CUDA;
+		a.loc_slot = c->d_loc_slot.as<int32_t>(); a.pairs = c->d_pairs.as<SPair>(); a.pair_cap = pair_cap;
+		a.cands = c->d_cands.as<Cand>(); a.cscore = c->d_cscore.as<int32_t>(); a.cpaired = c->d_cpaired.as<int32_t>(); a.corient = c->d_corient.as<int32_t>();
+		a.cfrag = c->d_cfrag.as<int32_t>(); a.cnfrag = c->d_cnfrag.as<int32_t>(); a.ctmp = c->d_ctmp.as<int32_t>();
+		a.frags = c->d_frags.as<mc_frag_out>(); a.frag_cap = frag_cap; a.aln = c->d_aln.as<uint8_t>(); a.aln_cap = aln_cap;
+		a.tasks = c->d_tasks.as<DpTask>(); a.task_cap = task_cap; a.dpws = c->d_dpws.as<uint8_t>(); a.dpws_cap = dpws_cap;
+
+		launch_expand(a, st.n_slots, s);
+		launch_locate(a, n_locs, s);
+		ev_record(&c->ev[EV_LOCATE], s);
+		launch_cluster(a, n, s);
+		ev_record(&c->ev[EV_CLUSTER], s);
+
+		// ---- speculative pairing / alignment with avgDist verification ----
+		std::vector<int32_t> est(n_chunks, (int32_t)(c->tot.avg_dist * 1.5));
+		std::vector<uint8_t> active(n_chunks, 1), computed(n_chunks, 0);
+		// avgDist stays at its initial value until more than 1000 pairs have been seen (src/ReadMapping.cpp:539) and then
+		// jumps: while warming up only the chunks that can still use the initial value are speculated on
+		if (paired && c->tot.total_paired <= 1000)
+			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2; k < n_chunks; k++) active[k] = 0;
+		Bumps hb; memset(&hb, 0, sizeof(hb)); hb.pair = (mc_u64)n_locs;
+		bad |= dev_h2d(db, &hb, sizeof(hb), s);
+		mc_totals run = c->tot;
+		c->chunks_final.assign(n_chunks, mc_chunk_out());
+		int64_t first_open = 0, prev_tasks = 0, prev_rtasks = 0;
+		int replays = 0; bool overflow = false, first_attempt = true;
+		ev_record(&c->ev[EV_PAIR0], s);
+		while (first_open < n_chunks)
+		{
+			bad |= dev_h2d(c->d_est.p, est.data(), n_chunks * 4, s) || dev_h2d(c->d_active.p, active.data(), n_chunks, s);
+			if (paired) launch_pair(a, n_pairs, s); else launch_single(a, n, s);
+			if (paired)
+			{
+				bad |= dev_d2h(h_small, &db->rtask, 8, s) || dev_sync(s);
+				if (bad) return MC_ERR_CUDA;
+				const int64_t rt = h_small[0];
+				// rescue tasks of this attempt are rtask[prev_rtasks, rt)
+				if (rt > prev_rtasks) { PipeArgs b = a; b.rtask = a.rtask + prev_rtasks; launch_rescue(b, rt - prev_rtasks, s); }
+				prev_rtasks = rt;
+			}
+			if (first_attempt) ev_record(&c->ev[EV_PAIR1], s);
+			first_attempt = false;
+			launch_alnprep(a, n, s);
+			bad |= dev_d2h(h_small, &db->task, 8, s) || dev_sync(s);
+			if (bad) return MC_ERR_CUDA;
+			int64_t nt = h_small[0]; if (nt > task_cap) nt = task_cap;
+			if (nt > prev_tasks) { PipeArgs b = a; b.tasks = a.tasks + prev_tasks; launch_dp(b, nt - prev_tasks, s); }
+			prev_tasks = nt;
+			launch_alnfin(a, n, s);
+			if (paired) launch_pairstat(a, n_pairs, s);
+			launch_chunkstat(a, n_chunks, s);
+			DevStats* hst = (DevStats*)(h_small + 8);
+			bad |= dev_d2h(c->h_chunk.p, c->d_chunk_out.p, n_chunks * sizeof(mc_chunk_out), s) || dev_d2h(c->h_chunk_lo.p, c->d_chunk_lo.p, n_chunks * 4, s);
+			bad |= dev_d2h(c->h_chunk_hi.p, c->d_chunk_hi.p, n_chunks * 4, s) || dev_d2h(hst, c->d_stats.p, sizeof(DevStats), s) || dev_sync(s);
+			if (bad) return MC_ERR_CUDA;
+			if (hst->overflow) { overflow = true; break; }
+			for (int64_t k = 0; k < n_chunks; k++) if (active[k]) computed[k] = 1;
+			// walk the chunks in file order (reference src/ReadMapping.cpp:537-539)
+			const mc_chunk_out* hc = c->h_chunk.as<mc_chunk_out>(); const int32_t* lo = c->h_chunk_lo.as<int32_t>(); const int32_t* hi = c->h_chunk_hi.as<int32_t>();
+			std::fill(active.begin(), active.end(), 0);
+			while (first_open < n_chunks)
+			{
+				const int64_t k = first_open;
+				const int32_t true_est = (int32_t)(run.avg_dist * 1.5);
+				if (!computed[k] || (paired && !(lo[k] <= true_est && true_est <= hi[k])))
+				{
+					// (re)run everything from here on with the value this chunk really sees
+					if (computed[k]) replays++;
+					for (int64_t j = k; j < n_chunks; j++) { est[j] = true_est; active[j] = 1; computed[j] = 0; }
+					break;
+				}
+				mc_chunk_out ck = hc[k]; ck.est_distance = paired ? true_est : 0;
+				c->chunks_final[k] = ck;
+				run.total_reads += ck.n_reads; run.total_mapped += ck.mapped; run.total_paired += ck.paired;
+				run.total_distance += ck.dist_sum; run.read_length_sum += ck.len_sum;
+				if (paired && run.total_paired > 1000) run.avg_dist = (uint32_t)(int)(1. * run.total_distance / run.total_paired + .5);
+				first_open++;
+			}
+		}
+		if (overflow)
+		{
+			c->frag_factor *= 2; c->aln_factor *= 2; c->dpws_factor *= 4; c->rescue_cap *= 4;
+			if (c->frag_factor > 4096) { mc_set_error("mc_map_batch: arena overflow persists"); return MC_ERR_OVERFLOW; }
+			if (getenv("MC_DEBUG")) fprintf(stderr, "[mc] arena overflow: growing (frag x%.0f aln x%.0f dpws x%.0f rescue %lld)\n", c->frag_factor, c->aln_factor, c->dpws_factor, (long long)c->rescue_cap);
+			bad |= dev_zero(&c->d_stats.as<DevStats>()->locate_blocks, sizeof(DevStats) - sizeof(mc_u64), s); // keep only the seeding counter
+			continue;
+		}
+		ev_record(&c->ev[EV_ALN1], s);
+		out->replays = replays;
+
+		// ---- profile ----
+		bad |= dev_d2h(&hb, db, sizeof(hb), s) || dev_sync(s);
+		if (bad) return MC_ERR_CUDA;
+		ev_record(&c->ev[EV_PROF0], s);
+		if (c->prm.update_profile)
+		{
+			PersistBumps pb;
+			bad |= dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s);
+			const int64_t need_bp = (int64_t)pb.bp + 2 * n, need_ind = (int64_t)pb.ind + (int64_t)hb.frag + 16, need_seq = (int64_t)pb.ind_seq + (int64_t)hb.aln + 16;
+			bad |= c->d_bp.grow_keep(need_bp * 8, pb.bp * 8, s) || c->d_ind.grow_keep(need_ind * sizeof(mc_indel_rec), pb.ind * sizeof(mc_indel_rec), s);
+			bad |= c->d_ind_seq.grow_keep(need_seq, pb.ind_seq, s);
+			bad |= c->d_keys.reserve((n + 1) * 8) || c->d_keys_tmp.reserve((n + 1) * 8) || c->d_sort.reserve(device_sort_scratch_bytes(n));
+			if (bad) return MC_ERR_CUDA;
+			c->bp_cap = c->d_bp.cap / 8; c->ind_cap = c->d_ind.cap / sizeof(mc_indel_rec); c->ind_seq_cap = c->d_ind_seq.cap;
+			if (c->ind_seq_cap >= 0x7fffffffll) { mc_set_error("indel sequence arena exceeds 2 GiB; call mc_profile_indels() earlier"); return MC_ERR_OVERFLOW; }
+			PersistBumps* dpb = c->d_pbump.as<PersistBumps>();
+			ProfArgs q; memset(&q, 0, sizeof(q));
+			q.keys = c->d_keys.as<uint64_t>(); q.key_bump = &db->key; q.accept = c->d_accept.as<uint8_t>();
+			q.bp_pos = c->d_bp.as<int64_t>(); q.bp_bump = &dpb->bp; q.bp_cap = c->bp_cap;
+			q.ind = c->d_ind.as<mc_indel_rec>(); q.ind_bump = &dpb->ind; q.ind_cap = c->ind_cap;
+			q.ind_seq = c->d_ind_seq.as<uint8_t>(); q.ind_seq_bump = &dpb->ind_seq; q.ind_seq_cap = c->ind_seq_cap;
+			launch_profkey(a, q, n, s);
+			bad |= dev_d2h(h_small, &db->key, 8, s) || dev_sync(s);
+			if (bad) return MC_ERR_CUDA;
+			q.n_keys = h_small[0];
+			device_sort_u64(q.keys, c->d_keys_tmp.as<uint64_t>(), q.n_keys, c->d_sort.p, c->d_sort.cap, s);
+			launch_gate(a, q, q.n_keys, s);
+			launch_gateupd(a, q, q.n_keys, s);
+			launch_scatter(a, q, n, s);
+		}
+		ev_record(&c->ev[EV_PROF1], s);
+
+		// ---- results back to the host ----
+		bad |= c->h_pairs.reserve((n_pairs + 1) * sizeof(mc_pair_out));
+		if (paired) bad |= dev_d2h(c->h_pairs.p, c->d_pair_out.p, n_pairs * sizeof(mc_pair_out), s);
+		int64_t n_cand_out = 0;
+		if (c->prm.want_alignments)
+		{
+			const size_t cb = (size_t)cand_total * 4;
+			bad |= c->h_reads.reserve(n * (sizeof(ReadSum) + 4)) || c->h_cands.reserve(cb * 5) || c->h_frags.reserve((size_t)hb.frag * sizeof(mc_frag_out)) || c->h_aln.reserve((size_t)hb.aln + 16);
+			if (bad) return MC_ERR_CUDA;
+			bad |= dev_d2h(c->h_reads.p, c->d_rsum.p, n * sizeof(ReadSum), s) || dev_d2h(c->h_reads.as<uint8_t>() + n * sizeof(ReadSum), c->d_ncand.p, n * 4, s);
+			uint8_t* hcb = c->h_cands.as<uint8_t>();
+			bad |= dev_d2h(hcb, c->d_cscore.p, cb, s) || dev_d2h(hcb + cb, c->d_cpaired.p, cb, s) || dev_d2h(hcb + 2 * cb, c->d_corient.p, cb, s);
+			bad |= dev_d2h(hcb + 3 * cb, c->d_cfrag.p, cb, s) || dev_d2h(hcb + 4 * cb, c->d_cnfrag.p, cb, s);
+			bad |= dev_d2h(c->h_frags.p, c->d_frags.p, (size_t)hb.frag * sizeof(mc_frag_out), s) || dev_d2h(c->h_aln.p, c->d_aln.p, (size_t)hb.aln, s);
+		}
+		DevStats* hst = (DevStats*)(h_small + 8);
+		bad |= dev_d2h(hst, c->d_stats.p, sizeof(DevStats), s);
+		ev_record(&c->ev[EV_D2H], s);
+		bad |= dev_sync(s);
+		if (bad) return MC_ERR_CUDA;
+		if (hst->overflow) { mc_set_error("mc_map_batch: persistent profile arena overflow"); return MC_ERR_OVERFLOW; }
+
+		if (c->prm.want_alignments)
+		{
+			const ReadSum* rs = c->h_reads.as<ReadSum>(); const int32_t* nc = (const int32_t*)(c->h_reads.as<uint8_t>() + n * sizeof(ReadSum));
+			const size_t ct = (size_t)cand_total; const int32_t* hc = c->h_cands.as<int32_t>();
+			c->reads_out.resize(n); c->cands_out.clear();
+			for (int64_t r = 0; r < n; r++)
+			{
+				// candidate slice of read r inside the device arena (same formula as pa_cand_off)
+				int64_t po0, co;
+				const int64_t* so = nullptr; (void)so;
+				mc_read_out ro; ro.score = rs[r].score; ro.sub_score = rs[r].sub_score; ro.best_idx = rs[r].best_idx; ro.n_cand = nc[r];
+				ro.rlen = (int32_t)(st.h_roff[r + 1] - st.h_roff[r]); ro.cand_begin = (int32_t)c->cands_out.size();
+				(void)po0; (void)co;
+				c->reads_out[r] = ro;
+				// filled below once the offsets are known
+			}
+			n_cand_out = (int64_t)ct; (void)hc;
+		}
+
+		// pair classification that the reference does in file order with thread-local state (src/ReadMapping.cpp:486-522)
+		if (paired && c->prm.update_profile)
+		{
+			const mc_pair_out* hp = c->h_pairs.as<mc_pair_out>();
+			const int64_t G = c->G, twoG = 2 * c->G;
+			for (int64_t p = 0; p < n_pairs; p++)
+			{
+				const mc_pair_out& q = hp[p];
+				if (q.dist == 0 || q.gPos1 == -1 || q.gPos2 == -1) continue;
+				if (q.gPos1 < G && q.gPos2 >= G)
+				{
+					c->discord_dist = llabs(twoG - q.gPos1 - q.gPos2);
+					if (c->discord_dist > 1000 && c->discord_dist < 10000000) { c->discord_gpos = q.gPos1; c->inv_sites.push_back({c->discord_gpos, c->discord_dist}); }
+				}
+				else if (q.gPos1 >= G && q.gPos2 < G)
+				{
+					c->discord_dist = llabs(twoG - q.gPos1 - q.gPos2);
+					if (c->discord_dist > 1000 && c->discord_dist < 10000000) c->discord_gpos = q.gPos2;
+					c->inv_sites.push_back({c->discord_gpos, c->discord_dist}); // the reference pushes unconditionally here (:502)
+				}
+				else if (q.dist > 1000)
+				{
+					c->discord_dist = q.dist;
+					if (q.gPos1 < G && q.gPos2 < G) { c->tnl_sites.push_back({q.gPos1, q.dist}); c->tnl_sites.push_back({q.gPos2, q.dist}); c->discord_gpos = q.gPos2; }
+					else if (q.gPos1 >= G && q.gPos2 >= G) { c->tnl_sites.push_back({twoG - q.gPos1, q.dist}); c->tnl_sites.push_back({twoG - q.gPos2, q.dist}); c->discord_gpos = twoG - q.gPos2; }
+				}
+			}
+		}
+
+		c->tot = run;
+		// stats
+		c->stats.ms_h2d += ev_ms(&c->ev[EV_START], &c->ev[EV_H2D]);
+		c->stats.ms_seed += ev_ms(&c->ev[EV_H2D], &c->ev[EV_SEED]);
+		c->stats.ms_locate += ev_ms(&c->ev[EV_SEED], &c->ev[EV_LOCATE]);
+		c->stats.ms_cluster += ev_ms(&c->ev[EV_LOCATE], &c->ev[EV_CLUSTER]);
+		c->stats.ms_pair += ev_ms(&c->ev[EV_PAIR0], &c->ev[EV_PAIR1]);
+		c->stats.ms_align += ev_ms(&c->ev[EV_PAIR1], &c->ev[EV_ALN1]);
+		c->stats.ms_profile += ev_ms(&c->ev[EV_PROF0], &c->ev[EV_PROF1]);
+		c->stats.ms_d2h += ev_ms(&c->ev[EV_PROF1], &c->ev[EV_D2H]);
+		c->stats.ms_total += ev_ms(&c->ev[EV_START], &c->ev[EV_D2H]);
+		c->stats.seed_blocks += hst->seed_blocks; c->stats.locate_blocks += hst->locate_blocks; c->stats.sa_reads += hst->sa_reads;
+		c->stats.dp_cells += hst->dp_cells; c->stats.dp_tasks += hst->dp_tasks; c->stats.profile_columns += hst->profile_columns;
+		c->dstats_last = *hst;
+
+		out->n_reads = n; out->n_pairs = n_pairs; out->n_chunks = n_chunks;
+		out->pairs = paired ? c->h_pairs.as<mc_pair_out>() : nullptr;
+		out->chunks = c->chunks_final.data();
+		if (c->prm.want_alignments)
+		{
+			// rebuild the per-read candidate table from the device's structure-of-arrays
+			const size_t ct = (size_t)cand_total; const int32_t* hc = c->h_cands.as<int32_t>();
+			const int32_t *sc = hc, *pi = hc + ct, *ori = hc + 2 * ct, *fb = hc + 3 * ct, *nf = hc + 4 * ct;
+			// device candidate offsets need the per-read pair offsets: recompute them from slot_loc on the host side is not
+			// possible without another copy, so fetch the two small arrays that define them
+			std::vector<int64_t> slot_loc(st.n_slots + 1);
+			bad |= dev_d2h(slot_loc.data(), c->d_slot_loc.p, (st.n_slots + 1) * 8, s) || dev_sync(s);
+			if (bad) return MC_ERR_CUDA;
+			const int64_t* so = c->h_seed_off.as<int64_t>();
+			c->cands_out.clear();
+			for (int64_t r = 0; r < n; r++)
+			{
+				int64_t co;
+				if (!paired) co = slot_loc[so[r]];
+				else { int64_t r0 = r & ~1ll; int64_t base = 2 * slot_loc[so[r0]]; co = (r & 1) ? base + (slot_loc[so[r0 + 2]] - slot_loc[so[r0]]) : base; }
+				mc_read_out& ro = c->reads_out[r];
+				ro.cand_begin = (int32_t)c->cands_out.size();
+				for (int k = 0; k < ro.n_cand; k++)
+				{
+					mc_cand_out o; o.score = sc[co + k]; o.orientation = o.score > 0 ? ori[co + k] : -1; o.paired_idx = pi[co + k];
+					o.frag_begin = o.score > 0 ? fb[co + k] : 0; o.n_frag = o.score > 0 ? nf[co + k] : 0; o.pad = 0;
+					c->cands_out.push_back(o);
+				}
+			}
+			out->reads = c->reads_out.data(); out->cands = c->cands_out.data(); out->n_cands = (int64_t)c->cands_out.size();
+			out->frags = c->h_frags.as<mc_frag_out>(); out->n_frags = (int64_t)hb.frag; out->aln = c->h_aln.as<uint8_t>(); out->n_aln_bytes = (int64_t)hb.aln;
+		}
+		(void)n_cand_out;
+		return MC_OK;
+	}
+}
+
+extern "C" {
+
+int mc_map_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
+{
+	if (!c || !in || !out) { mc_set_error("mc_map_batch: null argument"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	ev_record(&c->ev[EV_START], c->stream);
+	int rc = stage_reads(c, in, c->cur);
+	if (rc) return rc;
+	return run_batch(c, c->cur, out, true);
+}
+
+int mc_stage_batch(mc_ctx* c, const mc_batch_in* in, int32_t slot)
+{
+	if (!c || !in || slot < 0 || slot >= 4) { mc_set_error("mc_stage_batch: bad argument"); return MC_ERR_ARG; }
+	int rc = stage_reads(c, in, c->slots[slot]);
+	if (rc) return rc;
+	// reverse-complement mate 2 once; the staged copy is then immutable
+	PipeArgs a; memset(&a, 0, sizeof(a));
+	a.pr.paired = c->prm.paired; a.seq = c->slots[slot].seq.as<uint8_t>(); a.roff = c->slots[slot].roff.as<int64_t>(); a.n_reads = in->n_reads;
+	launch_prep(a, in->n_reads, c->stream);
+	return dev_sync(c->stream) ? MC_ERR_CUDA : MC_OK;
+}
+
+int mc_map_staged(mc_ctx* c, int32_t slot, mc_batch_out* out)
+{
+	if (!c || !out || slot < 0 || slot >= 4 || !c->slots[slot].valid) { mc_set_error("mc_map_staged: slot not staged"); return MC_ERR_ARG; }
+	ev_record(&c->ev[EV_START], c->stream);
+	// stage_reads left this slot's seed offsets in the shared pinned buffer only transiently: rebuild them
+	Staged& st = c->slots[slot];
+	if (c->h_seed_off.reserve((st.n_reads + 1) * 8)) return MC_ERR_CUDA;
+	int64_t* so = c->h_seed_off.as<int64_t>(); int64_t slots = 0;
+	for (int64_t i = 0; i < st.n_reads; i++) { so[i] = slots; slots += (st.h_roff[i + 1] - st.h_roff[i]) / 17 + 1; }
+	so[st.n_reads] = slots;
+	return run_batch(c, st, out, false);
+}
+
+int mc_profile_read(mc_ctx* c, int64_t beg, int64_t end, void* outp)
+{
+	if (!c || !outp || beg < 0 || end > c->G || beg > end) { mc_set_error("mc_profile_read: bad range"); return MC_ERR_ARG; }
+	if (!c->prm.update_profile) { mc_set_error("mc_profile_read: context was created without update_profile"); return MC_ERR_ARG; }
+	DevProfile p; p.cnt16 = c->d_cnt16.as<uint32_t>(); p.multi = c->d_multi.as<uint32_t>(); p.rcount = c->d_rcount.as<uint8_t>();
+	const int64_t tile = 1 << 24;
+	if (c->d_sort.reserve((size_t)tile * 16)) return MC_ERR_CUDA;
+	for (int64_t b = beg; b < end; b += tile)
+	{
+		const int64_t m = std::min(tile, end - b);
+		launch_profpack(p, b, m, c->d_sort.as<uint64_t>(), c->stream);
+		if (dev_d2h((uint8_t*)outp + (b - beg) * 16, c->d_sort.p, (size_t)m * 16, c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
+	}
+	return MC_OK;
+}
+
+int mc_profile_indels(mc_ctx* c, const mc_indel_rec** recs, int64_t* n_recs, const uint8_t** seq_arena)
+{
+	if (!c || !recs || !n_recs || !seq_arena) { mc_set_error("mc_profile_indels: null argument"); return MC_ERR_ARG; }
+	PersistBumps pb;
+	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
+	std::vector<mc_indel_rec> raw((size_t)pb.ind); std::vector<uint8_t> seq((size_t)pb.ind_seq + 1);
+	if (dev_d2h(raw.data(), c->d_ind.p, raw.size() * sizeof(mc_indel_rec), c->stream) || dev_d2h(seq.data(), c->d_ind_seq.p, (size_t)pb.ind_seq, c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
+	// aggregate like map<int64, map<string, uint16_t>>::operator[]++ (reference src/AlignmentProfile.cpp:123,129)
+	std::map<std::pair<int, int64_t>, std::map<std::string, uint32_t> > agg;
+	for (size_t i = 0; i < raw.size(); i++)
+		agg[std::make_pair(raw[i].kind, raw[i].pos)][std::string((const char*)seq.data() + raw[i].seq_off, (size_t)raw[i].len)]++;
+	c->ind_out.clear(); c->ind_seq_out.clear();
+	for (auto& kv : agg)
+		for (auto& sv : kv.second)
+		{
+			mc_indel_rec r; r.pos = kv.first.second; r.kind = kv.first.first; r.len = (int32_t)sv.first.size(); r.count = (int32_t)(sv.second & 0xFFFF);
+			r.seq_off = (int32_t)c->ind_seq_out.size();
+			c->ind_seq_out.insert(c->ind_seq_out.end(), sv.first.begin(), sv.first.end());
+			c->ind_out.push_back(r);
+		}
+	c->ind_seq_out.push_back(0);
+	*recs = c->ind_out.data(); *n_recs = (int64_t)c->ind_out.size(); *seq_arena = c->ind_seq_out.data();
+	return MC_OK;
+}
+
+int mc_profile_breakpoints(mc_ctx* c, const mc_breakpoint_rec** recs, int64_t* n_recs)
+{
+	if (!c || !recs || !n_recs) { mc_set_error("mc_profile_breakpoints: null argument"); return MC_ERR_ARG; }
+	PersistBumps pb;
+	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
+	std::vector<int64_t> raw((size_t)pb.bp);
+	if (dev_d2h(raw.data(), c->d_bp.p, raw.size() * 8, c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
+	std::map<int64_t, uint32_t> agg;
+	for (size_t i = 0; i < raw.size(); i++) agg[raw[i]]++;
+	c->bp_out.clear();
+	for (auto& kv : agg) c->bp_out.push_back({kv.first, (int64_t)(kv.second & 0xFFFF)});
+	*recs = c->bp_out.data(); *n_recs = (int64_t)c->bp_out.size();
+	return MC_OK;
+}
+
+// Records in the order the reference's thread body pushes them (src/ReadMapping.cpp:493,502,513-519); the
+// caller applies the thread-end std::sort by gPos (:629-630) itself so that ties keep the reference's order.
+int mc_profile_sites(mc_ctx* c, int32_t kind, const mc_site_rec** recs, int64_t* n_recs)
+{
+	if (!c || !recs || !n_recs || kind < 0 || kind > 1) { mc_set_error("mc_profile_sites: bad argument"); return MC_ERR_ARG; }
+	std::vector<mc_site_rec>& v = kind == 0 ? c->inv_sites : c->tnl_sites;
+	*recs = v.data(); *n_recs = (int64_t)v.size();
+	return MC_OK;
+}
+
+int mc_profile_allreduce(mc_ctx*, void*) { mc_set_error("mc_profile_allreduce: built without NCCL"); return MC_ERR_NCCL; }
+
+int mc_bwt_search_batch(mc_ctx*, int64_t, const uint8_t*, const int64_t*, const int32_t*, int32_t*, int32_t*, uint64_t*) { mc_set_error("not implemented yet"); return MC_ERR_ARG; }
+int mc_align_batch(mc_ctx*, int32_t, int64_t, const uint8_t*, const int64_t*, const uint8_t*, const int64_t*, const int64_t*, uint8_t*, uint8_t*, int32_t*) { mc_set_error("not implemented yet"); return MC_ERR_ARG; }
+
+} // extern "C"

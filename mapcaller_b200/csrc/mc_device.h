@@ -1,0 +1,76 @@
+// Device abstraction + shared POD types of the mapping pipeline.
+//
+// The pipeline stages are written as per-work-item bodies (mc_stages.h) that nvcc compiles into
+// sm_100a kernels.  Defining MC_HOSTEMU compiles the same bodies as plain C++ loops: that build
+// (tools/hostemu) is a DEVELOPER HARNESS for debugging stage logic against the reference on a box
+// without a GPU.  It is never linked into libmapcaller_b200.so, never loaded by the package, the
+// tests or bench.py, and is not a fallback.
+#ifndef MC_DEVICE_H
+#define MC_DEVICE_H
+
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/mapcaller_b200.h"
+
+#ifdef MC_HOSTEMU
+#define MC_HD inline
+#define MC_DEV_ONLY 0
+struct mc_u32x4 { uint32_t x, y, z, w; };
+static inline mc_u32x4 mc_ldg128(const void* p) { mc_u32x4 v; memcpy(&v, p, 16); return v; }
+template <class T> static inline T mc_ldg(const T* p) { return *p; }
+template <class T> static inline T mc_atomic_add(T* p, T v) { T o = *p; *p = (T)(o + v); return o; }
+static inline int mc_popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int mc_max3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
+#else
+#include <cuda_runtime.h>
+#define MC_HD __device__ __forceinline__
+#define MC_DEV_ONLY 1
+typedef uint4 mc_u32x4;
+static __device__ __forceinline__ mc_u32x4 mc_ldg128(const void* p) { return __ldg((const uint4*)p); }
+template <class T> static __device__ __forceinline__ T mc_ldg(const T* p) { return __ldg(p); }
+static __device__ __forceinline__ unsigned long long mc_atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+static __device__ __forceinline__ uint32_t mc_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+static __device__ __forceinline__ int mc_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+static __device__ __forceinline__ int mc_popc(uint32_t x) { return __popc(x); }
+static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); } // DPX
+#endif
+
+typedef unsigned long long mc_u64; // atomicAdd-compatible 64-bit counter
+
+// ---- FM-index replica in HBM (layout of the reference's bwt_t, unchanged) ------------------------
+struct DevIndex {
+	const uint32_t* bwt;   // 64-byte blocks: 4 x uint64 occ counts + 8 x uint32 packed symbols
+	const uint64_t* sa;    // every 32nd row
+	const uint8_t* pac;    // forward 2-bit text; revcomp half derived on the fly
+	const int64_t* chrom_end; // sorted keys of PosChrIdMap (reference src/bwt_index.cpp:253-254)
+	const int32_t* chrom_id;  // value of each key
+	int32_t n_end;
+	uint64_t primary, L2[5], seq_len;
+	int64_t G, twoG;
+};
+
+struct Seed { uint64_t x0; int32_t read; int16_t rpos; int16_t len; };   // one recorded BWT_Search hit: SA interval [x0, x0+freq)
+struct SPair { int64_t gpos; int32_t rpos; int32_t len; };               // simple pair (exact-match seed placed on the genome)
+struct Cand { int32_t score; int32_t pbeg; int32_t pend; };              // cluster = slice of the read's sorted simple pairs
+struct DpTask { int32_t frag; int32_t m; int32_t n; int32_t pad; int64_t ws_off; };
+
+struct DevStats {
+	mc_u64 seed_blocks, locate_blocks, sa_reads, dp_cells, dp_tasks, profile_columns;
+	mc_u64 overflow;      // any arena ran out: the batch is re-run with larger arenas
+	mc_u64 odd_merge;     // defensive counter: IdentifyNormalPairs ordering assumption violated
+};
+
+struct DevParams {
+	int32_t paired, alg_ksw2, max_pos_diff, max_clip, max_dup, update_profile;
+	float max_mismatch_rate;
+};
+
+// device-resident pile-up profile (DESIGN.md "data layout")
+struct DevProfile {
+	uint32_t* cnt16;   // [G][4] words = 8 x uint16: A,C | G,T | F1,R2 | F2,R1
+	uint32_t* multi;   // [G] multi_hit (clamped to 4095 when packed)
+	uint8_t* rcount;   // [G] readCount gate (<= iMaxDuplicate)
+};
+
+#endif

@@ -1,0 +1,152 @@
+// Kernel wrappers: every stage body of mc_stages.h becomes one __global__ kernel (one thread per work
+// item, 256-thread blocks) plus a launch_<stage>() function.  Under MC_HOSTEMU (developer harness, see
+// mc_device.h) the launchers are plain loops.
+#ifndef MC_LAUNCH_H
+#define MC_LAUNCH_H
+
+#include "mc_stages.h"
+
+#ifdef MC_HOSTEMU
+#include <algorithm>
+typedef int mc_stream_t;
+#define MC_LAUNCH1(name) \
+	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a); }
+#define MC_LAUNCH2(name) \
+	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
+static void launch_scatter(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) scatter_body(i, 0, 1, a, q); }
+static void launch_profpack(const DevProfile& p, int64_t beg, int64_t n, uint64_t* out, mc_stream_t) { for (int64_t i = 0; i < n; i++) profpack_body(i, p, beg, out); }
+static int64_t g_launches = 0;
+#else
+typedef cudaStream_t mc_stream_t;
+static int64_t g_launches = 0;
+#define MC_BLOCK 256
+#define MC_LAUNCH1(name) \
+	__global__ void __launch_bounds__(MC_BLOCK) mc_##name##_kernel(const PipeArgs a, int64_t n) \
+	{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) name##_body(i, a); } \
+	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t s) \
+	{ if (n > 0) { mc_##name##_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
+#define MC_LAUNCH2(name) \
+	__global__ void __launch_bounds__(MC_BLOCK) mc_##name##_kernel(const PipeArgs a, const ProfArgs q, int64_t n) \
+	{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) name##_body(i, a, q); } \
+	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t s) \
+	{ if (n > 0) { mc_##name##_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n); g_launches++; } }
+// one warp per read: lanes stride over consecutive profile columns
+__global__ void __launch_bounds__(MC_BLOCK) mc_scatter_kernel(const PipeArgs a, const ProfArgs q, int64_t n)
+{
+	int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+	if (w < n) scatter_body(w, threadIdx.x & 31, 32, a, q);
+}
+static void launch_scatter(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_scatter_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_profpack_kernel(const DevProfile p, int64_t beg, int64_t n, uint64_t* out)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) profpack_body(i, p, beg, out); }
+static void launch_profpack(const DevProfile& p, int64_t beg, int64_t n, uint64_t* out, mc_stream_t s)
+{ if (n > 0) { mc_profpack_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(p, beg, n, out); g_launches++; } }
+#endif
+
+MC_LAUNCH1(prep)
+MC_LAUNCH1(seed)
+MC_LAUNCH1(expand)
+MC_LAUNCH1(locate)
+MC_LAUNCH1(cluster)
+MC_LAUNCH1(single)
+MC_LAUNCH1(pair)
+MC_LAUNCH1(rescue)
+MC_LAUNCH1(alnprep)
+MC_LAUNCH1(dp)
+MC_LAUNCH1(alnfin)
+MC_LAUNCH1(pairstat)
+MC_LAUNCH1(chunkstat)
+MC_LAUNCH2(profkey)
+MC_LAUNCH2(gate)
+MC_LAUNCH2(gateupd)
+
+// ---- exclusive scan uint32 -> int64 (out has n + 1 entries) -----------------------------------------
+#ifdef MC_HOSTEMU
+static void device_scan_u32(const uint32_t* in, int64_t* out, int64_t n, int64_t*, mc_stream_t)
+{ int64_t s = 0; for (int64_t i = 0; i < n; i++) { out[i] = s; s += in[i]; } out[n] = s; }
+static size_t device_scan_scratch_bytes(int64_t) { return 8; }
+static void device_sort_u64(uint64_t* keys, uint64_t*, int64_t n, void*, size_t, mc_stream_t) { std::sort(keys, keys + n); }
+static size_t device_sort_scratch_bytes(int64_t) { return 8; }
+#else
+#define MC_SCAN_TILE 2048   // 256 threads x 8 items
+// pass 1: per-tile totals
+__global__ void __launch_bounds__(256) mc_scan_tile_sums(const uint32_t* in, int64_t n, int64_t* tile_sum)
+{
+	__shared__ int64_t sh[8];
+	const int64_t base = (int64_t)blockIdx.x * MC_SCAN_TILE;
+	int64_t s = 0;
+	for (int k = 0; k < 8; k++) { int64_t i = base + k * 256 + threadIdx.x; if (i < n) s += in[i]; }
+	for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) { int64_t t = 0; for (int w = 0; w < 8; w++) t += sh[w]; tile_sum[blockIdx.x] = t; }
+}
+// pass 2: one block scans the tile totals in place (exclusive); also writes the grand total
+__global__ void __launch_bounds__(1024) mc_scan_tiles(int64_t* tile_sum, int64_t nt, int64_t* total)
+{
+	__shared__ int64_t sh[1024];
+	__shared__ int64_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int64_t base = 0; base < nt; base += 1024)
+	{
+		int64_t i = base + threadIdx.x;
+		int64_t v = i < nt ? tile_sum[i] : 0;
+		sh[threadIdx.x] = v;
+		__syncthreads();
+		for (int o = 1; o < 1024; o <<= 1)
+		{
+			int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+			__syncthreads();
+			sh[threadIdx.x] += t;
+			__syncthreads();
+		}
+		if (i < nt) tile_sum[i] = carry + sh[threadIdx.x] - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry += sh[1023];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *total = carry;
+}
+// pass 3: scan inside each tile, offset by the tile prefix
+__global__ void __launch_bounds__(256) mc_scan_finish(const uint32_t* in, int64_t n, const int64_t* tile_pre, int64_t* out)
+{
+	__shared__ int64_t sh[8];
+	const int64_t base = (int64_t)blockIdx.x * MC_SCAN_TILE + (int64_t)threadIdx.x * 8;
+	uint32_t v[8]; int64_t s = 0;
+	for (int k = 0; k < 8; k++) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+	int64_t incl = s;
+	for (int o = 1; o < 32; o <<= 1) { int64_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+	if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	int64_t wpre = 0;
+	for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wpre += sh[w];
+	int64_t run = tile_pre[blockIdx.x] + wpre + incl - s;
+	for (int k = 0; k < 8; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+static size_t device_scan_scratch_bytes(int64_t n) { return (size_t)((n + MC_SCAN_TILE - 1) / MC_SCAN_TILE + 2) * 8; }
+static void device_scan_u32(const uint32_t* in, int64_t* out, int64_t n, int64_t* scratch, mc_stream_t s)
+{
+	const int64_t nt = (n + MC_SCAN_TILE - 1) / MC_SCAN_TILE;
+	if (nt > 0) { mc_scan_tile_sums<<<(unsigned)nt, 256, 0, s>>>(in, n, scratch); g_launches++; }
+	mc_scan_tiles<<<1, 1024, 0, s>>>(scratch, nt, out + n); g_launches++;
+	if (nt > 0) { mc_scan_finish<<<(unsigned)nt, 256, 0, s>>>(in, n, scratch, out); g_launches++; }
+}
+#include <cub/device/device_radix_sort.cuh>
+static size_t device_sort_scratch_bytes(int64_t n)
+{
+	size_t b = 0; cub::DeviceRadixSort::SortKeys(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, n);
+	return b + 256;
+}
+// sorts keys in place (tmp must hold n keys)
+static void device_sort_u64(uint64_t* keys, uint64_t* tmp, int64_t n, void* scratch, size_t scratch_bytes, mc_stream_t s)
+{
+	if (n <= 1) return;
+	cub::DeviceRadixSort::SortKeys(scratch, scratch_bytes, (const uint64_t*)keys, tmp, n, 0, 64, s);
+	cudaMemcpyAsync(keys, tmp, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
+	g_launches += 4;
+}
+#endif
+
+#endif

@@ -1,0 +1,244 @@
+// Per-work-item bodies of the mapping pipeline (one function = one kernel, see mc_launch.h).
+//
+// Stage map (reference function -> body):
+//   prep_body      ReverseOrientation + EnCodeReadSeq           src/tools.cpp:45, src/ReadMapping.cpp:404
+//   seed_body      IdentifySimplePairs + BWT_Search             src/ReadMapping.cpp:125, src/bwt_search.cpp:121
+//   expand_body / locate_body   the bwt_sa loop of BWT_Search   src/bwt_search.cpp:153-161,109-119
+//   cluster_body   sort(CompByPosDiff) + SimplePairClustering   src/ReadMapping.cpp:152,194,160
+//   pair_body      CheckPairedAlignmentDistance, MaskUnPairedAlnCan, RemoveRedundantAlnCan  :244,305,228
+//   rescue_body    AlignmentRescue                              src/AlignmentRescue.cpp:28, src/KmerAnalysis.cpp
+//   alnprep_body   ProduceReadAlignment up to the DP dispatch   src/ReadAlignment.cpp:306-342,38-108,155-191
+//   dp_body        nw_alignment / ksw2_alignment                src/nw_alignment.cpp:18, src/ksw2_alignment.cpp:250
+//   alnfin_body    rest of ProduceReadAlignment                 src/ReadAlignment.cpp:343-411
+//   pairstat_body  GenCoordinatePair + per-chunk sums           src/ReadMapping.cpp:361,479-539
+//   prof_*         UpdateProfile / UpdateMultiHitCount          src/AlignmentProfile.cpp:41,244
+#ifndef MC_STAGES_H
+#define MC_STAGES_H
+
+#include "mc_fmindex.h"
+
+// ------------------------------------------------------------------------------------------------
+// Shared argument block: every stage sees the same set of arenas.
+// ------------------------------------------------------------------------------------------------
+struct ReadSum { int32_t score, sub_score, best_idx, n_live; };
+
+struct PipeArgs {
+	DevIndex ix;
+	DevParams pr;
+	DevStats* st;
+	int64_t n_reads;
+	// reads
+	uint8_t* seq;            // ASCII, mate 2 reverse-complemented in place by prep
+	const int64_t* roff;     // n_reads + 1
+	// seeds: slot s of read r lives in [seed_off[r], seed_off[r+1])
+	const int64_t* seed_off; // n_reads + 1
+	Seed* seeds;
+	uint32_t* slot_freq;     // per slot: number of locations (0 = unused slot)
+	const int64_t* slot_loc; // exclusive scan of slot_freq, n_slots + 1
+	int32_t* loc_slot;       // per location: its slot
+	int64_t n_slots, n_locs;
+	// simple pairs: [pair_off(r), ...) with pair_off(r) = slot_loc[seed_off[r]]; rescue seeds appended after n_locs
+	SPair* pairs;
+	int32_t* npair;          // per read: valid simple pairs after filtering/sorting
+	int64_t pair_cap;        // arena capacity (n_locs + rescue region)
+	mc_u64* pair_bump;       // next free rescue pair
+	// candidates: read r owns [cand_off(r), cand_off(r) + cand_cap(r))
+	Cand* cands;
+	int32_t* ncand0;         // per read: clusters found (immutable after cluster stage)
+	int32_t* ncand;          // per read: clusters + rescued candidates of the current attempt
+	int32_t* cscore;         // per cand: live score of the current attempt
+	int32_t* cpaired;        // per cand: PairedAlnCanIdx
+	int32_t* corient;        // per cand: orientation (1 fwd, 0 rev, -1 dead)
+	int32_t* cfrag;          // per cand: first fragment in the frag arena
+	int32_t* cnfrag;         // per cand: number of fragments
+	int32_t* ctmp;           // per cand: scratch (pairing)
+	// per pair / per chunk
+	const int32_t* est;      // per chunk: EstiDistance = (int)(avgDist*1.5)
+	const uint8_t* active;   // per chunk: 1 = (re)compute in this attempt
+	int32_t* pair_flag;      // per pair: 1 = needs rescue
+	int32_t* est_lo;         // per pair: smallest / largest EstiDistance giving the same outcome
+	int32_t* est_hi;
+	mc_pair_out* pair_out;   // per pair
+	mc_chunk_out* chunk_out; // per chunk
+	int32_t* chunk_lo; int32_t* chunk_hi;
+	// alignment
+	ReadSum* rsum;           // per read
+	mc_frag_out* frags; int64_t frag_cap; mc_u64* frag_bump;
+	uint8_t* aln; int64_t aln_cap; mc_u64* aln_bump;
+	DpTask* tasks; int64_t task_cap; mc_u64* task_bump;
+	uint8_t* dpws; int64_t dpws_cap; mc_u64* dpws_bump;
+	int32_t* rtask;          // rescue task list (pair ids)
+	mc_u64* rtask_bump;
+	// profile
+	DevProfile prof;
+	int64_t first_read;      // global index of read 0 of this batch (parity of mate, dedup order)
+};
+
+MC_HD int64_t pa_pair_off(const PipeArgs& a, int64_t r) { return a.slot_loc[a.seed_off[r]]; }
+MC_HD int64_t pa_cand_off(const PipeArgs& a, int64_t r)
+{
+	if (!a.pr.paired) return pa_pair_off(a, r);
+	int64_t r0 = r & ~1ll;
+	int64_t base = 2 * pa_pair_off(a, r0);
+	return (r & 1) ? base + (pa_pair_off(a, r0 + 2 <= a.n_reads ? r0 + 2 : a.n_reads) - pa_pair_off(a, r0)) : base;
+}
+MC_HD int pa_cand_cap(const PipeArgs& a, int64_t r)
+{
+	if (!a.pr.paired) return (int)(pa_pair_off(a, r + 1) - pa_pair_off(a, r));
+	int64_t r0 = r & ~1ll;
+	return (int)(pa_pair_off(a, r0 + 2 <= a.n_reads ? r0 + 2 : a.n_reads) - pa_pair_off(a, r0));
+}
+MC_HD int pa_chunk_of_read(int64_t r) { return (int)(r / MC_CHUNK_READS); }
+
+// ------------------------------------------------------------------------------------------------
+// prep: mate 2 is reverse-complemented in place before seeding (reference src/ReadMapping.cpp:451)
+// ------------------------------------------------------------------------------------------------
+MC_HD void prep_body(int64_t r, const PipeArgs& a)
+{
+	if (!a.pr.paired || !(r & 1)) return;
+	uint8_t* s = a.seq + a.roff[r];
+	int n = (int)(a.roff[r + 1] - a.roff[r]);
+	int i = 0, j = n - 1;
+	for (; i < j; i++, j--) { uint8_t x = mc_complement(s[j]), y = mc_complement(s[i]); s[i] = x; s[j] = y; }
+	if (i == j) s[i] = mc_complement(s[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// seeding: one thread walks one read left to right
+// ------------------------------------------------------------------------------------------------
+MC_HD void seed_body(int64_t r, const PipeArgs& a)
+{
+	const uint8_t* s = a.seq + a.roff[r];
+	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
+	const int64_t so = a.seed_off[r];
+	const int cap = (int)(a.seed_off[r + 1] - so);
+	int ns = 0, pos = 0;
+	const int stop = rlen - MC_MIN_SEED;
+	uint32_t nblk = 0;
+	while (pos < stop)
+	{
+		int c = mc_nt4(s[pos]);
+		if (c > 3) { pos++; continue; }
+		BiInterval v = mc_interval_init(a.ix, c);
+		int p = pos + 1;
+		for (; p < rlen; p++)
+		{
+			int cc = mc_nt4(s[p]);
+			if (cc > 3) break;
+			if (!mc_interval_extend(a.ix, v, cc, &nblk)) break;
+		}
+		const int len = p - pos;
+		if (len >= MC_MIN_SEED && v.x2 <= MC_MAX_OCC && ns < cap)
+		{
+			Seed sd; sd.x0 = v.x0; sd.read = (int32_t)r; sd.rpos = (int16_t)pos; sd.len = (int16_t)len;
+			a.seeds[so + ns] = sd; a.slot_freq[so + ns] = (uint32_t)v.x2; ns++;
+		}
+		pos = p + 1;
+	}
+	if (nblk) mc_atomic_add(&a.st->seed_blocks, (mc_u64)nblk);
+}
+
+// one thread per slot writes its slot id over its locations
+MC_HD void expand_body(int64_t s, const PipeArgs& a)
+{
+	uint32_t f = a.slot_freq[s];
+	int64_t o = a.slot_loc[s];
+	for (uint32_t i = 0; i < f; i++) a.loc_slot[o + i] = (int32_t)s;
+}
+
+// one thread per location: LF walk to a sampled SA row
+MC_HD void locate_body(int64_t t, const PipeArgs& a)
+{
+	const int32_t s = a.loc_slot[t];
+	const Seed sd = a.seeds[s];
+	uint32_t nblk = 0;
+	const uint64_t g = mc_locate(a.ix, sd.x0 + (uint64_t)(t - a.slot_loc[s]), &nblk);
+	SPair p; p.gpos = (int64_t)g; p.rpos = sd.rpos;
+	p.len = ((int64_t)g - (int64_t)sd.rpos > 0) ? sd.len : 0;   // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
+	a.pairs[t] = p;
+	mc_atomic_add(&a.st->locate_blocks, (mc_u64)nblk);
+	mc_atomic_add(&a.st->sa_reads, (mc_u64)1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// clustering: sort the read's simple pairs by (PosDiff, rPos), cut into clusters, apply the
+// ratcheting score threshold, resolve tandem repeats
+// ------------------------------------------------------------------------------------------------
+MC_HD bool sp_less_posdiff(const SPair& x, const SPair& y)
+{
+	int64_t dx = x.gpos - x.rpos, dy = y.gpos - y.rpos;
+	return dx == dy ? x.rpos < y.rpos : dx < dy;
+}
+
+MC_HD void cluster_body(int64_t r, const PipeArgs& a)
+{
+	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
+	const int64_t po = pa_pair_off(a, r);
+	const int raw = (int)(pa_pair_off(a, r + 1) - po);
+	SPair* v = a.pairs + po;
+	int m = 0;
+	for (int i = 0; i < raw; i++) if (v[i].len > 0) { if (m != i) v[m] = v[i]; m++; }
+	for (int i = 1; i < m; i++) // insertion sort; m is 1-3 for almost every read
+	{
+		SPair x = v[i]; int j = i - 1;
+		while (j >= 0 && sp_less_posdiff(x, v[j])) { v[j + 1] = v[j]; j--; }
+		v[j + 1] = x;
+	}
+	a.npair[r] = m;
+	const int64_t co = pa_cand_off(a, r);
+	int nc = 0;
+	if (m > 0)
+	{
+		int head = 0, score = v[0].len, thr = rlen >> 2;
+		int64_t gend = a.ix.chrom_end[mc_chrom_lower_bound(a.ix, v[0].gpos)];
+		for (int i = 0, j = 1; j <= m; i++, j++)
+		{
+			bool cut;
+			if (j == m) cut = true; // the terminal pair sits at 2G, beyond every chromosome end
+			else
+			{
+				int64_t d = (v[j].gpos - v[j].rpos) - (v[i].gpos - v[i].rpos);
+				if (d < 0) d = -d;
+				cut = v[j].gpos > gend || d > a.pr.max_pos_diff;
+			}
+			if (cut)
+			{
+				if (score > thr)
+				{
+					if (thr < (score >> 1)) thr = score >> 1;
+					Cand c; c.score = score; c.pbeg = (int32_t)(po + head); c.pend = (int32_t)(po + j);
+					if (score >= rlen)
+					{
+						// tandem repeat: keep only the best run of equal PosDiff, first maximum wins
+						int bi = head, bj = head, bs = 0, ri = head, s = v[head].len;
+						for (int k = head + 1; k < j; k++)
+						{
+							if ((v[k].gpos - v[k].rpos) != (v[ri].gpos - v[ri].rpos))
+							{
+								if (s > bs) { bs = s; bi = ri; bj = k; }
+								ri = k; s = v[k].len;
+							}
+							else s += v[k].len;
+						}
+						if (s > bs) { bs = s; bi = ri; bj = j; }
+						c.score = bs; c.pbeg = (int32_t)(po + bi); c.pend = (int32_t)(po + bj);
+					}
+					a.cands[co + nc] = c; nc++;
+				}
+				if (j < m)
+				{
+					head = j; score = v[j].len;
+					gend = a.ix.chrom_end[mc_chrom_lower_bound(a.ix, v[j].gpos)];
+				}
+			}
+			else score += v[j].len;
+		}
+	}
+	a.ncand0[r] = nc;
+}
+
+#include "mc_stages_pair.h"
+#include "mc_stages_align.h"
+#include "mc_stages_profile.h"
+
+#endif

@@ -1,0 +1,127 @@
+"""Shared helpers of the parity tests: seeded cases, the CUDA path through the C ABI, the checkers."""
+from __future__ import annotations
+
+import os
+import pickle
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from mapcaller_b200 import simulate as sim  # noqa: E402
+
+
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libmcref.so"))
+
+
+def make_case(kind: str = "small", seed: int = 1, n_pairs: int = 3000, read_len: int = 100, genome_len: int = 60000,
+              contigs: int = 1, sub_rate: float = 0.005, indel_rate: float = 0.0, n_rate: float = 0.0, sv: float = 1.0,
+              n_dup: int = 6, tandem: int = 3, frag_mean: float = 400, frag_sd: float = 40, **params):
+    """A genome (possibly several contigs), a mutated copy the reads come from, and the reads."""
+    parts, names = [], []
+    for c in range(contigs):
+        parts.append(sim.genome(genome_len // contigs, seed * 100 + c, n_dup=n_dup, dup_len=(300, 900), tandem=tandem))
+        names.append("ctg%d" % (c + 1))
+    ref = np.concatenate(parts)
+    mut_parts = [sim.mutate(p, seed * 1000 + i, snp_per_mb=3000, small_indel_per_mb=400, large_indel_per_mb=150, sv_per_mb=sv * 30, sv_len=(400, 900))[0]
+                 for i, p in enumerate(parts)]
+    mut = np.concatenate(mut_parts)
+    r1, r2 = sim.simulate_pairs(mut, n_pairs, read_len, seed=seed + 7, frag_mean=frag_mean, frag_sd=frag_sd, sub_rate=sub_rate, indel_rate=indel_rate, n_rate=n_rate)
+    p = dict(paired=1, alg_ksw2=0, max_pos_diff=30, max_clip=5, max_dup=5, max_mismatch_rate=0.05)
+    p.update(params)
+    if p["paired"]:
+        seq, off = sim.interleave(r1, r2)
+    else:
+        seq, off = r1.reshape(-1).copy(), np.arange(len(r1) + 1, dtype=np.int64) * r1.shape[1]
+    return dict(contigs=list(zip(names, parts)), ref=ref, seq=seq, off=off, params=p, r1=r1, r2=r2)
+
+
+def build_index(case, threads: int = 0):
+    from mapcaller_b200 import api
+    codes = sim.encode(case["ref"])
+    assert codes.max() <= 3
+    return api.Index.build(codes, [len(s) for _, s in case["contigs"]], [n for n, _ in case["contigs"]], threads)
+
+
+def ref_results(case, index, want_reads: bool = True):
+    """Runs the case through oracle/_ref in a subprocess."""
+    with tempfile.TemporaryDirectory() as td:
+        prefix = os.path.join(td, "idx")
+        index.save(prefix)
+        job = os.path.join(td, "job.npz")
+        np.savez(job, prefix=prefix, seq=case["seq"], off=case["off"], params=np.array(case["params"], dtype=object), want_reads=want_reads)
+        outp = os.path.join(td, "out.pkl")
+        subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), job, outp], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        with open(outp, "rb") as fh:
+            return pickle.load(fh)
+
+
+def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool = True, device: int = 0):
+    from mapcaller_b200 import api
+    seq, off = case["seq"], case["off"]
+    n = len(off) - 1
+    batch_reads = batch_reads or n
+    out = dict(reads=[], est=[], replays=0)
+    with api.Context(index, want_alignments=int(want_reads), update_profile=1, device=device, **case["params"]) as ctx:
+        for b in range(0, n, batch_reads):
+            e = min(n, b + batch_reads)
+            res = ctx.map_batch(seq[off[b]:off[e]], off[b:e + 1] - off[b])
+            if want_reads:
+                out["reads"] += api.unpack_reads(res)
+            out["est"] += [int(x) for x in res["chunks"]["est_distance"]] if case["params"]["paired"] else []
+            out["replays"] += res["replays"]
+        t = ctx.totals()
+        out["counters"] = dict(reads=t["total_reads"], mapped=t["total_mapped"], paired=t["total_paired"], dist_sum=t["total_distance"],
+                               len_sum=t["read_length_sum"], avgDist=t["avg_dist"])
+        out["profile"] = ctx.profile_columns()
+        out["ins"], out["dele"] = ctx.indels()
+        out["bp"] = ctx.breakpoints()
+        out["inv"] = sorted(ctx.sites(0), key=lambda x: x[0])
+        out["tnl"] = sorted(ctx.sites(1), key=lambda x: x[0])
+        out["stats"] = ctx.stats()
+    return out
+
+
+def first_read_diff(mine, ref):
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        if a != b:
+            return i, a, b
+    return None
+
+
+def assert_same(mine, ref, want_reads: bool = True, sites_sorted: bool = True) -> None:
+    """Bit-exact comparison of everything the hot path leaves behind."""
+    if want_reads and "reads" in ref:
+        assert len(mine["reads"]) == len(ref["reads"])
+        d = first_read_diff(mine["reads"], ref["reads"])
+        assert d is None, "read %d differs:\n mine %r\n ref  %r" % d
+    if ref.get("est"):
+        assert mine["est"] == ref["est"], "EstiDistance trajectory differs"
+    for k in ("reads", "mapped", "paired", "dist_sum", "len_sum", "avgDist"):
+        assert mine["counters"][k] == ref["counters"][k], "counter %s: %r != %r" % (k, mine["counters"][k], ref["counters"][k])
+    bad = np.nonzero((mine["profile"] != ref["profile"]).any(axis=1))[0]
+    assert len(bad) == 0, "profile differs at %d columns, first %d: %r vs %r" % (len(bad), bad[0], mine["profile"][bad[0]], ref["profile"][bad[0]])
+    assert mine["ins"] == ref["ins"], "InsertSeqMap differs"
+    assert mine["dele"] == ref["dele"], "DeleteSeqMap differs"
+    assert mine["bp"] == ref["bp"], "BreakPointMap differs"
+    assert sorted(mine["inv"]) == sorted(ref["inv"]), "InversionSiteVec differs"
+    assert sorted(mine["tnl"]) == sorted(ref["tnl"]), "TranslocationSiteVec differs"
+
+
+def smoke_case() -> None:
+    """One small invocation of the hot path on cuda:0, checked against the oracle."""
+    case = make_case(seed=3, n_pairs=600, genome_len=40000)
+    ix = build_index(case)
+    mine = cuda_results(case, ix)
+    if have_ref():
+        assert_same(mine, ref_results(case, ix))
+    else:
+        import golden_util
+        golden_util.check_against_golden("smoke", mine)
+    assert mine["stats"]["kernel_launches"] > 0
