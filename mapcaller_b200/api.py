@@ -101,6 +101,8 @@ def lib():
         L.mc_profile_breakpoints.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_sites.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
+        L.mc_align_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 8
+        L.mc_bwt_search_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         _lib = L
     return _lib
 
@@ -221,6 +223,20 @@ class Context:
         out = BatchOut()
         _check(lib().mc_map_staged(self._h, slot, C.byref(out)), "mc_map_staged")
         return self._wrap(out, copy)
+
+    def align_batch(self, pairs, ksw2: bool = False):
+        """pairs: list of (read piece bytes, genome piece bytes) -> list of (aln1, aln2) through the DP kernel."""
+        n = len(pairs)
+        s1 = np.frombuffer(b"".join(p[0] for p in pairs), dtype=np.uint8)
+        s2 = np.frombuffer(b"".join(p[1] for p in pairs), dtype=np.uint8)
+        o1 = np.zeros(n + 1, dtype=np.int64); o1[1:] = np.cumsum([len(p[0]) for p in pairs])
+        o2 = np.zeros(n + 1, dtype=np.int64); o2[1:] = np.cumsum([len(p[1]) for p in pairs])
+        oo = o1 + o2
+        out1 = np.zeros(int(oo[-1]) + 1, dtype=np.uint8); out2 = np.zeros(int(oo[-1]) + 1, dtype=np.uint8)
+        ln = np.zeros(n, dtype=np.int32)
+        _check(lib().mc_align_batch(self._h, int(ksw2), n, s1.ctypes.data, o1.ctypes.data, s2.ctypes.data, o2.ctypes.data, oo.ctypes.data,
+                                    out1.ctypes.data, out2.ctypes.data, ln.ctypes.data), "mc_align_batch")
+        return [(out1[oo[i]:oo[i] + ln[i]].tobytes(), out2[oo[i]:oo[i] + ln[i]].tobytes()) for i in range(n)]
 
     def totals(self) -> dict:
         t = Totals()

@@ -123,7 +123,7 @@ struct mc_ctx {
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
 	DBuf d_keys, d_keys_tmp, d_accept, d_sort;
-	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0; int64_t rescue_cap = 1 << 20;
+	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
 	HBuf h_in_seq, h_in_off, h_seed_off, h_small, h_chunk, h_chunk_lo, h_chunk_hi, h_pairs, h_reads, h_cands, h_frags, h_aln, h_misc;
 	std::vector<mc_read_out> reads_out; std::vector<mc_cand_out> cands_out;
@@ -317,6 +317,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	if (bad) return MC_ERR_CUDA;
 	const int64_t n_locs = h_small[0];
 	a.n_locs = n_locs;
+	if (getenv("MC_DEBUG")) fprintf(stderr, "[mc] batch: %lld reads, %lld bytes, %lld seed slots, %lld seed locations\n", (long long)n, (long long)st.n_bytes, (long long)st.n_slots, (long long)n_locs);
 
 	// ---- locate + cluster ----
 	const int64_t cand_total = (paired ? 2 : 1) * n_locs + 1;
@@ -326,7 +327,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		const int64_t frag_cap = (int64_t)(c->frag_factor * (double)(n_locs + 1024)) + n;
 		const int64_t aln_cap = (int64_t)(c->aln_factor * (double)st.n_bytes) + (1 << 20);
 		const int64_t dpws_cap = (int64_t)(c->dpws_factor * (double)st.n_bytes) + (8 << 20);
-		const int64_t task_cap = n + 1024;
+		const int64_t task_cap = (int64_t)(c->task_factor * (double)n) + 1024;
 		if (frag_cap >= 0x7fffffffll || aln_cap >= 0x7fffffffll) { mc_set_error("mc_map_batch: batch too large for 32-bit arena offsets; split it"); return MC_ERR_ARG; }
 		bad |= c->d_loc_slot.reserve((n_locs + 1) * 4) || c->d_pairs.reserve(pair_cap * sizeof(SPair));
 		bad |= c->d_cands.reserve(cand_total * sizeof(Cand)) || c->d_cscore.reserve(cand_total * 4) || c->d_cpaired.reserve(cand_total * 4);
@@ -413,9 +414,15 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		}
 		if (overflow)
 		{
-			c->frag_factor *= 2; c->aln_factor *= 2; c->dpws_factor *= 4; c->rescue_cap *= 4;
-			if (c->frag_factor > 4096) { mc_set_error("mc_map_batch: arena overflow persists"); return MC_ERR_OVERFLOW; }
-			if (getenv("MC_DEBUG")) fprintf(stderr, "[mc] arena overflow: growing (frag x%.0f aln x%.0f dpws x%.0f rescue %lld)\n", c->frag_factor, c->aln_factor, c->dpws_factor, (long long)c->rescue_cap);
+			const mc_u64 ovf = ((DevStats*)(h_small + 8))->overflow;
+			if ((ovf >> 0) & 0xFF) c->rescue_cap *= 4;
+			if ((ovf >> 8) & 0xFF) c->frag_factor *= 2;
+			if ((ovf >> 16) & 0xFF) c->aln_factor *= 2;
+			if ((ovf >> 24) & 0xFF) c->task_factor *= 2;
+			if ((ovf >> 32) & 0xFF) c->dpws_factor *= 4;
+			if ((ovf >> 40) & 0xFF) { mc_set_error("mc_map_batch: internal error: candidate table overflow"); return MC_ERR_OVERFLOW; }
+			if (c->frag_factor > 4096 || c->aln_factor > 4096 || c->task_factor > 4096 || c->dpws_factor > 65536) { mc_set_error("mc_map_batch: arena overflow persists"); return MC_ERR_OVERFLOW; }
+			if (getenv("MC_DEBUG")) fprintf(stderr, "[mc] arena overflow %llx: now frag x%.0f aln x%.0f task x%.0f dpws x%.0f rescue %lld\n", (unsigned long long)ovf, c->frag_factor, c->aln_factor, c->task_factor, c->dpws_factor, (long long)c->rescue_cap);
 			bad |= dev_zero(&c->d_stats.as<DevStats>()->locate_blocks, sizeof(DevStats) - sizeof(mc_u64), s); // keep only the seeding counter
 			continue;
 		}
@@ -684,6 +691,49 @@ int mc_profile_sites(mc_ctx* c, int32_t kind, const mc_site_rec** recs, int64_t*
 int mc_profile_allreduce(mc_ctx*, void*) { mc_set_error("mc_profile_allreduce: built without NCCL"); return MC_ERR_NCCL; }
 
 int mc_bwt_search_batch(mc_ctx*, int64_t, const uint8_t*, const int64_t*, const int32_t*, int32_t*, int32_t*, uint64_t*) { mc_set_error("not implemented yet"); return MC_ERR_ARG; }
-int mc_align_batch(mc_ctx*, int32_t, int64_t, const uint8_t*, const int64_t*, const uint8_t*, const int64_t*, const int64_t*, uint8_t*, uint8_t*, int32_t*) { mc_set_error("not implemented yet"); return MC_ERR_ARG; }
+// Operator-level entry: n independent gapped fills through dp_body (the kernel the pipeline uses).
+int mc_align_batch(mc_ctx* c, int32_t use_ksw2, int64_t n, const uint8_t* s1, const int64_t* off1, const uint8_t* s2, const int64_t* off2,
+                   const int64_t* out_off, uint8_t* out1, uint8_t* out2, int32_t* out_len)
+{
+	if (!c || n < 0 || (n > 0 && (!s1 || !off1 || !s2 || !off2 || !out_off || !out1 || !out2 || !out_len))) { mc_set_error("mc_align_batch: bad argument"); return MC_ERR_ARG; }
+	if (n == 0) return MC_OK;
+	const mc_stream_t s = c->stream;
+	std::vector<mc_frag_out> fr((size_t)n); std::vector<DpTask> tk((size_t)n);
+	int64_t aln_bytes = 0, ws_bytes = 0;
+	for (int64_t i = 0; i < n; i++)
+	{
+		const int64_t m = off1[i + 1] - off1[i], g = off2[i + 1] - off2[i];
+		if (m <= 0 || g <= 0 || m > MC_MAX_RLEN || g > 2 * MC_MAX_RLEN || out_off[i + 1] - out_off[i] < m + g) { mc_set_error("mc_align_batch: problem %lld has bad sizes", (long long)i); return MC_ERR_ARG; }
+		mc_frag_out& f = fr[i]; memset(&f, 0, sizeof(f));
+		f.rLen = (int32_t)m; f.gLen = (int32_t)g; f.aln_cap = (int32_t)(m + g); f.aln_off = (int32_t)aln_bytes; aln_bytes += 2 * (m + g);
+		DpTask& t = tk[i]; t.frag = (int32_t)i; t.m = (int32_t)m; t.n = (int32_t)g; t.pad = 0; t.ws_off = ws_bytes; ws_bytes += dp_ws_bytes((int)m, (int)g);
+		if (aln_bytes >= 0x7fffffffll) { mc_set_error("mc_align_batch: too many bases in one call"); return MC_ERR_ARG; }
+	}
+	std::vector<uint8_t> h_aln((size_t)aln_bytes);
+	for (int64_t i = 0; i < n; i++)
+	{
+		memcpy(h_aln.data() + fr[i].aln_off, s1 + off1[i], (size_t)fr[i].rLen);
+		memcpy(h_aln.data() + fr[i].aln_off + fr[i].aln_cap, s2 + off2[i], (size_t)fr[i].gLen);
+	}
+	DBuf d_fr, d_tk, d_aln, d_ws;
+	int bad = d_fr.reserve(n * sizeof(mc_frag_out)) || d_tk.reserve(n * sizeof(DpTask)) || d_aln.reserve(aln_bytes) || d_ws.reserve(ws_bytes);
+	bad = bad || dev_h2d(d_fr.p, fr.data(), n * sizeof(mc_frag_out), s) || dev_h2d(d_tk.p, tk.data(), n * sizeof(DpTask), s) || dev_h2d(d_aln.p, h_aln.data(), aln_bytes, s);
+	if (!bad)
+	{
+		PipeArgs a; memset(&a, 0, sizeof(a));
+		a.pr.alg_ksw2 = use_ksw2; a.st = c->d_stats.as<DevStats>(); a.frags = d_fr.as<mc_frag_out>(); a.tasks = d_tk.as<DpTask>(); a.aln = d_aln.as<uint8_t>(); a.dpws = d_ws.as<uint8_t>();
+		launch_dp(a, n, s);
+		bad = dev_d2h(fr.data(), d_fr.p, n * sizeof(mc_frag_out), s) || dev_d2h(h_aln.data(), d_aln.p, aln_bytes, s) || dev_sync(s);
+	}
+	d_fr.release(); d_tk.release(); d_aln.release(); d_ws.release();
+	if (bad) return MC_ERR_CUDA;
+	for (int64_t i = 0; i < n; i++)
+	{
+		out_len[i] = fr[i].aln_len;
+		memcpy(out1 + out_off[i], h_aln.data() + fr[i].aln_off, (size_t)fr[i].aln_len);
+		memcpy(out2 + out_off[i], h_aln.data() + fr[i].aln_off + fr[i].aln_cap, (size_t)fr[i].aln_len);
+	}
+	return MC_OK;
+}
 
 } // extern "C"

@@ -14,17 +14,22 @@
 #include "../../include/mapcaller_b200.h"
 
 #ifdef MC_HOSTEMU
+#include <stdio.h>
+#include <stdlib.h>
 #define MC_HD inline
+#define MC_HOST_HD inline
 #define MC_DEV_ONLY 0
 struct mc_u32x4 { uint32_t x, y, z, w; };
 static inline mc_u32x4 mc_ldg128(const void* p) { mc_u32x4 v; memcpy(&v, p, 16); return v; }
 template <class T> static inline T mc_ldg(const T* p) { return *p; }
 template <class T> static inline T mc_atomic_add(T* p, T v) { T o = *p; *p = (T)(o + v); return o; }
+template <class T> static inline void mc_atomic_or(T* p, T v) { *p = (T)(*p | v); }
 static inline int mc_popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int mc_max3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
 #else
 #include <cuda_runtime.h>
 #define MC_HD __device__ __forceinline__
+#define MC_HOST_HD __host__ __device__ __forceinline__
 #define MC_DEV_ONLY 1
 typedef uint4 mc_u32x4;
 static __device__ __forceinline__ mc_u32x4 mc_ldg128(const void* p) { return __ldg((const uint4*)p); }
@@ -32,6 +37,7 @@ template <class T> static __device__ __forceinline__ T mc_ldg(const T* p) { retu
 static __device__ __forceinline__ unsigned long long mc_atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 static __device__ __forceinline__ uint32_t mc_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 static __device__ __forceinline__ int mc_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+static __device__ __forceinline__ void mc_atomic_or(unsigned long long* p, unsigned long long v) { atomicOr(p, v); }
 static __device__ __forceinline__ int mc_popc(uint32_t x) { return __popc(x); }
 static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); } // DPX
 #endif

@@ -8,7 +8,7 @@ MC_HD bool frag_less_readpos(const mc_frag_out& x, const mc_frag_out& y)
 }
 
 // workspace bytes of one fill: traceback matrix + two int rows
-MC_HD int64_t dp_ws_bytes(int m, int n)
+MC_HOST_HD int64_t dp_ws_bytes(int m, int n)
 {
 	const int64_t tb = (((int64_t)(m + 1) * (n + 1)) + 7) & ~7ll;
 	return tb + 8 * (int64_t)((m > n ? m : n) + 2);
@@ -36,7 +36,7 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 		const int ns = c.pend - c.pbeg;
 		const int cap = 2 * ns + 1;
 		const int64_t fb = (int64_t)mc_atomic_add(a.frag_bump, (mc_u64)cap);
-		if (fb + cap > a.frag_cap) { mc_atomic_add(&a.st->overflow, (mc_u64)1); a.cscore[co + ci] = 0; continue; }
+		if (fb + cap > a.frag_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 8); a.cscore[co + ci] = 0; continue; }
 		mc_frag_out* f = a.frags + fb;
 		// seeds sorted by (rPos, gPos), written into the upper half so the final list can be built in place below
 		mc_frag_out* s = f + (cap - ns);
@@ -114,7 +114,7 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 		if (need)
 		{
 			ab = (int64_t)mc_atomic_add(a.aln_bump, (mc_u64)need);
-			if (ab + need > a.aln_cap) { mc_atomic_add(&a.st->overflow, (mc_u64)1); a.cscore[co + ci] = 0; continue; }
+			if (ab + need > a.aln_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 16); a.cscore[co + ci] = 0; continue; }
 		}
 		for (int i = 0; i < nf; i++)
 		{
@@ -151,7 +151,8 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 					const int64_t t = (int64_t)mc_atomic_add(a.task_bump, (mc_u64)1);
 					const int64_t wsn = dp_ws_bytes(x.rLen, x.gLen);
 					const int64_t ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
-					if (t >= a.task_cap || ws + wsn > a.dpws_cap) { mc_atomic_add(&a.st->overflow, (mc_u64)1); continue; }
+					if (t >= a.task_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 24); continue; }
+					if (ws + wsn > a.dpws_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); continue; }
 					DpTask tk; tk.frag = (int32_t)(fb + i); tk.m = x.rLen; tk.n = x.gLen; tk.pad = 0; tk.ws_off = ws;
 					a.tasks[t] = tk;
 				}
@@ -369,6 +370,13 @@ MC_HD void alnfin_body(int64_t r, const PipeArgs& a)
 			}
 			if (score != 0 && score < min_score && mism > max_mm) score = 0;
 		}
+#ifdef MC_HOSTEMU
+		if (getenv("MC_TRACE"))
+		{
+			fprintf(stderr, "[trace] read %lld cand %d: dead=%d head_ok=%d tail_ok=%d score=%d min=%d maxmm=%d\n", (long long)r, ci, dead, head_ok, tail_ok, score, min_score, max_mm);
+			for (int i = 0; i < nf; i++) { const mc_frag_out& x = f[i]; fprintf(stderr, "    frag %d simple=%d r=%d g=%lld rl=%d gl=%d aln=%.*s | %.*s\n", i, x.bSimple, x.rPos, (long long)x.gPos, x.rLen, x.gLen, x.bSimple ? 0 : x.aln_len, a.aln + x.aln_off, x.bSimple ? 0 : x.aln_len, a.aln + x.aln_off + x.aln_cap); }
+		}
+#endif
 		a.cscore[co + ci] = score;
 		if (score == 0) continue;
 		const bool fwd = f[0].gPos < a.ix.G;

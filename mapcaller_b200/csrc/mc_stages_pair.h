@@ -98,49 +98,98 @@ MC_HD void pair_body(int64_t p, const PipeArgs& a)
 }
 
 // ---- rescue ---------------------------------------------------------------------------------------
-// AlignmentRescue (reference src/AlignmentRescue.cpp:28-111) matches every 8-mer of the unplaced mate
-// against every 8-mer of a reference window, sorts the hits by diagonal and merges runs of consecutive
-// hits into seeds of >= 10 bases (src/KmerAnalysis.cpp:57-163).  A run of k consecutive 8-mer hits on
-// one diagonal is exactly a maximal stretch of k+7 matching bases inside the window, so the same seeds
-// come out of a direct scan of each diagonal; the best diagonal is the one with the largest total seed
-// length, smallest PosDiff first on ties (IdentifyBestAlnCan, src/AlignmentRescue.cpp:3-26).
-// Read bases that are not ACGT/acgt never match (the reference skips windows with 'N').
-struct RescueHit { int score; int64_t diag; };
+// AlignmentRescue (reference src/AlignmentRescue.cpp:28-111) joins the 8-mers of the unplaced mate with the
+// 8-mers of a reference window on their 16-bit word id, sorts the hits by (diagonal, read offset) and merges
+// runs of hits with consecutive read offsets into seeds of >= 10 bases (src/KmerAnalysis.cpp:57-163); the
+// best diagonal is the one with the largest total seed length, smallest diagonal first on ties
+// (IdentifyBestAlnCan, src/AlignmentRescue.cpp:3-26).  The sort + join is equivalent to walking each
+// diagonal with the read's word list, which is what rescue_scan_diag does.
+//
+// The read's word list has to be produced exactly as CreateKmerVecFromReadSeq does (src/KmerAnalysis.cpp:57-103),
+// including what happens after an 'N': the scan restarts with a fresh word at [t-8, t), but the loop
+// increment then steps over base t, so every later word of the read is labelled one position early and the
+// first seven of them straddle the skipped base.  Rescued seeds inherit those labels.
+struct KmerEnt { int32_t label; uint32_t wid; };
 
-// scans diagonal d (window offset minus read offset) and returns the sum of seed lengths; when out != 0
-// also writes the seeds
-MC_HD int rescue_scan_diag(const PipeArgs& a, const uint8_t* rs, int rlen, int64_t left, int slen, int d, SPair* out, int* nout)
+MC_HD uint32_t kmer_fresh_id(const uint8_t* s, int pos)
 {
-	int lo = d < 0 ? -d : 0;                 // first read offset whose window base exists
-	int hi = rlen; if (hi > slen - d) hi = slen - d;
-	int total = 0, run = 0, n = 0;
-	for (int q = lo; q <= hi; q++)
+	uint32_t id = 0;
+	for (int i = 0; i < 8; i++) id = (id << 2) + (uint32_t)mc_nt4(s[pos + i]);
+	return id;
+}
+
+// returns the number of words written to `out` (at most len)
+MC_HD int kmer_list_of_read(const uint8_t* s, int len, KmerEnt* out)
+{
+	int n = 0, tail = 0, cnt = 0;
+	while (cnt < 8 && tail < len) { if (s[tail++] != 'N') cnt++; else cnt = 0; }
+	if (cnt != 8) return 0;
+	int head = tail - 8;
+	uint32_t wid = kmer_fresh_id(s, head);
+	out[n].label = head; out[n].wid = wid; n++;
+	for (head += 1; tail < len; head++, tail++)
 	{
-		bool match = false;
-		if (q < hi)
+		if (s[tail] != 'N')
 		{
-			int c = mc_nt4(rs[q]);
-			int64_t g = left + d + q;
-			match = c <= 3 && g >= 0 && c == mc_ref_code(a.ix, g);
+			wid = ((wid & 0x3FFFu) << 2) + (uint32_t)mc_nt4(s[tail]);
+			out[n].label = head; out[n].wid = wid; n++;
 		}
-		if (match) run++;
 		else
 		{
-			if (run >= 10)
+			cnt = 0; tail++;
+			while (cnt < 8 && tail < len) { if (s[tail++] != 'N') cnt++; else cnt = 0; }
+			if (cnt != 8) break;
+			head = tail - 8; wid = kmer_fresh_id(s, head);
+			out[n].label = head; out[n].wid = wid; n++;
+			// the for-increment now advances head AND tail: base `tail` is never rolled in (reference behaviour)
+		}
+	}
+	return n;
+}
+
+// word id of the reference 8-mer at absolute position g (RefSequence holds ACGT only)
+MC_HD uint32_t ref_kmer_id(const PipeArgs& a, int64_t g, int64_t* last_g, uint32_t* last_wid)
+{
+	uint32_t w;
+	if (g == *last_g + 1) w = ((*last_wid & 0x3FFFu) << 2) + (uint32_t)mc_ref_code(a.ix, g + 7);
+	else { w = 0; for (int i = 0; i < 8; i++) w = (w << 2) + (uint32_t)mc_ref_code(a.ix, g + i); }
+	*last_g = g; *last_wid = w;
+	return w;
+}
+
+// walks diagonal d (window offset minus word label); returns the sum of seed lengths, optionally writes the seeds
+MC_HD int rescue_scan_diag(const PipeArgs& a, const KmerEnt* km, int nk, int64_t left, int slen, int d, SPair* out, int* nout)
+{
+	int total = 0, run = 0, first = 0, n = 0, prev_label = -2;
+	int64_t last_g = -10; uint32_t last_wid = 0;
+	for (int i = 0; i <= nk; i++)
+	{
+		bool hit = false;
+		if (i < nk)
+		{
+			const int g = km[i].label + d;
+			if (g >= 0 && g <= slen - 8 && left + g >= 0) hit = ref_kmer_id(a, left + g, &last_g, &last_wid) == km[i].wid;
+		}
+		if (hit && run > 0 && km[i].label == prev_label + 1) run++;
+		else
+		{
+			if (run >= 3)
 			{
-				total += run;
-				if (out) { SPair s; s.rpos = q - run; s.gpos = left + d + (q - run); s.len = run; out[n] = s; }
+				const int l = 7 + run;
+				total += l;
+				if (out) { SPair s; s.rpos = km[first].label; s.gpos = left + d + km[first].label; s.len = l; out[n] = s; }
 				n++;
 			}
-			run = 0;
+			run = hit ? 1 : 0; first = i;
 		}
+		prev_label = hit ? km[i].label : -2;
 	}
 	if (nout) *nout = n;
 	return total;
 }
 
-// tries to place `rs` (the mate without a partner) inside [left, right); appends a candidate to read `rt`
-MC_HD bool rescue_try(const PipeArgs& a, int64_t rt, const uint8_t* rs, int rlen, int64_t left, int64_t right, int floor_score,
+// tries to place a mate (word list km) inside [left, right); appends a candidate to read `rt`
+MC_HD bool rescue_try(const PipeArgs& a, int64_t rt, const KmerEnt* km, int nk, int rlen, int64_t left, int64_t right, int floor_score,
                       int anchor_idx, int32_t* new_idx)
 {
 	if (right > a.ix.twoG) right = a.ix.twoG;
@@ -153,18 +202,22 @@ MC_HD bool rescue_try(const PipeArgs& a, int64_t rt, const uint8_t* rs, int rlen
 	int best = 0, bd = 0;
 	for (int d = -(rlen - 8); d <= slen - 8; d++)
 	{
-		int sc = rescue_scan_diag(a, rs, rlen, left, slen, d, 0, 0);
+		int sc = rescue_scan_diag(a, km, nk, left, slen, d, 0, 0);
 		if (sc > best) { best = sc; bd = d; }
 	}
 	if (best == 0 || best <= floor_score) return false;
 	int n = 0;
-	rescue_scan_diag(a, rs, rlen, left, slen, bd, 0, &n);
+	rescue_scan_diag(a, km, nk, left, slen, bd, 0, &n);
 	const int64_t pb = (int64_t)mc_atomic_add(a.pair_bump, (mc_u64)n);
-	if (pb + n > a.pair_cap) { mc_atomic_add(&a.st->overflow, (mc_u64)1); return false; }
-	rescue_scan_diag(a, rs, rlen, left, slen, bd, a.pairs + pb, &n);
+	if (pb + n > a.pair_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 0); return false; }
+	rescue_scan_diag(a, km, nk, left, slen, bd, a.pairs + pb, &n);
 	const int64_t co = pa_cand_off(a, rt);
 	const int k = a.ncand[rt];
-	if (k >= pa_cand_cap(a, rt)) { mc_atomic_add(&a.st->overflow, (mc_u64)1); return false; }
+#ifdef MC_HOSTEMU
+	if (k >= pa_cand_cap(a, rt)) fprintf(stderr, "[trace] cand overflow read %lld k=%d cap=%d ncand0=%d,%d np=%lld,%lld\n", (long long)rt, k, pa_cand_cap(a, rt), a.ncand0[rt & ~1ll], a.ncand0[(rt & ~1ll) + 1],
+		(long long)(pa_pair_off(a, (rt & ~1ll) + 1) - pa_pair_off(a, rt & ~1ll)), (long long)(pa_pair_off(a, (rt & ~1ll) + 2) - pa_pair_off(a, (rt & ~1ll) + 1)));
+#endif
+	if (k >= pa_cand_cap(a, rt)) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 40); return false; }
 	Cand c; c.score = best; c.pbeg = (int32_t)pb; c.pend = (int32_t)(pb + n);
 	a.cands[co + k] = c; a.cscore[co + k] = best; a.cpaired[co + k] = anchor_idx;
 	a.ncand[rt] = k + 1;
@@ -186,19 +239,26 @@ MC_HD void rescue_body(int64_t t, const PipeArgs& a)
 	for (int j = 0; j < n1; j++) if (s1[j] > b1) b1 = s1[j];
 	int strat = (b0 - b1 > (l1 >> 2)) ? 1 : (b1 - b0 > (l0 >> 2)) ? 2 : 3;
 	int rescued = 0;
+	// word lists of both mates live in the (still unused) gapped-fill workspace
+	const int64_t wsn = (int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt);
+	const int64_t ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
+	if (ws + wsn > a.dpws_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
+	KmerEnt* km0 = (KmerEnt*)(a.dpws + ws); KmerEnt* km1 = km0 + l0 + 1;
 	if (strat == 1 || strat == 3) // place mate 2 next to mate 1's candidates
 	{
+		const int nk = kmer_list_of_read(a.seq + a.roff[r1], l1, km1);
 		const int thr = b0 >> 1;
 		for (int i = 0; i < n0; i++)
 		{
 			if (s0[i] < thr || p0[i] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c0 + i]);
 			int32_t k;
-			if (rescue_try(a, r1, a.seq + a.roff[r1], l1, d, d + (int64_t)(uint32_t)est + l1, b1, i, &k)) { p0[i] = k; rescued++; }
+			if (rescue_try(a, r1, km1, nk, l1, d, d + (int64_t)(uint32_t)est + l1, b1, i, &k)) { p0[i] = k; rescued++; }
 		}
 	}
 	if (strat == 2 || strat == 3) // place mate 1 next to mate 2's candidates
 	{
+		const int nk = kmer_list_of_read(a.seq + a.roff[r0], l0, km0);
 		const int thr = b1 >> 1;
 		const int n1_now = a.ncand[r1];
 		for (int j = 0; j < n1_now; j++)
@@ -206,7 +266,7 @@ MC_HD void rescue_body(int64_t t, const PipeArgs& a)
 			if (s1[j] < thr || p1[j] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c1 + j]);
 			int32_t k;
-			if (rescue_try(a, r0, a.seq + a.roff[r0], l0, d - (int64_t)(uint32_t)est, d + l0, b0, j, &k)) { p1[j] = k; rescued++; }
+			if (rescue_try(a, r0, km0, nk, l0, d - (int64_t)(uint32_t)est, d + l0, b0, j, &k)) { p1[j] = k; rescued++; }
 		}
 	}
 	n0 = a.ncand[r0]; n1 = a.ncand[r1];

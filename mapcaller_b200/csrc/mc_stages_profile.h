@@ -39,7 +39,7 @@ MC_HD void profkey_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 		if (first.rPos > 20)
 		{
 			int64_t k = (int64_t)mc_atomic_add(q.bp_bump, (mc_u64)1);
-			if (k < q.bp_cap) q.bp_pos[k] = first.gPos < a.ix.G ? first.gPos : a.ix.twoG - 1 - first.gPos; else mc_atomic_add(&a.st->overflow, (mc_u64)1);
+			if (k < q.bp_cap) q.bp_pos[k] = first.gPos < a.ix.G ? first.gPos : a.ix.twoG - 1 - first.gPos; else mc_atomic_or(&a.st->overflow, (mc_u64)1 << 48);
 		}
 		if (first.rPos > a.pr.max_clip) return;
 	}
@@ -48,7 +48,7 @@ MC_HD void profkey_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 		if (rlen - last.rPos > 20)
 		{
 			int64_t k = (int64_t)mc_atomic_add(q.bp_bump, (mc_u64)1);
-			if (k < q.bp_cap) q.bp_pos[k] = last.gPos < a.ix.G ? last.gPos : a.ix.twoG - 1 - last.gPos; else mc_atomic_add(&a.st->overflow, (mc_u64)1);
+			if (k < q.bp_cap) q.bp_pos[k] = last.gPos < a.ix.G ? last.gPos : a.ix.twoG - 1 - last.gPos; else mc_atomic_or(&a.st->overflow, (mc_u64)1 << 48);
 		}
 		if (rlen - last.rPos > a.pr.max_clip) return;
 	}
@@ -90,7 +90,7 @@ MC_HD void indel_emit(const PipeArgs& a, const ProfArgs& q, int kind, int64_t po
 {
 	const int64_t k = (int64_t)mc_atomic_add(q.ind_bump, (mc_u64)1);
 	const int64_t o = (int64_t)mc_atomic_add(q.ind_seq_bump, (mc_u64)len);
-	if (k >= q.ind_cap || o + len > q.ind_seq_cap) { mc_atomic_add(&a.st->overflow, (mc_u64)1); return; }
+	if (k >= q.ind_cap || o + len > q.ind_seq_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 48); return; }
 	mc_indel_rec rec; rec.pos = pos; rec.kind = kind; rec.len = len; rec.count = 1; rec.seq_off = (int32_t)o;
 	q.ind[k] = rec;
 	for (int i = 0; i < len; i++) q.ind_seq[o + i] = s[i];
