@@ -32,7 +32,10 @@ def make_case(kind: str = "small", seed: int = 1, n_pairs: int = 3000, read_len:
     mut_parts = [sim.mutate(p, seed * 1000 + i, snp_per_mb=3000, small_indel_per_mb=400, large_indel_per_mb=150, sv_per_mb=sv * 30, sv_len=(400, 900))[0]
                  for i, p in enumerate(parts)]
     mut = np.concatenate(mut_parts)
-    r1, r2 = sim.simulate_pairs(mut, n_pairs, read_len, seed=seed + 7, frag_mean=frag_mean, frag_sd=frag_sd, sub_rate=sub_rate, indel_rate=indel_rate, n_rate=n_rate)
+    # Fragments stay clear of the first 3 kbp: for a mate anchored there the reference's rescue window starts before
+    # RefSequence[0] (src/AlignmentRescue.cpp:87,93) and the unmodified reference reads out of bounds (it segfaults on
+    # some hosts), so such reads cannot be pinned against it.
+    r1, r2 = sim.simulate_pairs(mut[3000:], n_pairs, read_len, seed=seed + 7, frag_mean=frag_mean, frag_sd=frag_sd, sub_rate=sub_rate, indel_rate=indel_rate, n_rate=n_rate)
     p = dict(paired=1, alg_ksw2=0, max_pos_diff=30, max_clip=5, max_dup=5, max_mismatch_rate=0.05)
     p.update(params)
     if p["paired"]:
@@ -60,6 +63,23 @@ def ref_results(case, index, want_reads: bool = True):
         subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), job, outp], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         with open(outp, "rb") as fh:
             return pickle.load(fh)
+
+
+def oracle_results(case, index, want_reads: bool = True):
+    """Runs the case through the CPU restatement (oracle/libmcoracle.so)."""
+    import cpu_oracle
+    with tempfile.TemporaryDirectory() as td:
+        prefix = os.path.join(td, "idx")
+        index.save(prefix)
+        orc = cpu_oracle.Oracle(prefix, **case["params"])
+        paired = bool(case["params"]["paired"])
+        reads, est = orc.map_reads(case["seq"], case["off"], paired, True)
+        out = dict(est=est, counters=orc.counters(), profile=orc.profile(), ins=orc.indels(0), dele=orc.indels(1), bp=orc.breakpoints(),
+                   inv=orc.sites(0), tnl=orc.sites(1), work=orc.work())
+        if want_reads:
+            out["reads"] = reads
+        orc.close()
+        return out
 
 
 def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool = True, device: int = 0):
@@ -126,9 +146,5 @@ def smoke_case() -> None:
     case = make_case(seed=3, n_pairs=600, genome_len=40000)
     ix = build_index(case)
     mine = cuda_results(case, ix)
-    if have_ref():
-        assert_same(mine, ref_results(case, ix))
-    else:
-        import golden_util
-        golden_util.check_against_golden("smoke", mine)
+    assert_same(mine, oracle_results(case, ix))
     assert mine["stats"]["kernel_launches"] > 0

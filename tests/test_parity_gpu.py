@@ -1,0 +1,124 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: bit-exact per-read records, EstiDistance trajectory,
+totals, profile, indel maps, break points and SV site lists.
+
+Checker used, in order of availability on the box: oracle/_ref (the unmodified reference; only for cases that
+stay clear of its undefined behaviour), the CPU restatement oracle/libmcoracle.so (pinned against the
+reference by tests/test_oracle.py), and the committed golden vectors."""
+import random
+
+import numpy as np
+import pytest
+
+import cpu_oracle
+import golden_util as gu
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "small": dict(seed=3, n_pairs=600, genome_len=40000),
+    "multi_contig_sv": dict(seed=5, n_pairs=20000, genome_len=300000, contigs=3),
+    "ksw2_indels": dict(seed=6, n_pairs=5000, genome_len=100000, alg_ksw2=1, indel_rate=0.002),
+    "single_end": dict(seed=7, n_pairs=4000, genome_len=80000, paired=0),
+    "n_bases_noisy": dict(seed=8, n_pairs=5000, genome_len=80000, n_rate=0.01, sub_rate=0.02),
+    "sv_repeats": dict(seed=9, n_pairs=20000, genome_len=200000, sv=5.0, n_dup=30, tandem=20),
+    "long_reads_250": dict(seed=10, n_pairs=4000, genome_len=150000, read_len=250, frag_mean=600, frag_sd=80, indel_rate=0.003),
+    "deep_duplicates": dict(seed=11, n_pairs=30000, genome_len=20000, max_dup=3),
+    "params": dict(seed=13, n_pairs=3000, genome_len=60000, max_pos_diff=8, max_clip=2, max_dup=15, max_mismatch_rate=0.1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(gu.GOLDEN_CASES))
+def test_cuda_matches_golden(built, name):
+    """Committed outputs of the unmodified reference."""
+    case, ref = gu.load(name)
+    ix = pu.build_index(case)
+    mine = pu.cuda_results(case, ix)
+    pu.assert_same(mine, ref, paired=bool(case["params"]["paired"]))
+    assert mine["stats"]["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_oracle(built, name):
+    case = pu.make_case(**CASES[name])
+    ix = pu.build_index(case)
+    mine = pu.cuda_results(case, ix)
+    orc = pu.oracle_results(case, ix)
+    pu.assert_same(mine, orc, paired=bool(case["params"]["paired"]))
+    # the work counters the roofline is computed from are the oracle's, exactly
+    for k in ("seed_blocks", "locate_blocks", "sa_reads"):
+        assert mine["stats"][k] == orc["work"][k], k
+
+
+@pytest.mark.skipif(not pu.have_ref(), reason="oracle/_ref not on this box")
+@pytest.mark.parametrize("name", ["small", "ksw2_indels", "single_end", "n_bases_noisy"])
+def test_cuda_matches_reference(built, name):
+    case = pu.make_case(**CASES[name])
+    ix = pu.build_index(case)
+    pu.assert_same(pu.cuda_results(case, ix), pu.ref_results(case, ix), paired=bool(case["params"]["paired"]))
+
+
+@pytest.mark.parametrize("batch_reads", [200, 1000, 7400])
+def test_batch_split_invariance(built, batch_reads):
+    """The result must not depend on how the read stream is cut into batches (chunk protocol + avgDist feedback)."""
+    case = pu.make_case(seed=12, n_pairs=12000, genome_len=100000)
+    ix = pu.build_index(case)
+    whole = pu.cuda_results(case, ix)
+    parts = pu.cuda_results(case, ix, batch_reads=batch_reads)
+    pu.assert_same(parts, whole)
+
+
+def test_edge_cases(built):
+    """Empty batch, reads shorter than a seed, all-N reads, unmappable reads, a read longer than the limit."""
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=14, n_pairs=50, genome_len=30000)
+    ix = pu.build_index(case)
+    with api.Context(ix, paired=1, want_alignments=1) as ctx:
+        res = ctx.map_batch(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64))
+        assert len(res["chunks"]) == 0
+        reads = [b"ACGT", b"ACGTACGTACGTACGT", b"N" * 100, b"ACGT" * 25, case["r1"][0].tobytes(), case["r2"][0].tobytes(), b"", b"A"]
+        seq = np.frombuffer(b"".join(reads), dtype=np.uint8)
+        off = np.zeros(len(reads) + 1, dtype=np.int64); off[1:] = np.cumsum([len(r) for r in reads])
+        res = ctx.map_batch(seq, off)
+        got = api.unpack_reads(res)
+        assert [r["score"] for r in got[:4]] == [0, 0, 0, 0] and got[4]["score"] > 0 and got[5]["score"] > 0
+        with pytest.raises(api.McError):
+            ctx.map_batch(np.zeros(5000, dtype=np.uint8) + 65, np.array([0, 4500, 5000], dtype=np.int64))
+        with pytest.raises(api.McError):
+            ctx.map_batch(seq[:off[3]], off[:4])     # odd number of reads in paired mode
+    case2 = dict(case, seq=seq, off=off)
+    pu.assert_same(pu.cuda_results(case2, ix), pu.oracle_results(case2, ix))
+
+
+def test_gapped_fill_kernel_matches_oracle(built):
+    """mc_align_batch (the DP kernel on its own) vs the oracle's nw / ksw2 on random, mutated and tandem inputs."""
+    from mapcaller_b200 import api
+    rnd = random.Random(11)
+
+    def rs(n, alpha="ACGT"):
+        return "".join(rnd.choice(alpha) for _ in range(n))
+
+    probs = []
+    for _ in range(4000):
+        m = rnd.randint(1, 90)
+        k = rnd.random()
+        if k < 0.3:
+            a, b = rs(m), rs(rnd.randint(1, 90))
+        elif k < 0.8:
+            a = rs(m)
+            b = "".join(c if rnd.random() > 0.15 else rnd.choice(["", "A", "C", "G", "T", "N", c + rnd.choice("ACGT")]) for c in a) or "A"
+        else:
+            u = rs(rnd.randint(1, 3))
+            a, b = (u * 50)[:m], (u * 50)[:rnd.randint(1, 90)]
+        probs.append((a.encode(), b.encode()))
+    probs.append((b"A" * 300, b"A" * 250 + b"C" * 70))
+    case = pu.make_case(seed=14, n_pairs=10, genome_len=20000)
+    with api.Context(pu.build_index(case)) as ctx:
+        for ksw2 in (False, True):
+            mine = ctx.align_batch(probs, ksw2=ksw2)
+            for p, m in zip(probs, mine):
+                assert m == cpu_oracle.align(not ksw2, p[0], p[1]), (ksw2, p)
+
+
+def test_smoke(built):
+    pu.smoke_case()
