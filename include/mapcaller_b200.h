@@ -143,6 +143,8 @@ int mc_map_batch(mc_ctx *ctx, const mc_batch_in *in, mc_batch_out *out);
 typedef struct { int64_t total_reads, total_mapped, total_paired, total_distance, read_length_sum; uint32_t avg_dist; uint32_t pad; } mc_totals;
 int mc_get_totals(const mc_ctx *ctx, mc_totals *out);
 int mc_set_totals(mc_ctx *ctx, const mc_totals *in);
+/* Back to the state of a fresh context (empty profile, avgDist = 1000, totals 0): the start of a new library run. */
+int mc_reset(mc_ctx *ctx);
 
 /* ---- profile (reference MappingRecordArr / InsertSeqMap / DeleteSeqMap / BreakPointMap /
  *      InversionSiteVec / TranslocationSiteVec; src/structure.h:152-163,220-221) --------------- */

@@ -94,6 +94,7 @@ def lib():
         L.mc_map_staged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BatchOut)]
         L.mc_get_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
         L.mc_set_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
+        L.mc_reset.argtypes = [C.c_void_p]
         L.mc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.mc_reset_stats.argtypes = [C.c_void_p]
         L.mc_profile_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
@@ -249,6 +250,9 @@ class Context:
         for k, v in kw.items():
             setattr(t, k, v)
         _check(lib().mc_set_totals(self._h, C.byref(t)), "mc_set_totals")
+
+    def reset(self):
+        _check(lib().mc_reset(self._h), "mc_reset")
 
     def stats(self) -> dict:
         s = Stats()

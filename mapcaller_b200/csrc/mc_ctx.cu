@@ -98,7 +98,7 @@ struct HBuf {
 	template <class T> T* as() const { return (T*)p; }
 };
 
-enum { EV_START, EV_H2D, EV_SEED, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_COUNT };
+enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_COUNT };
 
 struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key; mc_u64 pad; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
@@ -122,7 +122,7 @@ struct mc_ctx {
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
-	DBuf d_keys, d_keys_tmp, d_accept, d_sort;
+	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo;
 	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
 	HBuf h_in_seq, h_in_off, h_seed_off, h_small, h_chunk, h_chunk_lo, h_chunk_hi, h_pairs, h_reads, h_cands, h_frags, h_aln, h_misc;
@@ -157,7 +157,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo};
 	for (DBuf* b : bufs) b->release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
@@ -230,6 +230,20 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	return MC_OK;
 }
 
+int mc_reset(mc_ctx* c)
+{
+	if (!c) { mc_set_error("mc_reset: null context"); return MC_ERR_ARG; }
+	int bad = 0;
+	if (c->prm.update_profile)
+	{
+		bad |= dev_zero(c->d_cnt16.p, (size_t)c->G * 16, c->stream) || dev_zero(c->d_multi.p, (size_t)c->G * 4, c->stream) || dev_zero(c->d_rcount.p, (size_t)c->G, c->stream);
+	}
+	bad |= dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream) || dev_sync(c->stream);
+	memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = 1000;
+	c->inv_sites.clear(); c->tnl_sites.clear(); c->discord_gpos = c->discord_dist = 0;
+	return bad ? MC_ERR_CUDA : MC_OK;
+}
+
 int mc_get_totals(const mc_ctx* c, mc_totals* out) { if (!c || !out) return MC_ERR_ARG; *out = c->tot; return MC_OK; }
 int mc_set_totals(mc_ctx* c, const mc_totals* in) { if (!c || !in) return MC_ERR_ARG; c->tot = *in; return MC_OK; }
 int mc_get_stats(const mc_ctx* c, mc_stats* out) { if (!c || !out) return MC_ERR_ARG; *out = c->stats; out->kernel_launches = g_launches; return MC_OK; }
@@ -292,7 +306,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(n_chunks * sizeof(mc_chunk_out));
 	bad |= c->d_chunk_lo.reserve(n_chunks * 4) || c->d_chunk_hi.reserve(n_chunks * 4);
 	bad |= c->d_pair_flag.reserve((n_pairs + 1) * 4) || c->d_est_lo.reserve((n_pairs + 1) * 4) || c->d_est_hi.reserve((n_pairs + 1) * 4);
-	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4) || c->d_accept.reserve(n + 1);
+	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4 * 4) || c->d_accept.reserve(n + 1) || c->d_read_redo.reserve(n + 1);
 	bad |= c->h_chunk.reserve(n_chunks * sizeof(mc_chunk_out)) || c->h_chunk_lo.reserve(n_chunks * 4) || c->h_chunk_hi.reserve(n_chunks * 4);
 	if (bad) return MC_ERR_CUDA;
 	a.slot_freq = c->d_slot_freq.as<uint32_t>(); a.seeds = c->d_seeds.as<Seed>(); a.slot_loc = c->d_slot_loc.as<int64_t>();
@@ -300,7 +314,8 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	a.est = c->d_est.as<int32_t>(); a.active = c->d_active.as<uint8_t>(); a.chunk_out = c->d_chunk_out.as<mc_chunk_out>();
 	a.chunk_lo = c->d_chunk_lo.as<int32_t>(); a.chunk_hi = c->d_chunk_hi.as<int32_t>();
 	a.pair_flag = c->d_pair_flag.as<int32_t>(); a.est_lo = c->d_est_lo.as<int32_t>(); a.est_hi = c->d_est_hi.as<int32_t>();
-	a.pair_out = c->d_pair_out.as<mc_pair_out>(); a.rtask = c->d_rtask.as<int32_t>();
+	a.pair_out = c->d_pair_out.as<mc_pair_out>(); a.rtask = c->d_rtask.as<int32_t>(); a.read_redo = c->d_read_redo.as<uint8_t>();
+	const int64_t rtask_cap = (n_pairs + 1) * 4;
 	Bumps* db = c->d_bumps.as<Bumps>();
 	a.pair_bump = &db->pair; a.frag_bump = &db->frag; a.aln_bump = &db->aln; a.task_bump = &db->task; a.dpws_bump = &db->dpws; a.rtask_bump = &db->rtask;
 	a.prof.cnt16 = c->d_cnt16.as<uint32_t>(); a.prof.multi = c->d_multi.as<uint32_t>(); a.prof.rcount = c->d_rcount.as<uint8_t>();
@@ -309,6 +324,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	ev_record(&c->ev[EV_H2D], s);
 	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats), s);
 	if (prep_needed) launch_prep(a, n, s);
+	ev_record(&c->ev[EV_SEED0], s);
 	launch_seed(a, n, s);
 	ev_record(&c->ev[EV_SEED], s);
 	device_scan_u32(a.slot_freq, c->d_slot_loc.as<int64_t>(), st.n_slots, c->d_scan.as<int64_t>(), s);
@@ -341,6 +357,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		a.tasks = c->d_tasks.as<DpTask>(); a.task_cap = task_cap; a.dpws = c->d_dpws.as<uint8_t>(); a.dpws_cap = dpws_cap;
 
 		launch_expand(a, st.n_slots, s);
+		ev_record(&c->ev[EV_LOC0], s);
 		launch_locate(a, n_locs, s);
 		ev_record(&c->ev[EV_LOCATE], s);
 		launch_cluster(a, n, s);
@@ -354,36 +371,29 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		if (paired && c->tot.total_paired <= 1000)
 			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2; k < n_chunks; k++) active[k] = 0;
 		Bumps hb; memset(&hb, 0, sizeof(hb)); hb.pair = (mc_u64)n_locs;
-		bad |= dev_h2d(db, &hb, sizeof(hb), s);
+		bad |= dev_h2d(db, &hb, sizeof(hb), s) || dev_zero(c->d_pair_flag.p, (n_pairs + 1) * 4, s);
 		mc_totals run = c->tot;
 		c->chunks_final.assign(n_chunks, mc_chunk_out());
-		int64_t first_open = 0, prev_tasks = 0, prev_rtasks = 0;
+		int64_t first_open = 0;
 		int replays = 0; bool overflow = false, first_attempt = true;
+		Bumps* hbp = (Bumps*)(h_small + 64);   // pinned copy of the arena cursors, refreshed at the end of every attempt
+		memset(hbp, 0, sizeof(Bumps));
 		ev_record(&c->ev[EV_PAIR0], s);
 		while (first_open < n_chunks)
 		{
+			// one attempt: no host round trip inside it, the task lists are consumed from their device-side cursors
+			a.rtask_begin = (int64_t)hbp->rtask; a.task_begin = (int64_t)hbp->task;
+			if (a.rtask_begin + n_pairs > rtask_cap) { mc_set_error("mc_map_batch: too many speculation replays in one batch"); return MC_ERR_OVERFLOW; }
 			bad |= dev_h2d(c->d_est.p, est.data(), n_chunks * 4, s) || dev_h2d(c->d_active.p, active.data(), n_chunks, s);
-			if (paired) launch_pair(a, n_pairs, s); else launch_single(a, n, s);
-			if (paired)
-			{
-				bad |= dev_d2h(h_small, &db->rtask, 8, s) || dev_sync(s);
-				if (bad) return MC_ERR_CUDA;
-				const int64_t rt = h_small[0];
-				// rescue tasks of this attempt are rtask[prev_rtasks, rt)
-				if (rt > prev_rtasks) { PipeArgs b = a; b.rtask = a.rtask + prev_rtasks; launch_rescue(b, rt - prev_rtasks, s); }
-				prev_rtasks = rt;
-			}
+			if (paired) { launch_pair(a, n_pairs, s); launch_rescue(a, n_pairs, s); } else launch_single(a, n, s);
 			if (first_attempt) ev_record(&c->ev[EV_PAIR1], s);
 			first_attempt = false;
 			launch_alnprep(a, n, s);
-			bad |= dev_d2h(h_small, &db->task, 8, s) || dev_sync(s);
-			if (bad) return MC_ERR_CUDA;
-			int64_t nt = h_small[0]; if (nt > task_cap) nt = task_cap;
-			if (nt > prev_tasks) { PipeArgs b = a; b.tasks = a.tasks + prev_tasks; launch_dp(b, nt - prev_tasks, s); }
-			prev_tasks = nt;
+			launch_dp(a, task_cap - a.task_begin, s);
 			launch_alnfin(a, n, s);
 			if (paired) launch_pairstat(a, n_pairs, s);
 			launch_chunkstat(a, n_chunks, s);
+			bad |= dev_d2h(hbp, db, sizeof(Bumps), s);
 			DevStats* hst = (DevStats*)(h_small + 8);
 			bad |= dev_d2h(c->h_chunk.p, c->d_chunk_out.p, n_chunks * sizeof(mc_chunk_out), s) || dev_d2h(c->h_chunk_lo.p, c->d_chunk_lo.p, n_chunks * 4, s);
 			bad |= dev_d2h(c->h_chunk_hi.p, c->d_chunk_hi.p, n_chunks * 4, s) || dev_d2h(hst, c->d_stats.p, sizeof(DevStats), s) || dev_sync(s);
@@ -534,8 +544,8 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		c->tot = run;
 		// stats
 		c->stats.ms_h2d += ev_ms(&c->ev[EV_START], &c->ev[EV_H2D]);
-		c->stats.ms_seed += ev_ms(&c->ev[EV_H2D], &c->ev[EV_SEED]);
-		c->stats.ms_locate += ev_ms(&c->ev[EV_SEED], &c->ev[EV_LOCATE]);
+		c->stats.ms_seed += ev_ms(&c->ev[EV_SEED0], &c->ev[EV_SEED]);     // the seed kernel alone
+		c->stats.ms_locate += ev_ms(&c->ev[EV_LOC0], &c->ev[EV_LOCATE]);   // the locate kernel alone
 		c->stats.ms_cluster += ev_ms(&c->ev[EV_LOCATE], &c->ev[EV_CLUSTER]);
 		c->stats.ms_pair += ev_ms(&c->ev[EV_PAIR0], &c->ev[EV_PAIR1]);
 		c->stats.ms_align += ev_ms(&c->ev[EV_PAIR1], &c->ev[EV_ALN1]);

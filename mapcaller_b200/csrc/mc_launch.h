@@ -14,6 +14,7 @@ typedef int mc_stream_t;
 #define MC_LAUNCH2(name) \
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
 static void launch_scatter(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) scatter_body(i, 0, 1, a, q); }
+static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a); }
 static void launch_profpack(const DevProfile& p, int64_t beg, int64_t n, uint64_t* out, mc_stream_t) { for (int64_t i = 0; i < n; i++) profpack_body(i, p, beg, out); }
 static int64_t g_launches = 0;
 #else
@@ -38,6 +39,14 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_scatter_kernel(const PipeArgs a, 
 }
 static void launch_scatter(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t s)
 { if (n > 0) { mc_scatter_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n); g_launches++; } }
+// one warp per rescue task
+__global__ void __launch_bounds__(MC_BLOCK) mc_rescue_kernel(const PipeArgs a, int64_t n)
+{
+	int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+	if (w < n) rescue_body(w, threadIdx.x & 31, 32, a);
+}
+static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_rescue_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profpack_kernel(const DevProfile p, int64_t beg, int64_t n, uint64_t* out)
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) profpack_body(i, p, beg, out); }
 static void launch_profpack(const DevProfile& p, int64_t beg, int64_t n, uint64_t* out, mc_stream_t s)
@@ -51,7 +60,6 @@ MC_LAUNCH1(locate)
 MC_LAUNCH1(cluster)
 MC_LAUNCH1(single)
 MC_LAUNCH1(pair)
-MC_LAUNCH1(rescue)
 MC_LAUNCH1(alnprep)
 MC_LAUNCH1(dp)
 MC_LAUNCH1(alnfin)

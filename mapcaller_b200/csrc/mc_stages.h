@@ -55,7 +55,8 @@ struct PipeArgs {
 	// per pair / per chunk
 	const int32_t* est;      // per chunk: EstiDistance = (int)(avgDist*1.5)
 	const uint8_t* active;   // per chunk: 1 = (re)compute in this attempt
-	int32_t* pair_flag;      // per pair: 1 = needs rescue
+	int32_t* pair_flag;      // per pair: bit0 = a result of this batch exists, bit1 = recomputed in the current attempt
+	uint8_t* read_redo;      // per read: 1 = (re)computed in the current attempt
 	int32_t* est_lo;         // per pair: smallest / largest EstiDistance giving the same outcome
 	int32_t* est_hi;
 	mc_pair_out* pair_out;   // per pair
@@ -69,6 +70,7 @@ struct PipeArgs {
 	uint8_t* dpws; int64_t dpws_cap; mc_u64* dpws_bump;
 	int32_t* rtask;          // rescue task list (pair ids)
 	mc_u64* rtask_bump;
+	int64_t rtask_begin, task_begin; // tasks of the current attempt are [begin, *bump)
 	// profile
 	DevProfile prof;
 	int64_t first_read;      // global index of read 0 of this batch (parity of mate, dedup order)

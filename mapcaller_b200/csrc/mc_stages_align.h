@@ -23,7 +23,7 @@ MC_HOST_HD int64_t dp_ws_bytes(int m, int n)
 // ------------------------------------------------------------------------------------------------
 MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 {
-	if (!a.active[pa_chunk_of_read(r)]) return;
+	if (!a.read_redo[r]) return;
 	const uint8_t* rs = a.seq + a.roff[r];
 	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
 	const int64_t co = pa_cand_off(a, r);
@@ -174,7 +174,11 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 
 MC_HD void dp_body(int64_t t, const PipeArgs& a)
 {
-	const DpTask tk = a.tasks[t];
+	{
+		int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
+		if (a.task_begin + t >= end) return;
+	}
+	const DpTask tk = a.tasks[a.task_begin + t];
 	mc_frag_out& x = a.frags[tk.frag];
 	const int m = tk.m, n = tk.n, cp = x.aln_cap;
 	uint8_t* s1 = a.aln + x.aln_off; uint8_t* s2 = s1 + cp;   // read piece (m), genome piece (n)
@@ -308,7 +312,7 @@ MC_HD bool local_quality_ok(const PipeArgs& a, const mc_frag_out& x)
 
 MC_HD void alnfin_body(int64_t r, const PipeArgs& a)
 {
-	if (!a.active[pa_chunk_of_read(r)]) return;
+	if (!a.read_redo[r]) return;
 	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
 	const int64_t co = pa_cand_off(a, r);
 	const int nc = a.ncand[r];
@@ -403,7 +407,7 @@ MC_HD int64_t cand_first_gpos(const PipeArgs& a, int64_t co, int ci) { return a.
 MC_HD void pairstat_body(int64_t p, const PipeArgs& a)
 {
 	const int64_t r0 = 2 * p, r1 = r0 + 1;
-	if (!a.active[pa_chunk_of_read(r0)]) return;
+	if (!a.read_redo[r0]) return;
 	const int64_t c0 = pa_cand_off(a, r0), c1 = pa_cand_off(a, r1);
 	const int n0 = a.ncand[r0], n1 = a.ncand[r1];
 	mc_pair_out o; o.gPos1 = 0; o.gPos2 = 0; o.dist = 0;

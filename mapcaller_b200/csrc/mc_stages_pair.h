@@ -25,6 +25,7 @@ MC_HD void mask_unpaired(int32_t* s0, int32_t* p0, int n0, int32_t* s1, int32_t*
 // single-end reads: RemoveRedundantAlnCan only (reference src/ReadMapping.cpp:583)
 MC_HD void single_body(int64_t r, const PipeArgs& a)
 {
+	a.read_redo[r] = a.active[pa_chunk_of_read(r)];
 	if (!a.active[pa_chunk_of_read(r)]) return;
 	const int64_t co = pa_cand_off(a, r);
 	const int n = a.ncand0[r];
@@ -41,8 +42,12 @@ MC_HD void pair_body(int64_t p, const PipeArgs& a)
 {
 	const int64_t r0 = 2 * p, r1 = r0 + 1;
 	const int chunk = pa_chunk_of_read(r0);
+	a.read_redo[r0] = 0; a.read_redo[r1] = 0;
 	if (!a.active[chunk]) return;
 	const int est = a.est[chunk];
+	// a result computed earlier in this batch stays valid while the new EstiDistance is inside its interval
+	if ((a.pair_flag[p] & 1) && a.est_lo[p] <= est && est <= a.est_hi[p]) return;
+	a.pair_flag[p] = 1; a.read_redo[r0] = 1; a.read_redo[r1] = 1;
 	const int64_t c0 = pa_cand_off(a, r0), c1 = pa_cand_off(a, r1);
 	const int n0 = a.ncand0[r0], n1 = a.ncand0[r1];
 	a.ncand[r0] = n0; a.ncand[r1] = n1;
@@ -85,15 +90,15 @@ MC_HD void pair_body(int64_t p, const PipeArgs& a)
 		for (int i = 0; i < n0; i++) if (s0[i] > b0) b0 = s0[i];
 		for (int j = 0; j < n1; j++) if (s1[j] > b1) b1 = s1[j];
 		const int l0 = (int)(a.roff[r0 + 1] - a.roff[r0]), l1 = (int)(a.roff[r1 + 1] - a.roff[r1]);
-		if (b0 < (l0 >> 2) && b1 < (l1 >> 2)) { remove_redundant(s0, n0); remove_redundant(s1, n1); a.pair_flag[p] = 0; }
+		if (b0 < (l0 >> 2) && b1 < (l1 >> 2)) { remove_redundant(s0, n0); remove_redundant(s1, n1); }
 		else
 		{
-			a.pair_flag[p] = 1; lo = est; hi = est;
+			lo = est; hi = est;
 			int64_t k = (int64_t)mc_atomic_add(a.rtask_bump, (mc_u64)1);
 			a.rtask[k] = (int32_t)p;
 		}
 	}
-	else { mask_unpaired(s0, p0, n0, s1, p1, n1); a.pair_flag[p] = 0; }
+	else mask_unpaired(s0, p0, n0, s1, p1, n1);
 	a.est_lo[p] = lo; a.est_hi[p] = hi;
 }
 
@@ -188,9 +193,13 @@ MC_HD int rescue_scan_diag(const PipeArgs& a, const KmerEnt* km, int nk, int64_t
 	return total;
 }
 
-// tries to place a mate (word list km) inside [left, right); appends a candidate to read `rt`
-MC_HD bool rescue_try(const PipeArgs& a, int64_t rt, const KmerEnt* km, int nk, int rlen, int64_t left, int64_t right, int floor_score,
-                      int anchor_idx, int32_t* new_idx)
+// tries to place a mate (word list km) inside [left, right); appends a candidate to read `rt`.
+// `nl` lanes cooperate (a warp on the GPU): (1) every reference 8-mer of the window is compared with the read's
+// words and the hits are histogrammed per diagonal, (2) only diagonals with >= 3 hits (a seed needs a run of 3) are
+// walked exactly, (3) the best diagonal is reduced over the lanes, (4) lane 0 appends the candidate.
+// All lanes return the same value.
+MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const KmerEnt* km, int nk, int rlen, int64_t left, int64_t right,
+                      int floor_score, int anchor_idx, uint32_t* hits, int32_t* lanebuf, int32_t* new_idx)
 {
 	if (right > a.ix.twoG) right = a.ix.twoG;
 	int i1 = mc_chrom_lower_bound(a.ix, left), i2 = mc_chrom_lower_bound(a.ix, right);
@@ -199,66 +208,113 @@ MC_HD bool rescue_try(const PipeArgs& a, int64_t rt, const KmerEnt* km, int nk, 
 	const int64_t sl = right - left;
 	if (sl < rlen) return false;
 	const int slen = (int)sl;
-	int best = 0, bd = 0;
-	for (int d = -(rlen - 8); d <= slen - 8; d++)
+	const int dmin = -(rlen - 8), ndiag = slen - 8 - dmin + 1;
+	for (int i = lane; i < ndiag; i += nl) hits[i] = 0;
+	MC_WARP_SYNC();
 	{
-		int sc = rescue_scan_diag(a, km, nk, left, slen, d, 0, 0);
-		if (sc > best) { best = sc; bd = d; }
+		// each lane owns a contiguous run of window positions so the reference word can be rolled
+		const int npos = slen - 7, per = (npos + nl - 1) / nl;
+		int g0 = lane * per, g1 = g0 + per; if (g1 > npos) g1 = npos;
+		int64_t last_g = -10; uint32_t last_wid = 0;
+		for (int g = g0; g < g1; g++)
+		{
+			if (left + g < 0) continue;
+			const uint32_t w = ref_kmer_id(a, left + g, &last_g, &last_wid);
+			for (int i = 0; i < nk; i++) if (km[i].wid == w) mc_atomic_add(&hits[g - km[i].label - dmin], 1u);
+		}
 	}
+	MC_WARP_SYNC();
+	int best = 0, bd = 0;
+	for (int i = lane; i < ndiag; i += nl)
+	{
+		if (hits[i] < 3) continue;
+		const int sc = rescue_scan_diag(a, km, nk, left, slen, i + dmin, 0, 0);
+		if (sc > best) { best = sc; bd = i + dmin; }   // ascending diagonals inside a lane: first maximum wins
+	}
+	lanebuf[2 * lane] = best; lanebuf[2 * lane + 1] = bd;
+	MC_WARP_SYNC();
+	best = 0; bd = 0;
+	for (int l = 0; l < nl; l++)
+	{
+		const int sc = lanebuf[2 * l], d = lanebuf[2 * l + 1];
+		if (sc > best || (sc == best && sc > 0 && d < bd)) { best = sc; bd = d; }
+	}
+	MC_WARP_SYNC();
 	if (best == 0 || best <= floor_score) return false;
-	int n = 0;
-	rescue_scan_diag(a, km, nk, left, slen, bd, 0, &n);
-	const int64_t pb = (int64_t)mc_atomic_add(a.pair_bump, (mc_u64)n);
-	if (pb + n > a.pair_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 0); return false; }
-	rescue_scan_diag(a, km, nk, left, slen, bd, a.pairs + pb, &n);
-	const int64_t co = pa_cand_off(a, rt);
-	const int k = a.ncand[rt];
-#ifdef MC_HOSTEMU
-	if (k >= pa_cand_cap(a, rt)) fprintf(stderr, "[trace] cand overflow read %lld k=%d cap=%d ncand0=%d,%d np=%lld,%lld\n", (long long)rt, k, pa_cand_cap(a, rt), a.ncand0[rt & ~1ll], a.ncand0[(rt & ~1ll) + 1],
-		(long long)(pa_pair_off(a, (rt & ~1ll) + 1) - pa_pair_off(a, rt & ~1ll)), (long long)(pa_pair_off(a, (rt & ~1ll) + 2) - pa_pair_off(a, (rt & ~1ll) + 1)));
-#endif
-	if (k >= pa_cand_cap(a, rt)) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 40); return false; }
-	Cand c; c.score = best; c.pbeg = (int32_t)pb; c.pend = (int32_t)(pb + n);
-	a.cands[co + k] = c; a.cscore[co + k] = best; a.cpaired[co + k] = anchor_idx;
-	a.ncand[rt] = k + 1;
-	*new_idx = k;
-	return true;
+	if (lane == 0)
+	{
+		int n = 0, ok = 1, k = -1;
+		rescue_scan_diag(a, km, nk, left, slen, bd, 0, &n);
+		const int64_t pb = (int64_t)mc_atomic_add(a.pair_bump, (mc_u64)n);
+		if (pb + n > a.pair_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 0); ok = 0; }
+		if (ok)
+		{
+			rescue_scan_diag(a, km, nk, left, slen, bd, a.pairs + pb, &n);
+			const int64_t co = pa_cand_off(a, rt);
+			k = a.ncand[rt];
+			if (k >= pa_cand_cap(a, rt)) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 40); ok = 0; }
+			else
+			{
+				Cand c; c.score = best; c.pbeg = (int32_t)pb; c.pend = (int32_t)(pb + n);
+				a.cands[co + k] = c; a.cscore[co + k] = best; a.cpaired[co + k] = anchor_idx;
+				a.ncand[rt] = k + 1;
+			}
+		}
+		lanebuf[2 * nl] = ok; lanebuf[2 * nl + 1] = k;
+	}
+	MC_WARP_SYNC();
+	const int ok = lanebuf[2 * nl]; *new_idx = lanebuf[2 * nl + 1];
+	MC_WARP_SYNC();
+	return ok != 0;
 }
 
-MC_HD void rescue_body(int64_t t, const PipeArgs& a)
+MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
 {
-	const int64_t p = a.rtask[t];
+	if (a.rtask_begin + t >= (int64_t)*a.rtask_bump) return;
+	const int64_t p = a.rtask[a.rtask_begin + t];
 	const int64_t r0 = 2 * p, r1 = r0 + 1;
 	const int est = a.est[pa_chunk_of_read(r0)];
 	const int64_t c0 = pa_cand_off(a, r0), c1 = pa_cand_off(a, r1);
 	const int l0 = (int)(a.roff[r0 + 1] - a.roff[r0]), l1 = (int)(a.roff[r1 + 1] - a.roff[r1]);
 	int32_t *s0 = a.cscore + c0, *s1 = a.cscore + c1, *p0 = a.cpaired + c0, *p1 = a.cpaired + c1;
-	int n0 = a.ncand[r0], n1 = a.ncand[r1];
+	const int n0 = a.ncand[r0], n1 = a.ncand[r1];
 	int b0 = 0, b1 = 0;
 	for (int i = 0; i < n0; i++) if (s0[i] > b0) b0 = s0[i];
 	for (int j = 0; j < n1; j++) if (s1[j] > b1) b1 = s1[j];
-	int strat = (b0 - b1 > (l1 >> 2)) ? 1 : (b1 - b0 > (l0 >> 2)) ? 2 : 3;
+	const int strat = (b0 - b1 > (l1 >> 2)) ? 1 : (b1 - b0 > (l0 >> 2)) ? 2 : 3;
 	int rescued = 0;
-	// word lists of both mates live in the (still unused) gapped-fill workspace
-	const int64_t wsn = (int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt);
-	const int64_t ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
-	if (ws + wsn > a.dpws_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
+	// scratch in the (still unused) gapped-fill workspace: both word lists, the diagonal histogram, the lane buffer
+	const int lmax = l0 > l1 ? l0 : l1;
+	const int64_t n_hits = (int64_t)(uint32_t)est + 3 * (int64_t)lmax + 16;
+	const int64_t wsn = ((int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (2 * nl + 2) * 4 + 15) & ~15ll;
+	int64_t ws = 0;
+	if (lane == 0) ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
+	ws = mc_bcast64(ws);
+	if (ws + wsn > a.dpws_cap) { if (lane == 0) mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
 	KmerEnt* km0 = (KmerEnt*)(a.dpws + ws); KmerEnt* km1 = km0 + l0 + 1;
+	uint32_t* hits = (uint32_t*)(km1 + l1 + 1); int32_t* lanebuf = (int32_t*)(hits + n_hits);
 	if (strat == 1 || strat == 3) // place mate 2 next to mate 1's candidates
 	{
-		const int nk = kmer_list_of_read(a.seq + a.roff[r1], l1, km1);
+		if (lane == 0) lanebuf[0] = kmer_list_of_read(a.seq + a.roff[r1], l1, km1);
+		MC_WARP_SYNC();
+		const int nk = lanebuf[0];
+		MC_WARP_SYNC();
 		const int thr = b0 >> 1;
 		for (int i = 0; i < n0; i++)
 		{
 			if (s0[i] < thr || p0[i] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c0 + i]);
 			int32_t k;
-			if (rescue_try(a, r1, km1, nk, l1, d, d + (int64_t)(uint32_t)est + l1, b1, i, &k)) { p0[i] = k; rescued++; }
+			if (rescue_try(a, lane, nl, r1, km1, nk, l1, d, d + (int64_t)(uint32_t)est + l1, b1, i, hits, lanebuf, &k)) { if (lane == 0) p0[i] = k; rescued++; }
+			MC_WARP_SYNC();
 		}
 	}
 	if (strat == 2 || strat == 3) // place mate 1 next to mate 2's candidates
 	{
-		const int nk = kmer_list_of_read(a.seq + a.roff[r0], l0, km0);
+		if (lane == 0) lanebuf[0] = kmer_list_of_read(a.seq + a.roff[r0], l0, km0);
+		MC_WARP_SYNC();
+		const int nk = lanebuf[0];
+		MC_WARP_SYNC();
 		const int thr = b1 >> 1;
 		const int n1_now = a.ncand[r1];
 		for (int j = 0; j < n1_now; j++)
@@ -266,12 +322,16 @@ MC_HD void rescue_body(int64_t t, const PipeArgs& a)
 			if (s1[j] < thr || p1[j] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c1 + j]);
 			int32_t k;
-			if (rescue_try(a, r0, km0, nk, l0, d - (int64_t)(uint32_t)est, d + l0, b0, j, &k)) { p1[j] = k; rescued++; }
+			if (rescue_try(a, lane, nl, r0, km0, nk, l0, d - (int64_t)(uint32_t)est, d + l0, b0, j, hits, lanebuf, &k)) { if (lane == 0) p1[j] = k; rescued++; }
+			MC_WARP_SYNC();
 		}
 	}
-	n0 = a.ncand[r0]; n1 = a.ncand[r1];
-	if (rescued == 0) { remove_redundant(s0, n0); remove_redundant(s1, n1); }
-	else mask_unpaired(s0, p0, n0, s1, p1, n1);
+	if (lane == 0)
+	{
+		const int m0 = a.ncand[r0], m1 = a.ncand[r1];
+		if (rescued == 0) { remove_redundant(s0, m0); remove_redundant(s1, m1); }
+		else mask_unpaired(s0, p0, m0, s1, p1, m1);
+	}
 }
 
 #endif
