@@ -725,17 +725,20 @@ int mc_align_batch(mc_ctx* c, int32_t use_ksw2, int64_t n, const uint8_t* s1, co
 		memcpy(h_aln.data() + fr[i].aln_off, s1 + off1[i], (size_t)fr[i].rLen);
 		memcpy(h_aln.data() + fr[i].aln_off + fr[i].aln_cap, s2 + off2[i], (size_t)fr[i].gLen);
 	}
-	DBuf d_fr, d_tk, d_aln, d_ws;
-	int bad = d_fr.reserve(n * sizeof(mc_frag_out)) || d_tk.reserve(n * sizeof(DpTask)) || d_aln.reserve(aln_bytes) || d_ws.reserve(ws_bytes);
+	DBuf d_fr, d_tk, d_aln, d_ws, d_cnt;
+	mc_u64 h_cnt = (mc_u64)n;
+	int bad = d_fr.reserve(n * sizeof(mc_frag_out)) || d_tk.reserve(n * sizeof(DpTask)) || d_aln.reserve(aln_bytes) || d_ws.reserve(ws_bytes) || d_cnt.reserve(8);
+	bad = bad || dev_h2d(d_cnt.p, &h_cnt, 8, s);
 	bad = bad || dev_h2d(d_fr.p, fr.data(), n * sizeof(mc_frag_out), s) || dev_h2d(d_tk.p, tk.data(), n * sizeof(DpTask), s) || dev_h2d(d_aln.p, h_aln.data(), aln_bytes, s);
 	if (!bad)
 	{
 		PipeArgs a; memset(&a, 0, sizeof(a));
 		a.pr.alg_ksw2 = use_ksw2; a.st = c->d_stats.as<DevStats>(); a.frags = d_fr.as<mc_frag_out>(); a.tasks = d_tk.as<DpTask>(); a.aln = d_aln.as<uint8_t>(); a.dpws = d_ws.as<uint8_t>();
+		a.task_bump = d_cnt.as<mc_u64>(); a.task_cap = n; a.task_begin = 0;
 		launch_dp(a, n, s);
 		bad = dev_d2h(fr.data(), d_fr.p, n * sizeof(mc_frag_out), s) || dev_d2h(h_aln.data(), d_aln.p, aln_bytes, s) || dev_sync(s);
 	}
-	d_fr.release(); d_tk.release(); d_aln.release(); d_ws.release();
+	d_fr.release(); d_tk.release(); d_aln.release(); d_ws.release(); d_cnt.release();
 	if (bad) return MC_ERR_CUDA;
 	for (int64_t i = 0; i < n; i++)
 	{

@@ -60,7 +60,7 @@ struct DevIndex {
 	int64_t G, twoG;
 };
 
-struct Seed { uint64_t x0; int32_t read; int16_t rpos; int16_t len; };   // one recorded BWT_Search hit: SA interval [x0, x0+freq)
+struct Seed { uint64_t x0; int32_t read; int16_t rpos; int16_t len; };   // one recorded BWT_Search hit: rows [x0, x0+freq) of the seed's reverse complement
 struct SPair { int64_t gpos; int32_t rpos; int32_t len; };               // simple pair (exact-match seed placed on the genome)
 struct Cand { int32_t score; int32_t pbeg; int32_t pend; };              // cluster = slice of the read's sorted simple pairs
 struct DpTask { int32_t frag; int32_t m; int32_t n; int32_t pad; int64_t ws_off; };

@@ -4,8 +4,10 @@
 // A 64-byte block covers 128 BWT symbols: 4 x uint64 running counts (A,C,G,T before the block)
 // followed by 8 x uint32 words holding 16 symbols each, first symbol in the top bits.  One block is
 // two 32-byte sectors; a thread fetches it with four 128-bit read-only loads (LDG.E.128.CONSTANT).
-// Instead of the reference's byte-wise cnt_table the symbol counts come from three popcounts per
-// word (pair masks for C, G, T; A is what is left of the symbols scanned).
+// Instead of the reference's byte-wise cnt_table the count of ONE symbol up to a row comes from popcounts:
+// the words are XOR-ed with a per-symbol pattern that turns the wanted symbol into binary 11, (w>>1)&w marks
+// it on the even bits, a funnel-shift builds the prefix mask, and two words share one POPC (the marks of the
+// second word are moved to the odd bits).
 #ifndef MC_FMINDEX_H
 #define MC_FMINDEX_H
 
@@ -48,65 +50,8 @@ MC_HD void mc_load_block(const DevIndex& ix, uint64_t blk, OccBlock& b)
 	b.q0 = mc_ldg128(p); b.q1 = mc_ldg128(p + 4); b.q2 = mc_ldg128(p + 8); b.q3 = mc_ldg128(p + 12);
 }
 
-// occ(A,C,G,T) over symbols [0, k] of the $-less BWT, k already adjusted for primary, block already loaded
-MC_HD void mc_occ4_in_block(const OccBlock& b, uint64_t k, uint64_t out[4])
-{
-	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};
-	const int full = (int)((k & 127) >> 4);
-	const uint32_t part = ~((1u << ((~(uint32_t)k & 15) << 1)) - 1u);
-	int n1 = 0, n2 = 0, n3 = 0;
-#pragma unroll
-	for (int j = 0; j < 8; j++)
-	{
-		uint32_t m = j < full ? 0x55555555u : (j == full ? (part & 0x55555555u) : 0u);
-		uint32_t lo = w[j], hi = w[j] >> 1;
-		n1 += mc_popc(~hi & lo & m); n2 += mc_popc(hi & ~lo & m); n3 += mc_popc(hi & lo & m);
-	}
-	const int total = (int)(k & 127) + 1;
-	out[0] = ((uint64_t)b.q0.y << 32 | b.q0.x) + (uint64_t)(total - n1 - n2 - n3);
-	out[1] = ((uint64_t)b.q0.w << 32 | b.q0.z) + (uint64_t)n1;
-	out[2] = ((uint64_t)b.q1.y << 32 | b.q1.x) + (uint64_t)n2;
-	out[3] = ((uint64_t)b.q1.w << 32 | b.q1.z) + (uint64_t)n3;
-}
-
-// bwt_2occ4 (reference src/bwt_search.cpp:68-99).  *nblk += number of 64-byte blocks the reference touches.
-MC_HD void mc_occ4_pair(const DevIndex& ix, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4], uint32_t* nblk)
-{
-	const bool kn = (k == ~0ull), ln = (l == ~0ull);
-	uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
-	OccBlock b;
-	if (kn) { ck[0] = ck[1] = ck[2] = ck[3] = 0; }
-	else { mc_load_block(ix, kk >> 7, b); mc_occ4_in_block(b, kk, ck); (*nblk)++; }
-	if (ln) { cl[0] = cl[1] = cl[2] = cl[3] = 0; }
-	else
-	{
-		if (kn || (kk >> 7) != (ll >> 7)) { mc_load_block(ix, ll >> 7, b); (*nblk)++; }
-		mc_occ4_in_block(b, ll, cl);
-	}
-}
-
 // bwt_invPsi (reference src/bwt_search.cpp:101-107): one LF step = one block
-MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k)
-{
-	if (k == ix.primary) return 0;
-	const uint64_t x = k - (k > ix.primary);
-	OccBlock b; mc_load_block(ix, x >> 7, b);
-	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};
-	const int full = (int)((x & 127) >> 4);
-	const int c = (int)(w[full] >> ((~(uint32_t)x & 15) << 1)) & 3;
-	const uint32_t part = ~((1u << ((~(uint32_t)x & 15) << 1)) - 1u);
-	int n = 0;
-#pragma unroll
-	for (int j = 0; j < 8; j++)
-	{
-		uint32_t m = j < full ? 0x55555555u : (j == full ? (part & 0x55555555u) : 0u);
-		uint32_t lo = w[j], hi = w[j] >> 1;
-		n += mc_popc(((c & 2) ? hi : ~hi) & ((c & 1) ? lo : ~lo) & m);
-	}
-	const uint64_t base = c == 0 ? ((uint64_t)b.q0.y << 32 | b.q0.x) : c == 1 ? ((uint64_t)b.q0.w << 32 | b.q0.z)
-	                    : c == 2 ? ((uint64_t)b.q1.y << 32 | b.q1.x) : ((uint64_t)b.q1.w << 32 | b.q1.z);
-	return ix.L2[c] + base + (uint64_t)n;
-}
+MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k);
 
 // bwt_sa (reference src/bwt_search.cpp:109-119): walk LF until a sampled row
 MC_HD uint64_t mc_locate(const DevIndex& ix, uint64_t k, uint32_t* nblk)
@@ -117,27 +62,81 @@ MC_HD uint64_t mc_locate(const DevIndex& ix, uint64_t k, uint32_t* nblk)
 	return steps + mc_ldg(ix.sa + (k >> 5));
 }
 
-struct BiInterval { uint64_t x0, x1, x2; };
+// Search state.  The reference carries the bi-interval (x0 = rows of the pattern, x1 = rows of its reverse
+// complement, x2 = size; src/bwt_search.cpp:121-151).  Extending the pattern forward by base c is a plain backward
+// step on the x1 interval with symbol 3-c, and x0 only serves to enumerate the hits at the end.  The text is its own
+// reverse complement, so the hits can be enumerated from the x1 interval just as well (an occurrence of the reverse
+// complement at q is an occurrence of the pattern at 2G - q - len); the reference's later sort makes the order of
+// the hits immaterial (src/ReadMapping.cpp:152).  Dropping x0 removes half of the counting work per step.
+struct RcInterval { uint64_t x1, x2; };
 
 // first base of BWT_Search (reference src/bwt_search.cpp:128-131)
-MC_HD BiInterval mc_interval_init(const DevIndex& ix, int c)
+MC_HD RcInterval mc_interval_init(const DevIndex& ix, int c)
 {
-	BiInterval v; v.x0 = ix.L2[c] + 1; v.x1 = ix.L2[3 - c] + 1; v.x2 = ix.L2[c + 1] - ix.L2[c];
+	RcInterval v; v.x1 = ix.L2[3 - c] + 1; v.x2 = ix.L2[c + 1] - ix.L2[c];
 	return v;
 }
 
-// one forward extension by base code c (reference src/bwt_search.cpp:138-149); false = empty child
-MC_HD bool mc_interval_extend(const DevIndex& ix, BiInterval& v, int c, uint32_t* nblk)
+#ifdef MC_HOSTEMU
+static inline uint32_t mc_prefix_pairs(int bits) { return bits <= 0 ? 0u : bits >= 32 ? 0x55555555u : (uint32_t)((0x5555555500000000ull >> bits) & 0xFFFFFFFFu); }
+#else
+// even-bit mask of the top `bits`/2 symbols of a word: low half of 0x55555555:00000000 >> bits, shift clamped to 32
+static __device__ __forceinline__ uint32_t mc_prefix_pairs(int bits) { return __funnelshift_rc(0u, 0x55555555u, (uint32_t)max(bits, 0)); }
+#endif
+
+// number of symbols equal to the symbol encoded in `flip` among the first nbits/2 symbols of the block
+MC_HD int mc_count_in_block(const OccBlock& b, uint32_t flip, int nbits)
 {
-	uint64_t tk[4], tl[4];
-	mc_occ4_pair(ix, v.x1 - 1, v.x1 - 1 + v.x2, tk, tl, nblk);
+	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};
+	int n = 0;
+#pragma unroll
+	for (int j = 0; j < 8; j += 2)
+	{
+		const uint32_t a = w[j] ^ flip, c = w[j + 1] ^ flip;
+		const uint32_t e0 = (a >> 1) & a & mc_prefix_pairs(nbits - 32 * j);
+		const uint32_t e1 = (c >> 1) & c & mc_prefix_pairs(nbits - 32 * (j + 1));
+		n += mc_popc(e0 + (e1 << 1));     // marks of the second word ride on the odd bits: one POPC for two words
+	}
+	return n;
+}
+MC_HD uint32_t mc_flip_of(int i) { return ((i & 2) ? 0u : 0xAAAAAAAAu) | ((i & 1) ? 0u : 0x55555555u); }
+MC_HD uint64_t mc_block_base(const OccBlock& b, int i)
+{
+	const uint64_t cA = (uint64_t)b.q0.y << 32 | b.q0.x, cC = (uint64_t)b.q0.w << 32 | b.q0.z;
+	const uint64_t cG = (uint64_t)b.q1.y << 32 | b.q1.x, cT = (uint64_t)b.q1.w << 32 | b.q1.z;
+	return (i & 2) ? ((i & 1) ? cT : cG) : ((i & 1) ? cC : cA);
+}
+
+// One forward extension by base code c (reference src/bwt_search.cpp:138-149); false = empty child.
+// The two rows k, l fall into the same 128-row block in most steps (the reference's bwt_2occ4 fast path, :73);
+// the second block is only fetched when they do not, everything after the fetch is the same code for every lane.
+MC_HD bool mc_interval_extend(const DevIndex& ix, RcInterval& v, int c, uint32_t* nblk)
+{
 	const int i = 3 - c;
-	const uint64_t n2 = tl[i] - tk[i];
-	if (n2 == 0) return false;
-	uint64_t n0 = v.x0 + ((v.x1 <= ix.primary && v.x1 + v.x2 - 1 >= ix.primary) ? 1 : 0);
-	for (int j = 3; j > i; j--) n0 += tl[j] - tk[j];
-	v.x0 = n0; v.x1 = ix.L2[i] + 1 + tk[i]; v.x2 = n2;
+	const uint32_t flip = mc_flip_of(i);
+	const uint64_t k = v.x1 - 1, l = v.x1 - 1 + v.x2;                 // x1 >= 1, so k never is the (uint64)-1 row
+	const uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
+	OccBlock bk, bl;
+	mc_load_block(ix, kk >> 7, bk);
+	const bool same = (kk >> 7) == (ll >> 7);
+	bl = bk;
+	if (!same) mc_load_block(ix, ll >> 7, bl);
+	*nblk += same ? 1u : 2u;
+	const uint64_t occ_k = mc_block_base(bk, i) + (uint64_t)mc_count_in_block(bk, flip, 2 * ((int)(kk & 127) + 1));
+	const uint64_t occ_l = mc_block_base(bl, i) + (uint64_t)mc_count_in_block(bl, flip, 2 * ((int)(ll & 127) + 1));
+	if (occ_l == occ_k) return false;
+	v.x1 = ix.L2[i] + 1 + occ_k; v.x2 = occ_l - occ_k;
 	return true;
+}
+
+MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k)
+{
+	if (k == ix.primary) return 0;
+	const uint64_t x = k - (k > ix.primary);
+	OccBlock b; mc_load_block(ix, x >> 7, b);
+	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};
+	const int c = (int)(w[(x & 127) >> 4] >> ((~(uint32_t)x & 15) << 1)) & 3;
+	return ix.L2[c] + mc_block_base(b, c) + (uint64_t)mc_count_in_block(b, mc_flip_of(c), 2 * ((int)(x & 127) + 1));
 }
 
 #endif

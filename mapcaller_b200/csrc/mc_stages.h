@@ -114,28 +114,39 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
 	const int64_t so = a.seed_off[r];
 	const int cap = (int)(a.seed_off[r + 1] - so);
-	int ns = 0, pos = 0;
 	const int stop = rlen - MC_MIN_SEED;
+	int ns = 0, pos = 0, p = 0;
+	bool in_seed = false;
 	uint32_t nblk = 0;
-	while (pos < stop)
+	RcInterval v; v.x1 = v.x2 = 0;
+	// One loop, one extension step per trip: lanes of a warp stay in lock step whatever their seed boundaries are
+	// (the nested search-inside-scan loops of the reference serialise lanes whose seeds end at different offsets).
+	for (;;)
 	{
-		int c = mc_nt4(s[pos]);
-		if (c > 3) { pos++; continue; }
-		BiInterval v = mc_interval_init(a.ix, c);
-		int p = pos + 1;
-		for (; p < rlen; p++)
+		if (!in_seed)
 		{
-			int cc = mc_nt4(s[p]);
-			if (cc > 3) break;
-			if (!mc_interval_extend(a.ix, v, cc, &nblk)) break;
+			if (pos >= stop) break;
+			const int c = mc_nt4(s[pos]);
+			if (c > 3) { pos++; continue; }
+			v = mc_interval_init(a.ix, c); p = pos + 1; in_seed = true;
 		}
-		const int len = p - pos;
-		if (len >= MC_MIN_SEED && v.x2 <= MC_MAX_OCC && ns < cap)
+		bool end = p >= rlen;
+		if (!end)
 		{
-			Seed sd; sd.x0 = v.x0; sd.read = (int32_t)r; sd.rpos = (int16_t)pos; sd.len = (int16_t)len;
-			a.seeds[so + ns] = sd; a.slot_freq[so + ns] = (uint32_t)v.x2; ns++;
+			const int cc = mc_nt4(s[p]);
+			end = cc > 3 || !mc_interval_extend(a.ix, v, cc, &nblk);
+			if (!end) p++;
 		}
-		pos = p + 1;
+		if (end)
+		{
+			const int len = p - pos;
+			if (len >= MC_MIN_SEED && v.x2 <= MC_MAX_OCC && ns < cap)
+			{
+				Seed sd; sd.x0 = v.x1; sd.read = (int32_t)r; sd.rpos = (int16_t)pos; sd.len = (int16_t)len;
+				a.seeds[so + ns] = sd; a.slot_freq[so + ns] = (uint32_t)v.x2; ns++;
+			}
+			pos = p + 1; in_seed = false;
+		}
 	}
 	if (nblk) mc_atomic_add(&a.st->seed_blocks, (mc_u64)nblk);
 }
@@ -154,7 +165,9 @@ MC_HD void locate_body(int64_t t, const PipeArgs& a)
 	const int32_t s = a.loc_slot[t];
 	const Seed sd = a.seeds[s];
 	uint32_t nblk = 0;
-	const uint64_t g = mc_locate(a.ix, sd.x0 + (uint64_t)(t - a.slot_loc[s]), &nblk);
+	// the seed carries the rows of its reverse complement: an occurrence of that at q is the seed at 2G - q - len
+	const uint64_t q = mc_locate(a.ix, sd.x0 + (uint64_t)(t - a.slot_loc[s]), &nblk);
+	const uint64_t g = (uint64_t)a.ix.twoG - q - (uint64_t)sd.len;
 	SPair p; p.gpos = (int64_t)g; p.rpos = sd.rpos;
 	p.len = ((int64_t)g - (int64_t)sd.rpos > 0) ? sd.len : 0;   // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
 	a.pairs[t] = p;
