@@ -16,6 +16,7 @@
 #ifndef MAPCALLER_B200_H
 #define MAPCALLER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -138,6 +139,11 @@ typedef struct {
  * update, bit-identical to a single reference thread processing the same reads in order. */
 int mc_map_batch(mc_ctx *ctx, const mc_batch_in *in, mc_batch_out *out);
 
+/* Page-locked host memory for batch inputs: reads placed here are DMA-ed to the GPU directly, pageable memory is
+ * bounced through two pinned buffers (still correct, one extra host copy). */
+int mc_host_alloc(size_t bytes, void **out);
+void mc_host_free(void *p);
+
 /* Sequential state (reference globals iTotalReadNum, iTotalMappingNum, iTotalPairedNum,
  * TotalPairedDistance, ReadLengthSum, avgDist; src/ReadMapping.cpp:20-21) */
 typedef struct { int64_t total_reads, total_mapped, total_paired, total_distance, read_length_sum; uint32_t avg_dist; uint32_t pad; } mc_totals;
@@ -187,7 +193,8 @@ typedef struct {
     int64_t sa_reads;         /* 8-byte sampled-SA reads */
     int64_t dp_cells;         /* sum of m*n over the gapped fills */
     int64_t dp_tasks;
-    int64_t profile_columns;  /* MappingRecord_t columns touched by the pile-up update */
+    int64_t profile_columns;  /* MappingRecord_t columns the reference's pile-up update touches */
+    int64_t profile_atomics;  /* atomic updates the device profile actually needed for them */
     int64_t kernel_launches;
 } mc_stats;
 int mc_get_stats(const mc_ctx *ctx, mc_stats *out);   /* accumulated since create / last reset */

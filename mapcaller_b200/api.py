@@ -55,7 +55,7 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile",
                                            "ms_h2d", "ms_d2h", "ms_total")] + \
                [(k, C.c_int64) for k in ("seed_blocks", "locate_blocks", "sa_reads", "dp_cells", "dp_tasks",
-                                          "profile_columns", "kernel_launches")]
+                                          "profile_columns", "profile_atomics", "kernel_launches")]
 
 
 READ_DT = np.dtype([("score", "<i4"), ("sub_score", "<i4"), ("best_idx", "<i4"), ("cand_begin", "<i4"), ("n_cand", "<i4"), ("rlen", "<i4")])
@@ -95,6 +95,8 @@ def lib():
         L.mc_get_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
         L.mc_set_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
         L.mc_reset.argtypes = [C.c_void_p]
+        L.mc_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.mc_host_free.argtypes = [C.c_void_p]
         L.mc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.mc_reset_stats.argtypes = [C.c_void_p]
         L.mc_profile_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
@@ -118,6 +120,16 @@ def _view(ptr, count, dtype):
         return np.zeros(0, dtype=dtype)
     buf = (C.c_uint8 * (count * dtype.itemsize)).from_address(ptr)
     return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+def pinned_array(shape, dtype) -> np.ndarray:
+    """numpy array backed by page-locked memory from mc_host_alloc (kept alive for the life of the process)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _check(lib().mc_host_alloc(max(n, 1), C.byref(p)), "mc_host_alloc")
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Index:

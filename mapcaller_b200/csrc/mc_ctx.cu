@@ -103,7 +103,7 @@ enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_P
 struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key; mc_u64 pad; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
-struct Staged { DBuf seq, roff, seed_off; int64_t n_reads = 0, n_bytes = 0, n_slots = 0; std::vector<int64_t> h_roff; bool valid = false; };
+struct Staged { DBuf seq, roff, seed_off; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false; };
 
 struct mc_ctx {
 	mc_params prm;
@@ -113,7 +113,7 @@ struct mc_ctx {
 	DevIndex ix;
 	int64_t G;
 	// profile
-	DBuf d_cnt16, d_multi, d_rcount;
+	DBuf d_base16, d_sdiff, d_cdiff, d_mdiff, d_rcount, d_rflag;
 	DBuf d_bp, d_ind, d_ind_seq, d_pbump;
 	int64_t bp_cap = 0, ind_cap = 0, ind_seq_cap = 0;
 	// batch arenas
@@ -122,7 +122,11 @@ struct mc_ctx {
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
-	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo;
+	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap;
+	HBuf h_bounce[2];
+#ifndef MC_HOSTEMU
+	cudaEvent_t ev_bounce[2];
+#endif
 	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
 	HBuf h_in_seq, h_in_off, h_seed_off, h_small, h_chunk, h_chunk_lo, h_chunk_hi, h_pairs, h_reads, h_cands, h_frags, h_aln, h_misc;
@@ -153,18 +157,20 @@ void mc_params_default(mc_params* p)
 void mc_ctx_destroy(mc_ctx* c)
 {
 	if (!c) return;
-	DBuf* bufs[] = {&c->d_bwt, &c->d_sa, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_cnt16, &c->d_multi, &c->d_rcount, &c->d_bp, &c->d_ind,
+	DBuf* bufs[] = {&c->d_bwt, &c->d_sa, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_base16, &c->d_sdiff, &c->d_cdiff, &c->d_mdiff, &c->d_rcount, &c->d_rflag, &c->d_bp, &c->d_ind,
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap};
 	for (DBuf* b : bufs) b->release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
 	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc};
 	for (HBuf* b : hb) b->release();
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
+	c->h_bounce[0].release(); c->h_bounce[1].release();
 #ifndef MC_HOSTEMU
+	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 #endif
 	delete c;
@@ -191,6 +197,9 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	c->stream = 0;
 #endif
 	for (int i = 0; i < EV_COUNT; i++) ev_create(&c->ev[i]);
+#ifndef MC_HOSTEMU
+	cudaEventCreateWithFlags(&c->ev_bounce[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bounce[1], cudaEventDisableTiming);
+#endif
 	const int64_t G = v.genome_size; c->G = G;
 	std::vector<int64_t> ends; std::vector<int32_t> ids;
 	{
@@ -213,9 +222,10 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	bad |= c->d_chrom_id.reserve(ids.size() * 4) || dev_h2d(c->d_chrom_id.p, ids.data(), ids.size() * 4, c->stream);
 	if (params->update_profile)
 	{
-		bad |= c->d_cnt16.reserve((size_t)G * 16) || dev_zero(c->d_cnt16.p, (size_t)G * 16, c->stream);
-		bad |= c->d_multi.reserve((size_t)G * 4) || dev_zero(c->d_multi.p, (size_t)G * 4, c->stream);
-		bad |= c->d_rcount.reserve((size_t)G) || dev_zero(c->d_rcount.p, (size_t)G, c->stream);
+		bad |= c->d_base16.reserve((size_t)G * 8) || c->d_sdiff.reserve((size_t)(G + 1) * 16) || c->d_cdiff.reserve((size_t)(G + 1) * 4);
+		bad |= c->d_mdiff.reserve((size_t)(G + 1) * 4) || c->d_rcount.reserve((size_t)G);
+		bad |= dev_zero(c->d_base16.p, (size_t)G * 8, c->stream) || dev_zero(c->d_sdiff.p, (size_t)(G + 1) * 16, c->stream) || dev_zero(c->d_cdiff.p, (size_t)(G + 1) * 4, c->stream);
+		bad |= dev_zero(c->d_mdiff.p, (size_t)(G + 1) * 4, c->stream) || dev_zero(c->d_rcount.p, (size_t)G, c->stream);
 	}
 	bad |= c->d_pbump.reserve(sizeof(PersistBumps)) || dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream);
 	bad |= c->d_bumps.reserve(sizeof(Bumps)) || c->d_stats.reserve(sizeof(DevStats)) || dev_zero(c->d_stats.p, sizeof(DevStats), c->stream);
@@ -236,13 +246,22 @@ int mc_reset(mc_ctx* c)
 	int bad = 0;
 	if (c->prm.update_profile)
 	{
-		bad |= dev_zero(c->d_cnt16.p, (size_t)c->G * 16, c->stream) || dev_zero(c->d_multi.p, (size_t)c->G * 4, c->stream) || dev_zero(c->d_rcount.p, (size_t)c->G, c->stream);
+		const size_t G = (size_t)c->G;
+		bad |= dev_zero(c->d_base16.p, G * 8, c->stream) || dev_zero(c->d_sdiff.p, (G + 1) * 16, c->stream) || dev_zero(c->d_cdiff.p, (G + 1) * 4, c->stream);
+		bad |= dev_zero(c->d_mdiff.p, (G + 1) * 4, c->stream) || dev_zero(c->d_rcount.p, G, c->stream);
 	}
 	bad |= dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream) || dev_sync(c->stream);
 	memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = 1000;
 	c->inv_sites.clear(); c->tnl_sites.clear(); c->discord_gpos = c->discord_dist = 0;
 	return bad ? MC_ERR_CUDA : MC_OK;
 }
+
+int mc_host_alloc(size_t bytes, void** out)
+{
+	if (!out) { mc_set_error("mc_host_alloc: null argument"); return MC_ERR_ARG; }
+	return host_alloc(out, bytes) ? MC_ERR_CUDA : MC_OK;
+}
+void mc_host_free(void* p) { host_free(p); }
 
 int mc_get_totals(const mc_ctx* c, mc_totals* out) { if (!c || !out) return MC_ERR_ARG; *out = c->tot; return MC_OK; }
 int mc_set_totals(mc_ctx* c, const mc_totals* in) { if (!c || !in) return MC_ERR_ARG; c->tot = *in; return MC_OK; }
@@ -252,6 +271,51 @@ int mc_reset_stats(mc_ctx* c) { if (!c) return MC_ERR_ARG; zero_stats(&c->stats)
 } // extern "C"
 
 // ---- staging ------------------------------------------------------------------------------------------
+// Host -> device copy of caller memory.  Pinned / registered memory (e.g. from mc_host_alloc) is handed to the copy engine
+// directly; pageable memory is streamed through two pinned bounce buffers so that the host memcpy of one piece overlaps the
+// DMA of the previous one.
+static int upload(mc_ctx* c, void* dst, const void* src, size_t bytes)
+{
+	if (!bytes) return 0;
+#ifndef MC_HOSTEMU
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, src) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged))
+		return dev_h2d(dst, src, bytes, c->stream);
+	cudaGetLastError();
+	const size_t piece = 8u << 20;
+	if (c->h_bounce[0].reserve(piece) || c->h_bounce[1].reserve(piece)) return -1;
+	for (size_t off = 0, k = 0; off < bytes; off += piece, k++)
+	{
+		const size_t m = std::min(piece, bytes - off);
+		const int slot = (int)(k & 1);
+		// the slot may still be feeding an earlier copy (also one issued by a previous upload() call)
+		if (cuda_fail(cudaEventSynchronize(c->ev_bounce[slot]), "bounce buffer wait")) return -1;
+		memcpy(c->h_bounce[slot].p, (const uint8_t*)src + off, m);
+		if (dev_h2d((uint8_t*)dst + off, c->h_bounce[slot].p, m, c->stream)) return -1;
+		cudaEventRecord(c->ev_bounce[slot], c->stream);
+	}
+	return 0;
+#else
+	return dev_h2d(dst, src, bytes, c->stream);
+#endif
+}
+
+struct CapArgs { const int64_t* roff; uint32_t* cap; DevStats* st; };
+MC_HD void seedcap_body(int64_t r, const CapArgs& q)
+{
+	const int64_t len = q.roff[r + 1] - q.roff[r];
+	if (len < 0 || len > MC_MAX_RLEN) { mc_atomic_or(&q.st->overflow, (mc_u64)1 << 56); q.cap[r] = 1; return; }
+	q.cap[r] = (uint32_t)(len / 17 + 1);   // a recorded seed is >= 16 bases and the next search starts one base later
+}
+#ifdef MC_HOSTEMU
+static void launch_seedcap(const CapArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) seedcap_body(i, q); }
+#else
+__global__ void __launch_bounds__(MC_BLOCK) mc_seedcap_kernel(const CapArgs q, int64_t n)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) seedcap_body(i, q); }
+static void launch_seedcap(const CapArgs& q, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_seedcap_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(q, n); g_launches++; } }
+#endif
+
 static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st)
 {
 	const int64_t n = in->n_reads;
@@ -259,24 +323,17 @@ static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st)
 	if (c->prm.paired && (n & 1)) { mc_set_error("mc_map_batch: paired mode needs an even number of reads"); return MC_ERR_ARG; }
 	if (n >= (1ll << MC_KEY_SHIFT)) { mc_set_error("mc_map_batch: at most %lld reads per batch", (1ll << MC_KEY_SHIFT) - 1); return MC_ERR_ARG; }
 	const int64_t base = n ? in->seq_off[0] : 0, bytes = n ? in->seq_off[n] - base : 0;
-	st.h_roff.resize(n + 1);
-	if (c->h_seed_off.reserve((n + 1) * 8) || c->h_in_off.reserve((n + 1) * 8)) return MC_ERR_CUDA;
-	int64_t* so = c->h_seed_off.as<int64_t>(); int64_t* ro = c->h_in_off.as<int64_t>();
-	int64_t slots = 0;
-	for (int64_t i = 0; i < n; i++)
-	{
-		const int64_t len = in->seq_off[i + 1] - in->seq_off[i];
-		if (len < 0 || len > MC_MAX_RLEN) { mc_set_error("mc_map_batch: read %lld has length %lld (limit %d)", (long long)i, (long long)len, MC_MAX_RLEN); return MC_ERR_ARG; }
-		ro[i] = in->seq_off[i] - base; so[i] = slots; slots += len / 17 + 1;
-	}
-	ro[n] = bytes; so[n] = slots;
-	memcpy(st.h_roff.data(), ro, (n + 1) * 8);
-	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 1) * 8)) return MC_ERR_CUDA;
-	// pageable caller memory goes through the pinned staging buffer so the copy is asynchronous
-	if (c->h_in_seq.reserve(bytes)) return MC_ERR_CUDA;
-	if (bytes) memcpy(c->h_in_seq.p, in->seq + base, bytes);
-	if (dev_h2d(st.seq.p, c->h_in_seq.p, bytes, c->stream) || dev_h2d(st.roff.p, ro, (n + 1) * 8, c->stream) || dev_h2d(st.seed_off.p, so, (n + 1) * 8, c->stream)) return MC_ERR_CUDA;
-	st.n_reads = n; st.n_bytes = bytes; st.n_slots = slots; st.valid = true;
+	if (bytes < 0 || bytes > n * (int64_t)MC_MAX_RLEN) { mc_set_error("mc_map_batch: read offsets are not increasing or a read exceeds %d bases", MC_MAX_RLEN); return MC_ERR_ARG; }
+	st.n_reads = n; st.n_bytes = bytes; st.base = base; st.n_slots = bytes / 17 + n;   // upper bound of the seed slots
+	st.h_roff.clear();
+	if (c->prm.want_alignments) st.h_roff.assign(in->seq_off, in->seq_off + n + 1);
+	if (n == 0) { st.valid = true; return MC_OK; }
+	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 2) * 8) || c->d_cap.reserve(n * 4) || c->d_scan.reserve(device_scan_scratch_bytes(n))) return MC_ERR_CUDA;
+	if (upload(c, st.seq.p, in->seq + base, bytes) || upload(c, st.roff.p, in->seq_off, (n + 1) * 8)) return MC_ERR_CUDA;
+	CapArgs q; q.roff = st.roff.as<int64_t>(); q.cap = c->d_cap.as<uint32_t>(); q.st = c->d_stats.as<DevStats>();
+	launch_seedcap(q, n, c->stream);
+	device_scan_u32(q.cap, st.seed_off.as<int64_t>(), n, c->d_scan.as<int64_t>(), c->stream);
+	st.valid = true;
 	return MC_OK;
 }
 
@@ -295,14 +352,14 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	a.ix = c->ix;
 	a.pr.paired = c->prm.paired; a.pr.alg_ksw2 = c->prm.alg_ksw2; a.pr.max_pos_diff = c->prm.max_pos_diff; a.pr.max_clip = c->prm.max_clip;
 	a.pr.max_dup = c->prm.max_dup; a.pr.update_profile = c->prm.update_profile; a.pr.max_mismatch_rate = c->prm.max_mismatch_rate;
-	a.st = c->d_stats.as<DevStats>(); a.n_reads = n; a.seq = st.seq.as<uint8_t>(); a.roff = st.roff.as<int64_t>(); a.seed_off = st.seed_off.as<int64_t>();
+	a.st = c->d_stats.as<DevStats>(); a.n_reads = n; a.seq = st.seq.as<uint8_t>() - st.base; a.roff = st.roff.as<int64_t>(); a.seed_off = st.seed_off.as<int64_t>();
 	a.first_read = c->tot.total_reads;
 	a.n_slots = st.n_slots;
 
 	int bad = 0;
 	bad |= c->d_slot_freq.reserve(st.n_slots * 4) || c->d_seeds.reserve(st.n_slots * sizeof(Seed)) || c->d_slot_loc.reserve((st.n_slots + 1) * 8);
 	bad |= c->d_scan.reserve(device_scan_scratch_bytes(st.n_slots));
-	bad |= c->d_npair.reserve(n * 4) || c->d_ncand0.reserve(n * 4) || c->d_ncand.reserve(n * 4) || c->d_rsum.reserve(n * sizeof(ReadSum));
+	bad |= c->d_rflag.reserve(n + 1) || c->d_npair.reserve(n * 4) || c->d_ncand0.reserve(n * 4) || c->d_ncand.reserve(n * 4) || c->d_rsum.reserve(n * sizeof(ReadSum));
 	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(n_chunks * sizeof(mc_chunk_out));
 	bad |= c->d_chunk_lo.reserve(n_chunks * 4) || c->d_chunk_hi.reserve(n_chunks * 4);
 	bad |= c->d_pair_flag.reserve((n_pairs + 1) * 4) || c->d_est_lo.reserve((n_pairs + 1) * 4) || c->d_est_hi.reserve((n_pairs + 1) * 4);
@@ -310,7 +367,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	bad |= c->h_chunk.reserve(n_chunks * sizeof(mc_chunk_out)) || c->h_chunk_lo.reserve(n_chunks * 4) || c->h_chunk_hi.reserve(n_chunks * 4);
 	if (bad) return MC_ERR_CUDA;
 	a.slot_freq = c->d_slot_freq.as<uint32_t>(); a.seeds = c->d_seeds.as<Seed>(); a.slot_loc = c->d_slot_loc.as<int64_t>();
-	a.npair = c->d_npair.as<int32_t>(); a.ncand0 = c->d_ncand0.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
+	a.rflag = c->d_rflag.as<uint8_t>(); a.npair = c->d_npair.as<int32_t>(); a.ncand0 = c->d_ncand0.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
 	a.est = c->d_est.as<int32_t>(); a.active = c->d_active.as<uint8_t>(); a.chunk_out = c->d_chunk_out.as<mc_chunk_out>();
 	a.chunk_lo = c->d_chunk_lo.as<int32_t>(); a.chunk_hi = c->d_chunk_hi.as<int32_t>();
 	a.pair_flag = c->d_pair_flag.as<int32_t>(); a.est_lo = c->d_est_lo.as<int32_t>(); a.est_hi = c->d_est_hi.as<int32_t>();
@@ -318,11 +375,12 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	const int64_t rtask_cap = (n_pairs + 1) * 4;
 	Bumps* db = c->d_bumps.as<Bumps>();
 	a.pair_bump = &db->pair; a.frag_bump = &db->frag; a.aln_bump = &db->aln; a.task_bump = &db->task; a.dpws_bump = &db->dpws; a.rtask_bump = &db->rtask;
-	a.prof.cnt16 = c->d_cnt16.as<uint32_t>(); a.prof.multi = c->d_multi.as<uint32_t>(); a.prof.rcount = c->d_rcount.as<uint8_t>();
+	a.prof.base16 = c->d_base16.as<uint32_t>(); a.prof.sdiff = c->d_sdiff.as<int32_t>(); a.prof.cdiff = c->d_cdiff.as<int32_t>(); a.prof.mdiff = c->d_mdiff.as<int32_t>();
+	a.prof.rcount = c->d_rcount.as<uint8_t>();
 
 	// ---- seeding ----
 	ev_record(&c->ev[EV_H2D], s);
-	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats), s);
+	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats) - 2 * sizeof(mc_u64), s);   // keeps the staging flags (overflow, odd_merge)
 	if (prep_needed) launch_prep(a, n, s);
 	ev_record(&c->ev[EV_SEED0], s);
 	launch_seed(a, n, s);
@@ -430,6 +488,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			if ((ovf >> 16) & 0xFF) c->aln_factor *= 2;
 			if ((ovf >> 24) & 0xFF) c->task_factor *= 2;
 			if ((ovf >> 32) & 0xFF) c->dpws_factor *= 4;
+			if ((ovf >> 56) & 0xFF) { mc_set_error("mc_map_batch: a read is longer than %d bases (or the offsets decrease)", MC_MAX_RLEN); dev_zero(c->d_stats.p, sizeof(DevStats), s); return MC_ERR_ARG; }
 			if ((ovf >> 40) & 0xFF) { mc_set_error("mc_map_batch: internal error: candidate table overflow"); return MC_ERR_OVERFLOW; }
 			if (c->frag_factor > 4096 || c->aln_factor > 4096 || c->task_factor > 4096 || c->dpws_factor > 65536) { mc_set_error("mc_map_batch: arena overflow persists"); return MC_ERR_OVERFLOW; }
 			if (getenv("MC_DEBUG")) fprintf(stderr, "[mc] arena overflow %llx: now frag x%.0f aln x%.0f task x%.0f dpws x%.0f rescue %lld\n", (unsigned long long)ovf, c->frag_factor, c->aln_factor, c->task_factor, c->dpws_factor, (long long)c->rescue_cap);
@@ -474,7 +533,6 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		// ---- results back to the host ----
 		bad |= c->h_pairs.reserve((n_pairs + 1) * sizeof(mc_pair_out));
 		if (paired) bad |= dev_d2h(c->h_pairs.p, c->d_pair_out.p, n_pairs * sizeof(mc_pair_out), s);
-		int64_t n_cand_out = 0;
 		if (c->prm.want_alignments)
 		{
 			const size_t cb = (size_t)cand_total * 4;
@@ -496,20 +554,13 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		if (c->prm.want_alignments)
 		{
 			const ReadSum* rs = c->h_reads.as<ReadSum>(); const int32_t* nc = (const int32_t*)(c->h_reads.as<uint8_t>() + n * sizeof(ReadSum));
-			const size_t ct = (size_t)cand_total; const int32_t* hc = c->h_cands.as<int32_t>();
-			c->reads_out.resize(n); c->cands_out.clear();
+			c->reads_out.resize(n);
 			for (int64_t r = 0; r < n; r++)
 			{
-				// candidate slice of read r inside the device arena (same formula as pa_cand_off)
-				int64_t po0, co;
-				const int64_t* so = nullptr; (void)so;
 				mc_read_out ro; ro.score = rs[r].score; ro.sub_score = rs[r].sub_score; ro.best_idx = rs[r].best_idx; ro.n_cand = nc[r];
-				ro.rlen = (int32_t)(st.h_roff[r + 1] - st.h_roff[r]); ro.cand_begin = (int32_t)c->cands_out.size();
-				(void)po0; (void)co;
+				ro.rlen = (int32_t)(st.h_roff[r + 1] - st.h_roff[r]); ro.cand_begin = 0;
 				c->reads_out[r] = ro;
-				// filled below once the offsets are known
 			}
-			n_cand_out = (int64_t)ct; (void)hc;
 		}
 
 		// pair classification that the reference does in file order with thread-local state (src/ReadMapping.cpp:486-522)
@@ -553,7 +604,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		c->stats.ms_d2h += ev_ms(&c->ev[EV_PROF1], &c->ev[EV_D2H]);
 		c->stats.ms_total += ev_ms(&c->ev[EV_START], &c->ev[EV_D2H]);
 		c->stats.seed_blocks += hst->seed_blocks; c->stats.locate_blocks += hst->locate_blocks; c->stats.sa_reads += hst->sa_reads;
-		c->stats.dp_cells += hst->dp_cells; c->stats.dp_tasks += hst->dp_tasks; c->stats.profile_columns += hst->profile_columns;
+		c->stats.dp_cells += hst->dp_cells; c->stats.dp_tasks += hst->dp_tasks; c->stats.profile_columns += hst->profile_columns; c->stats.profile_atomics += hst->profile_atomics;
 		c->dstats_last = *hst;
 
 		out->n_reads = n; out->n_pairs = n_pairs; out->n_chunks = n_chunks;
@@ -564,12 +615,10 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			// rebuild the per-read candidate table from the device's structure-of-arrays
 			const size_t ct = (size_t)cand_total; const int32_t* hc = c->h_cands.as<int32_t>();
 			const int32_t *sc = hc, *pi = hc + ct, *ori = hc + 2 * ct, *fb = hc + 3 * ct, *nf = hc + 4 * ct;
-			// device candidate offsets need the per-read pair offsets: recompute them from slot_loc on the host side is not
-			// possible without another copy, so fetch the two small arrays that define them
-			std::vector<int64_t> slot_loc(st.n_slots + 1);
-			bad |= dev_d2h(slot_loc.data(), c->d_slot_loc.p, (st.n_slots + 1) * 8, s) || dev_sync(s);
+			// the candidate slice of a read is defined by its seed slots and their location offsets (pa_cand_off)
+			std::vector<int64_t> slot_loc(st.n_slots + 1), so(n + 1);
+			bad |= dev_d2h(slot_loc.data(), c->d_slot_loc.p, (st.n_slots + 1) * 8, s) || dev_d2h(so.data(), st.seed_off.p, (n + 1) * 8, s) || dev_sync(s);
 			if (bad) return MC_ERR_CUDA;
-			const int64_t* so = c->h_seed_off.as<int64_t>();
 			c->cands_out.clear();
 			for (int64_t r = 0; r < n; r++)
 			{
@@ -588,7 +637,6 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			out->reads = c->reads_out.data(); out->cands = c->cands_out.data(); out->n_cands = (int64_t)c->cands_out.size();
 			out->frags = c->h_frags.as<mc_frag_out>(); out->n_frags = (int64_t)hb.frag; out->aln = c->h_aln.as<uint8_t>(); out->n_aln_bytes = (int64_t)hb.aln;
 		}
-		(void)n_cand_out;
 		return MC_OK;
 	}
 }
@@ -614,7 +662,7 @@ int mc_stage_batch(mc_ctx* c, const mc_batch_in* in, int32_t slot)
 	if (rc) return rc;
 	// reverse-complement mate 2 once; the staged copy is then immutable
 	PipeArgs a; memset(&a, 0, sizeof(a));
-	a.pr.paired = c->prm.paired; a.seq = c->slots[slot].seq.as<uint8_t>(); a.roff = c->slots[slot].roff.as<int64_t>(); a.n_reads = in->n_reads;
+	a.pr.paired = c->prm.paired; a.seq = c->slots[slot].seq.as<uint8_t>() - c->slots[slot].base; a.roff = c->slots[slot].roff.as<int64_t>(); a.n_reads = in->n_reads;
 	launch_prep(a, in->n_reads, c->stream);
 	return dev_sync(c->stream) ? MC_ERR_CUDA : MC_OK;
 }
@@ -623,29 +671,35 @@ int mc_map_staged(mc_ctx* c, int32_t slot, mc_batch_out* out)
 {
 	if (!c || !out || slot < 0 || slot >= 4 || !c->slots[slot].valid) { mc_set_error("mc_map_staged: slot not staged"); return MC_ERR_ARG; }
 	ev_record(&c->ev[EV_START], c->stream);
-	// stage_reads left this slot's seed offsets in the shared pinned buffer only transiently: rebuild them
-	Staged& st = c->slots[slot];
-	if (c->h_seed_off.reserve((st.n_reads + 1) * 8)) return MC_ERR_CUDA;
-	int64_t* so = c->h_seed_off.as<int64_t>(); int64_t slots = 0;
-	for (int64_t i = 0; i < st.n_reads; i++) { so[i] = slots; slots += (st.h_roff[i + 1] - st.h_roff[i]) / 17 + 1; }
-	so[st.n_reads] = slots;
-	return run_batch(c, st, out, false);
+	return run_batch(c, c->slots[slot], out, false);
 }
 
 int mc_profile_read(mc_ctx* c, int64_t beg, int64_t end, void* outp)
 {
 	if (!c || !outp || beg < 0 || end > c->G || beg > end) { mc_set_error("mc_profile_read: bad range"); return MC_ERR_ARG; }
 	if (!c->prm.update_profile) { mc_set_error("mc_profile_read: context was created without update_profile"); return MC_ERR_ARG; }
-	DevProfile p; p.cnt16 = c->d_cnt16.as<uint32_t>(); p.multi = c->d_multi.as<uint32_t>(); p.rcount = c->d_rcount.as<uint8_t>();
-	const int64_t tile = 1 << 24;
-	if (c->d_sort.reserve((size_t)tile * 16)) return MC_ERR_CUDA;
-	for (int64_t b = beg; b < end; b += tile)
+	if (beg == end) return MC_OK;
+	DevProfile p; p.base16 = c->d_base16.as<uint32_t>(); p.sdiff = c->d_sdiff.as<int32_t>(); p.cdiff = c->d_cdiff.as<int32_t>(); p.mdiff = c->d_mdiff.as<int32_t>();
+	p.rcount = c->d_rcount.as<uint8_t>();
+	// the range counters are difference arrays: block totals, exclusive scan over the blocks, then every block sums its own columns
+	const int64_t nb = (c->G + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK;
+	DBuf d_sums;
+	if (d_sums.reserve((size_t)(6 * nb + 8) * 8)) return MC_ERR_CUDA;
+	int64_t* sums = d_sums.as<int64_t>();
+	launch_profsum(p, c->G, nb, sums, c->stream);
+	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, c->stream);
+	const int64_t tile_blocks = (1 << 24) / MC_PROF_BLOCK;
+	int rc = MC_OK;
+	if (c->d_sort.reserve((size_t)(tile_blocks * MC_PROF_BLOCK) * 16)) rc = MC_ERR_CUDA;
+	for (int64_t b0 = beg / MC_PROF_BLOCK; rc == MC_OK && b0 * MC_PROF_BLOCK < end; b0 += tile_blocks)
 	{
-		const int64_t m = std::min(tile, end - b);
-		launch_profpack(p, b, m, c->d_sort.as<uint64_t>(), c->stream);
-		if (dev_d2h((uint8_t*)outp + (b - beg) * 16, c->d_sort.p, (size_t)m * 16, c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
+		const int64_t b1 = std::min(nb, b0 + tile_blocks);
+		const int64_t tb = std::max(beg, b0 * MC_PROF_BLOCK), te = std::min(end, b1 * MC_PROF_BLOCK);
+		launch_profpack(c->ix, p, nb, sums, b0, b1, tb, te, c->d_sort.as<uint64_t>(), c->stream);
+		if (dev_d2h((uint8_t*)outp + (tb - beg) * 16, c->d_sort.p, (size_t)(te - tb) * 16, c->stream) || dev_sync(c->stream)) rc = MC_ERR_CUDA;
 	}
-	return MC_OK;
+	d_sums.release();
+	return rc;
 }
 
 int mc_profile_indels(mc_ctx* c, const mc_indel_rec** recs, int64_t* n_recs, const uint8_t** seq_arena)

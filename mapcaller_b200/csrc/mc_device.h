@@ -48,6 +48,19 @@ static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vi
 
 typedef unsigned long long mc_u64; // atomicAdd-compatible 64-bit counter
 
+// Statistics counters are hit by every thread of a kernel: summing inside the warp first leaves one atomic per warp
+// instead of 32 same-address atomics (which serialise in the L2 atomic unit).
+#ifdef MC_HOSTEMU
+static inline void mc_stat_add(mc_u64* p, uint32_t v) { *p += v; }
+#else
+static __device__ __forceinline__ void mc_stat_add(mc_u64* p, uint32_t v)
+{
+	const unsigned m = __activemask();
+	const unsigned sum = __reduce_add_sync(m, v);
+	if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1) && sum) atomicAdd(p, (mc_u64)sum);
+}
+#endif
+
 // ---- FM-index replica in HBM (layout of the reference's bwt_t, unchanged) ------------------------
 struct DevIndex {
 	const uint32_t* bwt;   // 64-byte blocks: 4 x uint64 occ counts + 8 x uint32 packed symbols
@@ -66,7 +79,7 @@ struct Cand { int32_t score; int32_t pbeg; int32_t pend; };              // clus
 struct DpTask { int32_t frag; int32_t m; int32_t n; int32_t pad; int64_t ws_off; };
 
 struct DevStats {
-	mc_u64 seed_blocks, locate_blocks, sa_reads, dp_cells, dp_tasks, profile_columns;
+	mc_u64 seed_blocks, locate_blocks, sa_reads, dp_cells, dp_tasks, profile_columns, profile_atomics;
 	mc_u64 overflow;      // any arena ran out: the batch is re-run with larger arenas
 	mc_u64 odd_merge;     // defensive counter: IdentifyNormalPairs ordering assumption violated
 };
@@ -76,11 +89,18 @@ struct DevParams {
 	float max_mismatch_rate;
 };
 
-// device-resident pile-up profile (DESIGN.md "data layout")
+// device-resident pile-up profile (DESIGN.md "data layout").  Everything a read adds over a RANGE of columns
+// (strand coverage, multi-hit coverage, exact-match seeds that by construction carry the reference base) is kept as
+// a difference array (+1 at the first column, -1 one past the last) and only summed up when the profile is read
+// out; per-column counters exist only for bases that may differ from the reference.
 struct DevProfile {
-	uint32_t* cnt16;   // [G][4] words = 8 x uint16: A,C | G,T | F1,R2 | F2,R1
-	uint32_t* multi;   // [G] multi_hit (clamped to 4095 when packed)
+	uint32_t* base16;  // [G][2] words = 4 x uint16: A,C | G,T  (bases of gapped / mismatching pieces)
+	int32_t* sdiff;    // [G+1][4] difference arrays of F1, R2, F2, R1
+	int32_t* cdiff;    // [G+1] difference array: reads whose exact-match seed covers the column (counts the reference base)
+	int32_t* mdiff;    // [G+1] difference array of multi_hit
 	uint8_t* rcount;   // [G] readCount gate (<= iMaxDuplicate)
 };
+
+#define MC_PROF_BLOCK 1024   // columns per read-out block
 
 #endif

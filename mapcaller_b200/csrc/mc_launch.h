@@ -13,9 +13,12 @@ typedef int mc_stream_t;
 	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a); }
 #define MC_LAUNCH2(name) \
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
-static void launch_scatter(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) scatter_body(i, 0, 1, a, q); }
 static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a); }
-static void launch_profpack(const DevProfile& p, int64_t beg, int64_t n, uint64_t* out, mc_stream_t) { for (int64_t i = 0; i < n; i++) profpack_body(i, p, beg, out); }
+static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
+static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, p, G, nb, sums); }
+static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
+{ for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
+static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
 #else
 typedef cudaStream_t mc_stream_t;
@@ -31,14 +34,15 @@ static int64_t g_launches = 0;
 	{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) name##_body(i, a, q); } \
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t s) \
 	{ if (n > 0) { mc_##name##_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n); g_launches++; } }
-// one warp per read: lanes stride over consecutive profile columns
-__global__ void __launch_bounds__(MC_BLOCK) mc_scatter_kernel(const PipeArgs a, const ProfArgs q, int64_t n)
+// persistent lanes: a fixed grid, every thread takes locations tid, tid + nthreads, ...
+__global__ void __launch_bounds__(MC_BLOCK) mc_locate_kernel(const PipeArgs a)
+{ locate_body(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, a); }
+static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t s)
 {
-	int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-	if (w < n) scatter_body(w, threadIdx.x & 31, 32, a, q);
+	if (n <= 0) return;
+	int64_t blocks = (n + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;   // 8 resident 256-thread blocks per SM
+	mc_locate_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
-static void launch_scatter(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t s)
-{ if (n > 0) { mc_scatter_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n); g_launches++; } }
 // one warp per rescue task
 __global__ void __launch_bounds__(MC_BLOCK) mc_rescue_kernel(const PipeArgs a, int64_t n)
 {
@@ -47,27 +51,35 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_rescue_kernel(const PipeArgs a, i
 }
 static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t s)
 { if (n > 0) { mc_rescue_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
-__global__ void __launch_bounds__(MC_BLOCK) mc_profpack_kernel(const DevProfile p, int64_t beg, int64_t n, uint64_t* out)
-{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) profpack_body(i, p, beg, out); }
-static void launch_profpack(const DevProfile& p, int64_t beg, int64_t n, uint64_t* out, mc_stream_t s)
-{ if (n > 0) { mc_profpack_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(p, beg, n, out); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t* sums)
+{ int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < nb) profsum_body(b, p, G, nb, sums); }
+static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t s)
+{ if (nb > 0) { mc_profsum_kernel<<<(unsigned)((nb + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(p, G, nb, sums); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_profpack_kernel(const DevIndex ix, const DevProfile p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out)
+{ int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < b1) profpack_body(b, ix, p, nb, pre, beg, end, out); }
+static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t s)
+{ if (b1 > b0) { mc_profpack_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, p, nb, pre, b0, b1, beg, end, out); g_launches++; } }
 #endif
 
 MC_LAUNCH1(prep)
 MC_LAUNCH1(seed)
 MC_LAUNCH1(expand)
-MC_LAUNCH1(locate)
 MC_LAUNCH1(cluster)
 MC_LAUNCH1(single)
 MC_LAUNCH1(pair)
 MC_LAUNCH1(alnprep)
+#ifdef MC_HOSTEMU
 MC_LAUNCH1(dp)
+#else
+#include "mc_dp_warp.cuh"
+#endif
 MC_LAUNCH1(alnfin)
 MC_LAUNCH1(pairstat)
 MC_LAUNCH1(chunkstat)
 MC_LAUNCH2(profkey)
 MC_LAUNCH2(gate)
 MC_LAUNCH2(gateupd)
+MC_LAUNCH2(scatter)
 
 // ---- exclusive scan uint32 -> int64 (out has n + 1 entries) -----------------------------------------
 #ifdef MC_HOSTEMU
@@ -141,6 +153,7 @@ static void device_scan_u32(const uint32_t* in, int64_t* out, int64_t n, int64_t
 	mc_scan_tiles<<<1, 1024, 0, s>>>(scratch, nt, out + n); g_launches++;
 	if (nt > 0) { mc_scan_finish<<<(unsigned)nt, 256, 0, s>>>(in, n, scratch, out); g_launches++; }
 }
+static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t s) { mc_scan_tiles<<<1, 1024, 0, s>>>(a, n, total); g_launches++; }
 #include <cub/device/device_radix_sort.cuh>
 static size_t device_sort_scratch_bytes(int64_t n)
 {

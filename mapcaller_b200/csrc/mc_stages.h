@@ -40,6 +40,7 @@ struct PipeArgs {
 	// simple pairs: [pair_off(r), ...) with pair_off(r) = slot_loc[seed_off[r]]; rescue seeds appended after n_locs
 	SPair* pairs;
 	int32_t* npair;          // per read: valid simple pairs after filtering/sorting
+	uint8_t* rflag;          // per read: bit0 = a base walked by the seeding is lower case (profile counts upper case only)
 	int64_t pair_cap;        // arena capacity (n_locs + rescue region)
 	mc_u64* pair_bump;       // next free rescue pair
 	// candidates: read r owns [cand_off(r), cand_off(r) + cand_cap(r))
@@ -116,6 +117,7 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 	const int cap = (int)(a.seed_off[r + 1] - so);
 	const int stop = rlen - MC_MIN_SEED;
 	int ns = 0, pos = 0, p = 0;
+	uint32_t lower = 0;
 	bool in_seed = false;
 	uint32_t nblk = 0;
 	RcInterval v; v.x1 = v.x2 = 0;
@@ -126,16 +128,19 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 		if (!in_seed)
 		{
 			if (pos >= stop) break;
-			const int c = mc_nt4(s[pos]);
+			const uint8_t ch = s[pos];
+			const int c = mc_nt4(ch);
 			if (c > 3) { pos++; continue; }
+			lower |= ch;
 			v = mc_interval_init(a.ix, c); p = pos + 1; in_seed = true;
 		}
 		bool end = p >= rlen;
 		if (!end)
 		{
-			const int cc = mc_nt4(s[p]);
+			const uint8_t ch = s[p];
+			const int cc = mc_nt4(ch);
 			end = cc > 3 || !mc_interval_extend(a.ix, v, cc, &nblk);
-			if (!end) p++;
+			if (!end) { p++; lower |= ch; }
 		}
 		if (end)
 		{
@@ -148,7 +153,8 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 			pos = p + 1; in_seed = false;
 		}
 	}
-	if (nblk) mc_atomic_add(&a.st->seed_blocks, (mc_u64)nblk);
+	a.rflag[r] = (uint8_t)((lower >> 5) & 1);
+	if (nblk) mc_stat_add(&a.st->seed_blocks, (uint32_t)(nblk));
 }
 
 // one thread per slot writes its slot id over its locations
@@ -159,20 +165,37 @@ MC_HD void expand_body(int64_t s, const PipeArgs& a)
 	for (uint32_t i = 0; i < f; i++) a.loc_slot[o + i] = (int32_t)s;
 }
 
-// one thread per location: LF walk to a sampled SA row
-MC_HD void locate_body(int64_t t, const PipeArgs& a)
+// Locations: every lane walks LF steps (bwt_sa, src/bwt_search.cpp:109-119) and, the moment its row is a sampled one,
+// finishes that location and picks up its next one (locations tid, tid + nthreads, ...), so the lanes of a warp keep
+// stepping together although the walks have very different lengths (0..31+ steps).
+MC_HD void locate_body(int64_t tid, int64_t nthreads, const PipeArgs& a)
 {
-	const int32_t s = a.loc_slot[t];
-	const Seed sd = a.seeds[s];
-	uint32_t nblk = 0;
-	// the seed carries the rows of its reverse complement: an occurrence of that at q is the seed at 2G - q - len
-	const uint64_t q = mc_locate(a.ix, sd.x0 + (uint64_t)(t - a.slot_loc[s]), &nblk);
-	const uint64_t g = (uint64_t)a.ix.twoG - q - (uint64_t)sd.len;
-	SPair p; p.gpos = (int64_t)g; p.rpos = sd.rpos;
-	p.len = ((int64_t)g - (int64_t)sd.rpos > 0) ? sd.len : 0;   // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
-	a.pairs[t] = p;
-	mc_atomic_add(&a.st->locate_blocks, (mc_u64)nblk);
-	mc_atomic_add(&a.st->sa_reads, (mc_u64)1);
+	int64_t t = tid;
+	if (t >= a.n_locs) return;
+	uint32_t nblk = 0, nsa = 0;
+	int32_t s = a.loc_slot[t];
+	Seed sd = a.seeds[s];
+	uint64_t k = sd.x0 + (uint64_t)(t - a.slot_loc[s]), steps = 0;
+	bool live = true;
+	while (live)
+	{
+		if ((k & 31) == 0)
+		{
+			// the seed carries the rows of its reverse complement: an occurrence of that at q is the seed at 2G - q - len
+			const uint64_t q = steps + mc_ldg(a.ix.sa + (k >> 5));
+			const uint64_t g = (uint64_t)a.ix.twoG - q - (uint64_t)sd.len;
+			SPair p; p.gpos = (int64_t)g; p.rpos = sd.rpos;
+			p.len = ((int64_t)g - (int64_t)sd.rpos > 0) ? sd.len : 0;   // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
+			a.pairs[t] = p;
+			nsa++;
+			t += nthreads;
+			live = t < a.n_locs;
+			if (live) { s = a.loc_slot[t]; sd = a.seeds[s]; k = sd.x0 + (uint64_t)(t - a.slot_loc[s]); steps = 0; }
+		}
+		if (live && (k & 31)) { k = mc_lf_step(a.ix, k); steps++; nblk++; }
+	}
+	mc_stat_add(&a.st->locate_blocks, (uint32_t)(nblk));
+	mc_stat_add(&a.st->sa_reads, (uint32_t)(nsa));
 }
 
 // ------------------------------------------------------------------------------------------------

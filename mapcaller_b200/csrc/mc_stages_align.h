@@ -7,12 +7,16 @@ MC_HD bool frag_less_readpos(const mc_frag_out& x, const mc_frag_out& y)
 	return x.rPos == y.rPos ? x.gPos < y.gPos : x.rPos < y.rPos; // CompByReadPos, reference src/ReadAlignment.cpp:23
 }
 
-// workspace bytes of one fill: traceback matrix + two int rows
-MC_HOST_HD int64_t dp_ws_bytes(int m, int n)
+// workspace of one fill: traceback bytes (row-major for the per-thread form, anti-diagonal-major strips of 32 columns
+// for the warp form, whichever is larger and for either algorithm) followed by two int rows
+MC_HOST_HD int64_t dp_tb_bytes(int m, int n)
 {
-	const int64_t tb = (((int64_t)(m + 1) * (n + 1)) + 7) & ~7ll;
-	return tb + 8 * (int64_t)((m > n ? m : n) + 2);
+	const int64_t full = (int64_t)(m + 1) * (n + 1);
+	const int64_t w_nw = (int64_t)((n + 31) >> 5) * (m + 32) * 32, w_ksw = (int64_t)((m + 31) >> 5) * (n + 32) * 32;
+	int64_t t = full > w_nw ? full : w_nw; if (w_ksw > t) t = w_ksw;
+	return (t + 7) & ~7ll;
 }
+MC_HOST_HD int64_t dp_ws_bytes(int m, int n) { return dp_tb_bytes(m, n) + 8 * (int64_t)((m > n ? m : n) + 2); }
 
 // ------------------------------------------------------------------------------------------------
 // alnprep: one thread per read.  For every live candidate: order the seeds along the read, resolve
@@ -183,7 +187,7 @@ MC_HD void dp_body(int64_t t, const PipeArgs& a)
 	const int m = tk.m, n = tk.n, cp = x.aln_cap;
 	uint8_t* s1 = a.aln + x.aln_off; uint8_t* s2 = s1 + cp;   // read piece (m), genome piece (n)
 	uint8_t* tb = a.dpws + tk.ws_off;
-	int* row0 = (int*)(tb + ((((int64_t)(m + 1) * (n + 1)) + 7) & ~7ll));
+	int* row0 = (int*)(tb + dp_tb_bytes(m, n));
 	int* row1 = row0 + ((m > n ? m : n) + 2);
 	int len = 0;
 	if (!a.pr.alg_ksw2)

@@ -79,10 +79,19 @@ MC_HD void gateupd_body(int64_t i, const PipeArgs& a, const ProfArgs& q)
 	a.prof.rcount[s] = (uint8_t)(prior + n);
 }
 
-MC_HD void prof_add16(const PipeArgs& a, int64_t g, int field) // field: 0 A,1 C,2 G,3 T,4 F1,5 R2,6 F2,7 R1
+MC_HD void prof_base(const PipeArgs& a, int64_t g, int field) // field: 0 A, 1 C, 2 G, 3 T
 {
 	if (g < 0 || g >= a.ix.G) return;
-	mc_atomic_add(a.prof.cnt16 + g * 4 + (field >> 1), (uint32_t)(1u << ((field & 1) << 4)));
+	mc_atomic_add(a.prof.base16 + g * 2 + (field >> 1), (uint32_t)(1u << ((field & 1) << 4)));
+}
+// +1 on every column of [g0, g1) of a difference array with `stride` interleaved lanes
+MC_HD void prof_range(const PipeArgs& a, int32_t* diff, int stride, int lane, int64_t g0, int64_t g1)
+{
+	if (g0 < 0) g0 = 0;
+	if (g1 > a.ix.G) g1 = a.ix.G;
+	if (g0 >= g1) return;
+	mc_atomic_add(diff + g0 * stride + lane, 1);
+	mc_atomic_add(diff + g1 * stride + lane, -1);
 }
 MC_HD int base_field(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 
@@ -96,9 +105,9 @@ MC_HD void indel_emit(const PipeArgs& a, const ProfArgs& q, int kind, int64_t po
 	for (int i = 0; i < len; i++) q.ind_seq[o + i] = s[i];
 }
 
-// `nl` lanes cooperate on one read (a warp on the GPU); lane-strided loops give coalesced atomics over
-// consecutive profile columns
-MC_HD void scatter_body(int64_t r, int lane, int nl, const PipeArgs& a, const ProfArgs& q)
+// one thread per read.  An accepted read costs two atomics for its strand coverage, two per exact-match seed and one
+// per base of its gapped / mismatching pieces.
+MC_HD void scatter_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 {
 	const int mode = q.accept[r];
 	if (mode == 0) return;
@@ -116,8 +125,8 @@ MC_HD void scatter_body(int64_t r, int lane, int nl, const PipeArgs& a, const Pr
 			int64_t g0, g1;
 			if (a.corient[co + ci]) { g0 = f[0].gPos; g1 = f[nf - 1].gPos + f[nf - 1].gLen; }
 			else { g0 = a.ix.twoG - (f[0].gPos + f[0].gLen); g1 = a.ix.twoG - f[nf - 1].gPos; }
-			for (int64_t g = g0 + lane; g < g1; g += nl) if (g >= 0 && g < a.ix.G) mc_atomic_add(a.prof.multi + g, 1u);
-			if (lane == 0 && g1 > g0) mc_atomic_add(&a.st->profile_columns, (mc_u64)(g1 - g0));
+			prof_range(a, a.prof.mdiff, 1, 0, g0, g1);
+			if (g1 > g0) mc_stat_add(&a.st->profile_columns, (uint32_t)(g1 - g0));
 		}
 		return;
 	}
@@ -127,19 +136,35 @@ MC_HD void scatter_body(int64_t r, int lane, int nl, const PipeArgs& a, const Pr
 	const bool fwd = a.corient[co + ci] != 0;
 	const bool first_mate = a.pr.paired ? (((a.first_read + r) & 1) == 0) : true;
 	const int64_t start = fwd ? f[0].gPos : a.ix.twoG - (f[0].gPos + f[0].gLen);
-	const int sfield = first_mate ? (fwd ? 4 : 7) : (fwd ? 5 : 6);   // F1 / R1 / R2 / F2
-	for (int i = lane; i < rlen; i += nl) prof_add16(a, start + i, sfield);
-	if (lane == 0) mc_atomic_add(&a.st->profile_columns, (mc_u64)(2 * rlen));
+	const int sfield = first_mate ? (fwd ? 0 : 3) : (fwd ? 1 : 2);   // F1 / R1 / R2 / F2 inside [F1,R2,F2,R1]
+	prof_range(a, a.prof.sdiff, 4, sfield, start, start + rlen);
+	// seeds found by the FM index match the reference exactly, so they add the reference base over their span; seeds of a
+	// rescued candidate may carry shifted labels (src/KmerAnalysis.cpp quirk) and lower-case bases are not counted by
+	// the reference at all: both go base by base
+	const bool exact = a.cands[co + ci].pbeg < a.n_locs && !(a.rflag[r] & 1);
+	int natom = 2;
 	for (int k = 0; k < nf; k++)
 	{
 		const mc_frag_out x = f[k];
 		if (x.bSimple)
 		{
-			if (fwd) { for (int j = lane; j < x.rLen; j += nl) { int b = base_field(rs[x.rPos + j]); if (b >= 0) prof_add16(a, x.gPos + j, b); } }
-			else { for (int j = lane; j < x.rLen; j += nl) { int b = base_field(rs[x.rPos + j]); if (b >= 0) prof_add16(a, a.ix.twoG - 1 - x.gPos - j, 3 - b); } }
+			if (exact)
+			{
+				if (fwd) prof_range(a, a.prof.cdiff, 1, 0, x.gPos, x.gPos + x.rLen);
+				else prof_range(a, a.prof.cdiff, 1, 0, a.ix.twoG - x.gPos - x.rLen, a.ix.twoG - x.gPos);
+				natom += 2;
+			}
+			else
+			{
+				for (int j = 0; j < x.rLen; j++)
+				{
+					const int b = base_field(rs[x.rPos + j]);
+					if (b >= 0) { if (fwd) prof_base(a, x.gPos + j, b); else prof_base(a, a.ix.twoG - 1 - x.gPos - j, 3 - b); }
+				}
+				natom += x.rLen;
+			}
 			continue;
 		}
-		if (lane != 0) continue; // gapped / indel pieces are short: one lane walks the columns
 		const uint8_t* a1 = a.aln + x.aln_off; const uint8_t* a2 = a1 + x.aln_cap;
 		// note: an emptied clip piece (rLen == gLen == 0) also lands here and registers an empty insertion string, as the reference does (:121)
 		if (x.gLen == 0) { indel_emit(a, q, 0, (fwd ? x.gPos : a.ix.twoG - x.gPos) - 1, a1, x.aln_len); continue; }
@@ -157,20 +182,48 @@ MC_HD void scatter_body(int64_t r, int lane, int nl, const PipeArgs& a, const Pr
 				int e = 1; while (j + e < x.aln_len && a1[j + e] == '-') e++;
 				indel_emit(a, q, 1, g - 1, a2 + j, e); j += e; g += e;
 			}
-			else { int b = base_field(a1[j]); if (b >= 0) prof_add16(a, g, b); j++; g++; }
+			else { int b = base_field(a1[j]); if (b >= 0) { prof_base(a, g, b); natom++; } j++; g++; }
 		}
 	}
+	mc_stat_add(&a.st->profile_columns, (uint32_t)(2 * rlen));
+	mc_stat_add(&a.st->profile_atomics, (uint32_t)(natom));
 }
 
-// MappingRecord_t image of one column (reference src/structure.h:152-163)
-MC_HD void profpack_body(int64_t i, const DevProfile& p, int64_t beg, uint64_t* out)
+// ---- read-out: difference arrays -> MappingRecord_t ------------------------------------------------------------
+// per MC_PROF_BLOCK columns: totals of the six difference arrays (sums[6][n_blocks], scanned afterwards)
+MC_HD void profsum_body(int64_t b, const DevProfile& p, int64_t G, int64_t n_blocks, int64_t* sums)
 {
-	const int64_t g = beg + i;
-	const uint32_t w0 = p.cnt16[g * 4], w1 = p.cnt16[g * 4 + 1], w2 = p.cnt16[g * 4 + 2], w3 = p.cnt16[g * 4 + 3];
-	uint64_t A = w0 & 0xFFFF, C = w0 >> 16, G_ = w1 & 0xFFFF, T = w1 >> 16, M = p.multi[g], R = p.rcount[g];
-	if (A > 4095) A = 4095; if (C > 4095) C = 4095; if (G_ > 4095) G_ = 4095; if (T > 4095) T = 4095; if (M > 4095) M = 4095;
-	out[2 * i] = A | C << 12 | G_ << 24 | T << 36 | M << 48 | (R & 15) << 60;
-	out[2 * i + 1] = (uint64_t)w2 | (uint64_t)w3 << 32;
+	const int64_t g0 = b * MC_PROF_BLOCK; int64_t g1 = g0 + MC_PROF_BLOCK; if (g1 > G) g1 = G;
+	int64_t t[6] = {0, 0, 0, 0, 0, 0};
+	for (int64_t g = g0; g < g1; g++)
+	{
+		t[0] += p.sdiff[g * 4]; t[1] += p.sdiff[g * 4 + 1]; t[2] += p.sdiff[g * 4 + 2]; t[3] += p.sdiff[g * 4 + 3];
+		t[4] += p.cdiff[g]; t[5] += p.mdiff[g];
+	}
+	for (int k = 0; k < 6; k++) sums[k * n_blocks + b] = t[k];
+}
+
+// MappingRecord_t image (reference src/structure.h:152-163) of the columns of block b that fall into [beg, end);
+// pre[6][n_blocks] holds the exclusive block prefixes
+MC_HD void profpack_body(int64_t b, const DevIndex& ix, const DevProfile& p, int64_t n_blocks, const int64_t* pre, int64_t beg, int64_t end, uint64_t* out)
+{
+	const int64_t g0 = b * MC_PROF_BLOCK; int64_t g1 = g0 + MC_PROF_BLOCK; if (g1 > ix.G) g1 = ix.G;
+	int64_t t[6]; for (int k = 0; k < 6; k++) t[k] = pre[k * n_blocks + b];
+	for (int64_t g = g0; g < g1; g++)
+	{
+		t[0] += p.sdiff[g * 4]; t[1] += p.sdiff[g * 4 + 1]; t[2] += p.sdiff[g * 4 + 2]; t[3] += p.sdiff[g * 4 + 3];
+		t[4] += p.cdiff[g]; t[5] += p.mdiff[g];
+		if (g < beg || g >= end) continue;
+		const uint32_t w0 = p.base16[g * 2], w1 = p.base16[g * 2 + 1];
+		uint64_t c[4] = {w0 & 0xFFFF, w0 >> 16, w1 & 0xFFFF, w1 >> 16};
+		c[mc_ref_code(ix, g)] += (uint64_t)t[4];
+		uint64_t M = (uint64_t)t[5], R = p.rcount[g];
+		for (int k = 0; k < 4; k++) if (c[k] > 4095) c[k] = 4095;
+		if (M > 4095) M = 4095;
+		const int64_t i = g - beg;
+		out[2 * i] = c[0] | c[1] << 12 | c[2] << 24 | c[3] << 36 | M << 48 | (R & 15) << 60;
+		out[2 * i + 1] = ((uint64_t)t[0] & 0xFFFF) | ((uint64_t)t[1] & 0xFFFF) << 16 | ((uint64_t)t[2] & 0xFFFF) << 32 | ((uint64_t)t[3] & 0xFFFF) << 48;
+	}
 }
 
 #endif
