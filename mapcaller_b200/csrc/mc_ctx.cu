@@ -100,7 +100,7 @@ struct HBuf {
 
 enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_COUNT };
 
-struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key; mc_u64 pad; };
+struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
 struct Staged { DBuf seq, roff, seed_off; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false; };
@@ -122,7 +122,7 @@ struct mc_ctx {
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
-	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap;
+	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask;
 	HBuf h_bounce[2];
 #ifndef MC_HOSTEMU
 	cudaEvent_t ev_bounce[2];
@@ -161,7 +161,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask};
 	for (DBuf* b : bufs) b->release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
@@ -374,7 +374,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	a.pair_out = c->d_pair_out.as<mc_pair_out>(); a.rtask = c->d_rtask.as<int32_t>(); a.read_redo = c->d_read_redo.as<uint8_t>();
 	const int64_t rtask_cap = (n_pairs + 1) * 4;
 	Bumps* db = c->d_bumps.as<Bumps>();
-	a.pair_bump = &db->pair; a.frag_bump = &db->frag; a.aln_bump = &db->aln; a.task_bump = &db->task; a.dpws_bump = &db->dpws; a.rtask_bump = &db->rtask;
+	a.pair_bump = &db->pair; a.frag_bump = &db->frag; a.aln_bump = &db->aln; a.task_bump = &db->task; a.dpws_bump = &db->dpws; a.rtask_bump = &db->rtask; a.ptask_bump = &db->ptask;
 	a.prof.base16 = c->d_base16.as<uint32_t>(); a.prof.sdiff = c->d_sdiff.as<int32_t>(); a.prof.cdiff = c->d_cdiff.as<int32_t>(); a.prof.mdiff = c->d_mdiff.as<int32_t>();
 	a.prof.rcount = c->d_rcount.as<uint8_t>();
 
@@ -406,12 +406,12 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		bad |= c->d_loc_slot.reserve((n_locs + 1) * 4) || c->d_pairs.reserve(pair_cap * sizeof(SPair));
 		bad |= c->d_cands.reserve(cand_total * sizeof(Cand)) || c->d_cscore.reserve(cand_total * 4) || c->d_cpaired.reserve(cand_total * 4);
 		bad |= c->d_corient.reserve(cand_total * 4) || c->d_cfrag.reserve(cand_total * 4) || c->d_cnfrag.reserve(cand_total * 4) || c->d_ctmp.reserve(cand_total * 4);
-		bad |= c->d_frags.reserve(frag_cap * sizeof(mc_frag_out)) || c->d_aln.reserve(aln_cap) || c->d_tasks.reserve(task_cap * sizeof(DpTask)) || c->d_dpws.reserve(dpws_cap);
+		bad |= c->d_ptask.reserve(frag_cap * 4) || c->d_frags.reserve(frag_cap * sizeof(mc_frag_out)) || c->d_aln.reserve(aln_cap) || c->d_tasks.reserve(task_cap * sizeof(DpTask)) || c->d_dpws.reserve(dpws_cap);
 		if (bad) return MC_ERR_CUDA;
 		a.loc_slot = c->d_loc_slot.as<int32_t>(); a.pairs = c->d_pairs.as<SPair>(); a.pair_cap = pair_cap;
 		a.cands = c->d_cands.as<Cand>(); a.cscore = c->d_cscore.as<int32_t>(); a.cpaired = c->d_cpaired.as<int32_t>(); a.corient = c->d_corient.as<int32_t>();
 		a.cfrag = c->d_cfrag.as<int32_t>(); a.cnfrag = c->d_cnfrag.as<int32_t>(); a.ctmp = c->d_ctmp.as<int32_t>();
-		a.frags = c->d_frags.as<mc_frag_out>(); a.frag_cap = frag_cap; a.aln = c->d_aln.as<uint8_t>(); a.aln_cap = aln_cap;
+		a.ptask = c->d_ptask.as<int32_t>(); a.frags = c->d_frags.as<mc_frag_out>(); a.frag_cap = frag_cap; a.aln = c->d_aln.as<uint8_t>(); a.aln_cap = aln_cap;
 		a.tasks = c->d_tasks.as<DpTask>(); a.task_cap = task_cap; a.dpws = c->d_dpws.as<uint8_t>(); a.dpws_cap = dpws_cap;
 
 		launch_expand(a, st.n_slots, s);
@@ -440,13 +440,14 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		while (first_open < n_chunks)
 		{
 			// one attempt: no host round trip inside it, the task lists are consumed from their device-side cursors
-			a.rtask_begin = (int64_t)hbp->rtask; a.task_begin = (int64_t)hbp->task;
+			a.rtask_begin = (int64_t)hbp->rtask; a.task_begin = (int64_t)hbp->task; a.ptask_begin = (int64_t)hbp->ptask;
 			if (a.rtask_begin + n_pairs > rtask_cap) { mc_set_error("mc_map_batch: too many speculation replays in one batch"); return MC_ERR_OVERFLOW; }
 			bad |= dev_h2d(c->d_est.p, est.data(), n_chunks * 4, s) || dev_h2d(c->d_active.p, active.data(), n_chunks, s);
 			if (paired) { launch_pair(a, n_pairs, s); launch_rescue(a, n_pairs, s); } else launch_single(a, n, s);
 			if (first_attempt) ev_record(&c->ev[EV_PAIR1], s);
 			first_attempt = false;
 			launch_alnprep(a, n, s);
+			launch_piece(a, frag_cap, s);
 			launch_dp(a, task_cap - a.task_begin, s);
 			launch_alnfin(a, n, s);
 			if (paired) launch_pairstat(a, n_pairs, s);

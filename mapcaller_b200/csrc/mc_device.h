@@ -27,6 +27,7 @@ template <class T> static inline void mc_atomic_or(T* p, T v) { *p = (T)(*p | v)
 static inline int mc_popc(uint32_t x) { return __builtin_popcount(x); }
 #define MC_WARP_SYNC() do { } while (0)
 static inline int64_t mc_bcast64(int64_t v) { return v; }
+static inline int mc_warp_sum(int v) { return v; }
 static inline int mc_max3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
 #else
 #include <cuda_runtime.h>
@@ -43,6 +44,7 @@ static __device__ __forceinline__ void mc_atomic_or(unsigned long long* p, unsig
 static __device__ __forceinline__ int mc_popc(uint32_t x) { return __popc(x); }
 #define MC_WARP_SYNC() __syncwarp()
 static __device__ __forceinline__ int64_t mc_bcast64(int64_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+static __device__ __forceinline__ int mc_warp_sum(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
 static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); } // DPX
 #endif
 

@@ -110,20 +110,48 @@ MC_HD uint64_t mc_block_base(const OccBlock& b, int i)
 // One forward extension by base code c (reference src/bwt_search.cpp:138-149); false = empty child.
 // The two rows k, l fall into the same 128-row block in most steps (the reference's bwt_2occ4 fast path, :73);
 // the second block is only fetched when they do not, everything after the fetch is the same code for every lane.
+// the 48 bytes of a block that a count of symbol i needs: the 8 words and the 16-byte quarter holding count[i]
+// (A,C sit in the first quarter, G,T in the second).  Three 128-bit loads instead of four: the L1TEX tag stage, which
+// sees one wavefront per lane and load because every lane reads a different line, is what bounds this kernel (profiles/).
+struct OccPart { mc_u32x4 qc, q2, q3; };
+MC_HD void mc_load_part(const DevIndex& ix, uint64_t blk, int i, OccPart& b)
+{
+	const uint32_t* p = ix.bwt + (blk << 4);
+	b.qc = mc_ldg128(p + ((i & 2) << 1)); b.q2 = mc_ldg128(p + 8); b.q3 = mc_ldg128(p + 12);
+}
+MC_HD uint64_t mc_part_base(const OccPart& b, int i) { return (i & 1) ? ((uint64_t)b.qc.w << 32 | b.qc.z) : ((uint64_t)b.qc.y << 32 | b.qc.x); }
+MC_HD int mc_count_in_part(const OccPart& b, uint32_t flip, int nbits)
+{
+	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};
+	int n = 0;
+#pragma unroll
+	for (int j = 0; j < 8; j += 2)
+	{
+		const uint32_t a = w[j] ^ flip, c = w[j + 1] ^ flip;
+		const uint32_t e0 = (a >> 1) & a & mc_prefix_pairs(nbits - 32 * j);
+		const uint32_t e1 = (c >> 1) & c & mc_prefix_pairs(nbits - 32 * (j + 1));
+		n += mc_popc(e0 + (e1 << 1));
+	}
+	return n;
+}
+
+// One forward extension by base code c (reference src/bwt_search.cpp:138-149); false = empty child.
+// The two rows k, l fall into the same 128-row block in most steps (the reference's bwt_2occ4 fast path, :73);
+// the second block is only fetched when they do not, everything after the fetch is the same code for every lane.
 MC_HD bool mc_interval_extend(const DevIndex& ix, RcInterval& v, int c, uint32_t* nblk)
 {
 	const int i = 3 - c;
 	const uint32_t flip = mc_flip_of(i);
 	const uint64_t k = v.x1 - 1, l = v.x1 - 1 + v.x2;                 // x1 >= 1, so k never is the (uint64)-1 row
 	const uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
-	OccBlock bk, bl;
-	mc_load_block(ix, kk >> 7, bk);
+	OccPart bk, bl;
+	mc_load_part(ix, kk >> 7, i, bk);
 	const bool same = (kk >> 7) == (ll >> 7);
 	bl = bk;
-	if (!same) mc_load_block(ix, ll >> 7, bl);
+	if (!same) mc_load_part(ix, ll >> 7, i, bl);
 	*nblk += same ? 1u : 2u;
-	const uint64_t occ_k = mc_block_base(bk, i) + (uint64_t)mc_count_in_block(bk, flip, 2 * ((int)(kk & 127) + 1));
-	const uint64_t occ_l = mc_block_base(bl, i) + (uint64_t)mc_count_in_block(bl, flip, 2 * ((int)(ll & 127) + 1));
+	const uint64_t occ_k = mc_part_base(bk, i) + (uint64_t)mc_count_in_part(bk, flip, 2 * ((int)(kk & 127) + 1));
+	const uint64_t occ_l = mc_part_base(bl, i) + (uint64_t)mc_count_in_part(bl, flip, 2 * ((int)(ll & 127) + 1));
 	if (occ_l == occ_k) return false;
 	v.x1 = ix.L2[i] + 1 + occ_k; v.x2 = occ_l - occ_k;
 	return true;

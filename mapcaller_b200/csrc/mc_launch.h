@@ -15,6 +15,7 @@ typedef int mc_stream_t;
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
 static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a); }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
+static void launch_piece(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, p, G, nb, sums); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
@@ -43,14 +44,32 @@ static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t s)
 	int64_t blocks = (n + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;   // 8 resident 256-thread blocks per SM
 	mc_locate_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
-// one warp per rescue task
-__global__ void __launch_bounds__(MC_BLOCK) mc_rescue_kernel(const PipeArgs a, int64_t n)
+// normal pieces: persistent warps over the current attempt's piece list
+__global__ void __launch_bounds__(MC_BLOCK) mc_piece_kernel(const PipeArgs a)
 {
-	int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-	if (w < n) rescue_body(w, threadIdx.x & 31, 32, a);
+	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin;
+	for (int64_t t = warp; t < n; t += n_warps) { piece_body(t, threadIdx.x & 31, 32, a); __syncwarp(); }
 }
-static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t s)
-{ if (n > 0) { mc_rescue_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
+static void launch_piece(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
+{
+	if (max_tasks <= 0) return;
+	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
+	mc_piece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
+}
+// rescue tasks: persistent warps, warp w takes tasks w, w + n_warps, ... of the current attempt's window
+__global__ void __launch_bounds__(MC_BLOCK) mc_rescue_kernel(const PipeArgs a)
+{
+	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	const int64_t n = (int64_t)*a.rtask_bump - a.rtask_begin;
+	for (int64_t t = warp; t < n; t += n_warps) { rescue_body(t, threadIdx.x & 31, 32, a); __syncwarp(); }
+}
+static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
+{
+	if (max_tasks <= 0) return;
+	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
+	mc_rescue_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
+}
 __global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t* sums)
 { int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < nb) profsum_body(b, p, G, nb, sums); }
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t s)

@@ -7,7 +7,8 @@
 //   cluster_body   sort(CompByPosDiff) + SimplePairClustering   src/ReadMapping.cpp:152,194,160
 //   pair_body      CheckPairedAlignmentDistance, MaskUnPairedAlnCan, RemoveRedundantAlnCan  :244,305,228
 //   rescue_body    AlignmentRescue                              src/AlignmentRescue.cpp:28, src/KmerAnalysis.cpp
-//   alnprep_body   ProduceReadAlignment up to the DP dispatch   src/ReadAlignment.cpp:306-342,38-108,155-191
+//   alnprep_body   ProduceReadAlignment: fragment lists          src/ReadAlignment.cpp:306-342,38-108
+//   piece_body     ProcessNormalPair: strings + DP dispatch      src/ReadAlignment.cpp:155-191
 //   dp_body        nw_alignment / ksw2_alignment                src/nw_alignment.cpp:18, src/ksw2_alignment.cpp:250
 //   alnfin_body    rest of ProduceReadAlignment                 src/ReadAlignment.cpp:343-411
 //   pairstat_body  GenCoordinatePair + per-chunk sums           src/ReadMapping.cpp:361,479-539
@@ -68,6 +69,7 @@ struct PipeArgs {
 	mc_frag_out* frags; int64_t frag_cap; mc_u64* frag_bump;
 	uint8_t* aln; int64_t aln_cap; mc_u64* aln_bump;
 	DpTask* tasks; int64_t task_cap; mc_u64* task_bump;
+	int32_t* ptask; mc_u64* ptask_bump; int64_t ptask_begin;   // normal pieces whose strings still have to be laid out
 	uint8_t* dpws; int64_t dpws_cap; mc_u64* dpws_bump;
 	int32_t* rtask;          // rescue task list (pair ids)
 	mc_u64* rtask_bump;
@@ -109,6 +111,17 @@ MC_HD void prep_body(int64_t r, const PipeArgs& a)
 // ------------------------------------------------------------------------------------------------
 // seeding: one thread walks one read left to right
 // ------------------------------------------------------------------------------------------------
+// read bases are fetched four at a time through an aligned 32-bit window (one load every fourth step instead of a byte
+// load per step: every load of this kernel costs a full L1TEX wavefront per lane)
+struct BaseWindow { const uint32_t* w; uint32_t cur; int have; int shift0; };
+MC_HD uint8_t base_at(const uint8_t* s, int p, BaseWindow& bw)
+{
+	const int q = p + bw.shift0;            // byte offset from the aligned base
+	const int word = q >> 2;
+	if (word != bw.have) { bw.cur = mc_ldg(bw.w + word); bw.have = word; }
+	return (uint8_t)(bw.cur >> ((q & 3) << 3));
+}
+
 MC_HD void seed_body(int64_t r, const PipeArgs& a)
 {
 	const uint8_t* s = a.seq + a.roff[r];
@@ -116,6 +129,7 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 	const int64_t so = a.seed_off[r];
 	const int cap = (int)(a.seed_off[r + 1] - so);
 	const int stop = rlen - MC_MIN_SEED;
+	BaseWindow bw; bw.shift0 = (int)((uintptr_t)s & 3); bw.w = (const uint32_t*)(s - bw.shift0); bw.have = -1; bw.cur = 0;
 	int ns = 0, pos = 0, p = 0;
 	uint32_t lower = 0;
 	bool in_seed = false;
@@ -128,7 +142,7 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 		if (!in_seed)
 		{
 			if (pos >= stop) break;
-			const uint8_t ch = s[pos];
+			const uint8_t ch = base_at(s, pos, bw);
 			const int c = mc_nt4(ch);
 			if (c > 3) { pos++; continue; }
 			lower |= ch;
@@ -137,7 +151,7 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 		bool end = p >= rlen;
 		if (!end)
 		{
-			const uint8_t ch = s[p];
+			const uint8_t ch = base_at(s, p, bw);
 			const int cc = mc_nt4(ch);
 			end = cc > 3 || !mc_interval_extend(a.ix, v, cc, &nblk);
 			if (!end) { p++; lower |= ch; }

@@ -111,58 +111,75 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 			}
 			if (!ok) { a.cscore[co + ci] = 0; continue; }
 		}
-		// strings of the normal pieces
-		int need = 0;
-		for (int i = 0; i < nf; i++) if (!f[i].bSimple) need += 2 * (f[i].rLen + f[i].gLen);
-		int64_t ab = 0;
-		if (need)
+		// space for the strings of the normal pieces; piece_body lays them out
+		int need = 0, np = 0;
+		for (int i = 0; i < nf; i++) if (!f[i].bSimple) { need += 2 * (f[i].rLen + f[i].gLen); np++; }
+		if (np)
 		{
-			ab = (int64_t)mc_atomic_add(a.aln_bump, (mc_u64)need);
+			int64_t ab = (int64_t)mc_atomic_add(a.aln_bump, (mc_u64)need);
 			if (ab + need > a.aln_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 16); a.cscore[co + ci] = 0; continue; }
-		}
-		for (int i = 0; i < nf; i++)
-		{
-			mc_frag_out& x = f[i];
-			if (x.bSimple) continue;
-			const int cp = x.rLen + x.gLen;
-			x.aln_off = (int32_t)ab; x.aln_cap = cp; ab += 2 * cp;
-			uint8_t* a1 = a.aln + x.aln_off; uint8_t* a2 = a1 + cp;
-			const bool rev = x.gPos >= a.ix.G;
-			if (x.rLen > 0)
+			const int64_t pt = (int64_t)mc_atomic_add(a.ptask_bump, (mc_u64)np);   // pieces never outnumber fragments: the list has frag_cap entries
+			int k = 0;
+			for (int i = 0; i < nf; i++)
 			{
-				if (!rev) for (int k = 0; k < x.rLen; k++) a1[k] = rs[x.rPos + k];
-				else for (int k = 0; k < x.rLen; k++) a1[k] = mc_complement(rs[x.rPos + x.rLen - 1 - k]);
-			}
-			else for (int k = 0; k < x.gLen; k++) a1[k] = '-';
-			if (x.gLen > 0)
-			{
-				if (!rev) for (int k = 0; k < x.gLen; k++) a2[k] = mc_ref_char(a.ix, x.gPos + k);
-				else for (int k = 0; k < x.gLen; k++) a2[k] = (uint8_t)("TGCA"[mc_ref_code(a.ix, x.gPos + x.gLen - 1 - k)]);
-			}
-			else for (int k = 0; k < x.rLen; k++) a2[k] = '-';
-			x.aln_len = x.rLen > x.gLen ? x.rLen : x.gLen;
-			if (x.rLen > 0 && x.gLen > 0)
-			{
-				bool dp = x.rLen != x.gLen;
-				if (!dp)
-				{
-					int mis = 0;
-					for (int k = 0; k < x.rLen; k++) if (a1[k] != a2[k]) mis++;
-					dp = mis > 1 && mis >= (int)(x.rLen * 0.2);
-				}
-				if (dp)
-				{
-					const int64_t t = (int64_t)mc_atomic_add(a.task_bump, (mc_u64)1);
-					const int64_t wsn = dp_ws_bytes(x.rLen, x.gLen);
-					const int64_t ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
-					if (t >= a.task_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 24); continue; }
-					if (ws + wsn > a.dpws_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); continue; }
-					DpTask tk; tk.frag = (int32_t)(fb + i); tk.m = x.rLen; tk.n = x.gLen; tk.pad = 0; tk.ws_off = ws;
-					a.tasks[t] = tk;
-				}
+				mc_frag_out& x = f[i];
+				if (x.bSimple) continue;
+				const int cp = x.rLen + x.gLen;
+				x.aln_off = (int32_t)ab; x.aln_cap = cp; ab += 2 * cp;
+				x.aln_len = x.rLen > x.gLen ? x.rLen : x.gLen;
+				x.pad = (int32_t)r;                     // internal: the read this piece belongs to
+				if (pt + k < a.frag_cap) a.ptask[pt + k] = (int32_t)(fb + i); else mc_atomic_or(&a.st->overflow, (mc_u64)1 << 8);
+				k++;
 			}
 		}
 		a.cfrag[co + ci] = (int32_t)fb; a.cnfrag[co + ci] = nf;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// piece: `nl` lanes (a warp) lay out the two strings of one normal piece - read bases against RefSequence, both
+// reverse-complemented on the reverse strand - count the mismatches and queue the piece for a gapped fill when the
+// reference would run one (ProcessNormalPair, reference src/ReadAlignment.cpp:155-191)
+// ------------------------------------------------------------------------------------------------
+MC_HD void piece_body(int64_t t, int lane, int nl, const PipeArgs& a)
+{
+	if (a.ptask_begin + t >= (int64_t)*a.ptask_bump) return;
+	const int32_t fi = a.ptask[a.ptask_begin + t];
+	const mc_frag_out x = a.frags[fi];
+	const uint8_t* rs = a.seq + a.roff[x.pad];
+	uint8_t* a1 = a.aln + x.aln_off; uint8_t* a2 = a1 + x.aln_cap;
+	const bool rev = x.gPos >= a.ix.G;
+	if (x.rLen > 0)
+	{
+		if (!rev) for (int k = lane; k < x.rLen; k += nl) a1[k] = rs[x.rPos + k];
+		else for (int k = lane; k < x.rLen; k += nl) a1[k] = mc_complement(rs[x.rPos + x.rLen - 1 - k]);
+	}
+	else for (int k = lane; k < x.gLen; k += nl) a1[k] = '-';
+	if (x.gLen > 0)
+	{
+		if (!rev) for (int k = lane; k < x.gLen; k += nl) a2[k] = mc_ref_char(a.ix, x.gPos + k);
+		else for (int k = lane; k < x.gLen; k += nl) a2[k] = (uint8_t)("TGCA"[mc_ref_code(a.ix, x.gPos + x.gLen - 1 - k)]);
+	}
+	else for (int k = lane; k < x.rLen; k += nl) a2[k] = '-';
+	if (x.rLen <= 0 || x.gLen <= 0) return;
+	bool dp = x.rLen != x.gLen;
+	if (!dp)
+	{
+		MC_WARP_SYNC();
+		int mis = 0;
+		for (int k = lane; k < x.rLen; k += nl) if (a1[k] != a2[k]) mis++;
+		mis = mc_warp_sum(mis);
+		dp = mis > 1 && mis >= (int)(x.rLen * 0.2);
+	}
+	if (dp && lane == 0)
+	{
+		const int64_t tt = (int64_t)mc_atomic_add(a.task_bump, (mc_u64)1);
+		const int64_t wsn = dp_ws_bytes(x.rLen, x.gLen);
+		const int64_t ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
+		if (tt >= a.task_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 24); return; }
+		if (ws + wsn > a.dpws_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
+		DpTask tk; tk.frag = fi; tk.m = x.rLen; tk.n = x.gLen; tk.pad = 0; tk.ws_off = ws;
+		a.tasks[tt] = tk;
 	}
 }
 

@@ -1,0 +1,230 @@
+// Drop-in replacement for the reference's hot-path translation units
+//   ReadMapping.cpp bwt_search.cpp ReadAlignment.cpp nw_alignment.cpp ksw2_alignment.cpp AlignmentProfile.cpp
+//   AlignmentRescue.cpp KmerAnalysis.cpp
+// It is compiled against the reference's own (unchanged) src/structure.h and linked with the reference's unchanged
+// main.o GetData.o VariantCalling.o SamReport.o tools.o bwt_index.o (+ BWT_Index), giving a MapCaller binary with the same
+// command line whose mapping runs on the GPU through libmapcaller_b200.so.  It provides exactly the
+// symbols the kept objects import from the replaced ones: Mapping(), CompByDiscordPos(),
+// avgDist, avgReadLength, BreakPointMap, InsertSeqMap, DeleteSeqMap, InversionSiteVec, TranslocationSiteVec.
+//
+// What stays on the host, unchanged and in file order: FASTQ/FASTA reading (GetNextChunk), ReverseOrientation of mate 2
+// for the SAM text, SAM generation (GeneratePairedSamStream / GenerateSingleSamStream) and everything after Mapping().
+#include "structure.h"
+#include "mapcaller_b200.h"
+
+// ---- symbols the kept objects import ----------------------------------------------------------------------
+vector<DiscordPair_t> InversionSiteVec, TranslocationSiteVec;
+map<int64_t, map<string, uint16_t> > InsertSeqMap, DeleteSeqMap;
+map<int64_t, uint16_t> BreakPointMap;
+uint32_t avgCov, avgReadLength, avgDist = 1000;
+int64_t iTotalReadNum = 0, iTotalMappingNum = 0, iTotalPairedNum = 0, iAlignedBase = 0, iTotalCoverage = 0, TotalPairedDistance = 0, ReadLengthSum = 0;
+extern float MaxMisMatchRate;
+
+bool CompByDiscordPos(const DiscordPair_t& p1, const DiscordPair_t& p2) { return p1.gPos < p2.gPos; }
+
+namespace {
+
+const int kBatchChunks = 2500;   // 200-read chunks per GPU batch (500 k reads)
+
+void die(const char* what) { fprintf(stderr, "\n[mapcaller_b200] %s: %s\n", what, mc_last_error()); exit(1); }
+
+struct Library { FILE *f1, *f2; gzFile g1, g2; bool sep, gz; };
+
+// one GPU batch: up to kBatchChunks chunks pulled with the reference's own reader
+int64_t pull_batch(Library& lib, vector<ReadItem_t>& reads)
+{
+	reads.clear();
+	vector<ReadItem_t> chunk(ReadChunkSize);
+	for (int c = 0; c < kBatchChunks; c++)
+	{
+		int n = lib.gz ? gzGetNextChunk(lib.sep, lib.g1, lib.g2, chunk.data()) : GetNextChunk(lib.sep, lib.f1, lib.f2, chunk.data());
+		if (n == 0) break;
+		reads.insert(reads.end(), chunk.begin(), chunk.begin() + n);
+		if (n < ReadChunkSize) break;
+	}
+	return (int64_t)reads.size();
+}
+
+void free_reads(vector<ReadItem_t>& reads)
+{
+	for (size_t i = 0; i < reads.size(); i++) { delete[] reads[i].header; delete[] reads[i].seq; delete[] reads[i].qual; }
+	reads.clear();
+}
+
+// AlnSummary / AlnCanVec of one read from the flat batch result (inverse of the library's CSR layout)
+void rebuild(ReadItem_t& rd, const mc_batch_out& out, int64_t r)
+{
+	const mc_read_out& ro = out.reads[r];
+	rd.AlnSummary.score = ro.score; rd.AlnSummary.sub_score = ro.sub_score; rd.AlnSummary.BestAlnCanIdx = ro.best_idx;
+	rd.AlnCanVec.clear(); rd.AlnCanVec.resize(ro.n_cand);
+	for (int k = 0; k < ro.n_cand; k++)
+	{
+		const mc_cand_out& co = out.cands[ro.cand_begin + k];
+		AlnCan_t& ac = rd.AlnCanVec[k];
+		ac.score = co.score; ac.SamFlag = 0; ac.orientation = co.orientation == 1; ac.PairedAlnCanIdx = co.paired_idx;
+		ac.FragPairVec.resize(co.n_frag);
+		for (int f = 0; f < co.n_frag; f++)
+		{
+			const mc_frag_out& fo = out.frags[co.frag_begin + f];
+			FragPair_t& fp = ac.FragPairVec[f];
+			fp.bSimple = fo.bSimple != 0; fp.rPos = fo.rPos; fp.gPos = fo.gPos; fp.rLen = fo.rLen; fp.gLen = fo.gLen; fp.PosDiff = fo.gPos - fo.rPos;
+			if (!fp.bSimple && fo.aln_len > 0)
+			{
+				fp.aln1.assign((const char*)out.aln + fo.aln_off, fo.aln_len);
+				fp.aln2.assign((const char*)out.aln + fo.aln_off + fo.aln_cap, fo.aln_len);
+			}
+		}
+	}
+}
+
+void* coverage_worker(void* arg)
+{
+	int tid = *(int*)arg; int64_t bases = 0, cov = 0;
+	for (int64_t g = tid; g < GenomeSize; g += iThreadNum) { int c = GetProfileColumnSize(MappingRecordArr[g]); if (c > 0) { bases++; cov += c; } }
+	pthread_mutex_lock(&ProfileLock); iAlignedBase += bases; iTotalCoverage += cov; pthread_mutex_unlock(&ProfileLock);
+	return (void*)1;
+}
+
+} // namespace
+
+void Mapping()
+{
+	FILE* sam_out = NULL;
+	if (bSAMoutput && !bSAMFormat) { fprintf(stderr, "Error! -bam is not supported by the GPU build; use -sam\n"); exit(1); }
+	if (bSAMoutput && SamFileName != NULL) sam_out = strcmp(SamFileName, "-") == 0 ? fopen("/dev/stdout", "w") : fopen(SamFileName, "w");
+	if (bSAMoutput)
+	{
+		fprintf(sam_out, "@PG\tID:MapCaller\tPN:MapCaller\tVN:%s\n", VersionStr);
+		for (int i = 0; i < iChromsomeNum; i++) fprintf(sam_out, "@SQ\tSN:%s\tLN:%d\n", ChromosomeVec[i].name, ChromosomeVec[i].len);
+	}
+
+	// the index the reference has just loaded, handed over without copying
+	vector<int32_t> clen(iChromsomeNum); vector<const char*> cname(iChromsomeNum);
+	for (int i = 0; i < iChromsomeNum; i++) { clen[i] = ChromosomeVec[i].len; cname[i] = ChromosomeVec[i].name; }
+	mc_index_view v; memset(&v, 0, sizeof(v));
+	v.bwt = Refbwt->bwt; v.bwt_size = Refbwt->bwt_size; v.primary = Refbwt->primary; for (int i = 0; i < 5; i++) v.L2[i] = Refbwt->L2[i];
+	v.seq_len = Refbwt->seq_len; v.sa = Refbwt->sa; v.n_sa = Refbwt->n_sa; v.sa_intv = Refbwt->sa_intv; v.pac = RefIdx->pac; v.genome_size = GenomeSize;
+	v.n_chrom = iChromsomeNum; v.chrom_len = clen.data(); v.chrom_name = cname.data();
+	mc_index* idx = NULL; if (mc_index_wrap(&v, &idx)) die("mc_index_wrap");
+
+	mc_ctx* ctx = NULL;
+	for (int lib_id = 0; lib_id < (int)ReadFileNameVec1.size(); lib_id++)
+	{
+		Library lib; memset(&lib, 0, sizeof(lib));
+		const string& n1 = ReadFileNameVec1[lib_id];
+		lib.gz = gzCompressed = n1.substr(n1.find_last_of('.') + 1) == "gz";
+		FastQFormat = CheckReadFormat(n1.c_str());
+		if (lib.gz) lib.g1 = gzopen(n1.c_str(), "rb"); else lib.f1 = fopen(n1.c_str(), "r");
+		if (ReadFileNameVec1.size() == ReadFileNameVec2.size())
+		{
+			lib.sep = bPairEnd = true;
+			const string& n2 = ReadFileNameVec2[lib_id];
+			if (FastQFormat != CheckReadFormat(n2.c_str())) { fprintf(stderr, "Error! %s and %s are with different format...\n", n1.c_str(), n2.c_str()); continue; }
+			if (lib.gz) lib.g2 = gzopen(n2.c_str(), "rb"); else lib.f2 = fopen(n2.c_str(), "r");
+		}
+		if (lib.f1 == NULL && lib.g1 == NULL) continue;
+		if (lib.sep && lib.f2 == NULL && lib.g2 == NULL) continue;
+
+		if (ctx == NULL)   // bPairEnd is only known once the first library is open
+		{
+			mc_params p; mc_params_default(&p);
+			p.paired = bPairEnd; p.alg_ksw2 = !NW_ALG; p.max_pos_diff = MaxPosDiff; p.max_clip = MaxClipSize; p.max_dup = iMaxDuplicate;
+			p.max_mismatch_rate = MaxMisMatchRate; p.update_profile = bVCFoutput; p.want_alignments = bSAMoutput;
+			if (mc_ctx_create(idx, &p, &ctx)) die("mc_ctx_create");
+		}
+		vector<ReadItem_t> reads; vector<uint8_t> seq; vector<int64_t> off; vector<string> sam;
+		while (pull_batch(lib, reads) > 0)
+		{
+			int64_t n = (int64_t)reads.size();
+			if (bPairEnd && (n & 1)) { free_reads(reads); break; }   // the reference silently maps an odd chunk as single-end; not supported here
+			off.assign(1, 0); seq.clear();
+			for (int64_t i = 0; i < n; i++) { seq.insert(seq.end(), reads[i].seq, reads[i].seq + reads[i].rlen); off.push_back((int64_t)seq.size()); }
+			mc_batch_in in; in.n_reads = n; in.seq = seq.data(); in.seq_off = off.data();
+			mc_batch_out out;
+			if (mc_map_batch(ctx, &in, &out)) die("mc_map_batch");
+			mc_totals t; mc_get_totals(ctx, &t);
+			fprintf(stderr, "\r%lld %s reads have been processed in %lld seconds...", (long long)t.total_reads, (bPairEnd ? "paired-end" : "singled-end"), (long long)(time(NULL) - StartProcessTime));
+			if (bSAMoutput)
+			{
+				sam.clear();
+				for (int64_t i = 0; i < n; i++) rebuild(reads[i], out, i);
+				if (bPairEnd) for (int64_t i = 0; i < n; i += 2) { ReverseOrientation(&reads[i + 1]); GeneratePairedSamStream(reads[i], reads[i + 1], sam); }
+				else for (int64_t i = 0; i < n; i++) GenerateSingleSamStream(reads[i], sam);
+				for (size_t i = 0; i < sam.size(); i++) fprintf(sam_out, "%s\n", sam[i].c_str());
+				fflush(sam_out);
+			}
+			free_reads(reads);
+		}
+		if (lib.gz) { if (lib.g1) gzclose(lib.g1); if (lib.g2) gzclose(lib.g2); } else { if (lib.f1) fclose(lib.f1); if (lib.f2) fclose(lib.f2); }
+	}
+
+	if (ctx != NULL)
+	{
+		mc_totals t; mc_get_totals(ctx, &t);
+		iTotalReadNum = t.total_reads; iTotalMappingNum = t.total_mapped; iTotalPairedNum = t.total_paired; TotalPairedDistance = t.total_distance; ReadLengthSum = t.read_length_sum;
+		avgDist = t.avg_dist;
+		if (bVCFoutput)
+		{
+			// device profile -> the structures VariantCalling() reads
+			if (mc_profile_read(ctx, 0, GenomeSize, MappingRecordArr)) die("mc_profile_read");
+			const mc_indel_rec* ir; int64_t ni; const uint8_t* arena;
+			if (mc_profile_indels(ctx, &ir, &ni, &arena)) die("mc_profile_indels");
+			for (int64_t i = 0; i < ni; i++) (ir[i].kind == 0 ? InsertSeqMap : DeleteSeqMap)[ir[i].pos][string((const char*)arena + ir[i].seq_off, ir[i].len)] = (uint16_t)ir[i].count;
+			const mc_breakpoint_rec* br; int64_t nb;
+			if (mc_profile_breakpoints(ctx, &br, &nb)) die("mc_profile_breakpoints");
+			for (int64_t i = 0; i < nb; i++) BreakPointMap[br[i].pos] = (uint16_t)br[i].count;
+			for (int kind = 0; kind < 2; kind++)
+			{
+				const mc_site_rec* sr; int64_t ns;
+				if (mc_profile_sites(ctx, kind, &sr, &ns)) die("mc_profile_sites");
+				vector<DiscordPair_t>& dst = kind == 0 ? InversionSiteVec : TranslocationSiteVec;
+				for (int64_t i = 0; i < ns; i++) { DiscordPair_t d; d.gPos = sr[i].gPos; d.dist = sr[i].dist; dst.push_back(d); }
+				sort(dst.begin(), dst.end(), CompByDiscordPos);   // the thread-end sort of the reference (src/ReadMapping.cpp:629-630)
+			}
+		}
+		mc_ctx_destroy(ctx);
+	}
+	mc_index_free(idx);
+
+	// run summary, as the reference prints it (src/ReadMapping.cpp:749-790)
+	FILE* log = fopen(LogFileName, "a");
+	const char* kind = bPairEnd ? "paired-end" : "single-end";
+	const long long secs = (long long)(time(NULL) - StartProcessTime);
+	fprintf(log, "All the %lld %s reads have been processed in %lld seconds.\n", (long long)iTotalReadNum, kind, secs);
+	fprintf(stderr, "\rAll the %lld %s reads have been processed in %lld seconds.\n", (long long)iTotalReadNum, kind, secs);
+	if (iTotalReadNum > 0)
+	{
+		double pct = (int)(10000 * (1.0 * iTotalMappingNum / iTotalReadNum) + 0.00005) / 100.0;
+		fprintf(log, "%12lld (%6.2f%%) reads are mapped properly.\n", (long long)iTotalMappingNum, pct);
+		fprintf(stderr, "%12lld (%6.2f%%) reads are mapped properly.\n", (long long)iTotalMappingNum, pct);
+	}
+	if (iTotalReadNum > 0 && iTotalPairedNum > 0)
+	{
+		double pct = (int)(10000 * (1.0 * (iTotalPairedNum << 1) / iTotalReadNum) + 0.00005) / 100.0;
+		fprintf(log, "%12lld (%6.2f%%) reads are mapped in pairs.\n", (long long)(iTotalPairedNum << 1), pct);
+		fprintf(stderr, "%12lld (%6.2f%%) reads are mapped in pairs.\n", (long long)(iTotalPairedNum << 1), pct);
+	}
+	if (bSAMoutput) fclose(sam_out);
+	if (bVCFoutput)
+	{
+		vector<pthread_t> th(iThreadNum); vector<int> ids(iThreadNum);
+		for (int i = 0; i < iThreadNum; i++) { ids[i] = i; pthread_create(&th[i], NULL, coverage_worker, &ids[i]); }
+		for (int i = 0; i < iThreadNum; i++) pthread_join(th[i], NULL);
+		avgCov = (int)(1.0 * iTotalCoverage / iAlignedBase + .5);
+		fprintf(log, "\tEstimated AvgCoverage = %d\n", avgCov); fprintf(stderr, "\tEstimated AvgCoverage = %d\n", avgCov);
+		int64_t sites = 0, total = 0;
+		for (int64_t g = 0; g < GenomeSize; g++) if (MappingRecordArr[g].readCount > 0) { sites++; total += MappingRecordArr[g].readCount; }
+		total -= sites;
+		fprintf(log, "\tDuplication rate=%4.2f%%\n", 100 * (1.0 * total / sites)); fprintf(stderr, "\tDuplication rate=%4.2f%%\n", 100 * (1.0 * total / sites));
+	}
+	if (iTotalReadNum > 0 && iTotalPairedNum > 0)
+	{
+		avgDist = (int)(1. * TotalPairedDistance / iTotalPairedNum + .5);
+		avgReadLength = (int)(1. * ReadLengthSum / (iTotalPairedNum << 1) + .5);
+		FragmentSize = avgDist + avgReadLength;
+		fprintf(log, "\tAverage read length = %d, Estimated fragment size = %d, insert size = %d\n", avgReadLength, FragmentSize, avgDist - avgReadLength);
+		fprintf(stderr, "\tAverage read length = %d, Estimated fragment size = %d, insert size = %d\n", avgReadLength, FragmentSize, avgDist - avgReadLength);
+	}
+	else avgDist = avgReadLength = 0;
+	fclose(log);
+}
