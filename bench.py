@@ -203,7 +203,12 @@ def main():
     g, r1, r2, seq, off = make_workload(args.pairs, seed_shift=rank)
     ix = api.Index.build(sim.encode(g))
     n_pairs = len(r1)
-    ctx = api.Context(ix, paired=1, alg_ksw2=0, update_profile=1, want_alignments=0, device=local)
+    ctx = api.Context(ix, paired=1, alg_ksw2=0, update_profile=1, want_alignments=0, device=local, shard_rank=rank, shard_count=world)
+    if dist is not None:
+        # the library's own NCCL communicator (NVLink / NVSwitch) for the end-of-pass profile reduction
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
 
     def barrier():
         if dist is not None:
@@ -212,13 +217,18 @@ def main():
 
     # ---- resident leg (value) ----
     ctx.stage_batch(seq, off, 0)
-    for _ in range(args.warmup):
+    def one_pass():
         ctx.reset(); ctx.map_staged(0)
+        if dist is not None:
+            ctx.profile_allreduce()      # every rank ends the pass with the whole-library profile
+
+    for _ in range(args.warmup):
+        one_pass()
     ctx.reset_stats()
     sampler = ClockSampler(local); sampler.start()
     barrier(); t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.reset(); ctx.map_staged(0)
+        one_pass()
     barrier(); wall_resident = time.perf_counter() - t0
     clocks = sampler.stop()
     st = ctx.stats()
@@ -235,6 +245,8 @@ def main():
     barrier(); t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.reset(); res = ctx.map_batch(pseq, poff, copy=False)
+        if dist is not None:
+            ctx.profile_allreduce()
     barrier(); wall_e2e = time.perf_counter() - t0
     # same call with ordinary pageable numpy arrays (bounced through pinned buffers inside the library)
     t0 = time.perf_counter()
@@ -247,7 +259,9 @@ def main():
 
     if dist is not None:
         import torch
-        t = torch.tensor([dev_s, wall_e2e, wall_resident], device="cuda", dtype=torch.float64)
+        # multi-GPU: the pass includes the NCCL reduction, which the per-context CUDA events do not see -> the time between the
+        # barriers (each with a device synchronize) is the step time, max over ranks
+        t = torch.tensor([wall_resident, wall_e2e, wall_resident], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, wall_e2e, wall_resident = [float(x) for x in t.tolist()]
     total_pairs = n_pairs * world * args.steps

@@ -169,8 +169,13 @@ typedef struct { int64_t gPos, dist; } mc_site_rec;
 /* kind 0 = InversionSiteVec, 1 = TranslocationSiteVec, sorted by gPos as the thread-end merge does */
 int mc_profile_sites(mc_ctx *ctx, int32_t kind, const mc_site_rec **recs, int64_t *n_recs);
 
-/* Multi-GPU: sum the device counters / gather the records of all ranks (NCCL over NVLink) so that
- * rank 0 holds the whole-library profile.  `nccl_comm` is an ncclComm_t. */
+/* Multi-GPU (one context per GPU, one process per GPU): reads shard across the ranks, every rank holds a full index
+ * replica.  mc_comm_unique_id() on rank 0 -> ship the 128 bytes to the other ranks -> mc_comm_init() on every rank.
+ * mc_profile_allreduce() then sums the device counters of all ranks (ncclAllReduce over NVLink) and gathers the indel /
+ * break-point / SV-site records, so that every rank holds the whole-library profile.  `nccl_comm` may be an existing
+ * ncclComm_t of the caller, or NULL to use the communicator of mc_comm_init(). */
+int mc_comm_unique_id(uint8_t *out128);
+int mc_comm_init(mc_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t n_ranks);
 int mc_profile_allreduce(mc_ctx *ctx, void *nccl_comm);
 
 /* ---- operator-level entry points (per-kernel parity tests and micro-benchmarks) ---------------- */

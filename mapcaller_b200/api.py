@@ -104,6 +104,8 @@ def lib():
         L.mc_profile_breakpoints.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_sites.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
+        L.mc_comm_unique_id.argtypes = [C.c_void_p]
+        L.mc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.mc_align_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 8
         L.mc_bwt_search_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         _lib = L
@@ -262,6 +264,18 @@ class Context:
         for k, v in kw.items():
             setattr(t, k, v)
         _check(lib().mc_set_totals(self._h, C.byref(t)), "mc_set_totals")
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().mc_comm_unique_id(buf), "mc_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        _check(lib().mc_comm_init(self._h, uid, rank, n_ranks), "mc_comm_init")
+
+    def profile_allreduce(self):
+        _check(lib().mc_profile_allreduce(self._h, None), "mc_profile_allreduce")
 
     def reset(self):
         _check(lib().mc_reset(self._h), "mc_reset")

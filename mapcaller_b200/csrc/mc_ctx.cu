@@ -8,6 +8,9 @@
 // outcome unchanged, and the host walks the chunk statistics in file order, re-running only the chunks
 // whose true EstiDistance falls outside their interval.
 #include "mc_launch.h"
+#ifndef MC_HOSTEMU
+#include <nccl.h>
+#endif
 
 #include <algorithm>
 #include <cstdio>
@@ -141,6 +144,9 @@ struct mc_ctx {
 	// stats
 	mc_stats stats; DevStats dstats_last;
 	mc_event_t ev[EV_COUNT];
+#ifndef MC_HOSTEMU
+	ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;
+#endif
 };
 
 static void zero_stats(mc_stats* s) { memset(s, 0, sizeof(*s)); }
@@ -167,6 +173,9 @@ void mc_ctx_destroy(mc_ctx* c)
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
 	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc};
 	for (HBuf* b : hb) b->release();
+#ifndef MC_HOSTEMU
+	if (c->comm) ncclCommDestroy(c->comm);
+#endif
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
 	c->h_bounce[0].release(); c->h_bounce[1].release();
 #ifndef MC_HOSTEMU
@@ -753,7 +762,136 @@ int mc_profile_sites(mc_ctx* c, int32_t kind, const mc_site_rec** recs, int64_t*
 	return MC_OK;
 }
 
-int mc_profile_allreduce(mc_ctx*, void*) { mc_set_error("mc_profile_allreduce: built without NCCL"); return MC_ERR_NCCL; }
+// ---- multi-GPU: NCCL over NVLink ------------------------------------------------------------------------
+#ifdef MC_HOSTEMU
+int mc_comm_unique_id(uint8_t*) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
+int mc_comm_init(mc_ctx*, const uint8_t*, int32_t, int32_t) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
+int mc_profile_allreduce(mc_ctx*, void*) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
+#else
+static int nccl_fail(ncclResult_t r, const char* what)
+{
+	if (r == ncclSuccess) return 0;
+	mc_set_error("NCCL error in %s: %s", what, ncclGetErrorString(r));
+	return -1;
+}
+int mc_comm_unique_id(uint8_t* out)
+{
+	if (!out) { mc_set_error("mc_comm_unique_id: null argument"); return MC_ERR_ARG; }
+	ncclUniqueId id;
+	if (nccl_fail(ncclGetUniqueId(&id), "ncclGetUniqueId")) return MC_ERR_NCCL;
+	memcpy(out, &id, sizeof(id));
+	return MC_OK;
+}
+int mc_comm_init(mc_ctx* c, const uint8_t* id_bytes, int32_t rank, int32_t n_ranks)
+{
+	if (!c || !id_bytes || rank < 0 || rank >= n_ranks) { mc_set_error("mc_comm_init: bad argument"); return MC_ERR_ARG; }
+	cudaSetDevice(c->prm.device);
+	ncclUniqueId id; memcpy(&id, id_bytes, sizeof(id));
+	if (nccl_fail(ncclCommInitRank(&c->comm, n_ranks, id, rank), "ncclCommInitRank")) return MC_ERR_NCCL;
+	c->comm_rank = rank; c->comm_size = n_ranks;
+	return MC_OK;
+}
+
+// gathers variable-length byte records of every rank into every rank (sizes first, then one broadcast per rank)
+static int allgather_bytes(mc_ctx* c, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t> >& all)
+{
+	const int n = c->comm_size; cudaStream_t s = c->stream;
+	DBuf d_sz, d_buf;
+	if (d_sz.reserve(8 * (n + 1))) return -1;
+	long long my = (long long)mine.size();
+	std::vector<long long> sz(n);
+	if (dev_h2d(d_sz.as<long long>() + n, &my, 8, s)) return -1;
+	if (nccl_fail(ncclAllGather(d_sz.as<long long>() + n, d_sz.p, 1, ncclInt64, c->comm, s), "ncclAllGather")) return -1;
+	if (dev_d2h(sz.data(), d_sz.p, 8 * n, s) || dev_sync(s)) return -1;
+	long long mx = 1; for (int r = 0; r < n; r++) mx = std::max(mx, sz[r]);
+	if (d_buf.reserve((size_t)mx)) return -1;
+	all.assign(n, std::vector<uint8_t>());
+	for (int r = 0; r < n; r++)
+	{
+		if (sz[r] == 0) continue;
+		if (r == c->comm_rank && dev_h2d(d_buf.p, mine.data(), mine.size(), s)) return -1;
+		if (nccl_fail(ncclBroadcast(d_buf.p, d_buf.p, (size_t)sz[r], ncclUint8, r, c->comm, s), "ncclBroadcast")) return -1;
+		all[r].resize((size_t)sz[r]);
+		if (dev_d2h(all[r].data(), d_buf.p, (size_t)sz[r], s) || dev_sync(s)) return -1;
+	}
+	d_sz.release(); d_buf.release();
+	return 0;
+}
+
+__global__ void mc_clamp_u8_kernel(uint8_t* p, int64_t n, int hi)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n && p[i] > hi) p[i] = (uint8_t)hi; }
+
+// Sums what is additive across the shards (difference arrays, base counters, dedup counts, totals) with ncclAllReduce and
+// gathers the variable-length records (indels, break points, SV sites), so that afterwards every rank holds the profile
+// of the whole library.  `nccl_comm` may be an ncclComm_t created by the caller; NULL uses the one set up by mc_comm_init.
+int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
+{
+	if (!c) { mc_set_error("mc_profile_allreduce: null context"); return MC_ERR_ARG; }
+	ncclComm_t comm = nccl_comm ? (ncclComm_t)nccl_comm : c->comm;
+	if (!comm) { mc_set_error("mc_profile_allreduce: no communicator (call mc_comm_init first)"); return MC_ERR_NCCL; }
+	if (!c->prm.update_profile) { mc_set_error("mc_profile_allreduce: context was created without update_profile"); return MC_ERR_ARG; }
+	cudaSetDevice(c->prm.device);
+	cudaStream_t s = c->stream;
+	const size_t G = (size_t)c->G;
+	int bad = 0;
+	// packed 2 x uint16 counters are summed as uint32 words: no carry can cross the halves while every column stays below 65536
+	bad |= nccl_fail(ncclAllReduce(c->d_base16.p, c->d_base16.p, G * 2, ncclUint32, ncclSum, comm, s), "ncclAllReduce(base16)");
+	bad |= nccl_fail(ncclAllReduce(c->d_sdiff.p, c->d_sdiff.p, (G + 1) * 4, ncclInt32, ncclSum, comm, s), "ncclAllReduce(sdiff)");
+	bad |= nccl_fail(ncclAllReduce(c->d_cdiff.p, c->d_cdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(cdiff)");
+	bad |= nccl_fail(ncclAllReduce(c->d_mdiff.p, c->d_mdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(mdiff)");
+	bad |= nccl_fail(ncclAllReduce(c->d_rcount.p, c->d_rcount.p, G, ncclUint8, ncclSum, comm, s), "ncclAllReduce(rcount)");
+	if (bad) return MC_ERR_NCCL;
+	mc_clamp_u8_kernel<<<(unsigned)((G + 255) / 256), 256, 0, s>>>(c->d_rcount.as<uint8_t>(), (int64_t)G, c->prm.max_dup);
+	// totals
+	DBuf d_t; if (d_t.reserve(5 * 8)) return MC_ERR_CUDA;
+	long long t[5] = {c->tot.total_reads, c->tot.total_mapped, c->tot.total_paired, c->tot.total_distance, c->tot.read_length_sum};
+	if (dev_h2d(d_t.p, t, sizeof(t), s)) return MC_ERR_CUDA;
+	if (nccl_fail(ncclAllReduce(d_t.p, d_t.p, 5, ncclInt64, ncclSum, comm, s), "ncclAllReduce(totals)")) return MC_ERR_NCCL;
+	if (dev_d2h(t, d_t.p, sizeof(t), s) || dev_sync(s)) return MC_ERR_CUDA;
+	d_t.release();
+	c->tot.total_reads = t[0]; c->tot.total_mapped = t[1]; c->tot.total_paired = t[2]; c->tot.total_distance = t[3]; c->tot.read_length_sum = t[4];
+	if (c->tot.total_paired > 1000) c->tot.avg_dist = (uint32_t)(int)(1. * c->tot.total_distance / c->tot.total_paired + .5);
+	// variable-length records: every rank ends up with the records of all ranks, in rank (= file) order
+	ncclComm_t keep = c->comm; c->comm = comm;
+	PersistBumps pb;
+	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s)) { c->comm = keep; return MC_ERR_CUDA; }
+	std::vector<uint8_t> mine, tmp; std::vector<std::vector<uint8_t> > all;
+	auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; mine.insert(mine.end(), b, b + n); };
+	long long hdr[5] = {(long long)pb.bp, (long long)pb.ind, (long long)pb.ind_seq, (long long)c->inv_sites.size(), (long long)c->tnl_sites.size()};
+	put(hdr, sizeof(hdr));
+	tmp.resize((size_t)pb.bp * 8 + (size_t)pb.ind * sizeof(mc_indel_rec) + (size_t)pb.ind_seq);
+	bad = dev_d2h(tmp.data(), c->d_bp.p, (size_t)pb.bp * 8, s) || dev_d2h(tmp.data() + pb.bp * 8, c->d_ind.p, (size_t)pb.ind * sizeof(mc_indel_rec), s)
+	   || dev_d2h(tmp.data() + pb.bp * 8 + pb.ind * sizeof(mc_indel_rec), c->d_ind_seq.p, (size_t)pb.ind_seq, s) || dev_sync(s);
+	if (bad) { c->comm = keep; return MC_ERR_CUDA; }
+	put(tmp.data(), tmp.size());
+	put(c->inv_sites.data(), c->inv_sites.size() * sizeof(mc_site_rec)); put(c->tnl_sites.data(), c->tnl_sites.size() * sizeof(mc_site_rec));
+	if (allgather_bytes(c, mine, all)) { c->comm = keep; return MC_ERR_NCCL; }
+	c->comm = keep;
+	std::vector<int64_t> bp; std::vector<mc_indel_rec> ind; std::vector<uint8_t> seq; std::vector<mc_site_rec> inv, tnl;
+	for (size_t r = 0; r < all.size(); r++)
+	{
+		if (all[r].size() < sizeof(hdr)) continue;
+		long long h[5]; memcpy(h, all[r].data(), sizeof(h));
+		const uint8_t* p = all[r].data() + sizeof(h);
+		const size_t seq_base = seq.size();
+		bp.insert(bp.end(), (const int64_t*)p, (const int64_t*)p + h[0]); p += h[0] * 8;
+		for (long long i = 0; i < h[1]; i++) { mc_indel_rec x; memcpy(&x, p + i * sizeof(x), sizeof(x)); x.seq_off += (int32_t)seq_base; ind.push_back(x); }
+		p += h[1] * sizeof(mc_indel_rec);
+		seq.insert(seq.end(), p, p + h[2]); p += h[2];
+		inv.insert(inv.end(), (const mc_site_rec*)p, (const mc_site_rec*)p + h[3]); p += h[3] * sizeof(mc_site_rec);
+		tnl.insert(tnl.end(), (const mc_site_rec*)p, (const mc_site_rec*)p + h[4]);
+	}
+	if (seq.size() >= 0x7fffffffull) { mc_set_error("mc_profile_allreduce: merged indel sequences exceed 2 GiB"); return MC_ERR_OVERFLOW; }
+	bad = c->d_bp.reserve(bp.size() * 8 + 64) || c->d_ind.reserve(ind.size() * sizeof(mc_indel_rec) + 64) || c->d_ind_seq.reserve(seq.size() + 64);
+	bad = bad || dev_h2d(c->d_bp.p, bp.data(), bp.size() * 8, s) || dev_h2d(c->d_ind.p, ind.data(), ind.size() * sizeof(mc_indel_rec), s) || dev_h2d(c->d_ind_seq.p, seq.data(), seq.size(), s);
+	pb.bp = bp.size(); pb.ind = ind.size(); pb.ind_seq = seq.size();
+	bad = bad || dev_h2d(c->d_pbump.p, &pb, sizeof(pb), s) || dev_sync(s);
+	if (bad) return MC_ERR_CUDA;
+	c->bp_cap = c->d_bp.cap / 8; c->ind_cap = c->d_ind.cap / sizeof(mc_indel_rec); c->ind_seq_cap = c->d_ind_seq.cap;
+	c->inv_sites = inv; c->tnl_sites = tnl;
+	return MC_OK;
+}
+#endif
 
 int mc_bwt_search_batch(mc_ctx*, int64_t, const uint8_t*, const int64_t*, const int32_t*, int32_t*, int32_t*, uint64_t*) { mc_set_error("not implemented yet"); return MC_ERR_ARG; }
 // Operator-level entry: n independent gapped fills through dp_body (the kernel the pipeline uses).

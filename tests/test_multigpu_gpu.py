@@ -1,0 +1,74 @@
+"""Two contexts on two GPUs of one box: each maps its shard, mc_profile_allreduce (NCCL over NVLink) leaves the sum of both
+shard profiles on both ranks.  Checked against the CPU oracle run on the same two shards (as separate libraries)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    try:
+        return len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.strip().splitlines())
+    except OSError:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_two_gpu_shards_reduce_to_the_sum(built, tmp_path):
+    code = textwrap.dedent("""
+        import os, sys, pickle
+        import numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import torch, torch.distributed as dist
+        import parity_util as pu
+        from mapcaller_b200 import api, shard
+        rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+        torch.cuda.set_device(rank); dist.init_process_group('nccl')
+        case = pu.make_case(seed=61, n_pairs=8000, genome_len=120000, contigs=2, sv=2.0)
+        ix = pu.build_index(case)
+        seq, off = shard.take_shard(case['seq'], case['off'], world, rank)
+        ctx = api.Context(ix, paired=1, device=rank, shard_rank=rank, shard_count=world)
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        ctx.map_batch(seq, off)
+        ctx.profile_allreduce()
+        ins, dele = ctx.indels()
+        out = dict(profile=ctx.profile_columns(), totals=ctx.totals(), ins=ins, dele=dele, bp=ctx.breakpoints(), inv=sorted(ctx.sites(0)), tnl=sorted(ctx.sites(1)))
+        pickle.dump(out, open(%r + '/r%%d.pkl' %% rank, 'wb'))
+        dist.destroy_process_group()
+    """) % (ROOT, os.path.join(ROOT, "tests"), str(tmp_path))
+    script = tmp_path / "w.py"
+    script.write_text(code)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)])
+    import pickle
+    from collections import Counter
+    from mapcaller_b200 import shard
+    got = [pickle.load(open(str(tmp_path / ("r%d.pkl" % r)), "rb")) for r in range(2)]
+    case = pu.make_case(seed=61, n_pairs=8000, genome_len=120000, contigs=2, sv=2.0)
+    ix = pu.build_index(case)
+    parts = []
+    for r in range(2):
+        seq, off = shard.take_shard(case["seq"], case["off"], 2, r)
+        parts.append(pu.oracle_results(dict(case, seq=seq, off=off), ix, want_reads=False))
+    want = parts[0]["profile"].astype(np.int64) + parts[1]["profile"].astype(np.int64)
+    want[:, :5] = np.minimum(want[:, :5], 4095); want[:, 5] = np.minimum(want[:, 5], 5)
+    for g in got:                                           # both ranks hold the reduced profile
+        assert np.array_equal(g["profile"], want)
+        assert g["totals"]["total_reads"] == 16000
+        assert g["totals"]["total_paired"] == parts[0]["counters"]["paired"] + parts[1]["counters"]["paired"]
+        for key in ("ins", "dele"):
+            c = Counter()
+            for p in parts:
+                for pos, s, n in p[key]:
+                    c[(pos, s)] += n
+            assert sorted((k[0], k[1], v) for k, v in c.items()) == sorted(g[key])
+        assert sorted(g["inv"]) == sorted(parts[0]["inv"] + parts[1]["inv"])
+        assert sorted(g["tnl"]) == sorted(parts[0]["tnl"] + parts[1]["tnl"])
