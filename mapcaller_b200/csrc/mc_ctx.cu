@@ -9,7 +9,8 @@
 // whose true EstiDistance falls outside their interval.
 #include "mc_launch.h"
 #ifndef MC_HOSTEMU
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
 #endif
 
 #include <algorithm>
@@ -64,6 +65,54 @@ static void ev_create(mc_event_t* e) { cudaEventCreate(e); }
 static void ev_destroy(mc_event_t* e) { cudaEventDestroy(*e); }
 static void ev_record(mc_event_t* e, mc_stream_t s) { cudaEventRecord(*e, s); }
 static double ev_ms(mc_event_t* a, mc_event_t* b) { float ms = 0; cudaEventElapsedTime(&ms, *a, *b); return ms; }
+#endif
+
+#ifndef MC_HOSTEMU
+// NCCL is bound with dlopen at the first multi-GPU call instead of at link time: a process that also imports torch must end
+// up with ONE libnccl.so.2 (torch bundles a newer one than the system's and refuses to start on an older, already loaded copy).
+struct NcclApi {
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+	ncclResult_t (*CommDestroy)(ncclComm_t);
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+	const char* (*GetErrorString)(ncclResult_t);
+	bool ok;
+};
+static NcclApi* nccl_api()
+{
+	static NcclApi api; static bool tried = false;
+	if (!tried)
+	{
+		tried = true; api.ok = false;
+		void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (h)
+		{
+			*(void**)&api.GetUniqueId = dlsym(h, "ncclGetUniqueId"); *(void**)&api.CommInitRank = dlsym(h, "ncclCommInitRank");
+			*(void**)&api.CommDestroy = dlsym(h, "ncclCommDestroy"); *(void**)&api.AllReduce = dlsym(h, "ncclAllReduce");
+			*(void**)&api.AllGather = dlsym(h, "ncclAllGather"); *(void**)&api.Broadcast = dlsym(h, "ncclBroadcast");
+			*(void**)&api.GetErrorString = dlsym(h, "ncclGetErrorString");
+			api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Broadcast && api.GetErrorString;
+		}
+	}
+	if (!api.ok) { mc_set_error("libnccl.so.2 could not be loaded"); return nullptr; }
+	return &api;
+}
+static bool nccl_api_loaded() { return nccl_api() != nullptr; }
+static void nccl_destroy(ncclComm_t comm) { nccl_api()->CommDestroy(comm); }
+#define ncclGetUniqueId nccl_api()->GetUniqueId
+#define ncclCommInitRank nccl_api()->CommInitRank
+#define ncclAllReduce nccl_api()->AllReduce
+#define ncclAllGather nccl_api()->AllGather
+#define ncclBroadcast nccl_api()->Broadcast
+static int nccl_fail(ncclResult_t r, const char* what)
+{
+	if (r == ncclSuccess) return 0;
+	mc_set_error("NCCL error in %s: %s", what, nccl_api()->GetErrorString(r));
+	return -1;
+}
 #endif
 
 struct DBuf {
@@ -174,7 +223,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc};
 	for (HBuf* b : hb) b->release();
 #ifndef MC_HOSTEMU
-	if (c->comm) ncclCommDestroy(c->comm);
+	if (c->comm && nccl_api_loaded()) nccl_destroy(c->comm);
 #endif
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
 	c->h_bounce[0].release(); c->h_bounce[1].release();
@@ -768,15 +817,10 @@ int mc_comm_unique_id(uint8_t*) { mc_set_error("no NCCL in the developer harness
 int mc_comm_init(mc_ctx*, const uint8_t*, int32_t, int32_t) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
 int mc_profile_allreduce(mc_ctx*, void*) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
 #else
-static int nccl_fail(ncclResult_t r, const char* what)
-{
-	if (r == ncclSuccess) return 0;
-	mc_set_error("NCCL error in %s: %s", what, ncclGetErrorString(r));
-	return -1;
-}
 int mc_comm_unique_id(uint8_t* out)
 {
 	if (!out) { mc_set_error("mc_comm_unique_id: null argument"); return MC_ERR_ARG; }
+	if (!nccl_api()) return MC_ERR_NCCL;
 	ncclUniqueId id;
 	if (nccl_fail(ncclGetUniqueId(&id), "ncclGetUniqueId")) return MC_ERR_NCCL;
 	memcpy(out, &id, sizeof(id));
@@ -785,6 +829,7 @@ int mc_comm_unique_id(uint8_t* out)
 int mc_comm_init(mc_ctx* c, const uint8_t* id_bytes, int32_t rank, int32_t n_ranks)
 {
 	if (!c || !id_bytes || rank < 0 || rank >= n_ranks) { mc_set_error("mc_comm_init: bad argument"); return MC_ERR_ARG; }
+	if (!nccl_api()) return MC_ERR_NCCL;
 	cudaSetDevice(c->prm.device);
 	ncclUniqueId id; memcpy(&id, id_bytes, sizeof(id));
 	if (nccl_fail(ncclCommInitRank(&c->comm, n_ranks, id, rank), "ncclCommInitRank")) return MC_ERR_NCCL;
@@ -829,6 +874,7 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	if (!c) { mc_set_error("mc_profile_allreduce: null context"); return MC_ERR_ARG; }
 	ncclComm_t comm = nccl_comm ? (ncclComm_t)nccl_comm : c->comm;
 	if (!comm) { mc_set_error("mc_profile_allreduce: no communicator (call mc_comm_init first)"); return MC_ERR_NCCL; }
+	if (!nccl_api()) return MC_ERR_NCCL;
 	if (!c->prm.update_profile) { mc_set_error("mc_profile_allreduce: context was created without update_profile"); return MC_ERR_ARG; }
 	cudaSetDevice(c->prm.device);
 	cudaStream_t s = c->stream;
