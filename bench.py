@@ -255,7 +255,7 @@ def main():
     wall_pageable = time.perf_counter() - t0
     n_reads = 2 * n_pairs
     h2d = int(seq.nbytes + (n_reads + 1) * 8 + 5 * ((n_reads + 199) // 200))
-    d2h = int(n_pairs * 24 + ((n_reads + 199) // 200) * (32 + 8) + 64 + 64 + 8 * 4)
+    d2h = int(((n_reads + 199) // 200) * (32 + 8) + 72 + 64 + 8 * 4 + 40 * 2048)   # per-chunk sums + intervals, counters, cursors, the list of discordant pairs (<= ~2 k records here)
 
     if dist is not None:
         import torch

@@ -96,7 +96,7 @@ typedef struct {
     int32_t device;            /* CUDA device ordinal */
     int32_t shard_rank;        /* multi-GPU: this context's position in file order (0 when single) */
     int32_t shard_count;       /* multi-GPU: number of shards (1 when single) */
-    int32_t reserved[5];
+    int32_t reserved[5];       /* reserved[0] != 0: return the per-pair coordinates (mc_batch_out::pairs) even without want_alignments */
 } mc_params;
 
 void mc_params_default(mc_params *p);   /* defaults of reference src/main.cpp:159-191 */
@@ -129,7 +129,7 @@ typedef struct {
     const mc_cand_out *cands;      /* arena; index through reads[].cand_begin */
     const mc_frag_out *frags;      /* arena; index through cands[].frag_begin */
     const uint8_t *aln;            /* arena of alignment strings */
-    const mc_pair_out *pairs;      /* n_pairs (paired mode) */
+    const mc_pair_out *pairs;      /* n_pairs (paired mode, with want_alignments or reserved[0]) */
     const mc_chunk_out *chunks;    /* n_chunks */
     int32_t replays;               /* chunks re-run because the avgDist speculation missed (diagnostic) */
 } mc_batch_out;

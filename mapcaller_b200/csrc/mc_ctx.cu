@@ -14,6 +14,7 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -78,6 +79,8 @@ struct NcclApi {
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
 	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
 	const char* (*GetErrorString)(ncclResult_t);
+	ncclResult_t (*GroupStart)();
+	ncclResult_t (*GroupEnd)();
 	bool ok;
 };
 static NcclApi* nccl_api()
@@ -94,7 +97,8 @@ static NcclApi* nccl_api()
 			*(void**)&api.CommDestroy = dlsym(h, "ncclCommDestroy"); *(void**)&api.AllReduce = dlsym(h, "ncclAllReduce");
 			*(void**)&api.AllGather = dlsym(h, "ncclAllGather"); *(void**)&api.Broadcast = dlsym(h, "ncclBroadcast");
 			*(void**)&api.GetErrorString = dlsym(h, "ncclGetErrorString");
-			api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Broadcast && api.GetErrorString;
+			*(void**)&api.GroupStart = dlsym(h, "ncclGroupStart"); *(void**)&api.GroupEnd = dlsym(h, "ncclGroupEnd");
+			api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Broadcast && api.GetErrorString && api.GroupStart && api.GroupEnd;
 		}
 	}
 	if (!api.ok) { mc_set_error("libnccl.so.2 could not be loaded"); return nullptr; }
@@ -174,7 +178,8 @@ struct mc_ctx {
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
-	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask;
+	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc;
+	HBuf h_disc;
 	HBuf h_bounce[2];
 #ifndef MC_HOSTEMU
 	cudaEvent_t ev_bounce[2];
@@ -195,6 +200,7 @@ struct mc_ctx {
 	mc_event_t ev[EV_COUNT];
 #ifndef MC_HOSTEMU
 	ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;
+	DBuf d_comm_small, d_comm_buf; HBuf h_comm_buf;
 #endif
 };
 
@@ -216,14 +222,15 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc};
 	for (DBuf* b : bufs) b->release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
-	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc};
+	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc, &c->h_disc};
 	for (HBuf* b : hb) b->release();
 #ifndef MC_HOSTEMU
 	if (c->comm && nccl_api_loaded()) nccl_destroy(c->comm);
+	c->d_comm_small.release(); c->d_comm_buf.release(); c->h_comm_buf.release();
 #endif
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
 	c->h_bounce[0].release(); c->h_bounce[1].release();
@@ -590,8 +597,21 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		ev_record(&c->ev[EV_PROF1], s);
 
 		// ---- results back to the host ----
-		bad |= c->h_pairs.reserve((n_pairs + 1) * sizeof(mc_pair_out));
-		if (paired) bad |= dev_d2h(c->h_pairs.p, c->d_pair_out.p, n_pairs * sizeof(mc_pair_out), s);
+		const bool want_pairs = paired && (c->prm.want_alignments || c->prm.reserved[0]);
+		if (want_pairs) { bad |= c->h_pairs.reserve((n_pairs + 1) * sizeof(mc_pair_out)); bad |= dev_d2h(c->h_pairs.p, c->d_pair_out.p, n_pairs * sizeof(mc_pair_out), s); }
+		// the few pairs that are neither proper nor unanchored go to the host for the in-order SV-site bookkeeping
+		int64_t disc_cap = 0;
+		if (paired && c->prm.update_profile)
+		{
+			disc_cap = n_pairs;
+			bad |= c->d_disc.reserve((size_t)disc_cap * sizeof(DiscRec) + 64) || dev_zero(&db->key, 8, s);   // the gate-key cursor is free again
+			launch_disclist(a, n_pairs, c->d_disc.as<DiscRec>(), &db->key, disc_cap, s);
+			bad |= dev_d2h(h_small + 32, &db->key, 8, s) || dev_sync(s);
+			if (bad) return MC_ERR_CUDA;
+			const int64_t nd = std::min(h_small[32], disc_cap);
+			bad |= c->h_disc.reserve((size_t)nd * sizeof(DiscRec) + 64) || dev_d2h(c->h_disc.p, c->d_disc.p, (size_t)nd * sizeof(DiscRec), s);
+			h_small[33] = nd;
+		}
 		if (c->prm.want_alignments)
 		{
 			const size_t cb = (size_t)cand_total * 4;
@@ -625,12 +645,12 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		// pair classification that the reference does in file order with thread-local state (src/ReadMapping.cpp:486-522)
 		if (paired && c->prm.update_profile)
 		{
-			const mc_pair_out* hp = c->h_pairs.as<mc_pair_out>();
+			DiscRec* d = c->h_disc.as<DiscRec>(); const int64_t nd = h_small[33];
+			std::sort(d, d + nd, [](const DiscRec& x, const DiscRec& y) { return x.pair < y.pair; });
 			const int64_t G = c->G, twoG = 2 * c->G;
-			for (int64_t p = 0; p < n_pairs; p++)
+			for (int64_t k = 0; k < nd; k++)
 			{
-				const mc_pair_out& q = hp[p];
-				if (q.dist == 0 || q.gPos1 == -1 || q.gPos2 == -1) continue;
+				const mc_pair_out& q = d[k].v;
 				if (q.gPos1 < G && q.gPos2 >= G)
 				{
 					c->discord_dist = llabs(twoG - q.gPos1 - q.gPos2);
@@ -667,7 +687,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		c->dstats_last = *hst;
 
 		out->n_reads = n; out->n_pairs = n_pairs; out->n_chunks = n_chunks;
-		out->pairs = paired ? c->h_pairs.as<mc_pair_out>() : nullptr;
+		out->pairs = want_pairs ? c->h_pairs.as<mc_pair_out>() : nullptr; if (!want_pairs) out->n_pairs = 0;
 		out->chunks = c->chunks_final.data();
 		if (c->prm.want_alignments)
 		{
@@ -837,29 +857,26 @@ int mc_comm_init(mc_ctx* c, const uint8_t* id_bytes, int32_t rank, int32_t n_ran
 	return MC_OK;
 }
 
-// gathers variable-length byte records of every rank into every rank (sizes first, then one broadcast per rank)
-static int allgather_bytes(mc_ctx* c, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t> >& all)
+// gathers variable-length byte records of every rank into every rank: sizes first, then ONE padded all-gather
+static int allgather_bytes(mc_ctx* c, ncclComm_t comm, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t> >& all)
 {
 	const int n = c->comm_size; cudaStream_t s = c->stream;
-	DBuf d_sz, d_buf;
-	if (d_sz.reserve(8 * (n + 1))) return -1;
+	if (c->d_comm_small.reserve(8 * (n + 8))) return -1;
+	long long* d_sz = c->d_comm_small.as<long long>();
 	long long my = (long long)mine.size();
 	std::vector<long long> sz(n);
-	if (dev_h2d(d_sz.as<long long>() + n, &my, 8, s)) return -1;
-	if (nccl_fail(ncclAllGather(d_sz.as<long long>() + n, d_sz.p, 1, ncclInt64, c->comm, s), "ncclAllGather")) return -1;
-	if (dev_d2h(sz.data(), d_sz.p, 8 * n, s) || dev_sync(s)) return -1;
-	long long mx = 1; for (int r = 0; r < n; r++) mx = std::max(mx, sz[r]);
-	if (d_buf.reserve((size_t)mx)) return -1;
+	if (dev_h2d(d_sz + n, &my, 8, s)) return -1;
+	if (nccl_fail(ncclAllGather(d_sz + n, d_sz, 1, ncclInt64, comm, s), "ncclAllGather(sizes)")) return -1;
+	if (dev_d2h(sz.data(), d_sz, 8 * n, s) || dev_sync(s)) return -1;
+	long long mx = 16; for (int r = 0; r < n; r++) mx = std::max(mx, sz[r]);
+	mx = (mx + 15) & ~15ll;
+	if (c->d_comm_buf.reserve((size_t)mx * (n + 1)) || c->h_comm_buf.reserve((size_t)mx * n)) return -1;
+	uint8_t* d_all = c->d_comm_buf.as<uint8_t>(); uint8_t* d_mine = d_all + (size_t)mx * n;
+	if (dev_h2d(d_mine, mine.data(), mine.size(), s)) return -1;
+	if (nccl_fail(ncclAllGather(d_mine, d_all, (size_t)mx, ncclUint8, comm, s), "ncclAllGather(records)")) return -1;
+	if (dev_d2h(c->h_comm_buf.p, d_all, (size_t)mx * n, s) || dev_sync(s)) return -1;
 	all.assign(n, std::vector<uint8_t>());
-	for (int r = 0; r < n; r++)
-	{
-		if (sz[r] == 0) continue;
-		if (r == c->comm_rank && dev_h2d(d_buf.p, mine.data(), mine.size(), s)) return -1;
-		if (nccl_fail(ncclBroadcast(d_buf.p, d_buf.p, (size_t)sz[r], ncclUint8, r, c->comm, s), "ncclBroadcast")) return -1;
-		all[r].resize((size_t)sz[r]);
-		if (dev_d2h(all[r].data(), d_buf.p, (size_t)sz[r], s) || dev_sync(s)) return -1;
-	}
-	d_sz.release(); d_buf.release();
+	for (int r = 0; r < n; r++) all[r].assign(c->h_comm_buf.as<uint8_t>() + (size_t)mx * r, c->h_comm_buf.as<uint8_t>() + (size_t)mx * r + sz[r]);
 	return 0;
 }
 
@@ -880,27 +897,31 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	cudaStream_t s = c->stream;
 	const size_t G = (size_t)c->G;
 	int bad = 0;
+	const bool dbg = getenv("MC_DEBUG") != nullptr;
+	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_begin = now();
+	if (c->d_comm_small.reserve(8 * (c->comm_size + 8))) return MC_ERR_CUDA;
+	long long* d_tot = c->d_comm_small.as<long long>() + c->comm_size + 1;
+	long long t[5] = {c->tot.total_reads, c->tot.total_mapped, c->tot.total_paired, c->tot.total_distance, c->tot.read_length_sum};
+	if (dev_h2d(d_tot, t, sizeof(t), s)) return MC_ERR_CUDA;
+	nccl_api()->GroupStart();
 	// packed 2 x uint16 counters are summed as uint32 words: no carry can cross the halves while every column stays below 65536
 	bad |= nccl_fail(ncclAllReduce(c->d_base16.p, c->d_base16.p, G * 2, ncclUint32, ncclSum, comm, s), "ncclAllReduce(base16)");
 	bad |= nccl_fail(ncclAllReduce(c->d_sdiff.p, c->d_sdiff.p, (G + 1) * 4, ncclInt32, ncclSum, comm, s), "ncclAllReduce(sdiff)");
 	bad |= nccl_fail(ncclAllReduce(c->d_cdiff.p, c->d_cdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(cdiff)");
 	bad |= nccl_fail(ncclAllReduce(c->d_mdiff.p, c->d_mdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(mdiff)");
 	bad |= nccl_fail(ncclAllReduce(c->d_rcount.p, c->d_rcount.p, G, ncclUint8, ncclSum, comm, s), "ncclAllReduce(rcount)");
+	bad |= nccl_fail(ncclAllReduce(d_tot, d_tot, 5, ncclInt64, ncclSum, comm, s), "ncclAllReduce(totals)");
+	bad |= nccl_fail(nccl_api()->GroupEnd(), "ncclGroupEnd");
 	if (bad) return MC_ERR_NCCL;
 	mc_clamp_u8_kernel<<<(unsigned)((G + 255) / 256), 256, 0, s>>>(c->d_rcount.as<uint8_t>(), (int64_t)G, c->prm.max_dup);
-	// totals
-	DBuf d_t; if (d_t.reserve(5 * 8)) return MC_ERR_CUDA;
-	long long t[5] = {c->tot.total_reads, c->tot.total_mapped, c->tot.total_paired, c->tot.total_distance, c->tot.read_length_sum};
-	if (dev_h2d(d_t.p, t, sizeof(t), s)) return MC_ERR_CUDA;
-	if (nccl_fail(ncclAllReduce(d_t.p, d_t.p, 5, ncclInt64, ncclSum, comm, s), "ncclAllReduce(totals)")) return MC_ERR_NCCL;
-	if (dev_d2h(t, d_t.p, sizeof(t), s) || dev_sync(s)) return MC_ERR_CUDA;
-	d_t.release();
+	if (dev_d2h(t, d_tot, sizeof(t), s)) return MC_ERR_CUDA;   // completes with the next synchronize (record exchange below)
+	PersistBumps pb;
+	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s)) return MC_ERR_CUDA;
+	const double t_reduced = now();
 	c->tot.total_reads = t[0]; c->tot.total_mapped = t[1]; c->tot.total_paired = t[2]; c->tot.total_distance = t[3]; c->tot.read_length_sum = t[4];
 	if (c->tot.total_paired > 1000) c->tot.avg_dist = (uint32_t)(int)(1. * c->tot.total_distance / c->tot.total_paired + .5);
 	// variable-length records: every rank ends up with the records of all ranks, in rank (= file) order
-	ncclComm_t keep = c->comm; c->comm = comm;
-	PersistBumps pb;
-	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s)) { c->comm = keep; return MC_ERR_CUDA; }
 	std::vector<uint8_t> mine, tmp; std::vector<std::vector<uint8_t> > all;
 	auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; mine.insert(mine.end(), b, b + n); };
 	long long hdr[5] = {(long long)pb.bp, (long long)pb.ind, (long long)pb.ind_seq, (long long)c->inv_sites.size(), (long long)c->tnl_sites.size()};
@@ -908,11 +929,10 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	tmp.resize((size_t)pb.bp * 8 + (size_t)pb.ind * sizeof(mc_indel_rec) + (size_t)pb.ind_seq);
 	bad = dev_d2h(tmp.data(), c->d_bp.p, (size_t)pb.bp * 8, s) || dev_d2h(tmp.data() + pb.bp * 8, c->d_ind.p, (size_t)pb.ind * sizeof(mc_indel_rec), s)
 	   || dev_d2h(tmp.data() + pb.bp * 8 + pb.ind * sizeof(mc_indel_rec), c->d_ind_seq.p, (size_t)pb.ind_seq, s) || dev_sync(s);
-	if (bad) { c->comm = keep; return MC_ERR_CUDA; }
+	if (bad) return MC_ERR_CUDA;
 	put(tmp.data(), tmp.size());
 	put(c->inv_sites.data(), c->inv_sites.size() * sizeof(mc_site_rec)); put(c->tnl_sites.data(), c->tnl_sites.size() * sizeof(mc_site_rec));
-	if (allgather_bytes(c, mine, all)) { c->comm = keep; return MC_ERR_NCCL; }
-	c->comm = keep;
+	if (allgather_bytes(c, comm, mine, all)) return MC_ERR_NCCL;
 	std::vector<int64_t> bp; std::vector<mc_indel_rec> ind; std::vector<uint8_t> seq; std::vector<mc_site_rec> inv, tnl;
 	for (size_t r = 0; r < all.size(); r++)
 	{
@@ -928,13 +948,14 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 		tnl.insert(tnl.end(), (const mc_site_rec*)p, (const mc_site_rec*)p + h[4]);
 	}
 	if (seq.size() >= 0x7fffffffull) { mc_set_error("mc_profile_allreduce: merged indel sequences exceed 2 GiB"); return MC_ERR_OVERFLOW; }
-	bad = c->d_bp.reserve(bp.size() * 8 + 64) || c->d_ind.reserve(ind.size() * sizeof(mc_indel_rec) + 64) || c->d_ind_seq.reserve(seq.size() + 64);
+	bad = c->d_bp.grow_keep(bp.size() * 8 + 64, 0, s) || c->d_ind.grow_keep(ind.size() * sizeof(mc_indel_rec) + 64, 0, s) || c->d_ind_seq.grow_keep(seq.size() + 64, 0, s);
 	bad = bad || dev_h2d(c->d_bp.p, bp.data(), bp.size() * 8, s) || dev_h2d(c->d_ind.p, ind.data(), ind.size() * sizeof(mc_indel_rec), s) || dev_h2d(c->d_ind_seq.p, seq.data(), seq.size(), s);
 	pb.bp = bp.size(); pb.ind = ind.size(); pb.ind_seq = seq.size();
 	bad = bad || dev_h2d(c->d_pbump.p, &pb, sizeof(pb), s) || dev_sync(s);
 	if (bad) return MC_ERR_CUDA;
 	c->bp_cap = c->d_bp.cap / 8; c->ind_cap = c->d_ind.cap / sizeof(mc_indel_rec); c->ind_seq_cap = c->d_ind_seq.cap;
 	c->inv_sites = inv; c->tnl_sites = tnl;
+	if (dbg) fprintf(stderr, "[mc] rank %d allreduce: counters %.3f ms, records %.3f ms (%zu bytes mine)\n", c->comm_rank, t_reduced - t_begin, now() - t_reduced, mine.size());
 	return MC_OK;
 }
 #endif

@@ -16,6 +16,7 @@ typedef int mc_stream_t;
 static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a); }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
 static void launch_piece(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
+static void launch_disclist(const PipeArgs& a, int64_t n, DiscRec* out, mc_u64* bump, int64_t cap, mc_stream_t) { for (int64_t i = 0; i < n; i++) disclist_body(i, a, out, bump, cap); }
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, p, G, nb, sums); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
@@ -44,6 +45,10 @@ static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t s)
 	int64_t blocks = (n + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;   // 8 resident 256-thread blocks per SM
 	mc_locate_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
+__global__ void __launch_bounds__(MC_BLOCK) mc_disclist_kernel(const PipeArgs a, int64_t n, DiscRec* out, mc_u64* bump, int64_t cap)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) disclist_body(i, a, out, bump, cap); }
+static void launch_disclist(const PipeArgs& a, int64_t n, DiscRec* out, mc_u64* bump, int64_t cap, mc_stream_t s)
+{ if (n > 0) { mc_disclist_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n, out, bump, cap); g_launches++; } }
 // normal pieces: persistent warps over the current attempt's piece list
 __global__ void __launch_bounds__(MC_BLOCK) mc_piece_kernel(const PipeArgs a)
 {

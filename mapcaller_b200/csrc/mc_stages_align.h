@@ -458,6 +458,19 @@ MC_HD void pairstat_body(int64_t p, const PipeArgs& a)
 	a.pair_out[p] = o;
 }
 
+// pairs the host has to look at in file order (inversion / translocation candidates, src/ReadMapping.cpp:486-522):
+// everything that is neither unmapped / one-end-anchored nor a proper pair.  Run once, after the last attempt.
+struct DiscRec { int64_t pair; mc_pair_out v; };
+MC_HD void disclist_body(int64_t p, const PipeArgs& a, DiscRec* out, mc_u64* bump, int64_t cap)
+{
+	const mc_pair_out q = a.pair_out[p];
+	if (q.dist == 0 || q.gPos1 == -1 || q.gPos2 == -1) return;
+	const bool h1 = q.gPos1 < a.ix.G, h2 = q.gPos2 < a.ix.G;
+	if (h1 == h2 && q.dist <= 1000) return;
+	const int64_t k = (int64_t)mc_atomic_add(bump, (mc_u64)1);
+	if (k < cap) { DiscRec d; d.pair = p; d.v = q; out[k] = d; }
+}
+
 MC_HD void chunkstat_body(int64_t c, const PipeArgs& a)
 {
 	if (!a.active[c]) return;
