@@ -178,7 +178,7 @@ struct mc_ctx {
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
-	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc;
+	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off;
 	HBuf h_disc;
 	HBuf h_bounce[2];
 #ifndef MC_HOSTEMU
@@ -222,7 +222,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
 	for (DBuf* b : bufs) b->release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
@@ -424,7 +424,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	int bad = 0;
 	bad |= c->d_slot_freq.reserve(st.n_slots * 4) || c->d_seeds.reserve(st.n_slots * sizeof(Seed)) || c->d_slot_loc.reserve((st.n_slots + 1) * 8);
 	bad |= c->d_scan.reserve(device_scan_scratch_bytes(st.n_slots));
-	bad |= c->d_rflag.reserve(n + 1) || c->d_npair.reserve(n * 4) || c->d_ncand0.reserve(n * 4) || c->d_ncand.reserve(n * 4) || c->d_rsum.reserve(n * sizeof(ReadSum));
+	bad |= c->d_cand_off.reserve((n + 1) * 4) || c->d_rflag.reserve(n + 1) || c->d_npair.reserve(n * 4) || c->d_ncand0.reserve(n * 4) || c->d_ncand.reserve(n * 4) || c->d_rsum.reserve(n * sizeof(ReadSum));
 	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(n_chunks * sizeof(mc_chunk_out));
 	bad |= c->d_chunk_lo.reserve(n_chunks * 4) || c->d_chunk_hi.reserve(n_chunks * 4);
 	bad |= c->d_pair_flag.reserve((n_pairs + 1) * 4) || c->d_est_lo.reserve((n_pairs + 1) * 4) || c->d_est_hi.reserve((n_pairs + 1) * 4);
@@ -432,7 +432,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	bad |= c->h_chunk.reserve(n_chunks * sizeof(mc_chunk_out)) || c->h_chunk_lo.reserve(n_chunks * 4) || c->h_chunk_hi.reserve(n_chunks * 4);
 	if (bad) return MC_ERR_CUDA;
 	a.slot_freq = c->d_slot_freq.as<uint32_t>(); a.seeds = c->d_seeds.as<Seed>(); a.slot_loc = c->d_slot_loc.as<int64_t>();
-	a.rflag = c->d_rflag.as<uint8_t>(); a.npair = c->d_npair.as<int32_t>(); a.ncand0 = c->d_ncand0.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
+	a.cand_off = c->d_cand_off.as<int32_t>(); a.rflag = c->d_rflag.as<uint8_t>(); a.npair = c->d_npair.as<int32_t>(); a.ncand0 = c->d_ncand0.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
 	a.est = c->d_est.as<int32_t>(); a.active = c->d_active.as<uint8_t>(); a.chunk_out = c->d_chunk_out.as<mc_chunk_out>();
 	a.chunk_lo = c->d_chunk_lo.as<int32_t>(); a.chunk_hi = c->d_chunk_hi.as<int32_t>();
 	a.pair_flag = c->d_pair_flag.as<int32_t>(); a.est_lo = c->d_est_lo.as<int32_t>(); a.est_hi = c->d_est_hi.as<int32_t>();
@@ -467,13 +467,13 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		const int64_t aln_cap = (int64_t)(c->aln_factor * (double)st.n_bytes) + (1 << 20);
 		const int64_t dpws_cap = (int64_t)(c->dpws_factor * (double)st.n_bytes) + (8 << 20);
 		const int64_t task_cap = (int64_t)(c->task_factor * (double)n) + 1024;
-		if (frag_cap >= 0x7fffffffll || aln_cap >= 0x7fffffffll) { mc_set_error("mc_map_batch: batch too large for 32-bit arena offsets; split it"); return MC_ERR_ARG; }
-		bad |= c->d_loc_slot.reserve((n_locs + 1) * 4) || c->d_pairs.reserve(pair_cap * sizeof(SPair));
+		if (frag_cap >= 0x7fffffffll || aln_cap >= 0x7fffffffll || cand_total >= 0x7fffffffll) { mc_set_error("mc_map_batch: batch too large for 32-bit arena offsets; split it"); return MC_ERR_ARG; }
+		bad |= c->d_pairs.reserve(pair_cap * sizeof(SPair));
 		bad |= c->d_cands.reserve(cand_total * sizeof(Cand)) || c->d_cscore.reserve(cand_total * 4) || c->d_cpaired.reserve(cand_total * 4);
 		bad |= c->d_corient.reserve(cand_total * 4) || c->d_cfrag.reserve(cand_total * 4) || c->d_cnfrag.reserve(cand_total * 4) || c->d_ctmp.reserve(cand_total * 4);
 		bad |= c->d_ptask.reserve(frag_cap * 4) || c->d_frags.reserve(frag_cap * sizeof(mc_frag_out)) || c->d_aln.reserve(aln_cap) || c->d_tasks.reserve(task_cap * sizeof(DpTask)) || c->d_dpws.reserve(dpws_cap);
 		if (bad) return MC_ERR_CUDA;
-		a.loc_slot = c->d_loc_slot.as<int32_t>(); a.pairs = c->d_pairs.as<SPair>(); a.pair_cap = pair_cap;
+		a.pairs = c->d_pairs.as<SPair>(); a.pair_cap = pair_cap;
 		a.cands = c->d_cands.as<Cand>(); a.cscore = c->d_cscore.as<int32_t>(); a.cpaired = c->d_cpaired.as<int32_t>(); a.corient = c->d_corient.as<int32_t>();
 		a.cfrag = c->d_cfrag.as<int32_t>(); a.cnfrag = c->d_cnfrag.as<int32_t>(); a.ctmp = c->d_ctmp.as<int32_t>();
 		a.ptask = c->d_ptask.as<int32_t>(); a.frags = c->d_frags.as<mc_frag_out>(); a.frag_cap = frag_cap; a.aln = c->d_aln.as<uint8_t>(); a.aln_cap = aln_cap;
@@ -592,7 +592,9 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			device_sort_u64(q.keys, c->d_keys_tmp.as<uint64_t>(), q.n_keys, c->d_sort.p, c->d_sort.cap, s);
 			launch_gate(a, q, q.n_keys, s);
 			launch_gateupd(a, q, q.n_keys, s);
+			bad |= dev_zero(&db->ptask, 8, s);            // the piece list of the alignment stage is free again: reuse it
 			launch_scatter(a, q, n, s);
+			launch_profpiece(a, q, frag_cap, s);
 		}
 		ev_record(&c->ev[EV_PROF1], s);
 
@@ -694,16 +696,14 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			// rebuild the per-read candidate table from the device's structure-of-arrays
 			const size_t ct = (size_t)cand_total; const int32_t* hc = c->h_cands.as<int32_t>();
 			const int32_t *sc = hc, *pi = hc + ct, *ori = hc + 2 * ct, *fb = hc + 3 * ct, *nf = hc + 4 * ct;
-			// the candidate slice of a read is defined by its seed slots and their location offsets (pa_cand_off)
-			std::vector<int64_t> slot_loc(st.n_slots + 1), so(n + 1);
-			bad |= dev_d2h(slot_loc.data(), c->d_slot_loc.p, (st.n_slots + 1) * 8, s) || dev_d2h(so.data(), st.seed_off.p, (n + 1) * 8, s) || dev_sync(s);
+			// the candidate slice of every read inside the device arena
+			std::vector<int32_t> cand_off(n + 1);
+			bad |= dev_d2h(cand_off.data(), c->d_cand_off.p, n * 4, s) || dev_sync(s);
 			if (bad) return MC_ERR_CUDA;
 			c->cands_out.clear();
 			for (int64_t r = 0; r < n; r++)
 			{
-				int64_t co;
-				if (!paired) co = slot_loc[so[r]];
-				else { int64_t r0 = r & ~1ll; int64_t base = 2 * slot_loc[so[r0]]; co = (r & 1) ? base + (slot_loc[so[r0 + 2]] - slot_loc[so[r0]]) : base; }
+				const int64_t co = cand_off[r];
 				mc_read_out& ro = c->reads_out[r];
 				ro.cand_begin = (int32_t)c->cands_out.size();
 				for (int k = 0; k < ro.n_cand; k++)

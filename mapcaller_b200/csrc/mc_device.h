@@ -28,6 +28,7 @@ static inline int mc_popc(uint32_t x) { return __builtin_popcount(x); }
 #define MC_WARP_SYNC() do { } while (0)
 static inline int64_t mc_bcast64(int64_t v) { return v; }
 static inline int mc_warp_sum(int v) { return v; }
+static inline int mc_warp_max(int v) { return v; }
 static inline int mc_max3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
 #else
 #include <cuda_runtime.h>
@@ -41,14 +42,37 @@ static __device__ __forceinline__ unsigned long long mc_atomic_add(unsigned long
 static __device__ __forceinline__ uint32_t mc_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 static __device__ __forceinline__ int mc_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 static __device__ __forceinline__ void mc_atomic_or(unsigned long long* p, unsigned long long v) { atomicOr(p, v); }
+static __device__ __forceinline__ void mc_atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 static __device__ __forceinline__ int mc_popc(uint32_t x) { return __popc(x); }
 #define MC_WARP_SYNC() __syncwarp()
 static __device__ __forceinline__ int64_t mc_bcast64(int64_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 static __device__ __forceinline__ int mc_warp_sum(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
+static __device__ __forceinline__ int mc_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); } // DPX
 #endif
 
 typedef unsigned long long mc_u64; // atomicAdd-compatible 64-bit counter
+
+// Arena cursors are bumped by (nearly) every thread of a kernel.  Same-address atomics serialise in the L2 atomic unit
+// (about one lane per clock), so the lanes that arrive together first scan their sizes inside the warp and issue ONE
+// atomic for the group; each lane then owns [base + prefix, base + prefix + n).
+#ifdef MC_HOSTEMU
+static inline int64_t mc_bump_alloc(mc_u64* bump, uint32_t n) { mc_u64 o = *bump; *bump += n; return (int64_t)o; }
+#else
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+static __device__ __forceinline__ int64_t mc_bump_alloc(mc_u64* bump, uint32_t n)
+{
+	namespace cg = cooperative_groups;
+	cg::coalesced_group g = cg::coalesced_threads();
+	const uint32_t pre = cg::exclusive_scan(g, n);
+	const uint32_t total = g.shfl(pre + n, g.size() - 1);
+	mc_u64 base = 0;
+	if (g.thread_rank() == 0) base = atomicAdd(bump, (mc_u64)total);
+	base = g.shfl(base, 0);
+	return (int64_t)(base + pre);
+}
+#endif
 
 // Statistics counters are hit by every thread of a kernel: summing inside the warp first leaves one atomic per warp
 // instead of 32 same-address atomics (which serialise in the L2 atomic unit).

@@ -16,7 +16,7 @@
 #define MC_NW_NEG (-131072)
 
 template <bool KSW>
-static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask tk, const int lane)
+static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask tk, const int lane, uint32_t& cells)
 {
 	const unsigned full = 0xffffffffu;
 	mc_frag_out& x = a.frags[tk.frag];
@@ -131,8 +131,7 @@ static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask 
 			}
 		}
 		x.aln_len = len;
-		mc_atomic_add(&a.st->dp_cells, (mc_u64)((int64_t)m * n));
-		mc_atomic_add(&a.st->dp_tasks, (mc_u64)1);
+		cells += (uint32_t)(m * n);
 	}
 }
 
@@ -142,12 +141,15 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_dp_kernel(const PipeArgs a)
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
 	int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
+	uint32_t cells = 0, tasks = 0;     // lane 0 of the warp counts, one atomic per warp at the end
 	for (int64_t t = a.task_begin + warp; t < end; t += n_warps)
 	{
 		const DpTask tk = a.tasks[t];
-		if (a.pr.alg_ksw2) dpw_task<true>(a, tk, lane); else dpw_task<false>(a, tk, lane);
+		if (a.pr.alg_ksw2) dpw_task<true>(a, tk, lane, cells); else dpw_task<false>(a, tk, lane, cells);
+		tasks++;
 		__syncwarp();
 	}
+	if (lane == 0 && tasks) { atomicAdd(&a.st->dp_cells, (mc_u64)cells); atomicAdd(&a.st->dp_tasks, (mc_u64)tasks); }
 }
 static void launch_dp(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {

@@ -15,7 +15,9 @@ typedef int mc_stream_t;
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
 static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a); }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
-static void launch_piece(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
+static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin; for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
+static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
+static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump; for (int64_t i = 0; i < n; i++) a.st->profile_atomics += profpiece_body(i, 0, 1, a, q); }
 static void launch_disclist(const PipeArgs& a, int64_t n, DiscRec* out, mc_u64* bump, int64_t cap, mc_stream_t) { for (int64_t i = 0; i < n; i++) disclist_body(i, a, out, bump, cap); }
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, p, G, nb, sums); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
@@ -49,6 +51,14 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_disclist_kernel(const PipeArgs a,
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) disclist_body(i, a, out, bump, cap); }
 static void launch_disclist(const PipeArgs& a, int64_t n, DiscRec* out, mc_u64* bump, int64_t cap, mc_stream_t s)
 { if (n > 0) { mc_disclist_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n, out, bump, cap); g_launches++; } }
+// one warp per 200-read chunk
+__global__ void __launch_bounds__(MC_BLOCK) mc_chunkstat_kernel(const PipeArgs a, int64_t n)
+{
+	const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+	if (w < n) chunkstat_body(w, threadIdx.x & 31, 32, a);
+}
+static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_chunkstat_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
 // normal pieces: persistent warps over the current attempt's piece list
 __global__ void __launch_bounds__(MC_BLOCK) mc_piece_kernel(const PipeArgs a)
 {
@@ -99,11 +109,27 @@ MC_LAUNCH1(dp)
 #endif
 MC_LAUNCH1(alnfin)
 MC_LAUNCH1(pairstat)
-MC_LAUNCH1(chunkstat)
 MC_LAUNCH2(profkey)
 MC_LAUNCH2(gate)
 MC_LAUNCH2(gateupd)
 MC_LAUNCH2(scatter)
+#ifndef MC_HOSTEMU
+// persistent warps over the pieces queued by mc_scatter_kernel
+__global__ void __launch_bounds__(MC_BLOCK) mc_profpiece_kernel(const PipeArgs a, const ProfArgs q)
+{
+	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	const int64_t n = (int64_t)*a.ptask_bump;
+	int natom = 0;
+	for (int64_t t = warp; t < n; t += n_warps) { natom += profpiece_body(t, threadIdx.x & 31, 32, a, q); __syncwarp(); }
+	mc_stat_add(&a.st->profile_atomics, (uint32_t)natom);
+}
+static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t max_tasks, mc_stream_t s)
+{
+	if (max_tasks <= 0) return;
+	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
+	mc_profpiece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a, q); g_launches++;
+}
+#endif
 
 // ---- exclusive scan uint32 -> int64 (out has n + 1 entries) -----------------------------------------
 #ifdef MC_HOSTEMU

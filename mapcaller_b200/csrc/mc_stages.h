@@ -36,7 +36,6 @@ struct PipeArgs {
 	Seed* seeds;
 	uint32_t* slot_freq;     // per slot: number of locations (0 = unused slot)
 	const int64_t* slot_loc; // exclusive scan of slot_freq, n_slots + 1
-	int32_t* loc_slot;       // per location: its slot
 	int64_t n_slots, n_locs;
 	// simple pairs: [pair_off(r), ...) with pair_off(r) = slot_loc[seed_off[r]]; rescue seeds appended after n_locs
 	SPair* pairs;
@@ -46,6 +45,7 @@ struct PipeArgs {
 	mc_u64* pair_bump;       // next free rescue pair
 	// candidates: read r owns [cand_off(r), cand_off(r) + cand_cap(r))
 	Cand* cands;
+	int32_t* cand_off;       // per read: first candidate slot (written by the cluster stage)
 	int32_t* ncand0;         // per read: clusters found (immutable after cluster stage)
 	int32_t* ncand;          // per read: clusters + rescued candidates of the current attempt
 	int32_t* cscore;         // per cand: live score of the current attempt
@@ -80,13 +80,14 @@ struct PipeArgs {
 };
 
 MC_HD int64_t pa_pair_off(const PipeArgs& a, int64_t r) { return a.slot_loc[a.seed_off[r]]; }
-MC_HD int64_t pa_cand_off(const PipeArgs& a, int64_t r)
+MC_HD int64_t pa_cand_off_compute(const PipeArgs& a, int64_t r)
 {
 	if (!a.pr.paired) return pa_pair_off(a, r);
 	int64_t r0 = r & ~1ll;
 	int64_t base = 2 * pa_pair_off(a, r0);
 	return (r & 1) ? base + (pa_pair_off(a, r0 + 2 <= a.n_reads ? r0 + 2 : a.n_reads) - pa_pair_off(a, r0)) : base;
 }
+MC_HD int64_t pa_cand_off(const PipeArgs& a, int64_t r) { return a.cand_off[r]; }
 MC_HD int pa_cand_cap(const PipeArgs& a, int64_t r)
 {
 	if (!a.pr.paired) return (int)(pa_pair_off(a, r + 1) - pa_pair_off(a, r));
@@ -171,12 +172,15 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 	if (nblk) mc_stat_add(&a.st->seed_blocks, (uint32_t)(nblk));
 }
 
-// one thread per slot writes its slot id over its locations
+// one thread per slot lays out its locations: read offset, length and - in the place of the genome position - the BWT row
+// the location starts from, so that the locate kernel needs a single 16-byte load per location
 MC_HD void expand_body(int64_t s, const PipeArgs& a)
 {
-	uint32_t f = a.slot_freq[s];
-	int64_t o = a.slot_loc[s];
-	for (uint32_t i = 0; i < f; i++) a.loc_slot[o + i] = (int32_t)s;
+	const uint32_t f = a.slot_freq[s];
+	if (!f) return;
+	const int64_t o = a.slot_loc[s];
+	const Seed sd = a.seeds[s];
+	for (uint32_t i = 0; i < f; i++) { SPair p; p.gpos = (int64_t)(sd.x0 + i); p.rpos = sd.rpos; p.len = sd.len; a.pairs[o + i] = p; }
 }
 
 // Locations: every lane walks LF steps (bwt_sa, src/bwt_search.cpp:109-119) and, the moment its row is a sampled one,
@@ -187,9 +191,8 @@ MC_HD void locate_body(int64_t tid, int64_t nthreads, const PipeArgs& a)
 	int64_t t = tid;
 	if (t >= a.n_locs) return;
 	uint32_t nblk = 0, nsa = 0;
-	int32_t s = a.loc_slot[t];
-	Seed sd = a.seeds[s];
-	uint64_t k = sd.x0 + (uint64_t)(t - a.slot_loc[s]), steps = 0;
+	SPair p = a.pairs[t];
+	uint64_t k = (uint64_t)p.gpos, steps = 0;
 	bool live = true;
 	while (live)
 	{
@@ -197,14 +200,14 @@ MC_HD void locate_body(int64_t tid, int64_t nthreads, const PipeArgs& a)
 		{
 			// the seed carries the rows of its reverse complement: an occurrence of that at q is the seed at 2G - q - len
 			const uint64_t q = steps + mc_ldg(a.ix.sa + (k >> 5));
-			const uint64_t g = (uint64_t)a.ix.twoG - q - (uint64_t)sd.len;
-			SPair p; p.gpos = (int64_t)g; p.rpos = sd.rpos;
-			p.len = ((int64_t)g - (int64_t)sd.rpos > 0) ? sd.len : 0;   // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
+			const int64_t g = (int64_t)((uint64_t)a.ix.twoG - q - (uint64_t)p.len);
+			p.gpos = g;
+			if (g - (int64_t)p.rpos <= 0) p.len = 0;                    // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
 			a.pairs[t] = p;
 			nsa++;
 			t += nthreads;
 			live = t < a.n_locs;
-			if (live) { s = a.loc_slot[t]; sd = a.seeds[s]; k = sd.x0 + (uint64_t)(t - a.slot_loc[s]); steps = 0; }
+			if (live) { p = a.pairs[t]; k = (uint64_t)p.gpos; steps = 0; }
 		}
 		if (live && (k & 31)) { k = mc_lf_step(a.ix, k); steps++; nblk++; }
 	}
@@ -237,7 +240,8 @@ MC_HD void cluster_body(int64_t r, const PipeArgs& a)
 		v[j + 1] = x;
 	}
 	a.npair[r] = m;
-	const int64_t co = pa_cand_off(a, r);
+	const int64_t co = pa_cand_off_compute(a, r);
+	a.cand_off[r] = (int32_t)co;
 	int nc = 0;
 	if (m > 0)
 	{

@@ -39,7 +39,7 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 		const Cand c = a.cands[co + ci];
 		const int ns = c.pend - c.pbeg;
 		const int cap = 2 * ns + 1;
-		const int64_t fb = (int64_t)mc_atomic_add(a.frag_bump, (mc_u64)cap);
+		const int64_t fb = mc_bump_alloc(a.frag_bump, (uint32_t)cap);
 		if (fb + cap > a.frag_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 8); a.cscore[co + ci] = 0; continue; }
 		mc_frag_out* f = a.frags + fb;
 		// seeds sorted by (rPos, gPos), written into the upper half so the final list can be built in place below
@@ -116,9 +116,9 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 		for (int i = 0; i < nf; i++) if (!f[i].bSimple) { need += 2 * (f[i].rLen + f[i].gLen); np++; }
 		if (np)
 		{
-			int64_t ab = (int64_t)mc_atomic_add(a.aln_bump, (mc_u64)need);
+			int64_t ab = mc_bump_alloc(a.aln_bump, (uint32_t)need);
 			if (ab + need > a.aln_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 16); a.cscore[co + ci] = 0; continue; }
-			const int64_t pt = (int64_t)mc_atomic_add(a.ptask_bump, (mc_u64)np);   // pieces never outnumber fragments: the list has frag_cap entries
+			const int64_t pt = mc_bump_alloc(a.ptask_bump, (uint32_t)np);   // pieces never outnumber fragments: the list has frag_cap entries
 			int k = 0;
 			for (int i = 0; i < nf; i++)
 			{
@@ -143,8 +143,7 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 // ------------------------------------------------------------------------------------------------
 MC_HD void piece_body(int64_t t, int lane, int nl, const PipeArgs& a)
 {
-	if (a.ptask_begin + t >= (int64_t)*a.ptask_bump) return;
-	const int32_t fi = a.ptask[a.ptask_begin + t];
+	const int32_t fi = a.ptask[a.ptask_begin + t];   // the caller bounds t by the list's cursor
 	const mc_frag_out x = a.frags[fi];
 	const uint8_t* rs = a.seq + a.roff[x.pad];
 	uint8_t* a1 = a.aln + x.aln_off; uint8_t* a2 = a1 + x.aln_cap;
@@ -471,17 +470,17 @@ MC_HD void disclist_body(int64_t p, const PipeArgs& a, DiscRec* out, mc_u64* bum
 	if (k < cap) { DiscRec d; d.pair = p; d.v = q; out[k] = d; }
 }
 
-MC_HD void chunkstat_body(int64_t c, const PipeArgs& a)
+MC_HD void chunkstat_body(int64_t c, int lane, int nl, const PipeArgs& a)
 {
 	if (!a.active[c]) return;
 	const int64_t rb = c * MC_CHUNK_READS;
 	int64_t re = rb + MC_CHUNK_READS; if (re > a.n_reads) re = a.n_reads;
-	mc_chunk_out o; o.n_reads = (int32_t)(re - rb); o.mapped = 0; o.paired = 0; o.est_distance = a.pr.paired ? a.est[c] : 0; o.dist_sum = 0; o.len_sum = 0;
+	int mapped = 0, paired = 0, dsum = 0, lsum = 0;   // a chunk holds 100 pairs with dist <= 1000: the sums fit an int
 	int lo = -2147483647, hi = 2147483647;
-	for (int64_t r = rb; r < re; r++) if (a.rsum[r].score > 0) o.mapped++;
+	for (int64_t r = rb + lane; r < re; r += nl) if (a.rsum[r].score > 0) mapped++;
 	if (a.pr.paired)
 	{
-		for (int64_t p = rb / 2; p < re / 2; p++)
+		for (int64_t p = rb / 2 + lane; p < re / 2; p += nl)
 		{
 			if (a.est_lo[p] > lo) lo = a.est_lo[p];
 			if (a.est_hi[p] < hi) hi = a.est_hi[p];
@@ -490,11 +489,17 @@ MC_HD void chunkstat_body(int64_t c, const PipeArgs& a)
 			const bool h1 = q.gPos1 < a.ix.G, h2 = q.gPos2 < a.ix.G;
 			if (h1 != h2) continue;                 // inversion candidates (handled on the host in file order)
 			if (q.dist > 1000) continue;            // translocation candidates (MinTranslocationSize)
-			o.paired++; o.dist_sum += q.dist;
-			o.len_sum += (a.roff[2 * p + 1] - a.roff[2 * p]) + (a.roff[2 * p + 2] - a.roff[2 * p + 1]);
+			paired++; dsum += (int)q.dist;
+			lsum += (int)((a.roff[2 * p + 1] - a.roff[2 * p]) + (a.roff[2 * p + 2] - a.roff[2 * p + 1]));
 		}
 	}
-	a.chunk_out[c] = o; a.chunk_lo[c] = lo; a.chunk_hi[c] = hi;
+	mapped = mc_warp_sum(mapped); paired = mc_warp_sum(paired); dsum = mc_warp_sum(dsum); lsum = mc_warp_sum(lsum);
+	lo = mc_warp_max(lo); hi = -mc_warp_max(-hi);
+	if (lane == 0)
+	{
+		mc_chunk_out o; o.n_reads = (int32_t)(re - rb); o.mapped = mapped; o.paired = paired; o.est_distance = a.pr.paired ? a.est[c] : 0; o.dist_sum = dsum; o.len_sum = lsum;
+		a.chunk_out[c] = o; a.chunk_lo[c] = lo; a.chunk_hi[c] = hi;
+	}
 }
 
 #endif

@@ -94,7 +94,7 @@ MC_HD void pair_body(int64_t p, const PipeArgs& a)
 		else
 		{
 			lo = est; hi = est;
-			int64_t k = (int64_t)mc_atomic_add(a.rtask_bump, (mc_u64)1);
+			int64_t k = mc_bump_alloc(a.rtask_bump, 1u);
 			a.rtask[k] = (int32_t)p;
 		}
 	}
@@ -199,7 +199,7 @@ MC_HD int rescue_scan_diag(const PipeArgs& a, const KmerEnt* km, int nk, int64_t
 // walked exactly, (3) the best diagonal is reduced over the lanes, (4) lane 0 appends the candidate.
 // All lanes return the same value.
 MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const KmerEnt* km, int nk, int rlen, int64_t left, int64_t right,
-                      int floor_score, int anchor_idx, uint32_t* hits, int32_t* lanebuf, int32_t* new_idx)
+                      int floor_score, int anchor_idx, uint32_t* hits, int32_t* lanebuf, const uint32_t* bloom, int32_t* new_idx)
 {
 	if (right > a.ix.twoG) right = a.ix.twoG;
 	int i1 = mc_chrom_lower_bound(a.ix, left), i2 = mc_chrom_lower_bound(a.ix, right);
@@ -212,7 +212,12 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const Kme
 	for (int i = lane; i < ndiag; i += nl) hits[i] = 0;
 	MC_WARP_SYNC();
 	{
-		// each lane owns a contiguous run of window positions so the reference word can be rolled
+		// pass 1: each lane owns a contiguous run of window positions (so the reference word can be rolled) and keeps the
+		// positions whose word passes the filter; pass 2: the warp takes the survivors one by one and all lanes compare them
+		// with the read's words (a per-lane inner loop would stall the whole warp on one lane's false positive)
+		uint32_t* clist = (uint32_t*)(bloom + 128); int32_t* ccount = lanebuf + 2 * nl + 2;
+		if (lane == 0) *ccount = 0;
+		MC_WARP_SYNC();
 		const int npos = slen - 7, per = (npos + nl - 1) / nl;
 		int g0 = lane * per, g1 = g0 + per; if (g1 > npos) g1 = npos;
 		int64_t last_g = -10; uint32_t last_wid = 0;
@@ -220,7 +225,15 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const Kme
 		{
 			if (left + g < 0) continue;
 			const uint32_t w = ref_kmer_id(a, left + g, &last_g, &last_wid);
-			for (int i = 0; i < nk; i++) if (km[i].wid == w) mc_atomic_add(&hits[g - km[i].label - dmin], 1u);
+			if (!((bloom[(w & 4095) >> 5] >> (w & 31)) & 1)) continue;   // no word of the read ends in these six bases
+			clist[mc_atomic_add(ccount, 1)] = ((uint32_t)g << 16) | (w & 0xFFFFu);
+		}
+		MC_WARP_SYNC();
+		const int nc = *ccount;
+		for (int c = 0; c < nc; c++)
+		{
+			const uint32_t e = clist[c]; const int g = (int)(e >> 16); const uint32_t w = e & 0xFFFFu;
+			for (int i = lane; i < nk; i += nl) if (km[i].wid == w) mc_atomic_add(&hits[g - km[i].label - dmin], 1u);
 		}
 	}
 	MC_WARP_SYNC();
@@ -286,18 +299,21 @@ MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
 	// scratch in the (still unused) gapped-fill workspace: both word lists, the diagonal histogram, the lane buffer
 	const int lmax = l0 > l1 ? l0 : l1;
 	const int64_t n_hits = (int64_t)(uint32_t)est + 3 * (int64_t)lmax + 16;
-	const int64_t wsn = ((int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (2 * nl + 2) * 4 + 15) & ~15ll;
+	const int64_t wsn = ((int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (2 * nl + 4) * 4 + 128 * 4 + n_hits * 4 + 15) & ~15ll;
 	int64_t ws = 0;
 	if (lane == 0) ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
 	ws = mc_bcast64(ws);
 	if (ws + wsn > a.dpws_cap) { if (lane == 0) mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
 	KmerEnt* km0 = (KmerEnt*)(a.dpws + ws); KmerEnt* km1 = km0 + l0 + 1;
 	uint32_t* hits = (uint32_t*)(km1 + l1 + 1); int32_t* lanebuf = (int32_t*)(hits + n_hits);
+	uint32_t* bloom = (uint32_t*)(lanebuf + 2 * nl + 4);   // 4096-bit filter over the low 12 bits of the read's word ids
 	if (strat == 1 || strat == 3) // place mate 2 next to mate 1's candidates
 	{
+		for (int i = lane; i < 128; i += nl) bloom[i] = 0;
 		if (lane == 0) lanebuf[0] = kmer_list_of_read(a.seq + a.roff[r1], l1, km1);
 		MC_WARP_SYNC();
 		const int nk = lanebuf[0];
+		for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km1[i].wid & 4095) >> 5], 1u << (km1[i].wid & 31));
 		MC_WARP_SYNC();
 		const int thr = b0 >> 1;
 		for (int i = 0; i < n0; i++)
@@ -305,15 +321,17 @@ MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
 			if (s0[i] < thr || p0[i] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c0 + i]);
 			int32_t k;
-			if (rescue_try(a, lane, nl, r1, km1, nk, l1, d, d + (int64_t)(uint32_t)est + l1, b1, i, hits, lanebuf, &k)) { if (lane == 0) p0[i] = k; rescued++; }
+			if (rescue_try(a, lane, nl, r1, km1, nk, l1, d, d + (int64_t)(uint32_t)est + l1, b1, i, hits, lanebuf, bloom, &k)) { if (lane == 0) p0[i] = k; rescued++; }
 			MC_WARP_SYNC();
 		}
 	}
 	if (strat == 2 || strat == 3) // place mate 1 next to mate 2's candidates
 	{
+		for (int i = lane; i < 128; i += nl) bloom[i] = 0;
 		if (lane == 0) lanebuf[0] = kmer_list_of_read(a.seq + a.roff[r0], l0, km0);
 		MC_WARP_SYNC();
 		const int nk = lanebuf[0];
+		for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km0[i].wid & 4095) >> 5], 1u << (km0[i].wid & 31));
 		MC_WARP_SYNC();
 		const int thr = b1 >> 1;
 		const int n1_now = a.ncand[r1];
@@ -322,7 +340,7 @@ MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
 			if (s1[j] < thr || p1[j] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c1 + j]);
 			int32_t k;
-			if (rescue_try(a, lane, nl, r0, km0, nk, l0, d - (int64_t)(uint32_t)est, d + l0, b0, j, hits, lanebuf, &k)) { if (lane == 0) p1[j] = k; rescued++; }
+			if (rescue_try(a, lane, nl, r0, km0, nk, l0, d - (int64_t)(uint32_t)est, d + l0, b0, j, hits, lanebuf, bloom, &k)) { if (lane == 0) p1[j] = k; rescued++; }
 			MC_WARP_SYNC();
 		}
 	}

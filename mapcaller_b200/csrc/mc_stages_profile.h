@@ -54,7 +54,7 @@ MC_HD void profkey_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 	}
 	const int64_t start = a.corient[co + ci] ? first.gPos : a.ix.twoG - (first.gPos + first.gLen);
 	if (start < 0 || start >= a.ix.G) return; // the reference would index outside MappingRecordArr
-	const int64_t k = (int64_t)mc_atomic_add(q.key_bump, (mc_u64)1);
+	const int64_t k = mc_bump_alloc(q.key_bump, 1u);
 	q.keys[k] = ((uint64_t)start << MC_KEY_SHIFT) | (uint64_t)r;
 }
 
@@ -97,8 +97,8 @@ MC_HD int base_field(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' 
 
 MC_HD void indel_emit(const PipeArgs& a, const ProfArgs& q, int kind, int64_t pos, const uint8_t* s, int len)
 {
-	const int64_t k = (int64_t)mc_atomic_add(q.ind_bump, (mc_u64)1);
-	const int64_t o = (int64_t)mc_atomic_add(q.ind_seq_bump, (mc_u64)len);
+	const int64_t k = mc_bump_alloc(q.ind_bump, 1u);
+	const int64_t o = mc_bump_alloc(q.ind_seq_bump, (uint32_t)len);
 	if (k >= q.ind_cap || o + len > q.ind_seq_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 48); return; }
 	mc_indel_rec rec; rec.pos = pos; rec.kind = kind; rec.len = len; rec.count = 1; rec.seq_off = (int32_t)o;
 	q.ind[k] = rec;
@@ -169,7 +169,28 @@ MC_HD void scatter_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 		// note: an emptied clip piece (rLen == gLen == 0) also lands here and registers an empty insertion string, as the reference does (:121)
 		if (x.gLen == 0) { indel_emit(a, q, 0, (fwd ? x.gPos : a.ix.twoG - x.gPos) - 1, a1, x.aln_len); continue; }
 		if (x.rLen == 0) { indel_emit(a, q, 1, (fwd ? x.gPos : a.ix.twoG - x.gPos - x.gLen) - 1, a2, x.aln_len); continue; }
-		int64_t g = fwd ? x.gPos : a.ix.twoG - (x.gPos + x.gLen);
+		// pieces with aligned columns are left to profpiece_body (a warp per piece): queue the fragment
+		a.ptask[mc_bump_alloc(a.ptask_bump, 1u)] = a.cfrag[co + ci] + k;
+	}
+	mc_stat_add(&a.st->profile_columns, (uint32_t)(2 * rlen));
+	mc_stat_add(&a.st->profile_atomics, (uint32_t)(natom));
+}
+
+// `nl` lanes (a warp) count the columns of one gapped / mismatching piece of an accepted read: pieces without gaps go lane
+// by lane over consecutive columns, pieces with gaps are walked by one lane (UpdateProfile, src/AlignmentProfile.cpp:135-166)
+MC_HD int profpiece_body(int64_t t, int lane, int nl, const PipeArgs& a, const ProfArgs& q)
+{
+	const mc_frag_out x = a.frags[a.ptask[t]];
+	const bool fwd = x.gPos < a.ix.G;
+	const uint8_t* a1 = a.aln + x.aln_off; const uint8_t* a2 = a1 + x.aln_cap;
+	int64_t g = fwd ? x.gPos : a.ix.twoG - (x.gPos + x.gLen);
+	int natom = 0;
+	if (x.aln_len == x.rLen && x.aln_len == x.gLen)
+	{
+		for (int j = lane; j < x.aln_len; j += nl) { const int b = base_field(a1[j]); if (b >= 0) { prof_base(a, g + j, b); natom++; } }
+	}
+	else if (lane == 0)
+	{
 		for (int j = 0; j < x.aln_len;)
 		{
 			if (a2[j] == '-')
@@ -185,8 +206,7 @@ MC_HD void scatter_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 			else { int b = base_field(a1[j]); if (b >= 0) { prof_base(a, g, b); natom++; } j++; g++; }
 		}
 	}
-	mc_stat_add(&a.st->profile_columns, (uint32_t)(2 * rlen));
-	mc_stat_add(&a.st->profile_atomics, (uint32_t)(natom));
+	return natom;   // summed per warp by the caller
 }
 
 // ---- read-out: difference arrays -> MappingRecord_t ------------------------------------------------------------
