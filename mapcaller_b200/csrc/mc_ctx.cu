@@ -159,7 +159,7 @@ enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_P
 struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
-struct Staged { DBuf seq, roff, seed_off; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false; };
+struct Staged { DBuf seq, roff, seed_off, cap, scan; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false; };
 
 struct mc_ctx {
 	mc_params prm;
@@ -173,7 +173,8 @@ struct mc_ctx {
 	DBuf d_bp, d_ind, d_ind_seq, d_pbump;
 	int64_t bp_cap = 0, ind_cap = 0, ind_seq_cap = 0;
 	// batch arenas
-	Staged cur; Staged slots[4];
+	Staged cur; Staged pipe[2]; Staged slots[4];
+	std::vector<mc_chunk_out> chunks_all;
 	DBuf d_slot_freq, d_seeds, d_slot_loc, d_loc_slot, d_pairs, d_npair;
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
@@ -181,8 +182,9 @@ struct mc_ctx {
 	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off;
 	HBuf h_disc;
 	HBuf h_bounce[2];
+	mc_stream_t cstream;
 #ifndef MC_HOSTEMU
-	cudaEvent_t ev_bounce[2];
+	cudaEvent_t ev_bounce[2], ev_staged[2];
 #endif
 	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
@@ -224,8 +226,8 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
 	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
 	for (DBuf* b : bufs) b->release();
-	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
-	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); }
+	Staged* st[] = {&c->cur, &c->pipe[0], &c->pipe[1], &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
+	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); }
 	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc, &c->h_disc};
 	for (HBuf* b : hb) b->release();
 #ifndef MC_HOSTEMU
@@ -235,7 +237,8 @@ void mc_ctx_destroy(mc_ctx* c)
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
 	c->h_bounce[0].release(); c->h_bounce[1].release();
 #ifndef MC_HOSTEMU
-	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]);
+	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]); cudaEventDestroy(c->ev_staged[0]); cudaEventDestroy(c->ev_staged[1]);
+	if (c->cstream) cudaStreamDestroy(c->cstream);
 	if (c->stream) cudaStreamDestroy(c->stream);
 #endif
 	delete c;
@@ -258,12 +261,14 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	}
 	if (cuda_fail(cudaSetDevice(params->device), "cudaSetDevice")) { delete c; return MC_ERR_CUDA; }
 	if (cuda_fail(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
+	if (cuda_fail(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
 #else
-	c->stream = 0;
+	c->stream = 0; c->cstream = 0;
 #endif
 	for (int i = 0; i < EV_COUNT; i++) ev_create(&c->ev[i]);
 #ifndef MC_HOSTEMU
 	cudaEventCreateWithFlags(&c->ev_bounce[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bounce[1], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&c->ev_staged[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_staged[1], cudaEventDisableTiming);
 #endif
 	const int64_t G = v.genome_size; c->G = G;
 	std::vector<int64_t> ends; std::vector<int32_t> ids;
@@ -339,13 +344,13 @@ int mc_reset_stats(mc_ctx* c) { if (!c) return MC_ERR_ARG; zero_stats(&c->stats)
 // Host -> device copy of caller memory.  Pinned / registered memory (e.g. from mc_host_alloc) is handed to the copy engine
 // directly; pageable memory is streamed through two pinned bounce buffers so that the host memcpy of one piece overlaps the
 // DMA of the previous one.
-static int upload(mc_ctx* c, void* dst, const void* src, size_t bytes)
+static int upload(mc_ctx* c, void* dst, const void* src, size_t bytes, mc_stream_t stream)
 {
 	if (!bytes) return 0;
 #ifndef MC_HOSTEMU
 	cudaPointerAttributes at;
 	if (cudaPointerGetAttributes(&at, src) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged))
-		return dev_h2d(dst, src, bytes, c->stream);
+		return dev_h2d(dst, src, bytes, stream);
 	cudaGetLastError();
 	const size_t piece = 8u << 20;
 	if (c->h_bounce[0].reserve(piece) || c->h_bounce[1].reserve(piece)) return -1;
@@ -356,12 +361,12 @@ static int upload(mc_ctx* c, void* dst, const void* src, size_t bytes)
 		// the slot may still be feeding an earlier copy (also one issued by a previous upload() call)
 		if (cuda_fail(cudaEventSynchronize(c->ev_bounce[slot]), "bounce buffer wait")) return -1;
 		memcpy(c->h_bounce[slot].p, (const uint8_t*)src + off, m);
-		if (dev_h2d((uint8_t*)dst + off, c->h_bounce[slot].p, m, c->stream)) return -1;
-		cudaEventRecord(c->ev_bounce[slot], c->stream);
+		if (dev_h2d((uint8_t*)dst + off, c->h_bounce[slot].p, m, stream)) return -1;
+		cudaEventRecord(c->ev_bounce[slot], stream);
 	}
 	return 0;
 #else
-	return dev_h2d(dst, src, bytes, c->stream);
+	return dev_h2d(dst, src, bytes, stream);
 #endif
 }
 
@@ -381,7 +386,7 @@ static void launch_seedcap(const CapArgs& q, int64_t n, mc_stream_t s)
 { if (n > 0) { mc_seedcap_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(q, n); g_launches++; } }
 #endif
 
-static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st)
+static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st, mc_stream_t stream)
 {
 	const int64_t n = in->n_reads;
 	if (n < 0 || (n > 0 && (!in->seq || !in->seq_off))) { mc_set_error("mc_map_batch: bad batch"); return MC_ERR_ARG; }
@@ -393,11 +398,12 @@ static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st)
 	st.h_roff.clear();
 	if (c->prm.want_alignments) st.h_roff.assign(in->seq_off, in->seq_off + n + 1);
 	if (n == 0) { st.valid = true; return MC_OK; }
-	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 2) * 8) || c->d_cap.reserve(n * 4) || c->d_scan.reserve(device_scan_scratch_bytes(n))) return MC_ERR_CUDA;
-	if (upload(c, st.seq.p, in->seq + base, bytes) || upload(c, st.roff.p, in->seq_off, (n + 1) * 8)) return MC_ERR_CUDA;
-	CapArgs q; q.roff = st.roff.as<int64_t>(); q.cap = c->d_cap.as<uint32_t>(); q.st = c->d_stats.as<DevStats>();
-	launch_seedcap(q, n, c->stream);
-	device_scan_u32(q.cap, st.seed_off.as<int64_t>(), n, c->d_scan.as<int64_t>(), c->stream);
+	// scratch of the staging pass is private to the Staged slot: staging may run on the copy stream while another batch computes
+	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 2) * 8) || st.cap.reserve(n * 4) || st.scan.reserve(device_scan_scratch_bytes(n))) return MC_ERR_CUDA;
+	if (upload(c, st.seq.p, in->seq + base, bytes, stream) || upload(c, st.roff.p, in->seq_off, (n + 1) * 8, stream)) return MC_ERR_CUDA;
+	CapArgs q; q.roff = st.roff.as<int64_t>(); q.cap = st.cap.as<uint32_t>(); q.st = c->d_stats.as<DevStats>();
+	launch_seedcap(q, n, stream);
+	device_scan_u32(q.cap, st.seed_off.as<int64_t>(), n, st.scan.as<int64_t>(), stream);
 	st.valid = true;
 	return MC_OK;
 }
@@ -728,16 +734,68 @@ int mc_map_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
 #ifndef MC_HOSTEMU
 	cudaSetDevice(c->prm.device);
 #endif
-	ev_record(&c->ev[EV_START], c->stream);
-	int rc = stage_reads(c, in, c->cur);
+	const int64_t n = in->n_reads;
+	const int64_t n_chunks = (n + MC_CHUNK_READS - 1) / MC_CHUNK_READS;
+	// Profile-only runs of a large batch are cut into a few chunk-aligned pieces: piece i+1 travels over PCIe on the copy
+	// stream while piece i is being mapped.  The pieces are consecutive in file order, so the sequential state simply carries
+	// over.  (With want_alignments the result arenas of the pieces would have to be stitched; those batches go in one piece.)
+	const int kPieces = 4;
+	if (c->prm.want_alignments || c->prm.reserved[0] || n < 400000 || !in->seq || !in->seq_off)
+	{
+		ev_record(&c->ev[EV_START], c->stream);
+		int rc = stage_reads(c, in, c->cur, c->stream);
+		if (rc) return rc;
+		return run_batch(c, c->cur, out, true);
+	}
+	const int64_t per = ((n_chunks + kPieces - 1) / kPieces) * MC_CHUNK_READS;
+	auto piece_of = [&](int i, mc_batch_in& b) {
+		const int64_t r0 = std::min(n, (int64_t)i * per), r1 = std::min(n, (int64_t)(i + 1) * per);
+		b.n_reads = r1 - r0; b.seq = in->seq; b.seq_off = in->seq_off + r0;
+	};
+	c->chunks_all.clear();
+	int replays = 0;
+	mc_batch_in b;
+	const bool dbg = getenv("MC_DEBUG") != nullptr;
+	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t0 = now();
+	piece_of(0, b);
+	int rc = stage_reads(c, &b, c->pipe[0], c->cstream);
 	if (rc) return rc;
-	return run_batch(c, c->cur, out, true);
+#ifndef MC_HOSTEMU
+	cudaEventRecord(c->ev_staged[0], c->cstream);
+#endif
+	for (int i = 0; i < kPieces; i++)
+	{
+		if (i + 1 < kPieces)
+		{
+			piece_of(i + 1, b);
+			rc = stage_reads(c, &b, c->pipe[(i + 1) & 1], c->cstream);   // the slot's previous user (piece i-1) has completed: run_batch is synchronous
+			if (rc) return rc;
+#ifndef MC_HOSTEMU
+			cudaEventRecord(c->ev_staged[(i + 1) & 1], c->cstream);
+#endif
+		}
+#ifndef MC_HOSTEMU
+		cudaStreamWaitEvent(c->stream, c->ev_staged[i & 1], 0);
+#endif
+		ev_record(&c->ev[EV_START], c->stream);
+		mc_batch_out o;
+		const double t1 = now();
+		rc = run_batch(c, c->pipe[i & 1], &o, true);
+		if (rc) return rc;
+		if (dbg) fprintf(stderr, "[mc] piece %d: issued at %.3f ms, run_batch %.3f ms\n", i, t1 - t0, now() - t1);
+		c->chunks_all.insert(c->chunks_all.end(), o.chunks, o.chunks + o.n_chunks);
+		replays += o.replays;
+	}
+	memset(out, 0, sizeof(*out));
+	out->n_reads = n; out->n_chunks = (int64_t)c->chunks_all.size(); out->chunks = c->chunks_all.data(); out->replays = replays;
+	return MC_OK;
 }
 
 int mc_stage_batch(mc_ctx* c, const mc_batch_in* in, int32_t slot)
 {
 	if (!c || !in || slot < 0 || slot >= 4) { mc_set_error("mc_stage_batch: bad argument"); return MC_ERR_ARG; }
-	int rc = stage_reads(c, in, c->slots[slot]);
+	int rc = stage_reads(c, in, c->slots[slot], c->stream);
 	if (rc) return rc;
 	// reverse-complement mate 2 once; the staged copy is then immutable
 	PipeArgs a; memset(&a, 0, sizeof(a));

@@ -16,7 +16,7 @@
 #define MC_NW_NEG (-131072)
 
 template <bool KSW>
-static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask tk, const int lane, uint32_t& cells)
+static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask tk, const int lane, uint32_t& cells, uint8_t* fast, int fast_bytes)
 {
 	const unsigned full = 0xffffffffu;
 	mc_frag_out& x = a.frags[tk.frag];
@@ -26,8 +26,10 @@ static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask 
 	const int R = KSW ? n : m, C = KSW ? m : n;
 	const int nstrips = (C + 31) >> 5;
 	const int64_t strip_bytes = (int64_t)(R + 32) * 32;
-	uint8_t* tb = a.dpws + tk.ws_off;
-	int* bs = (int*)(tb + dp_tb_bytes(m, n)); int* bx = bs + ((m > n ? m : n) + 2);
+	uint8_t* gws = a.dpws + tk.ws_off;
+	int* bs = (int*)(gws + dp_tb_bytes(m, n)); int* bx = bs + ((m > n ? m : n) + 2);
+	// the traceback bytes of a small fill (almost all of them) stay in shared memory: the walk back is a chain of dependent loads
+	uint8_t* tb = (int64_t)nstrips * strip_bytes <= fast_bytes ? fast : gws;
 	for (int strip = 0; strip < nstrips; strip++)
 	{
 		const int j = strip * 32 + lane;                 // column, 0-based
@@ -38,13 +40,14 @@ static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask 
 		int upS = top, upY = KSW ? MC_NEG_INF : MC_NW_NEG;     // same column one row up: s / H and t / E
 		int diag = __shfl_up_sync(full, curS, 1);
 		if (lane == 0) diag = strip == 0 ? 0 : bs[0];
-		int rowc = 5;
+		int rowc = 5, rowchunk = 5;
 		uint8_t* tbs = tb + strip * strip_bytes;
 		const int steps = R + 31;
 		for (int t = 0; t < steps; t++)
 		{
 			const int i = t - lane;                      // row, 0-based
-			const int rc_new = t < R ? mc_nt4(rowstr[t]) : 5;
+			if ((t & 31) == 0) rowchunk = t + lane < R ? mc_nt4(rowstr[t + lane]) : 5;   // 32 row characters per load, handed out by shuffle
+			const int rc_new = __shfl_sync(full, rowchunk, t & 31);
 			const int rc_recv = __shfl_up_sync(full, rowc, 1);
 			rowc = lane == 0 ? rc_new : rc_recv;
 			int leftS = __shfl_up_sync(full, curS, 1), leftX = __shfl_up_sync(full, curX, 1);
@@ -87,19 +90,16 @@ static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask 
 		if (lane == 31 && strip + 1 < nstrips) bs[0] = top;
 		__syncwarp();
 	}
+	__syncwarp();
 	if (lane == 0)
 	{
-		int len = 0;
+		// one pass from the end of the matrix, writing the gapped strings right-aligned into their capacity (the write cursor
+		// never passes an unread source byte: k >= i + j - 1 throughout); aln_off then moves to where they start
+		const int cap = x.aln_cap;
+		int k = cap;
 		if (!KSW)
 		{
 			int i = m, j = n;
-			while (i > 0 || j > 0)
-			{
-				const uint8_t d = i == 0 ? 1 : j == 0 ? 2 : tb[((j - 1) >> 5) * strip_bytes + (int64_t)(i - 1 + ((j - 1) & 31)) * 32 + ((j - 1) & 31)];
-				if (d & 1) j--; else if (d & 2) i--; else { i--; j--; }
-				len++;
-			}
-			i = m; j = n; int k = len;
 			while (i > 0 || j > 0)
 			{
 				const uint8_t d = i == 0 ? 1 : j == 0 ? 2 : tb[((j - 1) >> 5) * strip_bytes + (int64_t)(i - 1 + ((j - 1) & 31)) * 32 + ((j - 1) & 31)];
@@ -111,33 +111,32 @@ static __device__ __forceinline__ void dpw_task(const PipeArgs& a, const DpTask 
 		}
 		else
 		{
-			for (int pass = 0; pass < 2; pass++)
+			int i = n - 1, j = m - 1, state = 0;
+			while (i >= 0 && j >= 0)
 			{
-				int i = n - 1, j = m - 1, state = 0, k = len, cnt = 0;
-				while (i >= 0 && j >= 0)
-				{
-					const uint32_t tmp = tb[(j >> 5) * strip_bytes + (int64_t)(i + (j & 31)) * 32 + (j & 31)];
-					if (state == 0) state = tmp & 7;
-					else if (!((tmp >> (state + 2)) & 1)) state = 0;
-					if (state == 0) state = tmp & 7;
-					if (state == 0) { if (pass) { k--; s1[k] = s1[j]; s2[k] = s2[i]; } i--; j--; }
-					else if (state == 1 || state == 3) { if (pass) { k--; s2[k] = s2[i]; s1[k] = '-'; } i--; }
-					else { if (pass) { k--; s1[k] = s1[j]; s2[k] = '-'; } j--; }
-					cnt++;
-				}
-				while (i >= 0) { if (pass) { k--; s2[k] = s2[i]; s1[k] = '-'; } i--; cnt++; }
-				while (j >= 0) { if (pass) { k--; s1[k] = s1[j]; s2[k] = '-'; } j--; cnt++; }
-				if (!pass) len = cnt;
+				const uint32_t tmp = tb[(j >> 5) * strip_bytes + (int64_t)(i + (j & 31)) * 32 + (j & 31)];
+				if (state == 0) state = tmp & 7;
+				else if (!((tmp >> (state + 2)) & 1)) state = 0;
+				if (state == 0) state = tmp & 7;
+				k--;
+				if (state == 0) { s1[k] = s1[j]; s2[k] = s2[i]; i--; j--; }
+				else if (state == 1 || state == 3) { s2[k] = s2[i]; s1[k] = '-'; i--; }
+				else { s1[k] = s1[j]; s2[k] = '-'; j--; }
 			}
+			while (i >= 0) { k--; s2[k] = s2[i]; s1[k] = '-'; i--; }
+			while (j >= 0) { k--; s1[k] = s1[j]; s2[k] = '-'; j--; }
 		}
-		x.aln_len = len;
+		x.aln_off += k; x.aln_len = cap - k;
 		cells += (uint32_t)(m * n);
 	}
 }
 
 // persistent warps: warp w takes tasks task_begin + w, + n_warps, ...
+#define MC_DP_SMEM (6 * 1024)     // traceback bytes per warp kept on chip: 6 KB covers fills up to ~160 rows x 32 columns
 __global__ void __launch_bounds__(MC_BLOCK) mc_dp_kernel(const PipeArgs a)
 {
+	__shared__ __align__(16) uint8_t dp_smem[(MC_BLOCK / 32) * MC_DP_SMEM];
+	uint8_t* fast = dp_smem + (threadIdx.x >> 5) * MC_DP_SMEM;
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
 	int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
@@ -145,7 +144,7 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_dp_kernel(const PipeArgs a)
 	for (int64_t t = a.task_begin + warp; t < end; t += n_warps)
 	{
 		const DpTask tk = a.tasks[t];
-		if (a.pr.alg_ksw2) dpw_task<true>(a, tk, lane, cells); else dpw_task<false>(a, tk, lane, cells);
+		if (a.pr.alg_ksw2) dpw_task<true>(a, tk, lane, cells, fast, MC_DP_SMEM); else dpw_task<false>(a, tk, lane, cells, fast, MC_DP_SMEM);
 		tasks++;
 		__syncwarp();
 	}

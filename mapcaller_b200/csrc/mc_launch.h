@@ -13,7 +13,7 @@ typedef int mc_stream_t;
 	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a); }
 #define MC_LAUNCH2(name) \
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
-static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a); }
+static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a, 0, 0); }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
 static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin; for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
@@ -72,18 +72,26 @@ static void launch_piece(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
 	mc_piece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
-// rescue tasks: persistent warps, warp w takes tasks w, w + n_warps, ... of the current attempt's window
-__global__ void __launch_bounds__(MC_BLOCK) mc_rescue_kernel(const PipeArgs a)
+// rescue tasks: persistent warps, warp w takes tasks w, w + n_warps, ... of the current attempt's window.  A task is a long,
+// serial, latency-bound piece of code over small tables (word list, diagonal histogram, filter): they live in shared memory
+// (28 KB per warp, 4 warps per block); a lone warp going to global memory for them was ~20x slower.
+#define MC_RESCUE_WARPS 4
+#define MC_RESCUE_SMEM (28 * 1024)
+__global__ void __launch_bounds__(MC_RESCUE_WARPS * 32) mc_rescue_kernel(const PipeArgs a)
 {
+	extern __shared__ __align__(16) uint8_t rescue_smem[];
 	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
 	const int64_t n = (int64_t)*a.rtask_bump - a.rtask_begin;
-	for (int64_t t = warp; t < n; t += n_warps) { rescue_body(t, threadIdx.x & 31, 32, a); __syncwarp(); }
+	uint8_t* mine = rescue_smem + (threadIdx.x >> 5) * MC_RESCUE_SMEM;
+	for (int64_t t = warp; t < n; t += n_warps) { rescue_body(t, threadIdx.x & 31, 32, a, mine, MC_RESCUE_SMEM); __syncwarp(); }
 }
 static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
-	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
-	mc_rescue_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
+	static bool configured = false;
+	if (!configured) { cudaFuncSetAttribute(mc_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_RESCUE_WARPS * MC_RESCUE_SMEM); configured = true; }
+	int64_t blocks = (max_tasks + MC_RESCUE_WARPS - 1) / MC_RESCUE_WARPS; if (blocks > 148 * 2) blocks = 148 * 2;
+	mc_rescue_kernel<<<(unsigned)blocks, MC_RESCUE_WARPS * 32, MC_RESCUE_WARPS * MC_RESCUE_SMEM, s>>>(a); g_launches++;
 }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t* sums)
 { int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < nb) profsum_body(b, p, G, nb, sums); }

@@ -93,8 +93,7 @@ MC_HD void pair_body(int64_t p, const PipeArgs& a)
 		if (b0 < (l0 >> 2) && b1 < (l1 >> 2)) { remove_redundant(s0, n0); remove_redundant(s1, n1); }
 		else
 		{
-			lo = est; hi = est;
-			int64_t k = mc_bump_alloc(a.rtask_bump, 1u);
+			int64_t k = mc_bump_alloc(a.rtask_bump, 1u);   // rescue_body narrows [lo, hi] further
 			a.rtask[k] = (int32_t)p;
 		}
 	}
@@ -152,28 +151,47 @@ MC_HD int kmer_list_of_read(const uint8_t* s, int len, KmerEnt* out)
 	return n;
 }
 
-// word id of the reference 8-mer at absolute position g (RefSequence holds ACGT only)
-MC_HD uint32_t ref_kmer_id(const PipeArgs& a, int64_t g, int64_t* last_g, uint32_t* last_wid)
+// The same list by all lanes of the warp when the read is plain ACGT/acgt (no 'N', nothing the sequential rolling
+// formula would treat specially): word p is the fresh id of bases [p, p+8) and is labelled p.  Otherwise lane 0 runs the
+// sequential routine.  Returns the number of words to every lane through lanebuf[0].
+MC_HD int kmer_list_coop(const uint8_t* s, int len, KmerEnt* out, int lane, int nl, int32_t* lanebuf)
 {
-	uint32_t w;
-	if (g == *last_g + 1) w = ((*last_wid & 0x3FFFu) << 2) + (uint32_t)mc_ref_code(a.ix, g + 7);
-	else { w = 0; for (int i = 0; i < 8; i++) w = (w << 2) + (uint32_t)mc_ref_code(a.ix, g + i); }
-	*last_g = g; *last_wid = w;
-	return w;
+	int bad = 0;
+	for (int i = lane; i < len; i += nl) if (mc_nt4(s[i]) > 3) bad = 1;
+	bad = mc_warp_max(bad);
+	if (!bad)
+	{
+		const int n = len >= 8 ? len - 7 : 0;
+		for (int p = lane; p < n; p += nl) { out[p].label = p; out[p].wid = kmer_fresh_id(s, p); }
+		MC_WARP_SYNC();
+		return n;
+	}
+	if (lane == 0) lanebuf[0] = kmer_list_of_read(s, len, out);
+	MC_WARP_SYNC();
+	const int n = lanebuf[0];
+	MC_WARP_SYNC();
+	return n;
+}
+
+// word id of the 8-mer at offset g of a staged window (codes 0..3, 4 = outside the text); 0xFFFFFFFF if it touches the outside
+MC_HD uint32_t win_kmer_id(const uint8_t* wref, int g)
+{
+	uint32_t w = 0, bad = 0;
+	for (int i = 0; i < 8; i++) { const uint32_t c = wref[g + i]; bad |= c & 4u; w = (w << 2) + (c & 3u); }
+	return bad ? 0xFFFFFFFFu : w;
 }
 
 // walks diagonal d (window offset minus word label); returns the sum of seed lengths, optionally writes the seeds
-MC_HD int rescue_scan_diag(const PipeArgs& a, const KmerEnt* km, int nk, int64_t left, int slen, int d, SPair* out, int* nout)
+MC_HD int rescue_scan_diag(const uint32_t* wkid0, const KmerEnt* km, int nk, int64_t left, int slen, int d, SPair* out, int* nout)
 {
 	int total = 0, run = 0, first = 0, n = 0, prev_label = -2;
-	int64_t last_g = -10; uint32_t last_wid = 0;
 	for (int i = 0; i <= nk; i++)
 	{
 		bool hit = false;
 		if (i < nk)
 		{
 			const int g = km[i].label + d;
-			if (g >= 0 && g <= slen - 8 && left + g >= 0) hit = ref_kmer_id(a, left + g, &last_g, &last_wid) == km[i].wid;
+			if (g >= 0 && g <= slen - 8) hit = wkid0[g] == km[i].wid;   // wkid0[g] = word id at window offset g
 		}
 		if (hit && run > 0 && km[i].label == prev_label + 1) run++;
 		else
@@ -193,16 +211,55 @@ MC_HD int rescue_scan_diag(const PipeArgs& a, const KmerEnt* km, int nk, int64_t
 	return total;
 }
 
-// tries to place a mate (word list km) inside [left, right); appends a candidate to read `rt`.
-// `nl` lanes cooperate (a warp on the GPU): (1) every reference 8-mer of the window is compared with the read's
-// words and the hits are histogrammed per diagonal, (2) only diagonals with >= 3 hits (a seed needs a run of 3) are
-// walked exactly, (3) the best diagonal is reduced over the lanes, (4) lane 0 appends the candidate.
-// All lanes return the same value.
-MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const KmerEnt* km, int nk, int rlen, int64_t left, int64_t right,
-                      int floor_score, int anchor_idx, uint32_t* hits, int32_t* lanebuf, const uint32_t* bloom, int32_t* new_idx)
+#define MC_RESCUE_MARGIN 32   // how far beyond the moving window edge hits are looked for (validity interval of EstiDistance)
+
+// Tries to place a mate (word list km) inside the window an anchored candidate of the other mate implies and appends a
+// candidate to read `rt` (one iteration of the loops of AlignmentRescue, reference src/AlignmentRescue.cpp:55-79 / :84-106).
+//   dir 0: window [d, d + est + rlen)   - the right edge moves with EstiDistance
+//   dir 1: window [d - est, d + rlen)   - the left edge moves
+// `nl` lanes cooperate (a warp on the GPU): (1) every reference 8-mer of the window (plus a margin beyond the moving edge) is
+// checked against a 4096-bit filter of the read's words, (2) the survivors are compared with all words by all lanes and
+// histogrammed per diagonal, (3) only diagonals with >= 3 hits (a seed needs a run of 3) are walked exactly, (4) the best
+// diagonal is reduced over the lanes, (5) lane 0 appends the candidate.
+// *iv_lo / *iv_hi are narrowed to the EstiDistance values for which this call provably does the same: the moving edge stays
+// between the same chromosome ends and no 8-mer hit enters or leaves the window.  All lanes return the same values.
+MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const KmerEnt* km, int nk, int rlen, int dir, int64_t d, int est,
+                      int floor_score, int anchor_idx, uint32_t* hits, int64_t n_hits, int32_t* lanebuf, const uint32_t* bloom, int32_t* new_idx, int* iv_lo, int* iv_hi)
 {
-	if (right > a.ix.twoG) right = a.ix.twoG;
-	int i1 = mc_chrom_lower_bound(a.ix, left), i2 = mc_chrom_lower_bound(a.ix, right);
+	const int M = MC_RESCUE_MARGIN;
+	int64_t left = dir == 0 ? d : d - (int64_t)(uint32_t)est;
+	int64_t right = dir == 0 ? d + (int64_t)(uint32_t)est + rlen : d + rlen;
+	const bool clipped = right > a.ix.twoG;
+	if (clipped) right = a.ix.twoG;
+	int lo = 0, hi = est + M;
+	const int i1 = mc_chrom_lower_bound(a.ix, left), i2 = mc_chrom_lower_bound(a.ix, right);
+	{
+		// the moving edge has to stay between the same two chromosome ends (and on the same side of the 2G clip)
+		bool pin = false;
+		if (dir == 0)
+		{
+			if (clipped) { const int64_t v = a.ix.twoG - d - rlen; if (v > lo) lo = (int)(v > est ? est : v); }
+			else if (i2 >= a.ix.n_end) pin = true;
+			else
+			{
+				const int64_t up = a.ix.chrom_end[i2] - d - rlen; if (up < hi) hi = (int)up;
+				if (i2 > 0) { const int64_t dn = a.ix.chrom_end[i2 - 1] - d - rlen + 1; if (dn > lo) lo = (int)dn; }
+			}
+		}
+		else
+		{
+			if (clipped || i1 >= a.ix.n_end) pin = true;
+			else
+			{
+				const int64_t dn = d - a.ix.chrom_end[i1]; if (dn > lo) lo = (int)dn;
+				if (i1 > 0) { const int64_t up = d - a.ix.chrom_end[i1 - 1] - 1; if (up < hi) hi = (int)up; }
+			}
+		}
+		if (pin) { lo = est; hi = est; }
+		if (lo > est) lo = est;
+		if (hi < est) hi = est;
+	}
+	*iv_lo = *iv_lo > lo ? *iv_lo : lo; *iv_hi = *iv_hi < hi ? *iv_hi : hi;
 	if (i1 >= a.ix.n_end || i2 >= a.ix.n_end) return false; // the reference dereferences end() here; treated as "different chromosome"
 	if (a.ix.chrom_id[i1] != a.ix.chrom_id[i2]) return false;
 	const int64_t sl = right - left;
@@ -210,59 +267,86 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const Kme
 	const int slen = (int)sl;
 	const int dmin = -(rlen - 8), ndiag = slen - 8 - dmin + 1;
 	for (int i = lane; i < ndiag; i += nl) hits[i] = 0;
+	uint32_t* clist = (uint32_t*)(bloom + 128); int32_t* ccount = lanebuf + 6 * nl + 2;
+	if (lane == 0) *ccount = 0;
+	// window offsets scanned: the window itself plus the margin beyond the moving edge
+	const int gs = dir == 1 ? -M : 0, ge = dir == 0 ? slen - 8 + M : slen - 8;
+	// stage the 2-bit codes of the scanned stretch once (lanes read consecutive bases); 4 marks positions outside the text
+	uint32_t* wkid = clist + n_hits; const uint32_t* wkid0 = wkid - gs;          // word id of every scanned offset
+	uint8_t* wref = (uint8_t*)(wkid + n_hits); const uint8_t* wref0 = wref - gs;
+	for (int i = lane; i < ge - gs + 8; i += nl) { const int64_t pos = left + gs + i; wref[i] = (pos < 0 || pos >= a.ix.twoG) ? 4 : (uint8_t)mc_ref_code(a.ix, pos); }
 	MC_WARP_SYNC();
 	{
-		// pass 1: each lane owns a contiguous run of window positions (so the reference word can be rolled) and keeps the
-		// positions whose word passes the filter; pass 2: the warp takes the survivors one by one and all lanes compare them
-		// with the read's words (a per-lane inner loop would stall the whole warp on one lane's false positive)
-		uint32_t* clist = (uint32_t*)(bloom + 128); int32_t* ccount = lanebuf + 2 * nl + 2;
-		if (lane == 0) *ccount = 0;
-		MC_WARP_SYNC();
-		const int npos = slen - 7, per = (npos + nl - 1) / nl;
-		int g0 = lane * per, g1 = g0 + per; if (g1 > npos) g1 = npos;
-		int64_t last_g = -10; uint32_t last_wid = 0;
+		// pass 1: each lane owns a contiguous run of offsets (so the reference word can be rolled) and keeps those whose word
+		// passes the filter; pass 2: the warp takes the survivors one by one and all lanes compare them with the read's words
+		const int npos = ge - gs + 1, per = (npos + nl - 1) / nl;
+		int g0 = gs + lane * per, g1 = g0 + per; if (g1 > ge + 1) g1 = ge + 1;
 		for (int g = g0; g < g1; g++)
 		{
-			if (left + g < 0) continue;
-			const uint32_t w = ref_kmer_id(a, left + g, &last_g, &last_wid);
+			const uint32_t w = win_kmer_id(wref0, g);
+			wkid[g - gs] = w;
+			if (w == 0xFFFFFFFFu) continue;
 			if (!((bloom[(w & 4095) >> 5] >> (w & 31)) & 1)) continue;   // no word of the read ends in these six bases
-			clist[mc_atomic_add(ccount, 1)] = ((uint32_t)g << 16) | (w & 0xFFFFu);
+			clist[mc_atomic_add(ccount, 1)] = ((uint32_t)(g + M) << 16) | (w & 0xFFFFu);
 		}
-		MC_WARP_SYNC();
+	}
+	MC_WARP_SYNC();
+	int in_far = -1, out_near = 1 << 30;   // inside hit closest to the moving edge (distance from it), margin hit closest to it
+	{
 		const int nc = *ccount;
 		for (int c = 0; c < nc; c++)
 		{
-			const uint32_t e = clist[c]; const int g = (int)(e >> 16); const uint32_t w = e & 0xFFFFu;
-			for (int i = lane; i < nk; i += nl) if (km[i].wid == w) mc_atomic_add(&hits[g - km[i].label - dmin], 1u);
+			const uint32_t e = clist[c]; const int g = (int)(e >> 16) - M; const uint32_t w = e & 0xFFFFu;
+			const bool inside = g >= 0 && g <= slen - 8;
+			for (int i = lane; i < nk; i += nl)
+			{
+				if (km[i].wid != w) continue;
+				if (inside)
+				{
+					mc_atomic_add(&hits[g - km[i].label - dmin], 1u);
+					const int dist = dir == 0 ? slen - 8 - g : g;          // how far the edge may retreat before this hit drops out
+					if (in_far < 0 || dist < in_far) in_far = dist;
+				}
+				else { const int dist = dir == 0 ? g - (slen - 8) : -g; if (dist < out_near) out_near = dist; }   // >= 1: advance that lets it in
+			}
 		}
 	}
+	lanebuf[4 * nl + lane] = in_far; lanebuf[5 * nl + lane] = out_near;
 	MC_WARP_SYNC();
 	int best = 0, bd = 0;
 	for (int i = lane; i < ndiag; i += nl)
 	{
 		if (hits[i] < 3) continue;
-		const int sc = rescue_scan_diag(a, km, nk, left, slen, i + dmin, 0, 0);
+		const int sc = rescue_scan_diag(wkid0, km, nk, left, slen, i + dmin, 0, 0);
 		if (sc > best) { best = sc; bd = i + dmin; }   // ascending diagonals inside a lane: first maximum wins
 	}
 	lanebuf[2 * lane] = best; lanebuf[2 * lane + 1] = bd;
 	MC_WARP_SYNC();
-	best = 0; bd = 0;
+	best = 0; bd = 0; in_far = -1; out_near = 1 << 30;
 	for (int l = 0; l < nl; l++)
 	{
-		const int sc = lanebuf[2 * l], d = lanebuf[2 * l + 1];
-		if (sc > best || (sc == best && sc > 0 && d < bd)) { best = sc; bd = d; }
+		const int sc = lanebuf[2 * l], dd = lanebuf[2 * l + 1];
+		if (sc > best || (sc == best && sc > 0 && dd < bd)) { best = sc; bd = dd; }
+		const int f = lanebuf[4 * nl + l], o = lanebuf[5 * nl + l];
+		if (f >= 0 && (in_far < 0 || f < in_far)) in_far = f;
+		if (o < out_near) out_near = o;
 	}
 	MC_WARP_SYNC();
+	if (!clipped || dir == 1)
+	{
+		if (in_far >= 0 && est - in_far > *iv_lo) *iv_lo = est - in_far;
+		if (out_near < (1 << 30) && est + out_near - 1 < *iv_hi) *iv_hi = est + out_near - 1;
+	}
 	if (best == 0 || best <= floor_score) return false;
 	if (lane == 0)
 	{
 		int n = 0, ok = 1, k = -1;
-		rescue_scan_diag(a, km, nk, left, slen, bd, 0, &n);
+		rescue_scan_diag(wkid0, km, nk, left, slen, bd, 0, &n);
 		const int64_t pb = (int64_t)mc_atomic_add(a.pair_bump, (mc_u64)n);
 		if (pb + n > a.pair_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 0); ok = 0; }
 		if (ok)
 		{
-			rescue_scan_diag(a, km, nk, left, slen, bd, a.pairs + pb, &n);
+			rescue_scan_diag(wkid0, km, nk, left, slen, bd, a.pairs + pb, &n);
 			const int64_t co = pa_cand_off(a, rt);
 			k = a.ncand[rt];
 			if (k >= pa_cand_cap(a, rt)) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 40); ok = 0; }
@@ -273,15 +357,17 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const Kme
 				a.ncand[rt] = k + 1;
 			}
 		}
-		lanebuf[2 * nl] = ok; lanebuf[2 * nl + 1] = k;
+		lanebuf[6 * nl] = ok; lanebuf[6 * nl + 1] = k;
 	}
 	MC_WARP_SYNC();
-	const int ok = lanebuf[2 * nl]; *new_idx = lanebuf[2 * nl + 1];
+	const int ok = lanebuf[6 * nl]; *new_idx = lanebuf[6 * nl + 1];
 	MC_WARP_SYNC();
 	return ok != 0;
 }
 
-MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
+// `fast` / `fast_bytes`: optional on-chip scratch of the calling warp (shared memory on the GPU); tasks that need more fall
+// back to the global gapped-fill workspace.
+MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* fast, int64_t fast_bytes)
 {
 	if (a.rtask_begin + t >= (int64_t)*a.rtask_bump) return;
 	const int64_t p = a.rtask[a.rtask_begin + t];
@@ -295,24 +381,29 @@ MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
 	for (int i = 0; i < n0; i++) if (s0[i] > b0) b0 = s0[i];
 	for (int j = 0; j < n1; j++) if (s1[j] > b1) b1 = s1[j];
 	const int strat = (b0 - b1 > (l1 >> 2)) ? 1 : (b1 - b0 > (l0 >> 2)) ? 2 : 3;
-	int rescued = 0;
-	// scratch in the (still unused) gapped-fill workspace: both word lists, the diagonal histogram, the lane buffer
+	int rescued = 0, iv_lo = -2147483647, iv_hi = 2147483647;
+	// scratch in the (still unused) gapped-fill workspace: both word lists, the diagonal histogram, the lane buffer, the filter,
+	// the list of filter survivors
 	const int lmax = l0 > l1 ? l0 : l1;
-	const int64_t n_hits = (int64_t)(uint32_t)est + 3 * (int64_t)lmax + 16;
-	const int64_t wsn = ((int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (2 * nl + 4) * 4 + 128 * 4 + n_hits * 4 + 15) & ~15ll;
-	int64_t ws = 0;
-	if (lane == 0) ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
-	ws = mc_bcast64(ws);
-	if (ws + wsn > a.dpws_cap) { if (lane == 0) mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
-	KmerEnt* km0 = (KmerEnt*)(a.dpws + ws); KmerEnt* km1 = km0 + l0 + 1;
+	const int64_t n_hits = (int64_t)(uint32_t)est + 3 * (int64_t)lmax + 2 * MC_RESCUE_MARGIN + 16;
+	const int64_t wsn = ((int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (6 * nl + 4) * 4 + 128 * 4 + n_hits * 4 + n_hits * 4 + n_hits + 15) & ~15ll;
+	uint8_t* scratch = fast;
+	if (!fast || wsn > fast_bytes)
+	{
+		int64_t ws = 0;
+		if (lane == 0) ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
+		ws = mc_bcast64(ws);
+		if (ws + wsn > a.dpws_cap) { if (lane == 0) mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
+		scratch = a.dpws + ws;
+	}
+	KmerEnt* km0 = (KmerEnt*)scratch; KmerEnt* km1 = km0 + l0 + 1;
 	uint32_t* hits = (uint32_t*)(km1 + l1 + 1); int32_t* lanebuf = (int32_t*)(hits + n_hits);
-	uint32_t* bloom = (uint32_t*)(lanebuf + 2 * nl + 4);   // 4096-bit filter over the low 12 bits of the read's word ids
+	uint32_t* bloom = (uint32_t*)(lanebuf + 6 * nl + 4);   // 4096-bit filter over the low 12 bits of the read's word ids
 	if (strat == 1 || strat == 3) // place mate 2 next to mate 1's candidates
 	{
 		for (int i = lane; i < 128; i += nl) bloom[i] = 0;
-		if (lane == 0) lanebuf[0] = kmer_list_of_read(a.seq + a.roff[r1], l1, km1);
 		MC_WARP_SYNC();
-		const int nk = lanebuf[0];
+		const int nk = kmer_list_coop(a.seq + a.roff[r1], l1, km1, lane, nl, lanebuf);
 		for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km1[i].wid & 4095) >> 5], 1u << (km1[i].wid & 31));
 		MC_WARP_SYNC();
 		const int thr = b0 >> 1;
@@ -321,16 +412,15 @@ MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
 			if (s0[i] < thr || p0[i] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c0 + i]);
 			int32_t k;
-			if (rescue_try(a, lane, nl, r1, km1, nk, l1, d, d + (int64_t)(uint32_t)est + l1, b1, i, hits, lanebuf, bloom, &k)) { if (lane == 0) p0[i] = k; rescued++; }
+			if (rescue_try(a, lane, nl, r1, km1, nk, l1, 0, d, est, b1, i, hits, n_hits, lanebuf, bloom, &k, &iv_lo, &iv_hi)) { if (lane == 0) p0[i] = k; rescued++; }
 			MC_WARP_SYNC();
 		}
 	}
 	if (strat == 2 || strat == 3) // place mate 1 next to mate 2's candidates
 	{
 		for (int i = lane; i < 128; i += nl) bloom[i] = 0;
-		if (lane == 0) lanebuf[0] = kmer_list_of_read(a.seq + a.roff[r0], l0, km0);
 		MC_WARP_SYNC();
-		const int nk = lanebuf[0];
+		const int nk = kmer_list_coop(a.seq + a.roff[r0], l0, km0, lane, nl, lanebuf);
 		for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km0[i].wid & 4095) >> 5], 1u << (km0[i].wid & 31));
 		MC_WARP_SYNC();
 		const int thr = b1 >> 1;
@@ -340,15 +430,22 @@ MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a)
 			if (s1[j] < thr || p1[j] != -1) continue;
 			const int64_t d = cand_posdiff(a, a.cands[c1 + j]);
 			int32_t k;
-			if (rescue_try(a, lane, nl, r0, km0, nk, l0, d - (int64_t)(uint32_t)est, d + l0, b0, j, hits, lanebuf, bloom, &k)) { if (lane == 0) p1[j] = k; rescued++; }
+			if (rescue_try(a, lane, nl, r0, km0, nk, l0, 1, d, est, b0, j, hits, n_hits, lanebuf, bloom, &k, &iv_lo, &iv_hi)) { if (lane == 0) p1[j] = k; rescued++; }
 			MC_WARP_SYNC();
 		}
 	}
+#ifdef MC_HOSTEMU
+	if (getenv("MC_TRACE_RESCUE")) fprintf(stderr, "[rescue] pair %lld strat %d n0 %d n1 %d b0 %d b1 %d rescued %d iv [%d,%d] est %d\n", (long long)p, strat, n0, n1, b0, b1, rescued, iv_lo, iv_hi, est);
+#endif
 	if (lane == 0)
 	{
 		const int m0 = a.ncand[r0], m1 = a.ncand[r1];
 		if (rescued == 0) { remove_redundant(s0, m0); remove_redundant(s1, m1); }
 		else mask_unpaired(s0, p0, m0, s1, p1, m1);
+		// the pair's outcome holds for every EstiDistance inside both the interval of its distance tests (pair_body) and the
+		// interval of its rescue windows
+		if (iv_lo > a.est_lo[p]) a.est_lo[p] = iv_lo;
+		if (iv_hi < a.est_hi[p]) a.est_hi[p] = iv_hi;
 	}
 }
 

@@ -22,7 +22,7 @@ def have_ref() -> bool:
 
 def make_case(kind: str = "small", seed: int = 1, n_pairs: int = 3000, read_len: int = 100, genome_len: int = 60000,
               contigs: int = 1, sub_rate: float = 0.005, indel_rate: float = 0.0, n_rate: float = 0.0, sv: float = 1.0,
-              n_dup: int = 6, tandem: int = 3, frag_mean: float = 400, frag_sd: float = 40, **params):
+              n_dup: int = 6, tandem: int = 3, frag_mean: float = 400, frag_sd: float = 40, lower_rate: float = 0.0, **params):
     """A genome (possibly several contigs), a mutated copy the reads come from, and the reads."""
     parts, names = [], []
     for c in range(contigs):
@@ -36,6 +36,13 @@ def make_case(kind: str = "small", seed: int = 1, n_pairs: int = 3000, read_len:
     # RefSequence[0] (src/AlignmentRescue.cpp:87,93) and the unmodified reference reads out of bounds (it segfaults on
     # some hosts), so such reads cannot be pinned against it.
     r1, r2 = sim.simulate_pairs(mut[3000:], n_pairs, read_len, seed=seed + 7, frag_mean=frag_mean, frag_sd=frag_sd, sub_rate=sub_rate, indel_rate=indel_rate, n_rate=n_rate)
+    if lower_rate > 0:   # soft-masked style input: the reference seeds through lower case but only counts upper-case bases in the profile
+        rng = np.random.default_rng(seed + 99)
+        for r in (r1, r2):
+            rows = rng.random(len(r)) < lower_rate
+            cols = rng.random(r.shape) < 0.3
+            m = rows[:, None] & cols & (r != ord("N"))
+            r[m] |= 0x20
     p = dict(paired=1, alg_ksw2=0, max_pos_diff=30, max_clip=5, max_dup=5, max_mismatch_rate=0.05)
     p.update(params)
     if p["paired"]:

@@ -24,6 +24,7 @@ CASES = {
     "sv_repeats": dict(seed=9, n_pairs=20000, genome_len=200000, sv=5.0, n_dup=30, tandem=20),
     "long_reads_250": dict(seed=10, n_pairs=4000, genome_len=150000, read_len=250, frag_mean=600, frag_sd=80, indel_rate=0.003),
     "deep_duplicates": dict(seed=11, n_pairs=30000, genome_len=20000, max_dup=3),
+    "lower_case_reads": dict(seed=15, n_pairs=4000, genome_len=60000, lower_rate=0.2),
     "params": dict(seed=13, n_pairs=3000, genome_len=60000, max_pos_diff=8, max_clip=2, max_dup=15, max_mismatch_rate=0.1),
 }
 
@@ -68,6 +69,35 @@ def test_batch_split_invariance(built, batch_reads):
     whole = pu.cuda_results(case, ix)
     parts = pu.cuda_results(case, ix, batch_reads=batch_reads)
     pu.assert_same(parts, whole)
+
+
+def test_pipelined_large_batch_equals_resident_path(built):
+    """A profile-only batch of >= 400 k reads is cut into pieces whose upload overlaps the mapping of the previous piece
+    (copy stream); the result must equal the single-piece path (mc_stage_batch + mc_map_staged) and the chunk-wise path."""
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=16, n_pairs=210000, genome_len=400000, contigs=2)
+    ix = pu.build_index(case)
+    seq, off = case["seq"], case["off"]
+    outs = []
+    for mode in ("pipelined", "staged", "pinned_pipelined"):
+        with api.Context(ix, paired=1, update_profile=1) as ctx:
+            if mode == "pipelined":
+                res = ctx.map_batch(seq, off)
+            elif mode == "staged":
+                ctx.stage_batch(seq, off, 0); res = ctx.map_staged(0, copy=True)
+            else:
+                ps = api.pinned_array(seq.shape, np.uint8); ps[:] = seq
+                po = api.pinned_array(off.shape, np.int64); po[:] = off
+                res = ctx.map_batch(ps, po)
+            ins, dele = ctx.indels()
+            outs.append(dict(chunks=res["chunks"].tolist(), totals=ctx.totals(), profile=ctx.profile_columns(), ins=ins, dele=dele, bp=ctx.breakpoints(),
+                             inv=sorted(ctx.sites(0)), tnl=sorted(ctx.sites(1))))
+    for o in outs[1:]:
+        assert o["totals"] == outs[0]["totals"] and o["chunks"] == outs[0]["chunks"]
+        assert np.array_equal(o["profile"], outs[0]["profile"])
+        for k in ("ins", "dele", "bp", "inv", "tnl"):
+            assert o[k] == outs[0][k], k
+    assert outs[0]["totals"]["total_reads"] == 420000
 
 
 def test_edge_cases(built):

@@ -15,6 +15,7 @@ CASES = {
     "sv": dict(seed=9, n_pairs=20000, genome_len=200000, sv=5.0, n_dup=30, tandem=20),
     "long": dict(seed=10, n_pairs=4000, genome_len=150000, read_len=250, frag_mean=600, frag_sd=80, indel_rate=0.003),
     "dup": dict(seed=11, n_pairs=30000, genome_len=20000, max_dup=3),
+    "lower": dict(seed=15, n_pairs=4000, genome_len=60000, lower_rate=0.2),
     "batched": dict(seed=12, n_pairs=12000, genome_len=100000),
 }
 names = sys.argv[1:] or list(CASES)
