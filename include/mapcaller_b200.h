@@ -96,7 +96,8 @@ typedef struct {
     int32_t device;            /* CUDA device ordinal */
     int32_t shard_rank;        /* multi-GPU: this context's position in file order (0 when single) */
     int32_t shard_count;       /* multi-GPU: number of shards (1 when single) */
-    int32_t reserved[5];       /* reserved[0] != 0: return the per-pair coordinates (mc_batch_out::pairs) even without want_alignments */
+    int32_t reserved[5];       /* reserved[0] != 0: return the per-pair coordinates (mc_batch_out::pairs) even without want_alignments;
+                                  reserved[1] != 0: keep the 128-row reference layout of the index in HBM (the path of texts >= 2^32 symbols) */
 } mc_params;
 
 void mc_params_default(mc_params *p);   /* defaults of reference src/main.cpp:159-191 */

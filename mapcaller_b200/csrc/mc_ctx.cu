@@ -156,7 +156,7 @@ struct HBuf {
 
 enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_COUNT };
 
-struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask; };
+struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask, rwin; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
 struct Staged { DBuf seq, roff, seed_off, cap, scan; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false; };
@@ -165,7 +165,7 @@ struct mc_ctx {
 	mc_params prm;
 	mc_stream_t stream;
 	// index replica
-	DBuf d_bwt, d_sa, d_pac, d_chrom_end, d_chrom_id;
+	DBuf d_bwt, d_cbwt, d_sa, d_pac, d_chrom_end, d_chrom_id;
 	DevIndex ix;
 	int64_t G;
 	// profile
@@ -178,7 +178,7 @@ struct mc_ctx {
 	DBuf d_slot_freq, d_seeds, d_slot_loc, d_loc_slot, d_pairs, d_npair;
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
-	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_bumps, d_stats, d_scan;
+	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_rwin, d_rw_beg, d_bumps, d_stats, d_scan;
 	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off;
 	HBuf h_disc;
 	HBuf h_bounce[2];
@@ -220,11 +220,11 @@ void mc_params_default(mc_params* p)
 void mc_ctx_destroy(mc_ctx* c)
 {
 	if (!c) return;
-	DBuf* bufs[] = {&c->d_bwt, &c->d_sa, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_base16, &c->d_sdiff, &c->d_cdiff, &c->d_mdiff, &c->d_rcount, &c->d_rflag, &c->d_bp, &c->d_ind,
+	DBuf* bufs[] = {&c->d_bwt, &c->d_cbwt, &c->d_sa, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_base16, &c->d_sdiff, &c->d_cdiff, &c->d_mdiff, &c->d_rcount, &c->d_rflag, &c->d_bp, &c->d_ind,
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
 	for (DBuf* b : bufs) b->release();
 	Staged* st[] = {&c->cur, &c->pipe[0], &c->pipe[1], &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); }
@@ -303,6 +303,17 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	bad |= dev_sync(c->stream);
 	if (bad) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
 	DevIndex& ix = c->ix;
+	ix.cbwt = nullptr;
+	if (v.seq_len < (1ull << 32) && !params->reserved[1])
+	{
+		// re-block the index into the compact 32-byte layout (mc_fmindex.h); the reference-layout copy is released afterwards
+		const int64_t ncb = (int64_t)((v.seq_len + 63) / 64) + 1;
+		if (c->d_cbwt.reserve((size_t)ncb * 32 + 64) || dev_zero(c->d_cbwt.p, (size_t)ncb * 32 + 64, c->stream)) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
+		launch_cbwt_build(ncb - 1, c->d_bwt.as<uint32_t>(), c->d_cbwt.as<uint32_t>(), c->stream);
+		if (dev_sync(c->stream)) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
+		ix.cbwt = c->d_cbwt.as<uint32_t>();
+		c->d_bwt.release();
+	}
 	ix.bwt = c->d_bwt.as<uint32_t>(); ix.sa = c->d_sa.as<uint64_t>(); ix.pac = c->d_pac.as<uint8_t>();
 	ix.chrom_end = c->d_chrom_end.as<int64_t>(); ix.chrom_id = c->d_chrom_id.as<int32_t>(); ix.n_end = (int32_t)ends.size();
 	ix.primary = v.primary; for (int i = 0; i < 5; i++) ix.L2[i] = v.L2[i]; ix.seq_len = v.seq_len; ix.G = G; ix.twoG = 2 * G;
@@ -434,7 +445,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(n_chunks * sizeof(mc_chunk_out));
 	bad |= c->d_chunk_lo.reserve(n_chunks * 4) || c->d_chunk_hi.reserve(n_chunks * 4);
 	bad |= c->d_pair_flag.reserve((n_pairs + 1) * 4) || c->d_est_lo.reserve((n_pairs + 1) * 4) || c->d_est_hi.reserve((n_pairs + 1) * 4);
-	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4 * 4) || c->d_accept.reserve(n + 1) || c->d_read_redo.reserve(n + 1);
+	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4 * 4) || c->d_rw_beg.reserve((n_pairs + 1) * 4) || c->d_accept.reserve(n + 1) || c->d_read_redo.reserve(n + 1);
 	bad |= c->h_chunk.reserve(n_chunks * sizeof(mc_chunk_out)) || c->h_chunk_lo.reserve(n_chunks * 4) || c->h_chunk_hi.reserve(n_chunks * 4);
 	if (bad) return MC_ERR_CUDA;
 	a.slot_freq = c->d_slot_freq.as<uint32_t>(); a.seeds = c->d_seeds.as<Seed>(); a.slot_loc = c->d_slot_loc.as<int64_t>();
@@ -442,10 +453,10 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	a.est = c->d_est.as<int32_t>(); a.active = c->d_active.as<uint8_t>(); a.chunk_out = c->d_chunk_out.as<mc_chunk_out>();
 	a.chunk_lo = c->d_chunk_lo.as<int32_t>(); a.chunk_hi = c->d_chunk_hi.as<int32_t>();
 	a.pair_flag = c->d_pair_flag.as<int32_t>(); a.est_lo = c->d_est_lo.as<int32_t>(); a.est_hi = c->d_est_hi.as<int32_t>();
-	a.pair_out = c->d_pair_out.as<mc_pair_out>(); a.rtask = c->d_rtask.as<int32_t>(); a.read_redo = c->d_read_redo.as<uint8_t>();
+	a.pair_out = c->d_pair_out.as<mc_pair_out>(); a.rtask = c->d_rtask.as<int32_t>(); a.rw_beg = c->d_rw_beg.as<int32_t>(); a.read_redo = c->d_read_redo.as<uint8_t>();
 	const int64_t rtask_cap = (n_pairs + 1) * 4;
 	Bumps* db = c->d_bumps.as<Bumps>();
-	a.pair_bump = &db->pair; a.frag_bump = &db->frag; a.aln_bump = &db->aln; a.task_bump = &db->task; a.dpws_bump = &db->dpws; a.rtask_bump = &db->rtask; a.ptask_bump = &db->ptask;
+	a.pair_bump = &db->pair; a.frag_bump = &db->frag; a.aln_bump = &db->aln; a.task_bump = &db->task; a.dpws_bump = &db->dpws; a.rtask_bump = &db->rtask; a.ptask_bump = &db->ptask; a.rwin_bump = &db->rwin; a.rwin_begin = 0;
 	a.prof.base16 = c->d_base16.as<uint32_t>(); a.prof.sdiff = c->d_sdiff.as<int32_t>(); a.prof.cdiff = c->d_cdiff.as<int32_t>(); a.prof.mdiff = c->d_mdiff.as<int32_t>();
 	a.prof.rcount = c->d_rcount.as<uint8_t>();
 
@@ -474,12 +485,12 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		const int64_t dpws_cap = (int64_t)(c->dpws_factor * (double)st.n_bytes) + (8 << 20);
 		const int64_t task_cap = (int64_t)(c->task_factor * (double)n) + 1024;
 		if (frag_cap >= 0x7fffffffll || aln_cap >= 0x7fffffffll || cand_total >= 0x7fffffffll) { mc_set_error("mc_map_batch: batch too large for 32-bit arena offsets; split it"); return MC_ERR_ARG; }
-		bad |= c->d_pairs.reserve(pair_cap * sizeof(SPair));
+		bad |= c->d_pairs.reserve(pair_cap * sizeof(SPair)) || c->d_rwin.reserve(c->rescue_cap * sizeof(RWin));
 		bad |= c->d_cands.reserve(cand_total * sizeof(Cand)) || c->d_cscore.reserve(cand_total * 4) || c->d_cpaired.reserve(cand_total * 4);
 		bad |= c->d_corient.reserve(cand_total * 4) || c->d_cfrag.reserve(cand_total * 4) || c->d_cnfrag.reserve(cand_total * 4) || c->d_ctmp.reserve(cand_total * 4);
 		bad |= c->d_ptask.reserve(frag_cap * 4) || c->d_frags.reserve(frag_cap * sizeof(mc_frag_out)) || c->d_aln.reserve(aln_cap) || c->d_tasks.reserve(task_cap * sizeof(DpTask)) || c->d_dpws.reserve(dpws_cap);
 		if (bad) return MC_ERR_CUDA;
-		a.pairs = c->d_pairs.as<SPair>(); a.pair_cap = pair_cap;
+		a.pairs = c->d_pairs.as<SPair>(); a.pair_cap = pair_cap; a.rwin = c->d_rwin.as<RWin>(); a.rwin_cap = c->rescue_cap;
 		a.cands = c->d_cands.as<Cand>(); a.cscore = c->d_cscore.as<int32_t>(); a.cpaired = c->d_cpaired.as<int32_t>(); a.corient = c->d_corient.as<int32_t>();
 		a.cfrag = c->d_cfrag.as<int32_t>(); a.cnfrag = c->d_cnfrag.as<int32_t>(); a.ctmp = c->d_ctmp.as<int32_t>();
 		a.ptask = c->d_ptask.as<int32_t>(); a.frags = c->d_frags.as<mc_frag_out>(); a.frag_cap = frag_cap; a.aln = c->d_aln.as<uint8_t>(); a.aln_cap = aln_cap;
@@ -514,7 +525,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			a.rtask_begin = (int64_t)hbp->rtask; a.task_begin = (int64_t)hbp->task; a.ptask_begin = (int64_t)hbp->ptask;
 			if (a.rtask_begin + n_pairs > rtask_cap) { mc_set_error("mc_map_batch: too many speculation replays in one batch"); return MC_ERR_OVERFLOW; }
 			bad |= dev_h2d(c->d_est.p, est.data(), n_chunks * 4, s) || dev_h2d(c->d_active.p, active.data(), n_chunks, s);
-			if (paired) { launch_pair(a, n_pairs, s); launch_rescue(a, n_pairs, s); } else launch_single(a, n, s);
+			if (paired) { bad |= dev_zero(&db->rwin, 8, s); launch_pair(a, n_pairs, s); launch_rescue(a, n_pairs, s); } else launch_single(a, n, s);
 			if (first_attempt) ev_record(&c->ev[EV_PAIR1], s);
 			first_attempt = false;
 			launch_alnprep(a, n, s);

@@ -107,9 +107,39 @@ MC_HD uint64_t mc_block_base(const OccBlock& b, int i)
 	return (i & 2) ? ((i & 1) ? cT : cG) : ((i & 1) ? cC : cA);
 }
 
-// One forward extension by base code c (reference src/bwt_search.cpp:138-149); false = empty child.
-// The two rows k, l fall into the same 128-row block in most steps (the reference's bwt_2occ4 fast path, :73);
-// the second block is only fetched when they do not, everything after the fetch is the same code for every lane.
+// ---- compact device layout ---------------------------------------------------------------------------------------
+// The on-disk / reference layout spends 32 of every 64 bytes on 64-bit counts and makes a lookup touch two 32-byte sectors
+// through four 128-bit loads.  For texts below 2^32 symbols the context re-blocks the index at upload time into 32-byte
+// blocks of 64 rows (4 x uint32 absolute counts + 4 x uint32 packed symbols, same density): a lookup is one sector and two
+// loads, and counts half as many words.  (mc_cbwt_build_body below; the 128-row layout stays the path for larger texts.)
+struct CBlock { mc_u32x4 cnt, w; };
+MC_HD void mc_load_cblock(const DevIndex& ix, uint64_t blk, CBlock& b)
+{
+	const uint32_t* p = ix.cbwt + (blk << 3);
+	b.cnt = mc_ldg128(p); b.w = mc_ldg128(p + 4);
+}
+MC_HD uint32_t mc_cblock_base(const CBlock& b, int i) { return (i & 2) ? ((i & 1) ? b.cnt.w : b.cnt.z) : ((i & 1) ? b.cnt.y : b.cnt.x); }
+MC_HD int mc_count_in_cblock(const CBlock& b, uint32_t flip, int nbits)
+{
+	const uint32_t a0 = b.w.x ^ flip, a1 = b.w.y ^ flip, a2 = b.w.z ^ flip, a3 = b.w.w ^ flip;
+	const uint32_t e0 = (a0 >> 1) & a0 & mc_prefix_pairs(nbits), e1 = (a1 >> 1) & a1 & mc_prefix_pairs(nbits - 32);
+	const uint32_t e2 = (a2 >> 1) & a2 & mc_prefix_pairs(nbits - 64), e3 = (a3 >> 1) & a3 & mc_prefix_pairs(nbits - 96);
+	return mc_popc(e0 + (e1 << 1)) + mc_popc(e2 + (e3 << 1));
+}
+// one compact block from the reference layout: block b covers rows [64 b, 64 b + 64) of source block b >> 1
+MC_HD void mc_cbwt_build_body(int64_t b, const uint32_t* src, uint32_t* dst)
+{
+	const uint32_t* s = src + ((b >> 1) << 4);
+	uint32_t c[4] = {(uint32_t)s[0], (uint32_t)s[2], (uint32_t)s[4], (uint32_t)s[6]};   // low halves of the 64-bit counts
+	const uint32_t* w = s + 8;
+	if (b & 1)
+		for (int j = 0; j < 4; j++)
+			for (int i = 0; i < 4; i++) { const uint32_t a = w[j] ^ mc_flip_of(i); c[i] += (uint32_t)mc_popc((a >> 1) & a & 0x55555555u); }
+	uint32_t* d = dst + (b << 3);
+	d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = c[3];
+	for (int j = 0; j < 4; j++) d[4 + j] = w[((b & 1) << 2) + j];
+}
+
 // the 48 bytes of a block that a count of symbol i needs: the 8 words and the 16-byte quarter holding count[i]
 // (A,C sit in the first quarter, G,T in the second).  Three 128-bit loads instead of four: the L1TEX tag stage, which
 // sees one wavefront per lane and load because every lane reads a different line, is what bounds this kernel (profiles/).
@@ -144,14 +174,26 @@ MC_HD bool mc_interval_extend(const DevIndex& ix, RcInterval& v, int c, uint32_t
 	const uint32_t flip = mc_flip_of(i);
 	const uint64_t k = v.x1 - 1, l = v.x1 - 1 + v.x2;                 // x1 >= 1, so k never is the (uint64)-1 row
 	const uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
-	OccPart bk, bl;
-	mc_load_part(ix, kk >> 7, i, bk);
-	const bool same = (kk >> 7) == (ll >> 7);
-	bl = bk;
-	if (!same) mc_load_part(ix, ll >> 7, i, bl);
-	*nblk += same ? 1u : 2u;
-	const uint64_t occ_k = mc_part_base(bk, i) + (uint64_t)mc_count_in_part(bk, flip, 2 * ((int)(kk & 127) + 1));
-	const uint64_t occ_l = mc_part_base(bl, i) + (uint64_t)mc_count_in_part(bl, flip, 2 * ((int)(ll & 127) + 1));
+	*nblk += (kk >> 7) == (ll >> 7) ? 1u : 2u;                         // blocks the reference algorithm touches (its layout)
+	uint64_t occ_k, occ_l;
+	if (ix.cbwt)
+	{
+		CBlock bk, bl;
+		mc_load_cblock(ix, kk >> 6, bk);
+		bl = bk;
+		if ((kk >> 6) != (ll >> 6)) mc_load_cblock(ix, ll >> 6, bl);
+		occ_k = (uint64_t)mc_cblock_base(bk, i) + (uint64_t)mc_count_in_cblock(bk, flip, 2 * ((int)(kk & 63) + 1));
+		occ_l = (uint64_t)mc_cblock_base(bl, i) + (uint64_t)mc_count_in_cblock(bl, flip, 2 * ((int)(ll & 63) + 1));
+	}
+	else
+	{
+		OccPart bk, bl;
+		mc_load_part(ix, kk >> 7, i, bk);
+		bl = bk;
+		if ((kk >> 7) != (ll >> 7)) mc_load_part(ix, ll >> 7, i, bl);
+		occ_k = mc_part_base(bk, i) + (uint64_t)mc_count_in_part(bk, flip, 2 * ((int)(kk & 127) + 1));
+		occ_l = mc_part_base(bl, i) + (uint64_t)mc_count_in_part(bl, flip, 2 * ((int)(ll & 127) + 1));
+	}
 	if (occ_l == occ_k) return false;
 	v.x1 = ix.L2[i] + 1 + occ_k; v.x2 = occ_l - occ_k;
 	return true;
@@ -161,6 +203,13 @@ MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k)
 {
 	if (k == ix.primary) return 0;
 	const uint64_t x = k - (k > ix.primary);
+	if (ix.cbwt)
+	{
+		CBlock b; mc_load_cblock(ix, x >> 6, b);
+		const uint32_t wsel = ((x & 63) >> 4) == 0 ? b.w.x : ((x & 63) >> 4) == 1 ? b.w.y : ((x & 63) >> 4) == 2 ? b.w.z : b.w.w;
+		const int c = (int)(wsel >> ((~(uint32_t)x & 15) << 1)) & 3;
+		return ix.L2[c] + (uint64_t)mc_cblock_base(b, c) + (uint64_t)mc_count_in_cblock(b, mc_flip_of(c), 2 * ((int)(x & 63) + 1));
+	}
 	OccBlock b; mc_load_block(ix, x >> 7, b);
 	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};
 	const int c = (int)(w[(x & 127) >> 4] >> ((~(uint32_t)x & 15) << 1)) & 3;

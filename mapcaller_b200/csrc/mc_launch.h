@@ -13,7 +13,14 @@ typedef int mc_stream_t;
 	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a); }
 #define MC_LAUNCH2(name) \
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
-static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) rescue_body(i, 0, 1, a, 0, 0); }
+static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t)
+{
+	for (int64_t i = 0; i < n; i++) rwenum_body(i, a);
+	if (a.st->overflow & 0xFF) return;
+	const int64_t nw = (int64_t)*a.rwin_bump - a.rwin_begin;
+	for (int64_t i = 0; i < nw; i++) rwin_body(i, 0, 1, a, 0, 0);
+	for (int64_t i = 0; i < n; i++) rcommit_body(i, a);
+}
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
 static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin; for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
@@ -22,6 +29,7 @@ static void launch_disclist(const PipeArgs& a, int64_t n, DiscRec* out, mc_u64* 
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, p, G, nb, sums); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
+static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
 #else
@@ -72,27 +80,46 @@ static void launch_piece(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
 	mc_piece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
-// rescue tasks: persistent warps, warp w takes tasks w, w + n_warps, ... of the current attempt's window.  A task is a long,
-// serial, latency-bound piece of code over small tables (word list, diagonal histogram, filter): they live in shared memory
-// (28 KB per warp, 4 warps per block); a lone warp going to global memory for them was ~20x slower.
+// rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent warps (warp w
+// takes windows w, w + n_warps, ...), commit per pair.  A window search is a serial, latency-bound piece of code over small
+// tables (word list, diagonal histogram, filter): they live in shared memory (28 KB per warp, 4 warps per block); a lone
+// warp going to global memory for them was ~20x slower.
 #define MC_RESCUE_WARPS 4
 #define MC_RESCUE_SMEM (28 * 1024)
+__global__ void __launch_bounds__(MC_BLOCK) mc_rwenum_kernel(const PipeArgs a)
+{
+	const int64_t n = (int64_t)*a.rtask_bump - a.rtask_begin;
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) rwenum_body(t, a);
+}
 __global__ void __launch_bounds__(MC_RESCUE_WARPS * 32) mc_rescue_kernel(const PipeArgs a)
 {
 	extern __shared__ __align__(16) uint8_t rescue_smem[];
+	if (a.st->overflow & 0xFF) return;          // the window list is incomplete: the attempt is going to be repeated with larger arenas
 	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-	const int64_t n = (int64_t)*a.rtask_bump - a.rtask_begin;
+	const int64_t n = (int64_t)*a.rwin_bump - a.rwin_begin;
 	uint8_t* mine = rescue_smem + (threadIdx.x >> 5) * MC_RESCUE_SMEM;
-	for (int64_t t = warp; t < n; t += n_warps) { rescue_body(t, threadIdx.x & 31, 32, a, mine, MC_RESCUE_SMEM); __syncwarp(); }
+	for (int64_t t = warp; t < n; t += n_warps) { rwin_body(t, threadIdx.x & 31, 32, a, mine, MC_RESCUE_SMEM); __syncwarp(); }
+}
+__global__ void __launch_bounds__(MC_BLOCK) mc_rcommit_kernel(const PipeArgs a)
+{
+	if (a.st->overflow & 0xFF) return;
+	const int64_t n = (int64_t)*a.rtask_bump - a.rtask_begin;
+	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) rcommit_body(t, a);
 }
 static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
 	static bool configured = false;
 	if (!configured) { cudaFuncSetAttribute(mc_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_RESCUE_WARPS * MC_RESCUE_SMEM); configured = true; }
-	int64_t blocks = (max_tasks + MC_RESCUE_WARPS - 1) / MC_RESCUE_WARPS; if (blocks > 148 * 2) blocks = 148 * 2;
-	mc_rescue_kernel<<<(unsigned)blocks, MC_RESCUE_WARPS * 32, MC_RESCUE_WARPS * MC_RESCUE_SMEM, s>>>(a); g_launches++;
+	int64_t tb = (max_tasks + MC_BLOCK - 1) / MC_BLOCK; if (tb > 148 * 2) tb = 148 * 2;
+	mc_rwenum_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
+	mc_rescue_kernel<<<148 * 2, MC_RESCUE_WARPS * 32, MC_RESCUE_WARPS * MC_RESCUE_SMEM, s>>>(a); g_launches++;
+	mc_rcommit_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
+__global__ void __launch_bounds__(MC_BLOCK) mc_cbwt_build_kernel(int64_t n, const uint32_t* src, uint32_t* dst)
+{ int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < n) mc_cbwt_build_body(b, src, dst); }
+static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t s)
+{ if (n > 0) { mc_cbwt_build_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, src, dst); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t* sums)
 { int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < nb) profsum_body(b, p, G, nb, sums); }
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t s)

@@ -22,6 +22,8 @@
 // Shared argument block: every stage sees the same set of arenas.
 // ------------------------------------------------------------------------------------------------
 struct ReadSum { int32_t score, sub_score, best_idx, n_live; };
+// one window of AlignmentRescue: place the mate of `pair` (dir 0: mate 2, dir 1: mate 1) next to candidate `cand` of the other mate
+struct RWin { int32_t pair; int16_t dir; int16_t pad; int32_t cand; int32_t floor; int32_t ok; int32_t score; int32_t pbeg; int32_t n; int32_t lo; int32_t hi; };
 
 struct PipeArgs {
 	DevIndex ix;
@@ -73,6 +75,8 @@ struct PipeArgs {
 	uint8_t* dpws; int64_t dpws_cap; mc_u64* dpws_bump;
 	int32_t* rtask;          // rescue task list (pair ids)
 	mc_u64* rtask_bump;
+	struct RWin* rwin; mc_u64* rwin_bump; int64_t rwin_begin, rwin_cap;   // rescue windows of the current attempt: [rwin_begin, *rwin_bump)
+	int32_t* rw_beg;         // per pair: first window of its rescue task
 	int64_t rtask_begin, task_begin; // tasks of the current attempt are [begin, *bump)
 	// profile
 	DevProfile prof;

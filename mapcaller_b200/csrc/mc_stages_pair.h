@@ -223,8 +223,8 @@ MC_HD int rescue_scan_diag(const uint32_t* wkid0, const KmerEnt* km, int nk, int
 // diagonal is reduced over the lanes, (5) lane 0 appends the candidate.
 // *iv_lo / *iv_hi are narrowed to the EstiDistance values for which this call provably does the same: the moving edge stays
 // between the same chromosome ends and no 8-mer hit enters or leaves the window.  All lanes return the same values.
-MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const KmerEnt* km, int nk, int rlen, int dir, int64_t d, int est,
-                      int floor_score, int anchor_idx, uint32_t* hits, int64_t n_hits, int32_t* lanebuf, const uint32_t* bloom, int32_t* new_idx, int* iv_lo, int* iv_hi)
+MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const KmerEnt* km, int nk, int rlen, int dir, int64_t d, int est,
+                      int floor_score, uint32_t* hits, int64_t n_hits, int32_t* lanebuf, const uint32_t* bloom, int* iv_lo, int* iv_hi)
 {
 	const int M = MC_RESCUE_MARGIN;
 	int64_t left = dir == 0 ? d : d - (int64_t)(uint32_t)est;
@@ -340,53 +340,64 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, int64_t rt, const Kme
 	if (best == 0 || best <= floor_score) return false;
 	if (lane == 0)
 	{
-		int n = 0, ok = 1, k = -1;
+		int n = 0, ok = 1;
 		rescue_scan_diag(wkid0, km, nk, left, slen, bd, 0, &n);
 		const int64_t pb = (int64_t)mc_atomic_add(a.pair_bump, (mc_u64)n);
 		if (pb + n > a.pair_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 0); ok = 0; }
-		if (ok)
-		{
-			rescue_scan_diag(wkid0, km, nk, left, slen, bd, a.pairs + pb, &n);
-			const int64_t co = pa_cand_off(a, rt);
-			k = a.ncand[rt];
-			if (k >= pa_cand_cap(a, rt)) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 40); ok = 0; }
-			else
-			{
-				Cand c; c.score = best; c.pbeg = (int32_t)pb; c.pend = (int32_t)(pb + n);
-				a.cands[co + k] = c; a.cscore[co + k] = best; a.cpaired[co + k] = anchor_idx;
-				a.ncand[rt] = k + 1;
-			}
-		}
-		lanebuf[6 * nl] = ok; lanebuf[6 * nl + 1] = k;
+		if (ok) { rescue_scan_diag(wkid0, km, nk, left, slen, bd, a.pairs + pb, &n); res->score = best; res->pbeg = (int32_t)pb; res->n = n; }
+		lanebuf[6 * nl] = ok;
 	}
 	MC_WARP_SYNC();
-	const int ok = lanebuf[6 * nl]; *new_idx = lanebuf[6 * nl + 1];
+	const int ok = lanebuf[6 * nl];
 	MC_WARP_SYNC();
 	return ok != 0;
 }
 
-// `fast` / `fast_bytes`: optional on-chip scratch of the calling warp (shared memory on the GPU); tasks that need more fall
-// back to the global gapped-fill workspace.
-MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* fast, int64_t fast_bytes)
+// AlignmentRescue (reference src/AlignmentRescue.cpp:28-111) in three steps, because one pair may imply dozens of windows
+// (a mate anchored in a repeat family) and the windows are independent of each other: the candidates they test, the score
+// floors (the mates' best scores on entry) and the skip tests do not change while the reference loops over them.
+//   rwenum_body   one thread per rescue pair: strategy, thresholds, the list of windows
+//   rwin_body     one warp per window: the search itself
+//   rcommit_body  one thread per rescue pair: appends the found candidates in the reference's order, links the partners,
+//                 masks, and intersects the EstiDistance validity intervals
+MC_HD void rwenum_body(int64_t t, const PipeArgs& a)
 {
 	if (a.rtask_begin + t >= (int64_t)*a.rtask_bump) return;
 	const int64_t p = a.rtask[a.rtask_begin + t];
 	const int64_t r0 = 2 * p, r1 = r0 + 1;
-	const int est = a.est[pa_chunk_of_read(r0)];
 	const int64_t c0 = pa_cand_off(a, r0), c1 = pa_cand_off(a, r1);
 	const int l0 = (int)(a.roff[r0 + 1] - a.roff[r0]), l1 = (int)(a.roff[r1 + 1] - a.roff[r1]);
-	int32_t *s0 = a.cscore + c0, *s1 = a.cscore + c1, *p0 = a.cpaired + c0, *p1 = a.cpaired + c1;
+	const int32_t *s0 = a.cscore + c0, *s1 = a.cscore + c1;
 	const int n0 = a.ncand[r0], n1 = a.ncand[r1];
 	int b0 = 0, b1 = 0;
 	for (int i = 0; i < n0; i++) if (s0[i] > b0) b0 = s0[i];
 	for (int j = 0; j < n1; j++) if (s1[j] > b1) b1 = s1[j];
 	const int strat = (b0 - b1 > (l1 >> 2)) ? 1 : (b1 - b0 > (l0 >> 2)) ? 2 : 3;
-	int rescued = 0, iv_lo = -2147483647, iv_hi = 2147483647;
-	// scratch in the (still unused) gapped-fill workspace: both word lists, the diagonal histogram, the lane buffer, the filter,
-	// the list of filter survivors
-	const int lmax = l0 > l1 ? l0 : l1;
-	const int64_t n_hits = (int64_t)(uint32_t)est + 3 * (int64_t)lmax + 2 * MC_RESCUE_MARGIN + 16;
-	const int64_t wsn = ((int64_t)(l0 + l1 + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (6 * nl + 4) * 4 + 128 * 4 + n_hits * 4 + n_hits * 4 + n_hits + 15) & ~15ll;
+	int nw = 0;
+	if (strat != 2) for (int i = 0; i < n0; i++) if (s0[i] >= (b0 >> 1)) nw++;   // nothing is paired yet: PairedAlnCanIdx == -1 everywhere
+	if (strat != 1) for (int j = 0; j < n1; j++) if (s1[j] >= (b1 >> 1)) nw++;
+	const int64_t wb = mc_bump_alloc(a.rwin_bump, (uint32_t)nw);
+	a.rw_beg[p] = (int32_t)wb;
+	if (wb + nw > a.rwin_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 0); return; }
+	RWin w; w.pair = (int32_t)p; w.pad = 0; w.ok = 0; w.score = 0; w.pbeg = 0; w.n = 0; w.lo = -2147483647; w.hi = 2147483647;
+	int k = 0;
+	if (strat != 2) for (int i = 0; i < n0; i++) if (s0[i] >= (b0 >> 1)) { w.dir = 0; w.cand = i; w.floor = b1; a.rwin[wb + k++] = w; }
+	if (strat != 1) for (int j = 0; j < n1; j++) if (s1[j] >= (b1 >> 1)) { w.dir = 1; w.cand = j; w.floor = b0; a.rwin[wb + k++] = w; }
+}
+
+// `fast` / `fast_bytes`: optional on-chip scratch of the calling warp (shared memory on the GPU); windows that need more fall
+// back to the global gapped-fill workspace.
+MC_HD void rwin_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* fast, int64_t fast_bytes)
+{
+	RWin* w = a.rwin + a.rwin_begin + t;
+	const int64_t p = w->pair;
+	const int dir = w->dir;
+	const int64_t ra = 2 * p + dir, rm = 2 * p + (1 - dir);       // anchored read, mate to place
+	const int est = a.est[pa_chunk_of_read(ra)];
+	const int lm = (int)(a.roff[rm + 1] - a.roff[rm]);
+	const int64_t d = cand_posdiff(a, a.cands[pa_cand_off(a, ra) + w->cand]);
+	const int64_t n_hits = (int64_t)(uint32_t)est + 2 * (int64_t)lm + 2 * MC_RESCUE_MARGIN + 32;
+	const int64_t wsn = ((int64_t)(lm + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (6 * nl + 4) * 4 + 128 * 4 + n_hits * 4 + n_hits * 4 + n_hits + 15) & ~15ll;
 	uint8_t* scratch = fast;
 	if (!fast || wsn > fast_bytes)
 	{
@@ -396,57 +407,50 @@ MC_HD void rescue_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* 
 		if (ws + wsn > a.dpws_cap) { if (lane == 0) mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
 		scratch = a.dpws + ws;
 	}
-	KmerEnt* km0 = (KmerEnt*)scratch; KmerEnt* km1 = km0 + l0 + 1;
-	uint32_t* hits = (uint32_t*)(km1 + l1 + 1); int32_t* lanebuf = (int32_t*)(hits + n_hits);
-	uint32_t* bloom = (uint32_t*)(lanebuf + 6 * nl + 4);   // 4096-bit filter over the low 12 bits of the read's word ids
-	if (strat == 1 || strat == 3) // place mate 2 next to mate 1's candidates
+	KmerEnt* km = (KmerEnt*)scratch;
+	uint32_t* hits = (uint32_t*)(km + lm + 2); int32_t* lanebuf = (int32_t*)(hits + n_hits);
+	uint32_t* bloom = (uint32_t*)(lanebuf + 6 * nl + 4);   // 4096-bit filter over the low 12 bits of the mate's word ids
+	for (int i = lane; i < 128; i += nl) bloom[i] = 0;
+	MC_WARP_SYNC();
+	const int nk = kmer_list_coop(a.seq + a.roff[rm], lm, km, lane, nl, lanebuf);
+	for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km[i].wid & 4095) >> 5], 1u << (km[i].wid & 31));
+	MC_WARP_SYNC();
+	int lo = -2147483647, hi = 2147483647;
+	const bool ok = rescue_try(a, lane, nl, w, km, nk, lm, dir, d, est, w->floor, hits, n_hits, lanebuf, bloom, &lo, &hi);
+	if (lane == 0) { w->ok = ok ? 1 : 0; w->lo = lo; w->hi = hi; }
+}
+
+MC_HD void rcommit_body(int64_t t, const PipeArgs& a)
+{
+	if (a.rtask_begin + t >= (int64_t)*a.rtask_bump) return;
+	const int64_t p = a.rtask[a.rtask_begin + t];
+	const int64_t r0 = 2 * p, r1 = r0 + 1;
+	const int64_t c0 = pa_cand_off(a, r0), c1 = pa_cand_off(a, r1);
+	int32_t *s0 = a.cscore + c0, *s1 = a.cscore + c1, *p0 = a.cpaired + c0, *p1 = a.cpaired + c1;
+	int rescued = 0, iv_lo = -2147483647, iv_hi = 2147483647;
+	const RWin* w = a.rwin + a.rw_beg[p];
+	// the windows of this pair are contiguous and in the reference's loop order; the list ends where another pair's begins
+	for (int k = 0; a.rw_beg[p] + k < (int64_t)*a.rwin_bump && w[k].pair == (int32_t)p; k++)
 	{
-		for (int i = lane; i < 128; i += nl) bloom[i] = 0;
-		MC_WARP_SYNC();
-		const int nk = kmer_list_coop(a.seq + a.roff[r1], l1, km1, lane, nl, lanebuf);
-		for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km1[i].wid & 4095) >> 5], 1u << (km1[i].wid & 31));
-		MC_WARP_SYNC();
-		const int thr = b0 >> 1;
-		for (int i = 0; i < n0; i++)
-		{
-			if (s0[i] < thr || p0[i] != -1) continue;
-			const int64_t d = cand_posdiff(a, a.cands[c0 + i]);
-			int32_t k;
-			if (rescue_try(a, lane, nl, r1, km1, nk, l1, 0, d, est, b1, i, hits, n_hits, lanebuf, bloom, &k, &iv_lo, &iv_hi)) { if (lane == 0) p0[i] = k; rescued++; }
-			MC_WARP_SYNC();
-		}
+		if (w[k].lo > iv_lo) iv_lo = w[k].lo;
+		if (w[k].hi < iv_hi) iv_hi = w[k].hi;
+		if (!w[k].ok) continue;
+		const int64_t rt = w[k].dir == 0 ? r1 : r0, ct = w[k].dir == 0 ? c1 : c0;
+		const int slot = a.ncand[rt];
+		if (slot >= pa_cand_cap(a, rt)) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 40); continue; }
+		Cand c; c.score = w[k].score; c.pbeg = w[k].pbeg; c.pend = w[k].pbeg + w[k].n;
+		a.cands[ct + slot] = c; a.cscore[ct + slot] = w[k].score; a.cpaired[ct + slot] = w[k].cand;
+		a.ncand[rt] = slot + 1;
+		if (w[k].dir == 0) p0[w[k].cand] = slot; else p1[w[k].cand] = slot;
+		rescued++;
 	}
-	if (strat == 2 || strat == 3) // place mate 1 next to mate 2's candidates
-	{
-		for (int i = lane; i < 128; i += nl) bloom[i] = 0;
-		MC_WARP_SYNC();
-		const int nk = kmer_list_coop(a.seq + a.roff[r0], l0, km0, lane, nl, lanebuf);
-		for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km0[i].wid & 4095) >> 5], 1u << (km0[i].wid & 31));
-		MC_WARP_SYNC();
-		const int thr = b1 >> 1;
-		const int n1_now = a.ncand[r1];
-		for (int j = 0; j < n1_now; j++)
-		{
-			if (s1[j] < thr || p1[j] != -1) continue;
-			const int64_t d = cand_posdiff(a, a.cands[c1 + j]);
-			int32_t k;
-			if (rescue_try(a, lane, nl, r0, km0, nk, l0, 1, d, est, b0, j, hits, n_hits, lanebuf, bloom, &k, &iv_lo, &iv_hi)) { if (lane == 0) p1[j] = k; rescued++; }
-			MC_WARP_SYNC();
-		}
-	}
-#ifdef MC_HOSTEMU
-	if (getenv("MC_TRACE_RESCUE")) fprintf(stderr, "[rescue] pair %lld strat %d n0 %d n1 %d b0 %d b1 %d rescued %d iv [%d,%d] est %d\n", (long long)p, strat, n0, n1, b0, b1, rescued, iv_lo, iv_hi, est);
-#endif
-	if (lane == 0)
-	{
-		const int m0 = a.ncand[r0], m1 = a.ncand[r1];
-		if (rescued == 0) { remove_redundant(s0, m0); remove_redundant(s1, m1); }
-		else mask_unpaired(s0, p0, m0, s1, p1, m1);
-		// the pair's outcome holds for every EstiDistance inside both the interval of its distance tests (pair_body) and the
-		// interval of its rescue windows
-		if (iv_lo > a.est_lo[p]) a.est_lo[p] = iv_lo;
-		if (iv_hi < a.est_hi[p]) a.est_hi[p] = iv_hi;
-	}
+	const int m0 = a.ncand[r0], m1 = a.ncand[r1];
+	if (rescued == 0) { remove_redundant(s0, m0); remove_redundant(s1, m1); }
+	else mask_unpaired(s0, p0, m0, s1, p1, m1);
+	// the pair's outcome holds for every EstiDistance inside both the interval of its distance tests (pair_body) and the
+	// intervals of its rescue windows
+	if (iv_lo > a.est_lo[p]) a.est_lo[p] = iv_lo;
+	if (iv_hi < a.est_hi[p]) a.est_hi[p] = iv_hi;
 }
 
 #endif

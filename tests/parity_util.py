@@ -89,13 +89,13 @@ def oracle_results(case, index, want_reads: bool = True):
         return out
 
 
-def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool = True, device: int = 0):
+def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool = True, device: int = 0, **extra):
     from mapcaller_b200 import api
     seq, off = case["seq"], case["off"]
     n = len(off) - 1
     batch_reads = batch_reads or n
     out = dict(reads=[], est=[], replays=0)
-    with api.Context(index, want_alignments=int(want_reads), update_profile=1, device=device, **case["params"]) as ctx:
+    with api.Context(index, want_alignments=int(want_reads), update_profile=1, device=device, **case["params"], **extra) as ctx:
         for b in range(0, n, batch_reads):
             e = min(n, b + batch_reads)
             res = ctx.map_batch(seq[off[b]:off[e]], off[b:e + 1] - off[b])

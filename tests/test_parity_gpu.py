@@ -71,6 +71,19 @@ def test_batch_split_invariance(built, batch_reads):
     pu.assert_same(parts, whole)
 
 
+def test_index_layouts_agree(built):
+    """Texts shorter than 2^32 symbols use the compact device index (32-byte blocks of 64 rows); longer ones the reference's
+    128-row blocks (mc_params.reserved[1] forces them).  Same results, same work counters."""
+    case = pu.make_case(seed=31, n_pairs=6000, genome_len=150000, contigs=2, n_rate=0.002, paired=1)
+    ix = pu.build_index(case)
+    compact = pu.cuda_results(case, ix)
+    wide = pu.cuda_results(case, ix, reserved=(0, 1, 0, 0, 0))
+    pu.assert_same(wide, compact)
+    for k in ("seed_blocks", "sa_reads", "locate_blocks"):
+        assert wide["stats"][k] == compact["stats"][k], k
+    pu.assert_same(wide, pu.oracle_results(case, ix))
+
+
 def test_pipelined_large_batch_equals_resident_path(built):
     """A profile-only batch of >= 400 k reads is cut into pieces whose upload overlaps the mapping of the previous piece
     (copy stream); the result must equal the single-piece path (mc_stage_batch + mc_map_staged) and the chunk-wise path."""
