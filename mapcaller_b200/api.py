@@ -253,6 +253,16 @@ class Context:
                                     out1.ctypes.data, out2.ctypes.data, ln.ctypes.data), "mc_align_batch")
         return [(out1[oo[i]:oo[i] + ln[i]].tobytes(), out2[oo[i]:oo[i] + ln[i]].tobytes()) for i in range(n)]
 
+    def bwt_search_batch(self, codes: np.ndarray, off: np.ndarray, start: np.ndarray):
+        """BWT_Search for n (codes[off[i]:off[i+1]], start[i]) queries -> (len[n], freq[n], list of sorted location arrays)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8); off = np.ascontiguousarray(off, dtype=np.int64)
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        n = len(start)
+        ln = np.zeros(n, dtype=np.int32); fr = np.zeros(n, dtype=np.int32); loc = np.zeros((n, 50), dtype=np.uint64)
+        _check(lib().mc_bwt_search_batch(self._h, n, codes.ctypes.data, off.ctypes.data, start.ctypes.data, ln.ctypes.data, fr.ctypes.data,
+                                         loc.ctypes.data), "mc_bwt_search_batch")
+        return ln, fr, [np.sort(loc[i, :fr[i]]) for i in range(n)]
+
     def totals(self) -> dict:
         t = Totals()
         _check(lib().mc_get_totals(self._h, C.byref(t)), "mc_get_totals")

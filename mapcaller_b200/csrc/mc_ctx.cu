@@ -1029,7 +1029,32 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 }
 #endif
 
-int mc_bwt_search_batch(mc_ctx*, int64_t, const uint8_t*, const int64_t*, const int32_t*, int32_t*, int32_t*, uint64_t*) { mc_set_error("not implemented yet"); return MC_ERR_ARG; }
+// Operator-level entry: n independent BWT_Search queries through the extension / locate primitives the pipeline uses.
+int mc_bwt_search_batch(mc_ctx* c, int64_t n, const uint8_t* codes, const int64_t* off, const int32_t* start, int32_t* out_len, int32_t* out_freq, uint64_t* out_loc)
+{
+	if (!c || n < 0 || (n > 0 && (!codes || !off || !start || !out_len || !out_freq || !out_loc))) { mc_set_error("mc_bwt_search_batch: bad argument"); return MC_ERR_ARG; }
+	if (n == 0) return MC_OK;
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	const mc_stream_t s = c->stream;
+	const int64_t bytes = off[n] - off[0];
+	if (bytes < 0) { mc_set_error("mc_bwt_search_batch: offsets decrease"); return MC_ERR_ARG; }
+	DBuf d_codes, d_off, d_start, d_len, d_freq, d_loc;
+	int bad = d_codes.reserve(bytes + 16) || d_off.reserve((n + 1) * 8) || d_start.reserve(n * 4) || d_len.reserve(n * 4) || d_freq.reserve(n * 4) || d_loc.reserve(n * MC_MAX_OCC * 8);
+	bad = bad || dev_h2d(d_codes.p, codes + off[0], bytes, s) || dev_h2d(d_off.p, off, (n + 1) * 8, s) || dev_h2d(d_start.p, start, n * 4, s) || dev_zero(d_loc.p, n * MC_MAX_OCC * 8, s);
+	if (!bad)
+	{
+		SearchArgs a; a.ix = c->ix; a.codes = d_codes.as<uint8_t>() - off[0]; a.off = d_off.as<int64_t>(); a.start = d_start.as<int32_t>();
+		a.len = d_len.as<int32_t>(); a.freq = d_freq.as<int32_t>(); a.loc = d_loc.as<uint64_t>();
+		launch_bwtsearch(a, n, s);
+		bad = dev_d2h(out_len, d_len.p, n * 4, s) || dev_d2h(out_freq, d_freq.p, n * 4, s) || dev_d2h(out_loc, d_loc.p, n * MC_MAX_OCC * 8, s) || dev_sync(s);
+	}
+	DBuf* all[] = {&d_codes, &d_off, &d_start, &d_len, &d_freq, &d_loc};
+	for (DBuf* b : all) b->release();
+	if (bad) { mc_set_error("mc_bwt_search_batch: CUDA failure"); return MC_ERR_CUDA; }
+	return MC_OK;
+}
 // Operator-level entry: n independent gapped fills through dp_body (the kernel the pipeline uses).
 int mc_align_batch(mc_ctx* c, int32_t use_ksw2, int64_t n, const uint8_t* s1, const int64_t* off1, const uint8_t* s2, const int64_t* off2,
                    const int64_t* out_off, uint8_t* out1, uint8_t* out2, int32_t* out_len)

@@ -90,7 +90,7 @@ static __device__ __forceinline__ void mc_stat_add(mc_u64* p, uint32_t v)
 // ---- FM-index replica in HBM (layout of the reference's bwt_t, unchanged) ------------------------
 struct DevIndex {
 	const uint32_t* bwt;   // reference layout, 64-byte blocks: 4 x uint64 occ counts + 8 x uint32 packed symbols (128 rows)
-	const uint32_t* cbwt;  // compact device layout (texts < 2^32 symbols), 32-byte blocks: 4 x uint32 counts + 4 x uint32 packed symbols (64 rows); 0 = not built
+	const uint32_t* cbwt;  // compact device layout (texts < 2^32 symbols), 32-byte blocks of 64 rows: 4 x uint32 counts + low-bit plane + high-bit plane; 0 = not built
 	const uint64_t* sa;    // every 32nd row
 	const uint8_t* pac;    // forward 2-bit text; revcomp half derived on the fly
 	const int64_t* chrom_end; // sorted keys of PosChrIdMap (reference src/bwt_index.cpp:253-254)

@@ -16,7 +16,10 @@
 MC_HD int mc_nt4(uint8_t c)
 {
 	// nst_nt4_table (reference src/BWT_Index/bntseq.c:40-57): ACGT / acgt -> 0..3, everything else 4
-	switch (c & 0xDF) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 4; }
+	// branch-free: bits 0, 2, 6, 19 of 0x80045 mark A, C, G, T among the folded letters; their bits 1..2 spell the code
+	const uint32_t u = c & 0xDFu, idx = u - 65u;
+	const uint32_t valid = (0x80045u >> (idx < 31u ? idx : 31u)) & 1u;
+	return valid ? (int)(((u >> 1) ^ (u >> 2)) & 3u) : 4;
 }
 
 MC_HD uint8_t mc_complement(uint8_t c)
@@ -110,21 +113,36 @@ MC_HD uint64_t mc_block_base(const OccBlock& b, int i)
 // ---- compact device layout ---------------------------------------------------------------------------------------
 // The on-disk / reference layout spends 32 of every 64 bytes on 64-bit counts and makes a lookup touch two 32-byte sectors
 // through four 128-bit loads.  For texts below 2^32 symbols the context re-blocks the index at upload time into 32-byte
-// blocks of 64 rows (4 x uint32 absolute counts + 4 x uint32 packed symbols, same density): a lookup is one sector and two
-// loads, and counts half as many words.  (mc_cbwt_build_body below; the 128-row layout stays the path for larger texts.)
-struct CBlock { mc_u32x4 cnt, w; };
-MC_HD void mc_load_cblock(const DevIndex& ix, uint64_t blk, CBlock& b)
+// blocks of 64 rows: 4 x uint32 absolute counts, then the 64 symbols as two bit planes (low bits, high bits; row r of the
+// block is bit r).  A lookup is ONE sector fetched by ONE 256-bit load (LDG.E.256 is new with sm_100), and the count of a
+// symbol among the first n rows is two 3-input logic ops and a POPC per 32 rows.  Rows fit 32 bits, so the search state
+// does as well.  (mc_cbwt_build_body below; the 128-row layout stays the path for larger texts.)
+struct CBlock { uint32_t c0, c1, c2, c3, lo0, lo1, hi0, hi1; };
+#ifdef MC_HOSTEMU
+static inline void mc_load_cblock(const DevIndex& ix, uint32_t blk, CBlock& b) { memcpy(&b, ix.cbwt + ((size_t)blk << 3), 32); }
+static inline uint32_t mc_prefix_bits(int n) { return n <= 0 ? 0u : n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1u; }
+#else
+static __device__ __forceinline__ void mc_load_cblock(const DevIndex& ix, uint32_t blk, CBlock& b)
 {
-	const uint32_t* p = ix.cbwt + (blk << 3);
-	b.cnt = mc_ldg128(p); b.w = mc_ldg128(p + 4);
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(b.lo0), "=r"(b.lo1), "=r"(b.hi0), "=r"(b.hi1) : "l"(ix.cbwt + ((size_t)blk << 3)));
 }
-MC_HD uint32_t mc_cblock_base(const CBlock& b, int i) { return (i & 2) ? ((i & 1) ? b.cnt.w : b.cnt.z) : ((i & 1) ? b.cnt.y : b.cnt.x); }
-MC_HD int mc_count_in_cblock(const CBlock& b, uint32_t flip, int nbits)
+// mask of the low min(n, 32) bits: high word of 0:FFFFFFFF << n, shift clamped to 32
+static __device__ __forceinline__ uint32_t mc_prefix_bits(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(n, 0)); }
+#endif
+MC_HD uint32_t mc_cblock_base(const CBlock& b, int i) { return (i & 2) ? ((i & 1) ? b.c3 : b.c2) : ((i & 1) ? b.c1 : b.c0); }
+// symbol i among the first n rows of the block (1 <= n <= 64)
+MC_HD uint32_t mc_count_in_cblock(const CBlock& b, int i, int n)
 {
-	const uint32_t a0 = b.w.x ^ flip, a1 = b.w.y ^ flip, a2 = b.w.z ^ flip, a3 = b.w.w ^ flip;
-	const uint32_t e0 = (a0 >> 1) & a0 & mc_prefix_pairs(nbits), e1 = (a1 >> 1) & a1 & mc_prefix_pairs(nbits - 32);
-	const uint32_t e2 = (a2 >> 1) & a2 & mc_prefix_pairs(nbits - 64), e3 = (a3 >> 1) & a3 & mc_prefix_pairs(nbits - 96);
-	return mc_popc(e0 + (e1 << 1)) + mc_popc(e2 + (e3 << 1));
+	const uint32_t fl = (i & 1) ? 0u : 0xFFFFFFFFu, fh = (i & 2) ? 0u : 0xFFFFFFFFu;
+	const uint32_t e0 = ((b.lo0 ^ fl) & mc_prefix_bits(n)) & (b.hi0 ^ fh);
+	const uint32_t e1 = ((b.lo1 ^ fl) & mc_prefix_bits(n - 32)) & (b.hi1 ^ fh);
+	return (uint32_t)(mc_popc(e0) + mc_popc(e1));
+}
+MC_HD int mc_cblock_symbol(const CBlock& b, uint32_t r)
+{
+	const uint32_t lo = (r & 32) ? b.lo1 : b.lo0, hi = (r & 32) ? b.hi1 : b.hi0;
+	return (int)(((lo >> (r & 31)) & 1u) | (((hi >> (r & 31)) & 1u) << 1));
 }
 // one compact block from the reference layout: block b covers rows [64 b, 64 b + 64) of source block b >> 1
 MC_HD void mc_cbwt_build_body(int64_t b, const uint32_t* src, uint32_t* dst)
@@ -135,9 +153,14 @@ MC_HD void mc_cbwt_build_body(int64_t b, const uint32_t* src, uint32_t* dst)
 	if (b & 1)
 		for (int j = 0; j < 4; j++)
 			for (int i = 0; i < 4; i++) { const uint32_t a = w[j] ^ mc_flip_of(i); c[i] += (uint32_t)mc_popc((a >> 1) & a & 0x55555555u); }
+	uint32_t lo[2] = {0, 0}, hi[2] = {0, 0};
+	for (int r = 0; r < 64; r++)
+	{
+		const uint32_t sym = (w[((b & 1) << 2) + (r >> 4)] >> ((~(uint32_t)r & 15) << 1)) & 3u;
+		lo[r >> 5] |= (sym & 1u) << (r & 31); hi[r >> 5] |= (sym >> 1) << (r & 31);
+	}
 	uint32_t* d = dst + (b << 3);
-	d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = c[3];
-	for (int j = 0; j < 4; j++) d[4 + j] = w[((b & 1) << 2) + j];
+	d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = c[3]; d[4] = lo[0]; d[5] = lo[1]; d[6] = hi[0]; d[7] = hi[1];
 }
 
 // the 48 bytes of a block that a count of symbol i needs: the 8 words and the 16-byte quarter holding count[i]
@@ -174,28 +197,39 @@ MC_HD bool mc_interval_extend(const DevIndex& ix, RcInterval& v, int c, uint32_t
 	const uint32_t flip = mc_flip_of(i);
 	const uint64_t k = v.x1 - 1, l = v.x1 - 1 + v.x2;                 // x1 >= 1, so k never is the (uint64)-1 row
 	const uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
-	*nblk += (kk >> 7) == (ll >> 7) ? 1u : 2u;                         // blocks the reference algorithm touches (its layout)
-	uint64_t occ_k, occ_l;
-	if (ix.cbwt)
-	{
-		CBlock bk, bl;
-		mc_load_cblock(ix, kk >> 6, bk);
-		bl = bk;
-		if ((kk >> 6) != (ll >> 6)) mc_load_cblock(ix, ll >> 6, bl);
-		occ_k = (uint64_t)mc_cblock_base(bk, i) + (uint64_t)mc_count_in_cblock(bk, flip, 2 * ((int)(kk & 63) + 1));
-		occ_l = (uint64_t)mc_cblock_base(bl, i) + (uint64_t)mc_count_in_cblock(bl, flip, 2 * ((int)(ll & 63) + 1));
-	}
-	else
-	{
-		OccPart bk, bl;
-		mc_load_part(ix, kk >> 7, i, bk);
-		bl = bk;
-		if ((kk >> 7) != (ll >> 7)) mc_load_part(ix, ll >> 7, i, bl);
-		occ_k = mc_part_base(bk, i) + (uint64_t)mc_count_in_part(bk, flip, 2 * ((int)(kk & 127) + 1));
-		occ_l = mc_part_base(bl, i) + (uint64_t)mc_count_in_part(bl, flip, 2 * ((int)(ll & 127) + 1));
-	}
+	*nblk += (kk >> 7) == (ll >> 7) ? 1u : 2u;                         // blocks the reference algorithm touches
+	OccPart bk, bl;
+	mc_load_part(ix, kk >> 7, i, bk);
+	bl = bk;
+	if ((kk >> 7) != (ll >> 7)) mc_load_part(ix, ll >> 7, i, bl);
+	const uint64_t occ_k = mc_part_base(bk, i) + (uint64_t)mc_count_in_part(bk, flip, 2 * ((int)(kk & 127) + 1));
+	const uint64_t occ_l = mc_part_base(bl, i) + (uint64_t)mc_count_in_part(bl, flip, 2 * ((int)(ll & 127) + 1));
 	if (occ_l == occ_k) return false;
 	v.x1 = ix.L2[i] + 1 + occ_k; v.x2 = occ_l - occ_k;
+	return true;
+}
+// the same step on the compact layout, all rows 32-bit
+struct RcInterval32 { uint32_t x1, x2; };
+MC_HD RcInterval32 mc_interval_init32(const DevIndex& ix, int c)
+{
+	RcInterval32 v; v.x1 = (uint32_t)ix.L2[3 - c] + 1u; v.x2 = (uint32_t)(ix.L2[c + 1] - ix.L2[c]);
+	return v;
+}
+MC_HD bool mc_interval_extend(const DevIndex& ix, RcInterval32& v, int c, uint32_t* nblk)
+{
+	const int i = 3 - c;
+	const uint32_t prim = (uint32_t)ix.primary;
+	const uint32_t k = v.x1 - 1u, l = k + v.x2;
+	const uint32_t kk = k - (k >= prim), ll = l - (l >= prim);
+	*nblk += (kk >> 7) == (ll >> 7) ? 1u : 2u;                         // blocks the reference algorithm touches (its layout)
+	CBlock bk, bl;
+	mc_load_cblock(ix, kk >> 6, bk);
+	bl = bk;
+	if ((kk >> 6) != (ll >> 6)) mc_load_cblock(ix, ll >> 6, bl);
+	const uint32_t occ_k = mc_cblock_base(bk, i) + mc_count_in_cblock(bk, i, (int)(kk & 63) + 1);
+	const uint32_t occ_l = mc_cblock_base(bl, i) + mc_count_in_cblock(bl, i, (int)(ll & 63) + 1);
+	if (occ_l == occ_k) return false;
+	v.x1 = (uint32_t)ix.L2[i] + 1u + occ_k; v.x2 = occ_l - occ_k;
 	return true;
 }
 
@@ -205,10 +239,10 @@ MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k)
 	const uint64_t x = k - (k > ix.primary);
 	if (ix.cbwt)
 	{
-		CBlock b; mc_load_cblock(ix, x >> 6, b);
-		const uint32_t wsel = ((x & 63) >> 4) == 0 ? b.w.x : ((x & 63) >> 4) == 1 ? b.w.y : ((x & 63) >> 4) == 2 ? b.w.z : b.w.w;
-		const int c = (int)(wsel >> ((~(uint32_t)x & 15) << 1)) & 3;
-		return ix.L2[c] + (uint64_t)mc_cblock_base(b, c) + (uint64_t)mc_count_in_cblock(b, mc_flip_of(c), 2 * ((int)(x & 63) + 1));
+		const uint32_t x32 = (uint32_t)x;
+		CBlock b; mc_load_cblock(ix, x32 >> 6, b);
+		const int c = mc_cblock_symbol(b, x32 & 63);
+		return (uint64_t)((uint32_t)ix.L2[c] + mc_cblock_base(b, c) + mc_count_in_cblock(b, c, (int)(x32 & 63) + 1));
 	}
 	OccBlock b; mc_load_block(ix, x >> 7, b);
 	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};

@@ -22,6 +22,7 @@ static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t)
 	for (int64_t i = 0; i < n; i++) rcommit_body(i, a);
 }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
+static void launch_prep(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t r = 1; r < n; r += 2) prep_body(r, 0, 1, a); }
 static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin; for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
 static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump; for (int64_t i = 0; i < n; i++) a.st->profile_atomics += profpiece_body(i, 0, 1, a, q); }
@@ -30,6 +31,7 @@ static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* 
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
+static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for (int64_t q = 0; q < n; q++) bwtsearch_body(q, a); }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
 #else
@@ -80,6 +82,17 @@ static void launch_piece(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
 	mc_piece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
+__global__ void __launch_bounds__(MC_BLOCK) mc_prep_kernel(const PipeArgs a, int64_t n_pairs)
+{
+	const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+	if (w < n_pairs) prep_body(2 * w + 1, threadIdx.x & 31, 32, a);
+}
+static void launch_prep(const PipeArgs& a, int64_t n, mc_stream_t s)
+{
+	const int64_t n_pairs = n / 2;
+	if (!a.pr.paired || n_pairs <= 0) return;
+	mc_prep_kernel<<<(unsigned)((n_pairs * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n_pairs); g_launches++;
+}
 // rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent warps (warp w
 // takes windows w, w + n_warps, ...), commit per pair.  A window search is a serial, latency-bound piece of code over small
 // tables (word list, diagonal histogram, filter): they live in shared memory (28 KB per warp, 4 warps per block); a lone
@@ -116,6 +129,10 @@ static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	mc_rescue_kernel<<<148 * 2, MC_RESCUE_WARPS * 32, MC_RESCUE_WARPS * MC_RESCUE_SMEM, s>>>(a); g_launches++;
 	mc_rcommit_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
+__global__ void __launch_bounds__(MC_BLOCK) mc_bwtsearch_kernel(const SearchArgs a, int64_t n)
+{ int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (q < n) bwtsearch_body(q, a); }
+static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_bwtsearch_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_cbwt_build_kernel(int64_t n, const uint32_t* src, uint32_t* dst)
 { int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < n) mc_cbwt_build_body(b, src, dst); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t s)
@@ -130,7 +147,6 @@ static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb,
 { if (b1 > b0) { mc_profpack_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, p, nb, pre, b0, b1, beg, end, out); g_launches++; } }
 #endif
 
-MC_LAUNCH1(prep)
 MC_LAUNCH1(seed)
 MC_LAUNCH1(expand)
 MC_LAUNCH1(cluster)

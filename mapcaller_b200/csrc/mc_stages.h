@@ -103,14 +103,14 @@ MC_HD int pa_chunk_of_read(int64_t r) { return (int)(r / MC_CHUNK_READS); }
 // ------------------------------------------------------------------------------------------------
 // prep: mate 2 is reverse-complemented in place before seeding (reference src/ReadMapping.cpp:451)
 // ------------------------------------------------------------------------------------------------
-MC_HD void prep_body(int64_t r, const PipeArgs& a)
+// one warp per mate 2: lane i swaps (and complements) bytes i and n-1-i, so both accesses of a warp are contiguous
+MC_HD void prep_body(int64_t r, int lane, int nl, const PipeArgs& a)
 {
 	if (!a.pr.paired || !(r & 1)) return;
 	uint8_t* s = a.seq + a.roff[r];
-	int n = (int)(a.roff[r + 1] - a.roff[r]);
-	int i = 0, j = n - 1;
-	for (; i < j; i++, j--) { uint8_t x = mc_complement(s[j]), y = mc_complement(s[i]); s[i] = x; s[j] = y; }
-	if (i == j) s[i] = mc_complement(s[i]);
+	const int n = (int)(a.roff[r + 1] - a.roff[r]);
+	for (int i = lane; i < (n >> 1); i += nl) { const int j = n - 1 - i; const uint8_t x = mc_complement(s[j]), y = mc_complement(s[i]); s[i] = x; s[j] = y; }
+	if ((n & 1) && lane == 0) s[n >> 1] = mc_complement(s[n >> 1]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -127,7 +127,11 @@ MC_HD uint8_t base_at(const uint8_t* s, int p, BaseWindow& bw)
 	return (uint8_t)(bw.cur >> ((q & 3) << 3));
 }
 
-MC_HD void seed_body(int64_t r, const PipeArgs& a)
+template <class Interval> struct SeedOps;
+template <> struct SeedOps<RcInterval> { static MC_HD RcInterval init(const DevIndex& ix, int c) { return mc_interval_init(ix, c); } };
+template <> struct SeedOps<RcInterval32> { static MC_HD RcInterval32 init(const DevIndex& ix, int c) { return mc_interval_init32(ix, c); } };
+
+template <class Interval> MC_HD void seed_walk(int64_t r, const PipeArgs& a)
 {
 	const uint8_t* s = a.seq + a.roff[r];
 	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
@@ -139,7 +143,7 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 	uint32_t lower = 0;
 	bool in_seed = false;
 	uint32_t nblk = 0;
-	RcInterval v; v.x1 = v.x2 = 0;
+	Interval v; v.x1 = v.x2 = 0;
 	// One loop, one extension step per trip: lanes of a warp stay in lock step whatever their seed boundaries are
 	// (the nested search-inside-scan loops of the reference serialise lanes whose seeds end at different offsets).
 	for (;;)
@@ -151,7 +155,7 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 			const int c = mc_nt4(ch);
 			if (c > 3) { pos++; continue; }
 			lower |= ch;
-			v = mc_interval_init(a.ix, c); p = pos + 1; in_seed = true;
+			v = SeedOps<Interval>::init(a.ix, c); p = pos + 1; in_seed = true;
 		}
 		bool end = p >= rlen;
 		if (!end)
@@ -174,6 +178,36 @@ MC_HD void seed_body(int64_t r, const PipeArgs& a)
 	}
 	a.rflag[r] = (uint8_t)((lower >> 5) & 1);
 	if (nblk) mc_stat_add(&a.st->seed_blocks, (uint32_t)(nblk));
+}
+MC_HD void seed_body(int64_t r, const PipeArgs& a)
+{
+	if (a.ix.cbwt) seed_walk<RcInterval32>(r, a); else seed_walk<RcInterval>(r, a);
+}
+
+// BWT_Search as an operator (reference src/bwt_search.cpp:121-164) for independent (codes, start) queries: the search loop of
+// seed_walk without the scan around it, followed by the locate of every hit.  The hits come out in the row order of the
+// reverse-complement interval (mc_fmindex.h), i.e. as a permutation of the reference's LocArr.
+struct SearchArgs { DevIndex ix; const uint8_t* codes; const int64_t* off; const int32_t* start; int32_t* len; int32_t* freq; uint64_t* loc; };
+template <class Interval> MC_HD void search_walk(int64_t q, const SearchArgs& a)
+{
+	const uint8_t* s = a.codes + a.off[q];
+	const int stop = (int)(a.off[q + 1] - a.off[q]), start = a.start[q];
+	a.len[q] = 0; a.freq[q] = 0;
+	if (start < 0 || start >= stop || s[start] > 3) return;
+	uint32_t nblk = 0;
+	Interval v = SeedOps<Interval>::init(a.ix, s[start]);
+	int pos = start + 1;
+	for (; pos < stop; pos++) { if (s[pos] > 3 || !mc_interval_extend(a.ix, v, s[pos], &nblk)) break; }
+	const int len = pos - start;
+	a.len[q] = len;
+	if (len < MC_MIN_SEED || v.x2 > MC_MAX_OCC) return;
+	a.freq[q] = (int32_t)v.x2;
+	for (uint32_t i = 0; i < (uint32_t)v.x2; i++)
+		a.loc[q * MC_MAX_OCC + i] = (uint64_t)a.ix.twoG - mc_locate(a.ix, (uint64_t)v.x1 + i, &nblk) - (uint64_t)len;
+}
+MC_HD void bwtsearch_body(int64_t q, const SearchArgs& a)
+{
+	if (a.ix.cbwt) search_walk<RcInterval32>(q, a); else search_walk<RcInterval>(q, a);
 }
 
 // one thread per slot lays out its locations: read offset, length and - in the place of the genome position - the BWT row

@@ -4,7 +4,9 @@ totals, profile, indel maps, break points and SV site lists.
 Checker used, in order of availability on the box: oracle/_ref (the unmodified reference; only for cases that
 stay clear of its undefined behaviour), the CPU restatement oracle/libmcoracle.so (pinned against the
 reference by tests/test_oracle.py), and the committed golden vectors."""
+import os
 import random
+import tempfile
 
 import numpy as np
 import pytest
@@ -133,6 +135,47 @@ def test_edge_cases(built):
             ctx.map_batch(seq[:off[3]], off[:4])     # odd number of reads in paired mode
     case2 = dict(case, seq=seq, off=off)
     pu.assert_same(pu.cuda_results(case2, ix), pu.oracle_results(case2, ix))
+
+
+@pytest.mark.parametrize("wide", [0, 1])
+def test_bwt_search_operator_matches_oracle(built, wide):
+    """mc_bwt_search_batch (BWT_Search, reference src/bwt_search.cpp:121) on its own: match length, frequency and the set of
+    locations for exact, mutated, repeat and N-interrupted queries, on both device index layouts."""
+    import cpu_oracle
+    from mapcaller_b200 import api, simulate as sim
+    case = pu.make_case(seed=21, n_pairs=10, genome_len=60000, contigs=2, n_dup=12)
+    ix = pu.build_index(case)
+    ref = case["ref"]
+    rnd = np.random.default_rng(5)
+    qs, starts = [], []
+    for i in range(1500):
+        n = int(rnd.integers(17, 120)); p = int(rnd.integers(0, len(ref) - n))
+        q = ref[p:p + n].copy()
+        if i % 3 == 1:
+            q = sim.revcomp(q)
+        if i % 4 == 2:
+            q[int(rnd.integers(0, n))] = ord("ACGT"[int(rnd.integers(0, 4))])
+        if i % 7 == 3:
+            q[int(rnd.integers(1, n))] = ord("N")
+        code = np.array([{65: 0, 67: 1, 71: 2, 84: 3}.get(int(c) & 0xDF, 4) for c in q], dtype=np.uint8)
+        st = int(rnd.integers(0, max(1, n - 16)))
+        if code[st] > 3:
+            st = 0 if code[0] <= 3 else 1
+        qs.append(code); starts.append(st)
+    codes = np.concatenate(qs); off = np.zeros(len(qs) + 1, dtype=np.int64); off[1:] = np.cumsum([len(q) for q in qs])
+    with api.Context(ix, reserved=(0, wide, 0, 0, 0)) as ctx:
+        ln, fr, loc = ctx.bwt_search_batch(codes, off, np.array(starts, dtype=np.int32))
+    with tempfile.TemporaryDirectory() as td:
+        ix.save(os.path.join(td, "idx"))
+        orc = cpu_oracle.Oracle(os.path.join(td, "idx"), **case["params"])
+        n_hits = 0
+        for i, q in enumerate(qs):
+            l, f, lo = orc.bwt_search(q, starts[i], len(q))
+            assert (ln[i], fr[i]) == (l, f), (i, ln[i], fr[i], l, f)
+            assert np.array_equal(loc[i], np.sort(lo)), i
+            n_hits += f
+        orc.close()
+    assert n_hits > 1000
 
 
 def test_gapped_fill_kernel_matches_oracle(built):
