@@ -159,7 +159,8 @@ enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_P
 struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask, rwin; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
-struct Staged { DBuf seq, roff, seed_off, cap, scan; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false; };
+struct Staged { DBuf seq, roff, seed_off, cap, scan; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false;
+	int n_pieces = 0; int64_t piece_end[8]; };   // read ranges [piece_end[p-1], piece_end[p]) whose bases arrive one after the other (events ev_piece[])
 
 struct mc_ctx {
 	mc_params prm;
@@ -173,8 +174,7 @@ struct mc_ctx {
 	DBuf d_bp, d_ind, d_ind_seq, d_pbump;
 	int64_t bp_cap = 0, ind_cap = 0, ind_seq_cap = 0;
 	// batch arenas
-	Staged cur; Staged pipe[2]; Staged slots[4];
-	std::vector<mc_chunk_out> chunks_all;
+	Staged cur; Staged slots[4];
 	DBuf d_slot_freq, d_seeds, d_slot_loc, d_loc_slot, d_pairs, d_npair;
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
@@ -184,7 +184,7 @@ struct mc_ctx {
 	HBuf h_bounce[2];
 	mc_stream_t cstream;
 #ifndef MC_HOSTEMU
-	cudaEvent_t ev_bounce[2], ev_staged[2];
+	cudaEvent_t ev_bounce[2], ev_piece[8];
 #endif
 	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
@@ -226,7 +226,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
 	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
 	for (DBuf* b : bufs) b->release();
-	Staged* st[] = {&c->cur, &c->pipe[0], &c->pipe[1], &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
+	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); }
 	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc, &c->h_disc};
 	for (HBuf* b : hb) b->release();
@@ -237,7 +237,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
 	c->h_bounce[0].release(); c->h_bounce[1].release();
 #ifndef MC_HOSTEMU
-	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]); cudaEventDestroy(c->ev_staged[0]); cudaEventDestroy(c->ev_staged[1]);
+	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]); for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev_piece[i]);
 	if (c->cstream) cudaStreamDestroy(c->cstream);
 	if (c->stream) cudaStreamDestroy(c->stream);
 #endif
@@ -268,7 +268,7 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	for (int i = 0; i < EV_COUNT; i++) ev_create(&c->ev[i]);
 #ifndef MC_HOSTEMU
 	cudaEventCreateWithFlags(&c->ev_bounce[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bounce[1], cudaEventDisableTiming);
-	cudaEventCreateWithFlags(&c->ev_staged[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_staged[1], cudaEventDisableTiming);
+	for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&c->ev_piece[i], cudaEventDisableTiming);
 #endif
 	const int64_t G = v.genome_size; c->G = G;
 	std::vector<int64_t> ends; std::vector<int32_t> ids;
@@ -397,7 +397,9 @@ static void launch_seedcap(const CapArgs& q, int64_t n, mc_stream_t s)
 { if (n > 0) { mc_seedcap_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(q, n); g_launches++; } }
 #endif
 
-static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st, mc_stream_t stream)
+// `pieces` > 1: the bases travel in that many chunk-aligned pieces, each followed by an event, so that the consumer can start
+// on a piece while the rest is still on the wire (the offsets and everything derived from them go first)
+static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st, mc_stream_t stream, int pieces)
 {
 	const int64_t n = in->n_reads;
 	if (n < 0 || (n > 0 && (!in->seq || !in->seq_off))) { mc_set_error("mc_map_batch: bad batch"); return MC_ERR_ARG; }
@@ -406,15 +408,34 @@ static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st, mc_stream_t
 	const int64_t base = n ? in->seq_off[0] : 0, bytes = n ? in->seq_off[n] - base : 0;
 	if (bytes < 0 || bytes > n * (int64_t)MC_MAX_RLEN) { mc_set_error("mc_map_batch: read offsets are not increasing or a read exceeds %d bases", MC_MAX_RLEN); return MC_ERR_ARG; }
 	st.n_reads = n; st.n_bytes = bytes; st.base = base; st.n_slots = bytes / 17 + n;   // upper bound of the seed slots
+	st.n_pieces = 0;
 	st.h_roff.clear();
 	if (c->prm.want_alignments) st.h_roff.assign(in->seq_off, in->seq_off + n + 1);
 	if (n == 0) { st.valid = true; return MC_OK; }
-	// scratch of the staging pass is private to the Staged slot: staging may run on the copy stream while another batch computes
+	// scratch of the staging pass is private to the Staged slot
 	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 2) * 8) || st.cap.reserve(n * 4) || st.scan.reserve(device_scan_scratch_bytes(n))) return MC_ERR_CUDA;
-	if (upload(c, st.seq.p, in->seq + base, bytes, stream) || upload(c, st.roff.p, in->seq_off, (n + 1) * 8, stream)) return MC_ERR_CUDA;
+	if (upload(c, st.roff.p, in->seq_off, (n + 1) * 8, stream)) return MC_ERR_CUDA;
 	CapArgs q; q.roff = st.roff.as<int64_t>(); q.cap = st.cap.as<uint32_t>(); q.st = c->d_stats.as<DevStats>();
 	launch_seedcap(q, n, stream);
 	device_scan_u32(q.cap, st.seed_off.as<int64_t>(), n, st.scan.as<int64_t>(), stream);
+#ifndef MC_HOSTEMU
+	if (pieces > 1)
+	{
+		const int64_t n_chunks = (n + MC_CHUNK_READS - 1) / MC_CHUNK_READS;
+		const int64_t per = ((n_chunks + pieces - 1) / pieces) * MC_CHUNK_READS;
+		for (int p = 0; p < pieces; p++)
+		{
+			const int64_t r0 = std::min(n, (int64_t)p * per), r1 = std::min(n, (int64_t)(p + 1) * per);
+			if (upload(c, st.seq.as<uint8_t>() + (in->seq_off[r0] - base), in->seq + in->seq_off[r0], (size_t)(in->seq_off[r1] - in->seq_off[r0]), stream)) return MC_ERR_CUDA;
+			if (cuda_fail(cudaEventRecord(c->ev_piece[p], stream), "cudaEventRecord")) return MC_ERR_CUDA;
+			st.piece_end[p] = r1;
+		}
+		st.n_pieces = pieces;
+		st.valid = true;
+		return MC_OK;
+	}
+#endif
+	if (upload(c, st.seq.p, in->seq + base, bytes, stream)) return MC_ERR_CUDA;
 	st.valid = true;
 	return MC_OK;
 }
@@ -463,9 +484,24 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	// ---- seeding ----
 	ev_record(&c->ev[EV_H2D], s);
 	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats) - 2 * sizeof(mc_u64), s);   // keeps the staging flags (overflow, odd_merge)
-	if (prep_needed) launch_prep(a, n, s);
 	ev_record(&c->ev[EV_SEED0], s);
-	launch_seed(a, n, s);
+	if (st.n_pieces > 1)
+	{
+#ifndef MC_HOSTEMU
+		for (int p = 0; p < st.n_pieces; p++)
+		{
+			const int64_t r0 = p ? st.piece_end[p - 1] : 0, r1 = st.piece_end[p];
+			if (cuda_fail(cudaStreamWaitEvent(s, c->ev_piece[p], 0), "cudaStreamWaitEvent")) return MC_ERR_CUDA;
+			if (prep_needed) launch_prep(a, r0, r1, s);
+			launch_seed(a, r0, r1, s);
+		}
+#endif
+	}
+	else
+	{
+		if (prep_needed) launch_prep(a, 0, n, s);
+		launch_seed(a, 0, n, s);
+	}
 	ev_record(&c->ev[EV_SEED], s);
 	device_scan_u32(a.slot_freq, c->d_slot_loc.as<int64_t>(), st.n_slots, c->d_scan.as<int64_t>(), s);
 	int64_t* h_small = c->h_small.as<int64_t>();
@@ -745,73 +781,24 @@ int mc_map_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
 #ifndef MC_HOSTEMU
 	cudaSetDevice(c->prm.device);
 #endif
-	const int64_t n = in->n_reads;
-	const int64_t n_chunks = (n + MC_CHUNK_READS - 1) / MC_CHUNK_READS;
-	// Profile-only runs of a large batch are cut into a few chunk-aligned pieces: piece i+1 travels over PCIe on the copy
-	// stream while piece i is being mapped.  The pieces are consecutive in file order, so the sequential state simply carries
-	// over.  (With want_alignments the result arenas of the pieces would have to be stitched; those batches go in one piece.)
-	const int kPieces = 4;
-	if (c->prm.want_alignments || c->prm.reserved[0] || n < 400000 || !in->seq || !in->seq_off)
-	{
-		ev_record(&c->ev[EV_START], c->stream);
-		int rc = stage_reads(c, in, c->cur, c->stream);
-		if (rc) return rc;
-		return run_batch(c, c->cur, out, true);
-	}
-	const int64_t per = ((n_chunks + kPieces - 1) / kPieces) * MC_CHUNK_READS;
-	auto piece_of = [&](int i, mc_batch_in& b) {
-		const int64_t r0 = std::min(n, (int64_t)i * per), r1 = std::min(n, (int64_t)(i + 1) * per);
-		b.n_reads = r1 - r0; b.seq = in->seq; b.seq_off = in->seq_off + r0;
-	};
-	c->chunks_all.clear();
-	int replays = 0;
-	mc_batch_in b;
-	const bool dbg = getenv("MC_DEBUG") != nullptr;
-	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-	const double t0 = now();
-	piece_of(0, b);
-	int rc = stage_reads(c, &b, c->pipe[0], c->cstream);
+	// A large batch travels over PCIe in a few chunk-aligned pieces on the copy stream; the compute stream reverses mate 2 and
+	// seeds piece i while piece i+1 is on the wire.  Everything after seeding sees the whole batch.
+	const int pieces = in->n_reads >= 400000 && !getenv("MC_NO_PIECES") ? 4 : 1;
+	ev_record(&c->ev[EV_START], c->stream);
+	int rc = stage_reads(c, in, c->cur, pieces > 1 ? c->cstream : c->stream, pieces);
 	if (rc) return rc;
-#ifndef MC_HOSTEMU
-	cudaEventRecord(c->ev_staged[0], c->cstream);
-#endif
-	for (int i = 0; i < kPieces; i++)
-	{
-		if (i + 1 < kPieces)
-		{
-			piece_of(i + 1, b);
-			rc = stage_reads(c, &b, c->pipe[(i + 1) & 1], c->cstream);   // the slot's previous user (piece i-1) has completed: run_batch is synchronous
-			if (rc) return rc;
-#ifndef MC_HOSTEMU
-			cudaEventRecord(c->ev_staged[(i + 1) & 1], c->cstream);
-#endif
-		}
-#ifndef MC_HOSTEMU
-		cudaStreamWaitEvent(c->stream, c->ev_staged[i & 1], 0);
-#endif
-		ev_record(&c->ev[EV_START], c->stream);
-		mc_batch_out o;
-		const double t1 = now();
-		rc = run_batch(c, c->pipe[i & 1], &o, true);
-		if (rc) return rc;
-		if (dbg) fprintf(stderr, "[mc] piece %d: issued at %.3f ms, run_batch %.3f ms\n", i, t1 - t0, now() - t1);
-		c->chunks_all.insert(c->chunks_all.end(), o.chunks, o.chunks + o.n_chunks);
-		replays += o.replays;
-	}
-	memset(out, 0, sizeof(*out));
-	out->n_reads = n; out->n_chunks = (int64_t)c->chunks_all.size(); out->chunks = c->chunks_all.data(); out->replays = replays;
-	return MC_OK;
+	return run_batch(c, c->cur, out, true);
 }
 
 int mc_stage_batch(mc_ctx* c, const mc_batch_in* in, int32_t slot)
 {
 	if (!c || !in || slot < 0 || slot >= 4) { mc_set_error("mc_stage_batch: bad argument"); return MC_ERR_ARG; }
-	int rc = stage_reads(c, in, c->slots[slot], c->stream);
+	int rc = stage_reads(c, in, c->slots[slot], c->stream, 1);
 	if (rc) return rc;
 	// reverse-complement mate 2 once; the staged copy is then immutable
 	PipeArgs a; memset(&a, 0, sizeof(a));
 	a.pr.paired = c->prm.paired; a.seq = c->slots[slot].seq.as<uint8_t>() - c->slots[slot].base; a.roff = c->slots[slot].roff.as<int64_t>(); a.n_reads = in->n_reads;
-	launch_prep(a, in->n_reads, c->stream);
+	launch_prep(a, 0, in->n_reads, c->stream);
 	return dev_sync(c->stream) ? MC_ERR_CUDA : MC_OK;
 }
 

@@ -22,7 +22,8 @@ static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t)
 	for (int64_t i = 0; i < n; i++) rcommit_body(i, a);
 }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
-static void launch_prep(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t r = 1; r < n; r += 2) prep_body(r, 0, 1, a); }
+static void launch_prep(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { for (int64_t r = first | 1; r < n; r += 2) prep_body(r, 0, 1, a); }
+static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { for (int64_t r = first; r < n; r++) seed_body(r, a); }
 static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin; for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
 static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump; for (int64_t i = 0; i < n; i++) a.st->profile_atomics += profpiece_body(i, 0, 1, a, q); }
@@ -82,17 +83,23 @@ static void launch_piece(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
 	mc_piece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
-__global__ void __launch_bounds__(MC_BLOCK) mc_prep_kernel(const PipeArgs a, int64_t n_pairs)
+// mate reversal and seeding take a read range [first, n): a batch that arrives from the host in pieces is seeded piece by
+// piece while the next piece is still on the wire (mc_map_batch)
+__global__ void __launch_bounds__(MC_BLOCK) mc_prep_kernel(const PipeArgs a, int64_t first_pair, int64_t n_pairs)
 {
-	const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+	const int64_t w = first_pair + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
 	if (w < n_pairs) prep_body(2 * w + 1, threadIdx.x & 31, 32, a);
 }
-static void launch_prep(const PipeArgs& a, int64_t n, mc_stream_t s)
+static void launch_prep(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t s)
 {
-	const int64_t n_pairs = n / 2;
-	if (!a.pr.paired || n_pairs <= 0) return;
-	mc_prep_kernel<<<(unsigned)((n_pairs * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n_pairs); g_launches++;
+	const int64_t p0 = first / 2, p1 = n / 2;
+	if (!a.pr.paired || p1 <= p0) return;
+	mc_prep_kernel<<<(unsigned)(((p1 - p0) * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, p0, p1); g_launches++;
 }
+__global__ void __launch_bounds__(MC_BLOCK) mc_seed_kernel(const PipeArgs a, int64_t first, int64_t n)
+{ const int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) seed_body(i, a); }
+static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t s)
+{ if (n > first) { mc_seed_kernel<<<(unsigned)((n - first + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, first, n); g_launches++; } }
 // rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent warps (warp w
 // takes windows w, w + n_warps, ...), commit per pair.  A window search is a serial, latency-bound piece of code over small
 // tables (word list, diagonal histogram, filter): they live in shared memory (28 KB per warp, 4 warps per block); a lone
@@ -147,7 +154,6 @@ static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb,
 { if (b1 > b0) { mc_profpack_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, p, nb, pre, b0, b1, beg, end, out); g_launches++; } }
 #endif
 
-MC_LAUNCH1(seed)
 MC_LAUNCH1(expand)
 MC_LAUNCH1(cluster)
 MC_LAUNCH1(single)
