@@ -170,7 +170,7 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "configs[1]: E. coli-sized 4.6 Mbp synthetic reference, 2x100 bp simulated PE reads at 50x (%d pairs per GPU), -alg nw, VCF profile on" % args.pairs,
-              "genome_bp": GENOME_LEN, "read_len": READ_LEN, "pairs_per_gpu": args.pairs, "alg": "nw", "parallelism": "reads sharded over %d GPU(s), full index replica per GPU" % world,
+              "genome_bp": GENOME_LEN, "read_len": READ_LEN, "pairs_per_gpu": args.pairs, "alg": "nw", "parallelism": "reads sharded over %d GPU(s) in file order (one library: avgDist / dedup gate / discordant-pair state exchanged over NCCL), full index replica per GPU" % world,
               "l2_policy": "inputs larger than L2: 2x%d MB of reads per step stream through; the 6.9 MB index stays L2-resident" % (args.pairs * READ_LEN // 1_000_000)}
 
     if args.impl == "reference":

@@ -202,7 +202,7 @@ struct mc_ctx {
 	mc_event_t ev[EV_COUNT];
 #ifndef MC_HOSTEMU
 	ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;
-	DBuf d_comm_small, d_comm_buf; HBuf h_comm_buf;
+	DBuf d_comm_small, d_comm_buf, d_glist, d_glist_all; HBuf h_comm_buf;
 #endif
 };
 
@@ -232,7 +232,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	for (HBuf* b : hb) b->release();
 #ifndef MC_HOSTEMU
 	if (c->comm && nccl_api_loaded()) nccl_destroy(c->comm);
-	c->d_comm_small.release(); c->d_comm_buf.release(); c->h_comm_buf.release();
+	c->d_comm_small.release(); c->d_comm_buf.release(); c->d_glist.release(); c->d_glist_all.release(); c->h_comm_buf.release();
 #endif
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
 	c->h_bounce[0].release(); c->h_bounce[1].release();
@@ -440,6 +440,88 @@ static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st, mc_stream_t
 	return MC_OK;
 }
 
+// ---- ordered exchange between the GPUs of one library ------------------------------------------------------
+// After mc_comm_init() the ranks map consecutive shards of ONE library: per mc_map_batch call (a collective), rank r's reads
+// follow those of rank r-1 in file order, and the next call continues after the last rank.  What the reference does
+// sequentially in file order is exchanged so that the result equals one reference thread over the whole library
+// (SURVEY.md section 8e):
+//   * avgDist feedback: the per-chunk sums and validity intervals of every rank are all-gathered after each attempt and
+//     every rank walks the global chunk sequence (same decisions everywhere, each rank re-runs its own chunks);
+//   * dedup gate: per-start candidate counts of the ranks before / after this one are added to readCount around the gate;
+//   * discordant pairs: the few records are gathered and replayed in global order, every rank keeps its own sites.
+// mc_params.reserved[2] = 1 turns the exchange off (independent shards, results summed by mc_profile_allreduce).
+struct Ordered { bool on = false; int n = 1, me = 0; std::vector<int64_t> nch, goff; int64_t NG = 0, mxc = 0; };
+#ifndef MC_HOSTEMU
+static bool ordered_mode(const mc_ctx* c) { return c->comm && c->comm_size > 1 && !c->prm.reserved[2]; }
+static int ordered_layout(mc_ctx* c, int64_t n_chunks, Ordered& o)
+{
+	o.on = true; o.n = c->comm_size; o.me = c->comm_rank;
+	cudaStream_t s = c->stream;
+	if (c->d_comm_small.reserve(8 * (o.n + 8))) return -1;
+	long long* d_sz = c->d_comm_small.as<long long>();
+	long long my = (long long)n_chunks; std::vector<long long> sz(o.n);
+	if (dev_h2d(d_sz + o.n, &my, 8, s)) return -1;
+	if (nccl_fail(ncclAllGather(d_sz + o.n, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(chunk counts)")) return -1;
+	if (dev_d2h(sz.data(), d_sz, 8 * o.n, s) || dev_sync(s)) return -1;
+	o.nch.assign(o.n, 0); o.goff.assign(o.n + 1, 0); o.mxc = 1;
+	for (int r = 0; r < o.n; r++) { o.nch[r] = sz[r]; o.goff[r + 1] = o.goff[r] + sz[r]; o.mxc = std::max(o.mxc, (int64_t)sz[r]); }
+	o.NG = o.goff[o.n];
+	return 0;
+}
+// all ranks' chunk sums, validity intervals and overflow flags after an attempt
+static int ordered_chunks(mc_ctx* c, const Ordered& o, std::vector<mc_chunk_out>& hc, std::vector<int32_t>& lo, std::vector<int32_t>& hi, mc_u64* any_overflow)
+{
+	cudaStream_t s = c->stream;
+	const size_t cb = (size_t)o.mxc * sizeof(mc_chunk_out), ib = (size_t)o.mxc * 4, per = cb + 2 * ib + 8;
+	if (c->d_comm_buf.reserve(per * o.n + 64) || c->h_comm_buf.reserve(per * o.n + 64)) return -1;
+	uint8_t* d = c->d_comm_buf.as<uint8_t>();
+	int bad = 0;
+	nccl_api()->GroupStart();
+	bad |= nccl_fail(ncclAllGather(c->d_chunk_out.p, d, cb, ncclUint8, c->comm, s), "ncclAllGather(chunk sums)");
+	bad |= nccl_fail(ncclAllGather(c->d_chunk_lo.p, d + cb * o.n, ib, ncclUint8, c->comm, s), "ncclAllGather(chunk lo)");
+	bad |= nccl_fail(ncclAllGather(c->d_chunk_hi.p, d + (cb + ib) * o.n, ib, ncclUint8, c->comm, s), "ncclAllGather(chunk hi)");
+	bad |= nccl_fail(ncclAllGather(&c->d_stats.as<DevStats>()->overflow, d + (cb + 2 * ib) * o.n, 8, ncclUint8, c->comm, s), "ncclAllGather(overflow)");
+	bad |= nccl_fail(nccl_api()->GroupEnd(), "ncclGroupEnd");
+	if (bad) return -1;
+	if (dev_d2h(c->h_comm_buf.p, d, per * o.n, s) || dev_sync(s)) return -1;
+	const uint8_t* h = c->h_comm_buf.as<uint8_t>();
+	*any_overflow = 0;
+	for (int r = 0; r < o.n; r++)
+	{
+		memcpy(hc.data() + o.goff[r], h + cb * r, (size_t)o.nch[r] * sizeof(mc_chunk_out));
+		memcpy(lo.data() + o.goff[r], h + cb * o.n + ib * r, (size_t)o.nch[r] * 4);
+		memcpy(hi.data() + o.goff[r], h + (cb + ib) * o.n + ib * r, (size_t)o.nch[r] * 4);
+		mc_u64 f; memcpy(&f, h + (cb + 2 * ib) * o.n + 8 * r, 8); *any_overflow |= f;
+	}
+	return 0;
+}
+// gathers variable-length byte records of every rank into every rank: sizes first, then ONE padded all-gather
+static int allgather_bytes(mc_ctx* c, ncclComm_t comm, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t> >& all)
+{
+	const int n = c->comm_size; cudaStream_t s = c->stream;
+	if (c->d_comm_small.reserve(8 * (n + 8))) return -1;
+	long long* d_sz = c->d_comm_small.as<long long>();
+	long long my = (long long)mine.size();
+	std::vector<long long> sz(n);
+	if (dev_h2d(d_sz + n, &my, 8, s)) return -1;
+	if (nccl_fail(ncclAllGather(d_sz + n, d_sz, 1, ncclInt64, comm, s), "ncclAllGather(sizes)")) return -1;
+	if (dev_d2h(sz.data(), d_sz, 8 * n, s) || dev_sync(s)) return -1;
+	long long mx = 16; for (int r = 0; r < n; r++) mx = std::max(mx, sz[r]);
+	mx = (mx + 15) & ~15ll;
+	if (c->d_comm_buf.reserve((size_t)mx * (n + 1)) || c->h_comm_buf.reserve((size_t)mx * n)) return -1;
+	uint8_t* d_all = c->d_comm_buf.as<uint8_t>(); uint8_t* d_mine = d_all + (size_t)mx * n;
+	if (dev_h2d(d_mine, mine.data(), mine.size(), s)) return -1;
+	if (nccl_fail(ncclAllGather(d_mine, d_all, (size_t)mx, ncclUint8, comm, s), "ncclAllGather(records)")) return -1;
+	if (dev_d2h(c->h_comm_buf.p, d_all, (size_t)mx * n, s) || dev_sync(s)) return -1;
+	all.assign(n, std::vector<uint8_t>());
+	for (int r = 0; r < n; r++) all[r].assign(c->h_comm_buf.as<uint8_t>() + (size_t)mx * r, c->h_comm_buf.as<uint8_t>() + (size_t)mx * r + sz[r]);
+	return 0;
+}
+
+#else
+static bool ordered_mode(const mc_ctx*) { return false; }
+#endif
+
 // ---- the batch controller -----------------------------------------------------------------------------
 static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 {
@@ -463,8 +545,14 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	bad |= c->d_slot_freq.reserve(st.n_slots * 4) || c->d_seeds.reserve(st.n_slots * sizeof(Seed)) || c->d_slot_loc.reserve((st.n_slots + 1) * 8);
 	bad |= c->d_scan.reserve(device_scan_scratch_bytes(st.n_slots));
 	bad |= c->d_cand_off.reserve((n + 1) * 4) || c->d_rflag.reserve(n + 1) || c->d_npair.reserve(n * 4) || c->d_ncand0.reserve(n * 4) || c->d_ncand.reserve(n * 4) || c->d_rsum.reserve(n * sizeof(ReadSum));
-	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(n_chunks * sizeof(mc_chunk_out));
-	bad |= c->d_chunk_lo.reserve(n_chunks * 4) || c->d_chunk_hi.reserve(n_chunks * 4);
+	// several GPUs on one library: the chunk grid of the controller below is the global one, this rank owns [g0, g0 + n_chunks)
+	Ordered od;
+#ifndef MC_HOSTEMU
+	if (ordered_mode(c) && ordered_layout(c, n_chunks, od)) return MC_ERR_NCCL;
+#endif
+	const int64_t NG = od.on ? od.NG : n_chunks, g0 = od.on ? od.goff[od.me] : 0, mxc = od.on ? od.mxc : n_chunks;
+	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(mxc * sizeof(mc_chunk_out));
+	bad |= c->d_chunk_lo.reserve(mxc * 4) || c->d_chunk_hi.reserve(mxc * 4);
 	bad |= c->d_pair_flag.reserve((n_pairs + 1) * 4) || c->d_est_lo.reserve((n_pairs + 1) * 4) || c->d_est_hi.reserve((n_pairs + 1) * 4);
 	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4 * 4) || c->d_rw_beg.reserve((n_pairs + 1) * 4) || c->d_accept.reserve(n + 1) || c->d_read_redo.reserve(n + 1);
 	bad |= c->h_chunk.reserve(n_chunks * sizeof(mc_chunk_out)) || c->h_chunk_lo.reserve(n_chunks * 4) || c->h_chunk_hi.reserve(n_chunks * 4);
@@ -540,27 +628,29 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		ev_record(&c->ev[EV_CLUSTER], s);
 
 		// ---- speculative pairing / alignment with avgDist verification ----
-		std::vector<int32_t> est(n_chunks, (int32_t)(c->tot.avg_dist * 1.5));
-		std::vector<uint8_t> active(n_chunks, 1), computed(n_chunks, 0);
+		std::vector<int32_t> est(NG, (int32_t)(c->tot.avg_dist * 1.5));
+		std::vector<uint8_t> active(NG, 1), computed(NG, 0);
+		std::vector<mc_chunk_out> g_hc; std::vector<int32_t> g_lo, g_hi;
+		if (od.on) { g_hc.resize(NG); g_lo.resize(NG); g_hi.resize(NG); }
 		// avgDist stays at its initial value until more than 1000 pairs have been seen (src/ReadMapping.cpp:539) and then
 		// jumps: while warming up only the chunks that can still use the initial value are speculated on
 		if (paired && c->tot.total_paired <= 1000)
-			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2; k < n_chunks; k++) active[k] = 0;
+			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2; k < NG; k++) active[k] = 0;
 		Bumps hb; memset(&hb, 0, sizeof(hb)); hb.pair = (mc_u64)n_locs;
 		bad |= dev_h2d(db, &hb, sizeof(hb), s) || dev_zero(c->d_pair_flag.p, (n_pairs + 1) * 4, s);
 		mc_totals run = c->tot;
-		c->chunks_final.assign(n_chunks, mc_chunk_out());
+		c->chunks_final.assign(NG, mc_chunk_out());
 		int64_t first_open = 0;
 		int replays = 0; bool overflow = false, first_attempt = true;
 		Bumps* hbp = (Bumps*)(h_small + 64);   // pinned copy of the arena cursors, refreshed at the end of every attempt
 		memset(hbp, 0, sizeof(Bumps));
 		ev_record(&c->ev[EV_PAIR0], s);
-		while (first_open < n_chunks)
+		while (first_open < NG)
 		{
 			// one attempt: no host round trip inside it, the task lists are consumed from their device-side cursors
 			a.rtask_begin = (int64_t)hbp->rtask; a.task_begin = (int64_t)hbp->task; a.ptask_begin = (int64_t)hbp->ptask;
 			if (a.rtask_begin + n_pairs > rtask_cap) { mc_set_error("mc_map_batch: too many speculation replays in one batch"); return MC_ERR_OVERFLOW; }
-			bad |= dev_h2d(c->d_est.p, est.data(), n_chunks * 4, s) || dev_h2d(c->d_active.p, active.data(), n_chunks, s);
+			bad |= dev_h2d(c->d_est.p, est.data() + g0, n_chunks * 4, s) || dev_h2d(c->d_active.p, active.data() + g0, n_chunks, s);
 			if (paired) { bad |= dev_zero(&db->rwin, 8, s); launch_pair(a, n_pairs, s); launch_rescue(a, n_pairs, s); } else launch_single(a, n, s);
 			if (first_attempt) ev_record(&c->ev[EV_PAIR1], s);
 			first_attempt = false;
@@ -575,12 +665,21 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			bad |= dev_d2h(c->h_chunk.p, c->d_chunk_out.p, n_chunks * sizeof(mc_chunk_out), s) || dev_d2h(c->h_chunk_lo.p, c->d_chunk_lo.p, n_chunks * 4, s);
 			bad |= dev_d2h(c->h_chunk_hi.p, c->d_chunk_hi.p, n_chunks * 4, s) || dev_d2h(hst, c->d_stats.p, sizeof(DevStats), s) || dev_sync(s);
 			if (bad) return MC_ERR_CUDA;
-			if (hst->overflow) { overflow = true; break; }
-			for (int64_t k = 0; k < n_chunks; k++) if (active[k]) computed[k] = 1;
-			// walk the chunks in file order (reference src/ReadMapping.cpp:537-539)
 			const mc_chunk_out* hc = c->h_chunk.as<mc_chunk_out>(); const int32_t* lo = c->h_chunk_lo.as<int32_t>(); const int32_t* hi = c->h_chunk_hi.as<int32_t>();
+#ifndef MC_HOSTEMU
+			if (od.on)
+			{
+				mc_u64 any = 0;
+				if (ordered_chunks(c, od, g_hc, g_lo, g_hi, &any)) return MC_ERR_NCCL;
+				hc = g_hc.data(); lo = g_lo.data(); hi = g_hi.data();
+				if (any) { overflow = true; break; }      // every rank repeats the batch (each grows only what it ran out of)
+			}
+#endif
+			if (hst->overflow) { overflow = true; break; }
+			for (int64_t k = 0; k < NG; k++) if (active[k]) computed[k] = 1;
+			// walk the chunks in file order (reference src/ReadMapping.cpp:537-539)
 			std::fill(active.begin(), active.end(), 0);
-			while (first_open < n_chunks)
+			while (first_open < NG)
 			{
 				const int64_t k = first_open;
 				const int32_t true_est = (int32_t)(run.avg_dist * 1.5);
@@ -588,7 +687,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 				{
 					// (re)run everything from here on with the value this chunk really sees
 					if (computed[k]) replays++;
-					for (int64_t j = k; j < n_chunks; j++) { est[j] = true_est; active[j] = 1; computed[j] = 0; }
+					for (int64_t j = k; j < NG; j++) { est[j] = true_est; active[j] = 1; computed[j] = 0; }
 					break;
 				}
 				mc_chunk_out ck = hc[k]; ck.est_distance = paired ? true_est : 0;
@@ -643,8 +742,33 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			if (bad) return MC_ERR_CUDA;
 			q.n_keys = h_small[0];
 			device_sort_u64(q.keys, c->d_keys_tmp.as<uint64_t>(), q.n_keys, c->d_sort.p, c->d_sort.cap, s);
+#ifndef MC_HOSTEMU
+			std::vector<long long> gl_n; long long gl_mx = 0; const uint64_t* gl_all = nullptr;
+			if (od.on)
+			{
+				// per-start candidate counts of every rank: the lists (heads of the sorted key runs) are all-gathered
+				if (c->d_glist.reserve((size_t)(q.n_keys + 2) * 8) || dev_zero(&db->rwin, 8, s)) return MC_ERR_CUDA;   // the window cursor is free: reuse it
+				launch_gatecnt(a, q, q.n_keys, c->d_glist.as<uint64_t>(), &db->rwin, s);
+				long long* d_sz = c->d_comm_small.as<long long>();
+				if (nccl_fail(ncclAllGather(&db->rwin, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(gate list sizes)")) return MC_ERR_NCCL;
+				gl_n.resize(od.n);
+				if (dev_d2h(gl_n.data(), d_sz, 8 * od.n, s) || dev_sync(s)) return MC_ERR_CUDA;
+				for (int r = 0; r < od.n; r++) gl_mx = std::max(gl_mx, gl_n[r]);
+				gl_mx = (gl_mx + 1) & ~1ll;
+				if (gl_mx)
+				{
+					if (c->d_glist.grow_keep((size_t)gl_mx * 8, (size_t)gl_n[od.me] * 8, s) || c->d_glist_all.reserve((size_t)gl_mx * 8 * od.n)) return MC_ERR_CUDA;
+					if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, (size_t)gl_mx * 8, ncclUint8, c->comm, s), "ncclAllGather(gate lists)")) return MC_ERR_NCCL;
+					gl_all = c->d_glist_all.as<uint64_t>();
+					for (int r = 0; r < od.me; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
+				}
+			}
+#endif
 			launch_gate(a, q, q.n_keys, s);
 			launch_gateupd(a, q, q.n_keys, s);
+#ifndef MC_HOSTEMU
+			if (od.on && gl_all) for (int r = od.me + 1; r < od.n; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
+#endif
 			bad |= dev_zero(&db->ptask, 8, s);            // the piece list of the alignment stage is free again: reuse it
 			launch_scatter(a, q, n, s);
 			launch_profpiece(a, q, frag_cap, s);
@@ -703,27 +827,40 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			DiscRec* d = c->h_disc.as<DiscRec>(); const int64_t nd = h_small[33];
 			std::sort(d, d + nd, [](const DiscRec& x, const DiscRec& y) { return x.pair < y.pair; });
 			const int64_t G = c->G, twoG = 2 * c->G;
-			for (int64_t k = 0; k < nd; k++)
+			// `keep` = the records are this rank's own: their sites are stored; other ranks' records only move the state along
+			auto replay = [&](const DiscRec* d, int64_t nd, bool keep) {
+				for (int64_t k = 0; k < nd; k++)
+				{
+					const mc_pair_out& q = d[k].v;
+					if (q.gPos1 < G && q.gPos2 >= G)
+					{
+						c->discord_dist = llabs(twoG - q.gPos1 - q.gPos2);
+						if (c->discord_dist > 1000 && c->discord_dist < 10000000) { c->discord_gpos = q.gPos1; if (keep) c->inv_sites.push_back({c->discord_gpos, c->discord_dist}); }
+					}
+					else if (q.gPos1 >= G && q.gPos2 < G)
+					{
+						c->discord_dist = llabs(twoG - q.gPos1 - q.gPos2);
+						if (c->discord_dist > 1000 && c->discord_dist < 10000000) c->discord_gpos = q.gPos2;
+						if (keep) c->inv_sites.push_back({c->discord_gpos, c->discord_dist}); // the reference pushes unconditionally here (:502)
+					}
+					else if (q.dist > 1000)
+					{
+						c->discord_dist = q.dist;
+						if (q.gPos1 < G && q.gPos2 < G) { if (keep) { c->tnl_sites.push_back({q.gPos1, q.dist}); c->tnl_sites.push_back({q.gPos2, q.dist}); } c->discord_gpos = q.gPos2; }
+						else if (q.gPos1 >= G && q.gPos2 >= G) { if (keep) { c->tnl_sites.push_back({twoG - q.gPos1, q.dist}); c->tnl_sites.push_back({twoG - q.gPos2, q.dist}); } c->discord_gpos = twoG - q.gPos2; }
+					}
+				}
+			};
+#ifndef MC_HOSTEMU
+			if (od.on)
 			{
-				const mc_pair_out& q = d[k].v;
-				if (q.gPos1 < G && q.gPos2 >= G)
-				{
-					c->discord_dist = llabs(twoG - q.gPos1 - q.gPos2);
-					if (c->discord_dist > 1000 && c->discord_dist < 10000000) { c->discord_gpos = q.gPos1; c->inv_sites.push_back({c->discord_gpos, c->discord_dist}); }
-				}
-				else if (q.gPos1 >= G && q.gPos2 < G)
-				{
-					c->discord_dist = llabs(twoG - q.gPos1 - q.gPos2);
-					if (c->discord_dist > 1000 && c->discord_dist < 10000000) c->discord_gpos = q.gPos2;
-					c->inv_sites.push_back({c->discord_gpos, c->discord_dist}); // the reference pushes unconditionally here (:502)
-				}
-				else if (q.dist > 1000)
-				{
-					c->discord_dist = q.dist;
-					if (q.gPos1 < G && q.gPos2 < G) { c->tnl_sites.push_back({q.gPos1, q.dist}); c->tnl_sites.push_back({q.gPos2, q.dist}); c->discord_gpos = q.gPos2; }
-					else if (q.gPos1 >= G && q.gPos2 >= G) { c->tnl_sites.push_back({twoG - q.gPos1, q.dist}); c->tnl_sites.push_back({twoG - q.gPos2, q.dist}); c->discord_gpos = twoG - q.gPos2; }
-				}
+				std::vector<uint8_t> mine((const uint8_t*)d, (const uint8_t*)(d + nd)); std::vector<std::vector<uint8_t> > all;
+				if (allgather_bytes(c, c->comm, mine, all)) return MC_ERR_NCCL;
+				for (int r = 0; r < od.n; r++) replay((const DiscRec*)all[r].data(), (int64_t)(all[r].size() / sizeof(DiscRec)), r == od.me);
 			}
+			else
+#endif
+				replay(d, nd, true);
 		}
 
 		c->tot = run;
@@ -743,7 +880,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 
 		out->n_reads = n; out->n_pairs = n_pairs; out->n_chunks = n_chunks;
 		out->pairs = want_pairs ? c->h_pairs.as<mc_pair_out>() : nullptr; if (!want_pairs) out->n_pairs = 0;
-		out->chunks = c->chunks_final.data();
+		out->chunks = c->chunks_final.data() + g0;
 		if (c->prm.want_alignments)
 		{
 			// rebuild the per-read candidate table from the device's structure-of-arrays
@@ -913,29 +1050,8 @@ int mc_comm_init(mc_ctx* c, const uint8_t* id_bytes, int32_t rank, int32_t n_ran
 	return MC_OK;
 }
 
-// gathers variable-length byte records of every rank into every rank: sizes first, then ONE padded all-gather
-static int allgather_bytes(mc_ctx* c, ncclComm_t comm, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t> >& all)
-{
-	const int n = c->comm_size; cudaStream_t s = c->stream;
-	if (c->d_comm_small.reserve(8 * (n + 8))) return -1;
-	long long* d_sz = c->d_comm_small.as<long long>();
-	long long my = (long long)mine.size();
-	std::vector<long long> sz(n);
-	if (dev_h2d(d_sz + n, &my, 8, s)) return -1;
-	if (nccl_fail(ncclAllGather(d_sz + n, d_sz, 1, ncclInt64, comm, s), "ncclAllGather(sizes)")) return -1;
-	if (dev_d2h(sz.data(), d_sz, 8 * n, s) || dev_sync(s)) return -1;
-	long long mx = 16; for (int r = 0; r < n; r++) mx = std::max(mx, sz[r]);
-	mx = (mx + 15) & ~15ll;
-	if (c->d_comm_buf.reserve((size_t)mx * (n + 1)) || c->h_comm_buf.reserve((size_t)mx * n)) return -1;
-	uint8_t* d_all = c->d_comm_buf.as<uint8_t>(); uint8_t* d_mine = d_all + (size_t)mx * n;
-	if (dev_h2d(d_mine, mine.data(), mine.size(), s)) return -1;
-	if (nccl_fail(ncclAllGather(d_mine, d_all, (size_t)mx, ncclUint8, comm, s), "ncclAllGather(records)")) return -1;
-	if (dev_d2h(c->h_comm_buf.p, d_all, (size_t)mx * n, s) || dev_sync(s)) return -1;
-	all.assign(n, std::vector<uint8_t>());
-	for (int r = 0; r < n; r++) all[r].assign(c->h_comm_buf.as<uint8_t>() + (size_t)mx * r, c->h_comm_buf.as<uint8_t>() + (size_t)mx * r + sz[r]);
-	return 0;
-}
-
+__global__ void mc_seqoff_kernel(mc_indel_rec* r, int64_t n, int32_t add)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) r[i].seq_off += add; }
 __global__ void mc_clamp_u8_kernel(uint8_t* p, int64_t n, int hi)
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n && p[i] > hi) p[i] = (uint8_t)hi; }
 
@@ -956,8 +1072,8 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	const bool dbg = getenv("MC_DEBUG") != nullptr;
 	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t_begin = now();
-	if (c->d_comm_small.reserve(8 * (c->comm_size + 8))) return MC_ERR_CUDA;
-	long long* d_tot = c->d_comm_small.as<long long>() + c->comm_size + 1;
+	if (c->d_comm_small.reserve(8 * (7 * c->comm_size + 32))) return MC_ERR_CUDA;
+	long long* d_tot = c->d_comm_small.as<long long>() + 6 * c->comm_size + 8;
 	long long t[5] = {c->tot.total_reads, c->tot.total_mapped, c->tot.total_paired, c->tot.total_distance, c->tot.read_length_sum};
 	if (dev_h2d(d_tot, t, sizeof(t), s)) return MC_ERR_CUDA;
 	nccl_api()->GroupStart();
@@ -966,52 +1082,85 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	bad |= nccl_fail(ncclAllReduce(c->d_sdiff.p, c->d_sdiff.p, (G + 1) * 4, ncclInt32, ncclSum, comm, s), "ncclAllReduce(sdiff)");
 	bad |= nccl_fail(ncclAllReduce(c->d_cdiff.p, c->d_cdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(cdiff)");
 	bad |= nccl_fail(ncclAllReduce(c->d_mdiff.p, c->d_mdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(mdiff)");
-	bad |= nccl_fail(ncclAllReduce(c->d_rcount.p, c->d_rcount.p, G, ncclUint8, ncclSum, comm, s), "ncclAllReduce(rcount)");
-	bad |= nccl_fail(ncclAllReduce(d_tot, d_tot, 5, ncclInt64, ncclSum, comm, s), "ncclAllReduce(totals)");
+	const bool independent = !ordered_mode(c) || comm != c->comm;   // with the ordered exchange readCount and the totals already are the library's
+	if (independent)
+	{
+		bad |= nccl_fail(ncclAllReduce(c->d_rcount.p, c->d_rcount.p, G, ncclUint8, ncclSum, comm, s), "ncclAllReduce(rcount)");
+		bad |= nccl_fail(ncclAllReduce(d_tot, d_tot, 5, ncclInt64, ncclSum, comm, s), "ncclAllReduce(totals)");
+	}
 	bad |= nccl_fail(nccl_api()->GroupEnd(), "ncclGroupEnd");
 	if (bad) return MC_ERR_NCCL;
-	mc_clamp_u8_kernel<<<(unsigned)((G + 255) / 256), 256, 0, s>>>(c->d_rcount.as<uint8_t>(), (int64_t)G, c->prm.max_dup);
+	if (independent) mc_clamp_u8_kernel<<<(unsigned)((G + 255) / 256), 256, 0, s>>>(c->d_rcount.as<uint8_t>(), (int64_t)G, c->prm.max_dup);
 	if (dev_d2h(t, d_tot, sizeof(t), s)) return MC_ERR_CUDA;   // completes with the next synchronize (record exchange below)
-	PersistBumps pb;
-	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s)) return MC_ERR_CUDA;
+	// variable-length records (break points, indels with their sequences, SV sites): every rank ends up with the records of
+	// all ranks in rank (= file) order.  The payload goes device to device; only the counts pass through the host.
+	const int n = c->comm_size;
+	long long* d_cnt = c->d_comm_small.as<long long>();                 // [n][4] persistent cursors, then [n][2] site counts, then mine
+	long long my_sites[2] = {(long long)c->inv_sites.size(), (long long)c->tnl_sites.size()};
+	if (c->d_comm_small.cap < (size_t)8 * (6 * n + 16)) { mc_set_error("mc_profile_allreduce: internal error (scratch)"); return MC_ERR_CUDA; }
+	if (dev_h2d(d_cnt + 6 * n, my_sites, 16, s)) return MC_ERR_CUDA;
+	nccl_api()->GroupStart();
+	bad |= nccl_fail(ncclAllGather(c->d_pbump.p, d_cnt, 4, ncclInt64, comm, s), "ncclAllGather(record counts)");
+	bad |= nccl_fail(ncclAllGather(d_cnt + 6 * n, d_cnt + 4 * n, 2, ncclInt64, comm, s), "ncclAllGather(site counts)");
+	bad |= nccl_fail(nccl_api()->GroupEnd(), "ncclGroupEnd");
+	if (bad) return MC_ERR_NCCL;
+	std::vector<long long> cnt((size_t)6 * n);
+	if (dev_d2h(cnt.data(), d_cnt, (size_t)8 * 6 * n, s) || dev_sync(s)) return MC_ERR_CUDA;
 	const double t_reduced = now();
-	c->tot.total_reads = t[0]; c->tot.total_mapped = t[1]; c->tot.total_paired = t[2]; c->tot.total_distance = t[3]; c->tot.read_length_sum = t[4];
-	if (c->tot.total_paired > 1000) c->tot.avg_dist = (uint32_t)(int)(1. * c->tot.total_distance / c->tot.total_paired + .5);
-	// variable-length records: every rank ends up with the records of all ranks, in rank (= file) order
-	std::vector<uint8_t> mine, tmp; std::vector<std::vector<uint8_t> > all;
-	auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; mine.insert(mine.end(), b, b + n); };
-	long long hdr[5] = {(long long)pb.bp, (long long)pb.ind, (long long)pb.ind_seq, (long long)c->inv_sites.size(), (long long)c->tnl_sites.size()};
-	put(hdr, sizeof(hdr));
-	tmp.resize((size_t)pb.bp * 8 + (size_t)pb.ind * sizeof(mc_indel_rec) + (size_t)pb.ind_seq);
-	bad = dev_d2h(tmp.data(), c->d_bp.p, (size_t)pb.bp * 8, s) || dev_d2h(tmp.data() + pb.bp * 8, c->d_ind.p, (size_t)pb.ind * sizeof(mc_indel_rec), s)
-	   || dev_d2h(tmp.data() + pb.bp * 8 + pb.ind * sizeof(mc_indel_rec), c->d_ind_seq.p, (size_t)pb.ind_seq, s) || dev_sync(s);
-	if (bad) return MC_ERR_CUDA;
-	put(tmp.data(), tmp.size());
-	put(c->inv_sites.data(), c->inv_sites.size() * sizeof(mc_site_rec)); put(c->tnl_sites.data(), c->tnl_sites.size() * sizeof(mc_site_rec));
-	if (allgather_bytes(c, comm, mine, all)) return MC_ERR_NCCL;
-	std::vector<int64_t> bp; std::vector<mc_indel_rec> ind; std::vector<uint8_t> seq; std::vector<mc_site_rec> inv, tnl;
-	for (size_t r = 0; r < all.size(); r++)
+	if (independent)
 	{
-		if (all[r].size() < sizeof(hdr)) continue;
-		long long h[5]; memcpy(h, all[r].data(), sizeof(h));
-		const uint8_t* p = all[r].data() + sizeof(h);
-		const size_t seq_base = seq.size();
-		bp.insert(bp.end(), (const int64_t*)p, (const int64_t*)p + h[0]); p += h[0] * 8;
-		for (long long i = 0; i < h[1]; i++) { mc_indel_rec x; memcpy(&x, p + i * sizeof(x), sizeof(x)); x.seq_off += (int32_t)seq_base; ind.push_back(x); }
-		p += h[1] * sizeof(mc_indel_rec);
-		seq.insert(seq.end(), p, p + h[2]); p += h[2];
-		inv.insert(inv.end(), (const mc_site_rec*)p, (const mc_site_rec*)p + h[3]); p += h[3] * sizeof(mc_site_rec);
-		tnl.insert(tnl.end(), (const mc_site_rec*)p, (const mc_site_rec*)p + h[4]);
+		c->tot.total_reads = t[0]; c->tot.total_mapped = t[1]; c->tot.total_paired = t[2]; c->tot.total_distance = t[3]; c->tot.read_length_sum = t[4];
+		if (c->tot.total_paired > 1000) c->tot.avg_dist = (uint32_t)(int)(1. * c->tot.total_distance / c->tot.total_paired + .5);
 	}
-	if (seq.size() >= 0x7fffffffull) { mc_set_error("mc_profile_allreduce: merged indel sequences exceed 2 GiB"); return MC_ERR_OVERFLOW; }
-	bad = c->d_bp.grow_keep(bp.size() * 8 + 64, 0, s) || c->d_ind.grow_keep(ind.size() * sizeof(mc_indel_rec) + 64, 0, s) || c->d_ind_seq.grow_keep(seq.size() + 64, 0, s);
-	bad = bad || dev_h2d(c->d_bp.p, bp.data(), bp.size() * 8, s) || dev_h2d(c->d_ind.p, ind.data(), ind.size() * sizeof(mc_indel_rec), s) || dev_h2d(c->d_ind_seq.p, seq.data(), seq.size(), s);
-	pb.bp = bp.size(); pb.ind = ind.size(); pb.ind_seq = seq.size();
-	bad = bad || dev_h2d(c->d_pbump.p, &pb, sizeof(pb), s) || dev_sync(s);
+	size_t mx[4] = {0, 0, 0, 0}, tot[4] = {0, 0, 0, 0};                  // 0 break points, 1 indel records, 2 indel sequences, 3 sites (inv then tnl)
+	const size_t esz[4] = {8, sizeof(mc_indel_rec), 1, sizeof(mc_site_rec)};
+	auto count_of = [&](int r, int k) -> size_t { return k < 3 ? (size_t)cnt[4 * r + k] : (size_t)(cnt[4 * n + 2 * r] + cnt[4 * n + 2 * r + 1]); };
+	for (int r = 0; r < n; r++) for (int k = 0; k < 4; k++) { mx[k] = std::max(mx[k], count_of(r, k)); tot[k] += count_of(r, k); }
+	for (int k = 0; k < 4; k++) mx[k] = ((mx[k] * esz[k] + 15) & ~(size_t)15);     // padded bytes per rank
+	if (tot[2] >= 0x7fffffffull) { mc_set_error("mc_profile_allreduce: merged indel sequences exceed 2 GiB"); return MC_ERR_OVERFLOW; }
+	// sources must be readable for the padded length
+	const size_t my_bp = (size_t)cnt[4 * c->comm_rank], my_ind = (size_t)cnt[4 * c->comm_rank + 1], my_seq = (size_t)cnt[4 * c->comm_rank + 2];
+	bad = c->d_bp.grow_keep(mx[0] + 64, my_bp * 8, s) || c->d_ind.grow_keep(mx[1] + 64, my_ind * sizeof(mc_indel_rec), s) || c->d_ind_seq.grow_keep(mx[2] + 64, my_seq, s);
+	std::vector<mc_site_rec> sites(c->inv_sites); sites.insert(sites.end(), c->tnl_sites.begin(), c->tnl_sites.end());
+	size_t goff[5] = {0, 0, 0, 0, 0};
+	for (int k = 0; k < 4; k++) goff[k + 1] = goff[k] + mx[k] * n;
+	bad = bad || c->d_comm_buf.reserve(goff[4] + mx[3] + 64) || c->h_comm_buf.reserve(mx[3] * n + 64);
+	if (bad) return MC_ERR_CUDA;
+	uint8_t* gb = c->d_comm_buf.as<uint8_t>(); uint8_t* d_my_sites = gb + goff[4];
+	if (dev_h2d(d_my_sites, sites.data(), sites.size() * sizeof(mc_site_rec), s)) return MC_ERR_CUDA;
+	nccl_api()->GroupStart();
+	if (mx[0]) bad |= nccl_fail(ncclAllGather(c->d_bp.p, gb + goff[0], mx[0], ncclUint8, comm, s), "ncclAllGather(break points)");
+	if (mx[1]) bad |= nccl_fail(ncclAllGather(c->d_ind.p, gb + goff[1], mx[1], ncclUint8, comm, s), "ncclAllGather(indel records)");
+	if (mx[2]) bad |= nccl_fail(ncclAllGather(c->d_ind_seq.p, gb + goff[2], mx[2], ncclUint8, comm, s), "ncclAllGather(indel sequences)");
+	if (mx[3]) bad |= nccl_fail(ncclAllGather(d_my_sites, gb + goff[3], mx[3], ncclUint8, comm, s), "ncclAllGather(sites)");
+	bad |= nccl_fail(nccl_api()->GroupEnd(), "ncclGroupEnd");
+	if (bad) return MC_ERR_NCCL;
+	// compact the padded segments back into the persistent arrays, rank after rank
+	bad = c->d_bp.reserve(tot[0] * 8 + 64) || c->d_ind.reserve(tot[1] * sizeof(mc_indel_rec) + 64) || c->d_ind_seq.reserve(tot[2] + 64);
+	if (bad) return MC_ERR_CUDA;
+	size_t o_bp = 0, o_ind = 0, o_seq = 0;
+	for (int r = 0; r < n; r++)
+	{
+		const size_t nb = count_of(r, 0), ni = count_of(r, 1), ns = count_of(r, 2);
+		bad |= nb ? dev_d2d(c->d_bp.as<uint8_t>() + o_bp * 8, gb + goff[0] + mx[0] * r, nb * 8, s) : 0;
+		bad |= ni ? dev_d2d(c->d_ind.as<uint8_t>() + o_ind * sizeof(mc_indel_rec), gb + goff[1] + mx[1] * r, ni * sizeof(mc_indel_rec), s) : 0;
+		bad |= ns ? dev_d2d(c->d_ind_seq.as<uint8_t>() + o_seq, gb + goff[2] + mx[2] * r, ns, s) : 0;
+		if (ni && o_seq) mc_seqoff_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, s>>>(c->d_ind.as<mc_indel_rec>() + o_ind, (int64_t)ni, (int32_t)o_seq);
+		o_bp += nb; o_ind += ni; o_seq += ns;
+	}
+	PersistBumps pb; pb.bp = tot[0]; pb.ind = tot[1]; pb.ind_seq = tot[2]; pb.pad = 0;
+	bad = bad || dev_h2d(c->d_pbump.p, &pb, sizeof(pb), s) || dev_d2h(c->h_comm_buf.p, gb + goff[3], mx[3] * n, s) || dev_sync(s);
 	if (bad) return MC_ERR_CUDA;
 	c->bp_cap = c->d_bp.cap / 8; c->ind_cap = c->d_ind.cap / sizeof(mc_indel_rec); c->ind_seq_cap = c->d_ind_seq.cap;
+	std::vector<mc_site_rec> inv, tnl;
+	for (int r = 0; r < n; r++)
+	{
+		const mc_site_rec* p = (const mc_site_rec*)(c->h_comm_buf.as<uint8_t>() + mx[3] * r);
+		inv.insert(inv.end(), p, p + cnt[4 * n + 2 * r]); tnl.insert(tnl.end(), p + cnt[4 * n + 2 * r], p + cnt[4 * n + 2 * r] + cnt[4 * n + 2 * r + 1]);
+	}
 	c->inv_sites = inv; c->tnl_sites = tnl;
-	if (dbg) fprintf(stderr, "[mc] rank %d allreduce: counters %.3f ms, records %.3f ms (%zu bytes mine)\n", c->comm_rank, t_reduced - t_begin, now() - t_reduced, mine.size());
+	const size_t mine_bytes = my_bp * 8 + my_ind * sizeof(mc_indel_rec) + my_seq;
+	if (dbg) fprintf(stderr, "[mc] rank %d allreduce: counters %.3f ms, records %.3f ms (%zu bytes mine)\n", c->comm_rank, t_reduced - t_begin, now() - t_reduced, mine_bytes);
 	return MC_OK;
 }
 #endif

@@ -32,6 +32,8 @@ static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* 
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
+static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatecnt_body(i, a, q, list, bump); }
+static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t) { for (int64_t i = 0; i < n; i++) gateadd_body(i, a, list); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for (int64_t q = 0; q < n; q++) bwtsearch_body(q, a); }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
@@ -136,6 +138,14 @@ static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	mc_rescue_kernel<<<148 * 2, MC_RESCUE_WARPS * 32, MC_RESCUE_WARPS * MC_RESCUE_SMEM, s>>>(a); g_launches++;
 	mc_rcommit_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
+__global__ void __launch_bounds__(MC_BLOCK) mc_gatecnt_kernel(const PipeArgs a, const ProfArgs q, int64_t n, uint64_t* list, mc_u64* bump)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) gatecnt_body(i, a, q, list, bump); }
+static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t s)
+{ if (n > 0) { mc_gatecnt_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n, list, bump); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_gateadd_kernel(const PipeArgs a, int64_t n, const uint64_t* list)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) gateadd_body(i, a, list); }
+static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t s)
+{ if (n > 0) { mc_gateadd_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n, list); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_bwtsearch_kernel(const SearchArgs a, int64_t n)
 { int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (q < n) bwtsearch_body(q, a); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t s)

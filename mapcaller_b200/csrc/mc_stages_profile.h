@@ -79,6 +79,27 @@ MC_HD void gateupd_body(int64_t i, const PipeArgs& a, const ProfArgs& q)
 	a.prof.rcount[s] = (uint8_t)(prior + n);
 }
 
+// Several GPUs mapping consecutive shards of one library (mc_ctx.cu, ordered exchange): every rank lists how many gate
+// candidates it has per start column (heads of the sorted key runs, capped at 15 = the 4-bit readCount) ...
+MC_HD void gatecnt_body(int64_t i, const PipeArgs& a, const ProfArgs& q, uint64_t* list, mc_u64* bump)
+{
+	const int64_t s = (int64_t)(q.keys[i] >> MC_KEY_SHIFT);
+	if (i > 0 && (int64_t)(q.keys[i - 1] >> MC_KEY_SHIFT) == s) return;
+	int n = 1;
+	while (n < 15 && i + n < q.n_keys && (int64_t)(q.keys[i + n] >> MC_KEY_SHIFT) == s) n++;
+	const int64_t k = mc_bump_alloc(bump, 1u);
+	list[k] = ((uint64_t)s << 8) | (uint64_t)n;
+}
+// ... and the lists of the ranks before this one in file order are added to readCount before the gate is evaluated, those
+// of the ranks after it afterwards: readCount[start] = min(iMaxDuplicate, earlier + own + later), the same on every rank.
+// A list holds every start once, so the plain read-modify-write is race free.
+MC_HD void gateadd_body(int64_t i, const PipeArgs& a, const uint64_t* list)
+{
+	const int64_t s = (int64_t)(list[i] >> 8);
+	const int v = (int)a.prof.rcount[s] + (int)(list[i] & 0xFF);
+	a.prof.rcount[s] = (uint8_t)(v < a.pr.max_dup ? v : a.pr.max_dup);
+}
+
 MC_HD void prof_base(const PipeArgs& a, int64_t g, int field) // field: 0 A, 1 C, 2 G, 3 T
 {
 	if (g < 0 || g >= a.ix.G) return;

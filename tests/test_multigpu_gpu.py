@@ -1,5 +1,11 @@
-"""Two contexts on two GPUs of one box: each maps its shard, mc_profile_allreduce (NCCL over NVLink) leaves the sum of both
-shard profiles on both ranks.  Checked against the CPU oracle run on the same two shards (as separate libraries)."""
+"""Two contexts on two GPUs of one box (one process per GPU, torchrun, NCCL over NVLink).
+
+* ordered exchange (the default once mc_comm_init was called): the ranks map consecutive shards of ONE library; the avgDist
+  trajectory, the dedup gate and the discordant-pair state are exchanged in file order, so every per-read record, the
+  EstiDistance of every chunk, the totals and - after mc_profile_allreduce - the profile equal the oracle's single run over
+  the whole library;
+* independent shards (mc_params.reserved[2] = 1): each rank maps its shard as a library of its own and
+  mc_profile_allreduce leaves the sum on both ranks; checked against the oracle run on the same two shards."""
 import os
 import subprocess
 import sys
@@ -35,7 +41,7 @@ def test_two_gpu_shards_reduce_to_the_sum(built, tmp_path):
         case = pu.make_case(seed=61, n_pairs=8000, genome_len=120000, contigs=2, sv=2.0)
         ix = pu.build_index(case)
         seq, off = shard.take_shard(case['seq'], case['off'], world, rank)
-        ctx = api.Context(ix, paired=1, device=rank, shard_rank=rank, shard_count=world)
+        ctx = api.Context(ix, paired=1, device=rank, shard_rank=rank, shard_count=world, reserved=(0, 0, 1, 0, 0))
         uid = [api.Context.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
         ctx.map_batch(seq, off)
@@ -72,3 +78,59 @@ def test_two_gpu_shards_reduce_to_the_sum(built, tmp_path):
             assert sorted((k[0], k[1], v) for k, v in c.items()) == sorted(g[key])
         assert sorted(g["inv"]) == sorted(parts[0]["inv"] + parts[1]["inv"])
         assert sorted(g["tnl"]) == sorted(parts[0]["tnl"] + parts[1]["tnl"])
+
+
+CASE = dict(seed=62, n_pairs=9000, genome_len=120000, contigs=2, sv=2.0, n_dup=10, frag_mean=380, frag_sd=60)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("super_batches", [1, 3])
+def test_two_gpus_one_library_equals_single_reference_run(built, tmp_path, super_batches):
+    code = textwrap.dedent("""
+        import os, sys, pickle
+        import numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import torch, torch.distributed as dist
+        import parity_util as pu
+        from mapcaller_b200 import api, shard
+        rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+        torch.cuda.set_device(rank); dist.init_process_group('nccl')
+        case = pu.make_case(**%r)
+        nsb = %d
+        ix = pu.build_index(case)
+        ctx = api.Context(ix, paired=1, device=rank, want_alignments=1, shard_rank=rank, shard_count=world)
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        parts = []
+        for b in range(nsb):
+            sseq, soff = shard.take_shard(case['seq'], case['off'], nsb, b)        # super-batch b of the library ...
+            seq, off = shard.take_shard(sseq, soff, world, rank)                   # ... and this rank's share of it
+            res = ctx.map_batch(seq, off)
+            parts.append(dict(reads=api.unpack_reads(res), est=[int(x) for x in res['chunks']['est_distance']], replays=res['replays']))
+        totals = ctx.totals()
+        ctx.profile_allreduce()
+        ins, dele = ctx.indels()
+        out = dict(parts=parts, totals=totals, profile=ctx.profile_columns(), ins=ins, dele=dele, bp=ctx.breakpoints(),
+                   inv=sorted(ctx.sites(0), key=lambda x: x[0]), tnl=sorted(ctx.sites(1), key=lambda x: x[0]))
+        pickle.dump(out, open(%r + '/o%%d.pkl' %% rank, 'wb'))
+        dist.destroy_process_group()
+    """) % (ROOT, os.path.join(ROOT, "tests"), CASE, super_batches, str(tmp_path))
+    script = tmp_path / "w.py"
+    script.write_text(code)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29612", str(script)])
+    import pickle
+    got = [pickle.load(open(str(tmp_path / ("o%d.pkl" % r)), "rb")) for r in range(2)]
+    case = pu.make_case(**CASE)
+    ix = pu.build_index(case)
+    want = pu.oracle_results(case, ix)
+    reads, est = [], []
+    for b in range(super_batches):
+        for r in range(2):
+            reads += got[r]["parts"][b]["reads"]; est += got[r]["parts"][b]["est"]
+    for r in range(2):
+        t = got[r]["totals"]
+        mine = dict(reads=reads, est=est, profile=got[r]["profile"], ins=got[r]["ins"], dele=got[r]["dele"], bp=got[r]["bp"], inv=got[r]["inv"], tnl=got[r]["tnl"],
+                    counters=dict(reads=t["total_reads"], mapped=t["total_mapped"], paired=t["total_paired"], dist_sum=t["total_distance"], len_sum=t["read_length_sum"],
+                                  avgDist=t["avg_dist"]))
+        pu.assert_same(mine, want)
