@@ -97,7 +97,8 @@ typedef struct {
     int32_t shard_rank;        /* multi-GPU: this context's position in file order (0 when single) */
     int32_t shard_count;       /* multi-GPU: number of shards (1 when single) */
     int32_t reserved[5];       /* reserved[0] != 0: return the per-pair coordinates (mc_batch_out::pairs) even without want_alignments;
-                                  reserved[1] != 0: keep the 128-row reference layout of the index in HBM (the path of texts >= 2^32 symbols) */
+                                  reserved[1] != 0: keep the 128-row reference layout of the index in HBM (the path of texts >= 2^32 symbols);
+                                  reserved[2] != 0: multi-GPU shards are independent libraries (no ordered exchange, see mc_comm_init) */
 } mc_params;
 
 void mc_params_default(mc_params *p);   /* defaults of reference src/main.cpp:159-191 */
@@ -137,7 +138,8 @@ typedef struct {
 
 /* Replaces the body of ReadMapping() (reference src/ReadMapping.cpp:416-646) for one batch:
  * seeding, clustering, pairing, rescue, gapped fills, scoring, pair statistics and the profile
- * update, bit-identical to a single reference thread processing the same reads in order. */
+ * update, bit-identical to a single reference thread processing the same reads in order.
+ * Host batches of >= 400 k reads travel in four pieces and are seeded piece by piece while the rest is on the wire. */
 int mc_map_batch(mc_ctx *ctx, const mc_batch_in *in, mc_batch_out *out);
 
 /* Page-locked host memory for batch inputs: reads placed here are DMA-ed to the GPU directly, pageable memory is
@@ -172,9 +174,19 @@ int mc_profile_sites(mc_ctx *ctx, int32_t kind, const mc_site_rec **recs, int64_
 
 /* Multi-GPU (one context per GPU, one process per GPU): reads shard across the ranks, every rank holds a full index
  * replica.  mc_comm_unique_id() on rank 0 -> ship the 128 bytes to the other ranks -> mc_comm_init() on every rank.
- * mc_profile_allreduce() then sums the device counters of all ranks (ncclAllReduce over NVLink) and gathers the indel /
- * break-point / SV-site records, so that every rank holds the whole-library profile.  `nccl_comm` may be an existing
- * ncclComm_t of the caller, or NULL to use the communicator of mc_comm_init(). */
+ *
+ * From then on the ranks work on ONE library and mc_map_batch() is a collective: within a call, the reads of rank r follow
+ * those of rank r-1 in file order, and the next call continues after the last rank.  The three things the reference does
+ * sequentially in file order - the avgDist feedback (src/ReadMapping.cpp:538-539), the PCR-duplicate gate
+ * (src/AlignmentProfile.cpp:76-77) and the thread-local discordant-pair state (src/ReadMapping.cpp:486-522) - are exchanged
+ * over NCCL inside the call, so every record a rank returns, and the totals (the same on every rank), equal what a single
+ * reference thread produces for the whole library.  Every rank must pass at least one chunk per call.
+ * mc_params.reserved[2] = 1 switches the exchange off: every shard is then mapped as a library of its own.
+ *
+ * mc_profile_allreduce() sums the device counters of all ranks (ncclAllReduce over NVLink) and gathers the indel /
+ * break-point / SV-site records device to device, so that every rank holds the whole-library profile; it ends a library
+ * run (mapping more reads afterwards would count the other ranks' share again).  `nccl_comm` may be an existing
+ * ncclComm_t of the caller (independent shards only), or NULL to use the communicator of mc_comm_init(). */
 int mc_comm_unique_id(uint8_t *out128);
 int mc_comm_init(mc_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t n_ranks);
 int mc_profile_allreduce(mc_ctx *ctx, void *nccl_comm);

@@ -629,7 +629,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 
 		// ---- speculative pairing / alignment with avgDist verification ----
 		std::vector<int32_t> est(NG, (int32_t)(c->tot.avg_dist * 1.5));
-		std::vector<uint8_t> active(NG, 1), computed(NG, 0);
+		std::vector<uint8_t> active(NG, 1), computed(NG, 0), ever(NG, 0);
 		std::vector<mc_chunk_out> g_hc; std::vector<int32_t> g_lo, g_hi;
 		if (od.on) { g_hc.resize(NG); g_lo.resize(NG); g_hi.resize(NG); }
 		// avgDist stays at its initial value until more than 1000 pairs have been seen (src/ReadMapping.cpp:539) and then
@@ -676,7 +676,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			}
 #endif
 			if (hst->overflow) { overflow = true; break; }
-			for (int64_t k = 0; k < NG; k++) if (active[k]) computed[k] = 1;
+			for (int64_t k = 0; k < NG; k++) if (active[k]) computed[k] = ever[k] = 1;
 			// walk the chunks in file order (reference src/ReadMapping.cpp:537-539)
 			std::fill(active.begin(), active.end(), 0);
 			while (first_open < NG)
@@ -685,9 +685,18 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 				const int32_t true_est = (int32_t)(run.avg_dist * 1.5);
 				if (!computed[k] || (paired && !(lo[k] <= true_est && true_est <= hi[k])))
 				{
-					// (re)run everything from here on with the value this chunk really sees
+					// (re)run everything from here on: this chunk with the value it really sees, the later ones with the values
+					// the trajectory is going to take if their sums stay what the previous attempt found (they nearly always do:
+					// only pairs at the edge of the distance window move) - the walk verifies every one of them again
 					if (computed[k]) replays++;
-					for (int64_t j = k; j < NG; j++) { est[j] = true_est; active[j] = 1; computed[j] = 0; }
+					mc_totals pred = run;
+					for (int64_t j = k; j < NG; j++)
+					{
+						est[j] = (int32_t)(pred.avg_dist * 1.5); active[j] = 1; computed[j] = 0;
+						if (!ever[j]) continue;
+						pred.total_paired += hc[j].paired; pred.total_distance += hc[j].dist_sum;
+						if (paired && pred.total_paired > 1000) pred.avg_dist = (uint32_t)(int)(1. * pred.total_distance / pred.total_paired + .5);
+					}
 					break;
 				}
 				mc_chunk_out ck = hc[k]; ck.est_distance = paired ? true_est : 0;

@@ -53,6 +53,25 @@ static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vi
 
 typedef unsigned long long mc_u64; // atomicAdd-compatible 64-bit counter
 
+// "group" = all threads that work on one item together; for the rescue windows that is a whole thread block
+#ifdef MC_HOSTEMU
+#define MC_GROUP_SYNC() do { } while (0)
+static inline int mc_group_any(int v) { return v; }
+static inline int64_t mc_group_bcast64(int64_t v, int) { return v; }
+#else
+#define MC_GROUP_SYNC() __syncthreads()
+static __device__ __forceinline__ int mc_group_any(int v) { return __syncthreads_or(v); }
+static __device__ __forceinline__ int64_t mc_group_bcast64(int64_t v, int lane)
+{
+	__shared__ long long slot;
+	if (lane == 0) slot = v;
+	__syncthreads();
+	v = slot;
+	__syncthreads();
+	return v;
+}
+#endif
+
 // Arena cursors are bumped by (nearly) every thread of a kernel.  Same-address atomics serialise in the L2 atomic unit
 // (about one lane per clock), so the lanes that arrive together first scan their sizes inside the warp and issue ONE
 // atomic for the group; each lane then owns [base + prefix, base + prefix + n).

@@ -102,25 +102,24 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_seed_kernel(const PipeArgs a, int
 { const int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) seed_body(i, a); }
 static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t s)
 { if (n > first) { mc_seed_kernel<<<(unsigned)((n - first + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, first, n); g_launches++; } }
-// rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent warps (warp w
-// takes windows w, w + n_warps, ...), commit per pair.  A window search is a serial, latency-bound piece of code over small
-// tables (word list, diagonal histogram, filter): they live in shared memory (28 KB per warp, 4 warps per block); a lone
-// warp going to global memory for them was ~20x slower.
-#define MC_RESCUE_WARPS 4
-#define MC_RESCUE_SMEM (28 * 1024)
+// rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent thread blocks
+// (block b takes windows b, b + n_blocks, ...), commit per pair.  A window search is a chain of short loops over small
+// tables (word list, diagonal histogram, filter, staged window): the tables live in shared memory (24 KB per block, so 8
+// blocks per SM) and the 128 threads of the block share every loop - windows in repeats cost 100x the typical one and
+// their latency is what a replay attempt waits for.
+#define MC_RESCUE_THREADS 128
+#define MC_RESCUE_SMEM (24 * 1024)
 __global__ void __launch_bounds__(MC_BLOCK) mc_rwenum_kernel(const PipeArgs a)
 {
 	const int64_t n = (int64_t)*a.rtask_bump - a.rtask_begin;
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) rwenum_body(t, a);
 }
-__global__ void __launch_bounds__(MC_RESCUE_WARPS * 32) mc_rescue_kernel(const PipeArgs a)
+__global__ void __launch_bounds__(MC_RESCUE_THREADS, 8) mc_rescue_kernel(const PipeArgs a)
 {
 	extern __shared__ __align__(16) uint8_t rescue_smem[];
 	if (a.st->overflow & 0xFF) return;          // the window list is incomplete: the attempt is going to be repeated with larger arenas
-	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
 	const int64_t n = (int64_t)*a.rwin_bump - a.rwin_begin;
-	uint8_t* mine = rescue_smem + (threadIdx.x >> 5) * MC_RESCUE_SMEM;
-	for (int64_t t = warp; t < n; t += n_warps) { rwin_body(t, threadIdx.x & 31, 32, a, mine, MC_RESCUE_SMEM); __syncwarp(); }
+	for (int64_t t = blockIdx.x; t < n; t += gridDim.x) { rwin_body(t, threadIdx.x, MC_RESCUE_THREADS, a, rescue_smem, MC_RESCUE_SMEM); __syncthreads(); }
 }
 __global__ void __launch_bounds__(MC_BLOCK) mc_rcommit_kernel(const PipeArgs a)
 {
@@ -132,10 +131,10 @@ static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
 	static bool configured = false;
-	if (!configured) { cudaFuncSetAttribute(mc_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_RESCUE_WARPS * MC_RESCUE_SMEM); configured = true; }
+	if (!configured) { cudaFuncSetAttribute(mc_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_RESCUE_SMEM); configured = true; }
 	int64_t tb = (max_tasks + MC_BLOCK - 1) / MC_BLOCK; if (tb > 148 * 2) tb = 148 * 2;
 	mc_rwenum_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
-	mc_rescue_kernel<<<148 * 2, MC_RESCUE_WARPS * 32, MC_RESCUE_WARPS * MC_RESCUE_SMEM, s>>>(a); g_launches++;
+	mc_rescue_kernel<<<148 * 8, MC_RESCUE_THREADS, MC_RESCUE_SMEM, s>>>(a); g_launches++;
 	mc_rcommit_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
 __global__ void __launch_bounds__(MC_BLOCK) mc_gatecnt_kernel(const PipeArgs a, const ProfArgs q, int64_t n, uint64_t* list, mc_u64* bump)

@@ -151,25 +151,25 @@ MC_HD int kmer_list_of_read(const uint8_t* s, int len, KmerEnt* out)
 	return n;
 }
 
-// The same list by all lanes of the warp when the read is plain ACGT/acgt (no 'N', nothing the sequential rolling
+// The same list by all lanes of the group when the read is plain ACGT/acgt (no 'N', nothing the sequential rolling
 // formula would treat specially): word p is the fresh id of bases [p, p+8) and is labelled p.  Otherwise lane 0 runs the
 // sequential routine.  Returns the number of words to every lane through lanebuf[0].
 MC_HD int kmer_list_coop(const uint8_t* s, int len, KmerEnt* out, int lane, int nl, int32_t* lanebuf)
 {
 	int bad = 0;
 	for (int i = lane; i < len; i += nl) if (mc_nt4(s[i]) > 3) bad = 1;
-	bad = mc_warp_max(bad);
+	bad = mc_group_any(bad);
 	if (!bad)
 	{
 		const int n = len >= 8 ? len - 7 : 0;
 		for (int p = lane; p < n; p += nl) { out[p].label = p; out[p].wid = kmer_fresh_id(s, p); }
-		MC_WARP_SYNC();
+		MC_GROUP_SYNC();
 		return n;
 	}
 	if (lane == 0) lanebuf[0] = kmer_list_of_read(s, len, out);
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	const int n = lanebuf[0];
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	return n;
 }
 
@@ -275,7 +275,7 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 	uint32_t* wkid = clist + n_hits; const uint32_t* wkid0 = wkid - gs;          // word id of every scanned offset
 	uint8_t* wref = (uint8_t*)(wkid + n_hits); const uint8_t* wref0 = wref - gs;
 	for (int i = lane; i < ge - gs + 8; i += nl) { const int64_t pos = left + gs + i; wref[i] = (pos < 0 || pos >= a.ix.twoG) ? 4 : (uint8_t)mc_ref_code(a.ix, pos); }
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	{
 		// pass 1: each lane owns a contiguous run of offsets (so the reference word can be rolled) and keeps those whose word
 		// passes the filter; pass 2: the warp takes the survivors one by one and all lanes compare them with the read's words
@@ -290,7 +290,7 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 			clist[mc_atomic_add(ccount, 1)] = ((uint32_t)(g + M) << 16) | (w & 0xFFFFu);
 		}
 	}
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	int in_far = -1, out_near = 1 << 30;   // inside hit closest to the moving edge (distance from it), margin hit closest to it
 	{
 		const int nc = *ccount;
@@ -312,7 +312,7 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 		}
 	}
 	lanebuf[4 * nl + lane] = in_far; lanebuf[5 * nl + lane] = out_near;
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	int best = 0, bd = 0;
 	for (int i = lane; i < ndiag; i += nl)
 	{
@@ -321,7 +321,7 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 		if (sc > best) { best = sc; bd = i + dmin; }   // ascending diagonals inside a lane: first maximum wins
 	}
 	lanebuf[2 * lane] = best; lanebuf[2 * lane + 1] = bd;
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	best = 0; bd = 0; in_far = -1; out_near = 1 << 30;
 	for (int l = 0; l < nl; l++)
 	{
@@ -331,7 +331,7 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 		if (f >= 0 && (in_far < 0 || f < in_far)) in_far = f;
 		if (o < out_near) out_near = o;
 	}
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	if (!clipped || dir == 1)
 	{
 		if (in_far >= 0 && est - in_far > *iv_lo) *iv_lo = est - in_far;
@@ -347,9 +347,9 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 		if (ok) { rescue_scan_diag(wkid0, km, nk, left, slen, bd, a.pairs + pb, &n); res->score = best; res->pbeg = (int32_t)pb; res->n = n; }
 		lanebuf[6 * nl] = ok;
 	}
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	const int ok = lanebuf[6 * nl];
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	return ok != 0;
 }
 
@@ -357,7 +357,7 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 // (a mate anchored in a repeat family) and the windows are independent of each other: the candidates they test, the score
 // floors (the mates' best scores on entry) and the skip tests do not change while the reference loops over them.
 //   rwenum_body   one thread per rescue pair: strategy, thresholds, the list of windows
-//   rwin_body     one warp per window: the search itself
+//   rwin_body     one thread block per window: the search itself
 //   rcommit_body  one thread per rescue pair: appends the found candidates in the reference's order, links the partners,
 //                 masks, and intersects the EstiDistance validity intervals
 MC_HD void rwenum_body(int64_t t, const PipeArgs& a)
@@ -403,7 +403,7 @@ MC_HD void rwin_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* fa
 	{
 		int64_t ws = 0;
 		if (lane == 0) ws = (int64_t)mc_atomic_add(a.dpws_bump, (mc_u64)wsn);
-		ws = mc_bcast64(ws);
+		ws = mc_group_bcast64(ws, lane);
 		if (ws + wsn > a.dpws_cap) { if (lane == 0) mc_atomic_or(&a.st->overflow, (mc_u64)1 << 32); return; }
 		scratch = a.dpws + ws;
 	}
@@ -411,10 +411,10 @@ MC_HD void rwin_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* fa
 	uint32_t* hits = (uint32_t*)(km + lm + 2); int32_t* lanebuf = (int32_t*)(hits + n_hits);
 	uint32_t* bloom = (uint32_t*)(lanebuf + 6 * nl + 4);   // 4096-bit filter over the low 12 bits of the mate's word ids
 	for (int i = lane; i < 128; i += nl) bloom[i] = 0;
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	const int nk = kmer_list_coop(a.seq + a.roff[rm], lm, km, lane, nl, lanebuf);
 	for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km[i].wid & 4095) >> 5], 1u << (km[i].wid & 31));
-	MC_WARP_SYNC();
+	MC_GROUP_SYNC();
 	int lo = -2147483647, hi = 2147483647;
 	const bool ok = rescue_try(a, lane, nl, w, km, nk, lm, dir, d, est, w->floor, hits, n_hits, lanebuf, bloom, &lo, &hi);
 	if (lane == 0) { w->ok = ok ? 1 : 0; w->lo = lo; w->hi = hi; }
