@@ -163,6 +163,13 @@ int mc_reset(mc_ctx *ctx);
  * reference does. `out` must hold (end-beg)*16 bytes. */
 int mc_profile_read(mc_ctx *ctx, int64_t beg, int64_t end, void *out);
 
+/* CheckMappingCoverage / ReportDuplicationRate (reference src/ReadMapping.cpp:648-687) as device reductions over the
+ * resident profile, without downloading it: columns with A+C+G+T > 0 (iAlignedBase) and their sum (iTotalCoverage);
+ * columns with readCount > 0 and the sum of their readCount.  avgCov = (int)(coverage_sum / aligned_bases + .5),
+ * duplication rate = 100 * (dup_reads - dup_sites) / dup_sites. */
+typedef struct { int64_t aligned_bases, coverage_sum, dup_sites, dup_reads; } mc_profile_stats;
+int mc_profile_summary(mc_ctx *ctx, mc_profile_stats *out);
+
 typedef struct { int64_t pos; int32_t kind /* 0 ins, 1 del */, len, count, seq_off; } mc_indel_rec;
 /* Unique (pos, kind, sequence) triples with their uint16-wrapped counts, sorted by (kind,pos,seq). */
 int mc_profile_indels(mc_ctx *ctx, const mc_indel_rec **recs, int64_t *n_recs, const uint8_t **seq_arena);

@@ -100,6 +100,7 @@ def lib():
         L.mc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.mc_reset_stats.argtypes = [C.c_void_p]
         L.mc_profile_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        L.mc_profile_summary.argtypes = [C.c_void_p, C.c_void_p]
         L.mc_profile_indels.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
         L.mc_profile_breakpoints.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_sites.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
@@ -313,6 +314,12 @@ class Context:
         cols = [(b >> np.uint64(s)) & np.uint64(0xFFF) for s in (0, 12, 24, 36, 48)] + [(b >> np.uint64(60)) & np.uint64(0xF)]
         cols += [p["F1"], p["R2"], p["F2"], p["R1"]]
         return np.stack([c.astype(np.int32) for c in cols], axis=1)
+
+    def profile_summary(self) -> dict:
+        """CheckMappingCoverage / ReportDuplicationRate figures from device reductions (no profile download)."""
+        v = (C.c_int64 * 4)()
+        _check(lib().mc_profile_summary(self._h, v), "mc_profile_summary")
+        return dict(aligned_bases=int(v[0]), coverage_sum=int(v[1]), dup_sites=int(v[2]), dup_reads=int(v[3]))
 
     def indels(self):
         """[(pos, seq bytes, count)] for insertions, same for deletions (InsertSeqMap / DeleteSeqMap)."""

@@ -955,11 +955,9 @@ int mc_map_staged(mc_ctx* c, int32_t slot, mc_batch_out* out)
 	return run_batch(c, c->slots[slot], out, false);
 }
 
-int mc_profile_read(mc_ctx* c, int64_t beg, int64_t end, void* outp)
+// packs the columns [beg, end) tile by tile; every tile is either copied to `outp` or reduced into the four counters `acc`
+static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64* d_acc)
 {
-	if (!c || !outp || beg < 0 || end > c->G || beg > end) { mc_set_error("mc_profile_read: bad range"); return MC_ERR_ARG; }
-	if (!c->prm.update_profile) { mc_set_error("mc_profile_read: context was created without update_profile"); return MC_ERR_ARG; }
-	if (beg == end) return MC_OK;
 	DevProfile p; p.base16 = c->d_base16.as<uint32_t>(); p.sdiff = c->d_sdiff.as<int32_t>(); p.cdiff = c->d_cdiff.as<int32_t>(); p.mdiff = c->d_mdiff.as<int32_t>();
 	p.rcount = c->d_rcount.as<uint8_t>();
 	// the range counters are difference arrays: block totals, exclusive scan over the blocks, then every block sums its own columns
@@ -977,9 +975,39 @@ int mc_profile_read(mc_ctx* c, int64_t beg, int64_t end, void* outp)
 		const int64_t b1 = std::min(nb, b0 + tile_blocks);
 		const int64_t tb = std::max(beg, b0 * MC_PROF_BLOCK), te = std::min(end, b1 * MC_PROF_BLOCK);
 		launch_profpack(c->ix, p, nb, sums, b0, b1, tb, te, c->d_sort.as<uint64_t>(), c->stream);
-		if (dev_d2h((uint8_t*)outp + (tb - beg) * 16, c->d_sort.p, (size_t)(te - tb) * 16, c->stream) || dev_sync(c->stream)) rc = MC_ERR_CUDA;
+		if (outp) { if (dev_d2h((uint8_t*)outp + (tb - beg) * 16, c->d_sort.p, (size_t)(te - tb) * 16, c->stream) || dev_sync(c->stream)) rc = MC_ERR_CUDA; }
+		else launch_profstat(te - tb, c->d_sort.as<uint64_t>(), d_acc, c->stream);
 	}
+	if (dev_sync(c->stream)) rc = MC_ERR_CUDA;
 	d_sums.release();
+	return rc;
+}
+
+int mc_profile_read(mc_ctx* c, int64_t beg, int64_t end, void* outp)
+{
+	if (!c || !outp || beg < 0 || end > c->G || beg > end) { mc_set_error("mc_profile_read: bad range"); return MC_ERR_ARG; }
+	if (!c->prm.update_profile) { mc_set_error("mc_profile_read: context was created without update_profile"); return MC_ERR_ARG; }
+	if (beg == end) return MC_OK;
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	return profile_walk(c, beg, end, outp, nullptr);
+}
+
+int mc_profile_summary(mc_ctx* c, mc_profile_stats* out)
+{
+	if (!c || !out) { mc_set_error("mc_profile_summary: null argument"); return MC_ERR_ARG; }
+	if (!c->prm.update_profile) { mc_set_error("mc_profile_summary: context was created without update_profile"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	DBuf d_acc;
+	if (d_acc.reserve(64) || dev_zero(d_acc.p, 64, c->stream)) return MC_ERR_CUDA;
+	int rc = profile_walk(c, 0, c->G, nullptr, d_acc.as<mc_u64>());
+	mc_u64 h[4] = {0, 0, 0, 0};
+	if (rc == MC_OK && (dev_d2h(h, d_acc.p, 32, c->stream) || dev_sync(c->stream))) rc = MC_ERR_CUDA;
+	d_acc.release();
+	out->aligned_bases = (int64_t)h[0]; out->coverage_sum = (int64_t)h[1]; out->dup_sites = (int64_t)h[2]; out->dup_reads = (int64_t)h[3];
 	return rc;
 }
 

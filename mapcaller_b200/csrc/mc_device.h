@@ -53,6 +53,21 @@ static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vi
 
 typedef unsigned long long mc_u64; // atomicAdd-compatible 64-bit counter
 
+// 8-lane tiles of a warp (one normal piece each, mc_stages_align.h): sync and sum inside the tile
+#ifdef MC_HOSTEMU
+#define MC_TILE8_SYNC() do { } while (0)
+static inline int mc_tile8_sum(int v) { return v; }
+#else
+#define MC_TILE8_MASK (0xFFu << (threadIdx.x & 24))
+#define MC_TILE8_SYNC() __syncwarp(MC_TILE8_MASK)
+static __device__ __forceinline__ int mc_tile8_sum(int v)
+{
+	const unsigned m = MC_TILE8_MASK;
+	v += __shfl_xor_sync(m, v, 4); v += __shfl_xor_sync(m, v, 2); v += __shfl_xor_sync(m, v, 1);
+	return v;
+}
+#endif
+
 // "group" = all threads that work on one item together; for the rescue windows that is a whole thread block
 #ifdef MC_HOSTEMU
 #define MC_GROUP_SYNC() do { } while (0)
@@ -77,6 +92,7 @@ static __device__ __forceinline__ int64_t mc_group_bcast64(int64_t v, int lane)
 // atomic for the group; each lane then owns [base + prefix, base + prefix + n).
 #ifdef MC_HOSTEMU
 static inline int64_t mc_bump_alloc(mc_u64* bump, uint32_t n) { mc_u64 o = *bump; *bump += n; return (int64_t)o; }
+static inline void mc_bump_alloc2(mc_u64* b0, uint32_t n0, mc_u64* b1, uint32_t n1, int64_t* o0, int64_t* o1) { *o0 = mc_bump_alloc(b0, n0); *o1 = mc_bump_alloc(b1, n1); }
 #else
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
@@ -90,6 +106,18 @@ static __device__ __forceinline__ int64_t mc_bump_alloc(mc_u64* bump, uint32_t n
 	if (g.thread_rank() == 0) base = atomicAdd(bump, (mc_u64)total);
 	base = g.shfl(base, 0);
 	return (int64_t)(base + pre);
+}
+// two cursors at once: both atomics are in flight together, one round trip instead of two
+static __device__ __forceinline__ void mc_bump_alloc2(mc_u64* b0, uint32_t n0, mc_u64* b1, uint32_t n1, int64_t* o0, int64_t* o1)
+{
+	namespace cg = cooperative_groups;
+	cg::coalesced_group g = cg::coalesced_threads();
+	const uint32_t p0 = cg::exclusive_scan(g, n0), p1 = cg::exclusive_scan(g, n1);
+	const uint32_t t0 = g.shfl(p0 + n0, g.size() - 1), t1 = g.shfl(p1 + n1, g.size() - 1);
+	mc_u64 a0 = 0, a1 = 0;
+	if (g.thread_rank() == 0) { a0 = atomicAdd(b0, (mc_u64)t0); a1 = atomicAdd(b1, (mc_u64)t1); }
+	a0 = g.shfl(a0, 0); a1 = g.shfl(a1, 0);
+	*o0 = (int64_t)(a0 + p0); *o1 = (int64_t)(a1 + p1);
 }
 #endif
 
@@ -105,6 +133,59 @@ static __device__ __forceinline__ void mc_stat_add(mc_u64* p, uint32_t v)
 	if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1) && sum) atomicAdd(p, (mc_u64)sum);
 }
 #endif
+
+// The same for kernels with one thread per read, where (nearly) every thread of a block needs a range: the sizes are scanned
+// across the BLOCK and one thread issues the atomic - returning atomics on one address complete at roughly one per 20 clocks
+// on B200 (the SHFL that waits for the warp's atomic was 57 % of the stall samples of the scatter kernel), so the count of
+// atomics is what matters.  EVERY thread of the block must call (n = 0 when it needs nothing).  Up to two cursors at once.
+#ifdef MC_HOSTEMU
+static inline void mc_block_bump2(mc_u64* b0, uint32_t n0, mc_u64* b1, uint32_t n1, int64_t* o0, int64_t* o1)
+{ *o0 = mc_bump_alloc(b0, n0); *o1 = b1 ? mc_bump_alloc(b1, n1) : 0; }
+#else
+static __device__ __forceinline__ void mc_block_bump2(mc_u64* b0, uint32_t n0, mc_u64* b1, uint32_t n1, int64_t* o0, int64_t* o1)
+{
+	__shared__ uint32_t wsum0[32], wsum1[32];
+	__shared__ unsigned long long base0, base1;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	uint32_t v0 = n0, v1 = n1;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const uint32_t t0 = __shfl_up_sync(0xffffffffu, v0, d), t1 = __shfl_up_sync(0xffffffffu, v1, d);
+		if (lane >= d) { v0 += t0; v1 += t1; }
+	}
+	if (lane == 31) { wsum0[w] = v0; wsum1[w] = v1; }
+	__syncthreads();
+	if (w == 0)
+	{
+		uint32_t s0 = lane < nw ? wsum0[lane] : 0, s1 = lane < nw ? wsum1[lane] : 0;
+		const uint32_t own0 = s0, own1 = s1;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, d), t1 = __shfl_up_sync(0xffffffffu, s1, d);
+			if (lane >= d) { s0 += t0; s1 += t1; }
+		}
+		wsum0[lane] = s0 - own0; wsum1[lane] = s1 - own1;     // exclusive prefix of the warp totals
+		if (lane == 31)
+		{
+			base0 = s0 ? atomicAdd(b0, (mc_u64)s0) : 0;
+			base1 = (b1 && s1) ? atomicAdd(b1, (mc_u64)s1) : 0;
+		}
+	}
+	__syncthreads();
+	*o0 = (int64_t)(base0 + wsum0[w] + v0 - n0);
+	*o1 = (int64_t)(base1 + wsum1[w] + v1 - n1);
+	__syncthreads();                                       // the scratch may be reused by the next call
+}
+#endif
+static
+#ifndef MC_HOSTEMU
+__device__ __forceinline__
+#else
+inline
+#endif
+int64_t mc_block_bump(mc_u64* bump, uint32_t n) { int64_t o0, o1; mc_block_bump2(bump, n, nullptr, 0, &o0, &o1); return o0; }
 
 // ---- FM-index replica in HBM (layout of the reference's bwt_t, unchanged) ------------------------
 struct DevIndex {

@@ -13,6 +13,11 @@ typedef int mc_stream_t;
 	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a); }
 #define MC_LAUNCH2(name) \
 	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, a, q); }
+// bodies that take part in block-wide cursor bumps get a `live` flag (false for the padding threads of the last block)
+#define MC_LAUNCH1B(name) \
+	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, true, a); }
+#define MC_LAUNCH2B(name) \
+	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) name##_body(i, true, a, q); }
 static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t)
 {
 	for (int64_t i = 0; i < n; i++) rwenum_body(i, a);
@@ -32,6 +37,7 @@ static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* 
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
+static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) profstat_body(i, recs, acc); }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatecnt_body(i, a, q, list, bump); }
 static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t) { for (int64_t i = 0; i < n; i++) gateadd_body(i, a, list); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for (int64_t q = 0; q < n; q++) bwtsearch_body(q, a); }
@@ -46,6 +52,17 @@ static int64_t g_launches = 0;
 	{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) name##_body(i, a); } \
 	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t s) \
 	{ if (n > 0) { mc_##name##_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
+// bodies that take part in block-wide cursor bumps: every thread of the block runs the body, `live` = inside the batch
+#define MC_LAUNCH1B(name) \
+	__global__ void __launch_bounds__(MC_BLOCK) mc_##name##_kernel(const PipeArgs a, int64_t n) \
+	{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; name##_body(i, i < n, a); } \
+	static void launch_##name(const PipeArgs& a, int64_t n, mc_stream_t s) \
+	{ if (n > 0) { mc_##name##_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
+#define MC_LAUNCH2B(name) \
+	__global__ void __launch_bounds__(MC_BLOCK) mc_##name##_kernel(const PipeArgs a, const ProfArgs q, int64_t n) \
+	{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; name##_body(i, i < n, a, q); } \
+	static void launch_##name(const PipeArgs& a, const ProfArgs& q, int64_t n, mc_stream_t s) \
+	{ if (n > 0) { mc_##name##_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n); g_launches++; } }
 #define MC_LAUNCH2(name) \
 	__global__ void __launch_bounds__(MC_BLOCK) mc_##name##_kernel(const PipeArgs a, const ProfArgs q, int64_t n) \
 	{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) name##_body(i, a, q); } \
@@ -72,17 +89,17 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_chunkstat_kernel(const PipeArgs a
 }
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t s)
 { if (n > 0) { mc_chunkstat_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n); g_launches++; } }
-// normal pieces: persistent warps over the current attempt's piece list
+// normal pieces: persistent 8-lane tiles over the current attempt's piece list (four independent load chains per warp)
 __global__ void __launch_bounds__(MC_BLOCK) mc_piece_kernel(const PipeArgs a)
 {
-	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	const int64_t tile = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3, n_tiles = ((int64_t)gridDim.x * blockDim.x) >> 3;
 	const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin;
-	for (int64_t t = warp; t < n; t += n_warps) { piece_body(t, threadIdx.x & 31, 32, a); __syncwarp(); }
+	for (int64_t t = tile; t < n; t += n_tiles) piece_body(t, threadIdx.x & 7, 8, a);
 }
 static void launch_piece(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
-	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
+	int64_t blocks = (max_tasks * 8 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
 	mc_piece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
 // mate reversal and seeding take a read range [first, n): a batch that arrives from the host in pieces is seeded piece by
@@ -137,6 +154,10 @@ static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	mc_rescue_kernel<<<148 * 8, MC_RESCUE_THREADS, MC_RESCUE_SMEM, s>>>(a); g_launches++;
 	mc_rcommit_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
+__global__ void __launch_bounds__(MC_BLOCK) mc_profstat_kernel(int64_t n, const uint64_t* recs, mc_u64* acc)
+{ for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (int64_t)gridDim.x * blockDim.x) if (i < n) profstat_body(i, recs, acc); }
+static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t s)
+{ if (n > 0) { int64_t b = (n + MC_BLOCK - 1) / MC_BLOCK; if (b > 148 * 8) b = 148 * 8; mc_profstat_kernel<<<(unsigned)b, MC_BLOCK, 0, s>>>(n, recs, acc); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_gatecnt_kernel(const PipeArgs a, const ProfArgs q, int64_t n, uint64_t* list, mc_u64* bump)
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) gatecnt_body(i, a, q, list, bump); }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t s)
@@ -167,7 +188,7 @@ MC_LAUNCH1(expand)
 MC_LAUNCH1(cluster)
 MC_LAUNCH1(single)
 MC_LAUNCH1(pair)
-MC_LAUNCH1(alnprep)
+MC_LAUNCH1B(alnprep)
 #ifdef MC_HOSTEMU
 MC_LAUNCH1(dp)
 #else
@@ -175,10 +196,10 @@ MC_LAUNCH1(dp)
 #endif
 MC_LAUNCH1(alnfin)
 MC_LAUNCH1(pairstat)
-MC_LAUNCH2(profkey)
+MC_LAUNCH2B(profkey)
 MC_LAUNCH2(gate)
 MC_LAUNCH2(gateupd)
-MC_LAUNCH2(scatter)
+MC_LAUNCH2B(scatter)
 #ifndef MC_HOSTEMU
 // persistent warps over the pieces queued by mc_scatter_kernel
 __global__ void __launch_bounds__(MC_BLOCK) mc_profpiece_kernel(const PipeArgs a, const ProfArgs q)

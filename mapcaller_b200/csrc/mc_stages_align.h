@@ -25,23 +25,35 @@ MC_HOST_HD int64_t dp_ws_bytes(int m, int n) { return dp_tb_bytes(m, n) + 8 * (i
 // gapped fill.  (reference src/ReadAlignment.cpp:306-342 with RemoveOverlaps :38, RemoveNullFragPairs :29,
 // IdentifyNormalPairs :67, CheckAlignmentValidity src/tools.cpp:119, ProcessNormalPair :155)
 // ------------------------------------------------------------------------------------------------
-MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
+// The three arenas (fragments, alignment strings, piece queue) are claimed with block-wide cursor bumps: every thread of the
+// block takes part in both (`live` = false for the threads past the end of the batch).
+MC_HD void alnprep_body(int64_t r, bool live, const PipeArgs& a)
 {
-	if (!a.read_redo[r]) return;
-	const uint8_t* rs = a.seq + a.roff[r];
-	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
-	const int64_t co = pa_cand_off(a, r);
-	const int nc = a.ncand[r];
+	live = live && a.read_redo[r];
+	const int rlen = live ? (int)(a.roff[r + 1] - a.roff[r]) : 0;
+	const int64_t co = live ? pa_cand_off(a, r) : 0;
+	const int nc = live ? a.ncand[r] : 0;
+	int cap_total = 0;
 	for (int ci = 0; ci < nc; ci++)
 	{
 		a.cfrag[co + ci] = 0; a.cnfrag[co + ci] = 0; a.corient[co + ci] = -1;
 		if (a.cscore[co + ci] == 0) continue;
 		const Cand c = a.cands[co + ci];
+		cap_total += 2 * (c.pend - c.pbeg) + 1;
+	}
+	int64_t fb = mc_block_bump(a.frag_bump, (uint32_t)cap_total);
+	bool dead = false;
+	if (cap_total && fb + cap_total > a.frag_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 8); dead = true; }
+	int need_total = 0, np_total = 0;
+	for (int ci = 0; ci < nc && !dead; ci++)
+	{
+		if (a.cscore[co + ci] == 0) continue;
+		const Cand c = a.cands[co + ci];
 		const int ns = c.pend - c.pbeg;
 		const int cap = 2 * ns + 1;
-		const int64_t fb = mc_bump_alloc(a.frag_bump, (uint32_t)cap);
-		if (fb + cap > a.frag_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 8); a.cscore[co + ci] = 0; continue; }
 		mc_frag_out* f = a.frags + fb;
+		const int64_t fbase = fb;
+		fb += cap;
 		// seeds sorted by (rPos, gPos), written into the upper half so the final list can be built in place below
 		mc_frag_out* s = f + (cap - ns);
 		for (int i = 0; i < ns; i++)
@@ -112,32 +124,41 @@ MC_HD void alnprep_body(int64_t r, const PipeArgs& a)
 			if (!ok) { a.cscore[co + ci] = 0; continue; }
 		}
 		// space for the strings of the normal pieces; piece_body lays them out
-		int need = 0, np = 0;
-		for (int i = 0; i < nf; i++) if (!f[i].bSimple) { need += 2 * (f[i].rLen + f[i].gLen); np++; }
-		if (np)
+		for (int i = 0; i < nf; i++) if (!f[i].bSimple) { need_total += 2 * (f[i].rLen + f[i].gLen); np_total++; }
+		a.cfrag[co + ci] = (int32_t)fbase; a.cnfrag[co + ci] = nf;
+	}
+	if (dead) for (int ci = 0; ci < nc; ci++) a.cscore[co + ci] = 0;
+	int64_t ab, pt;                                       // pieces never outnumber fragments: the piece list has frag_cap entries
+	mc_block_bump2(a.aln_bump, (uint32_t)need_total, a.ptask_bump, (uint32_t)np_total, &ab, &pt);
+	if (!np_total) return;
+	if (ab + need_total > a.aln_cap)
+	{
+		mc_atomic_or(&a.st->overflow, (mc_u64)1 << 16);
+		for (int ci = 0; ci < nc; ci++) { a.cscore[co + ci] = 0; a.cfrag[co + ci] = 0; a.cnfrag[co + ci] = 0; }
+		return;
+	}
+	for (int ci = 0; ci < nc; ci++)
+	{
+		const int nf = a.cnfrag[co + ci];
+		if (!nf || a.cscore[co + ci] == 0) continue;
+		const int64_t fbase = a.cfrag[co + ci];
+		mc_frag_out* f = a.frags + fbase;
+		for (int i = 0; i < nf; i++)
 		{
-			int64_t ab = mc_bump_alloc(a.aln_bump, (uint32_t)need);
-			if (ab + need > a.aln_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 16); a.cscore[co + ci] = 0; continue; }
-			const int64_t pt = mc_bump_alloc(a.ptask_bump, (uint32_t)np);   // pieces never outnumber fragments: the list has frag_cap entries
-			int k = 0;
-			for (int i = 0; i < nf; i++)
-			{
-				mc_frag_out& x = f[i];
-				if (x.bSimple) continue;
-				const int cp = x.rLen + x.gLen;
-				x.aln_off = (int32_t)ab; x.aln_cap = cp; ab += 2 * cp;
-				x.aln_len = x.rLen > x.gLen ? x.rLen : x.gLen;
-				x.pad = (int32_t)r;                     // internal: the read this piece belongs to
-				if (pt + k < a.frag_cap) a.ptask[pt + k] = (int32_t)(fb + i); else mc_atomic_or(&a.st->overflow, (mc_u64)1 << 8);
-				k++;
-			}
+			mc_frag_out& x = f[i];
+			if (x.bSimple) continue;
+			const int cp = x.rLen + x.gLen;
+			x.aln_off = (int32_t)ab; x.aln_cap = cp; ab += 2 * cp;
+			x.aln_len = x.rLen > x.gLen ? x.rLen : x.gLen;
+			x.pad = (int32_t)r;                     // internal: the read this piece belongs to
+			if (pt < a.frag_cap) a.ptask[pt] = (int32_t)(fbase + i); else mc_atomic_or(&a.st->overflow, (mc_u64)1 << 8);
+			pt++;
 		}
-		a.cfrag[co + ci] = (int32_t)fb; a.cnfrag[co + ci] = nf;
 	}
 }
 
 // ------------------------------------------------------------------------------------------------
-// piece: `nl` lanes (a warp) lay out the two strings of one normal piece - read bases against RefSequence, both
+// piece: `nl` lanes (an 8-lane tile of a warp: the median piece is 13 bases) lay out the two strings of one normal piece - read bases against RefSequence, both
 // reverse-complemented on the reverse strand - count the mismatches and queue the piece for a gapped fill when the
 // reference would run one (ProcessNormalPair, reference src/ReadAlignment.cpp:155-191)
 // ------------------------------------------------------------------------------------------------
@@ -164,10 +185,10 @@ MC_HD void piece_body(int64_t t, int lane, int nl, const PipeArgs& a)
 	bool dp = x.rLen != x.gLen;
 	if (!dp)
 	{
-		MC_WARP_SYNC();
+		MC_TILE8_SYNC();
 		int mis = 0;
 		for (int k = lane; k < x.rLen; k += nl) if (a1[k] != a2[k]) mis++;
-		mis = mc_warp_sum(mis);
+		mis = mc_tile8_sum(mis);
 		dp = mis > 1 && mis >= (int)(x.rLen * 0.2);
 	}
 	if (dp && lane == 0)

@@ -21,12 +21,14 @@ struct ProfArgs {
 };
 
 // one thread per read: which update applies, clip / break-point bookkeeping, gate key
-MC_HD void profkey_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
+// the read's gate key (start << 28 | read), or ~0 when it has none
+MC_HD uint64_t profkey_of(int64_t r, const PipeArgs& a, const ProfArgs& q)
 {
+	const uint64_t none = ~(uint64_t)0;
 	q.accept[r] = 0;
 	const ReadSum sum = a.rsum[r];
-	if (sum.score == 0) return;
-	if (sum.n_live != 1) { q.accept[r] = 2; return; }
+	if (sum.score == 0) return none;
+	if (sum.n_live != 1) { q.accept[r] = 2; return none; }
 	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
 	const int64_t co = pa_cand_off(a, r);
 	const int nc = a.ncand[r];
@@ -41,7 +43,7 @@ MC_HD void profkey_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 			int64_t k = (int64_t)mc_atomic_add(q.bp_bump, (mc_u64)1);
 			if (k < q.bp_cap) q.bp_pos[k] = first.gPos < a.ix.G ? first.gPos : a.ix.twoG - 1 - first.gPos; else mc_atomic_or(&a.st->overflow, (mc_u64)1 << 48);
 		}
-		if (first.rPos > a.pr.max_clip) return;
+		if (first.rPos > a.pr.max_clip) return none;
 	}
 	if (last.rLen == 0 && last.gLen == 0)
 	{
@@ -50,12 +52,18 @@ MC_HD void profkey_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 			int64_t k = (int64_t)mc_atomic_add(q.bp_bump, (mc_u64)1);
 			if (k < q.bp_cap) q.bp_pos[k] = last.gPos < a.ix.G ? last.gPos : a.ix.twoG - 1 - last.gPos; else mc_atomic_or(&a.st->overflow, (mc_u64)1 << 48);
 		}
-		if (rlen - last.rPos > a.pr.max_clip) return;
+		if (rlen - last.rPos > a.pr.max_clip) return none;
 	}
 	const int64_t start = a.corient[co + ci] ? first.gPos : a.ix.twoG - (first.gPos + first.gLen);
-	if (start < 0 || start >= a.ix.G) return; // the reference would index outside MappingRecordArr
-	const int64_t k = mc_bump_alloc(q.key_bump, 1u);
-	q.keys[k] = ((uint64_t)start << MC_KEY_SHIFT) | (uint64_t)r;
+	if (start < 0 || start >= a.ix.G) return none; // the reference would index outside MappingRecordArr
+	return ((uint64_t)start << MC_KEY_SHIFT) | (uint64_t)r;
+}
+MC_HD void profkey_body(int64_t r, bool live, const PipeArgs& a, const ProfArgs& q)
+{
+	const uint64_t key = live ? profkey_of(r, a, q) : ~(uint64_t)0;
+	const bool has = key != ~(uint64_t)0;
+	const int64_t k = mc_block_bump(q.key_bump, has ? 1u : 0u);
+	if (has) q.keys[k] = key;
 }
 
 // keys sorted ascending: entry i passes iff fewer than `remaining` earlier entries share its start
@@ -128,14 +136,13 @@ MC_HD void indel_emit(const PipeArgs& a, const ProfArgs& q, int kind, int64_t po
 
 // one thread per read.  An accepted read costs two atomics for its strand coverage, two per exact-match seed and one
 // per base of its gapped / mismatching pieces.
-MC_HD void scatter_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
+MC_HD void scatter_body(int64_t r, bool live, const PipeArgs& a, const ProfArgs& q)
 {
-	const int mode = q.accept[r];
-	if (mode == 0) return;
-	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
-	const uint8_t* rs = a.seq + a.roff[r];
-	const int64_t co = pa_cand_off(a, r);
-	const int nc = a.ncand[r];
+	const int mode = live ? q.accept[r] : 0;
+	const int rlen = mode ? (int)(a.roff[r + 1] - a.roff[r]) : 0;
+	const uint8_t* rs = mode ? a.seq + a.roff[r] : nullptr;
+	const int64_t co = mode ? pa_cand_off(a, r) : 0;
+	const int nc = mode ? a.ncand[r] : 0;
 	if (mode == 2)
 	{
 		for (int ci = 0; ci < nc; ci++)
@@ -149,11 +156,19 @@ MC_HD void scatter_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 			prof_range(a, a.prof.mdiff, 1, 0, g0, g1);
 			if (g1 > g0) mc_stat_add(&a.st->profile_columns, (uint32_t)(g1 - g0));
 		}
-		return;
 	}
-	int ci = 0; while (ci < nc && a.cscore[co + ci] == 0) ci++;
-	const mc_frag_out* f = a.frags + a.cfrag[co + ci];
-	const int nf = a.cnfrag[co + ci];
+	int ci = 0;
+	const mc_frag_out* f = nullptr; int nf = 0, np = 0;
+	if (mode == 1)
+	{
+		while (ci < nc && a.cscore[co + ci] == 0) ci++;
+		f = a.frags + a.cfrag[co + ci]; nf = a.cnfrag[co + ci];
+		for (int k = 0; k < nf; k++) if (!f[k].bSimple && f[k].gLen != 0 && f[k].rLen != 0) np++;
+	}
+	// pieces with aligned columns are left to profpiece_body (a tile per piece): their queue slots come from one block-wide
+	// cursor bump, in which every thread of the block takes part
+	int64_t pt = mc_block_bump(a.ptask_bump, (uint32_t)np);
+	if (mode != 1) return;
 	const bool fwd = a.corient[co + ci] != 0;
 	const bool first_mate = a.pr.paired ? (((a.first_read + r) & 1) == 0) : true;
 	const int64_t start = fwd ? f[0].gPos : a.ix.twoG - (f[0].gPos + f[0].gLen);
@@ -190,8 +205,7 @@ MC_HD void scatter_body(int64_t r, const PipeArgs& a, const ProfArgs& q)
 		// note: an emptied clip piece (rLen == gLen == 0) also lands here and registers an empty insertion string, as the reference does (:121)
 		if (x.gLen == 0) { indel_emit(a, q, 0, (fwd ? x.gPos : a.ix.twoG - x.gPos) - 1, a1, x.aln_len); continue; }
 		if (x.rLen == 0) { indel_emit(a, q, 1, (fwd ? x.gPos : a.ix.twoG - x.gPos - x.gLen) - 1, a2, x.aln_len); continue; }
-		// pieces with aligned columns are left to profpiece_body (a warp per piece): queue the fragment
-		a.ptask[mc_bump_alloc(a.ptask_bump, 1u)] = a.cfrag[co + ci] + k;
+		a.ptask[pt++] = a.cfrag[co + ci] + k;
 	}
 	mc_stat_add(&a.st->profile_columns, (uint32_t)(2 * rlen));
 	mc_stat_add(&a.st->profile_atomics, (uint32_t)(natom));
@@ -265,6 +279,16 @@ MC_HD void profpack_body(int64_t b, const DevIndex& ix, const DevProfile& p, int
 		out[2 * i] = c[0] | c[1] << 12 | c[2] << 24 | c[3] << 36 | M << 48 | (R & 15) << 60;
 		out[2 * i + 1] = ((uint64_t)t[0] & 0xFFFF) | ((uint64_t)t[1] & 0xFFFF) << 16 | ((uint64_t)t[2] & 0xFFFF) << 32 | ((uint64_t)t[3] & 0xFFFF) << 48;
 	}
+}
+
+// CheckMappingCoverage / ReportDuplicationRate (reference src/ReadMapping.cpp:648-687) over packed records: columns with
+// A+C+G+T > 0 and their sum, columns with readCount > 0 and their sum.  acc[4] = {aligned, coverage, sites, reads}
+MC_HD void profstat_body(int64_t i, const uint64_t* recs, mc_u64* acc)
+{
+	const uint64_t w = recs[2 * i];
+	const uint32_t cov = (uint32_t)((w & 4095) + ((w >> 12) & 4095) + ((w >> 24) & 4095) + ((w >> 36) & 4095)), rc = (uint32_t)(w >> 60);
+	mc_stat_add(acc + 0, cov ? 1u : 0u); mc_stat_add(acc + 1, cov);
+	mc_stat_add(acc + 2, rc ? 1u : 0u); mc_stat_add(acc + 3, rc);
 }
 
 #endif

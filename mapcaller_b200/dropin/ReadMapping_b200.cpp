@@ -77,14 +77,6 @@ void rebuild(ReadItem_t& rd, const mc_batch_out& out, int64_t r)
 	}
 }
 
-void* coverage_worker(void* arg)
-{
-	int tid = *(int*)arg; int64_t bases = 0, cov = 0;
-	for (int64_t g = tid; g < GenomeSize; g += iThreadNum) { int c = GetProfileColumnSize(MappingRecordArr[g]); if (c > 0) { bases++; cov += c; } }
-	pthread_mutex_lock(&ProfileLock); iAlignedBase += bases; iTotalCoverage += cov; pthread_mutex_unlock(&ProfileLock);
-	return (void*)1;
-}
-
 } // namespace
 
 void Mapping()
@@ -158,6 +150,7 @@ void Mapping()
 		if (lib.gz) { if (lib.g1) gzclose(lib.g1); if (lib.g2) gzclose(lib.g2); } else { if (lib.f1) fclose(lib.f1); if (lib.f2) fclose(lib.f2); }
 	}
 
+	mc_profile_stats pstat; memset(&pstat, 0, sizeof(pstat));
 	if (ctx != NULL)
 	{
 		mc_totals t; mc_get_totals(ctx, &t);
@@ -167,6 +160,9 @@ void Mapping()
 		{
 			// device profile -> the structures VariantCalling() reads
 			if (mc_profile_read(ctx, 0, GenomeSize, MappingRecordArr)) die("mc_profile_read");
+			// CheckMappingCoverage / ReportDuplicationRate (src/ReadMapping.cpp:648-687) as device reductions
+			if (mc_profile_summary(ctx, &pstat)) die("mc_profile_summary");
+			iAlignedBase = pstat.aligned_bases; iTotalCoverage = pstat.coverage_sum;
 			const mc_indel_rec* ir; int64_t ni; const uint8_t* arena;
 			if (mc_profile_indels(ctx, &ir, &ni, &arena)) die("mc_profile_indels");
 			for (int64_t i = 0; i < ni; i++) (ir[i].kind == 0 ? InsertSeqMap : DeleteSeqMap)[ir[i].pos][string((const char*)arena + ir[i].seq_off, ir[i].len)] = (uint16_t)ir[i].count;
@@ -207,14 +203,9 @@ void Mapping()
 	if (bSAMoutput) fclose(sam_out);
 	if (bVCFoutput)
 	{
-		vector<pthread_t> th(iThreadNum); vector<int> ids(iThreadNum);
-		for (int i = 0; i < iThreadNum; i++) { ids[i] = i; pthread_create(&th[i], NULL, coverage_worker, &ids[i]); }
-		for (int i = 0; i < iThreadNum; i++) pthread_join(th[i], NULL);
 		avgCov = (int)(1.0 * iTotalCoverage / iAlignedBase + .5);
 		fprintf(log, "\tEstimated AvgCoverage = %d\n", avgCov); fprintf(stderr, "\tEstimated AvgCoverage = %d\n", avgCov);
-		int64_t sites = 0, total = 0;
-		for (int64_t g = 0; g < GenomeSize; g++) if (MappingRecordArr[g].readCount > 0) { sites++; total += MappingRecordArr[g].readCount; }
-		total -= sites;
+		const int64_t sites = pstat.dup_sites, total = pstat.dup_reads - pstat.dup_sites;
 		fprintf(log, "\tDuplication rate=%4.2f%%\n", 100 * (1.0 * total / sites)); fprintf(stderr, "\tDuplication rate=%4.2f%%\n", 100 * (1.0 * total / sites));
 	}
 	if (iTotalReadNum > 0 && iTotalPairedNum > 0)

@@ -112,6 +112,7 @@ def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool =
         out["inv"] = sorted(ctx.sites(0), key=lambda x: x[0])
         out["tnl"] = sorted(ctx.sites(1), key=lambda x: x[0])
         out["stats"] = ctx.stats()
+        out["summary"] = ctx.profile_summary()
     return out
 
 
@@ -146,6 +147,10 @@ def assert_same(mine, ref, want_reads: bool = True, paired: bool = True) -> None
     assert mine["bp"] == ref["bp"], "BreakPointMap differs"
     assert sorted(mine["inv"]) == sorted(ref["inv"]), "InversionSiteVec differs"
     assert sorted(mine["tnl"]) == sorted(ref["tnl"]), "TranslocationSiteVec differs"
+    if "summary" in mine:   # CheckMappingCoverage / ReportDuplicationRate over the checker's profile
+        p = ref["profile"].astype(np.int64); cov = p[:, :4].sum(axis=1)
+        want = dict(aligned_bases=int((cov > 0).sum()), coverage_sum=int(cov.sum()), dup_sites=int((p[:, 5] > 0).sum()), dup_reads=int(p[:, 5].sum()))
+        assert mine["summary"] == want, "coverage / duplication summary differs: %r vs %r" % (mine["summary"], want)
 
 
 def smoke_case() -> None:
