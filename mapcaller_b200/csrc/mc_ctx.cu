@@ -472,6 +472,10 @@ static int ordered_layout(mc_ctx* c, int64_t n_chunks, Ordered& o)
 static int ordered_chunks(mc_ctx* c, const Ordered& o, std::vector<mc_chunk_out>& hc, std::vector<int32_t>& lo, std::vector<int32_t>& hi, mc_u64* any_overflow)
 {
 	cudaStream_t s = c->stream;
+	const bool dbg = getenv("MC_DEBUG") != nullptr;
+	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t0 = 0, t1 = 0, t2 = 0;
+	if (dbg) { t0 = now(); t1 = t0; }
 	const size_t cb = (size_t)o.mxc * sizeof(mc_chunk_out), ib = (size_t)o.mxc * 4, per = cb + 2 * ib + 8;
 	if (c->d_comm_buf.reserve(per * o.n + 64) || c->h_comm_buf.reserve(per * o.n + 64)) return -1;
 	uint8_t* d = c->d_comm_buf.as<uint8_t>();
@@ -483,7 +487,10 @@ static int ordered_chunks(mc_ctx* c, const Ordered& o, std::vector<mc_chunk_out>
 	bad |= nccl_fail(ncclAllGather(&c->d_stats.as<DevStats>()->overflow, d + (cb + 2 * ib) * o.n, 8, ncclUint8, c->comm, s), "ncclAllGather(overflow)");
 	bad |= nccl_fail(nccl_api()->GroupEnd(), "ncclGroupEnd");
 	if (bad) return -1;
+	if (dbg) t2 = now();
+	const double t3 = t2;
 	if (dev_d2h(c->h_comm_buf.p, d, per * o.n, s) || dev_sync(s)) return -1;
+	if (dbg) fprintf(stderr, "[mc] rank %d exchange: nccl enqueue %.3f ms, wait + d2h %.3f ms\n", o.me, t2 - t1, now() - t3);
 	const uint8_t* h = c->h_comm_buf.as<uint8_t>();
 	*any_overflow = 0;
 	for (int r = 0; r < o.n; r++)
@@ -633,9 +640,10 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		std::vector<mc_chunk_out> g_hc; std::vector<int32_t> g_lo, g_hi;
 		if (od.on) { g_hc.resize(NG); g_lo.resize(NG); g_hi.resize(NG); }
 		// avgDist stays at its initial value until more than 1000 pairs have been seen (src/ReadMapping.cpp:539) and then
-		// jumps: while warming up only the chunks that can still use the initial value are speculated on
+		// jumps: while warming up only the chunks that can still use the initial value are speculated on - plus a few hundred
+		// more, whose sums (nearly independent of the value) let the walk predict where the trajectory settles
 		if (paired && c->tot.total_paired <= 1000)
-			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2; k < NG; k++) active[k] = 0;
+			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2 + 256; k < NG; k++) active[k] = 0;
 		Bumps hb; memset(&hb, 0, sizeof(hb)); hb.pair = (mc_u64)n_locs;
 		bad |= dev_h2d(db, &hb, sizeof(hb), s) || dev_zero(c->d_pair_flag.p, (n_pairs + 1) * 4, s);
 		mc_totals run = c->tot;
@@ -647,6 +655,8 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		ev_record(&c->ev[EV_PAIR0], s);
 		while (first_open < NG)
 		{
+			const bool dbg_att = getenv("MC_DEBUG") != nullptr;
+			const auto att_t0 = std::chrono::steady_clock::now();
 			// one attempt: no host round trip inside it, the task lists are consumed from their device-side cursors
 			a.rtask_begin = (int64_t)hbp->rtask; a.task_begin = (int64_t)hbp->task; a.ptask_begin = (int64_t)hbp->ptask;
 			if (a.rtask_begin + n_pairs > rtask_cap) { mc_set_error("mc_map_batch: too many speculation replays in one batch"); return MC_ERR_OVERFLOW; }
@@ -676,6 +686,12 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			}
 #endif
 			if (hst->overflow) { overflow = true; break; }
+			if (dbg_att)
+			{
+				int64_t na = 0, nl = 0; for (int64_t k = 0; k < NG; k++) { na += active[k]; if (k >= g0 && k < g0 + n_chunks) nl += active[k]; }
+				fprintf(stderr, "[mc] rank %d attempt: %lld active chunks (%lld mine) of %lld, first open %lld, %.3f ms\n", od.on ? od.me : 0, (long long)na, (long long)nl, (long long)NG, (long long)first_open,
+				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - att_t0).count());
+			}
 			for (int64_t k = 0; k < NG; k++) if (active[k]) computed[k] = ever[k] = 1;
 			// walk the chunks in file order (reference src/ReadMapping.cpp:537-539)
 			std::fill(active.begin(), active.end(), 0);
