@@ -224,8 +224,14 @@ typedef struct {
 } mc_stats;
 int mc_get_stats(const mc_ctx *ctx, mc_stats *out);   /* accumulated since create / last reset */
 int mc_reset_stats(mc_ctx *ctx);
-/* Device-resident replay used by bench.py: maps a batch whose reads are already in HBM
- * (uploaded by mc_stage_batch) and returns nothing to the host but the chunk statistics. */
+/* Double-buffered feed: a batch is copied into one of four device slots and mapped from there, any number of times.
+ * mc_stage_batch_async() only queues the copy (and the reversal of mate 2) on the context's copy stream and returns; the
+ * caller's buffers must stay untouched until the next mc_map_staged() of that slot has returned (page-locked buffers from
+ * mc_host_alloc are copied by DMA, pageable ones are bounced synchronously).  A host that maps batch i from slot i & 1
+ * after staging batch i + 1 into the other slot hides the PCIe transfer behind the mapping of the previous batch; this is
+ * the loop bench.py times as `e2e`.  mc_stage_batch() is the same followed by a wait.  Do not stage into a slot while it
+ * is being mapped. */
+int mc_stage_batch_async(mc_ctx *ctx, const mc_batch_in *in, int32_t slot);
 int mc_stage_batch(mc_ctx *ctx, const mc_batch_in *in, int32_t slot);
 int mc_map_staged(mc_ctx *ctx, int32_t slot, mc_batch_out *out);
 

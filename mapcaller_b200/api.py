@@ -91,6 +91,7 @@ def lib():
         L.mc_ctx_destroy.argtypes = [C.c_void_p]
         L.mc_map_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut)]
         L.mc_stage_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.c_int32]
+        L.mc_stage_batch_async.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.c_int32]
         L.mc_map_staged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BatchOut)]
         L.mc_get_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
         L.mc_set_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
@@ -234,6 +235,13 @@ class Context:
     def stage_batch(self, seq: np.ndarray, off: np.ndarray, slot: int = 0):
         b, keep = self._batch(seq, off)
         _check(lib().mc_stage_batch(self._h, C.byref(b), slot), "mc_stage_batch")
+
+    def stage_batch_async(self, seq: np.ndarray, off: np.ndarray, slot: int = 0):
+        """Queues the copy of a batch into device slot `slot` and returns; the arrays must stay untouched (and alive: they are
+        kept referenced here) until the next map_staged(slot) has returned."""
+        b, keep = self._batch(seq, off)
+        self._staging = getattr(self, "_staging", {}); self._staging[slot] = keep
+        _check(lib().mc_stage_batch_async(self._h, C.byref(b), slot), "mc_stage_batch_async")
 
     def map_staged(self, slot: int = 0, copy: bool = False):
         out = BatchOut()

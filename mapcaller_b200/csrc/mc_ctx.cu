@@ -159,8 +159,9 @@ enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_P
 struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask, rwin; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
-struct Staged { DBuf seq, roff, seed_off, cap, scan; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false;
-	int n_pieces = 0; int64_t piece_end[8]; };   // read ranges [piece_end[p-1], piece_end[p]) whose bases arrive one after the other (events ev_piece[])
+struct Staged { DBuf seq, roff, seed_off, cap, scan, flag; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false;
+	int n_pieces = 0; int64_t piece_end[8];
+	bool pending = false; };   // staged asynchronously: the consumer has to wait for ev_slot[] first   // read ranges [piece_end[p-1], piece_end[p]) whose bases arrive one after the other (events ev_piece[])
 
 struct mc_ctx {
 	mc_params prm;
@@ -184,7 +185,7 @@ struct mc_ctx {
 	HBuf h_bounce[2];
 	mc_stream_t cstream;
 #ifndef MC_HOSTEMU
-	cudaEvent_t ev_bounce[2], ev_piece[8];
+	cudaEvent_t ev_bounce[2], ev_piece[8], ev_slot[4];
 #endif
 	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
@@ -238,6 +239,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	c->h_bounce[0].release(); c->h_bounce[1].release();
 #ifndef MC_HOSTEMU
 	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]); for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev_piece[i]);
+	for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev_slot[i]);
 	if (c->cstream) cudaStreamDestroy(c->cstream);
 	if (c->stream) cudaStreamDestroy(c->stream);
 #endif
@@ -269,6 +271,7 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 #ifndef MC_HOSTEMU
 	cudaEventCreateWithFlags(&c->ev_bounce[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bounce[1], cudaEventDisableTiming);
 	for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&c->ev_piece[i], cudaEventDisableTiming);
+	for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&c->ev_slot[i], cudaEventDisableTiming);
 #endif
 	const int64_t G = v.genome_size; c->G = G;
 	std::vector<int64_t> ends; std::vector<int32_t> ids;
@@ -381,11 +384,11 @@ static int upload(mc_ctx* c, void* dst, const void* src, size_t bytes, mc_stream
 #endif
 }
 
-struct CapArgs { const int64_t* roff; uint32_t* cap; DevStats* st; };
+struct CapArgs { const int64_t* roff; uint32_t* cap; mc_u64* flag; };   // flag: the slot's own copy of DevStats::overflow (staging may run beside a batch)
 MC_HD void seedcap_body(int64_t r, const CapArgs& q)
 {
 	const int64_t len = q.roff[r + 1] - q.roff[r];
-	if (len < 0 || len > MC_MAX_RLEN) { mc_atomic_or(&q.st->overflow, (mc_u64)1 << 56); q.cap[r] = 1; return; }
+	if (len < 0 || len > MC_MAX_RLEN) { mc_atomic_or(q.flag, (mc_u64)1 << 56); q.cap[r] = 1; return; }
 	q.cap[r] = (uint32_t)(len / 17 + 1);   // a recorded seed is >= 16 bases and the next search starts one base later
 }
 #ifdef MC_HOSTEMU
@@ -413,9 +416,9 @@ static int stage_reads(mc_ctx* c, const mc_batch_in* in, Staged& st, mc_stream_t
 	if (c->prm.want_alignments) st.h_roff.assign(in->seq_off, in->seq_off + n + 1);
 	if (n == 0) { st.valid = true; return MC_OK; }
 	// scratch of the staging pass is private to the Staged slot
-	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 2) * 8) || st.cap.reserve(n * 4) || st.scan.reserve(device_scan_scratch_bytes(n))) return MC_ERR_CUDA;
-	if (upload(c, st.roff.p, in->seq_off, (n + 1) * 8, stream)) return MC_ERR_CUDA;
-	CapArgs q; q.roff = st.roff.as<int64_t>(); q.cap = st.cap.as<uint32_t>(); q.st = c->d_stats.as<DevStats>();
+	if (st.seq.reserve(bytes + 16) || st.roff.reserve((n + 1) * 8) || st.seed_off.reserve((n + 2) * 8) || st.cap.reserve(n * 4) || st.scan.reserve(device_scan_scratch_bytes(n)) || st.flag.reserve(16)) return MC_ERR_CUDA;
+	if (dev_zero(st.flag.p, 16, stream) || upload(c, st.roff.p, in->seq_off, (n + 1) * 8, stream)) return MC_ERR_CUDA;
+	CapArgs q; q.roff = st.roff.as<int64_t>(); q.cap = st.cap.as<uint32_t>(); q.flag = st.flag.as<mc_u64>();
 	launch_seedcap(q, n, stream);
 	device_scan_u32(q.cap, st.seed_off.as<int64_t>(), n, st.scan.as<int64_t>(), stream);
 #ifndef MC_HOSTEMU
@@ -578,7 +581,8 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 
 	// ---- seeding ----
 	ev_record(&c->ev[EV_H2D], s);
-	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats) - 2 * sizeof(mc_u64), s);   // keeps the staging flags (overflow, odd_merge)
+	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats) - 2 * sizeof(mc_u64), s);
+	bad |= dev_d2d(&c->d_stats.as<DevStats>()->overflow, st.flag.p, 8, s);   // what staging found (a read longer than MC_MAX_RLEN)
 	ev_record(&c->ev[EV_SEED0], s);
 	if (st.n_pieces > 1)
 	{
@@ -952,21 +956,45 @@ int mc_map_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
 	return run_batch(c, c->cur, out, true);
 }
 
-int mc_stage_batch(mc_ctx* c, const mc_batch_in* in, int32_t slot)
+int mc_stage_batch_async(mc_ctx* c, const mc_batch_in* in, int32_t slot)
 {
 	if (!c || !in || slot < 0 || slot >= 4) { mc_set_error("mc_stage_batch: bad argument"); return MC_ERR_ARG; }
-	int rc = stage_reads(c, in, c->slots[slot], c->stream, 1);
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	Staged& st = c->slots[slot];
+	int rc = stage_reads(c, in, st, c->cstream, 1);
 	if (rc) return rc;
 	// reverse-complement mate 2 once; the staged copy is then immutable
 	PipeArgs a; memset(&a, 0, sizeof(a));
-	a.pr.paired = c->prm.paired; a.seq = c->slots[slot].seq.as<uint8_t>() - c->slots[slot].base; a.roff = c->slots[slot].roff.as<int64_t>(); a.n_reads = in->n_reads;
-	launch_prep(a, 0, in->n_reads, c->stream);
-	return dev_sync(c->stream) ? MC_ERR_CUDA : MC_OK;
+	a.pr.paired = c->prm.paired; a.seq = st.seq.as<uint8_t>() - st.base; a.roff = st.roff.as<int64_t>(); a.n_reads = in->n_reads;
+	launch_prep(a, 0, in->n_reads, c->cstream);
+#ifndef MC_HOSTEMU
+	if (cuda_fail(cudaEventRecord(c->ev_slot[slot], c->cstream), "cudaEventRecord")) return MC_ERR_CUDA;
+	st.pending = true;
+#endif
+	return MC_OK;
+}
+
+int mc_stage_batch(mc_ctx* c, const mc_batch_in* in, int32_t slot)
+{
+	int rc = mc_stage_batch_async(c, in, slot);
+	if (rc) return rc;
+	c->slots[slot].pending = false;
+	return dev_sync(c->cstream) ? MC_ERR_CUDA : MC_OK;
 }
 
 int mc_map_staged(mc_ctx* c, int32_t slot, mc_batch_out* out)
 {
 	if (!c || !out || slot < 0 || slot >= 4 || !c->slots[slot].valid) { mc_set_error("mc_map_staged: slot not staged"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+	if (c->slots[slot].pending)
+	{
+		if (cuda_fail(cudaStreamWaitEvent(c->stream, c->ev_slot[slot], 0), "cudaStreamWaitEvent")) return MC_ERR_CUDA;
+		c->slots[slot].pending = false;
+	}
+#endif
 	ev_record(&c->ev[EV_START], c->stream);
 	return run_batch(c, c->slots[slot], out, false);
 }

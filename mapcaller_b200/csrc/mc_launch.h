@@ -204,16 +204,18 @@ MC_LAUNCH2B(scatter)
 // persistent warps over the pieces queued by mc_scatter_kernel
 __global__ void __launch_bounds__(MC_BLOCK) mc_profpiece_kernel(const PipeArgs a, const ProfArgs q)
 {
-	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	// 8-lane tiles, one piece each (no communication between the lanes of a tile)
+	const int64_t tile = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3, n_tiles = ((int64_t)gridDim.x * blockDim.x) >> 3;
 	const int64_t n = (int64_t)*a.ptask_bump;
 	int natom = 0;
-	for (int64_t t = warp; t < n; t += n_warps) { natom += profpiece_body(t, threadIdx.x & 31, 32, a, q); __syncwarp(); }
+	for (int64_t t = tile; t < n; t += n_tiles) natom += profpiece_body(t, threadIdx.x & 7, 8, a, q);
+	__syncwarp();
 	mc_stat_add(&a.st->profile_atomics, (uint32_t)natom);
 }
 static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
-	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
+	int64_t blocks = (max_tasks * 8 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
 	mc_profpiece_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a, q); g_launches++;
 }
 #endif

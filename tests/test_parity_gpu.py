@@ -86,6 +86,36 @@ def test_index_layouts_agree(built):
     pu.assert_same(wide, pu.oracle_results(case, ix))
 
 
+def test_double_buffered_feed_equals_one_call(built):
+    """mc_stage_batch_async(batch i+1) while mc_map_staged(batch i) runs: same records, totals and profile as mc_map_batch."""
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=17, n_pairs=9000, genome_len=100000, n_rate=0.001)
+    ix = pu.build_index(case)
+    whole = pu.cuda_results(case, ix)
+    seq, off = case["seq"], case["off"]
+    n = len(off) - 1
+    cuts = [0, 4000, 9000, 13000, n]
+    parts = []
+    for b, e in zip(cuts, cuts[1:]):
+        ps = api.pinned_array((int(off[e] - off[b]),), np.uint8); ps[:] = seq[off[b]:off[e]]
+        po = api.pinned_array((e - b + 1,), np.int64); po[:] = off[b:e + 1] - off[b]
+        parts.append((ps, po))
+    got = dict(reads=[], est=[])
+    with api.Context(ix, want_alignments=1, update_profile=1, **case["params"]) as ctx:
+        ctx.stage_batch_async(*parts[0], 0)
+        for i in range(len(parts)):
+            if i + 1 < len(parts):
+                ctx.stage_batch_async(*parts[i + 1], (i + 1) & 1)
+            res = ctx.map_staged(i & 1, copy=True)
+            got["reads"] += api.unpack_reads(res); got["est"] += [int(x) for x in res["chunks"]["est_distance"]]
+        t = ctx.totals()
+        got["counters"] = dict(reads=t["total_reads"], mapped=t["total_mapped"], paired=t["total_paired"], dist_sum=t["total_distance"],
+                               len_sum=t["read_length_sum"], avgDist=t["avg_dist"])
+        got["profile"] = ctx.profile_columns(); got["ins"], got["dele"] = ctx.indels(); got["bp"] = ctx.breakpoints()
+        got["inv"] = sorted(ctx.sites(0), key=lambda x: x[0]); got["tnl"] = sorted(ctx.sites(1), key=lambda x: x[0])
+    pu.assert_same(got, whole)
+
+
 def test_pipelined_large_batch_equals_resident_path(built):
     """A profile-only batch of >= 400 k reads is cut into pieces whose upload overlaps the mapping of the previous piece
     (copy stream); the result must equal the single-piece path (mc_stage_batch + mc_map_staged) and the chunk-wise path."""
