@@ -115,10 +115,21 @@ static void launch_prep(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t
 	if (!a.pr.paired || p1 <= p0) return;
 	mc_prep_kernel<<<(unsigned)(((p1 - p0) * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, p0, p1); g_launches++;
 }
-__global__ void __launch_bounds__(MC_BLOCK) mc_seed_kernel(const PipeArgs a, int64_t first, int64_t n)
+template <int MINB> __global__ void __launch_bounds__(MC_BLOCK, MINB) mc_seed_kernel(const PipeArgs a, int64_t first, int64_t n)
 { const int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) seed_body(i, a); }
 static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t s)
-{ if (n > first) { mc_seed_kernel<<<(unsigned)((n - first + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, first, n); g_launches++; } }
+{
+	if (n <= first) return;
+	// an index that fits L2 leaves the kernel latency / issue bound: five resident blocks (48 registers, a few spills) beat four
+	// (1.41 vs 1.56 ms on the bench); from HBM the kernel is bandwidth bound and the spills only add traffic
+	static const int forced = getenv("MC_SEED_MINB") ? atoi(getenv("MC_SEED_MINB")) : 0;
+	const int variant = forced ? forced : (a.ix.cbwt && a.ix.seq_len < (200ll << 20) ? 5 : 4);
+	const unsigned g = (unsigned)((n - first + MC_BLOCK - 1) / MC_BLOCK);
+	if (variant == 6) mc_seed_kernel<6><<<g, MC_BLOCK, 0, s>>>(a, first, n);
+	else if (variant == 5) mc_seed_kernel<5><<<g, MC_BLOCK, 0, s>>>(a, first, n);
+	else mc_seed_kernel<4><<<g, MC_BLOCK, 0, s>>>(a, first, n);
+	g_launches++;
+}
 // rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent thread blocks
 // (block b takes windows b, b + n_blocks, ...), commit per pair.  A window search is a chain of short loops over small
 // tables (word list, diagonal histogram, filter, staged window): the tables live in shared memory (24 KB per block, so 8
