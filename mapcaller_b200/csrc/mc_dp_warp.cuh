@@ -144,15 +144,34 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_dp_kernel(const PipeArgs a)
 	for (int64_t t = a.task_begin + warp; t < end; t += n_warps)
 	{
 		const DpTask tk = a.tasks[t];
+		if (dp_is_small(tk.m, tk.n)) continue;            // mc_dp_small_kernel's
 		if (a.pr.alg_ksw2) dpw_task<true>(a, tk, lane, cells, fast, MC_DP_SMEM); else dpw_task<false>(a, tk, lane, cells, fast, MC_DP_SMEM);
 		tasks++;
 		__syncwarp();
 	}
 	if (lane == 0 && tasks) { atomicAdd(&a.st->dp_cells, (mc_u64)cells); atomicAdd(&a.st->dp_tasks, (mc_u64)tasks); }
 }
+// small fills: persistent threads, thread i takes tasks task_begin + i, + n_threads, ... and skips the large ones
+#define MC_DP_SMALL_THREADS 128
+__global__ void __launch_bounds__(MC_DP_SMALL_THREADS) mc_dp_small_kernel(const PipeArgs a)
+{
+	extern __shared__ __align__(16) uint8_t dp_small_smem[];
+	uint8_t* ws = dp_small_smem + (size_t)threadIdx.x * MC_DP_SMALL_STRIDE;
+	const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, n_threads = (int64_t)gridDim.x * blockDim.x;
+	int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
+	uint32_t cells = 0, tasks = 0;
+	for (int64_t t = a.task_begin + tid; t < end; t += n_threads) dp_small_body(t, a, ws, &cells, &tasks);
+	__syncwarp();
+	mc_stat_add(&a.st->dp_cells, cells); mc_stat_add(&a.st->dp_tasks, tasks);
+}
 static void launch_dp(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
+	static bool configured = false;
+	const int smem = MC_DP_SMALL_THREADS * MC_DP_SMALL_STRIDE;
+	if (!configured) { cudaFuncSetAttribute(mc_dp_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+	int64_t sb = (max_tasks + MC_DP_SMALL_THREADS - 1) / MC_DP_SMALL_THREADS; if (sb > 148 * 2) sb = 148 * 2;
+	mc_dp_small_kernel<<<(unsigned)sb, MC_DP_SMALL_THREADS, smem, s>>>(a); g_launches++;
 	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;
 	mc_dp_kernel<<<(unsigned)blocks, MC_BLOCK, 0, s>>>(a); g_launches++;
 }

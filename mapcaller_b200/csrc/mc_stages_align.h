@@ -213,21 +213,12 @@ MC_HD void piece_body(int64_t t, int lane, int nl, const PipeArgs& a)
 // ------------------------------------------------------------------------------------------------
 #define MC_NEG_INF (-0x20000000)
 
-MC_HD void dp_body(int64_t t, const PipeArgs& a)
+// s1 / s2: where the gapped strings go (the piece's slots in the alignment arena); in1 / in2: where the raw strings are
+// read from - the same place (rewritten in place, back to front) or a private copy
+MC_HD int dp_core(bool ksw2, int m, int n, uint8_t* s1, uint8_t* s2, const uint8_t* in1, const uint8_t* in2, uint8_t* tb, int* row0, int* row1)
 {
-	{
-		int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
-		if (a.task_begin + t >= end) return;
-	}
-	const DpTask tk = a.tasks[a.task_begin + t];
-	mc_frag_out& x = a.frags[tk.frag];
-	const int m = tk.m, n = tk.n, cp = x.aln_cap;
-	uint8_t* s1 = a.aln + x.aln_off; uint8_t* s2 = s1 + cp;   // read piece (m), genome piece (n)
-	uint8_t* tb = a.dpws + tk.ws_off;
-	int* row0 = (int*)(tb + dp_tb_bytes(m, n));
-	int* row1 = row0 + ((m > n ? m : n) + 2);
 	int len = 0;
-	if (!a.pr.alg_ksw2)
+	if (!ksw2)
 	{
 		// s1 down the rows (i), s2 along the columns (j); row0 = s[i-1][*], row1 = t[i-1][*]
 		const int W = n + 1;
@@ -235,7 +226,7 @@ MC_HD void dp_body(int64_t t, const PipeArgs& a)
 		for (int j = 1; j <= n; j++) { row0[j] = -2 - j; row1[j] = -131072; tb[j] = 1; }   // s[0][j] == r[0][j]
 		for (int i = 1; i <= m; i++)
 		{
-			const int c1 = mc_nt4(s1[i - 1]);
+			const int c1 = mc_nt4(in1[i - 1]);
 			int diag = row0[0];               // s[i-1][0]
 			int sl = -2 - i;                  // s[i][0] == t[i][0]
 			int rl = -131072;                 // r[i][0]
@@ -247,7 +238,7 @@ MC_HD void dp_body(int64_t t, const PipeArgs& a)
 				const int rr = (rl - 1 > sl - 3) ? rl - 1 : sl - 3;
 				const int up_t = row1[j], up_s = row0[j];
 				const int tt = (up_t - 1 > up_s - 3) ? up_t - 1 : up_s - 3;
-				const int dd = diag + (c1 == mc_nt4(s2[j - 1]) ? 2 : -2);
+				const int dd = diag + (c1 == mc_nt4(in2[j - 1]) ? 2 : -2);
 				const int ss = mc_max3(dd, rr, tt);
 				row[j] = (uint8_t)((ss == rr ? 1 : 0) | (ss == tt ? 2 : 0));
 				diag = up_s; row0[j] = ss; row1[j] = tt; sl = ss; rl = rr;
@@ -260,9 +251,9 @@ MC_HD void dp_body(int64_t t, const PipeArgs& a)
 		{
 			const uint8_t d = tb[(int64_t)i * W + j];
 			k--;
-			if (d & 1) { s2[k] = s2[j - 1]; s1[k] = '-'; j--; }
-			else if (d & 2) { s1[k] = s1[i - 1]; s2[k] = '-'; i--; }
-			else { s1[k] = s1[i - 1]; s2[k] = s2[j - 1]; i--; j--; }
+			if (d & 1) { s2[k] = in2[j - 1]; s1[k] = '-'; j--; }
+			else if (d & 2) { s1[k] = in1[i - 1]; s2[k] = '-'; i--; }
+			else { s1[k] = in1[i - 1]; s2[k] = in2[j - 1]; i--; j--; }
 		}
 	}
 	else
@@ -272,14 +263,14 @@ MC_HD void dp_body(int64_t t, const PipeArgs& a)
 		for (int j = 0; j < m; j++) { row0[j] = -(2 + (j + 1)); row1[j] = MC_NEG_INF; }
 		for (int i = 0; i < n; i++)
 		{
-			const int ct = mc_nt4(s2[i]);
+			const int ct = mc_nt4(in2[i]);
 			int hdiag = i == 0 ? 0 : -(2 + i);       // H(i-1, -1)
 			int hleft = -(2 + (i + 1));              // H(i, -1)
 			int f = MC_NEG_INF;
 			uint8_t* row = tb + (int64_t)i * Wq;
 			for (int j = 0; j < m; j++)
 			{
-				const int cq = mc_nt4(s1[j]);
+				const int cq = mc_nt4(in1[j]);
 				const int sc = (ct == 4 || cq == 4) ? 0 : (ct == cq ? 1 : -1);
 				const int hup = row0[j];
 				int e = MC_NEG_INF;
@@ -305,20 +296,57 @@ MC_HD void dp_body(int64_t t, const PipeArgs& a)
 				if (state == 0) state = tmp & 7;
 				else if (!((tmp >> (state + 2)) & 1)) state = 0;
 				if (state == 0) state = tmp & 7;
-				if (state == 0) { if (pass) { k--; s1[k] = s1[j]; s2[k] = s2[i]; } i--; j--; }
-				else if (state == 1 || state == 3) { if (pass) { k--; s2[k] = s2[i]; s1[k] = '-'; } i--; }
-				else { if (pass) { k--; s1[k] = s1[j]; s2[k] = '-'; } j--; }
+				if (state == 0) { if (pass) { k--; s1[k] = in1[j]; s2[k] = in2[i]; } i--; j--; }
+				else if (state == 1 || state == 3) { if (pass) { k--; s2[k] = in2[i]; s1[k] = '-'; } i--; }
+				else { if (pass) { k--; s1[k] = in1[j]; s2[k] = '-'; } j--; }
 				cnt++;
 			}
-			while (i >= 0) { if (pass) { k--; s2[k] = s2[i]; s1[k] = '-'; } i--; cnt++; }
-			while (j >= 0) { if (pass) { k--; s1[k] = s1[j]; s2[k] = '-'; } j--; cnt++; }
+			while (i >= 0) { if (pass) { k--; s2[k] = in2[i]; s1[k] = '-'; } i--; cnt++; }
+			while (j >= 0) { if (pass) { k--; s1[k] = in1[j]; s2[k] = '-'; } j--; cnt++; }
 			if (!pass) len = cnt;
 		}
 	}
-	x.aln_len = len;
+	return len;
+}
+
+MC_HD void dp_body(int64_t t, const PipeArgs& a)
+{
+	{
+		int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
+		if (a.task_begin + t >= end) return;
+	}
+	const DpTask tk = a.tasks[a.task_begin + t];
+	mc_frag_out& x = a.frags[tk.frag];
+	const int m = tk.m, n = tk.n;
+	uint8_t* s1 = a.aln + x.aln_off; uint8_t* s2 = s1 + x.aln_cap;   // read piece (m), genome piece (n)
+	uint8_t* tb = a.dpws + tk.ws_off;
+	int* row0 = (int*)(tb + dp_tb_bytes(m, n));
+	x.aln_len = dp_core(a.pr.alg_ksw2 != 0, m, n, s1, s2, s1, s2, tb, row0, row0 + ((m > n ? m : n) + 2));
 	mc_atomic_add(&a.st->dp_cells, (mc_u64)((int64_t)m * n));
 	mc_atomic_add(&a.st->dp_tasks, (mc_u64)1);
 }
+
+// Small fills (the bulk: the median piece is 13 x 13) by ONE thread each, everything it touches in a private slice of shared
+// memory: the 31 idle steps that fill and drain the 32-lane wavefront of the warp form cost more than such a matrix itself.
+#define MC_DP_SMALL_CELLS 289          // (m + 1) * (n + 1) <= 17 * 17
+#define MC_DP_SMALL_MAXLEN 32          // and m, n <= 32 (a 1 x 143 strip is not "small")
+#define MC_DP_SMALL_STRIDE 636         // bytes per thread: 292 traceback + 2 x 32 raw strings + 2 x 34 ints = 628, rounded up to an odd word count
+MC_HOST_HD bool dp_is_small(int m, int n) { return (m + 1) * (n + 1) <= MC_DP_SMALL_CELLS && m <= MC_DP_SMALL_MAXLEN && n <= MC_DP_SMALL_MAXLEN; }
+MC_HD void dp_small_body(int64_t t, const PipeArgs& a, uint8_t* ws, uint32_t* cells, uint32_t* tasks)
+{
+	const DpTask tk = a.tasks[t];
+	const int m = tk.m, n = tk.n;
+	if (!dp_is_small(m, n)) return;
+	mc_frag_out& x = a.frags[tk.frag];
+	uint8_t* s1 = a.aln + x.aln_off; uint8_t* s2 = s1 + x.aln_cap;
+	uint8_t* tb = ws; uint8_t* in1 = ws + 292; uint8_t* in2 = in1 + 32; int* row0 = (int*)(in2 + 32); int* row1 = row0 + 34;
+	for (int i = 0; i < m; i++) in1[i] = s1[i];
+	for (int j = 0; j < n; j++) in2[j] = s2[j];
+	x.aln_len = dp_core(a.pr.alg_ksw2 != 0, m, n, s1, s2, in1, in2, tb, row0, row1);
+	*cells += (uint32_t)(m * n); *tasks += 1;
+}
+
+
 
 // ------------------------------------------------------------------------------------------------
 // alnfin: one thread per read, candidates in order (best / sub-score bookkeeping is sequential)

@@ -3,7 +3,8 @@ The CUDA path (index in HBM, compact layout, several batches) against the CPU re
 record for record: per-read candidates / fragments / alignment strings, EstiDistance per chunk, totals, the whole profile
 (tile by tile), indel maps, break points, SV sites.  Not part of the default test suite (takes a few minutes and ~20 GB of
 host memory); its log is committed under profiles/.
-usage: python tools/parity_big.py [genome_bp] [pairs] [read_len] [batches]"""
+usage: python tools/parity_big.py [genome_bp] [pairs] [read_len] [batches] [ksw2]
+(`ksw2` as fifth argument = configs[4] flavour: -alg ksw2, small indels 2000/Mb, large 500/Mb, 0.2 % indel errors per read base)"""
 import os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -16,10 +17,15 @@ G = int(sys.argv[1]) if len(sys.argv) > 1 else 248_956_422
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 300_000
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 150
 NB = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+KSW2 = len(sys.argv) > 5 and sys.argv[5] == "ksw2"
 t = time.time()
 g = sim.genome(G, 13, n_dup=2000, repeat_frac=0.15 if G > 50_000_000 else 0.0)
-mut, _ = sim.mutate(g, 14, snp_per_mb=1000, small_indel_per_mb=100, large_indel_per_mb=20, sv_per_mb=1)
-r1, r2 = sim.simulate_pairs(mut[3000:], P, L, seed=15, frag_mean=450, frag_sd=50, sub_rate=0.003)
+if KSW2:
+    mut, _ = sim.mutate(g, 14, snp_per_mb=1000, small_indel_per_mb=2000, large_indel_per_mb=500, sv_per_mb=1)
+    r1, r2 = sim.simulate_pairs(mut[3000:], P, L, seed=15, frag_mean=max(450, 2 * L), frag_sd=50, sub_rate=0.003, indel_rate=0.002)
+else:
+    mut, _ = sim.mutate(g, 14, snp_per_mb=1000, small_indel_per_mb=100, large_indel_per_mb=20, sv_per_mb=1)
+    r1, r2 = sim.simulate_pairs(mut[3000:], P, L, seed=15, frag_mean=450, frag_sd=50, sub_rate=0.003)
 seq, off = sim.interleave(r1, r2)
 del mut
 print("data %.1fs" % (time.time() - t), flush=True)
@@ -29,7 +35,7 @@ NC = max(1, (G + 249_999_999) // 250_000_000)
 lens = [G // NC] * NC; lens[-1] += G - sum(lens)
 t = time.time(); ix = api.Index.build(sim.encode(g), chrom_len=lens, chrom_name=["ctg%d" % (i + 1) for i in range(NC)])
 print("index build %.1fs (%d contigs)" % (time.time() - t, NC), flush=True)
-params = dict(paired=1, alg_ksw2=0)
+params = dict(paired=1, alg_ksw2=int(KSW2))
 n = len(off) - 1
 mine = dict(reads=[], est=[], replays=0)
 t = time.time()
