@@ -1,4 +1,5 @@
-// Warp-per-task gapped fill (CUDA only): the production form of dp_body.
+// Warp-per-task gapped fill (CUDA only) for everything that is not "small" (dp_is_small, mc_stages_align.h: those go one
+// thread per fill through dp_core in shared memory, mc_dp_small_kernel below).
 //
 // One warp fills one (read piece x genome piece) matrix as an anti-diagonal wavefront: lane l owns one column of a
 // 32-column strip, at step t it computes row t-l, the left / diagonal neighbours arrive by __shfl_up_sync from lane
@@ -8,8 +9,7 @@
 // reference does and rewrites the two strings in place.
 //   nw   : reference src/nw_alignment.cpp:18-83 in doubled integers; rows = read piece, columns = genome piece
 //   ksw2 : reference src/ksw2_alignment.cpp:70-272;                    rows = genome piece (target), columns = read piece (query)
-// The per-thread dp_body of mc_stages_align.h computes the same thing serially; it is what the developer harness
-// (MC_HOSTEMU) runs and both are checked against the oracle by tests/test_parity_gpu.py::test_gapped_fill_kernel_matches_oracle.
+// dp_core of mc_stages_align.h computes the same thing serially (small fills, and the developer harness); both are checked against the oracle by tests/test_parity_gpu.py::test_gapped_fill_kernel_matches_oracle.
 #ifndef MC_DP_WARP_CUH
 #define MC_DP_WARP_CUH
 

@@ -1,4 +1,5 @@
-// Per-work-item bodies of the mapping pipeline (one function = one kernel, see mc_launch.h).
+// Per-work-item bodies of the mapping pipeline (one function = one kernel, see mc_launch.h; a work item is a read, a pair,
+// a piece, a rescue window, ... and is handled by a thread, an 8-lane tile, a warp or a thread block as noted at the body).
 //
 // Stage map (reference function -> body):
 //   prep_body      ReverseOrientation + EnCodeReadSeq           src/tools.cpp:45, src/ReadMapping.cpp:404
@@ -6,13 +7,14 @@
 //   expand_body / locate_body   the bwt_sa loop of BWT_Search   src/bwt_search.cpp:153-161,109-119
 //   cluster_body   sort(CompByPosDiff) + SimplePairClustering   src/ReadMapping.cpp:152,194,160
 //   pair_body      CheckPairedAlignmentDistance, MaskUnPairedAlnCan, RemoveRedundantAlnCan  :244,305,228
-//   rescue_body    AlignmentRescue                              src/AlignmentRescue.cpp:28, src/KmerAnalysis.cpp
+//   rwenum / rwin / rcommit_body   AlignmentRescue              src/AlignmentRescue.cpp:28, src/KmerAnalysis.cpp
 //   alnprep_body   ProduceReadAlignment: fragment lists          src/ReadAlignment.cpp:306-342,38-108
 //   piece_body     ProcessNormalPair: strings + DP dispatch      src/ReadAlignment.cpp:155-191
-//   dp_body        nw_alignment / ksw2_alignment                src/nw_alignment.cpp:18, src/ksw2_alignment.cpp:250
+//   dp_core (dp_small_body, mc_dp_warp.cuh)   nw_alignment / ksw2_alignment   src/nw_alignment.cpp:18, src/ksw2_alignment.cpp:250
 //   alnfin_body    rest of ProduceReadAlignment                 src/ReadAlignment.cpp:343-411
 //   pairstat_body  GenCoordinatePair + per-chunk sums           src/ReadMapping.cpp:361,479-539
-//   prof_*         UpdateProfile / UpdateMultiHitCount          src/AlignmentProfile.cpp:41,244
+//   profkey / gate / scatter / profpiece_body   UpdateProfile / UpdateMultiHitCount   src/AlignmentProfile.cpp:41,244
+//   search_walk    BWT_Search as an operator (mc_bwt_search_batch)
 #ifndef MC_STAGES_H
 #define MC_STAGES_H
 

@@ -443,13 +443,6 @@ MC_HD void alnfin_body(int64_t r, const PipeArgs& a)
 			}
 			if (score != 0 && score < min_score && mism > max_mm) score = 0;
 		}
-#ifdef MC_HOSTEMU
-		if (getenv("MC_TRACE"))
-		{
-			fprintf(stderr, "[trace] read %lld cand %d: dead=%d head_ok=%d tail_ok=%d score=%d min=%d maxmm=%d\n", (long long)r, ci, dead, head_ok, tail_ok, score, min_score, max_mm);
-			for (int i = 0; i < nf; i++) { const mc_frag_out& x = f[i]; fprintf(stderr, "    frag %d simple=%d r=%d g=%lld rl=%d gl=%d aln=%.*s | %.*s\n", i, x.bSimple, x.rPos, (long long)x.gPos, x.rLen, x.gLen, x.bSimple ? 0 : x.aln_len, a.aln + x.aln_off, x.bSimple ? 0 : x.aln_len, a.aln + x.aln_off + x.aln_cap); }
-		}
-#endif
 		a.cscore[co + ci] = score;
 		if (score == 0) continue;
 		const bool fwd = f[0].gPos < a.ix.G;

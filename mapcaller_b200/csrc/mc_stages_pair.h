@@ -35,7 +35,7 @@ MC_HD void single_body(int64_t r, const PipeArgs& a)
 }
 
 // one thread per read pair: CheckPairedAlignmentDistance (reference src/ReadMapping.cpp:244-303) and,
-// when something paired, MaskUnPairedAlnCan.  Pairs that found nothing are queued for rescue_body.
+// when something paired, MaskUnPairedAlnCan.  Pairs that found nothing are queued for the rescue stage.
 // Also records the interval [est_lo, est_hi] of EstiDistance values for which every distance test of
 // this pair has the same outcome (used to validate the avgDist speculation).
 MC_HD void pair_body(int64_t p, const PipeArgs& a)
@@ -93,7 +93,7 @@ MC_HD void pair_body(int64_t p, const PipeArgs& a)
 		if (b0 < (l0 >> 2) && b1 < (l1 >> 2)) { remove_redundant(s0, n0); remove_redundant(s1, n1); }
 		else
 		{
-			int64_t k = mc_bump_alloc(a.rtask_bump, 1u);   // rescue_body narrows [lo, hi] further
+			int64_t k = mc_bump_alloc(a.rtask_bump, 1u);   // rcommit_body narrows [lo, hi] further
 			a.rtask[k] = (int32_t)p;
 		}
 	}
