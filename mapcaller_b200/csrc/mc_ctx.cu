@@ -773,23 +773,44 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			device_sort_u64(q.keys, c->d_keys_tmp.as<uint64_t>(), q.n_keys, c->d_sort.p, c->d_sort.cap, s);
 #ifndef MC_HOSTEMU
 			std::vector<long long> gl_n; long long gl_mx = 0; const uint64_t* gl_all = nullptr;
+			const uint8_t* gd_all = nullptr; size_t gd_pitch = 0;
 			if (od.on)
 			{
-				// per-start candidate counts of every rank: the lists (heads of the sorted key runs) are all-gathered
-				if (c->d_glist.reserve((size_t)(q.n_keys + 2) * 8) || dev_zero(&db->rwin, 8, s)) return MC_ERR_CUDA;   // the window cursor is free: reuse it
-				launch_gatecnt(a, q, q.n_keys, c->d_glist.as<uint64_t>(), &db->rwin, s);
+				// per-start candidate counts of every rank (heads of the sorted key runs, capped at 15).  Small genomes: one byte
+				// per column, all-gathered and applied by streaming kernels; large ones: (start, count) lists, all-gathered and
+				// applied list by list.  The choice depends only on sizes every rank knows (G and the key counts).
 				long long* d_sz = c->d_comm_small.as<long long>();
-				if (nccl_fail(ncclAllGather(&db->rwin, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(gate list sizes)")) return MC_ERR_NCCL;
+				long long my_keys = q.n_keys;
+				if (dev_h2d(d_sz + od.n, &my_keys, 8, s)) return MC_ERR_CUDA;
+				if (nccl_fail(ncclAllGather(d_sz + od.n, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(key counts)")) return MC_ERR_NCCL;
 				gl_n.resize(od.n);
 				if (dev_d2h(gl_n.data(), d_sz, 8 * od.n, s) || dev_sync(s)) return MC_ERR_CUDA;
-				for (int r = 0; r < od.n; r++) gl_mx = std::max(gl_mx, gl_n[r]);
-				gl_mx = (gl_mx + 1) & ~1ll;
-				if (gl_mx)
+				long long keys_mx = 0; for (int r = 0; r < od.n; r++) keys_mx = std::max(keys_mx, gl_n[r]);
+				if (keys_mx == 0) {}
+				else if ((long long)c->G <= 8 * keys_mx)
 				{
-					if (c->d_glist.grow_keep((size_t)gl_mx * 8, (size_t)gl_n[od.me] * 8, s) || c->d_glist_all.reserve((size_t)gl_mx * 8 * od.n)) return MC_ERR_CUDA;
-					if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, (size_t)gl_mx * 8, ncclUint8, c->comm, s), "ncclAllGather(gate lists)")) return MC_ERR_NCCL;
-					gl_all = c->d_glist_all.as<uint64_t>();
-					for (int r = 0; r < od.me; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
+					gd_pitch = ((size_t)c->G + 255) & ~(size_t)255;
+					if (c->d_glist.reserve(gd_pitch) || c->d_glist_all.reserve(gd_pitch * od.n) || dev_zero(c->d_glist.p, gd_pitch, s)) return MC_ERR_CUDA;
+					launch_gatedense_fill(a, q, q.n_keys, c->d_glist.as<uint8_t>(), s);
+					if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, gd_pitch, ncclUint8, c->comm, s), "ncclAllGather(gate counts)")) return MC_ERR_NCCL;
+					gd_all = c->d_glist_all.as<uint8_t>();
+					launch_gatedense_apply(a, c->G, gd_all, gd_pitch, 0, od.me, s);
+				}
+				else
+				{
+					if (c->d_glist.reserve((size_t)(q.n_keys + 2) * 8) || dev_zero(&db->rwin, 8, s)) return MC_ERR_CUDA;   // the window cursor is free: reuse it
+					launch_gatecnt(a, q, q.n_keys, c->d_glist.as<uint64_t>(), &db->rwin, s);
+					if (nccl_fail(ncclAllGather(&db->rwin, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(gate list sizes)")) return MC_ERR_NCCL;
+					if (dev_d2h(gl_n.data(), d_sz, 8 * od.n, s) || dev_sync(s)) return MC_ERR_CUDA;
+					for (int r = 0; r < od.n; r++) gl_mx = std::max(gl_mx, gl_n[r]);
+					gl_mx = (gl_mx + 1) & ~1ll;
+					if (gl_mx)
+					{
+						if (c->d_glist.grow_keep((size_t)gl_mx * 8, (size_t)gl_n[od.me] * 8, s) || c->d_glist_all.reserve((size_t)gl_mx * 8 * od.n)) return MC_ERR_CUDA;
+						if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, (size_t)gl_mx * 8, ncclUint8, c->comm, s), "ncclAllGather(gate lists)")) return MC_ERR_NCCL;
+						gl_all = c->d_glist_all.as<uint64_t>();
+						for (int r = 0; r < od.me; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
+					}
 				}
 			}
 #endif
@@ -797,6 +818,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			launch_gateupd(a, q, q.n_keys, s);
 #ifndef MC_HOSTEMU
 			if (od.on && gl_all) for (int r = od.me + 1; r < od.n; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
+			if (od.on && gd_all) launch_gatedense_apply(a, c->G, gd_all, gd_pitch, od.me + 1, od.n, s);
 #endif
 			bad |= dev_zero(&db->ptask, 8, s);            // the piece list of the alignment stage is free again: reuse it
 			launch_scatter(a, q, n, s);

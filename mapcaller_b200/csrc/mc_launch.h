@@ -40,6 +40,8 @@ static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_
 static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) profstat_body(i, recs, acc); }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatecnt_body(i, a, q, list, bump); }
 static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t) { for (int64_t i = 0; i < n; i++) gateadd_body(i, a, list); }
+static void launch_gatedense_fill(const PipeArgs& a, const ProfArgs& q, int64_t n, uint8_t* dense, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatedense_fill_body(i, a, q, dense); }
+static void launch_gatedense_apply(const PipeArgs& a, int64_t G, const uint8_t* all, size_t pitch, int r0, int r1, mc_stream_t) { for (int64_t g = 0; g < G; g++) gatedense_apply_body(g, a, all, pitch, r0, r1); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for (int64_t q = 0; q < n; q++) bwtsearch_body(q, a); }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
@@ -177,6 +179,14 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_gateadd_kernel(const PipeArgs a, 
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) gateadd_body(i, a, list); }
 static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t s)
 { if (n > 0) { mc_gateadd_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n, list); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_gatedense_fill_kernel(const PipeArgs a, const ProfArgs q, int64_t n, uint8_t* dense)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) gatedense_fill_body(i, a, q, dense); }
+static void launch_gatedense_fill(const PipeArgs& a, const ProfArgs& q, int64_t n, uint8_t* dense, mc_stream_t s)
+{ if (n > 0) { mc_gatedense_fill_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, q, n, dense); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_gatedense_apply_kernel(const PipeArgs a, int64_t G, const uint8_t* all, size_t pitch, int r0, int r1)
+{ int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (g < G) gatedense_apply_body(g, a, all, pitch, r0, r1); }
+static void launch_gatedense_apply(const PipeArgs& a, int64_t G, const uint8_t* all, size_t pitch, int r0, int r1, mc_stream_t s)
+{ if (G > 0 && r1 > r0) { mc_gatedense_apply_kernel<<<(unsigned)((G + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, G, all, pitch, r0, r1); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_bwtsearch_kernel(const SearchArgs a, int64_t n)
 { int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (q < n) bwtsearch_body(q, a); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t s)

@@ -108,6 +108,25 @@ MC_HD void gateadd_body(int64_t i, const PipeArgs& a, const uint64_t* list)
 	a.prof.rcount[s] = (uint8_t)(v < a.pr.max_dup ? v : a.pr.max_dup);
 }
 
+// the same exchange with one byte per column (genomes whose size is comparable to the number of keys): fill ...
+MC_HD void gatedense_fill_body(int64_t i, const PipeArgs& a, const ProfArgs& q, uint8_t* dense)
+{
+	const int64_t s = (int64_t)(q.keys[i] >> MC_KEY_SHIFT);
+	if (i > 0 && (int64_t)(q.keys[i - 1] >> MC_KEY_SHIFT) == s) return;
+	int n = 1;
+	while (n < 15 && i + n < q.n_keys && (int64_t)(q.keys[i + n] >> MC_KEY_SHIFT) == s) n++;
+	dense[s] = (uint8_t)n;
+}
+// ... and add the counts of ranks [r0, r1) to readCount, column by column (streaming)
+MC_HD void gatedense_apply_body(int64_t g, const PipeArgs& a, const uint8_t* all, size_t pitch, int r0, int r1)
+{
+	int v = 0;
+	for (int r = r0; r < r1; r++) v += all[(size_t)r * pitch + g];
+	if (!v) return;
+	v += a.prof.rcount[g];
+	a.prof.rcount[g] = (uint8_t)(v < a.pr.max_dup ? v : a.pr.max_dup);
+}
+
 MC_HD void prof_base(const PipeArgs& a, int64_t g, int field) // field: 0 A, 1 C, 2 G, 3 T
 {
 	if (g < 0 || g >= a.ix.G) return;

@@ -80,7 +80,7 @@ def test_two_gpu_shards_reduce_to_the_sum(built, tmp_path):
         assert sorted(g["tnl"]) == sorted(parts[0]["tnl"] + parts[1]["tnl"])
 
 
-CASE = dict(seed=62, n_pairs=9000, genome_len=120000, contigs=2, sv=2.0, n_dup=10, frag_mean=380, frag_sd=60)
+CASE = dict(seed=62, n_pairs=20000, genome_len=120000, contigs=2, sv=2.0, n_dup=10, frag_mean=380, frag_sd=60)
 
 
 @pytest.mark.gpu
