@@ -198,6 +198,24 @@ int mc_comm_unique_id(uint8_t *out128);
 int mc_comm_init(mc_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t n_ranks);
 int mc_profile_allreduce(mc_ctx *ctx, void *nccl_comm);
 
+/* ---- read ingest (first "next" row) -----------------------------------------------------------
+ * GetNextEntry / GetNextChunk, FASTQ branch (reference src/GetData.cpp:32-99), on the device: the caller hands over raw
+ * blocks of uncompressed FASTQ text (one per mate file, or one with the mates as adjacent records) and gets a batch staged
+ * in device slot `slot`, ready for mc_map_staged().  A record is four lines; the read is the second and its length is the
+ * length of that line without the newline.  Only whole records are consumed; unless `final_block` is set the batch is cut
+ * to a multiple of the reference's 200-read chunk, so that batch boundaries do not move its chunk grid.  `consumed1/2`
+ * tell the caller where the next block has to start.  Read names and qualities stay with the caller (the mapping path
+ * does not use them; a SAM writer needs them). */
+typedef struct {
+    const uint8_t *text1; int64_t len1;   /* block of the first (or only) FASTQ file */
+    const uint8_t *text2; int64_t len2;   /* block of the second mate file, or NULL */
+    int64_t max_reads;                    /* 0 = as many as the blocks hold */
+    int32_t final_block;                  /* the blocks reach the end of the file(s) */
+    int32_t pad;
+} mc_fastq_in;
+typedef struct { int64_t n_reads, consumed1, consumed2, n_bases; } mc_fastq_out;
+int mc_ingest_fastq(mc_ctx *ctx, const mc_fastq_in *in, int32_t slot, mc_fastq_out *out);
+
 /* ---- operator-level entry points (per-kernel parity tests and micro-benchmarks) ---------------- */
 
 /* BWT_Search (reference src/bwt_search.cpp:121) for n independent (read, start) queries.

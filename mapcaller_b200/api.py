@@ -92,6 +92,7 @@ def lib():
         L.mc_map_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut)]
         L.mc_stage_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.c_int32]
         L.mc_stage_batch_async.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.c_int32]
+        L.mc_ingest_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.mc_map_staged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BatchOut)]
         L.mc_get_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
         L.mc_set_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
@@ -242,6 +243,16 @@ class Context:
         b, keep = self._batch(seq, off)
         self._staging = getattr(self, "_staging", {}); self._staging[slot] = keep
         _check(lib().mc_stage_batch_async(self._h, C.byref(b), slot), "mc_stage_batch_async")
+
+    def ingest_fastq(self, text1, text2=None, slot: int = 0, max_reads: int = 0, final: bool = True) -> dict:
+        """Parses blocks of FASTQ text (bytes / uint8 arrays; one per mate file, or one with adjacent mates) on the device into
+        slot `slot`; returns n_reads, consumed1, consumed2, n_bases.  map_staged(slot) maps the batch."""
+        t1 = np.frombuffer(text1, dtype=np.uint8) if isinstance(text1, (bytes, bytearray)) else np.ascontiguousarray(text1, dtype=np.uint8)
+        t2 = None if text2 is None else (np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else np.ascontiguousarray(text2, dtype=np.uint8))
+        arg = (C.c_int64 * 6)(t1.ctypes.data, len(t1), t2.ctypes.data if t2 is not None else 0, len(t2) if t2 is not None else 0, max_reads, int(bool(final)))
+        out = (C.c_int64 * 4)()
+        _check(lib().mc_ingest_fastq(self._h, arg, slot, out), "mc_ingest_fastq")
+        return dict(n_reads=int(out[0]), consumed1=int(out[1]), consumed2=int(out[2]), n_bases=int(out[3]))
 
     def map_staged(self, slot: int = 0, copy: bool = False):
         out = BatchOut()

@@ -1021,6 +1021,105 @@ int mc_map_staged(mc_ctx* c, int32_t slot, mc_batch_out* out)
 	return run_batch(c, c->slots[slot], out, false);
 }
 
+// Read ingest on the device: raw FASTQ text -> a staged batch (mc_map_staged maps it).  See include/mapcaller_b200.h.
+int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out* out)
+{
+	if (!c || !in || !out || slot < 0 || slot >= 4 || !in->text1 || in->len1 < 0 || (in->text2 && in->len2 < 0)) { mc_set_error("mc_ingest_fastq: bad argument"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	const mc_stream_t s = c->stream;
+	memset(out, 0, sizeof(*out));
+	Staged& st = c->slots[slot];
+	st.valid = false; st.pending = false; st.n_pieces = 0; st.h_roff.clear();
+	const int nf = in->text2 ? 2 : 1;
+	const uint8_t* text[2] = {in->text1, in->text2}; const int64_t len[2] = {in->len1, in->text2 ? in->len2 : 0};
+	FastqArgs q; memset(&q, 0, sizeof(q));
+	DBuf d_text[2], d_cnt[2], d_off[2], d_lines[2], d_scan, d_rlen, d_rsrc;
+	DBuf* tmp[] = {&d_text[0], &d_text[1], &d_cnt[0], &d_cnt[1], &d_off[0], &d_off[1], &d_lines[0], &d_lines[1], &d_scan, &d_rlen, &d_rsrc};
+	auto done = [&](int rc) { for (DBuf* b : tmp) b->release(); return rc; };
+	int bad = 0;
+	int64_t n_tiles[2] = {0, 0}, n_lines[2] = {0, 0}; bool open_end[2] = {false, false};
+	if (st.flag.reserve(16) || dev_zero(st.flag.p, 16, s)) return done(MC_ERR_CUDA);
+	for (int f = 0; f < nf; f++)
+	{
+		n_tiles[f] = (len[f] + MC_FQ_TILE - 1) / MC_FQ_TILE;
+		bad |= d_text[f].reserve(len[f] + 16) || d_cnt[f].reserve((n_tiles[f] + 1) * 4) || d_off[f].reserve((n_tiles[f] + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(n_tiles[f] + 1));
+		if (bad) return done(MC_ERR_CUDA);
+		bad |= upload(c, d_text[f].p, text[f], (size_t)len[f], s);
+		q.text[f] = d_text[f].as<uint8_t>(); q.len[f] = len[f]; q.tile_cnt[f] = d_cnt[f].as<uint32_t>(); q.tile_off[f] = d_off[f].as<int64_t>();
+		launch_fqcount(q, f, n_tiles[f], s);
+		device_scan_u32(q.tile_cnt[f], d_off[f].as<int64_t>(), n_tiles[f], d_scan.as<int64_t>(), s);
+		bad |= dev_d2h(&n_lines[f], d_off[f].as<int64_t>() + n_tiles[f], 8, s);
+	}
+	if (bad || dev_sync(s)) return done(MC_ERR_CUDA);
+	// whole records only (four lines each); at the end of the file a last line without newline still counts
+	int64_t n_rec = -1;
+	for (int f = 0; f < nf; f++)
+	{
+		open_end[f] = in->final_block && len[f] > 0 && text[f][len[f] - 1] != '\n';
+		const int64_t rec = (n_lines[f] + (open_end[f] ? 1 : 0)) / 4;
+		n_rec = n_rec < 0 ? rec : std::min(n_rec, rec);
+	}
+	int64_t n = nf == 2 ? 2 * n_rec : n_rec;
+	if (in->max_reads > 0 && n > in->max_reads) n = in->max_reads;
+	if (!in->final_block) n -= n % MC_CHUNK_READS;                      // keep the 200-read chunk grid of the reference intact
+	if (c->prm.paired) n &= ~(int64_t)1;
+	if (n >= (1ll << MC_KEY_SHIFT)) n = ((1ll << MC_KEY_SHIFT) - 1) / MC_CHUNK_READS * MC_CHUNK_READS;
+	n_rec = nf == 2 ? n / 2 : n;
+	out->n_reads = n;
+	for (int f = 0; f < nf; f++)
+	{
+		bad |= d_lines[f].reserve((size_t)(n_lines[f] + 2) * 8);
+		if (bad) return done(MC_ERR_CUDA);
+		q.line_end[f] = d_lines[f].as<int64_t>() + 1; q.n_lines[f] = n_lines[f];
+		const int64_t minus1 = -1;
+		bad |= dev_h2d(d_lines[f].p, &minus1, 8, s);                      // line_end[-1] = -1: the first record starts at offset 0
+		launch_fqlines(q, f, n_tiles[f], s);
+		if (open_end[f]) bad |= dev_h2d(q.line_end[f] + n_lines[f], &len[f], 8, s);
+	}
+	if (n == 0)
+	{
+		if (dev_sync(s)) return done(MC_ERR_CUDA);
+		st.n_reads = 0; st.n_bytes = 0; st.base = 0; st.n_slots = 0; st.valid = true;
+		return done(MC_OK);
+	}
+	// where the records end: the caller carries the rest of the block over to the next call
+	int64_t cons[2] = {0, 0};
+	for (int f = 0; f < nf; f++)
+	{
+		const int64_t last_line = 4 * n_rec - 1;                           // index of the last consumed line
+		if (last_line < n_lines[f]) bad |= dev_d2h(&cons[f], q.line_end[f] + last_line, 8, s); else cons[f] = len[f] - 1;
+	}
+	bad |= d_rlen.reserve((size_t)(n + 1) * 4) || d_rsrc.reserve((size_t)n * 8) || st.roff.reserve((size_t)(n + 1) * 8) || d_scan.reserve(device_scan_scratch_bytes(n + 1));
+	if (bad) return done(MC_ERR_CUDA);
+	q.n_reads = n; q.rlen = d_rlen.as<uint32_t>(); q.rsrc = d_rsrc.as<int64_t>(); q.flag = st.flag.as<mc_u64>();
+	launch_fqread(q, n, s);
+	device_scan_u32(q.rlen, st.roff.as<int64_t>(), n, d_scan.as<int64_t>(), s);
+	int64_t n_bases = 0;
+	bad |= dev_d2h(&n_bases, st.roff.as<int64_t>() + n, 8, s);
+	if (bad || dev_sync(s)) return done(MC_ERR_CUDA);
+	out->consumed1 = cons[0] + 1; out->consumed2 = nf == 2 ? cons[1] + 1 : 0; out->n_bases = n_bases;
+	st.n_reads = n; st.n_bytes = n_bases; st.base = 0; st.n_slots = n_bases / 17 + n;
+	bad |= st.seq.reserve((size_t)n_bases + 16) || st.seed_off.reserve((size_t)(n + 2) * 8) || st.cap.reserve((size_t)n * 4) || st.scan.reserve(device_scan_scratch_bytes(n));
+	if (bad) return done(MC_ERR_CUDA);
+	q.roff = st.roff.as<int64_t>(); q.seq = st.seq.as<uint8_t>();
+	launch_fqcopy(q, n, s);
+	CapArgs cq; cq.roff = st.roff.as<int64_t>(); cq.cap = st.cap.as<uint32_t>(); cq.flag = st.flag.as<mc_u64>();
+	launch_seedcap(cq, n, s);
+	device_scan_u32(cq.cap, st.seed_off.as<int64_t>(), n, st.scan.as<int64_t>(), s);
+	PipeArgs a; memset(&a, 0, sizeof(a));
+	a.pr.paired = c->prm.paired; a.seq = st.seq.as<uint8_t>(); a.roff = st.roff.as<int64_t>(); a.n_reads = n;
+	launch_prep(a, 0, n, s);
+	if (c->prm.want_alignments) { st.h_roff.resize((size_t)n + 1); bad |= dev_d2h(st.h_roff.data(), st.roff.p, (size_t)(n + 1) * 8, s); }
+	mc_u64 flag = 0;
+	bad |= dev_d2h(&flag, st.flag.p, 8, s);
+	if (bad || dev_sync(s)) return done(MC_ERR_CUDA);
+	if (flag) { mc_set_error("mc_ingest_fastq: a record has an empty read or one longer than %d bases", MC_MAX_RLEN); return done(MC_ERR_ARG); }
+	st.valid = true;
+	return done(MC_OK);
+}
+
 // packs the columns [beg, end) tile by tile; every tile is either copied to `outp` or reduced into the four counters `acc`
 static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64* d_acc)
 {

@@ -42,6 +42,10 @@ static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint
 static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t) { for (int64_t i = 0; i < n; i++) gateadd_body(i, a, list); }
 static void launch_gatedense_fill(const PipeArgs& a, const ProfArgs& q, int64_t n, uint8_t* dense, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatedense_fill_body(i, a, q, dense); }
 static void launch_gatedense_apply(const PipeArgs& a, int64_t G, const uint8_t* all, size_t pitch, int r0, int r1, mc_stream_t) { for (int64_t g = 0; g < G; g++) gatedense_apply_body(g, a, all, pitch, r0, r1); }
+static void launch_fqcount(const FastqArgs& q, int f, int64_t n, mc_stream_t) { for (int64_t t = 0; t < n; t++) fqcount_body(t, f, q); }
+static void launch_fqlines(const FastqArgs& q, int f, int64_t n, mc_stream_t) { for (int64_t t = 0; t < n; t++) fqlines_body(t, f, q); }
+static void launch_fqread(const FastqArgs& q, int64_t n, mc_stream_t) { for (int64_t r = 0; r < n; r++) fqread_body(r, q); }
+static void launch_fqcopy(const FastqArgs& q, int64_t n, mc_stream_t) { for (int64_t r = 0; r < n; r++) fqcopy_body(r, 0, 1, q); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for (int64_t q = 0; q < n; q++) bwtsearch_body(q, a); }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
@@ -187,6 +191,22 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_gatedense_apply_kernel(const Pipe
 { int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (g < G) gatedense_apply_body(g, a, all, pitch, r0, r1); }
 static void launch_gatedense_apply(const PipeArgs& a, int64_t G, const uint8_t* all, size_t pitch, int r0, int r1, mc_stream_t s)
 { if (G > 0 && r1 > r0) { mc_gatedense_apply_kernel<<<(unsigned)((G + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, G, all, pitch, r0, r1); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_fqcount_kernel(const FastqArgs q, int f, int64_t n)
+{ int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (t < n) fqcount_body(t, f, q); }
+__global__ void __launch_bounds__(MC_BLOCK) mc_fqlines_kernel(const FastqArgs q, int f, int64_t n)
+{ int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (t < n) fqlines_body(t, f, q); }
+__global__ void __launch_bounds__(MC_BLOCK) mc_fqread_kernel(const FastqArgs q, int64_t n)
+{ int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (r < n) fqread_body(r, q); }
+__global__ void __launch_bounds__(MC_BLOCK) mc_fqcopy_kernel(const FastqArgs q, int64_t n)
+{ const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; if (w < n) fqcopy_body(w, threadIdx.x & 31, 32, q); }
+static void launch_fqcount(const FastqArgs& q, int f, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_fqcount_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(q, f, n); g_launches++; } }
+static void launch_fqlines(const FastqArgs& q, int f, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_fqlines_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(q, f, n); g_launches++; } }
+static void launch_fqread(const FastqArgs& q, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_fqread_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(q, n); g_launches++; } }
+static void launch_fqcopy(const FastqArgs& q, int64_t n, mc_stream_t s)
+{ if (n > 0) { mc_fqcopy_kernel<<<(unsigned)((n * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(q, n); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_bwtsearch_kernel(const SearchArgs a, int64_t n)
 { int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (q < n) bwtsearch_body(q, a); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t s)

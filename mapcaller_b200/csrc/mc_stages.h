@@ -212,6 +212,50 @@ MC_HD void bwtsearch_body(int64_t q, const SearchArgs& a)
 	if (a.ix.cbwt) search_walk<RcInterval32>(q, a); else search_walk<RcInterval>(q, a);
 }
 
+// ------------------------------------------------------------------------------------------------
+// read ingest: FASTQ text -> the packed read arrays (reference GetNextEntry / GetNextChunk, FASTQ branch,
+// src/GetData.cpp:32-99).  A record is four lines; the read is the second one and its length is the line's length
+// without the newline (a '\r' before it would count as a base, as in the reference).
+// ------------------------------------------------------------------------------------------------
+#define MC_FQ_TILE 64
+struct FastqArgs {
+	const uint8_t* text[2]; int64_t len[2];       // one text per mate file; text[1] == 0: mates are adjacent records of text[0]
+	uint32_t* tile_cnt[2]; const int64_t* tile_off[2]; int64_t* line_end[2]; int64_t n_lines[2];   // newline positions
+	int64_t n_reads; uint32_t* rlen; int64_t* rsrc; const int64_t* roff; uint8_t* seq; mc_u64* flag;
+};
+MC_HD void fqcount_body(int64_t t, int f, const FastqArgs& q)
+{
+	const int64_t b = t * MC_FQ_TILE; int64_t e = b + MC_FQ_TILE; if (e > q.len[f]) e = q.len[f];
+	uint32_t n = 0;
+	for (int64_t i = b; i < e; i++) n += q.text[f][i] == '\n';
+	q.tile_cnt[f][t] = n;
+}
+MC_HD void fqlines_body(int64_t t, int f, const FastqArgs& q)
+{
+	const int64_t b = t * MC_FQ_TILE; int64_t e = b + MC_FQ_TILE; if (e > q.len[f]) e = q.len[f];
+	int64_t k = q.tile_off[f][t];
+	for (int64_t i = b; i < e; i++) if (q.text[f][i] == '\n') q.line_end[f][k++] = i;
+}
+// read r of the batch: record r (one file, mates adjacent) or record r/2 of file r&1; line_end[n_lines] = len (a last line
+// without newline) is provided by the host when the block is the end of the file
+MC_HD void fqread_body(int64_t r, const FastqArgs& q)
+{
+	const int f = q.text[1] ? (int)(r & 1) : 0;
+	const int64_t rec = q.text[1] ? (r >> 1) : r;
+	const int64_t beg = q.line_end[f][4 * rec] + 1, end = q.line_end[f][4 * rec + 1];
+	int64_t n = end - beg;
+	if (n <= 0 || n > MC_MAX_RLEN) { mc_atomic_or(q.flag, (mc_u64)1 << 56); n = 1; }
+	q.rlen[r] = (uint32_t)n; q.rsrc[r] = beg;
+}
+MC_HD void fqcopy_body(int64_t r, int lane, int nl, const FastqArgs& q)
+{
+	const int f = q.text[1] ? (int)(r & 1) : 0;
+	const uint8_t* src = q.text[f] + q.rsrc[r];
+	uint8_t* dst = q.seq + q.roff[r];
+	const int n = (int)(q.roff[r + 1] - q.roff[r]);
+	for (int i = lane; i < n; i += nl) dst[i] = src[i];
+}
+
 // one thread per slot lays out its locations: read offset, length and - in the place of the genome position - the BWT row
 // the location starts from, so that the locate kernel needs a single 16-byte load per location
 MC_HD void expand_body(int64_t s, const PipeArgs& a)

@@ -124,6 +124,35 @@ void Mapping()
 			p.max_mismatch_rate = MaxMisMatchRate; p.update_profile = bVCFoutput; p.want_alignments = bSAMoutput;
 			if (mc_ctx_create(idx, &p, &ctx)) die("mc_ctx_create");
 		}
+		// No SAM wanted and plain FASTQ on disk: nothing of the reference's reader is needed - raw file blocks go to the GPU, which
+		// finds the records itself (mc_ingest_fastq = GetNextEntry / GetNextChunk, src/GetData.cpp:32-99) and maps them.
+		if (!bSAMoutput && !lib.gz && FastQFormat)
+		{
+			const size_t BLK = (size_t)64 << 20;
+			vector<uint8_t> b1, b2; size_t have1 = 0, have2 = 0; bool eof1 = false, eof2 = !lib.sep;
+			for (;;)
+			{
+				if (!eof1) { b1.resize(have1 + BLK); size_t g = fread(b1.data() + have1, 1, BLK, lib.f1); have1 += g; eof1 = g < BLK; }
+				if (!eof2) { b2.resize(have2 + BLK); size_t g = fread(b2.data() + have2, 1, BLK, lib.f2); have2 += g; eof2 = g < BLK; }
+				const bool last = eof1 || eof2;      // the shorter file ends the library, as the reader of the reference would
+				mc_fastq_in fi; memset(&fi, 0, sizeof(fi));
+				fi.text1 = b1.data(); fi.len1 = (int64_t)have1; fi.text2 = lib.sep ? b2.data() : NULL; fi.len2 = (int64_t)have2; fi.final_block = last;
+				mc_fastq_out fo;
+				if (mc_ingest_fastq(ctx, &fi, 0, &fo)) die("mc_ingest_fastq");
+				if (fo.n_reads > 0)
+				{
+					mc_batch_out out;
+					if (mc_map_staged(ctx, 0, &out)) die("mc_map_staged");
+					mc_totals t; mc_get_totals(ctx, &t);
+					fprintf(stderr, "\r%lld %s reads have been processed in %lld seconds...", (long long)t.total_reads, (bPairEnd ? "paired-end" : "singled-end"), (long long)(time(NULL) - StartProcessTime));
+				}
+				if (last || fo.n_reads == 0) break;
+				memmove(b1.data(), b1.data() + fo.consumed1, have1 - (size_t)fo.consumed1); have1 -= (size_t)fo.consumed1;
+				if (lib.sep) { memmove(b2.data(), b2.data() + fo.consumed2, have2 - (size_t)fo.consumed2); have2 -= (size_t)fo.consumed2; }
+			}
+			fclose(lib.f1); if (lib.f2) fclose(lib.f2);
+			continue;
+		}
 		vector<ReadItem_t> reads; vector<uint8_t> seq; vector<int64_t> off; vector<string> sam;
 		while (pull_batch(lib, reads) > 0)
 		{

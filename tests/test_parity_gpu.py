@@ -116,6 +116,59 @@ def test_double_buffered_feed_equals_one_call(built):
     pu.assert_same(got, whole)
 
 
+def _fastq_text(reads, mate):
+    import io
+    from mapcaller_b200 import simulate as sim
+    with tempfile.TemporaryDirectory() as td:
+        sim.write_fastq(os.path.join(td, "x.fq"), reads, mate)
+        return open(os.path.join(td, "x.fq"), "rb").read()
+
+
+@pytest.mark.parametrize("layout", ["two_files", "interleaved", "unterminated"])
+def test_fastq_ingest_on_device(built, layout):
+    """mc_ingest_fastq (GetNextEntry / GetNextChunk, reference src/GetData.cpp:32-99): raw FASTQ blocks that end in the middle
+    of records, fed block by block, give the same batches - hence the same records, totals and profile - as the host-parsed
+    arrays; mates from two files or adjacent in one; a last line without newline is still a line."""
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=23, n_pairs=2600, genome_len=60000, n_rate=0.002)
+    ix = pu.build_index(case)
+    whole = pu.cuda_results(case, ix)
+    t1, t2 = _fastq_text(case["r1"], 1), _fastq_text(case["r2"], 2)
+    if layout == "interleaved":
+        a, b = t1.split(b"\n"), t2.split(b"\n")
+        recs = []
+        for i in range(0, len(a) - 1, 4):
+            recs += a[i:i + 4] + b[i:i + 4]
+        t1, t2 = b"\n".join(recs) + b"\n", None
+    if layout == "unterminated":
+        t1, t2 = t1[:-1], t2[:-1]
+    got = dict(reads=[], est=[])
+    with api.Context(ix, want_alignments=1, update_profile=1, **case["params"]) as ctx:
+        p1 = p2 = 0
+        blk1, blk2 = (150000, 157000) if t2 is not None else (310000, 0)
+        for it in range(100):
+            b1 = t1[p1:p1 + blk1]; b2 = None if t2 is None else t2[p2:p2 + blk2]
+            final = p1 + blk1 >= len(t1) and (t2 is None or p2 + blk2 >= len(t2))
+            r = ctx.ingest_fastq(b1, b2, slot=it & 1, final=final)
+            assert final or (r["n_reads"] > 0 and r["n_reads"] % 200 == 0)
+            assert r["consumed1"] <= len(b1)
+            p1 += r["consumed1"]; p2 += r["consumed2"]
+            res = ctx.map_staged(it & 1, copy=True)
+            got["reads"] += api.unpack_reads(res); got["est"] += [int(x) for x in res["chunks"]["est_distance"]]
+            if final:
+                break
+        assert p1 == len(t1)
+        t = ctx.totals()
+        got["counters"] = dict(reads=t["total_reads"], mapped=t["total_mapped"], paired=t["total_paired"], dist_sum=t["total_distance"],
+                               len_sum=t["read_length_sum"], avgDist=t["avg_dist"])
+        got["profile"] = ctx.profile_columns(); got["ins"], got["dele"] = ctx.indels(); got["bp"] = ctx.breakpoints()
+        got["inv"] = sorted(ctx.sites(0), key=lambda x: x[0]); got["tnl"] = sorted(ctx.sites(1), key=lambda x: x[0])
+        # malformed input: an empty read line
+        with pytest.raises(api.McError):
+            ctx.ingest_fastq(b"@x\n\n+\n\n@y\nACGT\n+\nIIII\n", None, slot=2, final=True)
+    pu.assert_same(got, whole)
+
+
 def test_pipelined_large_batch_equals_resident_path(built):
     """A profile-only batch of >= 400 k reads is cut into pieces whose upload overlaps the mapping of the previous piece
     (copy stream); the result must equal the single-piece path (mc_stage_batch + mc_map_staged) and the chunk-wise path."""
