@@ -205,6 +205,7 @@ struct mc_ctx {
 	ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;
 	DBuf d_comm_small, d_comm_buf, d_glist, d_glist_all; HBuf h_comm_buf;
 #endif
+	DBuf fq_text[2], fq_cnt[2], fq_off[2], fq_lines[2], fq_scan, fq_rlen, fq_rsrc;   // scratch of mc_ingest_fastq
 };
 
 static void zero_stats(mc_stats* s) { memset(s, 0, sizeof(*s)); }
@@ -228,7 +229,9 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
 	for (DBuf* b : bufs) b->release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
-	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); }
+	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); s->flag.release(); }
+	DBuf* fq[] = {&c->fq_text[0], &c->fq_text[1], &c->fq_cnt[0], &c->fq_cnt[1], &c->fq_off[0], &c->fq_off[1], &c->fq_lines[0], &c->fq_lines[1], &c->fq_scan, &c->fq_rlen, &c->fq_rsrc};
+	for (DBuf* b : fq) b->release();
 	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc, &c->h_disc};
 	for (HBuf* b : hb) b->release();
 #ifndef MC_HOSTEMU
@@ -1035,16 +1038,16 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	const int nf = in->text2 ? 2 : 1;
 	const uint8_t* text[2] = {in->text1, in->text2}; const int64_t len[2] = {in->len1, in->text2 ? in->len2 : 0};
 	FastqArgs q; memset(&q, 0, sizeof(q));
-	DBuf d_text[2], d_cnt[2], d_off[2], d_lines[2], d_scan, d_rlen, d_rsrc;
-	DBuf* tmp[] = {&d_text[0], &d_text[1], &d_cnt[0], &d_cnt[1], &d_off[0], &d_off[1], &d_lines[0], &d_lines[1], &d_scan, &d_rlen, &d_rsrc};
-	auto done = [&](int rc) { for (DBuf* b : tmp) b->release(); return rc; };
+	DBuf* d_text = c->fq_text; DBuf* d_cnt = c->fq_cnt; DBuf* d_off = c->fq_off; DBuf* d_lines = c->fq_lines;
+	DBuf& d_scan = c->fq_scan; DBuf& d_rlen = c->fq_rlen; DBuf& d_rsrc = c->fq_rsrc;   // kept between calls: no allocation in the steady state
+	auto done = [&](int rc) { return rc; };
 	int bad = 0;
 	int64_t n_tiles[2] = {0, 0}, n_lines[2] = {0, 0}; bool open_end[2] = {false, false};
 	if (st.flag.reserve(16) || dev_zero(st.flag.p, 16, s)) return done(MC_ERR_CUDA);
 	for (int f = 0; f < nf; f++)
 	{
 		n_tiles[f] = (len[f] + MC_FQ_TILE - 1) / MC_FQ_TILE;
-		bad |= d_text[f].reserve(len[f] + 16) || d_cnt[f].reserve((n_tiles[f] + 1) * 4) || d_off[f].reserve((n_tiles[f] + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(n_tiles[f] + 1));
+		bad |= d_text[f].reserve(len[f] + 2 * MC_FQ_TILE) || d_cnt[f].reserve((n_tiles[f] + 1) * 4) || d_off[f].reserve((n_tiles[f] + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(n_tiles[f] + 1));
 		if (bad) return done(MC_ERR_CUDA);
 		bad |= upload(c, d_text[f].p, text[f], (size_t)len[f], s);
 		q.text[f] = d_text[f].as<uint8_t>(); q.len[f] = len[f]; q.tile_cnt[f] = d_cnt[f].as<uint32_t>(); q.tile_off[f] = d_off[f].as<int64_t>();

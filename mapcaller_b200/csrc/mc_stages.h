@@ -223,18 +223,49 @@ struct FastqArgs {
 	uint32_t* tile_cnt[2]; const int64_t* tile_off[2]; int64_t* line_end[2]; int64_t n_lines[2];   // newline positions
 	int64_t n_reads; uint32_t* rlen; int64_t* rsrc; const int64_t* roff; uint8_t* seq; mc_u64* flag;
 };
+// A tile is 64 bytes = four 128-bit loads per thread (the text buffer is padded to a multiple of 64); the newline bytes
+// of a 32-bit word are found with the zero-byte trick on word ^ 0x0A0A0A0A.
+MC_HD uint32_t fq_newline_mask(uint32_t w)      // bit 7 of every byte that is a newline
+{
+	const uint32_t v = w ^ 0x0A0A0A0Au;
+	// exact per-byte zero test (no carries between bytes): a byte is zero iff its low seven bits and its top bit are zero
+	return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
 MC_HD void fqcount_body(int64_t t, int f, const FastqArgs& q)
 {
-	const int64_t b = t * MC_FQ_TILE; int64_t e = b + MC_FQ_TILE; if (e > q.len[f]) e = q.len[f];
+	const int64_t b = t * MC_FQ_TILE;
 	uint32_t n = 0;
-	for (int64_t i = b; i < e; i++) n += q.text[f][i] == '\n';
+	for (int k = 0; k < MC_FQ_TILE / 16; k++)
+	{
+		const mc_u32x4 v = mc_ldg128(q.text[f] + b + 16 * k);
+		const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+		for (int j = 0; j < 4; j++)
+		{
+			uint32_t m = fq_newline_mask(w[j]);
+			const int64_t pos = b + 16 * k + 4 * j;                 // bytes past the end of the text are padding
+			if (pos + 4 > q.len[f]) { const int keep = (int)(q.len[f] - pos); m = keep <= 0 ? 0u : (m & (0xFFFFFFFFu >> (32 - 8 * keep))); }
+			n += (uint32_t)mc_popc(m);
+		}
+	}
 	q.tile_cnt[f][t] = n;
 }
 MC_HD void fqlines_body(int64_t t, int f, const FastqArgs& q)
 {
-	const int64_t b = t * MC_FQ_TILE; int64_t e = b + MC_FQ_TILE; if (e > q.len[f]) e = q.len[f];
+	const int64_t b = t * MC_FQ_TILE;
 	int64_t k = q.tile_off[f][t];
-	for (int64_t i = b; i < e; i++) if (q.text[f][i] == '\n') q.line_end[f][k++] = i;
+	if (q.tile_off[f][t + 1] == k) return;                           // no newline in this tile
+	for (int c = 0; c < MC_FQ_TILE / 16; c++)
+	{
+		const mc_u32x4 v = mc_ldg128(q.text[f] + b + 16 * c);
+		const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+		for (int j = 0; j < 4; j++)
+		{
+			const uint32_t m = fq_newline_mask(w[j]);
+			if (!m) continue;
+			const int64_t pos = b + 16 * c + 4 * j;
+			for (int i = 0; i < 4; i++) if (((m >> (8 * i + 7)) & 1u) && pos + i < q.len[f]) q.line_end[f][k++] = pos + i;
+		}
+	}
 }
 // read r of the batch: record r (one file, mates adjacent) or record r/2 of file r&1; line_end[n_lines] = len (a last line
 // without newline) is provided by the host when the block is the end of the file

@@ -225,8 +225,8 @@ def read_fasta(path: str):
     return contigs
 
 
-def write_fastq(path: str, reads: np.ndarray, mate: int, prefix: str = "r") -> None:
-    """Fixed-width records `@r000000123/1` so the whole file is built as one numpy byte matrix."""
+def fastq_text(reads: np.ndarray, mate: int, prefix: str = "r") -> np.ndarray:
+    """The bytes of a FASTQ file with fixed-width records `@r000000123/1`, built as one numpy byte matrix."""
     n, L = reads.shape
     names = np.char.add(np.char.add("@" + prefix, np.char.zfill(np.arange(n).astype(str), 9)), "/%d" % mate)
     w = len(names[0])
@@ -239,8 +239,12 @@ def write_fastq(path: str, reads: np.ndarray, mate: int, prefix: str = "r") -> N
     rec[:, w + 3 + L] = 10
     rec[:, w + 4 + L:w + 4 + 2 * L] = ord("I")
     rec[:, w + 4 + 2 * L] = 10
+    return rec.reshape(-1)
+
+
+def write_fastq(path: str, reads: np.ndarray, mate: int, prefix: str = "r") -> None:
     with open(path, "wb") as fh:
-        fh.write(rec.tobytes())
+        fh.write(fastq_text(reads, mate, prefix).tobytes())
 
 
 def interleave(r1: np.ndarray, r2: np.ndarray):
