@@ -1,4 +1,5 @@
-"""Developer harness: the parity cases of tools/gpu_first.py through the host-compiled stage bodies."""
+"""Developer harness: parity cases through the host-compiled stage bodies (tools/hostemu/build.sh) against oracle/_ref on a
+box without a GPU.  Lives under tests/ because it uses the oracle; not collected by pytest, never imported elsewhere."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,9 +1,9 @@
 """Parity at BASELINE.json configs[2] scale: chr1-sized (248 Mbp) synthetic genome with repeat families, 2x150 bp pairs.
 The CUDA path (index in HBM, compact layout, several batches) against the CPU restatement of the reference (oracle/restate),
 record for record: per-read candidates / fragments / alignment strings, EstiDistance per chunk, totals, the whole profile
-(tile by tile), indel maps, break points, SV sites.  Not part of the default test suite (takes a few minutes and ~20 GB of
+(tile by tile), indel maps, break points, SV sites.  Test infrastructure like the rest of tests/ (it is the only kind of code that may use oracle/), but not collected by pytest (takes a few minutes and ~20 GB of
 host memory); its log is committed under profiles/.
-usage: python tools/parity_big.py [genome_bp] [pairs] [read_len] [batches] [ksw2]
+usage: python tests/scale_parity.py [genome_bp] [pairs] [read_len] [batches] [ksw2]
 (`ksw2` as fifth argument = configs[4] flavour: -alg ksw2, small indels 2000/Mb, large 500/Mb, 0.2 % indel errors per read base)"""
 import os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
