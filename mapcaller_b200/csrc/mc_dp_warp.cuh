@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_dp_kernel(const PipeArgs a)
 	uint8_t* fast = dp_smem + (threadIdx.x >> 5) * MC_DP_SMEM;
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	if (a.st->overflow) return;        // an arena ran out earlier in this attempt (a task slot may be unwritten): the attempt is repeated
 	int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
 	uint32_t cells = 0, tasks = 0;     // lane 0 of the warp counts, one atomic per warp at the end
 	for (int64_t t = a.task_begin + warp; t < end; t += n_warps)
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(MC_DP_SMALL_THREADS) mc_dp_small_kernel(const 
 	extern __shared__ __align__(16) uint8_t dp_small_smem[];
 	uint8_t* ws = dp_small_smem + (size_t)threadIdx.x * MC_DP_SMALL_STRIDE;
 	const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, n_threads = (int64_t)gridDim.x * blockDim.x;
+	if (a.st->overflow) return;        // see mc_dp_kernel
 	int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
 	uint32_t cells = 0, tasks = 0;
 	for (int64_t t = a.task_begin + tid; t < end; t += n_threads) dp_small_body(t, a, ws, &cells, &tasks);

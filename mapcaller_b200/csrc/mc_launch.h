@@ -138,17 +138,17 @@ static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t
 }
 // rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent thread blocks
 // (block b takes windows b, b + n_blocks, ...), commit per pair.  A window search is a chain of short loops over small
-// tables (word list, diagonal histogram, filter, staged window): the tables live in shared memory (24 KB per block, so 8
-// blocks per SM) and the 128 threads of the block share every loop - windows in repeats cost 100x the typical one and
+// tables (word list, diagonal histogram, filter, staged window): the tables live in shared memory (32 KB per block - enough for the 1500-base windows of the warm-up
+// chunks at 150-base reads -, six blocks per SM) and the 128 threads of the block share every loop - windows in repeats cost 100x the typical one and
 // their latency is what a replay attempt waits for.
 #define MC_RESCUE_THREADS 128
-#define MC_RESCUE_SMEM (24 * 1024)
+#define MC_RESCUE_SMEM (32 * 1024)
 __global__ void __launch_bounds__(MC_BLOCK) mc_rwenum_kernel(const PipeArgs a)
 {
 	const int64_t n = (int64_t)*a.rtask_bump - a.rtask_begin;
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) rwenum_body(t, a);
 }
-__global__ void __launch_bounds__(MC_RESCUE_THREADS, 8) mc_rescue_kernel(const PipeArgs a)
+__global__ void __launch_bounds__(MC_RESCUE_THREADS, 6) mc_rescue_kernel(const PipeArgs a)
 {
 	extern __shared__ __align__(16) uint8_t rescue_smem[];
 	if (a.st->overflow & 0xFF) return;          // the window list is incomplete: the attempt is going to be repeated with larger arenas
@@ -168,7 +168,7 @@ static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 	if (!configured) { cudaFuncSetAttribute(mc_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_RESCUE_SMEM); configured = true; }
 	int64_t tb = (max_tasks + MC_BLOCK - 1) / MC_BLOCK; if (tb > 148 * 2) tb = 148 * 2;
 	mc_rwenum_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
-	mc_rescue_kernel<<<148 * 8, MC_RESCUE_THREADS, MC_RESCUE_SMEM, s>>>(a); g_launches++;
+	mc_rescue_kernel<<<148 * 6, MC_RESCUE_THREADS, MC_RESCUE_SMEM, s>>>(a); g_launches++;
 	mc_rcommit_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
 }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profstat_kernel(int64_t n, const uint64_t* recs, mc_u64* acc)

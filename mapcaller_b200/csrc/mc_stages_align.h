@@ -381,6 +381,7 @@ MC_HD bool local_quality_ok(const PipeArgs& a, const mc_frag_out& x)
 
 MC_HD void alnfin_body(int64_t r, const PipeArgs& a)
 {
+	if (a.st->overflow) return;          // an arena ran out earlier in this attempt (fills may be missing): the attempt is repeated
 	if (!a.read_redo[r]) return;
 	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
 	const int64_t co = pa_cand_off(a, r);
@@ -468,6 +469,7 @@ MC_HD int64_t cand_first_gpos(const PipeArgs& a, int64_t co, int ci) { return a.
 
 MC_HD void pairstat_body(int64_t p, const PipeArgs& a)
 {
+	if (a.st->overflow) return;
 	const int64_t r0 = 2 * p, r1 = r0 + 1;
 	if (!a.read_redo[r0]) return;
 	const int64_t c0 = pa_cand_off(a, r0), c1 = pa_cand_off(a, r1);
@@ -514,7 +516,7 @@ MC_HD void disclist_body(int64_t p, const PipeArgs& a, DiscRec* out, mc_u64* bum
 
 MC_HD void chunkstat_body(int64_t c, int lane, int nl, const PipeArgs& a)
 {
-	if (!a.active[c]) return;
+	if (!a.active[c] || a.st->overflow) return;   // overflow: the attempt is repeated, nothing of it is used
 	const int64_t rb = c * MC_CHUNK_READS;
 	int64_t re = rb + MC_CHUNK_READS; if (re > a.n_reads) re = a.n_reads;
 	int mapped = 0, paired = 0, dsum = 0, lsum = 0;   // a chunk holds 100 pairs with dist <= 1000: the sums fit an int
