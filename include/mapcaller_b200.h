@@ -66,6 +66,10 @@ typedef struct {
  * fwd + revcomp from 2-bit codes (0..3) of the concatenated contigs. */
 int mc_index_build(const uint8_t *fwd_codes, int64_t genome_size, int32_t n_chrom, const int32_t *chrom_len,
                    const char *const *chrom_name, int32_t n_threads, mc_index **out);
+/* The same with the suffix array sorted on a GPU (prefix doubling with radix sorts, 36 bytes of HBM per text symbol; texts
+ * below 2^32 symbols): identical index, identical files. */
+int mc_index_build_gpu(const uint8_t *fwd_codes, int64_t genome_size, int32_t n_chrom, const int32_t *chrom_len,
+                       const char *const *chrom_name, int32_t device, mc_index **out);
 /* FASTA front end of the same: N / IUPAC bases are replaced exactly as bntseq.c:144,173 does
  * (srand48(11), lrand48()&3) and recorded in .amb. */
 int mc_index_build_fasta(const char *fasta_path, int32_t n_threads, mc_index **out);

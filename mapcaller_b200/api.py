@@ -80,6 +80,7 @@ def lib():
         L.mc_last_error.restype = C.c_char_p
         L.mc_version.restype = C.c_char_p
         L.mc_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.mc_index_build_gpu.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.mc_index_build_fasta.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.mc_index_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.mc_index_save.argtypes = [C.c_void_p, C.c_char_p]
@@ -144,7 +145,7 @@ class Index:
         self._h = handle
 
     @classmethod
-    def build(cls, fwd_codes: np.ndarray, chrom_len=None, chrom_name=None, threads: int = 0) -> "Index":
+    def build(cls, fwd_codes: np.ndarray, chrom_len=None, chrom_name=None, threads: int = 0, gpu_device=None) -> "Index":
         fwd_codes = np.ascontiguousarray(fwd_codes, dtype=np.uint8)
         h = C.c_void_p()
         if chrom_len is None:
@@ -153,6 +154,9 @@ class Index:
         names = None
         if chrom_name is not None:
             names = (C.c_char_p * len(chrom_name))(*[n.encode() for n in chrom_name])
+        if gpu_device is not None:   # suffix array sorted on the GPU (same index, same files)
+            _check(lib().mc_index_build_gpu(fwd_codes.ctypes.data, len(fwd_codes), len(lens), lens.ctypes.data, names, int(gpu_device), C.byref(h)), "mc_index_build_gpu")
+            return cls(h)
         _check(lib().mc_index_build(fwd_codes.ctypes.data, len(fwd_codes), len(lens), lens.ctypes.data, names, threads, C.byref(h)), "mc_index_build")
         return cls(h)
 

@@ -24,6 +24,10 @@
 #include <vector>
 
 void mc_set_error(const char* fmt, ...);
+#ifndef MC_HOSTEMU
+// index_gpu.cu: suffix array of the packed text by prefix doubling on the GPU
+extern "C" int mc_gpu_suffix_sort(const uint64_t* words, size_t n_words, int64_t n, int device, uint32_t* sa_out);
+#endif
 
 struct mc_index {
 	std::vector<uint32_t> bwt_store;
@@ -130,6 +134,8 @@ void finish_view(mc_index* ix, uint64_t primary, const uint64_t L2[5], uint64_t 
 	v.n_chrom = (int32_t)ix->chrom_len.size(); v.chrom_len = ix->chrom_len.data(); v.chrom_name = ix->chrom_name_ptr.data();
 }
 
+static thread_local int g_sort_device = -1;   // >= 0: mc_index_build_gpu is running, sort the suffixes on that device
+
 template <class IdxT>
 int build_core(mc_index* ix, const uint8_t* fwd, int64_t G, int n_threads)
 {
@@ -145,6 +151,15 @@ int build_core(mc_index* ix, const uint8_t* fwd, int64_t G, int n_threads)
 	for (int c = 0; c < 4; c++) L2[c + 1] += L2[c];
 
 	std::vector<IdxT> sa;
+#ifndef MC_HOSTEMU
+	if (g_sort_device >= 0 && sizeof(IdxT) == 4)
+	{
+		sa.resize(N);
+		int rc = mc_gpu_suffix_sort(t.w.data(), t.w.size(), N, g_sort_device, (uint32_t*)sa.data());
+		if (rc != MC_OK) return rc;
+	}
+	else
+#endif
 	sort_suffixes<IdxT>(t, sa, n_threads);
 
 	// rows: 0 = empty suffix, r >= 1 = sa[r-1].  BWT symbol of row r = text[pos-1]; the row with pos == 0 is `primary`.
@@ -206,6 +221,21 @@ int mc_index_build(const uint8_t* fwd_codes, int64_t genome_size, int32_t n_chro
 	if (rc != MC_OK) { delete ix; return rc; }
 	*out = ix;
 	return MC_OK;
+}
+
+int mc_index_build_gpu(const uint8_t* fwd_codes, int64_t genome_size, int32_t n_chrom, const int32_t* chrom_len,
+                       const char* const* chrom_name, int32_t device, mc_index** out)
+{
+#ifdef MC_HOSTEMU
+	mc_set_error("no GPU in the developer harness"); return MC_ERR_CUDA;
+#else
+	if (genome_size <= 0 || 2 * genome_size >= (1ll << 32) - 2) { mc_set_error("mc_index_build_gpu: texts of 2^32 symbols and more are sorted on the host (mc_index_build)"); return MC_ERR_ARG; }
+	if (device < 0) { mc_set_error("mc_index_build_gpu: bad device"); return MC_ERR_ARG; }
+	g_sort_device = device;
+	const int rc = mc_index_build(fwd_codes, genome_size, n_chrom, chrom_len, chrom_name, 1, out);
+	g_sort_device = -1;
+	return rc;
+#endif
 }
 
 int mc_index_build_fasta(const char* fasta_path, int32_t n_threads, mc_index** out)

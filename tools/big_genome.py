@@ -18,7 +18,10 @@ mut, _ = sim.mutate(g, 14, snp_per_mb=1000, small_indel_per_mb=2000 if KSW2 else
 t = time.time(); r1, r2 = sim.simulate_pairs(mut, P, L, seed=15, frag_mean=max(450, 2 * L), frag_sd=50, sub_rate=0.003, indel_rate=0.002 if KSW2 else 0.0)
 seq, off = sim.interleave(r1, r2); print("reads %.1fs" % (time.time() - t), flush=True)
 del mut
-t = time.time(); ix = api.Index.build(sim.encode(g)); print("index build %.1fs (%d threads)" % (time.time() - t, os.cpu_count()), flush=True)
+if os.environ.get("MC_GPU_INDEX"):
+    t = time.time(); ix = api.Index.build(sim.encode(g), gpu_device=0); print("index build %.1fs (suffix array on the GPU)" % (time.time() - t), flush=True)
+else:
+    t = time.time(); ix = api.Index.build(sim.encode(g)); print("index build %.1fs (%d threads)" % (time.time() - t, os.cpu_count()), flush=True)
 ctx = api.Context(ix, paired=1, alg_ksw2=int(KSW2))
 ctx.stage_batch(seq, off, 0)
 for i in range(3):
