@@ -85,8 +85,8 @@ CASE = dict(seed=62, n_pairs=20000, genome_len=120000, contigs=2, sv=2.0, n_dup=
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("super_batches", [1, 3])
-def test_two_gpus_one_library_equals_single_reference_run(built, tmp_path, super_batches):
+@pytest.mark.parametrize("super_batches,paired", [(1, 1), (3, 1), (2, 0)])
+def test_two_gpus_one_library_equals_single_reference_run(built, tmp_path, super_batches, paired):
     code = textwrap.dedent("""
         import os, sys, pickle
         import numpy as np
@@ -98,16 +98,17 @@ def test_two_gpus_one_library_equals_single_reference_run(built, tmp_path, super
         torch.cuda.set_device(rank); dist.init_process_group('nccl')
         case = pu.make_case(**%r)
         nsb = %d
+        paired = %d
         ix = pu.build_index(case)
-        ctx = api.Context(ix, paired=1, device=rank, want_alignments=1, shard_rank=rank, shard_count=world)
+        ctx = api.Context(ix, paired=paired, device=rank, want_alignments=1, shard_rank=rank, shard_count=world)
         uid = [api.Context.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
         parts = []
         for b in range(nsb):
-            sseq, soff = shard.take_shard(case['seq'], case['off'], nsb, b)        # super-batch b of the library ...
-            seq, off = shard.take_shard(sseq, soff, world, rank)                   # ... and this rank's share of it
+            sseq, soff = shard.take_shard(case['seq'], case['off'], nsb, b, bool(paired))        # super-batch b of the library ...
+            seq, off = shard.take_shard(sseq, soff, world, rank, bool(paired))                   # ... and this rank's share of it
             res = ctx.map_batch(seq, off)
-            parts.append(dict(reads=api.unpack_reads(res), est=[int(x) for x in res['chunks']['est_distance']], replays=res['replays']))
+            parts.append(dict(reads=api.unpack_reads(res), est=[int(x) for x in res['chunks']['est_distance']] if paired else [], replays=res['replays']))
         totals = ctx.totals()
         ctx.profile_allreduce()
         ins, dele = ctx.indels()
@@ -115,13 +116,13 @@ def test_two_gpus_one_library_equals_single_reference_run(built, tmp_path, super
                    inv=sorted(ctx.sites(0), key=lambda x: x[0]), tnl=sorted(ctx.sites(1), key=lambda x: x[0]))
         pickle.dump(out, open(%r + '/o%%d.pkl' %% rank, 'wb'))
         dist.destroy_process_group()
-    """) % (ROOT, os.path.join(ROOT, "tests"), CASE, super_batches, str(tmp_path))
+    """) % (ROOT, os.path.join(ROOT, "tests"), dict(CASE, paired=paired), super_batches, paired, str(tmp_path))
     script = tmp_path / "w.py"
     script.write_text(code)
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29612", str(script)])
     import pickle
     got = [pickle.load(open(str(tmp_path / ("o%d.pkl" % r)), "rb")) for r in range(2)]
-    case = pu.make_case(**CASE)
+    case = pu.make_case(**dict(CASE, paired=paired))
     ix = pu.build_index(case)
     want = pu.oracle_results(case, ix)
     reads, est = [], []
@@ -133,4 +134,4 @@ def test_two_gpus_one_library_equals_single_reference_run(built, tmp_path, super
         mine = dict(reads=reads, est=est, profile=got[r]["profile"], ins=got[r]["ins"], dele=got[r]["dele"], bp=got[r]["bp"], inv=got[r]["inv"], tnl=got[r]["tnl"],
                     counters=dict(reads=t["total_reads"], mapped=t["total_mapped"], paired=t["total_paired"], dist_sum=t["total_distance"], len_sum=t["read_length_sum"],
                                   avgDist=t["avg_dist"]))
-        pu.assert_same(mine, want)
+        pu.assert_same(mine, want, paired=bool(paired))
