@@ -221,6 +221,9 @@ void mc_params_default(mc_params* p)
 
 void mc_ctx_destroy(mc_ctx* c)
 {
+#ifndef MC_HOSTEMU
+	if (c) cudaSetDevice(c->prm.device);   // a process may hold contexts on several GPUs
+#endif
 	if (!c) return;
 	DBuf* bufs[] = {&c->d_bwt, &c->d_cbwt, &c->d_sa, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_base16, &c->d_sdiff, &c->d_cdiff, &c->d_mdiff, &c->d_rcount, &c->d_rflag, &c->d_bp, &c->d_ind,
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
@@ -329,6 +332,9 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 
 int mc_reset(mc_ctx* c)
 {
+#ifndef MC_HOSTEMU
+	if (c) cudaSetDevice(c->prm.device);   // a process may hold contexts on several GPUs
+#endif
 	if (!c) { mc_set_error("mc_reset: null context"); return MC_ERR_ARG; }
 	int bad = 0;
 	if (c->prm.update_profile)
@@ -1181,6 +1187,9 @@ int mc_profile_summary(mc_ctx* c, mc_profile_stats* out)
 
 int mc_profile_indels(mc_ctx* c, const mc_indel_rec** recs, int64_t* n_recs, const uint8_t** seq_arena)
 {
+#ifndef MC_HOSTEMU
+	if (c) cudaSetDevice(c->prm.device);   // a process may hold contexts on several GPUs
+#endif
 	if (!c || !recs || !n_recs || !seq_arena) { mc_set_error("mc_profile_indels: null argument"); return MC_ERR_ARG; }
 	PersistBumps pb;
 	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
@@ -1206,6 +1215,9 @@ int mc_profile_indels(mc_ctx* c, const mc_indel_rec** recs, int64_t* n_recs, con
 
 int mc_profile_breakpoints(mc_ctx* c, const mc_breakpoint_rec** recs, int64_t* n_recs)
 {
+#ifndef MC_HOSTEMU
+	if (c) cudaSetDevice(c->prm.device);   // a process may hold contexts on several GPUs
+#endif
 	if (!c || !recs || !n_recs) { mc_set_error("mc_profile_breakpoints: null argument"); return MC_ERR_ARG; }
 	PersistBumps pb;
 	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
@@ -1223,6 +1235,9 @@ int mc_profile_breakpoints(mc_ctx* c, const mc_breakpoint_rec** recs, int64_t* n
 // caller applies the thread-end std::sort by gPos (:629-630) itself so that ties keep the reference's order.
 int mc_profile_sites(mc_ctx* c, int32_t kind, const mc_site_rec** recs, int64_t* n_recs)
 {
+#ifndef MC_HOSTEMU
+	if (c) cudaSetDevice(c->prm.device);   // a process may hold contexts on several GPUs
+#endif
 	if (!c || !recs || !n_recs || kind < 0 || kind > 1) { mc_set_error("mc_profile_sites: bad argument"); return MC_ERR_ARG; }
 	std::vector<mc_site_rec>& v = kind == 0 ? c->inv_sites : c->tnl_sites;
 	*recs = v.data(); *n_recs = (int64_t)v.size();
@@ -1400,6 +1415,9 @@ int mc_bwt_search_batch(mc_ctx* c, int64_t n, const uint8_t* codes, const int64_
 int mc_align_batch(mc_ctx* c, int32_t use_ksw2, int64_t n, const uint8_t* s1, const int64_t* off1, const uint8_t* s2, const int64_t* off2,
                    const int64_t* out_off, uint8_t* out1, uint8_t* out2, int32_t* out_len)
 {
+#ifndef MC_HOSTEMU
+	if (c) cudaSetDevice(c->prm.device);   // a process may hold contexts on several GPUs
+#endif
 	if (!c || n < 0 || (n > 0 && (!s1 || !off1 || !s2 || !off2 || !out_off || !out1 || !out2 || !out_len))) { mc_set_error("mc_align_batch: bad argument"); return MC_ERR_ARG; }
 	if (n == 0) return MC_OK;
 	const mc_stream_t s = c->stream;

@@ -169,9 +169,10 @@ __global__ void __launch_bounds__(MC_DP_SMALL_THREADS) mc_dp_small_kernel(const 
 static void launch_dp(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
-	static bool configured = false;
+	static bool configured[64];          // per device, see launch_rescue
 	const int smem = MC_DP_SMALL_THREADS * MC_DP_SMALL_STRIDE;
-	if (!configured) { cudaFuncSetAttribute(mc_dp_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+	int dev = 0; cudaGetDevice(&dev); dev &= 63;
+	if (!configured[dev]) { cudaFuncSetAttribute(mc_dp_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured[dev] = true; }
 	int64_t sb = (max_tasks + MC_DP_SMALL_THREADS - 1) / MC_DP_SMALL_THREADS; if (sb > 148 * 2) sb = 148 * 2;
 	mc_dp_small_kernel<<<(unsigned)sb, MC_DP_SMALL_THREADS, smem, s>>>(a); g_launches++;
 	int64_t blocks = (max_tasks * 32 + MC_BLOCK - 1) / MC_BLOCK; if (blocks > 148 * 8) blocks = 148 * 8;

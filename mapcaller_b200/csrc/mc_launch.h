@@ -164,8 +164,9 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_rcommit_kernel(const PipeArgs a)
 static void launch_rescue(const PipeArgs& a, int64_t max_tasks, mc_stream_t s)
 {
 	if (max_tasks <= 0) return;
-	static bool configured = false;
-	if (!configured) { cudaFuncSetAttribute(mc_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_RESCUE_SMEM); configured = true; }
+	static bool configured[64];          // the attribute is per device: a process may hold contexts on several GPUs
+	int dev = 0; cudaGetDevice(&dev); dev &= 63;
+	if (!configured[dev]) { cudaFuncSetAttribute(mc_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_RESCUE_SMEM); configured[dev] = true; }
 	int64_t tb = (max_tasks + MC_BLOCK - 1) / MC_BLOCK; if (tb > 148 * 2) tb = 148 * 2;
 	mc_rwenum_kernel<<<(unsigned)tb, MC_BLOCK, 0, s>>>(a); g_launches++;
 	mc_rescue_kernel<<<148 * 6, MC_RESCUE_THREADS, MC_RESCUE_SMEM, s>>>(a); g_launches++;

@@ -135,3 +135,33 @@ def test_two_gpus_one_library_equals_single_reference_run(built, tmp_path, super
                     counters=dict(reads=t["total_reads"], mapped=t["total_mapped"], paired=t["total_paired"], dist_sum=t["total_distance"], len_sum=t["read_length_sum"],
                                   avgDist=t["avg_dist"]))
         pu.assert_same(mine, want, paired=bool(paired))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_one_process_two_devices(built):
+    """Two contexts on two GPUs inside ONE process, used alternately: every entry point selects its context's device, and the
+    per-device kernel attributes (dynamic shared memory of the rescue / small-fill kernels) are set on both."""
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=63, n_pairs=5000, genome_len=90000, sv=3.0, n_dup=10, tandem=5)
+    ix = pu.build_index(case)
+    want = pu.oracle_results(case, ix)
+    seq, off = case["seq"], case["off"]
+    n = len(off) - 1
+    half = (n // 400) * 200
+    ctxs = [api.Context(ix, want_alignments=1, update_profile=1, device=d, **case["params"]) for d in (0, 1)]
+    got = [dict(reads=[], est=[]) for _ in ctxs]
+    for b, e in ((0, half), (half, n)):
+        for k, ctx in enumerate(ctxs):                       # interleaved: device 0, device 1, device 0, device 1
+            res = ctx.map_batch(seq[off[b]:off[e]], off[b:e + 1] - off[b])
+            got[k]["reads"] += api.unpack_reads(res); got[k]["est"] += [int(x) for x in res["chunks"]["est_distance"]]
+    for k, ctx in enumerate(ctxs):
+        t = ctx.totals()
+        got[k]["counters"] = dict(reads=t["total_reads"], mapped=t["total_mapped"], paired=t["total_paired"], dist_sum=t["total_distance"],
+                                  len_sum=t["read_length_sum"], avgDist=t["avg_dist"])
+        got[k]["profile"] = ctx.profile_columns(); got[k]["ins"], got[k]["dele"] = ctx.indels(); got[k]["bp"] = ctx.breakpoints()
+        got[k]["inv"] = sorted(ctx.sites(0), key=lambda x: x[0]); got[k]["tnl"] = sorted(ctx.sites(1), key=lambda x: x[0])
+        got[k]["summary"] = ctx.profile_summary()
+        pu.assert_same(got[k], want)
+    for ctx in ctxs:
+        ctx.close()
