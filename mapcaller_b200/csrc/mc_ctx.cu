@@ -550,6 +550,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	const int64_t n_pairs = paired ? n / 2 : 0;
 	const int64_t n_chunks = (n + MC_CHUNK_READS - 1) / MC_CHUNK_READS;
 	memset(out, 0, sizeof(*out));
+	if (n == 0 && ordered_mode(c)) { mc_set_error("mc_map_batch: with the ordered multi-GPU exchange every rank has to pass reads in every call (mc_comm_init)"); return MC_ERR_ARG; }
 	if (n == 0) return MC_OK;
 
 	PipeArgs a; memset(&a, 0, sizeof(a));
