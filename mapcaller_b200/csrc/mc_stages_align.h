@@ -311,6 +311,7 @@ MC_HD int dp_core(bool ksw2, int m, int n, uint8_t* s1, uint8_t* s2, const uint8
 
 MC_HD void dp_body(int64_t t, const PipeArgs& a)
 {
+	if (a.st->overflow) return;            // an arena ran out earlier in this attempt: a task slot may be unwritten, the attempt is repeated
 	{
 		int64_t end = (int64_t)*a.task_bump; if (end > a.task_cap) end = a.task_cap;
 		if (a.task_begin + t >= end) return;

@@ -25,6 +25,8 @@ CASES = {
     "n_bases_noisy": dict(seed=8, n_pairs=5000, genome_len=80000, n_rate=0.01, sub_rate=0.02),
     "sv_repeats": dict(seed=9, n_pairs=20000, genome_len=200000, sv=5.0, n_dup=30, tandem=20),
     "long_reads_250": dict(seed=10, n_pairs=4000, genome_len=150000, read_len=250, frag_mean=600, frag_sd=80, indel_rate=0.003),
+    "long_reads_900": dict(seed=27, n_pairs=600, genome_len=150000, read_len=900, frag_mean=2200, frag_sd=200, indel_rate=0.002, sv=3.0),
+    "long_reads_900_ksw2": dict(seed=28, n_pairs=400, genome_len=150000, read_len=900, frag_mean=2200, frag_sd=200, indel_rate=0.003, alg_ksw2=1),
     "deep_duplicates": dict(seed=11, n_pairs=30000, genome_len=20000, max_dup=3),
     "lower_case_reads": dict(seed=15, n_pairs=4000, genome_len=60000, lower_rate=0.2),
     "params": dict(seed=13, n_pairs=3000, genome_len=60000, max_pos_diff=8, max_clip=2, max_dup=15, max_mismatch_rate=0.1),
@@ -218,6 +220,25 @@ def test_edge_cases(built):
             ctx.map_batch(seq[:off[3]], off[:4])     # odd number of reads in paired mode
     case2 = dict(case, seq=seq, off=off)
     pu.assert_same(pu.cuda_results(case2, ix), pu.oracle_results(case2, ix))
+
+
+def ragged_case(seed=19, n_pairs=6000, genome_len=120000):
+    """Reads of very different lengths in one library (trimmed reads): 20 .. 150 bases, a few shorter than a seed."""
+    case = pu.make_case(seed=seed, n_pairs=n_pairs, genome_len=genome_len, read_len=150, frag_mean=420, frag_sd=60, contigs=2)
+    rng = np.random.default_rng(seed)
+    seq, off = case["seq"], case["off"]
+    n = len(off) - 1
+    keep = rng.integers(20, 151, size=n); keep[rng.random(n) < 0.01] = rng.integers(1, 16, size=int((rng.random(n) < 0.01).sum()) or 1)[0]
+    parts = [seq[off[i]:off[i] + min(int(keep[i]), int(off[i + 1] - off[i]))] for i in range(n)]
+    noff = np.zeros(n + 1, dtype=np.int64); noff[1:] = np.cumsum([len(p) for p in parts])
+    return dict(case, seq=np.concatenate(parts), off=noff)
+
+
+def test_ragged_read_lengths(built):
+    case = ragged_case()
+    ix = pu.build_index(case)
+    mine = pu.cuda_results(case, ix, batch_reads=5000)
+    pu.assert_same(mine, pu.oracle_results(case, ix))
 
 
 @pytest.mark.parametrize("wide", [0, 1])
