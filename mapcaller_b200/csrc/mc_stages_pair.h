@@ -260,8 +260,11 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 		if (hi < est) hi = est;
 	}
 	*iv_lo = *iv_lo > lo ? *iv_lo : lo; *iv_hi = *iv_hi < hi ? *iv_hi : hi;
-	if (i1 >= a.ix.n_end || i2 >= a.ix.n_end) return false; // the reference dereferences end() here; treated as "different chromosome"
-	if (a.ix.chrom_id[i1] != a.ix.chrom_id[i2]) return false;
+	// A window that reaches 2G makes the reference read PosChrIdMap.end()->second (src/AlignmentRescue.cpp:62-63).  What it finds
+	// there, with GCC's layout of the globals of src/main.cpp, is the zeroed first word of the map defined next: chromosome id
+	// 0 - which is also the id of the chromosome that ends at 2G.  Reproduced as such (checked against oracle/_ref).
+	if (i1 >= a.ix.n_end) return false;
+	if (a.ix.chrom_id[i1] != (i2 >= a.ix.n_end ? 0 : a.ix.chrom_id[i2])) return false;
 	const int64_t sl = right - left;
 	if (sl < rlen) return false;
 	const int slen = (int)sl;

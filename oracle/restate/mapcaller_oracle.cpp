@@ -311,8 +311,10 @@ bool rescue_window(State& S, const std::vector<Kmer>& rk, int rlen, i64 left, i6
 {
 	if (right > S.ix.G2) right = S.ix.G2;
 	int i1 = chrom_lb(S.ix, left), i2 = chrom_lb(S.ix, right);
-	if (i1 >= (int)S.ix.chrom_end.size() || i2 >= (int)S.ix.chrom_end.size()) return false;   // reference: undefined (end() dereferenced)
-	if (S.ix.chrom_id[i1] != S.ix.chrom_id[i2]) return false;
+	// right == 2G: the reference reads PosChrIdMap.end()->second (src/AlignmentRescue.cpp:62-63), which with GCC's layout of the
+	// globals of src/main.cpp is the zeroed first word of the next map, i.e. chromosome id 0 (pinned against oracle/_ref)
+	if (i1 >= (int)S.ix.chrom_end.size()) return false;
+	if (S.ix.chrom_id[i1] != (i2 >= (int)S.ix.chrom_end.size() ? 0 : S.ix.chrom_id[i2])) return false;
 	const i64 slen = right - left;
 	if (slen < rlen) return false;
 	// window k-mers; positions before the start of RefSequence (left < 0) hold no usable text
