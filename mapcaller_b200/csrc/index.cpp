@@ -21,6 +21,8 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <functional>
+#include <array>
 #include <vector>
 
 void mc_set_error(const char* fmt, ...);
@@ -141,12 +143,38 @@ int build_core(mc_index* ix, const uint8_t* fwd, int64_t G, int n_threads)
 {
 	const int64_t N = 2 * G;
 	PackedText t; t.n = N; t.w.assign((N + 31) / 32 + 2, 0);
-	auto put = [&](int64_t i, int c) { t.w[i >> 5] |= (uint64_t)c << ((~i & 31) << 1); };
+	if (n_threads < 1) n_threads = 1;
+	// every helper below cuts its index range into n_threads contiguous pieces
+	auto parallel = [&](int64_t n_items, const std::function<void(int, int64_t, int64_t)>& fn) {
+		const int T = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_items / 4096));
+		std::vector<std::thread> th;
+		for (int k = 0; k < T; k++)
+		{
+			const int64_t b = n_items * k / T, e = n_items * (k + 1) / T;
+			if (k + 1 < T) th.emplace_back(fn, k, b, e); else fn(k, b, e);
+		}
+		for (auto& x : th) x.join();
+	};
+	// packed text: word k holds positions 32k .. 32k+31 of forward + reverse complement (one writer per word)
 	uint64_t L2[5] = {0, 0, 0, 0, 0};
-	for (int64_t i = 0; i < G; i++)
 	{
-		int c = fwd[i] & 3; put(i, c); put(N - 1 - i, 3 - c);
-		L2[c + 1]++; L2[3 - c + 1]++;
+		std::vector<std::array<uint64_t, 4> > cnt((size_t)n_threads, std::array<uint64_t, 4>{{0, 0, 0, 0}});
+		parallel((N + 31) / 32, [&](int tid, int64_t w0, int64_t w1) {
+			std::array<uint64_t, 4> c{{0, 0, 0, 0}};
+			for (int64_t k = w0; k < w1; k++)
+			{
+				uint64_t word = 0;
+				const int64_t p1 = std::min<int64_t>(N, 32 * k + 32);
+				for (int64_t p = 32 * k; p < p1; p++)
+				{
+					const int sym = p < G ? (fwd[p] & 3) : 3 - (fwd[N - 1 - p] & 3);
+					word |= (uint64_t)sym << ((~p & 31) << 1); c[sym]++;
+				}
+				t.w[k] = word;
+			}
+			cnt[tid] = c;
+		});
+		for (auto& c : cnt) for (int k = 0; k < 4; k++) L2[k + 1] += c[k];
 	}
 	for (int c = 0; c < 4; c++) L2[c + 1] += L2[c];
 
@@ -166,23 +194,54 @@ int build_core(mc_index* ix, const uint8_t* fwd, int64_t G, int n_threads)
 	const uint64_t n_occ = (uint64_t)(N + 127) / 128 + 1;
 	ix->bwt_store.assign(((uint64_t)(N + 15) >> 4) + n_occ * 8, 0);
 	uint32_t* out = ix->bwt_store.data();
-	uint64_t primary = 0, c4[4] = {0, 0, 0, 0}, k = 0; // k counts symbols emitted (the $ row is skipped)
-	uint64_t w = 0; // write cursor in words
-	auto emit = [&](int sym) {
-		if ((k & 127) == 0) { memcpy(out + w, c4, 32); w += 8; }
-		if ((k & 15) == 0) w++;
-		out[w - 1] |= (uint32_t)sym << ((~k & 15) << 1);
-		c4[sym]++; k++;
-	};
-	emit(t.base(N - 1));
-	for (int64_t r = 1; r <= N; r++)
+	// the row that holds the whole text ($ in its BWT column) is skipped: symbol k of the BWT string belongs to row k
+	// below it and to row k + 1 from it on
+	uint64_t primary = 0;
 	{
-		uint64_t pos = (uint64_t)sa[r - 1];
-		if (pos == 0) { primary = (uint64_t)r; continue; }
-		emit(t.base((int64_t)pos - 1));
+		std::vector<uint64_t> found((size_t)n_threads, 0);
+		parallel(N, [&](int tid, int64_t r0, int64_t r1) { for (int64_t r = r0; r < r1; r++) if (sa[r] == 0) found[tid] = (uint64_t)r + 1; });
+		for (uint64_t f : found) if (f) primary = f;
 	}
-	memcpy(out + w, c4, 32); w += 8;
-	if (w != ix->bwt_store.size() || k != (uint64_t)N) { mc_set_error("index build: inconsistent bwt size"); return MC_ERR_ARG; }
+	auto symbol = [&](uint64_t k) -> int {
+		if (k == 0) return t.base(N - 1);
+		const uint64_t r = k < primary ? k : k + 1;
+		return t.base((int64_t)sa[r - 1] - 1);
+	};
+	// blocks of 128 symbols: 8 words of running counts, then 8 words of symbols; a last record of counts closes the string.
+	// Two passes over contiguous block ranges: symbol counts per range, then the ranges are written with their start counts.
+	const int64_t n_blocks = (N + 127) / 128;
+	{
+		std::vector<std::array<uint64_t, 4> > cnt((size_t)n_threads, std::array<uint64_t, 4>{{0, 0, 0, 0}});
+		std::vector<std::pair<int64_t, int64_t> > range((size_t)n_threads, std::make_pair((int64_t)0, (int64_t)0));
+		parallel(n_blocks, [&](int tid, int64_t b0, int64_t b1) {
+			std::array<uint64_t, 4> c{{0, 0, 0, 0}};
+			const uint64_t k1 = std::min<uint64_t>((uint64_t)N, (uint64_t)b1 * 128);
+			for (uint64_t k = (uint64_t)b0 * 128; k < k1; k++) c[symbol(k)]++;
+			cnt[tid] = c; range[tid] = std::make_pair(b0, b1);
+		});
+		std::vector<std::array<uint64_t, 4> > start((size_t)n_threads);
+		uint64_t run[4] = {0, 0, 0, 0};
+		for (int k = 0; k < n_threads; k++) { for (int c = 0; c < 4; c++) { start[k][c] = run[c]; run[c] += cnt[k][c]; } }
+		parallel(n_blocks, [&](int tid, int64_t b0, int64_t b1) {
+			uint64_t c4[4] = {start[tid][0], start[tid][1], start[tid][2], start[tid][3]};
+			if (range[tid].first != b0 || range[tid].second != b1) return;   // cannot happen: same cut as the counting pass
+			for (int64_t b = b0; b < b1; b++)
+			{
+				uint32_t* rec = out + 16 * b;
+				memcpy(rec, c4, 32);
+				const uint64_t k1 = std::min<uint64_t>((uint64_t)N, (uint64_t)b * 128 + 128);
+				for (uint64_t k = (uint64_t)b * 128; k < k1; k++)
+				{
+					const int sym = symbol(k);
+					rec[8 + ((k & 127) >> 4)] |= (uint32_t)sym << ((~k & 15) << 1);
+					c4[sym]++;
+				}
+			}
+		});
+		const uint64_t w = 8 * (uint64_t)n_blocks + ((uint64_t)(N + 15) >> 4);
+		memcpy(out + w, run, 32);
+		if (w + 8 != ix->bwt_store.size()) { mc_set_error("index build: inconsistent bwt size"); return MC_ERR_ARG; }
+	}
 
 	const uint64_t n_sa = ((uint64_t)N + 32) / 32;
 	ix->sa_store.assign(n_sa, 0);
@@ -232,7 +291,7 @@ int mc_index_build_gpu(const uint8_t* fwd_codes, int64_t genome_size, int32_t n_
 	if (genome_size <= 0 || 2 * genome_size >= (1ll << 32) - 2) { mc_set_error("mc_index_build_gpu: texts of 2^32 symbols and more are sorted on the host (mc_index_build)"); return MC_ERR_ARG; }
 	if (device < 0) { mc_set_error("mc_index_build_gpu: bad device"); return MC_ERR_ARG; }
 	g_sort_device = device;
-	const int rc = mc_index_build(fwd_codes, genome_size, n_chrom, chrom_len, chrom_name, 1, out);
+	const int rc = mc_index_build(fwd_codes, genome_size, n_chrom, chrom_len, chrom_name, 0, out);   // host threads for packing and the BWT string
 	g_sort_device = -1;
 	return rc;
 #endif
