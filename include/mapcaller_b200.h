@@ -143,7 +143,10 @@ typedef struct {
 /* Replaces the body of ReadMapping() (reference src/ReadMapping.cpp:416-646) for one batch:
  * seeding, clustering, pairing, rescue, gapped fills, scoring, pair statistics and the profile
  * update, bit-identical to a single reference thread processing the same reads in order.
- * Host batches of >= 400 k reads travel in four pieces and are seeded piece by piece while the rest is on the wire. */
+ * Host batches of >= 400 k reads travel in four pieces and are seeded piece by piece while the rest is on the wire.
+ * Every batch but the last of a library must be a whole number of 200-read chunks (MC_CHUNK_READS): the reference cuts the
+ * library into chunks from its start, and a batch that ends inside one is taken as the end (a later batch is refused until
+ * mc_reset). */
 int mc_map_batch(mc_ctx *ctx, const mc_batch_in *in, mc_batch_out *out);
 
 /* Page-locked host memory for batch inputs: reads placed here are DMA-ed to the GPU directly, pageable memory is

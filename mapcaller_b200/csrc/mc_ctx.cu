@@ -195,6 +195,7 @@ struct mc_ctx {
 	// sequential state
 	mc_totals tot;
 	bool discord_init = false; int64_t discord_gpos = 0, discord_dist = 0;
+	bool library_closed = false;   // a batch that was not a whole number of 200-read chunks has been mapped: only the last batch of a library may be
 	std::vector<mc_site_rec> inv_sites, tnl_sites;
 	// finalize products
 	std::vector<mc_indel_rec> ind_out; std::vector<uint8_t> ind_seq_out; std::vector<mc_breakpoint_rec> bp_out;
@@ -345,7 +346,7 @@ int mc_reset(mc_ctx* c)
 	}
 	bad |= dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream) || dev_sync(c->stream);
 	memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = 1000;
-	c->inv_sites.clear(); c->tnl_sites.clear(); c->discord_gpos = c->discord_dist = 0;
+	c->inv_sites.clear(); c->tnl_sites.clear(); c->discord_gpos = c->discord_dist = 0; c->library_closed = false;
 	return bad ? MC_ERR_CUDA : MC_OK;
 }
 
@@ -550,6 +551,9 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	const int64_t n_pairs = paired ? n / 2 : 0;
 	const int64_t n_chunks = (n + MC_CHUNK_READS - 1) / MC_CHUNK_READS;
 	memset(out, 0, sizeof(*out));
+	// the reference cuts the library into 200-read chunks from its start; a batch that ends inside a chunk can only be the last
+	if (n > 0 && c->library_closed && !ordered_mode(c)) { mc_set_error("mc_map_batch: the previous batch was not a multiple of %d reads, which ends the library (mc_reset starts a new one)", MC_CHUNK_READS); return MC_ERR_ARG; }
+	if (n % MC_CHUNK_READS) c->library_closed = true;
 	if (n == 0 && ordered_mode(c)) { mc_set_error("mc_map_batch: with the ordered multi-GPU exchange every rank has to pass reads in every call (mc_comm_init)"); return MC_ERR_ARG; }
 	if (n == 0) return MC_OK;
 
