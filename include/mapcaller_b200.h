@@ -246,6 +246,7 @@ typedef struct {
     int64_t profile_columns;  /* MappingRecord_t columns the reference's pile-up update touches */
     int64_t profile_atomics;  /* atomic updates the device profile actually needed for them */
     int64_t kernel_launches;
+    double ms_reduce;         /* device time of mc_profile_allreduce (multi-GPU), CUDA events on the context's stream */
 } mc_stats;
 int mc_get_stats(const mc_ctx *ctx, mc_stats *out);   /* accumulated since create / last reset */
 int mc_reset_stats(mc_ctx *ctx);

@@ -55,7 +55,7 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile",
                                            "ms_h2d", "ms_d2h", "ms_total")] + \
                [(k, C.c_int64) for k in ("seed_blocks", "locate_blocks", "sa_reads", "dp_cells", "dp_tasks",
-                                          "profile_columns", "profile_atomics", "kernel_launches")]
+                                          "profile_columns", "profile_atomics", "kernel_launches")] + [("ms_reduce", C.c_double)]
 
 
 READ_DT = np.dtype([("score", "<i4"), ("sub_score", "<i4"), ("best_idx", "<i4"), ("cand_begin", "<i4"), ("n_cand", "<i4"), ("rlen", "<i4")])

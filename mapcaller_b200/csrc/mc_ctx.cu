@@ -154,7 +154,7 @@ struct HBuf {
 	template <class T> T* as() const { return (T*)p; }
 };
 
-enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_COUNT };
+enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_RED0, EV_RED1, EV_COUNT };
 
 struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask, rwin; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
@@ -1297,6 +1297,7 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	const bool dbg = getenv("MC_DEBUG") != nullptr;
 	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t_begin = now();
+	ev_record(&c->ev[EV_RED0], s);
 	if (c->d_comm_small.reserve(8 * (7 * c->comm_size + 32))) return MC_ERR_CUDA;
 	long long* d_tot = c->d_comm_small.as<long long>() + 6 * c->comm_size + 8;
 	long long t[5] = {c->tot.total_reads, c->tot.total_mapped, c->tot.total_paired, c->tot.total_distance, c->tot.read_length_sum};
@@ -1384,6 +1385,9 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 		inv.insert(inv.end(), p, p + cnt[4 * n + 2 * r]); tnl.insert(tnl.end(), p + cnt[4 * n + 2 * r], p + cnt[4 * n + 2 * r] + cnt[4 * n + 2 * r + 1]);
 	}
 	c->inv_sites = inv; c->tnl_sites = tnl;
+	ev_record(&c->ev[EV_RED1], s);
+	if (dev_sync(s)) return MC_ERR_CUDA;
+	c->stats.ms_reduce += ev_ms(&c->ev[EV_RED0], &c->ev[EV_RED1]);
 	const size_t mine_bytes = my_bp * 8 + my_ind * sizeof(mc_indel_rec) + my_seq;
 	if (dbg) fprintf(stderr, "[mc] rank %d allreduce: counters %.3f ms, records %.3f ms (%zu bytes mine)\n", c->comm_rank, t_reduced - t_begin, now() - t_reduced, mine_bytes);
 	return MC_OK;
