@@ -229,6 +229,22 @@ int mc_ingest_fastq(mc_ctx *ctx, const mc_fastq_in *in, int32_t slot, mc_fastq_o
  * codes: concatenated 0..4 codes, off[n+1]; start[n].  out_len/out_freq[n]; out_loc[n*MC_MAX_OCC]. */
 int mc_bwt_search_batch(mc_ctx *ctx, int64_t n, const uint8_t *codes, const int64_t *off, const int32_t *start,
                         int32_t *out_len, int32_t *out_freq, uint64_t *out_loc);
+/* IdentifySimplePairs + SimplePairClustering (reference src/ReadMapping.cpp:125-226) for n independent reads, taken as they
+ * are (no mate reversal): per read its simple pairs sorted by (PosDiff, rPos) - the sentinel left out - and its candidate
+ * clusters as [pair_begin, pair_end) slices of that list (for a tandem-repeat cluster: the best equal-PosDiff run).
+ * The arrays are the library's, valid until the next call on the context. */
+typedef struct { int64_t gPos; int32_t rPos, len; } mc_simple_pair;
+typedef struct { int32_t score, pair_begin, pair_end; } mc_cluster;
+typedef struct {
+    int64_t n_reads;
+    const int64_t *pair_off;        /* n_reads + 1: read r owns pairs [pair_off[r], pair_off[r] + n_pairs[r]) */
+    const int32_t *n_pairs;         /* n_reads */
+    const mc_simple_pair *pairs;
+    const int64_t *cluster_off;     /* n_reads + 1 (same spacing as pair_off) */
+    const int32_t *n_clusters;      /* n_reads */
+    const mc_cluster *clusters;     /* pair_begin / pair_end index `pairs` directly */
+} mc_seed_cluster_out;
+int mc_seed_cluster_batch(mc_ctx *ctx, const mc_batch_in *in, mc_seed_cluster_out *out);
 /* nw_alignment / ksw2_alignment (reference src/nw_alignment.cpp:18, src/ksw2_alignment.cpp:250) for n
  * independent problems.  s1/s2 concatenated ASCII with offsets; out1/out2 receive the gapped strings at
  * out_off[i] (caller provides out_off[i+1]-out_off[i] >= len1+len2); out_len[i] = aligned length. */

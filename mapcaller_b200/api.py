@@ -112,6 +112,7 @@ def lib():
         L.mc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.mc_align_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 8
         L.mc_bwt_search_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.mc_seed_cluster_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.c_void_p]
         _lib = L
     return _lib
 
@@ -286,6 +287,27 @@ class Context:
         _check(lib().mc_bwt_search_batch(self._h, n, codes.ctypes.data, off.ctypes.data, start.ctypes.data, ln.ctypes.data, fr.ctypes.data,
                                          loc.ctypes.data), "mc_bwt_search_batch")
         return ln, fr, [np.sort(loc[i, :fr[i]]) for i in range(n)]
+
+    def seed_cluster_batch(self, seq: np.ndarray, off: np.ndarray):
+        """IdentifySimplePairs + SimplePairClustering per read (taken as given): list of (pairs, clusters) with
+        pairs = [(rPos, gPos, len)] sorted by (PosDiff, rPos) and clusters = [(score, [(rPos, gPos, len)])]."""
+        b, keep = self._batch(seq, off)
+        out = (C.c_int64 * 7)()
+        _check(lib().mc_seed_cluster_batch(self._h, C.byref(b), out), "mc_seed_cluster_batch")
+        n = int(out[0])
+        if n == 0:
+            return []
+        poff = _view(out[1], n + 1, np.dtype("<i8")); npair = _view(out[2], n, np.dtype("<i4")); nclu = _view(out[5], n, np.dtype("<i4"))
+        total = int(poff[n])
+        pairs = _view(out[3], total, np.dtype([("gPos", "<i8"), ("rPos", "<i4"), ("len", "<i4")]))
+        clus = _view(out[6], total, np.dtype([("score", "<i4"), ("b", "<i4"), ("e", "<i4")]))
+        res = []
+        for r in range(n):
+            o = int(poff[r])
+            ps = [(int(p["rPos"]), int(p["gPos"]), int(p["len"])) for p in pairs[o:o + int(npair[r])]]
+            cs = [(int(c["score"]), [(int(p["rPos"]), int(p["gPos"]), int(p["len"])) for p in pairs[int(c["b"]):int(c["e"])]]) for c in clus[o:o + int(nclu[r])]]
+            res.append((ps, cs))
+        return res
 
     def totals(self) -> dict:
         t = Totals()

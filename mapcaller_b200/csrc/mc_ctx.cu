@@ -191,6 +191,8 @@ struct mc_ctx {
 	// pinned host staging
 	HBuf h_in_seq, h_in_off, h_seed_off, h_small, h_chunk, h_chunk_lo, h_chunk_hi, h_pairs, h_reads, h_cands, h_frags, h_aln, h_misc;
 	std::vector<mc_read_out> reads_out; std::vector<mc_cand_out> cands_out;
+	// results of mc_seed_cluster_batch
+	std::vector<int64_t> sc_pair_off; std::vector<int32_t> sc_npairs, sc_nclusters; std::vector<SPair> sc_pairs; std::vector<Cand> sc_clusters;
 	std::vector<mc_chunk_out> chunks_final;
 	// sequential state
 	mc_totals tot;
@@ -1393,6 +1395,65 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	return MC_OK;
 }
 #endif
+
+// Operator-level entry: seeding, locate and clustering of a batch (the front of run_batch), results back to the host.
+int mc_seed_cluster_batch(mc_ctx* c, const mc_batch_in* in, mc_seed_cluster_out* out)
+{
+	if (!c || !in || !out) { mc_set_error("mc_seed_cluster_batch: null argument"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	memset(out, 0, sizeof(*out));
+	const mc_stream_t s = c->stream;
+	const int32_t paired_saved = c->prm.paired;
+	c->prm.paired = 0;                                   // staging must not insist on an even number of reads
+	int rc = stage_reads(c, in, c->cur, s, 1);
+	c->prm.paired = paired_saved;
+	if (rc) return rc;
+	Staged& st = c->cur;
+	const int64_t n = st.n_reads;
+	out->n_reads = n;
+	if (n == 0) return MC_OK;
+	PipeArgs a; memset(&a, 0, sizeof(a));
+	a.ix = c->ix; a.pr.paired = 0; a.pr.max_pos_diff = c->prm.max_pos_diff;
+	a.st = c->d_stats.as<DevStats>(); a.n_reads = n; a.seq = st.seq.as<uint8_t>() - st.base; a.roff = st.roff.as<int64_t>(); a.seed_off = st.seed_off.as<int64_t>();
+	a.n_slots = st.n_slots;
+	int bad = c->d_slot_freq.reserve(st.n_slots * 4) || c->d_seeds.reserve(st.n_slots * sizeof(Seed)) || c->d_slot_loc.reserve((st.n_slots + 1) * 8) || c->d_scan.reserve(device_scan_scratch_bytes(st.n_slots));
+	bad |= c->d_cand_off.reserve((n + 1) * 4) || c->d_rflag.reserve(n + 1) || c->d_npair.reserve(n * 4) || c->d_ncand0.reserve(n * 4);
+	if (bad) return MC_ERR_CUDA;
+	a.slot_freq = c->d_slot_freq.as<uint32_t>(); a.seeds = c->d_seeds.as<Seed>(); a.slot_loc = c->d_slot_loc.as<int64_t>();
+	a.cand_off = c->d_cand_off.as<int32_t>(); a.rflag = c->d_rflag.as<uint8_t>(); a.npair = c->d_npair.as<int32_t>(); a.ncand0 = c->d_ncand0.as<int32_t>();
+	bad |= dev_zero(c->d_slot_freq.p, st.n_slots * 4, s) || dev_zero(c->d_stats.p, sizeof(DevStats) - 2 * sizeof(mc_u64), s) || dev_d2d(&c->d_stats.as<DevStats>()->overflow, st.flag.p, 8, s);
+	launch_seed(a, 0, n, s);
+	device_scan_u32(a.slot_freq, c->d_slot_loc.as<int64_t>(), st.n_slots, c->d_scan.as<int64_t>(), s);
+	int64_t* h_small = c->h_small.as<int64_t>();
+	bad |= dev_d2h(h_small, c->d_slot_loc.as<int64_t>() + st.n_slots, 8, s) || dev_sync(s);
+	if (bad) return MC_ERR_CUDA;
+	const int64_t n_locs = h_small[0];
+	a.n_locs = n_locs;
+	if (n_locs >= 0x7fffffffll) { mc_set_error("mc_seed_cluster_batch: batch too large; split it"); return MC_ERR_ARG; }
+	bad |= c->d_pairs.reserve((size_t)(n_locs + 1) * sizeof(SPair)) || c->d_cands.reserve((size_t)(n_locs + 1) * sizeof(Cand));
+	if (bad) return MC_ERR_CUDA;
+	a.pairs = c->d_pairs.as<SPair>(); a.pair_cap = n_locs; a.cands = c->d_cands.as<Cand>();
+	launch_expand(a, st.n_slots, s);
+	launch_locate(a, n_locs, s);
+	launch_cluster(a, n, s);
+	// back to the host: the per-read offsets are slot_loc[seed_off[r]] (pairs and, in single-end layout, clusters alike)
+	std::vector<int64_t> seed_off((size_t)n + 1), slot_loc((size_t)st.n_slots + 1);
+	c->sc_pair_off.assign((size_t)n + 1, 0); c->sc_npairs.resize((size_t)n); c->sc_nclusters.resize((size_t)n);
+	c->sc_pairs.resize((size_t)n_locs + 1); c->sc_clusters.resize((size_t)n_locs + 1);
+	mc_u64 flag = 0;
+	bad |= dev_d2h(seed_off.data(), st.seed_off.p, (size_t)(n + 1) * 8, s) || dev_d2h(slot_loc.data(), c->d_slot_loc.p, (size_t)(st.n_slots + 1) * 8, s);
+	bad |= dev_d2h(c->sc_npairs.data(), c->d_npair.p, (size_t)n * 4, s) || dev_d2h(c->sc_nclusters.data(), c->d_ncand0.p, (size_t)n * 4, s);
+	bad |= dev_d2h(c->sc_pairs.data(), c->d_pairs.p, (size_t)n_locs * sizeof(SPair), s) || dev_d2h(c->sc_clusters.data(), c->d_cands.p, (size_t)n_locs * sizeof(Cand), s);
+	bad |= dev_d2h(&flag, &c->d_stats.as<DevStats>()->overflow, 8, s) || dev_sync(s);
+	if (bad) return MC_ERR_CUDA;
+	if (flag) { mc_set_error("mc_seed_cluster_batch: a read is longer than %d bases (or the offsets decrease)", MC_MAX_RLEN); return MC_ERR_ARG; }
+	for (int64_t r = 0; r <= n; r++) c->sc_pair_off[(size_t)r] = slot_loc[(size_t)seed_off[(size_t)r]];
+	out->pair_off = c->sc_pair_off.data(); out->n_pairs = c->sc_npairs.data(); out->pairs = (const mc_simple_pair*)c->sc_pairs.data();
+	out->cluster_off = c->sc_pair_off.data(); out->n_clusters = c->sc_nclusters.data(); out->clusters = (const mc_cluster*)c->sc_clusters.data();
+	return MC_OK;
+}
 
 // Operator-level entry: n independent BWT_Search queries through the extension / locate primitives the pipeline uses.
 int mc_bwt_search_batch(mc_ctx* c, int64_t n, const uint8_t* codes, const int64_t* off, const int32_t* start, int32_t* out_len, int32_t* out_freq, uint64_t* out_loc)

@@ -189,3 +189,26 @@ def sites(which: int):
     blob = _take(lib().mcref_sites(which, C.byref(n)), n)
     a = np.frombuffer(blob, dtype=np.int64).reshape(-1, 2)
     return [(int(x), int(y)) for x, y in a]
+
+
+def seed_cluster(seq: bytes):
+    """IdentifySimplePairs + SimplePairClustering of the reference for one read (mcref_seed_cluster): (pairs, clusters) with
+    pairs = [(rPos, gPos, len)] in the reference's sorted order and clusters = [(score, [(rPos, gPos, len)])]."""
+    import struct
+    n = C.c_int64()
+    p = lib().mcref_seed_cluster(seq, len(seq), C.byref(n))
+    b = _take(p, n)
+    o = 0
+    ns = struct.unpack_from("<i", b, o)[0]; o += 4
+    sp = []
+    for _ in range(ns):
+        r, g, l = struct.unpack_from("<iqi", b, o); o += 16; sp.append((r, g, l))
+    nc = struct.unpack_from("<i", b, o)[0]; o += 4
+    cv = []
+    for _ in range(nc):
+        sc, nf = struct.unpack_from("<ii", b, o); o += 8
+        fr = []
+        for _ in range(nf):
+            r, g, l = struct.unpack_from("<iqi", b, o); o += 16; fr.append((r, g, l))
+        cv.append((sc, fr))
+    return sp, cv

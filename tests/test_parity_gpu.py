@@ -282,6 +282,28 @@ def test_bwt_search_operator_matches_oracle(built, wide):
     assert n_hits > 1000
 
 
+@pytest.mark.skipif(not pu.have_ref(), reason="oracle/_ref not on this box")
+def test_seed_cluster_operator_matches_reference(built):
+    """mc_seed_cluster_batch against the reference's own IdentifySimplePairs + SimplePairClustering (src/ReadMapping.cpp:125,194)
+    read by read: the sorted simple pairs and the candidate clusters (scores, members, tandem-repeat resolution)."""
+    import ref_oracle as ro
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=9, n_pairs=1500, genome_len=60000, sv=5.0, n_dup=30, tandem=20, n_rate=0.004, contigs=2)
+    ix = pu.build_index(case)
+    seq, off = case["seq"], case["off"]
+    n = len(off) - 1
+    with api.Context(ix, paired=1) as ctx:
+        got = ctx.seed_cluster_batch(seq, off)
+    with tempfile.TemporaryDirectory() as td:
+        ix.save(os.path.join(td, "idx")); ro.load(os.path.join(td, "idx"))
+        n_clusters = 0
+        for r in range(n):
+            want = ro.seed_cluster(bytes(seq[off[r]:off[r + 1]]))
+            assert got[r] == want, "read %d" % r
+            n_clusters += len(want[1])
+    assert n_clusters > n
+
+
 def test_gapped_fill_kernel_matches_oracle(built):
     """mc_align_batch (the DP kernel on its own) vs the oracle's nw / ksw2 on random, mutated and tandem inputs."""
     from mapcaller_b200 import api
