@@ -164,6 +164,7 @@ MC_HD void alnprep_body(int64_t r, bool live, const PipeArgs& a)
 // ------------------------------------------------------------------------------------------------
 MC_HD void piece_body(int64_t t, int lane, int nl, const PipeArgs& a)
 {
+	if (a.st->overflow) return;                      // an arena ran out in alnprep: queue slots may be unwritten, the attempt is repeated
 	const int32_t fi = a.ptask[a.ptask_begin + t];   // the caller bounds t by the list's cursor
 	const mc_frag_out x = a.frags[fi];
 	const uint8_t* rs = a.seq + a.roff[x.pad];
