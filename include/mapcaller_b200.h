@@ -186,6 +186,35 @@ typedef struct { int64_t gPos, dist; } mc_site_rec;
 /* kind 0 = InversionSiteVec, 1 = TranslocationSiteVec, sorted by gPos as the thread-end merge does */
 int mc_profile_sites(mc_ctx *ctx, int32_t kind, const mc_site_rec **recs, int64_t *n_recs);
 
+/* ---- variant-calling scan (reference src/VariantCalling.cpp:106-120 CalBlockReadDepth, :550-680 IdentifyVariants,
+ *      :60-98 GetAreaIndFrequency, :523-548 DetermineGenotype) over the device-resident profile, without downloading
+ *      the 16-byte-per-column MappingRecordArr.  The columns are scanned on the GPU in blocks of 100 (the reference's
+ *      BlockSize): block depths, gap / duplication runs and gVCF segments are carried across blocks with device scans.
+ *      The +-5-column indel-window join runs over the aggregated indel records of mc_profile_indels() (sparse, host).
+ *      Output = the reference's VariantVec after IdentifyVariants (+ RemoveConsecutiveGenomicVariant under gvcf), sorted
+ *      by (gPos, VarType) like CompByVarPos; structural variants (IdentifyInversions / IdentifyTranslocations) and the
+ *      VCF text stay with the caller, who has everything they need in `record` and `block_depth`.
+ *      Fields the reference leaves stale for a type (e.g. AD_alt of a gap record) are 0 here.  DP of gap / dup records is
+ *      the run length truncated to 16 bits exactly as Variant_t::DP does. */
+typedef struct {
+	int32_t min_allele_depth;   /* MinAlleleDepth (-ad), >= 1 */
+	float frequency_thr;        /* FrequencyThr (-maxmm is unrelated; src/main.cpp:183) */
+	int32_t somatic, gvcf, monomorphic, ploidy, min_cnv_size, min_unmapped_size;
+} mc_vc_params;
+void mc_vc_params_default(mc_vc_params *p);   /* src/main.cpp:159-185 */
+enum { MC_VAR_SUB = 0, MC_VAR_INS = 1, MC_VAR_DEL = 2, MC_VAR_CNV = 5, MC_VAR_UMR = 6, MC_VAR_NOR = 10, MC_VAR_MON = 11 };
+typedef struct {
+	int64_t gPos;
+	uint64_t record[2];         /* MappingRecord_t of gPos (as mc_profile_read packs it); 0 for CNV / UMR */
+	int32_t alt_off, alt_len;   /* INS / DEL: ALTstr in the sequence arena of mc_profile_indels(); otherwise 0, 0 */
+	uint16_t DP, AD_ref, AD_alt;
+	uint8_t GenoType, qscore, VarType;
+	char alt[3];                /* SUB: "X" or "X,Y" (unused bytes 0) */
+} mc_variant_rec;
+/* `recs`, `alt_arena` and `block_depth` stay valid until the next mc_variant_scan / mc_profile_indels / mc_reset on ctx. */
+int mc_variant_scan(mc_ctx *ctx, const mc_vc_params *vp, const mc_variant_rec **recs, int64_t *n_recs,
+                    const uint8_t **alt_arena, const int32_t **block_depth, int64_t *n_blocks);
+
 /* Multi-GPU (one context per GPU, one process per GPU): reads shard across the ranks, every rank holds a full index
  * replica.  mc_comm_unique_id() on rank 0 -> ship the 128 bytes to the other ranks -> mc_comm_init() on every rank.
  *

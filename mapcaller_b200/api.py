@@ -51,6 +51,18 @@ class Totals(C.Structure):
                 ("total_distance", C.c_int64), ("read_length_sum", C.c_int64), ("avg_dist", C.c_uint32), ("pad", C.c_uint32)]
 
 
+class VcParams(C.Structure):
+    """mc_vc_params (include/mapcaller_b200.h): thresholds of the variant-calling scan."""
+    _fields_ = [("min_allele_depth", C.c_int32), ("frequency_thr", C.c_float)] + \
+               [(k, C.c_int32) for k in ("somatic", "gvcf", "monomorphic", "ploidy", "min_cnv_size", "min_unmapped_size")]
+
+
+VARIANT_DT = np.dtype([("gPos", "<i8"), ("rec0", "<u8"), ("rec1", "<u8"), ("alt_off", "<i4"), ("alt_len", "<i4"),
+                       ("DP", "<u2"), ("AD_ref", "<u2"), ("AD_alt", "<u2"), ("GenoType", "u1"), ("qscore", "u1"),
+                       ("VarType", "u1"), ("alt", "S3"), ("pad", "V4")])
+assert VARIANT_DT.itemsize == 48
+
+
 class Stats(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile",
                                            "ms_h2d", "ms_d2h", "ms_total")] + \
@@ -107,6 +119,10 @@ def lib():
         L.mc_profile_indels.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
         L.mc_profile_breakpoints.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_sites.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.mc_vc_params_default.argtypes = [C.POINTER(VcParams)]
+        L.mc_vc_params_default.restype = None
+        L.mc_variant_scan.argtypes = [C.c_void_p, C.POINTER(VcParams), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
         L.mc_comm_unique_id.argtypes = [C.c_void_p]
         L.mc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
@@ -376,6 +392,27 @@ class Context:
             s = C.string_at(arena.value + int(x["seq_off"]), int(x["len"]))
             out[int(x["kind"])].append((int(x["pos"]), s, int(x["count"])))
         return out
+
+    def variant_scan(self, **kw):
+        """CalBlockReadDepth + IdentifyVariants of the reference (src/VariantCalling.cpp:106-120, 550-680) on the device.
+        -> (list of dicts {gPos, VarType, DP, AD_ref, AD_alt, GenoType, qscore, alt, record}, block depths int32)."""
+        vp = VcParams()
+        lib().mc_vc_params_default(C.byref(vp))
+        for k, v in kw.items():
+            if not hasattr(vp, k):
+                raise TypeError("unknown variant-scan parameter %r" % k)
+            setattr(vp, k, v)
+        recs, n, arena, depth, nb = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _check(lib().mc_variant_scan(self._h, C.byref(vp), C.byref(recs), C.byref(n), C.byref(arena), C.byref(depth), C.byref(nb)),
+               "mc_variant_scan")
+        r = _view(recs.value, n.value, VARIANT_DT)
+        out = []
+        for x in r:
+            t = int(x["VarType"])
+            alt = C.string_at(arena.value + int(x["alt_off"]), int(x["alt_len"])) if t in (1, 2) else bytes(x["alt"])
+            out.append(dict(gPos=int(x["gPos"]), VarType=t, DP=int(x["DP"]), AD_ref=int(x["AD_ref"]), AD_alt=int(x["AD_alt"]),
+                            GenoType=int(x["GenoType"]), qscore=int(x["qscore"]), alt=alt, record=(int(x["rec0"]), int(x["rec1"]))))
+        return out, _view(depth.value, nb.value, np.dtype("<i4")).copy()
 
     def breakpoints(self):
         recs, n = C.c_void_p(), C.c_int64()

@@ -201,6 +201,7 @@ struct mc_ctx {
 	std::vector<mc_site_rec> inv_sites, tnl_sites;
 	// finalize products
 	std::vector<mc_indel_rec> ind_out; std::vector<uint8_t> ind_seq_out; std::vector<mc_breakpoint_rec> bp_out;
+	std::vector<mc_variant_rec> vc_out; std::vector<int32_t> vc_depth;
 	// stats
 	mc_stats stats; DevStats dstats_last;
 	mc_event_t ev[EV_COUNT];
@@ -1249,6 +1250,116 @@ int mc_profile_sites(mc_ctx* c, int32_t kind, const mc_site_rec** recs, int64_t*
 	std::vector<mc_site_rec>& v = kind == 0 ? c->inv_sites : c->tnl_sites;
 	*recs = v.data(); *n_recs = (int64_t)v.size();
 	return MC_OK;
+}
+
+// ---- variant-calling scan (reference src/VariantCalling.cpp:106-120, 550-680) ---------------------------------
+void mc_vc_params_default(mc_vc_params* p)
+{
+	memset(p, 0, sizeof(*p));
+	p->min_allele_depth = 5; p->frequency_thr = 0.2f; p->ploidy = 2; p->min_cnv_size = 50; p->min_unmapped_size = 50;
+}
+
+// GetAreaIndFrequency (src/VariantCalling.cpp:60-98) for every key of one indel map: recs[i0, i1) are the aggregated
+// records of one kind in (pos, sequence) order, i.e. the iteration order of map<int64_t, map<string, uint16_t>>.
+// A key is a candidate when the window's winner sits on it (the function returns 0 everywhere else).
+static void vc_window_join(const std::vector<mc_indel_rec>& recs, size_t i0, size_t i1, std::vector<VcCand>& out)
+{
+	size_t lo = i0, hi = i0;
+	for (size_t i = i0; i < i1; i++)
+	{
+		const int64_t g = recs[i].pos;
+		if (i > i0 && recs[i - 1].pos == g) continue;
+		while (lo < i1 && recs[lo].pos < g - 5) lo++;
+		while (hi < i1 && recs[hi].pos <= g + 5) hi++;
+		int64_t max_pos = 0; int freq = 0, max_freq = 0, best_len = 0, best_off = 0;
+		for (size_t k = lo; k < hi; k++)
+		{
+			const int cnt = recs[k].count;
+			freq += cnt;
+			if (max_freq < cnt) { max_freq = cnt; best_len = recs[k].len; best_off = recs[k].seq_off; max_pos = recs[k].pos; }
+			else if (max_freq == cnt && recs[k].len > best_len) { best_len = recs[k].len; best_off = recs[k].seq_off; max_pos = recs[k].pos; }
+		}
+		if (max_pos == g) { VcCand c; c.pos = g; c.kind = recs[i].kind; c.freq = freq; c.alt_off = best_off; c.alt_len = best_len; out.push_back(c); }
+	}
+}
+
+int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** recs, int64_t* n_recs, const uint8_t** alt_arena, const int32_t** block_depth, int64_t* n_blocks)
+{
+	if (!c || !vp || !recs || !n_recs || !alt_arena || !block_depth || !n_blocks) { mc_set_error("mc_variant_scan: null argument"); return MC_ERR_ARG; }
+	if (!c->prm.update_profile) { mc_set_error("mc_variant_scan: context was created without update_profile"); return MC_ERR_ARG; }
+	if (vp->min_allele_depth < 1) { mc_set_error("mc_variant_scan: min_allele_depth must be >= 1"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	// indel window winners from the aggregated records (sparse; sorted by (kind, pos, sequence))
+	const mc_indel_rec* ir; int64_t nir; const uint8_t* arena;
+	int rc = mc_profile_indels(c, &ir, &nir, &arena);
+	if (rc != MC_OK) return rc;
+	std::vector<VcCand> cand;
+	{
+		size_t split = 0; while (split < c->ind_out.size() && c->ind_out[split].kind == 0) split++;
+		vc_window_join(c->ind_out, 0, split, cand); vc_window_join(c->ind_out, split, c->ind_out.size(), cand);
+		std::sort(cand.begin(), cand.end(), [](const VcCand& x, const VcCand& y) { return x.pos != y.pos ? x.pos < y.pos : x.kind < y.kind; });
+	}
+	mc_stream_t s = c->stream;
+	DevProfile p; p.base16 = c->d_base16.as<uint32_t>(); p.sdiff = c->d_sdiff.as<int32_t>(); p.cdiff = c->d_cdiff.as<int32_t>(); p.mdiff = c->d_mdiff.as<int32_t>();
+	p.rcount = c->d_rcount.as<uint8_t>();
+	const int64_t G = c->G, nb = (G + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK, nvb = (G + MC_VC_BLOCK - 1) / MC_VC_BLOCK;
+	const int64_t tile_cols = (int64_t)25600 * 640;   // a multiple of MC_PROF_BLOCK and of MC_VC_BLOCK
+	const int64_t n_tiles = (G + tile_cols - 1) / tile_cols;
+	DBuf d_sums, d_depth, d_ng, d_nd, d_ln, d_le, d_lead, d_cnt, d_off, d_scan, d_cand, d_out;
+	DBuf* all[] = {&d_sums, &d_depth, &d_ng, &d_nd, &d_ln, &d_le, &d_lead, &d_cnt, &d_off, &d_scan, &d_cand, &d_out};
+	auto done = [&](int r) { dev_sync(s); for (DBuf* b : all) b->release(); return r; };
+	int bad = d_sums.reserve((size_t)(6 * nb + 8) * 8) || d_depth.reserve((size_t)nvb * 4) || d_ng.reserve((size_t)nvb * 8) || d_nd.reserve((size_t)nvb * 8);
+	bad |= d_ln.reserve((size_t)nvb * 8) || d_le.reserve((size_t)nvb * 8) || d_lead.reserve((size_t)nvb * 4) || d_cnt.reserve((size_t)(nvb + 1) * 4);
+	bad |= d_off.reserve((size_t)(nvb + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(nvb)) || d_cand.reserve((cand.size() + 1) * sizeof(VcCand));
+	bad |= c->d_sort.reserve((size_t)std::min(tile_cols, nb * MC_PROF_BLOCK) * 16);
+	if (bad) return done(MC_ERR_CUDA);
+	if (dev_h2d(d_cand.p, cand.data(), cand.size() * sizeof(VcCand), s)) return done(MC_ERR_CUDA);
+	int64_t* sums = d_sums.as<int64_t>();
+	launch_profsum(p, G, nb, sums, s);
+	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, s);
+	VcArgs a; memset(&a, 0, sizeof(a));
+	a.vp = *vp; if (a.vp.gvcf && a.vp.monomorphic) a.vp.gvcf = 0;   // src/main.cpp:322
+	a.ix = c->ix; a.G = G; a.n_blocks = nvb; a.recs = c->d_sort.as<uint64_t>();
+	a.depth = d_depth.as<int32_t>(); a.last_nongap = d_ng.as<int64_t>(); a.last_nondup = d_nd.as<int64_t>(); a.last_normal = d_ln.as<int64_t>(); a.last_event = d_le.as<int64_t>();
+	a.lead_min = d_lead.as<int32_t>(); a.cnt = d_cnt.as<uint32_t>(); a.off = d_off.as<int64_t>(); a.cand = d_cand.as<VcCand>(); a.n_cand = (int64_t)cand.size();
+	int64_t packed = -1;
+	auto pack = [&](int64_t t) {   // MappingRecord_t image of tile t in d_sort (kept when the genome is a single tile)
+		a.tile_beg = t * tile_cols; a.tile_end = std::min(G, a.tile_beg + tile_cols);
+		if (packed == t) return;
+		launch_profpack(c->ix, p, nb, sums, a.tile_beg / MC_PROF_BLOCK, (a.tile_end + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK, a.tile_beg, a.tile_end, c->d_sort.as<uint64_t>(), s);
+		packed = t;
+	};
+	auto vb0 = [&](int64_t t) { return t * (tile_cols / MC_VC_BLOCK); };
+	auto vb1 = [&](int64_t t) { return std::min(nvb, (t + 1) * (tile_cols / MC_VC_BLOCK)); };
+	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcdepth(a, vb0(t), vb1(t), s); }
+	device_incmax_i64(a.last_nongap, nvb, s); device_incmax_i64(a.last_nondup, nvb, s);
+	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), false, s); }
+	if (a.vp.gvcf) { device_incmax_i64(a.last_normal, nvb, s); device_incmax_i64(a.last_event, nvb, s); }
+	device_scan_u32(a.cnt, d_off.as<int64_t>(), nvb, d_scan.as<int64_t>(), s);
+	int64_t total = 0;
+	if (dev_d2h(&total, d_off.as<int64_t>() + nvb, 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	if (d_out.reserve((size_t)(total + 1) * sizeof(mc_variant_rec))) return done(MC_ERR_CUDA);
+	a.out = d_out.as<mc_variant_rec>();
+	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), true, s); }
+	std::vector<mc_variant_rec> raw((size_t)total);
+	c->vc_depth.resize((size_t)nvb);
+	if (dev_d2h(raw.data(), d_out.p, (size_t)total * sizeof(mc_variant_rec), s) || dev_d2h(c->vc_depth.data(), d_depth.p, (size_t)nvb * 4, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	c->vc_out.clear();
+	for (size_t i = 0; i < raw.size(); i++) if (raw[i].VarType != MC_VAR_NIL) c->vc_out.push_back(raw[i]);
+	// CompByVarPos (src/VariantCalling.cpp:51-55); (gPos, VarType) is unique within one scan
+	std::sort(c->vc_out.begin(), c->vc_out.end(), [](const mc_variant_rec& x, const mc_variant_rec& y) { return x.gPos != y.gPos ? x.gPos < y.gPos : x.VarType < y.VarType; });
+	if (a.vp.gvcf)   // RemoveConsecutiveGenomicVariant (:682-694)
+	{
+		size_t w = 0;
+		for (size_t i = 0; i < c->vc_out.size(); i++)
+			if (!(w > 0 && c->vc_out[w - 1].VarType == MC_VAR_NOR && c->vc_out[i].VarType == MC_VAR_NOR)) c->vc_out[w++] = c->vc_out[i];
+		c->vc_out.resize(w);
+	}
+	*recs = c->vc_out.data(); *n_recs = (int64_t)c->vc_out.size(); *alt_arena = c->ind_seq_out.data();
+	*block_depth = c->vc_depth.data(); *n_blocks = nvb;
+	return done(MC_OK);
 }
 
 // ---- multi-GPU: NCCL over NVLink ------------------------------------------------------------------------

@@ -47,6 +47,9 @@ static void launch_fqlines(const FastqArgs& q, int f, int64_t n, mc_stream_t) { 
 static void launch_fqread(const FastqArgs& q, int64_t n, mc_stream_t) { for (int64_t r = 0; r < n; r++) fqread_body(r, q); }
 static void launch_fqcopy(const FastqArgs& q, int64_t n, mc_stream_t) { for (int64_t r = 0; r < n; r++) fqcopy_body(r, 0, 1, q); }
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for (int64_t q = 0; q < n; q++) bwtsearch_body(q, a); }
+static void launch_vcdepth(const VcArgs& a, int64_t b0, int64_t b1, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcdepth_body(b, a); }
+static void launch_vcscan(const VcArgs& a, int64_t b0, int64_t b1, bool emit, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcscan_body(b, a, emit); }
+static void device_incmax_i64(int64_t* a, int64_t n, mc_stream_t) { for (int64_t i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
 #else
@@ -335,6 +338,41 @@ static void device_scan_u32(const uint32_t* in, int64_t* out, int64_t n, int64_t
 	if (nt > 0) { mc_scan_finish<<<(unsigned)nt, 256, 0, s>>>(in, n, scratch, out); g_launches++; }
 }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t s) { mc_scan_tiles<<<1, 1024, 0, s>>>(a, n, total); g_launches++; }
+__global__ void __launch_bounds__(MC_BLOCK) mc_vcdepth_kernel(const VcArgs a, int64_t b0, int64_t b1)
+{ int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < b1) vcdepth_body(b, a); }
+static void launch_vcdepth(const VcArgs& a, int64_t b0, int64_t b1, mc_stream_t s)
+{ if (b1 > b0) { mc_vcdepth_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, b0, b1); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_vcscan_kernel(const VcArgs a, int64_t b0, int64_t b1, bool emit)
+{ int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < b1) vcscan_body(b, a, emit); }
+static void launch_vcscan(const VcArgs& a, int64_t b0, int64_t b1, bool emit, mc_stream_t s)
+{ if (b1 > b0) { mc_vcscan_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, b0, b1, emit); g_launches++; } }
+// in-place inclusive max-scan (one block walks the array in 1024-element steps, like mc_scan_tiles)
+__global__ void __launch_bounds__(1024) mc_incmax_kernel(int64_t* a, int64_t n)
+{
+	__shared__ int64_t sh[1024];
+	__shared__ int64_t carry;
+	if (threadIdx.x == 0) carry = INT64_MIN;
+	__syncthreads();
+	for (int64_t base = 0; base < n; base += 1024)
+	{
+		const int64_t i = base + threadIdx.x;
+		sh[threadIdx.x] = i < n ? a[i] : INT64_MIN;
+		__syncthreads();
+		for (int o = 1; o < 1024; o <<= 1)
+		{
+			const int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : INT64_MIN;
+			__syncthreads();
+			if (t > sh[threadIdx.x]) sh[threadIdx.x] = t;
+			__syncthreads();
+		}
+		const int64_t v = sh[threadIdx.x] > carry ? sh[threadIdx.x] : carry;
+		if (i < n) a[i] = v;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = v;
+		__syncthreads();
+	}
+}
+static void device_incmax_i64(int64_t* a, int64_t n, mc_stream_t s) { if (n > 0) { mc_incmax_kernel<<<1, 1024, 0, s>>>(a, n); g_launches++; } }
 #include <cub/device/device_radix_sort.cuh>
 static size_t device_sort_scratch_bytes(int64_t n)
 {

@@ -32,6 +32,9 @@ extern uint32_t avgReadLength;
 extern int64_t iTotalReadNum, iTotalMappingNum, iTotalPairedNum, TotalPairedDistance, ReadLengthSum;
 extern int64_t iAlignedBase, iTotalCoverage;
 extern bwtint_t bwt_sa(bwtint_t k);
+// src/VariantCalling.cpp: globals and thread bodies of the per-column scan
+extern int* BlockDepthArr; extern int BlockNum; extern vector<Variant_t> VariantVec;
+extern void* CalBlockReadDepth(void* arg); extern void* IdentifyVariants(void* arg); extern void RemoveConsecutiveGenomicVariant();
 
 namespace {
 
@@ -365,6 +368,37 @@ int mcref_variant_calling(const char* vcf_path)
 	VcfFileName = strdup(vcf_path);
 	VariantCalling();
 	return 0;
+}
+
+// The per-column part of VariantCalling() (src/VariantCalling.cpp:706-717): CalBlockReadDepth, IdentifyVariants on one
+// thread (the reference forces iThreadNum = 1 there) and RemoveConsecutiveGenomicVariant, on the profile the mapping
+// left behind.  Records: int64 gPos, int32 VarType, DP, AD_ref, AD_alt, GenoType, qscore, alt_len, bytes; then int32
+// BlockNum and BlockDepthArr.  Fields the reference leaves stale for a type are serialised as they are.
+uint8_t* mcref_variant_scan(int min_ad, float freq_thr, int somatic, int gvcf, int mono, int ploidy, int min_cnv, int min_gap, int64_t* nbytes)
+{
+	MinAlleleDepth = min_ad; FrequencyThr = freq_thr; bSomatic = somatic != 0; bGVCF = gvcf != 0; bMonomorphic = mono != 0;
+	iPloidy = ploidy; MinCNVsize = min_cnv; MinUnmappedSize = min_gap;
+	if (bGVCF && bMonomorphic) bGVCF = false;   // src/main.cpp:322
+	const int saved = iThreadNum; iThreadNum = 1; int tid = 0;
+	BlockNum = (int)(GenomeSize / 100); if (((int64_t)BlockNum * 100) < GenomeSize) BlockNum += 1;
+	BlockDepthArr = new int[BlockNum]();
+	CalBlockReadDepth(&tid);
+	VariantVec.clear();
+	IdentifyVariants(&tid);
+	if (bGVCF && VariantVec.size() > 0) RemoveConsecutiveGenomicVariant();
+	Blob out;
+	out.put<int64_t>((int64_t)VariantVec.size());
+	for (size_t i = 0; i < VariantVec.size(); i++)
+	{
+		Variant_t& v = VariantVec[i];
+		out.put<int64_t>(v.gPos); out.put<int32_t>(v.VarType); out.put<int32_t>(v.DP); out.put<int32_t>(v.AD_ref); out.put<int32_t>(v.AD_alt);
+		out.put<int32_t>(v.GenoType); out.put<int32_t>(v.qscore); out.put<int32_t>((int32_t)v.ALTstr.size());
+		out.bytes(v.ALTstr.data(), v.ALTstr.size());
+	}
+	out.put<int32_t>(BlockNum);
+	out.bytes(BlockDepthArr, (size_t)BlockNum * 4);
+	delete[] BlockDepthArr; BlockDepthArr = NULL; VariantVec.clear(); iThreadNum = saved;
+	return blob_release(out, nbytes);
 }
 
 void mcref_counters(int64_t out[8])

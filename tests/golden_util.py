@@ -41,5 +41,12 @@ def load(name: str):
     return case, ref
 
 
+def load_vc(name: str):
+    """(parameter sets, [(variant dicts, BlockDepthArr)]) of tests/golden/make_golden_vc.py for golden case `name`."""
+    with open(path("vc_" + name), "rb") as fh:
+        payload = pickle.loads(zlib.decompress(fh.read()))
+    return payload["sets"], [(v, np.asarray(d, dtype=np.int32)) for v, d in payload["vc"]]
+
+
 def available(name: str) -> bool:
     return os.path.exists(path(name))

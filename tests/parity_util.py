@@ -52,6 +52,25 @@ def make_case(kind: str = "small", seed: int = 1, n_pairs: int = 3000, read_len:
     return dict(contigs=list(zip(names, parts)), ref=ref, seq=seq, off=off, params=p, r1=r1, r2=r2)
 
 
+def sparse_case(genome_len: int = 400000, covered: int = 60000, n_pairs: int = 6000, seed: int = 21, contigs: int = 1):
+    """Reads from the first `covered` and the last 40 k bases only: the gap run in between is longer than 65535 columns
+    (Variant_t::DP wraps, src/structure.h:187) and spans thousands of scan blocks."""
+    case = make_case(seed=seed, n_pairs=10, genome_len=genome_len, contigs=contigs, n_dup=2, tandem=1)
+    ref = case["ref"]
+    kw = dict(snp_per_mb=3000, small_indel_per_mb=400, large_indel_per_mb=150, sv_per_mb=0, sv_len=(400, 900))
+    head = sim.mutate(ref[:covered], seed * 31, **kw)[0]
+    tail = sim.mutate(ref[-40000:], seed * 37, **kw)[0]
+    r1, r2 = sim.simulate_pairs(head[3000:], n_pairs, 100, seed=seed + 7)
+    q1, q2 = sim.simulate_pairs(tail[:-3000], n_pairs // 2, 100, seed=seed + 9)
+    case["seq"], case["off"] = sim.interleave(np.concatenate([r1, q1]), np.concatenate([r2, q2]))
+    return case
+
+
+# parameter sets of the variant-calling scan used by the tests (defaults, gVCF, monomorphic, somatic, haploid / low thresholds)
+VC_SETS = [dict(), dict(gvcf=1), dict(monomorphic=1), dict(somatic=1), dict(ploidy=1, min_allele_depth=2, frequency_thr=0.1),
+           dict(min_cnv_size=5, min_unmapped_size=10, gvcf=1)]
+
+
 def build_index(case, threads: int = 0):
     from mapcaller_b200 import api
     codes = sim.encode(case["ref"])
@@ -59,13 +78,14 @@ def build_index(case, threads: int = 0):
     return api.Index.build(codes, [len(s) for _, s in case["contigs"]], [n for n, _ in case["contigs"]], threads)
 
 
-def ref_results(case, index, want_reads: bool = True):
-    """Runs the case through oracle/_ref in a subprocess."""
+def ref_results(case, index, want_reads: bool = True, vc=None):
+    """Runs the case through oracle/_ref in a subprocess; `vc` = list of variant-scan parameter sets to run afterwards."""
     with tempfile.TemporaryDirectory() as td:
         prefix = os.path.join(td, "idx")
         index.save(prefix)
         job = os.path.join(td, "job.npz")
-        np.savez(job, prefix=prefix, seq=case["seq"], off=case["off"], params=np.array(case["params"], dtype=object), want_reads=want_reads)
+        extra = dict(vc=np.array({"sets": list(vc)}, dtype=object)) if vc else {}
+        np.savez(job, prefix=prefix, seq=case["seq"], off=case["off"], params=np.array(case["params"], dtype=object), want_reads=want_reads, **extra)
         outp = os.path.join(td, "out.pkl")
         subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), job, outp], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         with open(outp, "rb") as fh:
@@ -89,7 +109,7 @@ def oracle_results(case, index, want_reads: bool = True):
         return out
 
 
-def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool = True, device: int = 0, **extra):
+def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool = True, device: int = 0, vc=None, **extra):
     from mapcaller_b200 import api
     seq, off = case["seq"], case["off"]
     n = len(off) - 1
@@ -113,7 +133,18 @@ def cuda_results(case, index, batch_reads: int | None = None, want_reads: bool =
         out["tnl"] = sorted(ctx.sites(1), key=lambda x: x[0])
         out["stats"] = ctx.stats()
         out["summary"] = ctx.profile_summary()
+        if vc:
+            out["vc"] = [ctx.variant_scan(**kw) for kw in vc]
     return out
+
+
+def assert_same_variants(mine, ref) -> None:
+    """mc_variant_scan against IdentifyVariants of the unmodified reference, one entry per parameter set."""
+    import ref_oracle as ro
+    assert len(mine["vc"]) == len(ref["vc"])
+    for i, ((mv, md), (rv, rd)) in enumerate(zip(mine["vc"], ref["vc"])):
+        assert np.array_equal(md, rd), "BlockDepthArr differs (set %d)" % i
+        assert ro.variants_equal(mv, rv), "variant records differ (set %d): %d vs %d" % (i, len(mv), len(rv))
 
 
 def _strip_paired(r):

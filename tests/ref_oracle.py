@@ -49,6 +49,8 @@ def lib():
         L.mcref_map.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]
         L.mcref_run_mapping.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
         L.mcref_variant_calling.argtypes = [C.c_char_p]
+        L.mcref_variant_scan.restype = C.c_void_p
+        L.mcref_variant_scan.argtypes = [C.c_int, C.c_float] + [C.c_int] * 6 + [C.POINTER(C.c_int64)]
         L.mcref_counters.argtypes = [C.POINTER(C.c_int64)]
         L.mcref_profile.argtypes = [C.c_int64, C.c_int64, C.c_void_p]
         L.mcref_indels.restype = C.c_void_p
@@ -189,6 +191,45 @@ def sites(which: int):
     blob = _take(lib().mcref_sites(which, C.byref(n)), n)
     a = np.frombuffer(blob, dtype=np.int64).reshape(-1, 2)
     return [(int(x), int(y)) for x, y in a]
+
+
+# fields of Variant_t the reference defines per VarType (the others are stale locals of IdentifyVariants)
+VARIANT_FIELDS = {0: ("DP", "AD_ref", "AD_alt", "GenoType", "qscore", "alt"), 1: ("DP", "AD_ref", "AD_alt", "GenoType", "qscore", "alt"),
+                  2: ("DP", "AD_ref", "AD_alt", "GenoType", "qscore", "alt"), 5: ("DP",), 6: ("DP",), 10: ("DP", "AD_alt", "qscore"),
+                  11: ("DP", "AD_ref", "GenoType", "qscore")}
+
+
+def variant_scan(min_allele_depth=5, frequency_thr=0.2, somatic=0, gvcf=0, monomorphic=0, ploidy=2, min_cnv_size=50,
+                 min_unmapped_size=50):
+    """CalBlockReadDepth + IdentifyVariants (+ RemoveConsecutiveGenomicVariant) of the unmodified reference on the
+    profile its mapping left behind -> (list of dicts like api.Context.variant_scan, BlockDepthArr int32)."""
+    n = C.c_int64()
+    p = lib().mcref_variant_scan(min_allele_depth, frequency_thr, somatic, gvcf, monomorphic, ploidy, min_cnv_size,
+                                 min_unmapped_size, C.byref(n))
+    b = _take(p, n)
+    (nv,) = struct.unpack_from("<q", b, 0); o = 8
+    out = []
+    for _ in range(nv):
+        g, t, dp, ar, aa, gt, q, al = struct.unpack_from("<q7i", b, o); o += 36
+        out.append(dict(gPos=g, VarType=t, DP=dp, AD_ref=ar, AD_alt=aa, GenoType=gt, qscore=q, alt=b[o:o + al])); o += al
+    (nb,) = struct.unpack_from("<i", b, o); o += 4
+    return out, np.frombuffer(b, dtype="<i4", count=nb, offset=o).copy()
+
+
+def variants_equal(mine, ref, limit=5):
+    """Compares two variant lists on (gPos, VarType) and the fields the reference defines for the type."""
+    bad = 0
+    if len(mine) != len(ref):
+        print("variant count", len(mine), len(ref)); bad += 1
+    for a, r in zip(mine, ref):
+        keys = ("gPos", "VarType") + VARIANT_FIELDS.get(r["VarType"], ())
+        av = tuple(a[k].rstrip(b"\0") if k == "alt" else a[k] for k in keys)
+        rv = tuple(r[k] for k in keys)
+        if av != rv:
+            bad += 1
+            if bad <= limit:
+                print("variant differs", dict(zip(keys, av)), dict(zip(keys, rv)))
+    return bad == 0
 
 
 def seed_cluster(seq: bytes):

@@ -23,6 +23,8 @@ def main(job_path: str, out_path: str) -> None:
     ro.lib().mcref_finish_sites()
     out = dict(est=est, counters=ro.counters(), profile=ro.profile(), ins=ro.indels(0), dele=ro.indels(1),
                bp=ro.breakpoints(), inv=ro.sites(0), tnl=ro.sites(1))
+    if "vc" in job.files:   # variant-calling scans of the profile just built, one per parameter set
+        out["vc"] = [ro.variant_scan(**kw) for kw in job["vc"].item()["sets"]]
     if bool(job["want_reads"]):
         out["reads"] = reads
     with open(out_path, "wb") as fh:
