@@ -202,6 +202,7 @@ struct mc_ctx {
 	// finalize products
 	std::vector<mc_indel_rec> ind_out; std::vector<uint8_t> ind_seq_out; std::vector<mc_breakpoint_rec> bp_out;
 	std::vector<mc_variant_rec> vc_out; std::vector<int32_t> vc_depth;
+	DBuf d_vc[12];   // scratch of mc_variant_scan, kept between calls
 	// stats
 	mc_stats stats; DevStats dstats_last;
 	mc_event_t ev[EV_COUNT];
@@ -235,6 +236,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
 	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
 	for (DBuf* b : bufs) b->release();
+	for (DBuf& b : c->d_vc) b.release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); s->flag.release(); }
 	DBuf* fq[] = {&c->fq_text[0], &c->fq_text[1], &c->fq_cnt[0], &c->fq_cnt[1], &c->fq_off[0], &c->fq_off[1], &c->fq_lines[0], &c->fq_lines[1], &c->fq_scan, &c->fq_rlen, &c->fq_rsrc};
@@ -1307,9 +1309,19 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	const int64_t G = c->G, nb = (G + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK, nvb = (G + MC_VC_BLOCK - 1) / MC_VC_BLOCK;
 	const int64_t tile_cols = (int64_t)25600 * 640;   // a multiple of MC_PROF_BLOCK and of MC_VC_BLOCK
 	const int64_t n_tiles = (G + tile_cols - 1) / tile_cols;
-	DBuf d_sums, d_depth, d_ng, d_nd, d_ln, d_le, d_lead, d_cnt, d_off, d_scan, d_cand, d_out;
-	DBuf* all[] = {&d_sums, &d_depth, &d_ng, &d_nd, &d_ln, &d_le, &d_lead, &d_cnt, &d_off, &d_scan, &d_cand, &d_out};
-	auto done = [&](int r) { dev_sync(s); for (DBuf* b : all) b->release(); return r; };
+	DBuf &d_sums = c->d_vc[0], &d_depth = c->d_vc[1], &d_ng = c->d_vc[2], &d_nd = c->d_vc[3], &d_ln = c->d_vc[4], &d_le = c->d_vc[5], &d_lead = c->d_vc[6],
+	     &d_cnt = c->d_vc[7], &d_off = c->d_vc[8], &d_scan = c->d_vc[9], &d_cand = c->d_vc[10], &d_out = c->d_vc[11];
+	const bool trace = getenv("MC_VC_TRACE") != nullptr;   // stage timings on stderr (each stage ends with a stream sync then)
+	auto t_last = std::chrono::steady_clock::now();
+	auto mark = [&](const char* what) {
+		if (!trace) return;
+		dev_sync(s);
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[mc_variant_scan] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+		t_last = now;
+	};
+	auto done = [&](int r) { dev_sync(s); return r; };
+	mark("indels");
 	int bad = d_sums.reserve((size_t)(6 * nb + 8) * 8) || d_depth.reserve((size_t)nvb * 4) || d_ng.reserve((size_t)nvb * 8) || d_nd.reserve((size_t)nvb * 8);
 	bad |= d_ln.reserve((size_t)nvb * 8) || d_le.reserve((size_t)nvb * 8) || d_lead.reserve((size_t)nvb * 4) || d_cnt.reserve((size_t)(nvb + 1) * 4);
 	bad |= d_off.reserve((size_t)(nvb + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(nvb)) || d_cand.reserve((cand.size() + 1) * sizeof(VcCand));
@@ -1333,19 +1345,23 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	};
 	auto vb0 = [&](int64_t t) { return t * (tile_cols / MC_VC_BLOCK); };
 	auto vb1 = [&](int64_t t) { return std::min(nvb, (t + 1) * (tile_cols / MC_VC_BLOCK)); };
+	mark("prefix");
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcdepth(a, vb0(t), vb1(t), s); }
+	mark("pack+depth");
 	device_incmax_i64(a.last_nongap, nvb, s); device_incmax_i64(a.last_nondup, nvb, s);
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), false, s); }
 	if (a.vp.gvcf) { device_incmax_i64(a.last_normal, nvb, s); device_incmax_i64(a.last_event, nvb, s); }
 	device_scan_u32(a.cnt, d_off.as<int64_t>(), nvb, d_scan.as<int64_t>(), s);
 	int64_t total = 0;
 	if (dev_d2h(&total, d_off.as<int64_t>() + nvb, 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	mark("count");
 	if (d_out.reserve((size_t)(total + 1) * sizeof(mc_variant_rec))) return done(MC_ERR_CUDA);
 	a.out = d_out.as<mc_variant_rec>();
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), true, s); }
 	std::vector<mc_variant_rec> raw((size_t)total);
 	c->vc_depth.resize((size_t)nvb);
 	if (dev_d2h(raw.data(), d_out.p, (size_t)total * sizeof(mc_variant_rec), s) || dev_d2h(c->vc_depth.data(), d_depth.p, (size_t)nvb * 4, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	mark("emit+d2h");
 	c->vc_out.clear();
 	for (size_t i = 0; i < raw.size(); i++) if (raw[i].VarType != MC_VAR_NIL) c->vc_out.push_back(raw[i]);
 	// CompByVarPos (src/VariantCalling.cpp:51-55); (gPos, VarType) is unique within one scan
@@ -1359,6 +1375,7 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	}
 	*recs = c->vc_out.data(); *n_recs = (int64_t)c->vc_out.size(); *alt_arena = c->ind_seq_out.data();
 	*block_depth = c->vc_depth.data(); *n_blocks = nvb;
+	mark("sort");
 	return done(MC_OK);
 }
 

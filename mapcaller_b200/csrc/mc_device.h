@@ -30,6 +30,8 @@ static inline int64_t mc_bcast64(int64_t v) { return v; }
 static inline int mc_warp_sum(int v) { return v; }
 static inline int mc_warp_max(int v) { return v; }
 static inline int mc_max3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
+static inline int mc_warp_incl_scan(int v, int) { return v; }
+static inline int mc_warp_last(int v) { return v; }
 #else
 #include <cuda_runtime.h>
 #define MC_HD __device__ __forceinline__
@@ -49,6 +51,14 @@ static __device__ __forceinline__ int64_t mc_bcast64(int64_t v) { return __shfl_
 static __device__ __forceinline__ int mc_warp_sum(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
 static __device__ __forceinline__ int mc_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 static __device__ __forceinline__ int mc_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); } // DPX
+// inclusive prefix sum over the 32 lanes of a (full) warp; mc_warp_last = the value lane 31 holds
+static __device__ __forceinline__ int mc_warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+	return v;
+}
+static __device__ __forceinline__ int mc_warp_last(int v) { return __shfl_sync(0xffffffffu, v, 31); }
 #endif
 
 typedef unsigned long long mc_u64; // atomicAdd-compatible 64-bit counter

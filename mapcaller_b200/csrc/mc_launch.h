@@ -33,9 +33,9 @@ static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
 static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump; for (int64_t i = 0; i < n; i++) a.st->profile_atomics += profpiece_body(i, 0, 1, a, q); }
 static void launch_disclist(const PipeArgs& a, int64_t n, DiscRec* out, mc_u64* bump, int64_t cap, mc_stream_t) { for (int64_t i = 0; i < n; i++) disclist_body(i, a, out, bump, cap); }
-static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, p, G, nb, sums); }
+static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, 0, 1, p, G, nb, sums); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
-{ for (int64_t b = b0; b < b1; b++) profpack_body(b, ix, p, nb, pre, beg, end, out); }
+{ for (int64_t b = b0; b < b1; b++) profpack_body(b, 0, 1, ix, p, nb, pre, beg, end, out); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
 static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) profstat_body(i, recs, acc); }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatecnt_body(i, a, q, list, bump); }
@@ -220,13 +220,13 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_cbwt_build_kernel(int64_t n, cons
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t s)
 { if (n > 0) { mc_cbwt_build_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, src, dst); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t* sums)
-{ int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < nb) profsum_body(b, p, G, nb, sums); }
+{ int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; if (b < nb) profsum_body(b, threadIdx.x & 31, 32, p, G, nb, sums); }   // whole warps leave together
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t s)
-{ if (nb > 0) { mc_profsum_kernel<<<(unsigned)((nb + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(p, G, nb, sums); g_launches++; } }
+{ if (nb > 0) { mc_profsum_kernel<<<(unsigned)((nb * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(p, G, nb, sums); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profpack_kernel(const DevIndex ix, const DevProfile p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out)
-{ int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < b1) profpack_body(b, ix, p, nb, pre, beg, end, out); }
+{ int64_t b = b0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5); if (b < b1) profpack_body(b, threadIdx.x & 31, 32, ix, p, nb, pre, beg, end, out); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t s)
-{ if (b1 > b0) { mc_profpack_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, p, nb, pre, b0, b1, beg, end, out); g_launches++; } }
+{ if (b1 > b0) { mc_profpack_kernel<<<(unsigned)(((b1 - b0) * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, p, nb, pre, b0, b1, beg, end, out); g_launches++; } }
 #endif
 
 MC_LAUNCH1(expand)

@@ -264,39 +264,45 @@ MC_HD int profpiece_body(int64_t t, int lane, int nl, const PipeArgs& a, const P
 }
 
 // ---- read-out: difference arrays -> MappingRecord_t ------------------------------------------------------------
-// per MC_PROF_BLOCK columns: totals of the six difference arrays (sums[6][n_blocks], scanned afterwards)
-MC_HD void profsum_body(int64_t b, const DevProfile& p, int64_t G, int64_t n_blocks, int64_t* sums)
+// One warp per MC_PROF_BLOCK columns, a lane per column (coalesced 16-byte / 4-byte loads, 16-byte stores); the running
+// sums of the six difference arrays are warp scans chained from one 32-column group to the next.
+// Pass 1: totals of the six difference arrays per block (sums[6][n_blocks], scanned afterwards).
+MC_HD void profsum_body(int64_t b, int lane, int nl, const DevProfile& p, int64_t G, int64_t n_blocks, int64_t* sums)
 {
 	const int64_t g0 = b * MC_PROF_BLOCK; int64_t g1 = g0 + MC_PROF_BLOCK; if (g1 > G) g1 = G;
-	int64_t t[6] = {0, 0, 0, 0, 0, 0};
-	for (int64_t g = g0; g < g1; g++)
+	int t[6] = {0, 0, 0, 0, 0, 0};   // a block's totals are differences of coverages: they fit 32 bits
+	for (int64_t g = g0 + lane; g < g1; g += nl)
 	{
-		t[0] += p.sdiff[g * 4]; t[1] += p.sdiff[g * 4 + 1]; t[2] += p.sdiff[g * 4 + 2]; t[3] += p.sdiff[g * 4 + 3];
+		const mc_u32x4 q = mc_ldg128(p.sdiff + g * 4);
+		t[0] += (int)q.x; t[1] += (int)q.y; t[2] += (int)q.z; t[3] += (int)q.w;
 		t[4] += p.cdiff[g]; t[5] += p.mdiff[g];
 	}
-	for (int k = 0; k < 6; k++) sums[k * n_blocks + b] = t[k];
+	for (int k = 0; k < 6; k++) { const int v = mc_warp_sum(t[k]); if (lane == 0) sums[k * n_blocks + b] = v; }
 }
 
-// MappingRecord_t image (reference src/structure.h:152-163) of the columns of block b that fall into [beg, end);
+// Pass 2: MappingRecord_t image (reference src/structure.h:152-163) of the columns of block b that fall into [beg, end);
 // pre[6][n_blocks] holds the exclusive block prefixes
-MC_HD void profpack_body(int64_t b, const DevIndex& ix, const DevProfile& p, int64_t n_blocks, const int64_t* pre, int64_t beg, int64_t end, uint64_t* out)
+MC_HD void profpack_body(int64_t b, int lane, int nl, const DevIndex& ix, const DevProfile& p, int64_t n_blocks, const int64_t* pre, int64_t beg, int64_t end, uint64_t* out)
 {
 	const int64_t g0 = b * MC_PROF_BLOCK; int64_t g1 = g0 + MC_PROF_BLOCK; if (g1 > ix.G) g1 = ix.G;
 	int64_t t[6]; for (int k = 0; k < 6; k++) t[k] = pre[k * n_blocks + b];
-	for (int64_t g = g0; g < g1; g++)
+	for (int64_t base = g0; base < g1; base += nl)   // every lane stays in the loop: the scans need the whole warp
 	{
-		t[0] += p.sdiff[g * 4]; t[1] += p.sdiff[g * 4 + 1]; t[2] += p.sdiff[g * 4 + 2]; t[3] += p.sdiff[g * 4 + 3];
-		t[4] += p.cdiff[g]; t[5] += p.mdiff[g];
-		if (g < beg || g >= end) continue;
+		const int64_t g = base + lane; const bool in = g < g1;
+		int d[6] = {0, 0, 0, 0, 0, 0};
+		if (in) { const mc_u32x4 q = mc_ldg128(p.sdiff + g * 4); d[0] = (int)q.x; d[1] = (int)q.y; d[2] = (int)q.z; d[3] = (int)q.w; d[4] = p.cdiff[g]; d[5] = p.mdiff[g]; }
+		int64_t v[6];
+		for (int k = 0; k < 6; k++) { const int s = mc_warp_incl_scan(d[k], lane); v[k] = t[k] + s; t[k] += mc_warp_last(s); }
+		if (!in || g < beg || g >= end) continue;
 		const uint32_t w0 = p.base16[g * 2], w1 = p.base16[g * 2 + 1];
 		uint64_t c[4] = {w0 & 0xFFFF, w0 >> 16, w1 & 0xFFFF, w1 >> 16};
-		c[mc_ref_code(ix, g)] += (uint64_t)t[4];
-		uint64_t M = (uint64_t)t[5], R = p.rcount[g];
+		c[mc_ref_code(ix, g)] += (uint64_t)v[4];
+		uint64_t M = (uint64_t)v[5], R = p.rcount[g];
 		for (int k = 0; k < 4; k++) if (c[k] > 4095) c[k] = 4095;
 		if (M > 4095) M = 4095;
 		const int64_t i = g - beg;
 		out[2 * i] = c[0] | c[1] << 12 | c[2] << 24 | c[3] << 36 | M << 48 | (R & 15) << 60;
-		out[2 * i + 1] = ((uint64_t)t[0] & 0xFFFF) | ((uint64_t)t[1] & 0xFFFF) << 16 | ((uint64_t)t[2] & 0xFFFF) << 32 | ((uint64_t)t[3] & 0xFFFF) << 48;
+		out[2 * i + 1] = ((uint64_t)v[0] & 0xFFFF) | ((uint64_t)v[1] & 0xFFFF) << 16 | ((uint64_t)v[2] & 0xFFFF) << 32 | ((uint64_t)v[3] & 0xFFFF) << 48;
 	}
 }
 
