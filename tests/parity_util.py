@@ -191,3 +191,9 @@ def smoke_case() -> None:
     mine = cuda_results(case, ix)
     assert_same(mine, oracle_results(case, ix))
     assert mine["stats"]["kernel_launches"] > 0
+    # the variant-calling scan of the same profile against the committed output of the unmodified reference (the smoke case
+    # is golden case pe_nw: same seed and sizes)
+    import golden_util as gu
+    gcase, _ = gu.load("pe_nw")
+    sets, gold = gu.load_vc("pe_nw")
+    assert_same_variants(cuda_results(gcase, build_index(gcase), want_reads=False, vc=sets), dict(vc=gold))
