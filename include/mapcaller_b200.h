@@ -186,6 +186,22 @@ typedef struct { int64_t gPos, dist; } mc_site_rec;
 /* kind 0 = InversionSiteVec, 1 = TranslocationSiteVec, sorted by gPos as the thread-end merge does */
 int mc_profile_sites(mc_ctx *ctx, int32_t kind, const mc_site_rec **recs, int64_t *n_recs);
 
+/* ---- SAM record fields of the batch just mapped (reference src/SamReport.cpp:7-316, 324-488): flag (SetPairedAlignmentFlag /
+ *      SetSingledAlignmentFlag), MAPQ (EvaluateMAPQ), RNAME / POS (GetAlnCoordinate + DetermineCoordinate), CIGAR text
+ *      (GenerateCIGARstring), mate position and TLEN, NM / AS / XS - computed on the device from the candidate, fragment and
+ *      alignment-string arenas of the last mc_map_batch / mc_map_staged call, one record per read (the reference's default
+ *      bUnique = true).  The caller prints the line; it owns QNAME, SEQ and QUAL:
+ *        QNAME flag RNAME pos mapq CIGAR (has_mate ? "=" mate_pos tlen : "*" 0 0) SEQ QUAL [NM:i:nm] AS:i:as XS:i:xs
+ *      with SEQ = the read as it stands in the FASTQ file (both mates), reverse-complemented and QUAL reversed when
+ *      `reverse` is set.  Unmapped read: chrom = -1 ("*", pos 0, mapq 0,
+ *      CIGAR "*"), nm = -1 (no NM tag).  flag = -1: the reference prints no line for this read. */
+typedef struct {
+	int64_t pos, mate_pos;
+	int32_t flag, chrom, mapq, tlen, nm, as, xs, cigar_off, cigar_len, reverse, has_mate, pad;
+} mc_sam_rec;
+/* `recs` (one per read of the batch) and `cigar_arena` stay valid until the next call on ctx. */
+int mc_sam_records(mc_ctx *ctx, const mc_sam_rec **recs, int64_t *n_recs, const uint8_t **cigar_arena);
+
 /* ---- variant-calling scan (reference src/VariantCalling.cpp:106-120 CalBlockReadDepth, :550-680 IdentifyVariants,
  *      :60-98 GetAreaIndFrequency, :523-548 DetermineGenotype) over the device-resident profile, without downloading
  *      the 16-byte-per-column MappingRecordArr.  The columns are scanned on the GPU in blocks of 100 (the reference's

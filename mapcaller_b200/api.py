@@ -63,6 +63,31 @@ VARIANT_DT = np.dtype([("gPos", "<i8"), ("rec0", "<u8"), ("rec1", "<u8"), ("alt_
 assert VARIANT_DT.itemsize == 48
 
 
+SAM_DT = np.dtype([("pos", "<i8"), ("mate_pos", "<i8")] + [(k, "<i4") for k in ("flag", "chrom", "mapq", "tlen", "nm", "as", "xs", "cigar_off",
+                                                                                 "cigar_len", "reverse", "has_mate", "pad")])
+assert SAM_DT.itemsize == 64
+_COMP = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+
+
+def complement_read(seq: bytes) -> bytes:
+    """GetComplementarySeq of the reference (src/tools.cpp:5-29): reverse complement, anything but ACGT/acgt -> N."""
+    return bytes(_COMP[b] if chr(b) in "ACGTacgt" else ord("N") for b in reversed(seq))
+
+
+def format_sam_line(rec, cigar: bytes, name: bytes, seq: bytes, qual: bytes | None, chrom_names) -> bytes | None:
+    """One SAM line from an mc_sam_rec, as GeneratePairedSamStream / GenerateSingleSamStream print it (src/SamReport.cpp:332,346-363,401-434)."""
+    if rec["flag"] < 0:
+        return None
+    if rec["reverse"]:
+        seq, qual = complement_read(seq), (qual[::-1] if qual is not None else None)
+    q = qual if qual is not None else b"*"
+    if rec["chrom"] < 0:
+        return b"%s\t%d\t*\t0\t0\t*\t*\t0\t0\t%s\t%s\tAS:i:0\tXS:i:0" % (name, rec["flag"], seq, q)
+    mate = b"=\t%d\t%d" % (rec["mate_pos"], rec["tlen"]) if rec["has_mate"] else b"*\t0\t0"
+    return b"%s\t%d\t%s\t%d\t%d\t%s\t%s\t%s\t%s\tNM:i:%d\tAS:i:%d\tXS:i:%d" % (
+        name, rec["flag"], chrom_names[rec["chrom"]], rec["pos"], rec["mapq"], cigar, mate, seq, q, rec["nm"], rec["as"], rec["xs"])
+
+
 class Stats(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile",
                                            "ms_h2d", "ms_d2h", "ms_total")] + \
@@ -123,6 +148,7 @@ def lib():
         L.mc_vc_params_default.restype = None
         L.mc_variant_scan.argtypes = [C.c_void_p, C.POINTER(VcParams), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.mc_sam_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
         L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
         L.mc_comm_unique_id.argtypes = [C.c_void_p]
         L.mc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
@@ -392,6 +418,15 @@ class Context:
             s = C.string_at(arena.value + int(x["seq_off"]), int(x["len"]))
             out[int(x["kind"])].append((int(x["pos"]), s, int(x["count"])))
         return out
+
+    def sam_records(self):
+        """SAM fields of the batch just mapped (mc_sam_records): (structured array SAM_DT, list of CIGAR byte strings)."""
+        recs, n, arena = C.c_void_p(), C.c_int64(), C.c_void_p()
+        _check(lib().mc_sam_records(self._h, C.byref(recs), C.byref(n), C.byref(arena)), "mc_sam_records")
+        r = _view(recs.value, n.value, SAM_DT).copy()
+        total = int((r["cigar_off"] + r["cigar_len"]).max()) if n.value else 0
+        text = C.string_at(arena.value, total)
+        return r, [text[o:o + l] if l else b"*" for o, l in zip(r["cigar_off"].tolist(), r["cigar_len"].tolist())]
 
     def variant_scan(self, **kw):
         """CalBlockReadDepth + IdentifyVariants of the reference (src/VariantCalling.cpp:106-120, 550-680) on the device.

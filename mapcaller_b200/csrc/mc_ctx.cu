@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -203,6 +204,8 @@ struct mc_ctx {
 	std::vector<mc_indel_rec> ind_out; std::vector<uint8_t> ind_seq_out; std::vector<mc_breakpoint_rec> bp_out;
 	std::vector<mc_variant_rec> vc_out; std::vector<int32_t> vc_depth;
 	DBuf d_vc[12];   // scratch of mc_variant_scan, kept between calls
+	int64_t last_n = 0; const int64_t* last_roff = nullptr;   // the batch whose arenas are still on the device (mc_sam_records)
+	DBuf d_sam[5]; std::vector<mc_sam_rec> sam_out; std::vector<uint8_t> sam_cigar;
 	// stats
 	mc_stats stats; DevStats dstats_last;
 	mc_event_t ev[EV_COUNT];
@@ -237,6 +240,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
 	for (DBuf* b : bufs) b->release();
 	for (DBuf& b : c->d_vc) b.release();
+	for (DBuf& b : c->d_sam) b.release();
 	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); s->flag.release(); }
 	DBuf* fq[] = {&c->fq_text[0], &c->fq_text[1], &c->fq_cnt[0], &c->fq_cnt[1], &c->fq_off[0], &c->fq_off[1], &c->fq_lines[0], &c->fq_lines[1], &c->fq_scan, &c->fq_rlen, &c->fq_rsrc};
@@ -556,6 +560,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	const int64_t n_pairs = paired ? n / 2 : 0;
 	const int64_t n_chunks = (n + MC_CHUNK_READS - 1) / MC_CHUNK_READS;
 	memset(out, 0, sizeof(*out));
+	c->last_n = 0;
 	// the reference cuts the library into 200-read chunks from its start; a batch that ends inside a chunk can only be the last
 	if (n > 0 && c->library_closed && !ordered_mode(c)) { mc_set_error("mc_map_batch: the previous batch was not a multiple of %d reads, which ends the library (mc_reset starts a new one)", MC_CHUNK_READS); return MC_ERR_ARG; }
 	if (n % MC_CHUNK_READS) c->library_closed = true;
@@ -976,6 +981,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			out->reads = c->reads_out.data(); out->cands = c->cands_out.data(); out->n_cands = (int64_t)c->cands_out.size();
 			out->frags = c->h_frags.as<mc_frag_out>(); out->n_frags = (int64_t)hb.frag; out->aln = c->h_aln.as<uint8_t>(); out->n_aln_bytes = (int64_t)hb.aln;
 		}
+		c->last_n = n; c->last_roff = st.roff.as<int64_t>();
 		return MC_OK;
 	}
 }
@@ -1251,6 +1257,49 @@ int mc_profile_sites(mc_ctx* c, int32_t kind, const mc_site_rec** recs, int64_t*
 	if (!c || !recs || !n_recs || kind < 0 || kind > 1) { mc_set_error("mc_profile_sites: bad argument"); return MC_ERR_ARG; }
 	std::vector<mc_site_rec>& v = kind == 0 ? c->inv_sites : c->tnl_sites;
 	*recs = v.data(); *n_recs = (int64_t)v.size();
+	return MC_OK;
+}
+
+// ---- SAM record fields of the last batch (reference src/SamReport.cpp:7-316, 324-488) -------------------------------
+int mc_sam_records(mc_ctx* c, const mc_sam_rec** recs, int64_t* n_recs, const uint8_t** cigar_arena)
+{
+	if (!c || !recs || !n_recs || !cigar_arena) { mc_set_error("mc_sam_records: null argument"); return MC_ERR_ARG; }
+	if (c->last_n <= 0) { mc_set_error("mc_sam_records: no mapped batch on the device (call it right after mc_map_batch / mc_map_staged)"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	const int64_t n = c->last_n; mc_stream_t s = c->stream;
+	DBuf &d_tab = c->d_sam[0], &d_out = c->d_sam[1], &d_len = c->d_sam[2], &d_off = c->d_sam[3], &d_cig = c->d_sam[4];
+	// EvaluateMAPQ (src/SamReport.cpp:86-101) mixes float and double arithmetic with log(): tabulated here with the host's libm
+	// for the only cases that reach the formula (score - sub_score = 1..5), so the device needs no transcendental
+	std::vector<uint8_t> tab((size_t)5 * (MC_MAX_RLEN + 1), 0);
+	for (int d = 1; d <= 5; d++)
+		for (int score = d; score <= MC_MAX_RLEN; score++)
+		{
+			int mapq = (int)(30 * (1 - (float)d / score) * log(score) + 0.4999);
+			if (mapq > 60) mapq = 60;
+			tab[(size_t)(d - 1) * (MC_MAX_RLEN + 1) + score] = (uint8_t)mapq;
+		}
+	int bad = d_tab.reserve(tab.size()) || d_out.reserve((size_t)n * sizeof(mc_sam_rec)) || d_len.reserve((size_t)(n + 1) * 4) || d_off.reserve((size_t)(n + 2) * 8) || c->d_scan.reserve(device_scan_scratch_bytes(n));
+	if (bad || dev_h2d(d_tab.p, tab.data(), tab.size(), s)) return MC_ERR_CUDA;
+	SamArgs a; memset(&a, 0, sizeof(a));
+	a.ix = c->ix; a.paired = c->prm.paired; a.n_reads = n; a.roff = c->last_roff;
+	a.cand_off = c->d_cand_off.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.cscore = c->d_cscore.as<int32_t>(); a.cpaired = c->d_cpaired.as<int32_t>();
+	a.corient = c->d_corient.as<int32_t>(); a.cfrag = c->d_cfrag.as<int32_t>(); a.cnfrag = c->d_cnfrag.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
+	a.frags = c->d_frags.as<mc_frag_out>(); a.aln = c->d_aln.as<uint8_t>(); a.mapq_tab = d_tab.as<uint8_t>();
+	a.out = d_out.as<mc_sam_rec>(); a.clen = d_len.as<uint32_t>(); a.coff = d_off.as<int64_t>();
+	launch_samrec(a, n, false, s);
+	device_scan_u32(a.clen, d_off.as<int64_t>(), n, c->d_scan.as<int64_t>(), s);
+	int64_t total = 0;
+	if (dev_d2h(&total, d_off.as<int64_t>() + n, 8, s) || dev_sync(s)) return MC_ERR_CUDA;
+	if (total > 0x7fffffffll) { mc_set_error("mc_sam_records: CIGAR text of the batch exceeds 2 GiB"); return MC_ERR_OVERFLOW; }
+	if (d_cig.reserve((size_t)total + 16)) return MC_ERR_CUDA;
+	a.cigar = d_cig.as<uint8_t>();
+	launch_samrec(a, n, true, s);
+	c->sam_out.resize((size_t)n); c->sam_cigar.resize((size_t)total + 1);
+	if (dev_d2h(c->sam_out.data(), d_out.p, (size_t)n * sizeof(mc_sam_rec), s) || dev_d2h(c->sam_cigar.data(), d_cig.p, (size_t)total, s) || dev_sync(s)) return MC_ERR_CUDA;
+	c->sam_cigar[(size_t)total] = 0;
+	*recs = c->sam_out.data(); *n_recs = n; *cigar_arena = c->sam_cigar.data();
 	return MC_OK;
 }
 

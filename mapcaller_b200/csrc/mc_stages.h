@@ -412,5 +412,6 @@ MC_HD void cluster_body(int64_t r, const PipeArgs& a)
 #include "mc_stages_align.h"
 #include "mc_stages_profile.h"
 #include "mc_stages_vc.h"
+#include "mc_stages_sam.h"
 
 #endif

@@ -22,11 +22,14 @@ def have_ref() -> bool:
 
 def make_case(kind: str = "small", seed: int = 1, n_pairs: int = 3000, read_len: int = 100, genome_len: int = 60000,
               contigs: int = 1, sub_rate: float = 0.005, indel_rate: float = 0.0, n_rate: float = 0.0, sv: float = 1.0,
-              n_dup: int = 6, tandem: int = 3, frag_mean: float = 400, frag_sd: float = 40, lower_rate: float = 0.0, **params):
+              n_dup: int = 6, tandem: int = 3, frag_mean: float = 400, frag_sd: float = 40, lower_rate: float = 0.0,
+              repeat_frac: float = 0.0, repeat_div: float = 0.02, **params):
     """A genome (possibly several contigs), a mutated copy the reads come from, and the reads."""
     parts, names = [], []
     for c in range(contigs):
-        parts.append(sim.genome(genome_len // contigs, seed * 100 + c, n_dup=n_dup, dup_len=(300, 900), tandem=tandem))
+        # repeat_frac > 0: interspersed families of slightly diverged copies (reads with 0 < score - sub_score <= 5: the MAPQ formula)
+        parts.append(sim.genome(genome_len // contigs, seed * 100 + c, n_dup=n_dup, dup_len=(300, 900), tandem=tandem, repeat_frac=repeat_frac,
+                                families=((300, repeat_div), (1000, repeat_div))))
         names.append("ctg%d" % (c + 1))
     ref = np.concatenate(parts)
     mut_parts = [sim.mutate(p, seed * 1000 + i, snp_per_mb=3000, small_indel_per_mb=400, large_indel_per_mb=150, sv_per_mb=sv * 30, sv_len=(400, 900))[0]
@@ -182,6 +185,76 @@ def assert_same(mine, ref, want_reads: bool = True, paired: bool = True) -> None
         p = ref["profile"].astype(np.int64); cov = p[:, :4].sum(axis=1)
         want = dict(aligned_bases=int((cov > 0).sum()), coverage_sum=int(cov.sum()), dup_sites=int((p[:, 5] > 0).sum()), dup_reads=int(p[:, 5].sum()))
         assert mine["summary"] == want, "coverage / duplication summary differs: %r vs %r" % (mine["summary"], want)
+
+
+def _write_inputs(case, td):
+    fa = os.path.join(td, "ref.fa")
+    sim.write_fasta(fa, case["contigs"])
+    paired = bool(case["params"]["paired"])
+    f1, f2 = os.path.join(td, "r1.fq"), os.path.join(td, "r2.fq")
+    sim.write_fastq(f1, case["r1"], 1)
+    if paired:
+        sim.write_fastq(f2, case["r2"], 2)
+    return fa, f1, (f2 if paired else None)
+
+
+def sam_lines_reference(case, td):
+    """SAM records (bytes, in file order, header lines dropped) of the unmodified reference CLI, -t 1."""
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "MapCaller")
+    fa, f1, f2 = _write_inputs(case, td)
+    idx = os.path.join(td, "idx")
+    subprocess.check_call([ref_bin, "index", fa, idx], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    sam = os.path.join(td, "ref.sam")
+    cmd = [ref_bin, "-i", idx, "-t", "1", "-f", f1] + (["-f2", f2] if f2 else []) + ["-sam", sam, "-no_vcf", "-log", os.path.join(td, "log")]
+    prm = case["params"]
+    if prm.get("alg_ksw2"):
+        cmd += ["-alg", "ksw2"]
+    assert prm.get("max_pos_diff", 30) == 30, "MaxPosDiff has no command-line switch"
+    cmd += ["-dup", str(prm.get("max_dup", 5)), "-maxclip", str(prm.get("max_clip", 5)), "-maxmm", repr(float(prm.get("max_mismatch_rate", 0.05)))]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=td)
+    return [l for l in open(sam, "rb").read().split(b"\n") if l and not l.startswith(b"@")]
+
+
+def sam_lines_cuda(case, device: int = 0, batch_reads: int | None = None):
+    """The same records printed from mc_sam_records (flag, position, MAPQ, CIGAR, mate fields and tags from the device;
+    names, bases and qualities from the FASTQ text)."""
+    from mapcaller_b200 import api
+    paired = bool(case["params"]["paired"])
+    texts = [sim.fastq_text(case["r1"], 1, "r").tobytes().split(b"\n")] + ([sim.fastq_text(case["r2"], 2, "r").tobytes().split(b"\n")] if paired else [])
+    seq, off = case["seq"], case["off"]
+    n = len(off) - 1
+    batch_reads = batch_reads or n
+    names = [nm for nm, _ in case["contigs"]]
+    lines = []
+    with api.Context(build_index(case), want_alignments=0, update_profile=0, device=device, **case["params"]) as ctx:
+        for b in range(0, n, batch_reads):
+            e = min(n, b + batch_reads)
+            ctx.map_batch(seq[off[b]:off[e]], off[b:e + 1] - off[b])
+            recs, cigars = ctx.sam_records()
+            for k in range(e - b):
+                r = b + k
+                t, i = (texts[r & 1], r >> 1) if paired else (texts[0], r)
+                head = t[4 * i][1:].split()[0]
+                if head.endswith(b"/1") or head.endswith(b"/2"):   # IdentifyHeaderEndPos, src/GetData.cpp:15-30
+                    head = head[:-2]
+                l = api.format_sam_line(recs[k], cigars[k], head, t[4 * i + 1], t[4 * i + 3], [x.encode() for x in names])
+                if l is not None:
+                    lines.append(l)
+    return lines
+
+
+def sam_comparable(lines, paired: bool):
+    """In single-end mode the reference's SamReport.cpp leaves the first byte of a reversed quality string uninitialised
+    (GetReverseQualityStr, src/SamReport.cpp:318-322; it may even be a NUL or a newline and cut the line), so only the
+    columns before QUAL are comparable there."""
+    if paired:
+        return lines
+    out = []
+    for l in lines:
+        f = l.split(b"\t")
+        if len(f) >= 10 and f[0].startswith(b"r"):
+            out.append(b"\t".join(f[:10]))
+    return out
 
 
 def smoke_case() -> None:

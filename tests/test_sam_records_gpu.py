@@ -1,0 +1,45 @@
+"""mc_sam_records (flag, RNAME / POS, MAPQ, CIGAR, mate fields, NM / AS / XS computed on the device) against the SAM text of
+the unmodified reference CLI (oracle/_ref/MapCaller -t 1): the lines printed from the device records plus the FASTQ text
+must equal the reference's lines byte for byte (single-end: up to QUAL, see parity_util.sam_comparable)."""
+import os
+
+import pytest
+
+import parity_util as pu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "MapCaller")
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not on this box")]
+
+CASES = {
+    "pe_two_contigs_sv": dict(seed=41, n_pairs=6000, genome_len=120000, contigs=2, sv=3.0),
+    "se_sv": dict(seed=42, n_pairs=4000, genome_len=80000, paired=0, sv=3.0),
+    "pe_ksw2_indels_n": dict(seed=43, n_pairs=4000, genome_len=90000, contigs=3, alg_ksw2=1, indel_rate=0.003, n_rate=0.004),
+    "pe_repeats": dict(seed=44, n_pairs=8000, genome_len=100000, sv=5.0, n_dup=30, tandem=20),
+    "pe_long_250": dict(seed=45, n_pairs=3000, genome_len=150000, read_len=250, frag_mean=600, frag_sd=80, indel_rate=0.003, contigs=2),
+    "pe_params": dict(seed=47, n_pairs=3000, genome_len=60000, max_clip=2, max_dup=15, max_mismatch_rate=0.1, contigs=4),
+    "se_diverged_repeats": dict(seed=51, n_pairs=6000, genome_len=120000, repeat_frac=0.5, repeat_div=0.01, paired=0),
+    "se_ksw2": dict(seed=48, n_pairs=3000, genome_len=80000, paired=0, alg_ksw2=1, indel_rate=0.004, contigs=2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_sam_lines_equal_the_reference_cli(built, tmp_path, name):
+    case = pu.make_case(**CASES[name])
+    paired = bool(case["params"]["paired"])
+    # two batches: the records always describe the batch mapped last
+    mine = pu.sam_comparable(pu.sam_lines_cuda(case, batch_reads=4000 if name == "pe_repeats" else None), paired)
+    ref = pu.sam_comparable(pu.sam_lines_reference(case, str(tmp_path)), paired)
+    assert len(mine) == len(ref) > 1000
+    bad = [k for k, (a, b) in enumerate(zip(mine, ref)) if a != b]
+    assert not bad, "%d SAM lines differ, first:\n%r\n%r" % (len(bad), mine[bad[0]], ref[bad[0]])
+    assert any(b"S" in l.split(b"\t")[5] for l in ref) and any(l.split(b"\t")[2] == b"*" for l in ref)
+
+
+def test_sam_records_need_a_mapped_batch(built):
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=3, n_pairs=200, genome_len=20000)
+    with api.Context(pu.build_index(case), **case["params"]) as ctx:
+        with pytest.raises(api.McError):
+            ctx.sam_records()
