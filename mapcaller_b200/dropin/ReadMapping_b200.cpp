@@ -77,6 +77,24 @@ void rebuild(ReadItem_t& rd, const mc_batch_out& out, int64_t r)
 	}
 }
 
+// One SAM line from the record the device computed (mc_sam_records): the text of GeneratePairedSamStream /
+// GenerateSingleSamStream (src/SamReport.cpp:332,351,385-434) with QNAME / SEQ / QUAL from the read as the reader delivered it.
+void print_sam_line(FILE* out, const ReadItem_t& rd, const mc_sam_rec& r, const uint8_t* cigar_arena, string& seq, string& qual)
+{
+	if (r.flag < 0) return;
+	seq.assign(rd.seq, rd.rlen);
+	if (FastQFormat) qual.assign(rd.qual, rd.rlen); else qual = "*";
+	if (r.reverse)
+	{
+		seq.resize(rd.rlen + 1); GetComplementarySeq(rd.rlen, rd.seq, &seq[0]); seq.resize(rd.rlen);
+		if (FastQFormat) reverse(qual.begin(), qual.end());
+	}
+	if (r.chrom < 0) { fprintf(out, "%s\t%d\t*\t0\t0\t*\t*\t0\t0\t%s\t%s\tAS:i:0\tXS:i:0\n", rd.header, r.flag, seq.c_str(), qual.c_str()); return; }
+	fprintf(out, "%s\t%d\t%s\t%lld\t%d\t%.*s\t", rd.header, r.flag, ChromosomeVec[r.chrom].name, (long long)r.pos, r.mapq, r.cigar_len, (const char*)cigar_arena + r.cigar_off);
+	if (r.has_mate) fprintf(out, "=\t%lld\t%d", (long long)r.mate_pos, r.tlen); else fprintf(out, "*\t0\t0");
+	fprintf(out, "\t%s\t%s\tNM:i:%d\tAS:i:%d\tXS:i:%d\n", seq.c_str(), qual.c_str(), r.nm, r.as, r.xs);
+}
+
 } // namespace
 
 void Mapping()
@@ -99,6 +117,10 @@ void Mapping()
 	v.n_chrom = iChromsomeNum; v.chrom_len = clen.data(); v.chrom_name = cname.data();
 	mc_index* idx = NULL; if (mc_index_wrap(&v, &idx)) die("mc_index_wrap");
 
+	// MC_B200_DEVICE_SAM=1: flags, positions, MAPQ, CIGAR and mate fields come from the device (mc_sam_records) and only the
+	// text is printed here, instead of downloading every candidate / fragment / alignment string and running the reference's
+	// SamReport.o over them.  One line per read, i.e. not with -m (bUnique = false).
+	const bool device_sam = bSAMoutput && bUnique && getenv("MC_B200_DEVICE_SAM") != NULL;
 	mc_ctx* ctx = NULL;
 	for (int lib_id = 0; lib_id < (int)ReadFileNameVec1.size(); lib_id++)
 	{
@@ -121,7 +143,7 @@ void Mapping()
 		{
 			mc_params p; mc_params_default(&p);
 			p.paired = bPairEnd; p.alg_ksw2 = !NW_ALG; p.max_pos_diff = MaxPosDiff; p.max_clip = MaxClipSize; p.max_dup = iMaxDuplicate;
-			p.max_mismatch_rate = MaxMisMatchRate; p.update_profile = bVCFoutput; p.want_alignments = bSAMoutput;
+			p.max_mismatch_rate = MaxMisMatchRate; p.update_profile = bVCFoutput; p.want_alignments = bSAMoutput && !device_sam;
 			if (mc_ctx_create(idx, &p, &ctx)) die("mc_ctx_create");
 		}
 		// No SAM wanted and plain FASTQ on disk: nothing of the reference's reader is needed - raw file blocks go to the GPU, which
@@ -165,7 +187,14 @@ void Mapping()
 			if (mc_map_batch(ctx, &in, &out)) die("mc_map_batch");
 			mc_totals t; mc_get_totals(ctx, &t);
 			fprintf(stderr, "\r%lld %s reads have been processed in %lld seconds...", (long long)t.total_reads, (bPairEnd ? "paired-end" : "singled-end"), (long long)(time(NULL) - StartProcessTime));
-			if (bSAMoutput)
+			if (device_sam)
+			{
+				const mc_sam_rec* sr; int64_t ns; const uint8_t* cig; string sq, ql;
+				if (mc_sam_records(ctx, &sr, &ns, &cig)) die("mc_sam_records");
+				for (int64_t i = 0; i < n; i++) print_sam_line(sam_out, reads[i], sr[i], cig, sq, ql);
+				fflush(sam_out);
+			}
+			else if (bSAMoutput)
 			{
 				sam.clear();
 				for (int64_t i = 0; i < n; i++) rebuild(reads[i], out, i);
