@@ -9,6 +9,7 @@
 //
 // What stays on the host, unchanged and in file order: FASTQ/FASTA reading (GetNextChunk), ReverseOrientation of mate 2
 // for the SAM text, SAM generation (GeneratePairedSamStream / GenerateSingleSamStream) and everything after Mapping().
+// With MC_B200_DEVICE_SAM=1 the SAM fields come from the device (mc_sam_records) and only print_sam_line() runs here.
 #include "structure.h"
 #include "mapcaller_b200.h"
 

@@ -30,7 +30,9 @@ def test_every_declared_symbol_is_exported(built):
 
 def test_header_compiles_as_plain_c(built, tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "mapcaller_b200.h"\nint main(void){ mc_params p; mc_params_default(&p); return p.max_dup == 5 ? 0 : 1; }\n')
+    src.write_text('#include "mapcaller_b200.h"\nint main(void){ mc_params p; mc_params_default(&p);\n'
+                   '  if (sizeof(mc_sam_rec) != 64 || sizeof(mc_variant_rec) != 48 || sizeof(mc_vc_params) != 32) return 2;   /* api.SAM_DT / VARIANT_DT / VcParams */\n'
+                   '  return p.max_dup == 5 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     lib = os.path.join(ROOT, "mapcaller_b200")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
