@@ -27,9 +27,14 @@ for seed in range(seed0, seed0 + n_cases):
     case = pu.make_case(**kw); paired = bool(kw["paired"])
     n = len(case["off"]) - 1
     batch = None if rng.random() < 0.5 else int(rng.integers(1, 6)) * 400
+    import subprocess
     with tempfile.TemporaryDirectory() as td:
+        try:
+            ref = pu.sam_comparable(pu.sam_lines_reference(case, td), paired)
+        except subprocess.CalledProcessError as e:   # the reference's own undefined behaviour: nothing to compare with
+            print("seed %d SKIP the reference CLI exited with %d" % (seed, e.returncode), flush=True)
+            continue
         mine = pu.sam_comparable(pu.sam_lines_cuda(case, batch_reads=batch), paired)
-        ref = pu.sam_comparable(pu.sam_lines_reference(case, td), paired)
     bad = [k for k, (a, b) in enumerate(zip(mine, ref)) if a != b]
     if bad or len(mine) != len(ref):
         bad_cases += 1
