@@ -1211,19 +1211,31 @@ int mc_profile_indels(mc_ctx* c, const mc_indel_rec** recs, int64_t* n_recs, con
 	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
 	std::vector<mc_indel_rec> raw((size_t)pb.ind); std::vector<uint8_t> seq((size_t)pb.ind_seq + 1);
 	if (dev_d2h(raw.data(), c->d_ind.p, raw.size() * sizeof(mc_indel_rec), c->stream) || dev_d2h(seq.data(), c->d_ind_seq.p, (size_t)pb.ind_seq, c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
-	// aggregate like map<int64, map<string, uint16_t>>::operator[]++ (reference src/AlignmentProfile.cpp:123,129)
-	std::map<std::pair<int, int64_t>, std::map<std::string, uint32_t> > agg;
-	for (size_t i = 0; i < raw.size(); i++)
-		agg[std::make_pair(raw[i].kind, raw[i].pos)][std::string((const char*)seq.data() + raw[i].seq_off, (size_t)raw[i].len)]++;
+	// aggregate like map<int64, map<string, uint16_t>>::operator[]++ (reference src/AlignmentProfile.cpp:123,129): sort the raw
+	// records by (kind, pos, sequence as std::string compares it) and count the runs - the order a walk over the maps gives
+	std::vector<uint32_t> order(raw.size());
+	for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+	const uint8_t* sq = seq.data();
+	auto key_less = [&](uint32_t x, uint32_t y) {
+		const mc_indel_rec &a = raw[x], &b = raw[y];
+		if (a.kind != b.kind) return a.kind < b.kind;
+		if (a.pos != b.pos) return a.pos < b.pos;
+		const int m = memcmp(sq + a.seq_off, sq + b.seq_off, (size_t)std::min(a.len, b.len));
+		return m != 0 ? m < 0 : a.len < b.len;
+	};
+	std::sort(order.begin(), order.end(), key_less);
 	c->ind_out.clear(); c->ind_seq_out.clear();
-	for (auto& kv : agg)
-		for (auto& sv : kv.second)
-		{
-			mc_indel_rec r; r.pos = kv.first.second; r.kind = kv.first.first; r.len = (int32_t)sv.first.size(); r.count = (int32_t)(sv.second & 0xFFFF);
-			r.seq_off = (int32_t)c->ind_seq_out.size();
-			c->ind_seq_out.insert(c->ind_seq_out.end(), sv.first.begin(), sv.first.end());
-			c->ind_out.push_back(r);
-		}
+	for (size_t i = 0; i < order.size();)
+	{
+		size_t j = i + 1;
+		while (j < order.size() && !key_less(order[i], order[j])) j++;   // sorted: not less = equal key
+		const mc_indel_rec& a = raw[order[i]];
+		mc_indel_rec r; r.pos = a.pos; r.kind = a.kind; r.len = a.len; r.count = (int32_t)((j - i) & 0xFFFF);
+		r.seq_off = (int32_t)c->ind_seq_out.size();
+		c->ind_seq_out.insert(c->ind_seq_out.end(), sq + a.seq_off, sq + a.seq_off + a.len);
+		c->ind_out.push_back(r);
+		i = j;
+	}
 	c->ind_seq_out.push_back(0);
 	*recs = c->ind_out.data(); *n_recs = (int64_t)c->ind_out.size(); *seq_arena = c->ind_seq_out.data();
 	return MC_OK;
