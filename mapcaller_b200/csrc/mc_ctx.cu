@@ -1423,10 +1423,28 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	c->vc_depth.resize((size_t)nvb);
 	if (dev_d2h(raw.data(), d_out.p, (size_t)total * sizeof(mc_variant_rec), s) || dev_d2h(c->vc_depth.data(), d_depth.p, (size_t)nvb * 4, s) || dev_sync(s)) return done(MC_ERR_CUDA);
 	mark("emit+d2h");
-	c->vc_out.clear();
-	for (size_t i = 0; i < raw.size(); i++) if (raw[i].VarType != MC_VAR_NIL) c->vc_out.push_back(raw[i]);
-	// CompByVarPos (src/VariantCalling.cpp:51-55); (gPos, VarType) is unique within one scan
-	std::sort(c->vc_out.begin(), c->vc_out.end(), [](const mc_variant_rec& x, const mc_variant_rec& y) { return x.gPos != y.gPos ? x.gPos < y.gPos : x.VarType < y.VarType; });
+	// CompByVarPos (src/VariantCalling.cpp:51-55); (gPos, VarType) is unique within one scan.  The slots are in column order
+	// except for gap / dup records, which are pushed where their run ends but carry its start: two sorted streams, one merge.
+	auto by_pos = [](const mc_variant_rec& x, const mc_variant_rec& y) { return x.gPos != y.gPos ? x.gPos < y.gPos : x.VarType < y.VarType; };
+	std::vector<mc_variant_rec> runs;
+	c->vc_out.clear(); c->vc_out.reserve(raw.size());
+	size_t n_main = 0;
+	for (size_t i = 0; i < raw.size(); i++)
+	{
+		if (raw[i].VarType == MC_VAR_NIL) continue;
+		if (raw[i].VarType == MC_VAR_UMR || raw[i].VarType == MC_VAR_CNV) runs.push_back(raw[i]); else raw[n_main++] = raw[i];
+	}
+	for (size_t i = 0; i < n_main;)   // one column pushes INS, DEL, SUB in that order: VarType 1, 2, 0
+	{
+		size_t j = i + 1;
+		while (j < n_main && raw[j].gPos == raw[i].gPos) j++;
+		if (j - i > 1) std::sort(raw.begin() + i, raw.begin() + j, by_pos);
+		i = j;
+	}
+	if (!std::is_sorted(raw.begin(), raw.begin() + n_main, by_pos)) std::sort(raw.begin(), raw.begin() + n_main, by_pos);
+	if (!std::is_sorted(runs.begin(), runs.end(), by_pos)) std::sort(runs.begin(), runs.end(), by_pos);
+	c->vc_out.resize(n_main + runs.size());
+	std::merge(raw.begin(), raw.begin() + n_main, runs.begin(), runs.end(), c->vc_out.begin(), by_pos);
 	if (a.vp.gvcf)   // RemoveConsecutiveGenomicVariant (:682-694)
 	{
 		size_t w = 0;
