@@ -48,5 +48,24 @@ def load_vc(name: str):
     return payload["sets"], [(v, np.asarray(d, dtype=np.int32)) for v, d in payload["vc"]]
 
 
+def with_mates(case):
+    """Adds the r1 / r2 read matrices (fixed read length) that the FASTQ writers want to a loaded golden case."""
+    off = case["off"]
+    L = int(off[1] - off[0])
+    assert (np.diff(off) == L).all()
+    rows = case["seq"].reshape(-1, L)
+    if case["params"]["paired"]:
+        case["r1"], case["r2"] = rows[0::2].copy(), rows[1::2].copy()
+    else:
+        case["r1"] = case["r2"] = rows.copy()
+    return case
+
+
+def load_sam(name: str):
+    """SAM records (bytes, header lines dropped) of the reference CLI for golden case `name` (tests/golden/make_golden_sam.py)."""
+    with open(path("sam_" + name), "rb") as fh:
+        return zlib.decompress(fh.read()).split(b"\n")
+
+
 def available(name: str) -> bool:
     return os.path.exists(path(name))

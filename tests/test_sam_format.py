@@ -35,3 +35,20 @@ def test_mapped_lines():
     l = api.format_sam_line(r, b"4M", b"q", b"AACG", None, [b"chr1"])   # FASTA reads: no qualities
     assert l == b"q\t16\tchr1\t7\t0\t4M\t*\t0\t0\tCGTT\t*\tNM:i:0\tAS:i:100\tXS:i:100"
     assert api.format_sam_line(rec(flag=-1), b"*", b"q", b"A", b"I", [b"c"]) is None   # the reference prints nothing for such a read
+
+
+def test_golden_sam_fixture_is_the_references_output(tmp_path):
+    """tests/golden/sam_*.golden pinned against the reference CLI where oracle/_ref is on the box."""
+    import os
+    import pytest
+    import golden_util as gu
+    import parity_util as pu
+    if not os.path.exists(os.path.join(pu.ROOT, "oracle", "_ref", "MapCaller")):
+        pytest.skip("oracle/_ref not on this box")
+    for name in ("pe_nw", "se_nw"):
+        case = gu.with_mates(gu.load(name)[0])
+        d = tmp_path / name
+        d.mkdir()
+        ref = pu.sam_comparable(pu.sam_lines_reference(case, str(d)), bool(case["params"]["paired"]))
+        assert ref == gu.load_sam(name)
+        assert len(ref) >= 800

@@ -5,12 +5,14 @@ import os
 
 import pytest
 
+import golden_util as gu
 import parity_util as pu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "MapCaller")
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not on this box")]
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not on this box")
 
 CASES = {
     "pe_two_contigs_sv": dict(seed=41, n_pairs=6000, genome_len=120000, contigs=2, sv=3.0),
@@ -24,6 +26,15 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("name", ("pe_nw", "pe_ksw2", "se_nw", "pe_multi"))
+def test_sam_lines_equal_the_golden_fixture(built, name):
+    """Committed output of the unmodified reference CLI (tests/golden/make_golden_sam.py)."""
+    case = gu.with_mates(gu.load(name)[0])
+    mine = pu.sam_comparable(pu.sam_lines_cuda(case), bool(case["params"]["paired"]))
+    assert mine == gu.load_sam(name)
+
+
+@needs_ref
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_sam_lines_equal_the_reference_cli(built, tmp_path, name):
     case = pu.make_case(**CASES[name])
