@@ -1,7 +1,7 @@
 """The drop-in binary with MC_B200_DEVICE_SAM=1: SAM lines printed from the device's records (mc_sam_records) instead of the
 reference's SamReport.o over downloaded candidates - SAM and VCF must still equal the reference CLI's.  (Last in the
-collection order on purpose: this path was checked on the host harness only when it was written; the C-ABI entry itself
-is covered by tests/test_sam_records_gpu.py.)"""
+collection order on purpose: when it was written only the pe_nw mode could still be run on a B200, the others on the host
+harness; the C-ABI entry itself is covered by tests/test_sam_records_gpu.py.)"""
 import os
 import subprocess
 
