@@ -54,3 +54,37 @@ def test_sam_records_need_a_mapped_batch(built):
     with api.Context(pu.build_index(case), **case["params"]) as ctx:
         with pytest.raises(api.McError):
             ctx.sam_records()
+
+
+def test_sam_record_properties_at_ecoli_size(built):
+    """configs[1] genome size: properties of the records that do not depend on the size (CIGAR spans the read, positions lie
+    inside their chromosome, flag bits agree with the record, mates that name each other have opposite TLEN)."""
+    import re
+    import numpy as np
+    from mapcaller_b200 import api, simulate as sim
+    G, P, L = 4_600_000, 50_000, 100
+    parts = [sim.genome(G // 2, 7, n_dup=100), sim.genome(G - G // 2, 8, n_dup=100)]
+    g = np.concatenate(parts)
+    mut, _ = sim.mutate(g, 9, snp_per_mb=3000, small_indel_per_mb=200, large_indel_per_mb=50, sv_per_mb=1)
+    r1, r2 = sim.simulate_pairs(mut, P, L, seed=11)
+    r1[::97, 10:40] = ord("N")   # some reads that cannot be placed
+    seq, off = sim.interleave(r1, r2)
+    with api.Context(api.Index.build(sim.encode(g), [len(x) for x in parts], ["a", "b"]), paired=1, update_profile=0) as ctx:
+        ctx.map_batch(seq, off)
+        recs, cigars = ctx.sam_records()
+    assert len(recs) == 2 * P
+    mapped = recs["chrom"] >= 0
+    assert mapped.mean() > 0.9 and (~mapped).sum() > 0
+    assert ((recs["flag"] & 4 != 0) == ~mapped).all() and (recs["flag"] & 1 == 1).all()
+    assert (recs["flag"][0::2] & 0x40 != 0).all() and (recs["flag"][1::2] & 0x80 != 0).all()
+    assert (recs["mapq"] >= 0).all() and (recs["mapq"] <= 60).all() and (recs["as"] >= recs["xs"]).all()
+    assert (recs["nm"][mapped] >= 0).all() and (recs["nm"][mapped] + recs["as"][mapped] == L).all() and (recs["nm"][~mapped] == -1).all()
+    clen = np.array([len(parts[c]) if c >= 0 else 0 for c in recs["chrom"]])
+    assert (recs["pos"][mapped] >= 1).all() and (recs["pos"][mapped] <= clen[mapped]).all()
+    for k in np.nonzero(mapped)[0][:20000]:
+        ops = re.findall(rb"(\d+)([MIDS])", cigars[k])
+        assert b"".join(a + b for a, b in ops) == cigars[k]
+        assert sum(int(a) for a, b in ops if b in b"MIS") == L, cigars[k]
+    a, b = recs[0::2], recs[1::2]
+    both = (a["has_mate"] == 1) & (b["has_mate"] == 1) & (a["mate_pos"] == b["pos"]) & (b["mate_pos"] == a["pos"])
+    assert both.mean() > 0.8 and (a["tlen"][both] == -b["tlen"][both]).all()
