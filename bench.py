@@ -1,27 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- read pairs mapped / s of the MapCaller hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P] [--genome BP]
 
-Workload (config.workload): BASELINE.json configs[1] -- E. coli-sized 4.6 Mbp synthetic reference (uniform ACGT +
-200 copied 1-3 kbp segments), reads simulated from a mutant carrying the reference simulator's variant rates
-(SNP 3000/Mb, small indel 200/Mb, large indel 50/Mb, SV 1/Mb), 2x100 bp at 50x = 1.15 M pairs, 0.5 % substitution
-errors.  One STEP = one complete pass of the hot path over that library: seeding, locate, clustering, pairing,
-rescue, gapped fills (nw), pair statistics and the pile-up profile update, starting from a freshly reset context
-(empty profile, avgDist = 1000) exactly like one run of the reference.
+Workload (config.workload): BASELINE.json configs[2] (SURVEY.md 8d "chr1-size") -- one contig of 248,956,422 bp, 85 %
+uniform ACGT + 15 % copies of three repeat families (300 bp / 1 kb / 6 kb consensus, 5-15 % divergence) + 2000 copied
+segments, reads simulated from a mutant with SNP 1000/Mb and small indels 100/Mb: 10 M pairs of 2x150 bp per GPU,
+fragment ~N(450, 50), 0.3 % substitution errors, -alg nw, VCF profile on.  The index is built on the GPU
+(mc_index_build_gpu) and is 0.37 GB (+ 0.12 GB sampled SA), i.e. the FM-index gathers come from HBM, not from L2.
 
-  value   device-timed throughput with the reads already resident in HBM (mc_stage_batch + mc_map_staged); CUDA
-          events on the library's stream bracket every step, summed over the K steps, max over ranks
-  e2e     the same metric through the public C ABI (mc_map_batch) with HOST buffers: pinned staging + H2D copy of
-          the reads and D2H copy of the per-pair / per-chunk results inside the timed region (wall clock)
-  roofline  the seed-search kernel (mc_seed_kernel): algorithmic bytes = 64 B x occ blocks the reference algorithm
-          touches (counted by the kernel, identical to the oracle's count) / CUDA-event time of that kernel alone
-  cpu_baseline  the unmodified reference (oracle/_ref, all host threads) or, if absent, the CPU restatement, timed
-          on a bounded prefix of the same reads
+One STEP = one complete pass of the hot path over the library, as one run of the reference's Mapping(): reset context
+(empty profile, avgDist = 1000), then the library in batches of 2 M pairs (seeding, locate, clustering, pairing, rescue,
+gapped fills, pair statistics, pile-up profile update); with N > 1 GPUs the N ranks map ONE library in file order
+(ordered exchange of avgDist / dedup gate / discordant-pair state inside every batch) and the pass ends with the NCCL
+profile reduction.
 
-With --gpus N > 1 (launched by torchrun, one rank per GPU) every rank maps its own library of the same size
-(weak scaling: reads shard across GPUs with a full index replica each, no data-path collective); value is the
-total over ranks / max-over-ranks time.
+  value     device-timed throughput, reads resident in HBM (mc_stage_batch once, step = mc_reset + mc_map_staged per
+            batch): CUDA events on the library's stream around every reset / batch / reduction, max over ranks
+  e2e       FASTQ TEXT in host memory -> result in host memory, through the C ABI, wall clock: every step copies the raw
+            bytes of both mate files host -> device (page-locked), parses them on the device (mc_ingest_fastq, a feeder
+            thread stages block i+1 while block i is mapped), maps them, runs the variant-calling scan on the resident
+            profile (mc_variant_scan) and brings the variant records + block depths back.  Bytes are the library's own
+            counters of what it copied.  e2e.sam = the same loop producing the SAM text of every read as well.
+  roofline  mc_seed_kernel: algorithmic bytes = 64 B x occ blocks the reference algorithm touches (counted by the kernel,
+            equal to the oracle's count) / CUDA-event time of the seed launches of the timed steps; `traffic` = DRAM bytes per
+            launch from the committed ncu --set full capture of this command (profiles/), if present.
+            roofline_locate / roofline_profile: the same for the locate and profile-update stages.
+  cpu_baseline  the unmodified reference (oracle/_ref, Mapping() on all host threads) on a prefix of the same reads
 """
 from __future__ import annotations
 
@@ -39,19 +44,36 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GENOME_LEN = 4_600_000
-READ_LEN = 100
-COVERAGE = 50
-FULL_PAIRS = GENOME_LEN * COVERAGE // (2 * READ_LEN)   # 1.15 M
+GENOME_LEN = 248_956_422
+READ_LEN = 150
+FULL_PAIRS = 10_000_000
+BATCH_PAIRS = 2_000_000
+SIM_BLOCK = 250_000          # simulate_pairs_fast generates independent blocks of this many pairs
+CHECK_PAIRS = 500_000        # per rank, for the N-GPU == 1-GPU profile check
 
 
-def make_workload(n_pairs: int, seed_shift: int = 0):
+def make_genome(genome_len: int):
     from mapcaller_b200 import simulate as sim
-    g = sim.genome(GENOME_LEN, 7, n_dup=200)
-    mut, _ = sim.mutate(g, 8)
-    r1, r2 = sim.simulate_pairs(mut, n_pairs, READ_LEN, seed=11 + seed_shift, frag_mean=400, frag_sd=40, sub_rate=0.005)
-    seq, off = sim.interleave(r1, r2)
-    return g, r1, r2, seq, off
+    g = sim.genome(genome_len, 13, n_dup=2000 if genome_len > 50_000_000 else 200, repeat_frac=0.15)
+    mut, _ = sim.mutate(g, 14, snp_per_mb=1000, small_indel_per_mb=100, large_indel_per_mb=0, sv_per_mb=0)
+    return g, mut
+
+
+def make_reads(mut, n_pairs: int, rank: int, first_block: int = 0):
+    from mapcaller_b200 import simulate as sim
+    return sim.simulate_pairs_fast(mut, n_pairs, READ_LEN, seed=15 + 1000 * rank, frag_mean=450, frag_sd=50, sub_rate=0.003,
+                                   block=SIM_BLOCK, first_block=first_block)
+
+
+def build_index(g, device):
+    from mapcaller_b200 import api, simulate as sim
+    codes = sim.encode(g)
+    if device is not None:
+        try:
+            return api.Index.build(codes, gpu_device=device), "mc_index_build_gpu"
+        except api.McError:
+            pass
+    return api.Index.build(codes), "mc_index_build (host)"
 
 
 class ClockSampler:
@@ -105,56 +127,92 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic():
-    """dram bytes per launch of the seed kernel from the committed ncu --set full capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "seed_kernel_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
+def recorded_traffic(genome_len: int):
+    """DRAM bytes per launch of the kernels from the committed ncu --set full capture of this command (profiles/), or {}."""
+    p = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        t = json.load(open(p))
+        return t if int(t.get("genome_bp", 0)) == genome_len else {}
+    except Exception:
+        return {}
+
+
+def bind_to_gpu_numa(device: int):
+    """Pin this process (threads and first-touch host memory) to the NUMA node of its GPU, when the box exposes it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]).read())
+        if node < 0:
             return None
-    return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline
+# reference arm / cpu baseline: Mapping() of the unmodified reference on the host cores
 # --------------------------------------------------------------------------------------------------------------
-def time_reference(g, r1, r2, n_sample: int, repeats: int = 1):
-    """Pairs/s of the reference's own CPU implementation on the first n_sample pairs, all host threads.
-    Returns (pairs_per_s, kind, cores, sample description, seconds per run)."""
-    from mapcaller_b200 import api, simulate as sim
+_REF_CODE = r"""
+import sys, time, os
+sys.path.insert(0, %(tests)r)
+import ref_oracle as ro
+ro.load(%(prefix)r); ro.set_params(threads=%(cores)d)
+for i in range(%(runs)d):
+    ro.lib().mcref_reset_state(); t = time.perf_counter()
+    ro.lib().mcref_run_mapping(%(f1)r.encode(), %(f2)r.encode(), b'', %(cores)d, 1)
+    print('SECONDS', time.perf_counter() - t, ro.counters()['reads'], flush=True)
+"""
+
+
+def time_reference(ix, text1, text2, n_sample: int, rec_bytes: int, runs: int):
+    """Seconds per run of the reference's own CPU implementation on the first n_sample pairs, all host threads.
+    Returns (list of seconds, kind, cores, description)."""
     cores = os.cpu_count() or 1
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libmcref.so")
-    td = tempfile.mkdtemp(prefix="mcbench_")
+    td = tempfile.mkdtemp(prefix="mcbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     prefix = os.path.join(td, "idx")
-    ix = api.Index.build(sim.encode(g))
-    ix.save(prefix)
-    if os.path.exists(ref_so):
-        f1, f2 = os.path.join(td, "r1.fq"), os.path.join(td, "r2.fq")
-        sim.write_fastq(f1, r1[:n_sample], 1); sim.write_fastq(f2, r2[:n_sample], 2)
-        code = ("import sys, time, os; sys.path.insert(0, %r); import ref_oracle as ro\n"
-                "ro.load(%r); ro.set_params(threads=%d)\n"
-                "ts = []\n"
-                "for i in range(%d):\n"
-                "    ro.lib().mcref_reset_state(); t = time.perf_counter(); ro.lib().mcref_run_mapping(%r.encode(), %r.encode(), b'', %d, 1); ts.append(time.perf_counter() - t)\n"
-                "print('SECONDS', min(ts), ro.counters()['reads'])\n") % (os.path.join(ROOT, "tests"), prefix, cores, repeats, f1, f2, cores)
-        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
-        line = [l for l in out.stdout.splitlines() if l.startswith("SECONDS")]
-        if not line:
-            raise RuntimeError("reference run failed: " + out.stderr[-500:])
-        sec = float(line[0].split()[1])
-        kind, used = "reference", cores
-        what = "Mapping() of the unmodified reference (oracle/_ref), -t %d, VCF profile on, FASTQ parse included" % cores
-    else:
+    try:
+        ix.save(prefix)
+        if os.path.exists(ref_so):
+            f1, f2 = os.path.join(td, "r1.fq"), os.path.join(td, "r2.fq")
+            text1[:n_sample * rec_bytes].tofile(f1); text2[:n_sample * rec_bytes].tofile(f2)
+            code = _REF_CODE % dict(tests=os.path.join(ROOT, "tests"), prefix=prefix, cores=cores, runs=runs, f1=f1, f2=f2)
+            out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+            secs = [float(l.split()[1]) for l in out.stdout.splitlines() if l.startswith("SECONDS")]
+            if len(secs) != runs:
+                raise RuntimeError("reference run failed: " + out.stderr[-500:])
+            return secs, "reference", cores, "first %d pairs of the library; Mapping() of the unmodified reference (oracle/_ref), -t %d, VCF profile on, FASTQ parse included, index load excluded" % (n_sample, cores)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import cpu_oracle
-        seq, off = sim.interleave(r1[:n_sample], r2[:n_sample])
+        from mapcaller_b200 import simulate as sim
+        L = READ_LEN
+        w = rec_bytes - (2 * L + 5)
+        m1 = text1[:n_sample * rec_bytes].reshape(n_sample, rec_bytes)[:, w + 1:w + 1 + L]
+        m2 = text2[:n_sample * rec_bytes].reshape(n_sample, rec_bytes)[:, w + 1:w + 1 + L]
+        seq, off = sim.interleave(m1, m2)
         orc = cpu_oracle.Oracle(prefix)
-        t = time.perf_counter(); orc.map_reads(seq, off, True, True); sec = time.perf_counter() - t
+        secs = []
+        for _ in range(runs):
+            t = time.perf_counter(); orc.map_reads(seq, off, True, True); secs.append(time.perf_counter() - t)
         orc.close()
-        kind, used = "port", 1
-        what = "CPU restatement oracle/libmcoracle.so, single thread"
-    return n_sample / sec, kind, used, "first %d of %d pairs; %s" % (n_sample, len(r1), what), sec
+        return secs, "port", 1, "first %d pairs of the library; CPU restatement oracle/libmcoracle.so, single thread" % n_sample
+    finally:
+        import shutil
+        shutil.rmtree(td, ignore_errors=True)
+
+
+def cpu_sample_size(n_pairs: int, override: int, per_core: int = 60_000) -> int:
+    n = override or min(n_pairs, per_core * (os.cpu_count() or 1))
+    return max(100, n - n % 100)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -164,29 +222,42 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=FULL_PAIRS, help="library size per GPU (default: the full 50x library)")
+    ap.add_argument("--pairs", type=int, default=FULL_PAIRS, help="library size per GPU (default: the config's 10 M pairs)")
+    ap.add_argument("--genome", type=int, default=GENOME_LEN, help="genome size in bp (default: the config's 248,956,422)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (default: sized for ~10-30 s)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sam", action="store_true", help="skip the SAM flavour of the end-to-end leg")
+    ap.add_argument("--resident-only", action="store_true", help="profiling runs: only the resident leg (the JSON line then has no e2e)")
     args = ap.parse_args()
+    args.pairs -= args.pairs % SIM_BLOCK
+    assert args.pairs >= SIM_BLOCK, "--pairs must be at least %d" % SIM_BLOCK
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "configs[1]: E. coli-sized 4.6 Mbp synthetic reference, 2x100 bp simulated PE reads at 50x (%d pairs per GPU), -alg nw, VCF profile on" % args.pairs,
-              "genome_bp": GENOME_LEN, "read_len": READ_LEN, "pairs_per_gpu": args.pairs, "alg": "nw", "parallelism": "reads sharded over %d GPU(s) in file order (one library: avgDist / dedup gate / discordant-pair state exchanged over NCCL), full index replica per GPU" % world,
-              "l2_policy": "inputs larger than L2: 2x%d MB of reads per step stream through; the 6.9 MB index stays L2-resident" % (args.pairs * READ_LEN // 1_000_000)}
+    n_batches = (args.pairs + BATCH_PAIRS - 1) // BATCH_PAIRS
+    config = {"workload": "configs[2]: chr1-sized %d bp synthetic reference (15 %% repeat families), 2x%d bp simulated PE reads, %d pairs per GPU in batches of %d, -alg nw, VCF profile on"
+                          % (args.genome, READ_LEN, args.pairs, min(BATCH_PAIRS, args.pairs)),
+              "genome_bp": args.genome, "read_len": READ_LEN, "pairs_per_gpu": args.pairs, "batch_pairs": min(BATCH_PAIRS, args.pairs), "alg": "nw",
+              "parallelism": "reads sharded over %d GPU(s) in file order (one library: avgDist / dedup gate / discordant-pair state exchanged over NCCL inside every batch, profile reduced at the end of the pass), full index replica per GPU" % world
+                             if world > 1 else "one GPU, one index replica",
+              "l2_policy": "inputs larger than L2: index %.2f GB + %.1f GB of reads per batch stream from HBM" % (args.genome * 1.5 / 1e9, 2 * min(BATCH_PAIRS, args.pairs) * READ_LEN / 1e9)}
+    numa = bind_to_gpu_numa(local)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        g, r1, r2, _, _ = make_workload(args.pairs)
-        n_sample = args.cpu_sample or min(args.pairs, 150_000 * max(1, (os.cpu_count() or 1) // 4))
-        vals = []
-        for _ in range(args.warmup + args.steps):
-            v, kind, cores, what, sec = time_reference(g, r1, r2, n_sample)
-            vals.append((v, sec))
-        vals = vals[args.warmup:]
-        v = float(np.mean([x[0] for x in vals]))
+        from mapcaller_b200 import simulate as sim
+        g, mut = make_genome(args.genome)
+        n_sample = cpu_sample_size(args.pairs, args.cpu_sample)
+        r1, r2 = make_reads(mut, (n_sample + SIM_BLOCK - 1) // SIM_BLOCK * SIM_BLOCK, 0)
+        t1, t2 = sim.fastq_text(r1[:n_sample], 1), sim.fastq_text(r2[:n_sample], 2)
+        has_gpu = subprocess.call(["nvidia-smi", "-L"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0 if _which("nvidia-smi") else False
+        ix, how = build_index(g, 0 if has_gpu else None)
+        secs, kind, cores, what = time_reference(ix, t1, t2, n_sample, len(t1) // n_sample, args.warmup + args.steps)
+        secs = secs[args.warmup:]
+        v = n_sample * len(secs) / sum(secs)
         print(json.dumps({"impl": "reference", "metric": "read pairs mapped/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1000 * float(np.mean([x[1] for x in vals])), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
-                          "data": "synthetic", "config": config,
+                          "ms_per_step": 1000 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
+                          "data": "synthetic", "config": dict(config, reference_sample_pairs_per_step=n_sample, index_built_by=how),
                           "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": what},
                           "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -200,12 +271,15 @@ def main():
         dist_mod.init_process_group("nccl")
         dist = dist_mod
 
-    g, r1, r2, seq, off = make_workload(args.pairs, seed_shift=rank)
-    ix = api.Index.build(sim.encode(g))
+    t_setup = time.perf_counter()
+    g, mut = make_genome(args.genome)
+    ix, index_how = build_index(g, local)
+    t_index = time.perf_counter() - t_setup
+    r1, r2 = make_reads(mut, args.pairs, rank)
     n_pairs = len(r1)
     ctx = api.Context(ix, paired=1, alg_ksw2=0, update_profile=1, want_alignments=0, device=local, shard_rank=rank, shard_count=world)
     if dist is not None:
-        # the library's own NCCL communicator (NVLink / NVSwitch) for the end-of-pass profile reduction
+        # the library's own NCCL communicator (NVLink / NVSwitch): ordered exchange inside the batches + profile reduction
         uid = [api.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
@@ -215,14 +289,32 @@ def main():
             import torch
             dist.barrier(); torch.cuda.synchronize()
 
-    # page-locked copies of the inputs for the end-to-end legs (allocated up front: the clock sampler below should not
-    # see an idle GPU between the legs)
-    pseq = api.pinned_array(seq.shape, np.uint8); pseq[:] = seq
-    poff = api.pinned_array(off.shape, np.int64); poff[:] = off
+    # inputs: packed batches staged once in HBM (resident leg), FASTQ text of every batch in page-locked host memory (e2e)
+    bounds = [(b * BATCH_PAIRS, min(n_pairs, (b + 1) * BATCH_PAIRS)) for b in range(n_batches)]
+    ptext = []
+    for b, (p0, p1) in enumerate(bounds):
+        seq, off = sim.interleave(r1[p0:p1], r2[p0:p1])
+        ctx.stage_batch(seq, off, b)
+        del seq, off
+        pair = []
+        for mate, r in ((1, r1), (2, r2)):
+            t = sim.fastq_text(r[p0:p1], mate, first=p0)
+            pt = api.pinned_array(t.shape, np.uint8); pt[:] = t
+            pair.append(pt)
+            del t
+        ptext.append(pair)
+    rec_bytes = len(ptext[0][0]) // (bounds[0][1] - bounds[0][0])
+    chk1, chk2 = r1[:CHECK_PAIRS].copy(), r2[:CHECK_PAIRS].copy()
+    del r1, r2
+    t_setup = time.perf_counter() - t_setup
+    S_IN0, S_IN1 = n_batches, n_batches + 1      # device slots of the double-buffered FASTQ feed
+    assert n_batches + 2 <= 8
+
     # ---- resident leg (value) ----
-    ctx.stage_batch(seq, off, 0)
     def one_pass():
-        ctx.reset(); ctx.map_staged(0)
+        ctx.reset()
+        for b in range(n_batches):
+            ctx.map_staged(b)
         if dist is not None:
             ctx.profile_allreduce()      # every rank ends the pass with the whole-library profile
 
@@ -235,106 +327,158 @@ def main():
         one_pass()
     barrier(); wall_resident = time.perf_counter() - t0
     st = ctx.stats()
-    dev_s = st["ms_total"] / 1000.0
+    dev_s = max((st["ms_total"] + st["ms_reduce"]) / 1000.0, 1e-12)
     totals = ctx.totals()
+    resident_fp = ctx.profile_checksum()
 
-    # ---- end-to-end leg (host buffers through mc_map_batch) ----
-    # the step's inputs sit in page-locked host memory (mc_host_alloc), as the contract asks; every step copies them to
-    # the device and reads the per-pair / per-chunk results back
-    # (a) the double-buffered feed of a host that streams batches (mc_stage_batch_async + mc_map_staged): the copy of step
-    #     i+1's inputs is queued before step i is mapped, so it overlaps that mapping; every step's bytes cross PCIe inside
-    #     the timed region (steps copies for steps steps, the first one is not overlapped with anything)
-    def feed(steps):
-        ctx.stage_batch_async(pseq, poff, 0)
-        for i in range(steps):
-            ctx.reset()
-            if i + 1 < steps:
-                ctx.stage_batch_async(pseq, poff, (i + 1) & 1)
-            ctx.map_staged(i & 1, copy=False)
-            if dist is not None:
-                ctx.profile_allreduce()
-    feed(max(2, args.warmup // 2))
-    barrier(); t0 = time.perf_counter()
-    feed(args.steps)
-    barrier(); wall_e2e = time.perf_counter() - t0
-    # (b) one synchronous mc_map_batch call per step (upload in four pieces, seeding overlapped)
-    for _ in range(max(1, args.warmup // 2)):
-        ctx.reset(); ctx.map_batch(pseq, poff, copy=False)
-    barrier(); t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.reset(); res = ctx.map_batch(pseq, poff, copy=False)
+    # ---- end-to-end leg: FASTQ text (host) -> variant records (host) ----
+    def fastq_pass(sam: bool):
+        ctx.reset()
+        err = []
+        ready = [threading.Semaphore(0), threading.Semaphore(0)]; free = [threading.Semaphore(1), threading.Semaphore(1)]
+
+        def feeder():
+            try:
+                for b in range(n_batches):
+                    free[b & 1].acquire()
+                    ctx.ingest_fastq(ptext[b][0], ptext[b][1], slot=S_IN0 + (b & 1), final=True, keep_text=sam)
+                    ready[b & 1].release()
+            except Exception as e:      # surfaces in the main thread
+                err.append(e)
+                for s in ready:
+                    s.release()
+        th = threading.Thread(target=feeder); th.start()
+        sam_bytes = 0
+        for b in range(n_batches):
+            ready[b & 1].acquire()
+            if err:
+                break
+            ctx.map_staged(S_IN0 + (b & 1))
+            if sam:
+                sam_bytes += ctx.sam_text_raw(S_IN0 + (b & 1))
+            free[b & 1].release()
+        th.join()
+        if err:
+            raise err[0]
         if dist is not None:
             ctx.profile_allreduce()
-    barrier(); wall_sync = time.perf_counter() - t0
-    clocks = sampler.stop()   # sampled every 20 ms across the resident and both end-to-end legs, back to back
-    # same call with ordinary pageable numpy arrays (bounced through pinned buffers inside the library)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.reset(); ctx.map_batch(seq, off, copy=False)
-    wall_pageable = time.perf_counter() - t0
-    # (c) from FASTQ text: the raw bytes of the two mate files in page-locked memory, parsed on the device (mc_ingest_fastq)
-    ft1, ft2 = sim.fastq_text(r1, 1), sim.fastq_text(r2, 2)
-    pf1 = api.pinned_array(ft1.shape, np.uint8); pf1[:] = ft1
-    pf2 = api.pinned_array(ft2.shape, np.uint8); pf2[:] = ft2
-    del ft1, ft2
-    for _ in range(2):
-        ctx.reset(); ctx.ingest_fastq(pf1, pf2, slot=2); ctx.map_staged(2, copy=False)
-    barrier(); t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.reset(); ctx.ingest_fastq(pf1, pf2, slot=2); ctx.map_staged(2, copy=False)
-        if dist is not None:
-            ctx.profile_allreduce()
-    barrier(); wall_fastq = time.perf_counter() - t0
-    n_reads = 2 * n_pairs
-    h2d = int(seq.nbytes + (n_reads + 1) * 8 + 5 * ((n_reads + 199) // 200))
-    d2h = int(((n_reads + 199) // 200) * (32 + 8) + 72 + 64 + 8 * 4 + 40 * 2048)   # per-chunk sums + intervals, counters, cursors, the list of discordant pairs (<= ~2 k records here)
+        n_var, n_blk = ctx.variant_scan_raw()
+        return n_var, sam_bytes
+
+    def timed_fastq(sam: bool):
+        for _ in range(max(2, args.warmup // 2)):
+            fastq_pass(sam)
+        s0 = ctx.stats()
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.steps):
+            n_var, sam_bytes = fastq_pass(sam)
+        barrier(); wall = time.perf_counter() - t0
+        s1 = ctx.stats()
+        return wall, (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps, (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps, n_var, sam_bytes
+
+    if args.resident_only:
+        wall_e2e, h2d, d2h, n_var, e2e_fp, e2e_totals = float("inf"), 0, 0, 0, resident_fp, totals
+    else:
+        wall_e2e, h2d, d2h, n_var, _ = timed_fastq(False)
+        e2e_fp = ctx.profile_checksum(); e2e_totals = ctx.totals()
+    sam_leg = None
+    if not args.no_sam and not args.resident_only and hasattr(api.Context, "sam_text_raw"):
+        w, h, d, _, sam_bytes = timed_fastq(True)
+        sam_leg = (w, h, d, sam_bytes)
+
+    # ---- packed-read feed (round-1 definition, kept for continuity): pre-parsed reads in page-locked memory ----
+    p0, p1 = bounds[0]
+    seq0 = api.pinned_array(((p1 - p0) * 2 * READ_LEN,), np.uint8); off0 = api.pinned_array(((p1 - p0) * 2 + 1,), np.int64)
+    w = rec_bytes - (2 * READ_LEN + 5)
+    m1 = ptext[0][0].reshape(p1 - p0, rec_bytes)[:, w + 1:w + 1 + READ_LEN]; m2 = ptext[0][1].reshape(p1 - p0, rec_bytes)[:, w + 1:w + 1 + READ_LEN]
+    seq0.reshape(-1, 2, READ_LEN)[:, 0] = m1; seq0.reshape(-1, 2, READ_LEN)[:, 1] = m2
+    off0[:] = np.arange(len(off0), dtype=np.int64) * READ_LEN
+    wall_packed = float("inf")
+    if not args.resident_only:
+        ctx.reset(); ctx.map_batch(seq0, off0, copy=False)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.reset(); ctx.map_batch(seq0, off0, copy=False)
+        barrier(); wall_packed = time.perf_counter() - t0
+    clocks = sampler.stop()   # sampled every 20 ms across the resident and the end-to-end legs, back to back
+
+    # ---- N GPUs on one library == one GPU on the same reads (bit-exact profile and totals) ----
+    check = {"mapped_fraction": totals["total_mapped"] / max(1, totals["total_reads"]), "avg_dist": totals["avg_dist"],
+             "fastq_path_equals_resident": bool(e2e_fp == resident_fp and e2e_totals == totals), "variant_records": int(n_var)}
+    if dist is not None:
+        cseq, coff = sim.interleave(chk1, chk2)
+        ctx.reset(); ctx.map_batch(cseq, coff, copy=False); ctx.profile_allreduce()
+        multi_fp, multi_tot = ctx.profile_checksum(), ctx.totals()
+        if rank == 0:
+            solo = api.Context(ix, paired=1, alg_ksw2=0, update_profile=1, want_alignments=0, device=local)
+            for r in range(world):
+                a1, a2 = (chk1, chk2) if r == 0 else make_reads(mut, CHECK_PAIRS, r)
+                s_, o_ = sim.interleave(a1, a2)
+                solo.map_batch(s_, o_, copy=False)
+            check["n_gpu_equals_1_gpu"] = bool(solo.profile_checksum() == multi_fp and solo.totals() == multi_tot)
+            check["n_gpu_check_pairs"] = CHECK_PAIRS * world
+            solo.close()
+        barrier()
 
     if dist is not None:
         import torch
-        # multi-GPU: the pass includes the NCCL reduction, which the per-context CUDA events do not see -> the time between the
-        # barriers (each with a device synchronize) is the step time, max over ranks
-        # device time of the resident leg = CUDA events of the mapping (ms_total) + of the reduction (ms_reduce) on the
-        # context's stream, max over ranks; the time between the barriers (wall, also max over ranks) is reported beside it
-        t = torch.tensor([(st["ms_total"] + st["ms_reduce"]) / 1000.0, wall_e2e, wall_resident, wall_sync], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_s, wall_e2e, wall_resident, wall_packed, sam_leg[0] if sam_leg else 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, wall_e2e, wall_resident, wall_sync = [float(x) for x in t.tolist()]
+        dev_s, wall_e2e, wall_resident, wall_packed, wsam = [float(x) for x in t.tolist()]
+        if sam_leg:
+            sam_leg = (wsam,) + sam_leg[1:]
     total_pairs = n_pairs * world * args.steps
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        seed_bytes = st["seed_blocks"] * 64 / args.steps
-        seed_ms = st["ms_seed"] / args.steps
-        achieved = seed_bytes / (seed_ms * 1e-3) / 1e9 if seed_ms > 0 else 0.0
-        tr = recorded_traffic()
+        tr = recorded_traffic(args.genome)
+        launches = n_batches * args.steps
+
+        def roof(kernel, alg_bytes, ms, note):
+            a = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            t = (tr.get("kernels") or {}).get(kernel) or {}
+            o = {"kernel": kernel, "bound": "hbm", "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak,
+                 "traffic": t.get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": alg_bytes / launches, "ms_per_launch": ms / launches, "launches_timed": launches, "note": note}
+            if t.get("dram_bytes_per_launch") and ms > 0:
+                o["dram_frac"] = t["dram_bytes_per_launch"] * launches / (ms * 1e-3) / 1e9 / peak
+                o["traffic_source"] = tr.get("source")
+            return o
         line = {"metric": "read pairs mapped/sec", "value": total_pairs / dev_s, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
                 "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(st["kernel_launches"]),
-                "e2e": {"value": total_pairs / wall_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * wall_e2e / args.steps,
-                        "how": "mc_stage_batch_async(step i+1) + mc_map_staged(step i) from page-locked host arrays: every step's inputs are copied inside the timed region, the copy overlaps the previous step's mapping",
-                        "sync_call_pairs_per_s": total_pairs / wall_sync, "sync_call_ms_per_step": 1000 * wall_sync / args.steps},
-                "roofline": {"kernel": "mc_seed_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": (tr or {}).get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": seed_bytes, "ms_per_launch": seed_ms,
-                             "note": "the 4.6 MB compact index is L2-resident at this genome size, so achieved (64 B x reference blocks, SURVEY 8d) counts L2-served bytes against the HBM peak and can exceed it; hbm_regime = the same kernel on a 248 Mbp genome (committed ncu capture, tools/big_genome.py)",
-                             "hbm_regime": {k: v for k, v in ((tr or {}).get("hbm_regime") or {}).items() if k != "metrics"} or None},
-                "stages_ms_per_step": {k: st[k] / args.steps for k in ("ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile", "ms_h2d", "ms_d2h", "ms_total")},
-                "work_per_step": {k: st[k] / args.steps for k in ("seed_blocks", "locate_blocks", "sa_reads", "dp_cells", "dp_tasks", "profile_columns")},
-                "locate_gbs": (st["locate_blocks"] * 64 + st["sa_reads"] * 8) / (st["ms_locate"] * 1e-3) / 1e9 if st["ms_locate"] > 0 else None,
+                "e2e": {"value": total_pairs / wall_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1000 * wall_e2e / args.steps,
+                        "how": "FASTQ text of both mate files in page-locked host memory -> mc_ingest_fastq (H2D + record parse on the device; a feeder thread stages block i+1 while block i is mapped) -> mc_map_staged -> "
+                               + ("mc_profile_allreduce -> " if world > 1 else "") + "mc_variant_scan (variant records + block depths back in host memory); bytes = the library's copy counters (this rank)",
+                        "variant_records": int(n_var)},
+                "roofline": roof("mc_seed_kernel", st["seed_blocks"] * 64, st["ms_seed"], "algorithmic bytes = 64 B x occ blocks of the reference algorithm (kernel counter = oracle count); time = CUDA events around the seed launches of the timed steps"),
+                "roofline_locate": roof("mc_locate_kernel", st["locate_blocks"] * 64 + st["sa_reads"] * 8, st["ms_locate"], "64 B per LF step + 8 B per sampled-SA read"),
+                "roofline_profile": roof("profile stage", st["profile_columns"] * 32, st["ms_profile"], "reference formulation: 32 B (read + write of one MappingRecord_t) per column a counted read covers; the stage = gate sort + scatter + piece kernels"),
+                "stages_ms_per_step": {k: st[k] / args.steps for k in ("ms_reset", "ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile", "ms_h2d", "ms_d2h", "ms_reduce", "ms_total")},
+                "work_per_step": {k: st[k] / args.steps for k in ("seed_blocks", "locate_blocks", "sa_reads", "dp_cells", "dp_tasks", "profile_columns", "profile_atomics")},
                 "dp_gcups": st["dp_cells"] / (st["ms_align"] * 1e-3) / 1e9 if st["ms_align"] > 0 else None,
-                "wall_ms_per_step_resident": 1000 * wall_resident / args.steps, "e2e_pageable_pairs_per_s": n_pairs * args.steps / wall_pageable,
-                "e2e_from_fastq_text": {"pairs_per_s_this_rank": n_pairs * args.steps / wall_fastq, "ms_per_step": 1000 * wall_fastq / args.steps, "fastq_bytes_per_step": int(pf1.nbytes + pf2.nbytes),
-                                        "how": "raw bytes of the two mate FASTQ files (page-locked) -> mc_ingest_fastq (records found on the device) -> mc_map_staged"},
-                "check": {"mapped_fraction": totals["total_mapped"] / max(1, totals["total_reads"]), "avg_dist": totals["avg_dist"]}}
-        if world == 1:
-            n_sample = args.cpu_sample or min(n_pairs, 150_000 * max(1, (os.cpu_count() or 1) // 4))
+                "wall_ms_per_step_resident": 1000 * wall_resident / args.steps,
+                "e2e_packed_reads": {"pairs_per_s_this_rank": (p1 - p0) * args.steps / wall_packed, "ms_per_batch": 1000 * wall_packed / args.steps,
+                                     "how": "one batch of pre-parsed reads in page-locked memory through mc_map_batch (the round-1 e2e definition; no FASTQ parse, no result read-out)"},
+                "setup_s": {"total": t_setup, "genome_and_index": t_index, "index": index_how}, "numa_node": numa, "check": check}
+        if sam_leg:
+            line["e2e"]["sam"] = {"value": total_pairs / sam_leg[0], "unit": "pairs/s", "ms_per_step": 1000 * sam_leg[0] / args.steps, "h2d_bytes_per_step": int(sam_leg[1]), "d2h_bytes_per_step": int(sam_leg[2]),
+                                  "sam_text_bytes_per_step": int(sam_leg[3]), "how": "the same loop with the SAM text of every read assembled on the device from the resident FASTQ text and copied back (mc_sam_text)"}
+        if world == 1 and not args.no_cpu:
+            n_sample = cpu_sample_size(bounds[0][1], args.cpu_sample, 150_000)
             try:
-                v, kind, cores, what, sec = time_reference(g, r1, r2, n_sample)
-                line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": what, "seconds": sec}
+                secs, kind, cores, what = time_reference(ix, ptext[0][0], ptext[0][1], n_sample, rec_bytes, 1)
+                line["cpu_baseline"] = {"value": n_sample / secs[0], "unit": "pairs/s", "cores": cores, "kind": kind, "sample": what, "seconds": secs[0]}
             except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
                 line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _which(x):
+    import shutil
+    return shutil.which(x)
 
 
 if __name__ == "__main__":

@@ -159,8 +159,12 @@ void mc_host_free(void *p);
 typedef struct { int64_t total_reads, total_mapped, total_paired, total_distance, read_length_sum; uint32_t avg_dist; uint32_t pad; } mc_totals;
 int mc_get_totals(const mc_ctx *ctx, mc_totals *out);
 int mc_set_totals(mc_ctx *ctx, const mc_totals *in);
-/* Back to the state of a fresh context (empty profile, avgDist = 1000, totals 0): the start of a new library run. */
+/* Back to the state of a fresh context (empty profile, avgDist = 1000, totals 0): the start of a new run. */
 int mc_reset(mc_ctx *ctx);
+/* The next batch starts a new library of the same run (the loop over -f files of Mapping(), reference
+ * src/ReadMapping.cpp:705-748): the 200-read chunk grid restarts, while the profile, the totals and avgDist keep
+ * accumulating.  Needed after a batch that was not a whole number of chunks (which ends a library). */
+int mc_begin_library(mc_ctx *ctx);
 
 /* ---- profile (reference MappingRecordArr / InsertSeqMap / DeleteSeqMap / BreakPointMap /
  *      InversionSiteVec / TranslocationSiteVec; src/structure.h:152-163,220-221) --------------- */
@@ -176,6 +180,10 @@ int mc_profile_read(mc_ctx *ctx, int64_t beg, int64_t end, void *out);
  * duplication rate = 100 * (dup_reads - dup_sites) / dup_sites. */
 typedef struct { int64_t aligned_bases, coverage_sum, dup_sites, dup_reads; } mc_profile_stats;
 int mc_profile_summary(mc_ctx *ctx, mc_profile_stats *out);
+/* Order-independent 128-bit fingerprint of the whole profile as mc_profile_read() would return it (every column's
+ * MappingRecord_t mixed with its position, summed and xor-ed over the genome) - computed on the device; equal profiles
+ * give equal fingerprints.  bench.py uses it to check that N GPUs on one library produce the single-GPU profile. */
+int mc_profile_checksum(mc_ctx *ctx, uint64_t out[2]);
 
 typedef struct { int64_t pos; int32_t kind /* 0 ins, 1 del */, len, count, seq_off; } mc_indel_rec;
 /* Unique (pos, kind, sequence) triples with their uint16-wrapped counts, sorted by (kind,pos,seq). */
@@ -267,6 +275,9 @@ typedef struct {
 } mc_fastq_in;
 typedef struct { int64_t n_reads, consumed1, consumed2, n_bases; } mc_fastq_out;
 int mc_ingest_fastq(mc_ctx *ctx, const mc_fastq_in *in, int32_t slot, mc_fastq_out *out);
+/* mc_ingest_fastq() works on the context's copy stream with scratch of its own: a second host thread may ingest the next
+ * block into slot s' while mc_map_staged() maps slot s != s' (the one exception to "calls on one ctx are serialised";
+ * the text must then lie in page-locked memory, mc_host_alloc). */
 
 /* ---- operator-level entry points (per-kernel parity tests and micro-benchmarks) ---------------- */
 
@@ -308,10 +319,13 @@ typedef struct {
     int64_t profile_atomics;  /* atomic updates the device profile actually needed for them */
     int64_t kernel_launches;
     double ms_reduce;         /* device time of mc_profile_allreduce (multi-GPU), CUDA events on the context's stream */
+    int64_t h2d_bytes;        /* bytes this process copied host -> device / device -> host through the library since the last */
+    int64_t d2h_bytes;        /* mc_reset_stats (counted where the copies are issued) */
+    double ms_reset;          /* device time of mc_reset (zeroing the profile); also part of ms_total */
 } mc_stats;
 int mc_get_stats(const mc_ctx *ctx, mc_stats *out);   /* accumulated since create / last reset */
 int mc_reset_stats(mc_ctx *ctx);
-/* Double-buffered feed: a batch is copied into one of four device slots and mapped from there, any number of times.
+/* Double-buffered feed: a batch is copied into one of eight device slots and mapped from there, any number of times.
  * mc_stage_batch_async() only queues the copy (and the reversal of mate 2) on the context's copy stream and returns; the
  * caller's buffers must stay untouched until the next mc_map_staged() of that slot has returned (page-locked buffers from
  * mc_host_alloc are copied by DMA, pageable ones are bounced synchronously).  A host that maps batch i from slot i & 1

@@ -92,7 +92,8 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("ms_seed", "ms_locate", "ms_cluster", "ms_pair", "ms_align", "ms_profile",
                                            "ms_h2d", "ms_d2h", "ms_total")] + \
                [(k, C.c_int64) for k in ("seed_blocks", "locate_blocks", "sa_reads", "dp_cells", "dp_tasks",
-                                          "profile_columns", "profile_atomics", "kernel_launches")] + [("ms_reduce", C.c_double)]
+                                          "profile_columns", "profile_atomics", "kernel_launches")] + [("ms_reduce", C.c_double)] + \
+               [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("ms_reset", C.c_double)]
 
 
 READ_DT = np.dtype([("score", "<i4"), ("sub_score", "<i4"), ("best_idx", "<i4"), ("cand_begin", "<i4"), ("n_cand", "<i4"), ("rlen", "<i4")])
@@ -141,6 +142,8 @@ def lib():
         L.mc_reset_stats.argtypes = [C.c_void_p]
         L.mc_profile_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.mc_profile_summary.argtypes = [C.c_void_p, C.c_void_p]
+        L.mc_profile_checksum.argtypes = [C.c_void_p, C.c_void_p]
+        L.mc_begin_library.argtypes = [C.c_void_p]
         L.mc_profile_indels.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
         L.mc_profile_breakpoints.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_profile_sites.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
@@ -291,7 +294,7 @@ class Context:
         self._staging = getattr(self, "_staging", {}); self._staging[slot] = keep
         _check(lib().mc_stage_batch_async(self._h, C.byref(b), slot), "mc_stage_batch_async")
 
-    def ingest_fastq(self, text1, text2=None, slot: int = 0, max_reads: int = 0, final: bool = True) -> dict:
+    def ingest_fastq(self, text1, text2=None, slot: int = 0, max_reads: int = 0, final: bool = True, keep_text: bool = False) -> dict:
         """Parses blocks of FASTQ text (bytes / uint8 arrays; one per mate file, or one with adjacent mates) on the device into
         slot `slot`; returns n_reads, consumed1, consumed2, n_bases.  map_staged(slot) maps the batch."""
         t1 = np.frombuffer(text1, dtype=np.uint8) if isinstance(text1, (bytes, bytearray)) else np.ascontiguousarray(text1, dtype=np.uint8)
@@ -378,6 +381,14 @@ class Context:
     def reset(self):
         _check(lib().mc_reset(self._h), "mc_reset")
 
+    def begin_library(self):
+        _check(lib().mc_begin_library(self._h), "mc_begin_library")
+
+    def profile_checksum(self):
+        v = (C.c_uint64 * 2)()
+        _check(lib().mc_profile_checksum(self._h, v), "mc_profile_checksum")
+        return int(v[0]), int(v[1])
+
     def stats(self) -> dict:
         s = Stats()
         _check(lib().mc_get_stats(self._h, C.byref(s)), "mc_get_stats")
@@ -448,6 +459,17 @@ class Context:
             out.append(dict(gPos=int(x["gPos"]), VarType=t, DP=int(x["DP"]), AD_ref=int(x["AD_ref"]), AD_alt=int(x["AD_alt"]),
                             GenoType=int(x["GenoType"]), qscore=int(x["qscore"]), alt=alt, record=(int(x["rec0"]), int(x["rec1"]))))
         return out, _view(depth.value, nb.value, np.dtype("<i4")).copy()
+
+    def variant_scan_raw(self, **kw):
+        """mc_variant_scan without unpacking: the records stay in the library's host buffers; returns (n_records, n_blocks)."""
+        vp = VcParams()
+        lib().mc_vc_params_default(C.byref(vp))
+        for k, v in kw.items():
+            setattr(vp, k, v)
+        recs, n, arena, depth, nb = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _check(lib().mc_variant_scan(self._h, C.byref(vp), C.byref(recs), C.byref(n), C.byref(arena), C.byref(depth), C.byref(nb)),
+               "mc_variant_scan")
+        return int(n.value), int(nb.value)
 
     def breakpoints(self):
         recs, n = C.c_void_p(), C.c_int64()

@@ -14,6 +14,7 @@
 #endif
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -32,6 +33,7 @@ static int dev_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0
 static void dev_free(void* p) { free(p); }
 static int host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : -1; }
 static void host_free(void* p) { free(p); }
+static std::atomic<int64_t> g_h2d_bytes(0), g_d2h_bytes(0);
 static int dev_h2d(void* d, const void* h, size_t n, mc_stream_t) { memcpy(d, h, n); return 0; }
 static int dev_d2h(void* h, const void* d, size_t n, mc_stream_t) { memcpy(h, d, n); return 0; }
 static int dev_d2d(void* d, const void* s, size_t n, mc_stream_t) { memcpy(d, s, n); return 0; }
@@ -53,8 +55,9 @@ static int dev_alloc(void** p, size_t n) { return cuda_fail(cudaMalloc(p, n ? n 
 static void dev_free(void* p) { if (p) cudaFree(p); }
 static int host_alloc(void** p, size_t n) { return cuda_fail(cudaMallocHost(p, n ? n : 1), "cudaMallocHost"); }
 static void host_free(void* p) { if (p) cudaFreeHost(p); }
-static int dev_h2d(void* d, const void* h, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "H2D copy") : 0; }
-static int dev_d2h(void* h, const void* d, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "D2H copy") : 0; }
+static std::atomic<int64_t> g_h2d_bytes(0), g_d2h_bytes(0);   // what really crossed PCIe (reported by mc_get_stats)
+static int dev_h2d(void* d, const void* h, size_t n, mc_stream_t s) { g_h2d_bytes += (int64_t)n; return n ? cuda_fail(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "H2D copy") : 0; }
+static int dev_d2h(void* h, const void* d, size_t n, mc_stream_t s) { g_d2h_bytes += (int64_t)n; return n ? cuda_fail(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "D2H copy") : 0; }
 static int dev_d2d(void* d, const void* sp, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemcpyAsync(d, sp, n, cudaMemcpyDeviceToDevice, s), "D2D copy") : 0; }
 static int dev_zero(void* d, size_t n, mc_stream_t s) { return n ? cuda_fail(cudaMemsetAsync(d, 0, n, s), "memset") : 0; }
 static int dev_sync(mc_stream_t s)
@@ -155,7 +158,7 @@ struct HBuf {
 	template <class T> T* as() const { return (T*)p; }
 };
 
-enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_RED0, EV_RED1, EV_COUNT };
+enum { EV_START, EV_H2D, EV_SEED0, EV_SEED, EV_LOC0, EV_LOCATE, EV_CLUSTER, EV_PAIR0, EV_PAIR1, EV_ALN1, EV_PROF0, EV_PROF1, EV_D2H, EV_RED0, EV_RED1, EV_RST0, EV_RST1, EV_COUNT };
 
 struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask, rwin; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
@@ -176,7 +179,7 @@ struct mc_ctx {
 	DBuf d_bp, d_ind, d_ind_seq, d_pbump;
 	int64_t bp_cap = 0, ind_cap = 0, ind_seq_cap = 0;
 	// batch arenas
-	Staged cur; Staged slots[4];
+	Staged cur; Staged slots[MC_SLOTS];
 	DBuf d_slot_freq, d_seeds, d_slot_loc, d_loc_slot, d_pairs, d_npair;
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
@@ -186,7 +189,7 @@ struct mc_ctx {
 	HBuf h_bounce[2];
 	mc_stream_t cstream;
 #ifndef MC_HOSTEMU
-	cudaEvent_t ev_bounce[2], ev_piece[8], ev_slot[4];
+	cudaEvent_t ev_bounce[2], ev_piece[8], ev_slot[MC_SLOTS];
 #endif
 	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
@@ -241,7 +244,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	for (DBuf* b : bufs) b->release();
 	for (DBuf& b : c->d_vc) b.release();
 	for (DBuf& b : c->d_sam) b.release();
-	Staged* st[] = {&c->cur, &c->slots[0], &c->slots[1], &c->slots[2], &c->slots[3]};
+	std::vector<Staged*> st; st.push_back(&c->cur); for (int i = 0; i < MC_SLOTS; i++) st.push_back(&c->slots[i]);
 	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); s->flag.release(); }
 	DBuf* fq[] = {&c->fq_text[0], &c->fq_text[1], &c->fq_cnt[0], &c->fq_cnt[1], &c->fq_off[0], &c->fq_off[1], &c->fq_lines[0], &c->fq_lines[1], &c->fq_scan, &c->fq_rlen, &c->fq_rsrc};
 	for (DBuf* b : fq) b->release();
@@ -255,7 +258,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	c->h_bounce[0].release(); c->h_bounce[1].release();
 #ifndef MC_HOSTEMU
 	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]); for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev_piece[i]);
-	for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev_slot[i]);
+	for (int i = 0; i < MC_SLOTS; i++) cudaEventDestroy(c->ev_slot[i]);
 	if (c->cstream) cudaStreamDestroy(c->cstream);
 	if (c->stream) cudaStreamDestroy(c->stream);
 #endif
@@ -287,7 +290,7 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 #ifndef MC_HOSTEMU
 	cudaEventCreateWithFlags(&c->ev_bounce[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bounce[1], cudaEventDisableTiming);
 	for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&c->ev_piece[i], cudaEventDisableTiming);
-	for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&c->ev_slot[i], cudaEventDisableTiming);
+	for (int i = 0; i < MC_SLOTS; i++) cudaEventCreateWithFlags(&c->ev_slot[i], cudaEventDisableTiming);
 #endif
 	const int64_t G = v.genome_size; c->G = G;
 	std::vector<int64_t> ends; std::vector<int32_t> ids;
@@ -347,16 +350,29 @@ int mc_reset(mc_ctx* c)
 #endif
 	if (!c) { mc_set_error("mc_reset: null context"); return MC_ERR_ARG; }
 	int bad = 0;
+	ev_record(&c->ev[EV_RST0], c->stream);
 	if (c->prm.update_profile)
 	{
 		const size_t G = (size_t)c->G;
 		bad |= dev_zero(c->d_base16.p, G * 8, c->stream) || dev_zero(c->d_sdiff.p, (G + 1) * 16, c->stream) || dev_zero(c->d_cdiff.p, (G + 1) * 4, c->stream);
 		bad |= dev_zero(c->d_mdiff.p, (G + 1) * 4, c->stream) || dev_zero(c->d_rcount.p, G, c->stream);
 	}
-	bad |= dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream) || dev_sync(c->stream);
+	bad |= dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream);
+	ev_record(&c->ev[EV_RST1], c->stream);
+	bad |= dev_sync(c->stream);
+	if (!bad) { const double ms = ev_ms(&c->ev[EV_RST0], &c->ev[EV_RST1]); c->stats.ms_reset += ms; c->stats.ms_total += ms; }
 	memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = 1000;
 	c->inv_sites.clear(); c->tnl_sites.clear(); c->discord_gpos = c->discord_dist = 0; c->library_closed = false;
 	return bad ? MC_ERR_CUDA : MC_OK;
+}
+
+// The loop over libraries of Mapping() (reference src/ReadMapping.cpp:705-748): every library is cut into 200-read chunks from
+// its own start; the profile, the totals and avgDist carry over.
+int mc_begin_library(mc_ctx* c)
+{
+	if (!c) { mc_set_error("mc_begin_library: null context"); return MC_ERR_ARG; }
+	c->library_closed = false;
+	return MC_OK;
 }
 
 int mc_host_alloc(size_t bytes, void** out)
@@ -368,8 +384,8 @@ void mc_host_free(void* p) { host_free(p); }
 
 int mc_get_totals(const mc_ctx* c, mc_totals* out) { if (!c || !out) return MC_ERR_ARG; *out = c->tot; return MC_OK; }
 int mc_set_totals(mc_ctx* c, const mc_totals* in) { if (!c || !in) return MC_ERR_ARG; c->tot = *in; return MC_OK; }
-int mc_get_stats(const mc_ctx* c, mc_stats* out) { if (!c || !out) return MC_ERR_ARG; *out = c->stats; out->kernel_launches = g_launches; return MC_OK; }
-int mc_reset_stats(mc_ctx* c) { if (!c) return MC_ERR_ARG; zero_stats(&c->stats); g_launches = 0; return MC_OK; }
+int mc_get_stats(const mc_ctx* c, mc_stats* out) { if (!c || !out) return MC_ERR_ARG; *out = c->stats; out->kernel_launches = g_launches; out->h2d_bytes = g_h2d_bytes; out->d2h_bytes = g_d2h_bytes; return MC_OK; }
+int mc_reset_stats(mc_ctx* c) { if (!c) return MC_ERR_ARG; zero_stats(&c->stats); g_launches = 0; g_h2d_bytes = 0; g_d2h_bytes = 0; return MC_OK; }
 
 } // extern "C"
 
@@ -1005,7 +1021,7 @@ int mc_map_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
 
 int mc_stage_batch_async(mc_ctx* c, const mc_batch_in* in, int32_t slot)
 {
-	if (!c || !in || slot < 0 || slot >= 4) { mc_set_error("mc_stage_batch: bad argument"); return MC_ERR_ARG; }
+	if (!c || !in || slot < 0 || slot >= MC_SLOTS) { mc_set_error("mc_stage_batch: bad argument"); return MC_ERR_ARG; }
 #ifndef MC_HOSTEMU
 	cudaSetDevice(c->prm.device);
 #endif
@@ -1033,7 +1049,7 @@ int mc_stage_batch(mc_ctx* c, const mc_batch_in* in, int32_t slot)
 
 int mc_map_staged(mc_ctx* c, int32_t slot, mc_batch_out* out)
 {
-	if (!c || !out || slot < 0 || slot >= 4 || !c->slots[slot].valid) { mc_set_error("mc_map_staged: slot not staged"); return MC_ERR_ARG; }
+	if (!c || !out || slot < 0 || slot >= MC_SLOTS || !c->slots[slot].valid) { mc_set_error("mc_map_staged: slot not staged"); return MC_ERR_ARG; }
 #ifndef MC_HOSTEMU
 	cudaSetDevice(c->prm.device);
 	if (c->slots[slot].pending)
@@ -1049,11 +1065,11 @@ int mc_map_staged(mc_ctx* c, int32_t slot, mc_batch_out* out)
 // Read ingest on the device: raw FASTQ text -> a staged batch (mc_map_staged maps it).  See include/mapcaller_b200.h.
 int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out* out)
 {
-	if (!c || !in || !out || slot < 0 || slot >= 4 || !in->text1 || in->len1 < 0 || (in->text2 && in->len2 < 0)) { mc_set_error("mc_ingest_fastq: bad argument"); return MC_ERR_ARG; }
+	if (!c || !in || !out || slot < 0 || slot >= MC_SLOTS || !in->text1 || in->len1 < 0 || (in->text2 && in->len2 < 0)) { mc_set_error("mc_ingest_fastq: bad argument"); return MC_ERR_ARG; }
 #ifndef MC_HOSTEMU
 	cudaSetDevice(c->prm.device);
 #endif
-	const mc_stream_t s = c->stream;
+	const mc_stream_t s = c->cstream;   // the copy stream: another host thread may be mapping a different slot on c->stream
 	memset(out, 0, sizeof(*out));
 	Staged& st = c->slots[slot];
 	st.valid = false; st.pending = false; st.n_pieces = 0; st.h_roff.clear();
@@ -1146,7 +1162,7 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 }
 
 // packs the columns [beg, end) tile by tile; every tile is either copied to `outp` or reduced into the four counters `acc`
-static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64* d_acc)
+static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64* d_acc, bool checksum = false)
 {
 	DevProfile p; p.base16 = c->d_base16.as<uint32_t>(); p.sdiff = c->d_sdiff.as<int32_t>(); p.cdiff = c->d_cdiff.as<int32_t>(); p.mdiff = c->d_mdiff.as<int32_t>();
 	p.rcount = c->d_rcount.as<uint8_t>();
@@ -1166,6 +1182,7 @@ static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64*
 		const int64_t tb = std::max(beg, b0 * MC_PROF_BLOCK), te = std::min(end, b1 * MC_PROF_BLOCK);
 		launch_profpack(c->ix, p, nb, sums, b0, b1, tb, te, c->d_sort.as<uint64_t>(), c->stream);
 		if (outp) { if (dev_d2h((uint8_t*)outp + (tb - beg) * 16, c->d_sort.p, (size_t)(te - tb) * 16, c->stream) || dev_sync(c->stream)) rc = MC_ERR_CUDA; }
+		else if (checksum) launch_profhash(tb, te - tb, c->d_sort.as<uint64_t>(), d_acc, c->stream);
 		else launch_profstat(te - tb, c->d_sort.as<uint64_t>(), d_acc, c->stream);
 	}
 	if (dev_sync(c->stream)) rc = MC_ERR_CUDA;
@@ -1198,6 +1215,23 @@ int mc_profile_summary(mc_ctx* c, mc_profile_stats* out)
 	if (rc == MC_OK && (dev_d2h(h, d_acc.p, 32, c->stream) || dev_sync(c->stream))) rc = MC_ERR_CUDA;
 	d_acc.release();
 	out->aligned_bases = (int64_t)h[0]; out->coverage_sum = (int64_t)h[1]; out->dup_sites = (int64_t)h[2]; out->dup_reads = (int64_t)h[3];
+	return rc;
+}
+
+int mc_profile_checksum(mc_ctx* c, uint64_t out[2])
+{
+	if (!c || !out) { mc_set_error("mc_profile_checksum: null argument"); return MC_ERR_ARG; }
+	if (!c->prm.update_profile) { mc_set_error("mc_profile_checksum: context was created without update_profile"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	DBuf d_acc;
+	if (d_acc.reserve(64) || dev_zero(d_acc.p, 64, c->stream)) return MC_ERR_CUDA;
+	int rc = profile_walk(c, 0, c->G, nullptr, d_acc.as<mc_u64>(), true);
+	mc_u64 h[2] = {0, 0};
+	if (rc == MC_OK && (dev_d2h(h, d_acc.p, 16, c->stream) || dev_sync(c->stream))) rc = MC_ERR_CUDA;
+	d_acc.release();
+	out[0] = h[0]; out[1] = h[1];
 	return rc;
 }
 

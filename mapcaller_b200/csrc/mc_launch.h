@@ -38,6 +38,7 @@ static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb,
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, 0, 1, ix, p, nb, pre, beg, end, out); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
 static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) profstat_body(i, recs, acc); }
+static void launch_profhash(int64_t g0, int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) { const uint64_t h = profhash_of(g0 + i, recs, i); acc[0] += h; acc[1] ^= h; } }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatecnt_body(i, a, q, list, bump); }
 static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t) { for (int64_t i = 0; i < n; i++) gateadd_body(i, a, list); }
 static void launch_gatedense_fill(const PipeArgs& a, const ProfArgs& q, int64_t n, uint8_t* dense, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatedense_fill_body(i, a, q, dense); }
@@ -53,9 +54,12 @@ static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t) {
 static void device_incmax_i64(int64_t* a, int64_t n, mc_stream_t) { for (int64_t i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
+#define MC_SLOTS 8
 #else
+#include <atomic>
 typedef cudaStream_t mc_stream_t;
-static int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches(0);   // a second host thread may be staging the next batch (mc_ingest_fastq)
+#define MC_SLOTS 8   // device slots for staged batches
 #define MC_BLOCK 256
 #define MC_LAUNCH1(name) \
 	__global__ void __launch_bounds__(MC_BLOCK) mc_##name##_kernel(const PipeArgs a, int64_t n) \
@@ -180,6 +184,15 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_profstat_kernel(int64_t n, const 
 { for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (int64_t)gridDim.x * blockDim.x) if (i < n) profstat_body(i, recs, acc); }
 static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t s)
 { if (n > 0) { int64_t b = (n + MC_BLOCK - 1) / MC_BLOCK; if (b > 148 * 8) b = 148 * 8; mc_profstat_kernel<<<(unsigned)b, MC_BLOCK, 0, s>>>(n, recs, acc); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_profhash_kernel(int64_t g0, int64_t n, const uint64_t* recs, mc_u64* acc)
+{
+	uint64_t sum = 0, x = 0;
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const uint64_t h = profhash_of(g0 + i, recs, i); sum += h; x ^= h; }
+	for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); x ^= __shfl_xor_sync(0xffffffffu, x, o); }
+	if ((threadIdx.x & 31) == 0) { atomicAdd(acc, (mc_u64)sum); atomicXor(acc + 1, (mc_u64)x); }
+}
+static void launch_profhash(int64_t g0, int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t s)
+{ if (n > 0) { int64_t b = (n + MC_BLOCK - 1) / MC_BLOCK; if (b > 148 * 8) b = 148 * 8; mc_profhash_kernel<<<(unsigned)b, MC_BLOCK, 0, s>>>(g0, n, recs, acc); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_gatecnt_kernel(const PipeArgs a, const ProfArgs q, int64_t n, uint64_t* list, mc_u64* bump)
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) gatecnt_body(i, a, q, list, bump); }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t s)

@@ -316,4 +316,16 @@ MC_HD void profstat_body(int64_t i, const uint64_t* recs, mc_u64* acc)
 	mc_stat_add(acc + 2, rc ? 1u : 0u); mc_stat_add(acc + 3, rc);
 }
 
+// fingerprint of the packed profile: every column's record mixed with its position (splitmix64 finaliser), summed into acc[0]
+// and xor-ed into acc[1] - independent of the order in which the columns are visited
+MC_HD uint64_t prof_mix(uint64_t x)
+{
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+	return x;
+}
+MC_HD uint64_t profhash_of(int64_t g, const uint64_t* recs, int64_t i)
+{
+	return prof_mix(recs[2 * i] + prof_mix(recs[2 * i + 1] + prof_mix((uint64_t)g + 0x9e3779b97f4a7c15ull)));
+}
+
 #endif

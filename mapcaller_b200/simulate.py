@@ -225,13 +225,19 @@ def read_fasta(path: str):
     return contigs
 
 
-def fastq_text(reads: np.ndarray, mate: int, prefix: str = "r") -> np.ndarray:
-    """The bytes of a FASTQ file with fixed-width records `@r000000123/1`, built as one numpy byte matrix."""
+def fastq_text(reads: np.ndarray, mate: int, prefix: str = "r", first: int = 0) -> np.ndarray:
+    """The bytes of a FASTQ file with fixed-width records `@r000000123/1` (record i is read number first + i), built as
+    one numpy byte matrix."""
     n, L = reads.shape
-    names = np.char.add(np.char.add("@" + prefix, np.char.zfill(np.arange(n).astype(str), 9)), "/%d" % mate)
-    w = len(names[0])
+    pre = np.frombuffer(("@" + prefix).encode(), dtype=np.uint8)
+    w = len(pre) + 9 + 2
     rec = np.empty((n, w + 1 + L + 1 + 2 + L + 1), dtype=np.uint8)
-    rec[:, :w] = np.frombuffer("".join(names.tolist()).encode(), dtype=np.uint8).reshape(n, w)
+    rec[:, :len(pre)] = pre
+    idx = np.arange(first, first + n, dtype=np.int64)
+    for k in range(9):                      # zero-padded decimal digits, most significant first
+        rec[:, len(pre) + k] = (idx // 10 ** (8 - k)) % 10 + 48
+    rec[:, w - 2] = ord("/")
+    rec[:, w - 1] = 48 + mate
     rec[:, w] = 10
     rec[:, w + 1:w + 1 + L] = reads
     rec[:, w + 1 + L] = 10
@@ -240,6 +246,34 @@ def fastq_text(reads: np.ndarray, mate: int, prefix: str = "r") -> np.ndarray:
     rec[:, w + 4 + L:w + 4 + 2 * L] = ord("I")
     rec[:, w + 4 + 2 * L] = 10
     return rec.reshape(-1)
+
+
+def simulate_pairs_fast(g: np.ndarray, n_pairs: int, read_len: int, seed: int, frag_mean: float = 400, frag_sd: float = 40,
+                        sub_rate: float = 0.005, block: int = 250_000, first_block: int = 0):
+    """The same read model as simulate_pairs() without indel / N errors, for libraries of millions of pairs: generated in
+    independent blocks of `block` pairs (block b depends on (seed, b) only, so any prefix or slice of a library can be
+    regenerated), rows gathered through a strided window view, substitution sites drawn by count instead of a mask."""
+    n = len(g)
+    win = np.lib.stride_tricks.sliding_window_view(g, read_len)
+    r1 = np.empty((n_pairs, read_len), dtype=np.uint8); r2 = np.empty((n_pairs, read_len), dtype=np.uint8)
+    for b0 in range(0, n_pairs, block):
+        m = min(block, n_pairs - b0)
+        rng = np.random.default_rng([seed, first_block + b0 // block])
+        flen = np.clip(np.rint(rng.normal(frag_mean, frag_sd, size=m)), read_len + 10, None).astype(np.int64)
+        flen = np.minimum(flen, n - 1)
+        start = (rng.random(m) * (n - flen)).astype(np.int64)
+        left = win[start]
+        right = _COMP[win[np.maximum(start + flen - read_len, 0)][:, ::-1]]
+        flip = rng.random(m) < 0.5
+        a = np.where(flip[:, None], right, left); c = np.where(flip[:, None], left, right)
+        for r in (a, c):
+            k = int(rng.binomial(r.size, sub_rate)) if sub_rate > 0 else 0
+            if k:
+                pos = rng.integers(0, r.size, size=k)
+                flat = r.reshape(-1)
+                flat[pos] = _ACGT[(_CODE[flat[pos]] + rng.integers(1, 4, size=k, dtype=np.uint8)) & 3]
+        r1[b0:b0 + m] = a; r2[b0:b0 + m] = c
+    return r1, r2
 
 
 def write_fastq(path: str, reads: np.ndarray, mate: int, prefix: str = "r") -> None:

@@ -11,7 +11,7 @@ idx = [i for i, x in enumerate(rows) if 'mc_seed_kernel' in x['Kernel Name']]
 start = idx[1] if len(idx) > 1 else idx[0]          # warm-up 1 + the timed resident step
 agg = collections.OrderedDict(); tot = 0
 for x in rows[start:]:
-    if x['Kernel Name'].startswith('mc_seedcap'): break
+    if x['Kernel Name'].startswith(('mc_seedcap', 'mc_profsum')): break
     k = x['Kernel Name'].split('(')[0].replace('void ', '')[:40]; a = agg.setdefault(k, [0, 0.0, []]); a[0] += 1; a[1] += ms(x); a[2].append(round(ms(x), 3)); tot += ms(x)
 print("kernel                                     launches   total ms   share   per launch")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
