@@ -273,7 +273,8 @@ typedef struct {
     int32_t final_block;                  /* the blocks reach the end of the file(s) */
     int32_t pad;
 } mc_fastq_in;
-typedef struct { int64_t n_reads, consumed1, consumed2, n_bases; } mc_fastq_out;
+typedef struct { int64_t n_reads, consumed1, consumed2, n_bases;
+                 int64_t records1, records2;   /* whole records the blocks held (before the cut to n_reads) */ } mc_fastq_out;
 int mc_ingest_fastq(mc_ctx *ctx, const mc_fastq_in *in, int32_t slot, mc_fastq_out *out);
 /* mc_ingest_fastq() works on the context's copy stream with scratch of its own: a second host thread may ingest the next
  * block into slot s' while mc_map_staged() maps slot s != s' (the one exception to "calls on one ctx are serialised";

@@ -300,9 +300,9 @@ class Context:
         t1 = np.frombuffer(text1, dtype=np.uint8) if isinstance(text1, (bytes, bytearray)) else np.ascontiguousarray(text1, dtype=np.uint8)
         t2 = None if text2 is None else (np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else np.ascontiguousarray(text2, dtype=np.uint8))
         arg = (C.c_int64 * 6)(t1.ctypes.data, len(t1), t2.ctypes.data if t2 is not None else 0, len(t2) if t2 is not None else 0, max_reads, int(bool(final)))
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 6)()
         _check(lib().mc_ingest_fastq(self._h, arg, slot, out), "mc_ingest_fastq")
-        return dict(n_reads=int(out[0]), consumed1=int(out[1]), consumed2=int(out[2]), n_bases=int(out[3]))
+        return dict(n_reads=int(out[0]), consumed1=int(out[1]), consumed2=int(out[2]), n_bases=int(out[3]), records1=int(out[4]), records2=int(out[5]))
 
     def map_staged(self, slot: int = 0, copy: bool = False):
         out = BatchOut()

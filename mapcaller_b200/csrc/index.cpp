@@ -19,6 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <cstdarg>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <functional>
@@ -342,72 +345,105 @@ int mc_index_build_fasta(const char* fasta_path, int32_t n_threads, mc_index** o
 	return MC_OK;
 }
 
+// fwrite / fprintf / fclose results are all checked: a full disk must not leave a truncated index behind a MC_OK
+struct OutFile {
+	FILE* fp; bool ok;
+	explicit OutFile(const std::string& path, const char* mode) : fp(fopen(path.c_str(), mode)), ok(fp != nullptr) {}
+	void put(const void* p, size_t size, size_t n) { if (ok && n && fwrite(p, size, n, fp) != n) ok = false; }
+	void printf(const char* fmt, ...) __attribute__((format(printf, 2, 3)))
+	{
+		if (!ok) return;
+		va_list ap; va_start(ap, fmt); if (vfprintf(fp, fmt, ap) < 0) ok = false; va_end(ap);
+	}
+	bool close() { if (fp && fclose(fp) != 0) ok = false; fp = nullptr; return ok; }
+	~OutFile() { if (fp) fclose(fp); }
+};
+
 int mc_index_save(const mc_index* ix, const char* prefix)
 {
+	if (!ix || !prefix) { mc_set_error("mc_index_save: null argument"); return MC_ERR_ARG; }
 	const mc_index_view& v = ix->v;
+	if (!v.bwt || !v.sa || !v.pac || v.n_sa == 0) { mc_set_error("mc_index_save: the index holds no data"); return MC_ERR_ARG; }
 	std::string p(prefix);
-	FILE* fp = fopen((p + ".bwt").c_str(), "wb");
-	if (!fp) { mc_set_error("cannot write %s.bwt", prefix); return MC_ERR_IO; }
-	fwrite(&v.primary, 8, 1, fp); fwrite(v.L2 + 1, 8, 4, fp); fwrite(v.bwt, 4, v.bwt_size, fp); fclose(fp);
-	fp = fopen((p + ".sa").c_str(), "wb");
-	if (!fp) { mc_set_error("cannot write %s.sa", prefix); return MC_ERR_IO; }
-	uint64_t intv = (uint64_t)v.sa_intv;
-	fwrite(&v.primary, 8, 1, fp); fwrite(v.L2 + 1, 8, 4, fp); fwrite(&intv, 8, 1, fp); fwrite(&v.seq_len, 8, 1, fp);
-	fwrite(v.sa + 1, 8, v.n_sa - 1, fp); fclose(fp);
-	fp = fopen((p + ".pac").c_str(), "wb");
-	if (!fp) { mc_set_error("cannot write %s.pac", prefix); return MC_ERR_IO; }
-	int64_t G = v.genome_size;
-	fwrite(v.pac, 1, (size_t)((G >> 2) + ((G & 3) == 0 ? 0 : 1)), fp);
-	unsigned char ct = 0; if (G % 4 == 0) fwrite(&ct, 1, 1, fp);
-	ct = (unsigned char)(G % 4); fwrite(&ct, 1, 1, fp); fclose(fp);
-	fp = fopen((p + ".ann").c_str(), "w");
-	if (!fp) { mc_set_error("cannot write %s.ann", prefix); return MC_ERR_IO; }
-	fprintf(fp, "%lld %d %u\n", (long long)G, v.n_chrom, 11u);
-	int64_t off = 0;
-	for (int i = 0; i < v.n_chrom; i++)
 	{
-		fprintf(fp, "%d %s", 0, ix->chrom_name[i].c_str());
-		if (i < (int)ix->chrom_anno.size() && !ix->chrom_anno[i].empty()) fprintf(fp, " %s\n", ix->chrom_anno[i].c_str()); else fprintf(fp, " (null)\n");
-		fprintf(fp, "%lld %d %d\n", (long long)off, v.chrom_len[i], i < (int)ix->chrom_n_ambs.size() ? ix->chrom_n_ambs[i] : 0);
-		off += v.chrom_len[i];
+		OutFile f(p + ".bwt", "wb");
+		f.put(&v.primary, 8, 1); f.put(v.L2 + 1, 8, 4); f.put(v.bwt, 4, v.bwt_size);
+		if (!f.close()) { mc_set_error("cannot write %s.bwt", prefix); return MC_ERR_IO; }
 	}
-	fclose(fp);
-	fp = fopen((p + ".amb").c_str(), "w");
-	if (!fp) { mc_set_error("cannot write %s.amb", prefix); return MC_ERR_IO; }
-	fprintf(fp, "%lld %d %u\n", (long long)G, v.n_chrom, (unsigned)ix->holes.size());
-	for (auto& h : ix->holes) fprintf(fp, "%lld %d %c\n", (long long)h.offset, h.len, h.amb);
-	fclose(fp);
+	{
+		OutFile f(p + ".sa", "wb");
+		uint64_t intv = (uint64_t)v.sa_intv;
+		f.put(&v.primary, 8, 1); f.put(v.L2 + 1, 8, 4); f.put(&intv, 8, 1); f.put(&v.seq_len, 8, 1); f.put(v.sa + 1, 8, v.n_sa - 1);
+		if (!f.close()) { mc_set_error("cannot write %s.sa", prefix); return MC_ERR_IO; }
+	}
+	const int64_t G = v.genome_size;
+	{
+		OutFile f(p + ".pac", "wb");
+		f.put(v.pac, 1, (size_t)((G >> 2) + ((G & 3) == 0 ? 0 : 1)));
+		unsigned char ct = 0; if (G % 4 == 0) f.put(&ct, 1, 1);
+		ct = (unsigned char)(G % 4); f.put(&ct, 1, 1);
+		if (!f.close()) { mc_set_error("cannot write %s.pac", prefix); return MC_ERR_IO; }
+	}
+	{
+		OutFile f(p + ".ann", "w");
+		f.printf("%lld %d %u\n", (long long)G, v.n_chrom, 11u);
+		int64_t off = 0;
+		for (int i = 0; i < v.n_chrom; i++)
+		{
+			f.printf("%d %s", 0, ix->chrom_name[i].c_str());
+			if (i < (int)ix->chrom_anno.size() && !ix->chrom_anno[i].empty()) f.printf(" %s\n", ix->chrom_anno[i].c_str()); else f.printf(" (null)\n");
+			f.printf("%lld %d %d\n", (long long)off, v.chrom_len[i], i < (int)ix->chrom_n_ambs.size() ? ix->chrom_n_ambs[i] : 0);
+			off += v.chrom_len[i];
+		}
+		if (!f.close()) { mc_set_error("cannot write %s.ann", prefix); return MC_ERR_IO; }
+	}
+	{
+		OutFile f(p + ".amb", "w");
+		f.printf("%lld %d %u\n", (long long)G, v.n_chrom, (unsigned)ix->holes.size());
+		for (auto& h : ix->holes) f.printf("%lld %d %c\n", (long long)h.offset, h.len, h.amb);
+		if (!f.close()) { mc_set_error("cannot write %s.amb", prefix); return MC_ERR_IO; }
+	}
 	return MC_OK;
 }
 
+static int index_load_impl(const char* prefix, mc_index** out);
 int mc_index_load(const char* prefix, mc_index** out)
 {
+	if (!prefix || !out) { mc_set_error("mc_index_load: null argument"); return MC_ERR_ARG; }
+	try { return index_load_impl(prefix, out); }          // no exception may cross the C ABI
+	catch (const std::exception& e) { mc_set_error("mc_index_load(%s): %s", prefix, e.what()); return MC_ERR_IO; }
+}
+static int index_load_impl(const char* prefix, mc_index** out)
+{
 	std::string p(prefix);
-	mc_index* ix = new mc_index();
+	std::unique_ptr<mc_index> holder(new mc_index());
+	mc_index* ix = holder.get();
 	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0};
 	FILE* fp = fopen((p + ".bwt").c_str(), "rb");
-	if (!fp) { delete ix; mc_set_error("cannot open %s.bwt", prefix); return MC_ERR_IO; }
+	if (!fp) { mc_set_error("cannot open %s.bwt", prefix); return MC_ERR_IO; }
 	fseek(fp, 0, SEEK_END); long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
+	if (sz < 40 + 64) { fclose(fp); mc_set_error("%s.bwt is too short to be an index (%ld bytes)", prefix, sz); return MC_ERR_IO; }
 	size_t words = ((size_t)sz - 40) >> 2;
 	ix->bwt_store.resize(words);
 	bool ok = read_exact(fp, &primary, 8) && read_exact(fp, L2 + 1, 32) && read_exact(fp, ix->bwt_store.data(), words * 4);
 	fclose(fp);
-	if (!ok) { delete ix; mc_set_error("%s.bwt is truncated", prefix); return MC_ERR_IO; }
+	if (!ok) { mc_set_error("%s.bwt is truncated", prefix); return MC_ERR_IO; }
 	uint64_t seq_len = L2[4];
+	if (seq_len == 0 || (seq_len & 1) || seq_len / 16 > words) { mc_set_error("%s.bwt is inconsistent (text length %llu for %zu words)", prefix, (unsigned long long)seq_len, words); return MC_ERR_IO; }
 	fp = fopen((p + ".sa").c_str(), "rb");
-	if (!fp) { delete ix; mc_set_error("cannot open %s.sa", prefix); return MC_ERR_IO; }
+	if (!fp) { mc_set_error("cannot open %s.sa", prefix); return MC_ERR_IO; }
 	uint64_t hdr[7];
 	ok = read_exact(fp, hdr, 56);
 	uint64_t intv = hdr[5];
-	if (!ok || intv != 32 || hdr[6] != seq_len) { fclose(fp); delete ix; mc_set_error("%s.sa does not match %s.bwt (sa_intv must be 32)", prefix, prefix); return MC_ERR_IO; }
+	if (!ok || intv != 32 || hdr[6] != seq_len) { fclose(fp); mc_set_error("%s.sa does not match %s.bwt (sa_intv must be 32)", prefix, prefix); return MC_ERR_IO; }
 	uint64_t n_sa = (seq_len + intv) / intv;
 	ix->sa_store.assign(n_sa, 0); ix->sa_store[0] = (uint64_t)-1;
 	ok = read_exact(fp, ix->sa_store.data() + 1, (n_sa - 1) * 8); fclose(fp);
-	if (!ok) { delete ix; mc_set_error("%s.sa is truncated", prefix); return MC_ERR_IO; }
+	if (!ok) { mc_set_error("%s.sa is truncated", prefix); return MC_ERR_IO; }
 	fp = fopen((p + ".ann").c_str(), "r");
-	if (!fp) { delete ix; mc_set_error("cannot open %s.ann", prefix); return MC_ERR_IO; }
+	if (!fp) { mc_set_error("cannot open %s.ann", prefix); return MC_ERR_IO; }
 	long long l_pac = 0; int n_seqs = 0; unsigned seed = 0;
-	if (fscanf(fp, "%lld%d%u", &l_pac, &n_seqs, &seed) != 3) { fclose(fp); delete ix; mc_set_error("%s.ann is malformed", prefix); return MC_ERR_IO; }
+	if (fscanf(fp, "%lld%d%u", &l_pac, &n_seqs, &seed) != 3) { fclose(fp); mc_set_error("%s.ann is malformed", prefix); return MC_ERR_IO; }
 	for (int i = 0; i < n_seqs; i++)
 	{
 		unsigned gi; char name[1024]; long long off; int len, nambs;
@@ -418,7 +454,7 @@ int mc_index_load(const char* prefix, mc_index** out)
 		ix->chrom_name.push_back(name); ix->chrom_anno.push_back(anno); ix->chrom_len.push_back(len); ix->chrom_n_ambs.push_back(nambs);
 	}
 	fclose(fp);
-	if ((int)ix->chrom_len.size() != n_seqs || (uint64_t)l_pac * 2 != seq_len) { delete ix; mc_set_error("%s.ann does not match %s.bwt", prefix, prefix); return MC_ERR_IO; }
+	if ((int)ix->chrom_len.size() != n_seqs || (uint64_t)l_pac * 2 != seq_len) { mc_set_error("%s.ann does not match %s.bwt", prefix, prefix); return MC_ERR_IO; }
 	fp = fopen((p + ".amb").c_str(), "r");
 	if (fp)
 	{
@@ -428,12 +464,12 @@ int mc_index_load(const char* prefix, mc_index** out)
 		fclose(fp);
 	}
 	fp = fopen((p + ".pac").c_str(), "rb");
-	if (!fp) { delete ix; mc_set_error("cannot open %s.pac", prefix); return MC_ERR_IO; }
+	if (!fp) { mc_set_error("cannot open %s.pac", prefix); return MC_ERR_IO; }
 	ix->pac_store.assign((size_t)(l_pac / 4 + 2), 0);
 	size_t got = fread(ix->pac_store.data(), 1, (size_t)(l_pac / 4 + 1), fp); fclose(fp);
-	if (got < (size_t)((l_pac + 3) / 4)) { delete ix; mc_set_error("%s.pac is truncated", prefix); return MC_ERR_IO; }
+	if (got < (size_t)((l_pac + 3) / 4)) { mc_set_error("%s.pac is truncated", prefix); return MC_ERR_IO; }
 	finish_view(ix, primary, L2, seq_len, l_pac);
-	*out = ix;
+	*out = holder.release();
 	return MC_OK;
 }
 

@@ -1100,6 +1100,7 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	{
 		open_end[f] = in->final_block && len[f] > 0 && text[f][len[f] - 1] != '\n';
 		const int64_t rec = (n_lines[f] + (open_end[f] ? 1 : 0)) / 4;
+		(f == 0 ? out->records1 : out->records2) = rec;
 		n_rec = n_rec < 0 ? rec : std::min(n_rec, rec);
 	}
 	int64_t n = nf == 2 ? 2 * n_rec : n_rec;

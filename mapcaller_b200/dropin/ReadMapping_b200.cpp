@@ -147,17 +147,20 @@ void Mapping()
 			p.max_mismatch_rate = MaxMisMatchRate; p.update_profile = bVCFoutput; p.want_alignments = bSAMoutput && !device_sam;
 			if (mc_ctx_create(idx, &p, &ctx)) die("mc_ctx_create");
 		}
+		if (mc_begin_library(ctx)) die("mc_begin_library");   // every -f library restarts the 200-read chunk grid; profile, totals and avgDist carry over
 		// No SAM wanted and plain FASTQ on disk: nothing of the reference's reader is needed - raw file blocks go to the GPU, which
 		// finds the records itself (mc_ingest_fastq = GetNextEntry / GetNextChunk, src/GetData.cpp:32-99) and maps them.
 		if (!bSAMoutput && !lib.gz && FastQFormat)
 		{
-			const size_t BLK = (size_t)64 << 20;
-			vector<uint8_t> b1, b2; size_t have1 = 0, have2 = 0; bool eof1 = false, eof2 = !lib.sep;
+			// MC_B200_FASTQ_BLOCK (bytes) overrides the 64 MiB block size - the tests use it to cross many block boundaries with small files
+			const size_t BLK = getenv("MC_B200_FASTQ_BLOCK") ? (size_t)atoll(getenv("MC_B200_FASTQ_BLOCK")) : (size_t)64 << 20;
+			vector<uint8_t> b1, b2; size_t have1 = 0, have2 = 0; bool eof1 = false, eof2 = !lib.sep, force_final = false;
 			for (;;)
 			{
+				// a file that reached its end just stops growing; its carried-over records are still consumed block by block
 				if (!eof1) { b1.resize(have1 + BLK); size_t g = fread(b1.data() + have1, 1, BLK, lib.f1); have1 += g; eof1 = g < BLK; }
 				if (!eof2) { b2.resize(have2 + BLK); size_t g = fread(b2.data() + have2, 1, BLK, lib.f2); have2 += g; eof2 = g < BLK; }
-				const bool last = eof1 || eof2;      // the shorter file ends the library, as the reader of the reference would
+				const bool last = (eof1 && eof2) || force_final;   // only then may a ragged tail (not a multiple of 200 reads) be mapped
 				mc_fastq_in fi; memset(&fi, 0, sizeof(fi));
 				fi.text1 = b1.data(); fi.len1 = (int64_t)have1; fi.text2 = lib.sep ? b2.data() : NULL; fi.len2 = (int64_t)have2; fi.final_block = last;
 				mc_fastq_out fo;
@@ -169,9 +172,16 @@ void Mapping()
 					mc_totals t; mc_get_totals(ctx, &t);
 					fprintf(stderr, "\r%lld %s reads have been processed in %lld seconds...", (long long)t.total_reads, (bPairEnd ? "paired-end" : "singled-end"), (long long)(time(NULL) - StartProcessTime));
 				}
-				if (last || fo.n_reads == 0) break;
+				if (last) break;
 				memmove(b1.data(), b1.data() + fo.consumed1, have1 - (size_t)fo.consumed1); have1 -= (size_t)fo.consumed1;
 				if (lib.sep) { memmove(b2.data(), b2.data() + fo.consumed2, have2 - (size_t)fo.consumed2); have2 -= (size_t)fo.consumed2; }
+				if (lib.sep && eof1 != eof2)
+				{
+					// mate files of unequal size: the shorter one ends the library (the reference's reader stops there too). Once the
+					// file still open has buffered more whole records than the ended one has left, nothing else can pair up.
+					const int64_t used = fo.n_reads / 2, left1 = fo.records1 - used, left2 = fo.records2 - used;
+					if (eof1 ? left2 > left1 : left1 > left2) force_final = true;
+				}
 			}
 			fclose(lib.f1); if (lib.f2) fclose(lib.f2);
 			continue;

@@ -63,3 +63,73 @@ def test_same_sam_and_vcf_as_the_reference_cli(tmp_path, mode):
     assert outs["gpu"][0] == outs["ref"][0], "SAM differs"
     assert outs["gpu"][1] == outs["ref"][1], "VCF differs"
     assert len(outs["ref"][1]) > 20
+
+
+def _run_both(tmp_path, idx, reads_args, env=None, extra=()):
+    """VCF bodies of the reference CLI and of the drop-in for the same command line (no SAM: the drop-in then feeds raw FASTQ
+    blocks to the device parser)."""
+    out = {}
+    for tag, exe in (("ref", REF_BIN), ("gpu", GPU_BIN)):
+        vcf = str(tmp_path / (tag + ".vcf"))
+        e = dict(os.environ); e.update(env or {})
+        subprocess.check_call([exe, "-i", idx, "-t", "1"] + list(reads_args) + ["-vcf", vcf, "-log", str(tmp_path / (tag + ".log"))] + list(extra),
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=str(tmp_path), env=e)
+        out[tag] = vcf_body(vcf)
+    return out
+
+
+def _case_files(tmp_path, seed=43, n_pairs=9000):
+    case = pu.make_case(seed=seed, n_pairs=n_pairs, genome_len=120000, contigs=2, sv=3.0)
+    fa = str(tmp_path / "ref.fa")
+    sim.write_fasta(fa, case["contigs"])
+    idx = str(tmp_path / "idx")
+    subprocess.check_call([REF_BIN, "index", fa, idx], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return case, idx
+
+
+@pytest.mark.parametrize("layout", ["two_files", "single_end", "interleaved", "unequal_mates"])
+def test_fastq_block_reader_crosses_block_boundaries(tmp_path, layout):
+    """The raw-FASTQ path of the drop-in reads the files in blocks (64 MiB; 40 kB here, so that a 2 MB library crosses ~50
+    block boundaries): every read of a single-file library has to be mapped, mate files whose byte sizes differ (trimmed
+    R2) have to stay in step, and the library ends with the shorter file."""
+    case, idx = _case_files(tmp_path)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    r1, r2 = case["r1"], case["r2"]
+    if layout == "unequal_mates":
+        r2 = r2[:, :70]                      # shorter records in the second file: the two files reach EOF in different blocks
+    if layout == "interleaved":
+        t1, t2 = sim.fastq_text(r1, 1).reshape(len(r1), -1), sim.fastq_text(r2, 2).reshape(len(r2), -1)
+        import numpy as np
+        np.concatenate([t1, t2], axis=1).reshape(-1).tofile(f1)
+        reads = ["-f", f1, "-p"]
+    else:
+        sim.write_fastq(f1, r1, 1); sim.write_fastq(f2, r2, 2)
+        reads = ["-f", f1] if layout == "single_end" else ["-f", f1, "-f2", f2]
+    out = _run_both(tmp_path, idx, reads, env={"MC_B200_FASTQ_BLOCK": "40000"})
+    assert out["gpu"] == out["ref"], "VCF differs"
+    assert len(out["ref"]) > 20
+
+
+@pytest.mark.parametrize("sam", [False, True])
+def test_two_libraries_in_one_run(tmp_path, sam):
+    """-f a.fq b.fq -f2 c.fq d.fq: the reference restarts its chunk grid per library and keeps accumulating the profile, the
+    totals and avgDist (src/ReadMapping.cpp:705-748).  Library 1 is not a multiple of 200 reads."""
+    case, idx = _case_files(tmp_path, seed=47, n_pairs=5150)
+    names = []
+    for k, (lo, hi) in enumerate(((0, 2150), (2150, 5150))):
+        f1, f2 = str(tmp_path / ("lib%d_1.fq" % k)), str(tmp_path / ("lib%d_2.fq" % k))
+        sim.write_fastq(f1, case["r1"][lo:hi], 1); sim.write_fastq(f2, case["r2"][lo:hi], 2)
+        names.append((f1, f2))
+    reads = ["-f", names[0][0], names[1][0], "-f2", names[0][1], names[1][1]]
+    if not sam:
+        out = _run_both(tmp_path, idx, reads)
+        assert out["gpu"] == out["ref"], "VCF differs"
+    else:
+        res = {}
+        for tag, exe in (("ref", REF_BIN), ("gpu", GPU_BIN)):
+            s, v = str(tmp_path / (tag + ".sam")), str(tmp_path / (tag + ".vcf"))
+            subprocess.check_call([exe, "-i", idx, "-t", "1"] + reads + ["-sam", s, "-vcf", v, "-log", str(tmp_path / (tag + ".log"))],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=str(tmp_path))
+            res[tag] = (sam_records(s, False), vcf_body(v))
+        assert res["gpu"][0] == res["ref"][0], "SAM differs"
+        assert res["gpu"][1] == res["ref"][1], "VCF differs"
