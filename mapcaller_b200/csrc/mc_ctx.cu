@@ -171,7 +171,7 @@ struct mc_ctx {
 	mc_params prm;
 	mc_stream_t stream;
 	// index replica
-	DBuf d_bwt, d_cbwt, d_sa, d_pac, d_chrom_end, d_chrom_id;
+	DBuf d_bwt, d_cbwt, d_sa, d_sa_dense, d_ktab, d_pac, d_chrom_end, d_chrom_id;
 	DevIndex ix;
 	int64_t G;
 	// profile
@@ -184,7 +184,7 @@ struct mc_ctx {
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_rwin, d_rw_beg, d_bumps, d_stats, d_scan;
-	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off;
+	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off, d_scan2;
 	HBuf h_disc;
 	HBuf h_bounce[2];
 	mc_stream_t cstream;
@@ -236,11 +236,11 @@ void mc_ctx_destroy(mc_ctx* c)
 	if (c) cudaSetDevice(c->prm.device);   // a process may hold contexts on several GPUs
 #endif
 	if (!c) return;
-	DBuf* bufs[] = {&c->d_bwt, &c->d_cbwt, &c->d_sa, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_base16, &c->d_sdiff, &c->d_cdiff, &c->d_mdiff, &c->d_rcount, &c->d_rflag, &c->d_bp, &c->d_ind,
+	DBuf* bufs[] = {&c->d_bwt, &c->d_cbwt, &c->d_sa, &c->d_sa_dense, &c->d_ktab, &c->d_pac, &c->d_chrom_end, &c->d_chrom_id, &c->d_base16, &c->d_sdiff, &c->d_cdiff, &c->d_mdiff, &c->d_rcount, &c->d_rflag, &c->d_bp, &c->d_ind,
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off, &c->d_scan2};
 	for (DBuf* b : bufs) b->release();
 	for (DBuf& b : c->d_vc) b.release();
 	for (DBuf& b : c->d_sam) b.release();
@@ -339,6 +339,41 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	ix.bwt = c->d_bwt.as<uint32_t>(); ix.sa = c->d_sa.as<uint64_t>(); ix.pac = c->d_pac.as<uint8_t>();
 	ix.chrom_end = c->d_chrom_end.as<int64_t>(); ix.chrom_id = c->d_chrom_id.as<int32_t>(); ix.n_end = (int32_t)ends.size();
 	ix.primary = v.primary; for (int i = 0; i < 5; i++) ix.L2[i] = v.L2[i]; ix.seq_len = v.seq_len; ix.G = G; ix.twoG = 2 * G;
+	ix.sa32 = nullptr; ix.sa_shift = 5; ix.ktab32 = nullptr; ix.ktab64 = nullptr; ix.ktab_k = 0;
+	{
+		// k-mer start table of the seed search (mc_fmindex.h): k = floor(log4(text length)) - 2, i.e. k-mers that still occur a few
+		// dozen times on average, so that nearly every lookup succeeds.  MC_KMER_K overrides (0 = no table).
+		int k = 0; for (uint64_t t = v.seq_len; t >= 4; t >>= 2) k++;
+		k -= 2; if (k > 14) k = 14; if (k < 4) k = 4;
+		if (getenv("MC_KMER_K")) k = atoi(getenv("MC_KMER_K"));
+		if (k >= 2 && k <= 15)
+		{
+			const bool narrow = ix.cbwt != nullptr;
+			const size_t ne = (size_t)1 << (2 * k);
+			if (c->d_ktab.reserve(ne * (narrow ? 8 : 16))) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
+			launch_ktab_build(ix, k, narrow ? c->d_ktab.as<uint32_t>() : nullptr, narrow ? nullptr : c->d_ktab.as<uint64_t>(), c->stream);
+			if (dev_sync(c->stream)) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
+			if (narrow) ix.ktab32 = c->d_ktab.as<uint32_t>(); else ix.ktab64 = c->d_ktab.as<uint64_t>();
+			ix.ktab_k = k;
+		}
+	}
+	{
+		// denser sample of the suffix array in HBM (mc_fmindex.h): every 4th row, 32-bit, for texts below 2^32 symbols; every 8th
+		// row, 64-bit, otherwise.  MC_SA_SHIFT=5 keeps the reference's every-32nd-row sample (A/B measurements).
+		const bool narrow = v.seq_len < (1ull << 32) && !params->reserved[1];   // reserved[1]: the whole >= 2^32 path, also on a small text (tests)
+		int shift = narrow ? 2 : 3;
+		if (getenv("MC_SA_SHIFT")) shift = atoi(getenv("MC_SA_SHIFT"));
+		if (shift >= 0 && shift < 5)
+		{
+			const int64_t nd = (int64_t)(v.seq_len >> shift) + 1;
+			if (c->d_sa_dense.reserve((size_t)nd * (narrow ? 4 : 8))) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
+			launch_sa_dense(ix, nd, shift, narrow ? c->d_sa_dense.as<uint32_t>() : nullptr, narrow ? nullptr : c->d_sa_dense.as<uint64_t>(), c->stream);
+			if (dev_sync(c->stream)) { mc_ctx_destroy(c); return MC_ERR_CUDA; }
+			if (narrow) ix.sa32 = c->d_sa_dense.as<uint32_t>(); else ix.sa = c->d_sa_dense.as<uint64_t>();
+			ix.sa_shift = shift;
+			c->d_sa.release();
+		}
+	}
 	*out = c;
 	return MC_OK;
 }
@@ -1170,10 +1205,10 @@ static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64*
 	// the range counters are difference arrays: block totals, exclusive scan over the blocks, then every block sums its own columns
 	const int64_t nb = (c->G + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK;
 	DBuf d_sums;
-	if (d_sums.reserve((size_t)(6 * nb + 8) * 8)) return MC_ERR_CUDA;
+	if (d_sums.reserve((size_t)(6 * nb + 8) * 8) || c->d_scan2.reserve(device_scan_scratch_bytes(nb))) return MC_ERR_CUDA;
 	int64_t* sums = d_sums.as<int64_t>();
 	launch_profsum(p, c->G, nb, sums, c->stream);
-	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, c->stream);
+	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, c->d_scan2.p, c->stream);
 	const int64_t tile_blocks = (1 << 24) / MC_PROF_BLOCK;
 	int rc = MC_OK;
 	if (c->d_sort.reserve((size_t)(tile_blocks * MC_PROF_BLOCK) * 16)) rc = MC_ERR_CUDA;
@@ -1421,12 +1456,12 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	int bad = d_sums.reserve((size_t)(6 * nb + 8) * 8) || d_depth.reserve((size_t)nvb * 4) || d_ng.reserve((size_t)nvb * 8) || d_nd.reserve((size_t)nvb * 8);
 	bad |= d_ln.reserve((size_t)nvb * 8) || d_le.reserve((size_t)nvb * 8) || d_lead.reserve((size_t)nvb * 4) || d_cnt.reserve((size_t)(nvb + 1) * 4);
 	bad |= d_off.reserve((size_t)(nvb + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(nvb)) || d_cand.reserve((cand.size() + 1) * sizeof(VcCand));
-	bad |= c->d_sort.reserve((size_t)std::min(tile_cols, nb * MC_PROF_BLOCK) * 16);
+	bad |= c->d_sort.reserve((size_t)std::min(tile_cols, nb * MC_PROF_BLOCK) * 16) || c->d_scan2.reserve(device_scan_scratch_bytes(std::max(nb, nvb)));
 	if (bad) return done(MC_ERR_CUDA);
 	if (dev_h2d(d_cand.p, cand.data(), cand.size() * sizeof(VcCand), s)) return done(MC_ERR_CUDA);
 	int64_t* sums = d_sums.as<int64_t>();
 	launch_profsum(p, G, nb, sums, s);
-	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, s);
+	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, c->d_scan2.p, s);
 	VcArgs a; memset(&a, 0, sizeof(a));
 	a.vp = *vp; if (a.vp.gvcf && a.vp.monomorphic) a.vp.gvcf = 0;   // src/main.cpp:322
 	a.ix = c->ix; a.G = G; a.n_blocks = nvb; a.recs = c->d_sort.as<uint64_t>();
@@ -1444,9 +1479,9 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	mark("prefix");
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcdepth(a, vb0(t), vb1(t), s); }
 	mark("pack+depth");
-	device_incmax_i64(a.last_nongap, nvb, s); device_incmax_i64(a.last_nondup, nvb, s);
+	device_incmax_i64(a.last_nongap, nvb, c->d_scan2.p, s); device_incmax_i64(a.last_nondup, nvb, c->d_scan2.p, s);
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), false, s); }
-	if (a.vp.gvcf) { device_incmax_i64(a.last_normal, nvb, s); device_incmax_i64(a.last_event, nvb, s); }
+	if (a.vp.gvcf) { device_incmax_i64(a.last_normal, nvb, c->d_scan2.p, s); device_incmax_i64(a.last_event, nvb, c->d_scan2.p, s); }
 	device_scan_u32(a.cnt, d_off.as<int64_t>(), nvb, d_scan.as<int64_t>(), s);
 	int64_t total = 0;
 	if (dev_d2h(&total, d_off.as<int64_t>() + nvb, 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);

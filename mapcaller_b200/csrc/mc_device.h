@@ -24,6 +24,7 @@ static inline mc_u32x4 mc_ldg128(const void* p) { mc_u32x4 v; memcpy(&v, p, 16);
 template <class T> static inline T mc_ldg(const T* p) { return *p; }
 template <class T> static inline T mc_atomic_add(T* p, T v) { T o = *p; *p = (T)(o + v); return o; }
 template <class T> static inline void mc_atomic_or(T* p, T v) { *p = (T)(*p | v); }
+static inline int mc_atomic_exch(int* p, int v) { int o = *p; *p = v; return o; }
 static inline int mc_popc(uint32_t x) { return __builtin_popcount(x); }
 #define MC_WARP_SYNC() do { } while (0)
 static inline int64_t mc_bcast64(int64_t v) { return v; }
@@ -45,6 +46,7 @@ static __device__ __forceinline__ uint32_t mc_atomic_add(uint32_t* p, uint32_t v
 static __device__ __forceinline__ int mc_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 static __device__ __forceinline__ void mc_atomic_or(unsigned long long* p, unsigned long long v) { atomicOr(p, v); }
 static __device__ __forceinline__ void mc_atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+static __device__ __forceinline__ int mc_atomic_exch(int* p, int v) { return atomicExch(p, v); }
 static __device__ __forceinline__ int mc_popc(uint32_t x) { return __popc(x); }
 #define MC_WARP_SYNC() __syncwarp()
 static __device__ __forceinline__ int64_t mc_bcast64(int64_t v) { return __shfl_sync(0xffffffffu, v, 0); }
@@ -201,7 +203,12 @@ int64_t mc_block_bump(mc_u64* bump, uint32_t n) { int64_t o0, o1; mc_block_bump2
 struct DevIndex {
 	const uint32_t* bwt;   // reference layout, 64-byte blocks: 4 x uint64 occ counts + 8 x uint32 packed symbols (128 rows)
 	const uint32_t* cbwt;  // compact device layout (texts < 2^32 symbols), 32-byte blocks of 64 rows: 4 x uint32 counts + low-bit plane + high-bit plane; 0 = not built
-	const uint64_t* sa;    // every 32nd row
+	const uint64_t* sa;    // sampled suffix array, one entry per (1 << sa_shift) rows: the reference's (every 32nd row) or, for texts >= 2^32 symbols, the denser device copy
+	const uint32_t* sa32;  // denser device copy for texts < 2^32 symbols (32-bit entries); 0 = use `sa`
+	int32_t sa_shift;      // log2 of the sampling interval of whichever table is in use
+	const uint32_t* ktab32; // k-mer start table of the seed search (mc_fmindex.h), 2 x uint32 per k-mer (compact layout); 0 = none
+	const uint64_t* ktab64; // the same with 2 x uint64 per k-mer (texts >= 2^32 symbols)
+	int32_t ktab_k;         // k (0 = no table)
 	const uint8_t* pac;    // forward 2-bit text; revcomp half derived on the fly
 	const int64_t* chrom_end; // sorted keys of PosChrIdMap (reference src/bwt_index.cpp:253-254)
 	const int32_t* chrom_id;  // value of each key

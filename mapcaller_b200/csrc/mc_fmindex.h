@@ -56,13 +56,25 @@ MC_HD void mc_load_block(const DevIndex& ix, uint64_t blk, OccBlock& b)
 // bwt_invPsi (reference src/bwt_search.cpp:101-107): one LF step = one block
 MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k);
 
+// The sampled suffix array in HBM.  The reference keeps SA[k] for every 32nd row (bwt.c:101-123) and walks LF until it meets
+// one: 31 dependent random block reads per location on average.  HBM is not the scarce resource on a B200, so the context
+// derives a denser sample from the reference's at upload time (mc_sa_dense_body: every 4th row in 32 bits for texts below 2^32
+// symbols = one byte per text symbol, every 8th row in 64 bits otherwise) and a location costs 3 (7) steps.  Same values:
+// SA[k] = steps + SA[LF^steps(k)] whichever sampled row the walk stops at.
+MC_HD bool mc_sa_sampled(const DevIndex& ix, uint64_t k) { return (k & ((1ull << ix.sa_shift) - 1)) == 0; }
+MC_HD uint64_t mc_sa_value(const DevIndex& ix, uint64_t k, uint64_t steps)
+{
+	// 32-bit entries: row 0 holds (uint32)-1 like the reference's sa[0] = -1, and is only ever reached after >= 1 step
+	if (ix.sa32) return (uint64_t)(uint32_t)((uint32_t)steps + mc_ldg(ix.sa32 + (k >> ix.sa_shift)));
+	return steps + mc_ldg(ix.sa + (k >> ix.sa_shift));
+}
 // bwt_sa (reference src/bwt_search.cpp:109-119): walk LF until a sampled row
 MC_HD uint64_t mc_locate(const DevIndex& ix, uint64_t k, uint32_t* nblk)
 {
 	uint64_t steps = 0;
-	while (k & 31) { steps++; k = mc_lf_step(ix, k); }
+	while (!mc_sa_sampled(ix, k)) { steps++; k = mc_lf_step(ix, k); }
 	*nblk += (uint32_t)steps;
-	return steps + mc_ldg(ix.sa + (k >> 5));
+	return mc_sa_value(ix, k, steps);
 }
 
 // Search state.  The reference carries the bi-interval (x0 = rows of the pattern, x1 = rows of its reverse
@@ -248,6 +260,66 @@ MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k)
 	const uint32_t w[8] = {b.q2.x, b.q2.y, b.q2.z, b.q2.w, b.q3.x, b.q3.y, b.q3.z, b.q3.w};
 	const int c = (int)(w[(x & 127) >> 4] >> ((~(uint32_t)x & 15) << 1)) & 3;
 	return ix.L2[c] + mc_block_base(b, c) + (uint64_t)mc_count_in_block(b, mc_flip_of(c), 2 * ((int)(x & 127) + 1));
+}
+
+// ---- k-mer start table -------------------------------------------------------------------------------------------
+// The first steps of every seed search are the expensive ones: the interval still spans millions of rows, so its two ends
+// lie in different blocks (two random lines per step, the reference's bwt_2occ4 slow path) - and they are the same steps for
+// every read that starts with the same bases.  The context therefore tabulates, for every k-mer (k ~ log4(text) - 2: 12 at
+// 248 Mbp), the search state after its k bases: entry = {x1, x2 | touched << 27} (32-bit) or {x1, x2 | touched << 56} (64-bit),
+// `touched` = the number of occ blocks the reference algorithm reads on those k - 1 steps, so that the work counter stays the
+// oracle's.  x2 == 0 marks a k-mer the table cannot answer (absent from the text - the search then has to find out WHERE it
+// fails -, or more than 2^27 occurrences): the search falls back to stepping, as it does at an N.
+#define MC_KTAB_BITS32 27
+#define MC_KTAB_BITS64 56
+template <class Interval> struct KtabOps;
+MC_HD void mc_ktab_build_body(int64_t m, const DevIndex& ix, int k, uint32_t* out32, uint64_t* out64);
+
+// entry j of the denser sample: SA[j << shift] from the reference's every-32nd-row sample (ix.sa, ix.sa_shift == 5 here)
+MC_HD void mc_sa_dense_body(int64_t j, const DevIndex& ix, int shift, uint32_t* out32, uint64_t* out64)
+{
+	uint64_t k = (uint64_t)j << shift, steps = 0;
+	while (k & 31) { k = mc_lf_step(ix, k); steps++; }
+	const uint64_t v = steps + mc_ldg(ix.sa + (k >> 5));
+	if (out32) out32[j] = (uint32_t)v; else out64[j] = v;
+}
+
+template <> struct KtabOps<RcInterval32> {
+	static MC_HD bool lookup(const DevIndex& ix, uint32_t m, RcInterval32& v, uint32_t* nblk)
+	{
+		const uint32_t x1 = mc_ldg(ix.ktab32 + 2 * (size_t)m), y = mc_ldg(ix.ktab32 + 2 * (size_t)m + 1);
+		if (!y) return false;
+		v.x1 = x1; v.x2 = y & ((1u << MC_KTAB_BITS32) - 1); *nblk += y >> MC_KTAB_BITS32;
+		return true;
+	}
+};
+template <> struct KtabOps<RcInterval> {
+	static MC_HD bool lookup(const DevIndex& ix, uint32_t m, RcInterval& v, uint32_t* nblk)
+	{
+		const uint64_t x1 = mc_ldg(ix.ktab64 + 2 * (size_t)m), y = mc_ldg(ix.ktab64 + 2 * (size_t)m + 1);
+		if (!y) return false;
+		v.x1 = x1; v.x2 = y & ((1ull << MC_KTAB_BITS64) - 1); *nblk += (uint32_t)(y >> MC_KTAB_BITS64);
+		return true;
+	}
+};
+// entry m of the table: the k bases of m, most significant pair first, searched step by step (ix.ktab_k is still 0 here)
+MC_HD void mc_ktab_build_body(int64_t m, const DevIndex& ix, int k, uint32_t* out32, uint64_t* out64)
+{
+	uint32_t nblk = 0; bool ok = true;
+	if (out32)
+	{
+		RcInterval32 v = mc_interval_init32(ix, (int)((m >> (2 * (k - 1))) & 3));
+		for (int j = k - 2; j >= 0 && ok; j--) ok = mc_interval_extend(ix, v, (int)((m >> (2 * j)) & 3), &nblk);
+		ok = ok && v.x2 > 0 && v.x2 < (1u << MC_KTAB_BITS32);
+		out32[2 * m] = ok ? v.x1 : 0u; out32[2 * m + 1] = ok ? (v.x2 | (nblk << MC_KTAB_BITS32)) : 0u;
+	}
+	else
+	{
+		RcInterval v = mc_interval_init(ix, (int)((m >> (2 * (k - 1))) & 3));
+		for (int j = k - 2; j >= 0 && ok; j--) ok = mc_interval_extend(ix, v, (int)((m >> (2 * j)) & 3), &nblk);
+		ok = ok && v.x2 > 0 && v.x2 < (1ull << MC_KTAB_BITS64);
+		out64[2 * m] = ok ? v.x1 : 0ull; out64[2 * m + 1] = ok ? (v.x2 | ((uint64_t)nblk << MC_KTAB_BITS64)) : 0ull;
+	}
 }
 
 #endif

@@ -37,6 +37,8 @@ static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* 
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, 0, 1, ix, p, nb, pre, beg, end, out); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
+static void launch_sa_dense(const DevIndex& ix, int64_t n, int shift, uint32_t* o32, uint64_t* o64, mc_stream_t) { for (int64_t j = 0; j < n; j++) mc_sa_dense_body(j, ix, shift, o32, o64); }
+static void launch_ktab_build(const DevIndex& ix, int k, uint32_t* o32, uint64_t* o64, mc_stream_t) { for (int64_t m = 0; m < (1ll << (2 * k)); m++) mc_ktab_build_body(m, ix, k, o32, o64); }
 static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) profstat_body(i, recs, acc); }
 static void launch_profhash(int64_t g0, int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) { const uint64_t h = profhash_of(g0 + i, recs, i); acc[0] += h; acc[1] ^= h; } }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatecnt_body(i, a, q, list, bump); }
@@ -51,8 +53,8 @@ static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for 
 static void launch_vcdepth(const VcArgs& a, int64_t b0, int64_t b1, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcdepth_body(b, a); }
 static void launch_vcscan(const VcArgs& a, int64_t b0, int64_t b1, bool emit, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcscan_body(b, a, emit); }
 static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t) { for (int64_t r = 0; r < n; r++) samrec_body(r, a, emit); }
-static void device_incmax_i64(int64_t* a, int64_t n, mc_stream_t) { for (int64_t i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
-static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
+static void device_incmax_i64(int64_t* a, int64_t n, void*, mc_stream_t) { for (int64_t i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
+static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, void*, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
 #define MC_SLOTS 8
 #else
@@ -146,7 +148,7 @@ static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t
 }
 // rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent thread blocks
 // (block b takes windows b, b + n_blocks, ...), commit per pair.  A window search is a chain of short loops over small
-// tables (word list, diagonal histogram, filter, staged window): the tables live in shared memory (32 KB per block - enough for the 1500-base windows of the warm-up
+// tables (word list and its hash chains, diagonal histogram, staged window): the tables live in shared memory (32 KB per block - enough for the 1500-base windows of the warm-up
 // chunks at 150-base reads -, six blocks per SM) and the 128 threads of the block share every loop - windows in repeats cost 100x the typical one and
 // their latency is what a replay attempt waits for.
 #define MC_RESCUE_THREADS 128
@@ -233,6 +235,14 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_cbwt_build_kernel(int64_t n, cons
 { int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < n) mc_cbwt_build_body(b, src, dst); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t s)
 { if (n > 0) { mc_cbwt_build_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, src, dst); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_sa_dense_kernel(const DevIndex ix, int64_t n, int shift, uint32_t* o32, uint64_t* o64)
+{ int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (j < n) mc_sa_dense_body(j, ix, shift, o32, o64); }
+static void launch_sa_dense(const DevIndex& ix, int64_t n, int shift, uint32_t* o32, uint64_t* o64, mc_stream_t s)
+{ if (n > 0) { mc_sa_dense_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, n, shift, o32, o64); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_ktab_build_kernel(const DevIndex ix, int k, uint32_t* o32, uint64_t* o64)
+{ int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (m < (1ll << (2 * k))) mc_ktab_build_body(m, ix, k, o32, o64); }
+static void launch_ktab_build(const DevIndex& ix, int k, uint32_t* o32, uint64_t* o64, mc_stream_t s)
+{ const int64_t n = 1ll << (2 * k); mc_ktab_build_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, k, o32, o64); g_launches++; }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t* sums)
 { int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; if (b < nb) profsum_body(b, threadIdx.x & 31, 32, p, G, nb, sums); }   // whole warps leave together
 static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t s)
@@ -287,71 +297,13 @@ static size_t device_scan_scratch_bytes(int64_t) { return 8; }
 static void device_sort_u64(uint64_t* keys, uint64_t*, int64_t n, void*, size_t, mc_stream_t) { std::sort(keys, keys + n); }
 static size_t device_sort_scratch_bytes(int64_t) { return 8; }
 #else
-#define MC_SCAN_TILE 2048   // 256 threads x 8 items
-// pass 1: per-tile totals
-__global__ void __launch_bounds__(256) mc_scan_tile_sums(const uint32_t* in, int64_t n, int64_t* tile_sum)
-{
-	__shared__ int64_t sh[8];
-	const int64_t base = (int64_t)blockIdx.x * MC_SCAN_TILE;
-	int64_t s = 0;
-	for (int k = 0; k < 8; k++) { int64_t i = base + k * 256 + threadIdx.x; if (i < n) s += in[i]; }
-	for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-	__syncthreads();
-	if (threadIdx.x == 0) { int64_t t = 0; for (int w = 0; w < 8; w++) t += sh[w]; tile_sum[blockIdx.x] = t; }
-}
-// pass 2: one block scans the tile totals in place (exclusive); also writes the grand total
-__global__ void __launch_bounds__(1024) mc_scan_tiles(int64_t* tile_sum, int64_t nt, int64_t* total)
-{
-	__shared__ int64_t sh[1024];
-	__shared__ int64_t carry;
-	if (threadIdx.x == 0) carry = 0;
-	__syncthreads();
-	for (int64_t base = 0; base < nt; base += 1024)
-	{
-		int64_t i = base + threadIdx.x;
-		int64_t v = i < nt ? tile_sum[i] : 0;
-		sh[threadIdx.x] = v;
-		__syncthreads();
-		for (int o = 1; o < 1024; o <<= 1)
-		{
-			int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-			__syncthreads();
-			sh[threadIdx.x] += t;
-			__syncthreads();
-		}
-		if (i < nt) tile_sum[i] = carry + sh[threadIdx.x] - v;
-		__syncthreads();
-		if (threadIdx.x == 1023) carry += sh[1023];
-		__syncthreads();
-	}
-	if (threadIdx.x == 0) *total = carry;
-}
-// pass 3: scan inside each tile, offset by the tile prefix
-__global__ void __launch_bounds__(256) mc_scan_finish(const uint32_t* in, int64_t n, const int64_t* tile_pre, int64_t* out)
-{
-	__shared__ int64_t sh[8];
-	const int64_t base = (int64_t)blockIdx.x * MC_SCAN_TILE + (int64_t)threadIdx.x * 8;
-	uint32_t v[8]; int64_t s = 0;
-	for (int k = 0; k < 8; k++) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
-	int64_t incl = s;
-	for (int o = 1; o < 32; o <<= 1) { int64_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
-	if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = incl;
-	__syncthreads();
-	int64_t wpre = 0;
-	for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wpre += sh[w];
-	int64_t run = tile_pre[blockIdx.x] + wpre + incl - s;
-	for (int k = 0; k < 8; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
-}
-static size_t device_scan_scratch_bytes(int64_t n) { return (size_t)((n + MC_SCAN_TILE - 1) / MC_SCAN_TILE + 2) * 8; }
+#include "mc_scan.cuh"
+// exclusive sums uint32 -> int64 (out has n + 1 entries: out[n] = total), in-place exclusive sums of int64 (+ total) and
+// in-place inclusive maxima of int64: one decoupled look-back kernel each (mc_scan.cuh)
 static void device_scan_u32(const uint32_t* in, int64_t* out, int64_t n, int64_t* scratch, mc_stream_t s)
-{
-	const int64_t nt = (n + MC_SCAN_TILE - 1) / MC_SCAN_TILE;
-	if (nt > 0) { mc_scan_tile_sums<<<(unsigned)nt, 256, 0, s>>>(in, n, scratch); g_launches++; }
-	mc_scan_tiles<<<1, 1024, 0, s>>>(scratch, nt, out + n); g_launches++;
-	if (nt > 0) { mc_scan_finish<<<(unsigned)nt, 256, 0, s>>>(in, n, scratch, out); g_launches++; }
-}
-static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, mc_stream_t s) { mc_scan_tiles<<<1, 1024, 0, s>>>(a, n, total); g_launches++; }
+{ device_lookback_scan<uint32_t, ScanSum, false>(in, out, n, scratch, out + n, s); g_launches++; }
+static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, void* scratch, mc_stream_t s)
+{ device_lookback_scan<int64_t, ScanSum, false>(a, a, n, scratch, total, s); g_launches++; }
 __global__ void __launch_bounds__(MC_BLOCK) mc_vcdepth_kernel(const VcArgs a, int64_t b0, int64_t b1)
 { int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < b1) vcdepth_body(b, a); }
 static void launch_vcdepth(const VcArgs& a, int64_t b0, int64_t b1, mc_stream_t s)
@@ -364,33 +316,8 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_samrec_kernel(const SamArgs a, in
 { int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (r < n) samrec_body(r, a, emit); }
 static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t s)
 { if (n > 0) { mc_samrec_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n, emit); g_launches++; } }
-// in-place inclusive max-scan (one block walks the array in 1024-element steps, like mc_scan_tiles)
-__global__ void __launch_bounds__(1024) mc_incmax_kernel(int64_t* a, int64_t n)
-{
-	__shared__ int64_t sh[1024];
-	__shared__ int64_t carry;
-	if (threadIdx.x == 0) carry = INT64_MIN;
-	__syncthreads();
-	for (int64_t base = 0; base < n; base += 1024)
-	{
-		const int64_t i = base + threadIdx.x;
-		sh[threadIdx.x] = i < n ? a[i] : INT64_MIN;
-		__syncthreads();
-		for (int o = 1; o < 1024; o <<= 1)
-		{
-			const int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : INT64_MIN;
-			__syncthreads();
-			if (t > sh[threadIdx.x]) sh[threadIdx.x] = t;
-			__syncthreads();
-		}
-		const int64_t v = sh[threadIdx.x] > carry ? sh[threadIdx.x] : carry;
-		if (i < n) a[i] = v;
-		__syncthreads();
-		if (threadIdx.x == 1023) carry = v;
-		__syncthreads();
-	}
-}
-static void device_incmax_i64(int64_t* a, int64_t n, mc_stream_t s) { if (n > 0) { mc_incmax_kernel<<<1, 1024, 0, s>>>(a, n); g_launches++; } }
+static void device_incmax_i64(int64_t* a, int64_t n, void* scratch, mc_stream_t s)
+{ if (n > 0) { device_lookback_scan<int64_t, ScanMax, true>(a, a, n, scratch, nullptr, s); g_launches++; } }
 #include <cub/device/device_radix_sort.cuh>
 static size_t device_sort_scratch_bytes(int64_t n)
 {

@@ -156,8 +156,16 @@ template <class Interval> MC_HD void seed_walk(int64_t r, const PipeArgs& a)
 			const uint8_t ch = base_at(s, pos, bw);
 			const int c = mc_nt4(ch);
 			if (c > 3) { pos++; continue; }
-			lower |= ch;
-			v = SeedOps<Interval>::init(a.ix, c); p = pos + 1; in_seed = true;
+			// the k-mer start table answers the first k bases with one load (mc_fmindex.h); at an N, an absent or an over-frequent
+			// k-mer the search steps through them as the reference does
+			if (a.ix.ktab_k)
+			{
+				const int K = a.ix.ktab_k;
+				uint32_t m = (uint32_t)c, low = ch; bool clean = true;
+				for (int j = 1; j < K; j++) { const uint8_t cj = base_at(s, pos + j, bw); const int x = mc_nt4(cj); clean = clean && x <= 3; m = (m << 2) | (uint32_t)(x & 3); low |= cj; }
+				if (clean && KtabOps<Interval>::lookup(a.ix, m, v, &nblk)) { lower |= low; p = pos + K; in_seed = true; }
+			}
+			if (!in_seed) { lower |= ch; v = SeedOps<Interval>::init(a.ix, c); p = pos + 1; in_seed = true; }
 		}
 		bool end = p >= rlen;
 		if (!end)
@@ -298,7 +306,7 @@ MC_HD void expand_body(int64_t s, const PipeArgs& a)
 	for (uint32_t i = 0; i < f; i++) { SPair p; p.gpos = (int64_t)(sd.x0 + i); p.rpos = sd.rpos; p.len = sd.len; a.pairs[o + i] = p; }
 }
 
-// Locations: every lane walks LF steps (bwt_sa, src/bwt_search.cpp:109-119) and, the moment its row is a sampled one,
+// Locations: every lane walks LF steps (bwt_sa, src/bwt_search.cpp:109-119; mc_sa_value for the sampling in HBM) and, the moment its row is a sampled one,
 // finishes that location and picks up its next one (locations tid, tid + nthreads, ...), so the lanes of a warp keep
 // stepping together although the walks have very different lengths (0..31+ steps).
 MC_HD void locate_body(int64_t tid, int64_t nthreads, const PipeArgs& a)
@@ -311,10 +319,11 @@ MC_HD void locate_body(int64_t tid, int64_t nthreads, const PipeArgs& a)
 	bool live = true;
 	while (live)
 	{
-		if ((k & 31) == 0)
+		const bool at = mc_sa_sampled(a.ix, k);
+		if (at)
 		{
 			// the seed carries the rows of its reverse complement: an occurrence of that at q is the seed at 2G - q - len
-			const uint64_t q = steps + mc_ldg(a.ix.sa + (k >> 5));
+			const uint64_t q = mc_sa_value(a.ix, k, steps);
 			const int64_t g = (int64_t)((uint64_t)a.ix.twoG - q - (uint64_t)p.len);
 			p.gpos = g;
 			if (g - (int64_t)p.rpos <= 0) p.len = 0;                    // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
@@ -324,7 +333,7 @@ MC_HD void locate_body(int64_t tid, int64_t nthreads, const PipeArgs& a)
 			live = t < a.n_locs;
 			if (live) { p = a.pairs[t]; k = (uint64_t)p.gpos; steps = 0; }
 		}
-		if (live && (k & 31)) { k = mc_lf_step(a.ix, k); steps++; nblk++; }
+		if (live && !mc_sa_sampled(a.ix, k)) { k = mc_lf_step(a.ix, k); steps++; nblk++; }
 	}
 	mc_stat_add(&a.st->locate_blocks, (uint32_t)(nblk));
 	mc_stat_add(&a.st->sa_reads, (uint32_t)(nsa));

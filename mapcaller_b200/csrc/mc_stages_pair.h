@@ -211,20 +211,21 @@ MC_HD int rescue_scan_diag(const uint32_t* wkid0, const KmerEnt* km, int nk, int
 	return total;
 }
 
+#define MC_RESCUE_HASH 2048  // chain heads of the read's 8-mer table (low 11 bits of the 16-bit word id)
 #define MC_RESCUE_MARGIN 32   // how far beyond the moving window edge hits are looked for (validity interval of EstiDistance)
 
 // Tries to place a mate (word list km) inside the window an anchored candidate of the other mate implies and appends a
 // candidate to read `rt` (one iteration of the loops of AlignmentRescue, reference src/AlignmentRescue.cpp:55-79 / :84-106).
 //   dir 0: window [d, d + est + rlen)   - the right edge moves with EstiDistance
 //   dir 1: window [d - est, d + rlen)   - the left edge moves
-// `nl` lanes cooperate (a warp on the GPU): (1) every reference 8-mer of the window (plus a margin beyond the moving edge) is
-// checked against a 4096-bit filter of the read's words, (2) the survivors are compared with all words by all lanes and
-// histogrammed per diagonal, (3) only diagonals with >= 3 hits (a seed needs a run of 3) are walked exactly, (4) the best
-// diagonal is reduced over the lanes, (5) lane 0 appends the candidate.
+// `nl` lanes cooperate (a thread block on the GPU): (1) every reference 8-mer of the window (plus a margin beyond the moving
+// edge) is looked up in a hash table of the read's words (2048 chain heads over the low 11 bits, built by rwin_body) - a lane
+// per window offset, the matching words of its chain are histogrammed per diagonal, (2) only diagonals with >= 3 hits (a seed
+// needs a run of 3) are walked exactly, (3) the best diagonal is reduced over the lanes, (4) lane 0 appends the candidate.
 // *iv_lo / *iv_hi are narrowed to the EstiDistance values for which this call provably does the same: the moving edge stays
 // between the same chromosome ends and no 8-mer hit enters or leaves the window.  All lanes return the same values.
 MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const KmerEnt* km, int nk, int rlen, int dir, int64_t d, int est,
-                      int floor_score, uint32_t* hits, int64_t n_hits, int32_t* lanebuf, const uint32_t* bloom, int* iv_lo, int* iv_hi)
+                      int floor_score, uint32_t* hits, int64_t n_hits, int32_t* lanebuf, const int32_t* khead, const int32_t* knext, uint32_t* wkid, int* iv_lo, int* iv_hi)
 {
 	const int M = MC_RESCUE_MARGIN;
 	int64_t left = dir == 0 ? d : d - (int64_t)(uint32_t)est;
@@ -270,48 +271,30 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 	const int slen = (int)sl;
 	const int dmin = -(rlen - 8), ndiag = slen - 8 - dmin + 1;
 	for (int i = lane; i < ndiag; i += nl) hits[i] = 0;
-	uint32_t* clist = (uint32_t*)(bloom + 128); int32_t* ccount = lanebuf + 6 * nl + 2;
-	if (lane == 0) *ccount = 0;
 	// window offsets scanned: the window itself plus the margin beyond the moving edge
 	const int gs = dir == 1 ? -M : 0, ge = dir == 0 ? slen - 8 + M : slen - 8;
 	// stage the 2-bit codes of the scanned stretch once (lanes read consecutive bases); 4 marks positions outside the text
-	uint32_t* wkid = clist + n_hits; const uint32_t* wkid0 = wkid - gs;          // word id of every scanned offset
+	const uint32_t* wkid0 = wkid - gs;                                          // word id of every scanned offset
 	uint8_t* wref = (uint8_t*)(wkid + n_hits); const uint8_t* wref0 = wref - gs;
 	for (int i = lane; i < ge - gs + 8; i += nl) { const int64_t pos = left + gs + i; wref[i] = (pos < 0 || pos >= a.ix.twoG) ? 4 : (uint8_t)mc_ref_code(a.ix, pos); }
 	MC_GROUP_SYNC();
-	{
-		// pass 1: each lane owns a contiguous run of offsets (so the reference word can be rolled) and keeps those whose word
-		// passes the filter; pass 2: the warp takes the survivors one by one and all lanes compare them with the read's words
-		const int npos = ge - gs + 1, per = (npos + nl - 1) / nl;
-		int g0 = gs + lane * per, g1 = g0 + per; if (g1 > ge + 1) g1 = ge + 1;
-		for (int g = g0; g < g1; g++)
-		{
-			const uint32_t w = win_kmer_id(wref0, g);
-			wkid[g - gs] = w;
-			if (w == 0xFFFFFFFFu) continue;
-			if (!((bloom[(w & 4095) >> 5] >> (w & 31)) & 1)) continue;   // no word of the read ends in these six bases
-			clist[mc_atomic_add(ccount, 1)] = ((uint32_t)(g + M) << 16) | (w & 0xFFFFu);
-		}
-	}
-	MC_GROUP_SYNC();
 	int in_far = -1, out_near = 1 << 30;   // inside hit closest to the moving edge (distance from it), margin hit closest to it
+	for (int g = gs + lane; g <= ge; g += nl)
 	{
-		const int nc = *ccount;
-		for (int c = 0; c < nc; c++)
+		const uint32_t w = win_kmer_id(wref0, g);
+		wkid[g - gs] = w;
+		if (w == 0xFFFFFFFFu) continue;
+		const bool inside = g >= 0 && g <= slen - 8;
+		for (int i = khead[w & (MC_RESCUE_HASH - 1)]; i >= 0; i = knext[i])      // the read's words that share the low bits
 		{
-			const uint32_t e = clist[c]; const int g = (int)(e >> 16) - M; const uint32_t w = e & 0xFFFFu;
-			const bool inside = g >= 0 && g <= slen - 8;
-			for (int i = lane; i < nk; i += nl)
+			if (km[i].wid != w) continue;
+			if (inside)
 			{
-				if (km[i].wid != w) continue;
-				if (inside)
-				{
-					mc_atomic_add(&hits[g - km[i].label - dmin], 1u);
-					const int dist = dir == 0 ? slen - 8 - g : g;          // how far the edge may retreat before this hit drops out
-					if (in_far < 0 || dist < in_far) in_far = dist;
-				}
-				else { const int dist = dir == 0 ? g - (slen - 8) : -g; if (dist < out_near) out_near = dist; }   // >= 1: advance that lets it in
+				mc_atomic_add(&hits[g - km[i].label - dmin], 1u);
+				const int dist = dir == 0 ? slen - 8 - g : g;          // how far the edge may retreat before this hit drops out
+				if (in_far < 0 || dist < in_far) in_far = dist;
 			}
+			else { const int dist = dir == 0 ? g - (slen - 8) : -g; if (dist < out_near) out_near = dist; }   // >= 1: advance that lets it in
 		}
 	}
 	lanebuf[4 * nl + lane] = in_far; lanebuf[5 * nl + lane] = out_near;
@@ -400,7 +383,7 @@ MC_HD void rwin_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* fa
 	const int lm = (int)(a.roff[rm + 1] - a.roff[rm]);
 	const int64_t d = cand_posdiff(a, a.cands[pa_cand_off(a, ra) + w->cand]);
 	const int64_t n_hits = (int64_t)(uint32_t)est + 2 * (int64_t)lm + 2 * MC_RESCUE_MARGIN + 32;
-	const int64_t wsn = ((int64_t)(lm + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (6 * nl + 4) * 4 + 128 * 4 + n_hits * 4 + n_hits * 4 + n_hits + 15) & ~15ll;
+	const int64_t wsn = ((int64_t)(lm + 2) * (int64_t)sizeof(KmerEnt) + n_hits * 4 + (6 * nl + 4) * 4 + MC_RESCUE_HASH * 4 + (int64_t)(lm + 2) * 4 + n_hits * 4 + n_hits + 15) & ~15ll;
 	uint8_t* scratch = fast;
 	if (!fast || wsn > fast_bytes)
 	{
@@ -412,14 +395,15 @@ MC_HD void rwin_body(int64_t t, int lane, int nl, const PipeArgs& a, uint8_t* fa
 	}
 	KmerEnt* km = (KmerEnt*)scratch;
 	uint32_t* hits = (uint32_t*)(km + lm + 2); int32_t* lanebuf = (int32_t*)(hits + n_hits);
-	uint32_t* bloom = (uint32_t*)(lanebuf + 6 * nl + 4);   // 4096-bit filter over the low 12 bits of the mate's word ids
-	for (int i = lane; i < 128; i += nl) bloom[i] = 0;
+	// hash table over the low bits of the mate's word ids: khead[h] = last word with that hash, knext[] chains the others
+	int32_t* khead = lanebuf + 6 * nl + 4; int32_t* knext = khead + MC_RESCUE_HASH; uint32_t* wkid = (uint32_t*)(knext + lm + 2);
+	for (int i = lane; i < MC_RESCUE_HASH; i += nl) khead[i] = -1;
 	MC_GROUP_SYNC();
 	const int nk = kmer_list_coop(a.seq + a.roff[rm], lm, km, lane, nl, lanebuf);
-	for (int i = lane; i < nk; i += nl) mc_atomic_or(&bloom[(km[i].wid & 4095) >> 5], 1u << (km[i].wid & 31));
+	for (int i = lane; i < nk; i += nl) knext[i] = mc_atomic_exch(&khead[km[i].wid & (MC_RESCUE_HASH - 1)], i);
 	MC_GROUP_SYNC();
 	int lo = -2147483647, hi = 2147483647;
-	const bool ok = rescue_try(a, lane, nl, w, km, nk, lm, dir, d, est, w->floor, hits, n_hits, lanebuf, bloom, &lo, &hi);
+	const bool ok = rescue_try(a, lane, nl, w, km, nk, lm, dir, d, est, w->floor, hits, n_hits, lanebuf, khead, knext, wkid, &lo, &hi);
 	if (lane == 0) { w->ok = ok ? 1 : 0; w->lo = lo; w->hi = hi; }
 }
 

@@ -50,11 +50,12 @@ def test_cuda_matches_oracle(built, name):
     mine = pu.cuda_results(case, ix)
     orc = pu.oracle_results(case, ix)
     pu.assert_same(mine, orc, paired=bool(case["params"]["paired"]))
-    # the work counter the seed-kernel roofline is computed from is the oracle's, exactly; the locate kernel walks the
-    # rows of the seed's reverse complement (same hits), so its block count only matches on average
+    # the work counter the seed-kernel roofline is computed from is the oracle's, exactly.  The locate kernel meets a sampled
+    # row after 3 LF steps on average (every 4th row is sampled in HBM) where the reference needs 31
     for k in ("seed_blocks", "sa_reads"):
         assert mine["stats"][k] == orc["work"][k], k
-    assert abs(mine["stats"]["locate_blocks"] - orc["work"]["locate_blocks"]) <= 0.1 * orc["work"]["locate_blocks"] + 2000
+    assert abs(mine["stats"]["locate_blocks"] - 3 * orc["work"]["sa_reads"]) <= 0.15 * 3 * orc["work"]["sa_reads"] + 2000
+    assert mine["stats"]["locate_blocks"] < orc["work"]["locate_blocks"]
 
 
 @pytest.mark.skipif(not pu.have_ref(), reason="oracle/_ref not on this box")
@@ -77,14 +78,16 @@ def test_batch_split_invariance(built, batch_reads):
 
 def test_index_layouts_agree(built):
     """Texts shorter than 2^32 symbols use the compact device index (32-byte blocks of 64 rows); longer ones the reference's
-    128-row blocks (mc_params.reserved[1] forces them).  Same results, same work counters."""
+    128-row blocks and a 64-bit suffix-array sample of every 8th row (mc_params.reserved[1] forces both).  Same results, same
+    seeding work."""
     case = pu.make_case(seed=31, n_pairs=6000, genome_len=150000, contigs=2, n_rate=0.002, paired=1)
     ix = pu.build_index(case)
     compact = pu.cuda_results(case, ix)
     wide = pu.cuda_results(case, ix, reserved=(0, 1, 0, 0, 0))
     pu.assert_same(wide, compact)
-    for k in ("seed_blocks", "sa_reads", "locate_blocks"):
+    for k in ("seed_blocks", "sa_reads"):
         assert wide["stats"][k] == compact["stats"][k], k
+    assert wide["stats"]["locate_blocks"] > compact["stats"]["locate_blocks"]      # 7 vs 3 steps per location on average
     pu.assert_same(wide, pu.oracle_results(case, ix))
 
 
