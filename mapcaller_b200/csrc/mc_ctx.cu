@@ -768,8 +768,8 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			if (dbg_att)
 			{
 				int64_t na = 0, nl = 0; for (int64_t k = 0; k < NG; k++) { na += active[k]; if (k >= g0 && k < g0 + n_chunks) nl += active[k]; }
-				fprintf(stderr, "[mc] rank %d attempt: %lld active chunks (%lld mine) of %lld, first open %lld, %.3f ms\n", od.on ? od.me : 0, (long long)na, (long long)nl, (long long)NG, (long long)first_open,
-				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - att_t0).count());
+				fprintf(stderr, "[mc] rank %d attempt: %lld active chunks (%lld mine) of %lld, first open %lld, %.3f ms; rescue pairs %lld windows %lld, pieces %lld, fills %lld\n", od.on ? od.me : 0, (long long)na, (long long)nl, (long long)NG, (long long)first_open,
+				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - att_t0).count(), (long long)hbp->rtask - (long long)a.rtask_begin, (long long)hbp->rwin, (long long)hbp->ptask - (long long)a.ptask_begin, (long long)hbp->task - (long long)a.task_begin);
 			}
 			for (int64_t k = 0; k < NG; k++) if (active[k]) computed[k] = ever[k] = 1;
 			// walk the chunks in file order (reference src/ReadMapping.cpp:537-539)

@@ -22,6 +22,9 @@
 struct mc_u32x4 { uint32_t x, y, z, w; };
 static inline mc_u32x4 mc_ldg128(const void* p) { mc_u32x4 v; memcpy(&v, p, 16); return v; }
 template <class T> static inline T mc_ldg(const T* p) { return *p; }
+static inline mc_u32x4 mc_gather128(const void* p) { return mc_ldg128(p); }
+static inline uint32_t mc_gather32(const uint32_t* p) { return *p; }
+static inline uint64_t mc_gather64(const uint64_t* p) { return *p; }
 template <class T> static inline T mc_atomic_add(T* p, T v) { T o = *p; *p = (T)(o + v); return o; }
 template <class T> static inline void mc_atomic_or(T* p, T v) { *p = (T)(*p | v); }
 static inline int mc_atomic_exch(int* p, int v) { int o = *p; *p = v; return o; }
@@ -41,6 +44,17 @@ static inline int mc_warp_last(int v) { return v; }
 typedef uint4 mc_u32x4;
 static __device__ __forceinline__ mc_u32x4 mc_ldg128(const void* p) { return __ldg((const uint4*)p); }
 template <class T> static __device__ __forceinline__ T mc_ldg(const T* p) { return __ldg(p); }
+// Random gathers from tables far larger than L2 (FM-index blocks, suffix-array samples, k-mer table): by default an L2 miss
+// fetches the whole 128-byte line from HBM; the .L2::64B prefetch-size qualifier halves that (tools/probes/gather_probe2.cu:
+// 123 -> 63 bytes of DRAM traffic per random 32-byte gather, no other load flavour changes it).
+static __device__ __forceinline__ mc_u32x4 mc_gather128(const void* p)
+{
+	mc_u32x4 v;
+	asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+static __device__ __forceinline__ uint32_t mc_gather32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+static __device__ __forceinline__ uint64_t mc_gather64(const uint64_t* p) { uint64_t v; asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
 static __device__ __forceinline__ unsigned long long mc_atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 static __device__ __forceinline__ uint32_t mc_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 static __device__ __forceinline__ int mc_atomic_add(int* p, int v) { return atomicAdd(p, v); }

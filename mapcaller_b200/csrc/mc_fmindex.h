@@ -50,7 +50,7 @@ struct OccBlock { mc_u32x4 q0, q1, q2, q3; };
 MC_HD void mc_load_block(const DevIndex& ix, uint64_t blk, OccBlock& b)
 {
 	const uint32_t* p = ix.bwt + (blk << 4);
-	b.q0 = mc_ldg128(p); b.q1 = mc_ldg128(p + 4); b.q2 = mc_ldg128(p + 8); b.q3 = mc_ldg128(p + 12);
+	b.q0 = mc_gather128(p); b.q1 = mc_gather128(p + 4); b.q2 = mc_gather128(p + 8); b.q3 = mc_gather128(p + 12);
 }
 
 // bwt_invPsi (reference src/bwt_search.cpp:101-107): one LF step = one block
@@ -65,8 +65,8 @@ MC_HD bool mc_sa_sampled(const DevIndex& ix, uint64_t k) { return (k & ((1ull <<
 MC_HD uint64_t mc_sa_value(const DevIndex& ix, uint64_t k, uint64_t steps)
 {
 	// 32-bit entries: row 0 holds (uint32)-1 like the reference's sa[0] = -1, and is only ever reached after >= 1 step
-	if (ix.sa32) return (uint64_t)(uint32_t)((uint32_t)steps + mc_ldg(ix.sa32 + (k >> ix.sa_shift)));
-	return steps + mc_ldg(ix.sa + (k >> ix.sa_shift));
+	if (ix.sa32) return (uint64_t)(uint32_t)((uint32_t)steps + mc_gather32(ix.sa32 + (k >> ix.sa_shift)));
+	return steps + mc_gather64(ix.sa + (k >> ix.sa_shift));
 }
 // bwt_sa (reference src/bwt_search.cpp:109-119): walk LF until a sampled row
 MC_HD uint64_t mc_locate(const DevIndex& ix, uint64_t k, uint32_t* nblk)
@@ -136,7 +136,7 @@ static inline uint32_t mc_prefix_bits(int n) { return n <= 0 ? 0u : n >= 32 ? 0x
 #else
 static __device__ __forceinline__ void mc_load_cblock(const DevIndex& ix, uint32_t blk, CBlock& b)
 {
-	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	asm volatile("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(b.lo0), "=r"(b.lo1), "=r"(b.hi0), "=r"(b.hi1) : "l"(ix.cbwt + ((size_t)blk << 3)));
 }
 // mask of the low min(n, 32) bits: high word of 0:FFFFFFFF << n, shift clamped to 32
@@ -182,7 +182,7 @@ struct OccPart { mc_u32x4 qc, q2, q3; };
 MC_HD void mc_load_part(const DevIndex& ix, uint64_t blk, int i, OccPart& b)
 {
 	const uint32_t* p = ix.bwt + (blk << 4);
-	b.qc = mc_ldg128(p + ((i & 2) << 1)); b.q2 = mc_ldg128(p + 8); b.q3 = mc_ldg128(p + 12);
+	b.qc = mc_gather128(p + ((i & 2) << 1)); b.q2 = mc_gather128(p + 8); b.q3 = mc_gather128(p + 12);
 }
 MC_HD uint64_t mc_part_base(const OccPart& b, int i) { return (i & 1) ? ((uint64_t)b.qc.w << 32 | b.qc.z) : ((uint64_t)b.qc.y << 32 | b.qc.x); }
 MC_HD int mc_count_in_part(const OccPart& b, uint32_t flip, int nbits)
@@ -287,7 +287,7 @@ MC_HD void mc_sa_dense_body(int64_t j, const DevIndex& ix, int shift, uint32_t* 
 template <> struct KtabOps<RcInterval32> {
 	static MC_HD bool lookup(const DevIndex& ix, uint32_t m, RcInterval32& v, uint32_t* nblk)
 	{
-		const uint32_t x1 = mc_ldg(ix.ktab32 + 2 * (size_t)m), y = mc_ldg(ix.ktab32 + 2 * (size_t)m + 1);
+		const uint64_t e = mc_gather64((const uint64_t*)ix.ktab32 + m); const uint32_t x1 = (uint32_t)e, y = (uint32_t)(e >> 32);
 		if (!y) return false;
 		v.x1 = x1; v.x2 = y & ((1u << MC_KTAB_BITS32) - 1); *nblk += y >> MC_KTAB_BITS32;
 		return true;
@@ -296,7 +296,7 @@ template <> struct KtabOps<RcInterval32> {
 template <> struct KtabOps<RcInterval> {
 	static MC_HD bool lookup(const DevIndex& ix, uint32_t m, RcInterval& v, uint32_t* nblk)
 	{
-		const uint64_t x1 = mc_ldg(ix.ktab64 + 2 * (size_t)m), y = mc_ldg(ix.ktab64 + 2 * (size_t)m + 1);
+		const mc_u32x4 e = mc_gather128(ix.ktab64 + 2 * (size_t)m); const uint64_t x1 = (uint64_t)e.y << 32 | e.x, y = (uint64_t)e.w << 32 | e.z;
 		if (!y) return false;
 		v.x1 = x1; v.x2 = y & ((1ull << MC_KTAB_BITS64) - 1); *nblk += (uint32_t)(y >> MC_KTAB_BITS64);
 		return true;

@@ -161,4 +161,128 @@ MC_HD void samrec_body(int64_t r, const SamArgs& a, bool emit)
 	a.out[r] = o;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SAM text on the device: the lines GenerateSingleSamStream / GeneratePairedSamStream sprintf (src/SamReport.cpp:324-488),
+// assembled from the fields above and the batch's FASTQ text where mc_ingest_fastq left it in HBM (QNAME as
+// IdentifyHeaderBegPos / IdentifyHeaderEndPos cut it, src/GetData.cpp:3-21; SEQ / QUAL reverse-complemented / reversed for a
+// reverse-strand alignment, GetComplementarySeq src/tools.cpp:19).  One thread per read, two passes (line length, then the
+// text at its scanned offset).  `unique` = bUnique: one line per read; otherwise (-m) one per candidate that reaches the
+// read's best score.
+struct SamTextArgs {
+	SamArgs s;
+	const uint8_t* text[2]; const int64_t* line_end[2];   // FASTQ text of the batch and its newline table (line_end[-1] = -1)
+	int32_t two_files, unique;
+	const uint8_t* chrom_names; const int32_t* chrom_name_off;   // names back to back, n_chrom + 1 offsets
+	uint32_t* tlen; const int64_t* toff; uint8_t* out;
+};
+struct SamWriter {
+	uint8_t* p; int64_t at;
+	MC_HD void ch(char c) { if (p) p[at] = (uint8_t)c; at++; }
+	MC_HD void bytes(const uint8_t* s, int n) { if (p) for (int i = 0; i < n; i++) p[at + i] = s[i]; at += n; }
+	MC_HD void lit(const char* s) { for (; *s; s++) ch(*s); }
+	MC_HD void num(long long v)
+	{
+		char d[24]; int nd = 0; unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+		if (v < 0) ch('-');
+		do { d[nd++] = (char)('0' + u % 10); u /= 10; } while (u > 0);
+		if (p) for (int k = 0; k < nd; k++) p[at + k] = (uint8_t)d[nd - 1 - k];
+		at += nd;
+	}
+};
+// bases / qualities of a read as the line shows them
+// `twice`: mate 2 on the reverse strand - it was reverse-complemented before mapping (ReverseOrientation) and is complemented
+// back for the line, which folds lower case to upper and everything that is not ACGT to N on the way
+MC_HD void sam_put_seq(SamWriter& w, const uint8_t* seq, int n, bool reverse, bool twice)
+{
+	if (w.p)
+	{
+		if (reverse) for (int i = 0; i < n; i++) w.p[w.at + i] = mc_complement(seq[n - 1 - i]);
+		else if (twice) for (int i = 0; i < n; i++) w.p[w.at + i] = mc_complement(mc_complement(seq[i]));
+		else for (int i = 0; i < n; i++) w.p[w.at + i] = seq[i];
+	}
+	w.at += n;
+}
+MC_HD void sam_put_qual(SamWriter& w, const uint8_t* q, int n, bool reverse)
+{
+	if (!reverse) { w.bytes(q, n); return; }
+	if (w.p) for (int i = 0; i < n; i++) w.p[w.at + i] = q[n - 1 - i];
+	w.at += n;
+}
+
+MC_HD void samtext_body(int64_t r, const SamTextArgs& t, bool emit)
+{
+	const SamArgs& a = t.s;
+	SamWriter w; w.p = emit ? t.out + t.toff[r] : nullptr; w.at = 0;
+	// the read's record in the FASTQ text: header line, bases, '+' line, qualities
+	const int f = t.two_files ? (int)(r & 1) : 0;
+	const int64_t rec = t.two_files ? (r >> 1) : r;
+	const int64_t* le = t.line_end[f] + 4 * rec;
+	const uint8_t* hdr = t.text[f] + le[-1] + 1; const int hlen = (int)(le[0] - le[-1]);   // including the newline, as getline() counts
+	const uint8_t* seq = t.text[f] + le[0] + 1; const int rlen = (int)(le[1] - le[0] - 1);
+	const uint8_t* qual = t.text[f] + le[2] + 1;
+	int p1 = hlen - 1, p2 = (hlen > 100 ? 100 : hlen) - 1;
+	for (int i = 1; i < hlen; i++) if (hdr[i] != '>' && hdr[i] != '@') { p1 = i; break; }
+	for (int i = 1; i < (hlen > 100 ? 100 : hlen); i++) if (hdr[i] == ' ' || hdr[i] == '/' || hdr[i] < 0x20 || hdr[i] > 0x7E) { p2 = i; break; }
+	const int nlen = p2 > p1 ? p2 - p1 : 0;
+
+	const ReadSum rs = a.rsum[r];
+	const bool paired = a.paired != 0, first = !(r & 1);
+	const int64_t m = paired ? (r ^ 1) : r;
+	const int64_t co = a.cand_off[r];
+	if (rs.score == 0)
+	{
+		int flag = 0x4;
+		if (paired)
+		{
+			flag = 0x1 | 0x4 | (first ? 0x40 : 0x80);
+			if (a.rsum[m].score == 0) flag |= 0x8; else if (a.ncand[m] > 0) flag |= 0x30;
+		}
+		const bool rev = paired && !first;      // an unmapped mate 2 is printed as it was mapped: reverse-complemented
+		w.bytes(hdr + p1, nlen); w.ch('\t'); w.num(flag); w.lit("\t*\t0\t0\t*\t*\t0\t0\t");
+		sam_put_seq(w, seq, rlen, rev, false); w.ch('\t'); sam_put_qual(w, qual, rlen, rev); w.lit("\tAS:i:0\tXS:i:0\n");
+		if (!emit) t.tlen[r] = (uint32_t)w.at;
+		return;
+	}
+	int mapq;
+	if (rs.score == rs.sub_score) mapq = 0;
+	else if (rs.sub_score == 0 || rs.score - rs.sub_score > 5) mapq = 60;
+	else mapq = a.mapq_tab[(rs.score - rs.sub_score - 1) * (MC_MAX_RLEN + 1) + rs.score];
+	const int nc = a.ncand[r];
+	const int64_t co2 = paired ? a.cand_off[m] : 0;
+	for (int i = rs.best_idx; i < nc; i++)
+	{
+		if (a.cscore[co + i] != rs.score) continue;
+		const bool fwd = a.corient[co + i] == 1;
+		const int j = paired ? a.cpaired[co + i] : -1;
+		int flag;
+		if (!paired) flag = fwd ? 0 : 0x10;
+		else
+		{
+			const bool uniq = rs.score > rs.sub_score, ok = j != -1 && a.cscore[co2 + j] > 0;
+			const int same = first ? (fwd ? 0x20 : 0x10) : (fwd ? 0x10 : 0x20), other = same ^ 0x30;
+			flag = (first ? 0x41 : 0x81) | same;
+			if (ok) flag |= 0x2; else { if (uniq) flag |= other; flag |= 0x8; }
+		}
+		const SamCoor c1 = sam_aln_coordinate(a, co + i, fwd);
+		const bool rev = (paired && !first) ? fwd : !fwd;
+		w.bytes(hdr + p1, nlen); w.ch('\t'); w.num(flag); w.ch('\t');
+		w.bytes(t.chrom_names + t.chrom_name_off[c1.chrom], t.chrom_name_off[c1.chrom + 1] - t.chrom_name_off[c1.chrom]); w.ch('\t');
+		w.num(c1.pos); w.ch('\t'); w.num(mapq); w.ch('\t');
+		w.at += sam_cigar(a, co + i, rlen, fwd, w.p ? w.p + w.at : nullptr);
+		if (paired && j != -1 && a.rsum[m].score > 0 && a.cscore[co2 + j] == a.rsum[m].score)
+		{
+			const bool mfwd = a.corient[co2 + j] == 1;
+			const SamCoor c2 = sam_aln_coordinate(a, co2 + j, mfwd);
+			const int mlen = (int)(a.roff[m + 1] - a.roff[m]);
+			const int tl = first ? (int)(c2.pos - c1.pos + (fwd ? mlen : 0 - rlen)) : 0 - (int)(c1.pos - c2.pos + (mfwd ? rlen : 0 - mlen));
+			w.lit("\t=\t"); w.num(c2.pos); w.ch('\t'); w.num(tl); w.ch('\t');
+		}
+		else w.lit("\t*\t0\t0\t");
+		sam_put_seq(w, seq, rlen, rev, paired && !first && !rev); w.ch('\t'); sam_put_qual(w, qual, rlen, rev);
+		w.lit("\tNM:i:"); w.num(rlen - a.cscore[co + i]); w.lit("\tAS:i:"); w.num(rs.score); w.lit("\tXS:i:"); w.num(rs.sub_score); w.ch('\n');
+		if (t.unique) break;
+	}
+	if (!emit) t.tlen[r] = (uint32_t)w.at;
+}
+
 #endif
