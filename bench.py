@@ -307,8 +307,8 @@ def main():
     chk1, chk2 = r1[:CHECK_PAIRS].copy(), r2[:CHECK_PAIRS].copy()
     del r1, r2
     t_setup = time.perf_counter() - t_setup
-    S_IN0, S_IN1 = n_batches, n_batches + 1      # device slots of the double-buffered FASTQ feed
-    assert n_batches + 2 <= 8
+    S_IN0 = n_batches                            # first of the three device slots of the FASTQ feed
+    assert n_batches + 3 <= 8
 
     # ---- resident leg (value) ----
     def one_pass():
@@ -333,30 +333,35 @@ def main():
 
     # ---- end-to-end leg: FASTQ text (host) -> variant records (host) ----
     def fastq_pass(sam: bool):
+        # three device slots in flight: block b+1 on the wire (mc_ingest_prefetch, plain DMA), block b being parsed
+        # (mc_ingest_fastq) by the feeder thread, block b-1 being mapped by this thread
         ctx.reset()
         err = []
-        ready = [threading.Semaphore(0), threading.Semaphore(0)]; free = [threading.Semaphore(1), threading.Semaphore(1)]
+        ready = [threading.Semaphore(0) for _ in range(3)]; free = [threading.Semaphore(1) for _ in range(3)]
+        slot = lambda b: S_IN0 + b % 3
 
         def feeder():
             try:
+                free[0].acquire(); ctx.ingest_prefetch(ptext[0][0], ptext[0][1], slot=slot(0))
                 for b in range(n_batches):
-                    free[b & 1].acquire()
-                    ctx.ingest_fastq(ptext[b][0], ptext[b][1], slot=S_IN0 + (b & 1), final=True, keep_text=sam)
-                    ready[b & 1].release()
+                    if b + 1 < n_batches:
+                        free[(b + 1) % 3].acquire(); ctx.ingest_prefetch(ptext[b + 1][0], ptext[b + 1][1], slot=slot(b + 1))
+                    ctx.ingest_fastq(ptext[b][0], ptext[b][1], slot=slot(b), final=True)
+                    ready[b % 3].release()
             except Exception as e:      # surfaces in the main thread
                 err.append(e)
-                for s in ready:
-                    s.release()
+                for s_ in ready:
+                    s_.release()
         th = threading.Thread(target=feeder); th.start()
         sam_bytes = 0
         for b in range(n_batches):
-            ready[b & 1].acquire()
+            ready[b % 3].acquire()
             if err:
                 break
-            ctx.map_staged(S_IN0 + (b & 1))
+            ctx.map_staged(slot(b))
             if sam:
-                sam_bytes += ctx.sam_text_raw(S_IN0 + (b & 1))
-            free[b & 1].release()
+                sam_bytes += ctx.sam_text_raw(slot(b))
+            free[b % 3].release()
         th.join()
         if err:
             raise err[0]
@@ -447,7 +452,7 @@ def main():
                 "ms_per_step": 1000 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
                 "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(st["kernel_launches"]),
                 "e2e": {"value": total_pairs / wall_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1000 * wall_e2e / args.steps,
-                        "how": "FASTQ text of both mate files in page-locked host memory -> mc_ingest_fastq (H2D + record parse on the device; a feeder thread stages block i+1 while block i is mapped) -> mc_map_staged -> "
+                        "how": "FASTQ text of both mate files in page-locked host memory -> mc_ingest_fastq (H2D by mc_ingest_prefetch + record parse on the device; a feeder thread keeps block i+2 on the wire and parses block i+1 while block i is mapped) -> mc_map_staged -> "
                                + ("mc_profile_allreduce -> " if world > 1 else "") + "mc_variant_scan (variant records + block depths back in host memory); bytes = the library's copy counters (this rank)",
                         "variant_records": int(n_var)},
                 "roofline": roof("mc_seed_kernel", st["seed_blocks"] * 64, st["ms_seed"], "algorithmic bytes = 64 B x occ blocks of the reference algorithm (kernel counter = oracle count); time = CUDA events around the seed launches of the timed steps"),

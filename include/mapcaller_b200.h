@@ -210,6 +210,14 @@ typedef struct {
 /* `recs` (one per read of the batch) and `cigar_arena` stay valid until the next call on ctx. */
 int mc_sam_records(mc_ctx *ctx, const mc_sam_rec **recs, int64_t *n_recs, const uint8_t **cigar_arena);
 
+/* The SAM TEXT of the batch just mapped, assembled on the device: the lines GeneratePairedSamStream / GenerateSingleSamStream
+ * print (reference src/SamReport.cpp:324-488), in read order, each terminated by '\n' (no line for a read the reference
+ * prints none for).  The batch must have been staged by mc_ingest_fastq(slot) and mapped by mc_map_staged(slot): its FASTQ
+ * text is still in the slot, and QNAME (IdentifyHeaderBegPos / IdentifyHeaderEndPos, src/GetData.cpp:3-21), SEQ and QUAL
+ * are taken from there.  all_best != 0 is the reference's -m (bUnique = false): one line per candidate that reaches the
+ * read's best score instead of one line per read.  `text` is page-locked library memory, valid until the next call. */
+int mc_sam_text(mc_ctx *ctx, int32_t slot, int32_t all_best, const uint8_t **text, int64_t *n_bytes);
+
 /* ---- variant-calling scan (reference src/VariantCalling.cpp:106-120 CalBlockReadDepth, :550-680 IdentifyVariants,
  *      :60-98 GetAreaIndFrequency, :523-548 DetermineGenotype) over the device-resident profile, without downloading
  *      the 16-byte-per-column MappingRecordArr.  The columns are scanned on the GPU in blocks of 100 (the reference's
@@ -276,6 +284,11 @@ typedef struct {
 typedef struct { int64_t n_reads, consumed1, consumed2, n_bases;
                  int64_t records1, records2;   /* whole records the blocks held (before the cut to n_reads) */ } mc_fastq_out;
 int mc_ingest_fastq(mc_ctx *ctx, const mc_fastq_in *in, int32_t slot, mc_fastq_out *out);
+/* Optional: queues the host -> device copy of the blocks a later mc_ingest_fastq(ctx, in, slot, ..) is going to parse (same
+ * pointers and lengths) and returns at once; the copy is plain DMA on a stream of its own, so PCIe stays busy while an
+ * earlier block is parsed and a still earlier one is mapped.  The blocks must lie in page-locked memory (mc_host_alloc)
+ * and stay untouched until that mc_ingest_fastq has returned. */
+int mc_ingest_prefetch(mc_ctx *ctx, const mc_fastq_in *in, int32_t slot);
 /* mc_ingest_fastq() works on the context's copy stream with scratch of its own: a second host thread may ingest the next
  * block into slot s' while mc_map_staged() maps slot s != s' (the one exception to "calls on one ctx are serialised";
  * the text must then lie in page-locked memory, mc_host_alloc). */

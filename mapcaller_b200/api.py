@@ -133,6 +133,8 @@ def lib():
         L.mc_stage_batch_async.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.c_int32]
         L.mc_ingest_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.mc_map_staged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BatchOut)]
+        L.mc_ingest_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.mc_sam_text.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_get_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
         L.mc_set_totals.argtypes = [C.c_void_p, C.POINTER(Totals)]
         L.mc_reset.argtypes = [C.c_void_p]
@@ -303,6 +305,31 @@ class Context:
         out = (C.c_int64 * 6)()
         _check(lib().mc_ingest_fastq(self._h, arg, slot, out), "mc_ingest_fastq")
         return dict(n_reads=int(out[0]), consumed1=int(out[1]), consumed2=int(out[2]), n_bases=int(out[3]), records1=int(out[4]), records2=int(out[5]))
+
+    @staticmethod
+    def _fastq_arg(text1, text2, max_reads, final):
+        t1 = np.frombuffer(text1, dtype=np.uint8) if isinstance(text1, (bytes, bytearray)) else np.ascontiguousarray(text1, dtype=np.uint8)
+        t2 = None if text2 is None else (np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else np.ascontiguousarray(text2, dtype=np.uint8))
+        arg = (C.c_int64 * 6)(t1.ctypes.data, len(t1), t2.ctypes.data if t2 is not None else 0, len(t2) if t2 is not None else 0, max_reads, int(bool(final)))
+        return arg, (t1, t2)
+
+    def ingest_prefetch(self, text1, text2=None, slot: int = 0):
+        """Queues the host -> device copy of the blocks the next ingest_fastq(slot) parses (page-locked arrays) and returns."""
+        arg, keep = self._fastq_arg(text1, text2, 0, True)
+        self._prefetched = getattr(self, "_prefetched", {}); self._prefetched[slot] = keep
+        _check(lib().mc_ingest_prefetch(self._h, arg, slot), "mc_ingest_prefetch")
+
+    def sam_text_raw(self, slot: int, all_best: bool = False) -> int:
+        """mc_sam_text: the SAM lines of the batch just mapped from `slot` are left in the library's page-locked buffer; returns
+        the number of bytes."""
+        p, n = C.c_void_p(), C.c_int64()
+        _check(lib().mc_sam_text(self._h, slot, int(all_best), C.byref(p), C.byref(n)), "mc_sam_text")
+        self._sam_text = (p.value, n.value)
+        return int(n.value)
+
+    def sam_text(self, slot: int, all_best: bool = False) -> bytes:
+        n = self.sam_text_raw(slot, all_best)
+        return C.string_at(self._sam_text[0], n)
 
     def map_staged(self, slot: int = 0, copy: bool = False):
         out = BatchOut()

@@ -164,6 +164,9 @@ struct Bumps { mc_u64 pair, frag, aln, task, dpws, rtask, key, ptask, rwin; };
 struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
 struct Staged { DBuf seq, roff, seed_off, cap, scan, flag; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false;
+	// a slot filled by mc_ingest_fastq keeps the FASTQ text and its newline table in HBM (mc_sam_text prints names, bases and qualities from them)
+	DBuf text[2], lines[2]; int n_files = 0; bool has_text = false;
+	const void* pre_src[2] = {nullptr, nullptr}; int64_t pre_len[2] = {0, 0}; bool prefetched = false;   // mc_ingest_prefetch
 	int n_pieces = 0; int64_t piece_end[8];
 	bool pending = false; };   // staged asynchronously: the consumer has to wait for ev_slot[] first   // read ranges [piece_end[p-1], piece_end[p]) whose bases arrive one after the other (events ev_piece[])
 
@@ -187,9 +190,9 @@ struct mc_ctx {
 	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off, d_scan2;
 	HBuf h_disc;
 	HBuf h_bounce[2];
-	mc_stream_t cstream;
+	mc_stream_t cstream, dstream;   // copy + staging kernels; plain DMA of prefetched FASTQ blocks
 #ifndef MC_HOSTEMU
-	cudaEvent_t ev_bounce[2], ev_piece[8], ev_slot[MC_SLOTS];
+	cudaEvent_t ev_bounce[2], ev_piece[8], ev_slot[MC_SLOTS], ev_text[MC_SLOTS];
 #endif
 	double frag_factor = 6.0, aln_factor = 3.0, dpws_factor = 2.0, task_factor = 1.0; int64_t rescue_cap = 1 << 20;
 	// pinned host staging
@@ -208,7 +211,8 @@ struct mc_ctx {
 	std::vector<mc_variant_rec> vc_out; std::vector<int32_t> vc_depth;
 	DBuf d_vc[12];   // scratch of mc_variant_scan, kept between calls
 	int64_t last_n = 0; const int64_t* last_roff = nullptr;   // the batch whose arenas are still on the device (mc_sam_records)
-	DBuf d_sam[5]; std::vector<mc_sam_rec> sam_out; std::vector<uint8_t> sam_cigar;
+	DBuf d_sam[5], d_chrom_names, d_chrom_name_off; HBuf h_sam_text; std::vector<mc_sam_rec> sam_out; std::vector<uint8_t> sam_cigar;
+	std::vector<std::string> chrom_names;
 	// stats
 	mc_stats stats; DevStats dstats_last;
 	mc_event_t ev[EV_COUNT];
@@ -216,7 +220,7 @@ struct mc_ctx {
 	ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;
 	DBuf d_comm_small, d_comm_buf, d_glist, d_glist_all; HBuf h_comm_buf;
 #endif
-	DBuf fq_text[2], fq_cnt[2], fq_off[2], fq_lines[2], fq_scan, fq_rlen, fq_rsrc;   // scratch of mc_ingest_fastq
+	DBuf fq_cnt[2], fq_off[2], fq_scan, fq_rlen, fq_rsrc;   // scratch of mc_ingest_fastq
 };
 
 static void zero_stats(mc_stats* s) { memset(s, 0, sizeof(*s)); }
@@ -244,9 +248,10 @@ void mc_ctx_destroy(mc_ctx* c)
 	for (DBuf* b : bufs) b->release();
 	for (DBuf& b : c->d_vc) b.release();
 	for (DBuf& b : c->d_sam) b.release();
+	c->d_chrom_names.release(); c->d_chrom_name_off.release(); c->h_sam_text.release();
 	std::vector<Staged*> st; st.push_back(&c->cur); for (int i = 0; i < MC_SLOTS; i++) st.push_back(&c->slots[i]);
-	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); s->flag.release(); }
-	DBuf* fq[] = {&c->fq_text[0], &c->fq_text[1], &c->fq_cnt[0], &c->fq_cnt[1], &c->fq_off[0], &c->fq_off[1], &c->fq_lines[0], &c->fq_lines[1], &c->fq_scan, &c->fq_rlen, &c->fq_rsrc};
+	for (Staged* s : st) { s->seq.release(); s->roff.release(); s->seed_off.release(); s->cap.release(); s->scan.release(); s->flag.release(); for (int f = 0; f < 2; f++) { s->text[f].release(); s->lines[f].release(); } }
+	DBuf* fq[] = {&c->fq_cnt[0], &c->fq_cnt[1], &c->fq_off[0], &c->fq_off[1], &c->fq_scan, &c->fq_rlen, &c->fq_rsrc};
 	for (DBuf* b : fq) b->release();
 	HBuf* hb[] = {&c->h_in_seq, &c->h_in_off, &c->h_seed_off, &c->h_small, &c->h_chunk, &c->h_chunk_lo, &c->h_chunk_hi, &c->h_pairs, &c->h_reads, &c->h_cands, &c->h_frags, &c->h_aln, &c->h_misc, &c->h_disc};
 	for (HBuf* b : hb) b->release();
@@ -258,7 +263,8 @@ void mc_ctx_destroy(mc_ctx* c)
 	c->h_bounce[0].release(); c->h_bounce[1].release();
 #ifndef MC_HOSTEMU
 	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]); for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev_piece[i]);
-	for (int i = 0; i < MC_SLOTS; i++) cudaEventDestroy(c->ev_slot[i]);
+	for (int i = 0; i < MC_SLOTS; i++) { cudaEventDestroy(c->ev_slot[i]); cudaEventDestroy(c->ev_text[i]); }
+	if (c->dstream) cudaStreamDestroy(c->dstream);
 	if (c->cstream) cudaStreamDestroy(c->cstream);
 	if (c->stream) cudaStreamDestroy(c->stream);
 #endif
@@ -273,6 +279,7 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	if (mc_index_get(idx, &v)) return MC_ERR_ARG;
 	mc_ctx* c = new mc_ctx();
 	c->prm = *params; memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = 1000; zero_stats(&c->stats);
+	for (int i = 0; i < v.n_chrom; i++) c->chrom_names.push_back(v.chrom_name && v.chrom_name[i] ? v.chrom_name[i] : "*");
 #ifndef MC_HOSTEMU
 	int ndev = 0;
 	if (cuda_fail(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev <= params->device)
@@ -283,14 +290,15 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	if (cuda_fail(cudaSetDevice(params->device), "cudaSetDevice")) { delete c; return MC_ERR_CUDA; }
 	if (cuda_fail(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
 	if (cuda_fail(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
+	if (cuda_fail(cudaStreamCreateWithFlags(&c->dstream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
 #else
-	c->stream = 0; c->cstream = 0;
+	c->stream = 0; c->cstream = 0; c->dstream = 0;
 #endif
 	for (int i = 0; i < EV_COUNT; i++) ev_create(&c->ev[i]);
 #ifndef MC_HOSTEMU
 	cudaEventCreateWithFlags(&c->ev_bounce[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bounce[1], cudaEventDisableTiming);
 	for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&c->ev_piece[i], cudaEventDisableTiming);
-	for (int i = 0; i < MC_SLOTS; i++) cudaEventCreateWithFlags(&c->ev_slot[i], cudaEventDisableTiming);
+	for (int i = 0; i < MC_SLOTS; i++) { cudaEventCreateWithFlags(&c->ev_slot[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_text[i], cudaEventDisableTiming); }
 #endif
 	const int64_t G = v.genome_size; c->G = G;
 	std::vector<int64_t> ends; std::vector<int32_t> ids;
@@ -1037,6 +1045,30 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	}
 }
 
+// EvaluateMAPQ (src/SamReport.cpp:86-101) mixes float and double arithmetic with log(): tabulated with the host's libm for
+// the only cases that reach the formula (score - sub_score = 1..5), so the device needs no transcendental
+static int sam_mapq_table(mc_ctx* c, DBuf& d_tab, mc_stream_t s)
+{
+	if (d_tab.cap) return 0;
+	std::vector<uint8_t> tab((size_t)5 * (MC_MAX_RLEN + 1), 0);
+	for (int d = 1; d <= 5; d++)
+		for (int score = d; score <= MC_MAX_RLEN; score++)
+		{
+			int mapq = (int)(30 * (1 - (float)d / score) * log(score) + 0.4999);
+			if (mapq > 60) mapq = 60;
+			tab[(size_t)(d - 1) * (MC_MAX_RLEN + 1) + score] = (uint8_t)mapq;
+		}
+	return d_tab.reserve(tab.size()) || dev_h2d(d_tab.p, tab.data(), tab.size(), s) || dev_sync(s);
+}
+static void sam_args_of(mc_ctx* c, SamArgs& a, int64_t n, DBuf& d_tab)
+{
+	memset(&a, 0, sizeof(a));
+	a.ix = c->ix; a.paired = c->prm.paired; a.n_reads = n; a.roff = c->last_roff;
+	a.cand_off = c->d_cand_off.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.cscore = c->d_cscore.as<int32_t>(); a.cpaired = c->d_cpaired.as<int32_t>();
+	a.corient = c->d_corient.as<int32_t>(); a.cfrag = c->d_cfrag.as<int32_t>(); a.cnfrag = c->d_cnfrag.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
+	a.frags = c->d_frags.as<mc_frag_out>(); a.aln = c->d_aln.as<uint8_t>(); a.mapq_tab = d_tab.as<uint8_t>();
+}
+
 extern "C" {
 
 int mc_map_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
@@ -1107,13 +1139,17 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	const mc_stream_t s = c->cstream;   // the copy stream: another host thread may be mapping a different slot on c->stream
 	memset(out, 0, sizeof(*out));
 	Staged& st = c->slots[slot];
-	st.valid = false; st.pending = false; st.n_pieces = 0; st.h_roff.clear();
+	st.valid = false; st.pending = false; st.n_pieces = 0; st.h_roff.clear(); st.has_text = false;
 	const int nf = in->text2 ? 2 : 1;
+	st.n_files = nf;
+#ifndef MC_HOSTEMU
+	if (st.prefetched && cuda_fail(cudaStreamWaitEvent(s, c->ev_text[slot], 0), "cudaStreamWaitEvent")) return MC_ERR_CUDA;   // the copy queued by mc_ingest_prefetch
+#endif
 	const uint8_t* text[2] = {in->text1, in->text2}; const int64_t len[2] = {in->len1, in->text2 ? in->len2 : 0};
 	FastqArgs q; memset(&q, 0, sizeof(q));
-	DBuf* d_text = c->fq_text; DBuf* d_cnt = c->fq_cnt; DBuf* d_off = c->fq_off; DBuf* d_lines = c->fq_lines;
+	DBuf* d_text = st.text; DBuf* d_cnt = c->fq_cnt; DBuf* d_off = c->fq_off; DBuf* d_lines = st.lines;
 	DBuf& d_scan = c->fq_scan; DBuf& d_rlen = c->fq_rlen; DBuf& d_rsrc = c->fq_rsrc;   // kept between calls: no allocation in the steady state
-	auto done = [&](int rc) { return rc; };
+	auto done = [&](int rc) { st.prefetched = false; return rc; };
 	int bad = 0;
 	int64_t n_tiles[2] = {0, 0}, n_lines[2] = {0, 0}; bool open_end[2] = {false, false};
 	if (st.flag.reserve(16) || dev_zero(st.flag.p, 16, s)) return done(MC_ERR_CUDA);
@@ -1122,7 +1158,7 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 		n_tiles[f] = (len[f] + MC_FQ_TILE - 1) / MC_FQ_TILE;
 		bad |= d_text[f].reserve(len[f] + 2 * MC_FQ_TILE) || d_cnt[f].reserve((n_tiles[f] + 1) * 4) || d_off[f].reserve((n_tiles[f] + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(n_tiles[f] + 1));
 		if (bad) return done(MC_ERR_CUDA);
-		bad |= upload(c, d_text[f].p, text[f], (size_t)len[f], s);
+		if (!(st.prefetched && st.pre_src[f] == (const void*)text[f] && st.pre_len[f] == len[f])) bad |= upload(c, d_text[f].p, text[f], (size_t)len[f], s);
 		q.text[f] = d_text[f].as<uint8_t>(); q.len[f] = len[f]; q.tile_cnt[f] = d_cnt[f].as<uint32_t>(); q.tile_off[f] = d_off[f].as<int64_t>();
 		launch_fqcount(q, f, n_tiles[f], s);
 		device_scan_u32(q.tile_cnt[f], d_off[f].as<int64_t>(), n_tiles[f], d_scan.as<int64_t>(), s);
@@ -1193,8 +1229,70 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	bad |= dev_d2h(&flag, st.flag.p, 8, s);
 	if (bad || dev_sync(s)) return done(MC_ERR_CUDA);
 	if (flag) { mc_set_error("mc_ingest_fastq: a record has an empty read or one longer than %d bases", MC_MAX_RLEN); return done(MC_ERR_ARG); }
-	st.valid = true;
+	st.valid = true; st.has_text = true;
 	return done(MC_OK);
+}
+
+// Queues the host -> device copy of the FASTQ blocks the next mc_ingest_fastq(slot) is going to parse and returns: plain DMA
+// on a stream of its own, so the PCIe link stays busy while an earlier block is parsed and a still earlier one is mapped.
+int mc_ingest_prefetch(mc_ctx* c, const mc_fastq_in* in, int32_t slot)
+{
+	if (!c || !in || slot < 0 || slot >= MC_SLOTS || !in->text1 || in->len1 < 0 || (in->text2 && in->len2 < 0)) { mc_set_error("mc_ingest_prefetch: bad argument"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	Staged& st = c->slots[slot];
+	st.valid = false; st.has_text = false; st.prefetched = false;
+	const uint8_t* text[2] = {in->text1, in->text2}; const int64_t len[2] = {in->len1, in->text2 ? in->len2 : 0};
+	for (int f = 0; f < (in->text2 ? 2 : 1); f++)
+	{
+		if (st.text[f].reserve((size_t)len[f] + 2 * MC_FQ_TILE) || upload(c, st.text[f].p, text[f], (size_t)len[f], c->dstream)) return MC_ERR_CUDA;
+		st.pre_src[f] = text[f]; st.pre_len[f] = len[f];
+	}
+#ifndef MC_HOSTEMU
+	if (cuda_fail(cudaEventRecord(c->ev_text[slot], c->dstream), "cudaEventRecord")) return MC_ERR_CUDA;
+#endif
+	st.prefetched = true;
+	return MC_OK;
+}
+
+// SAM text of the batch just mapped from `slot` (reference src/SamReport.cpp:324-488), assembled on the device from the
+// batch's arenas and the FASTQ text mc_ingest_fastq left in the slot.  See include/mapcaller_b200.h.
+int mc_sam_text(mc_ctx* c, int32_t slot, int32_t all_best, const uint8_t** text, int64_t* n_bytes)
+{
+	if (!c || !text || !n_bytes || slot < 0 || slot >= MC_SLOTS) { mc_set_error("mc_sam_text: bad argument"); return MC_ERR_ARG; }
+	Staged& st = c->slots[slot];
+	if (!st.has_text || c->last_n <= 0 || c->last_roff != st.roff.as<int64_t>()) { mc_set_error("mc_sam_text: slot %d does not hold the FASTQ text of the batch just mapped (mc_ingest_fastq + mc_map_staged)", slot); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	const int64_t n = c->last_n; mc_stream_t s = c->stream;
+	DBuf &d_tab = c->d_sam[0], &d_len = c->d_sam[2], &d_off = c->d_sam[3], &d_txt = c->d_sam[4];
+	if (sam_mapq_table(c, d_tab, s)) return MC_ERR_CUDA;
+	if (c->d_chrom_names.cap == 0)
+	{
+		// chromosome names for the RNAME column: back to back, n_chrom + 1 offsets
+		std::vector<uint8_t> names; std::vector<int32_t> off(1, 0);
+		for (const std::string& nm : c->chrom_names) { names.insert(names.end(), nm.begin(), nm.end()); off.push_back((int32_t)names.size()); }
+		if (c->d_chrom_names.reserve(names.size() + 16) || c->d_chrom_name_off.reserve(off.size() * 4) || dev_h2d(c->d_chrom_names.p, names.data(), names.size(), s) || dev_h2d(c->d_chrom_name_off.p, off.data(), off.size() * 4, s) || dev_sync(s)) return MC_ERR_CUDA;
+	}
+	if (d_len.reserve((size_t)(n + 1) * 4) || d_off.reserve((size_t)(n + 2) * 8) || c->d_scan.reserve(device_scan_scratch_bytes(n))) return MC_ERR_CUDA;
+	SamTextArgs t; memset(&t, 0, sizeof(t));
+	sam_args_of(c, t.s, n, d_tab);
+	for (int f = 0; f < st.n_files; f++) { t.text[f] = st.text[f].as<uint8_t>(); t.line_end[f] = st.lines[f].as<int64_t>() + 1; }
+	t.two_files = st.n_files == 2; t.unique = all_best ? 0 : 1;
+	t.chrom_names = c->d_chrom_names.as<uint8_t>(); t.chrom_name_off = c->d_chrom_name_off.as<int32_t>();
+	t.tlen = d_len.as<uint32_t>(); t.toff = d_off.as<int64_t>();
+	launch_samtext(t, n, false, s);
+	device_scan_u32(t.tlen, d_off.as<int64_t>(), n, c->d_scan.as<int64_t>(), s);
+	int64_t total = 0;
+	if (dev_d2h(&total, d_off.as<int64_t>() + n, 8, s) || dev_sync(s)) return MC_ERR_CUDA;
+	if (d_txt.reserve((size_t)total + 16) || c->h_sam_text.reserve((size_t)total + 16)) return MC_ERR_CUDA;
+	t.out = d_txt.as<uint8_t>();
+	launch_samtext(t, n, true, s);
+	if (dev_d2h(c->h_sam_text.p, d_txt.p, (size_t)total, s) || dev_sync(s)) return MC_ERR_CUDA;
+	*text = c->h_sam_text.as<uint8_t>(); *n_bytes = total;
+	return MC_OK;
 }
 
 // packs the columns [beg, end) tile by tile; every tile is either copied to `outp` or reduced into the four counters `acc`
@@ -1352,23 +1450,9 @@ int mc_sam_records(mc_ctx* c, const mc_sam_rec** recs, int64_t* n_recs, const ui
 #endif
 	const int64_t n = c->last_n; mc_stream_t s = c->stream;
 	DBuf &d_tab = c->d_sam[0], &d_out = c->d_sam[1], &d_len = c->d_sam[2], &d_off = c->d_sam[3], &d_cig = c->d_sam[4];
-	// EvaluateMAPQ (src/SamReport.cpp:86-101) mixes float and double arithmetic with log(): tabulated here with the host's libm
-	// for the only cases that reach the formula (score - sub_score = 1..5), so the device needs no transcendental
-	std::vector<uint8_t> tab((size_t)5 * (MC_MAX_RLEN + 1), 0);
-	for (int d = 1; d <= 5; d++)
-		for (int score = d; score <= MC_MAX_RLEN; score++)
-		{
-			int mapq = (int)(30 * (1 - (float)d / score) * log(score) + 0.4999);
-			if (mapq > 60) mapq = 60;
-			tab[(size_t)(d - 1) * (MC_MAX_RLEN + 1) + score] = (uint8_t)mapq;
-		}
-	int bad = d_tab.reserve(tab.size()) || d_out.reserve((size_t)n * sizeof(mc_sam_rec)) || d_len.reserve((size_t)(n + 1) * 4) || d_off.reserve((size_t)(n + 2) * 8) || c->d_scan.reserve(device_scan_scratch_bytes(n));
-	if (bad || dev_h2d(d_tab.p, tab.data(), tab.size(), s)) return MC_ERR_CUDA;
-	SamArgs a; memset(&a, 0, sizeof(a));
-	a.ix = c->ix; a.paired = c->prm.paired; a.n_reads = n; a.roff = c->last_roff;
-	a.cand_off = c->d_cand_off.as<int32_t>(); a.ncand = c->d_ncand.as<int32_t>(); a.cscore = c->d_cscore.as<int32_t>(); a.cpaired = c->d_cpaired.as<int32_t>();
-	a.corient = c->d_corient.as<int32_t>(); a.cfrag = c->d_cfrag.as<int32_t>(); a.cnfrag = c->d_cnfrag.as<int32_t>(); a.rsum = c->d_rsum.as<ReadSum>();
-	a.frags = c->d_frags.as<mc_frag_out>(); a.aln = c->d_aln.as<uint8_t>(); a.mapq_tab = d_tab.as<uint8_t>();
+	int bad = sam_mapq_table(c, d_tab, s) || d_out.reserve((size_t)n * sizeof(mc_sam_rec)) || d_len.reserve((size_t)(n + 1) * 4) || d_off.reserve((size_t)(n + 2) * 8) || c->d_scan.reserve(device_scan_scratch_bytes(n));
+	if (bad) return MC_ERR_CUDA;
+	SamArgs a; sam_args_of(c, a, n, d_tab);
 	a.out = d_out.as<mc_sam_rec>(); a.clen = d_len.as<uint32_t>(); a.coff = d_off.as<int64_t>();
 	launch_samrec(a, n, false, s);
 	device_scan_u32(a.clen, d_off.as<int64_t>(), n, c->d_scan.as<int64_t>(), s);

@@ -53,6 +53,7 @@ static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for 
 static void launch_vcdepth(const VcArgs& a, int64_t b0, int64_t b1, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcdepth_body(b, a); }
 static void launch_vcscan(const VcArgs& a, int64_t b0, int64_t b1, bool emit, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcscan_body(b, a, emit); }
 static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t) { for (int64_t r = 0; r < n; r++) samrec_body(r, a, emit); }
+static void launch_samtext(const SamTextArgs& t, int64_t n, bool emit, mc_stream_t) { for (int64_t r = 0; r < n; r++) samtext_body(r, t, emit); }
 static void device_incmax_i64(int64_t* a, int64_t n, void*, mc_stream_t) { for (int64_t i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, void*, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
 static int64_t g_launches = 0;
@@ -316,6 +317,10 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_samrec_kernel(const SamArgs a, in
 { int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (r < n) samrec_body(r, a, emit); }
 static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t s)
 { if (n > 0) { mc_samrec_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, n, emit); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_samtext_kernel(const SamTextArgs t, int64_t n, bool emit)
+{ int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (r < n) samtext_body(r, t, emit); }
+static void launch_samtext(const SamTextArgs& t, int64_t n, bool emit, mc_stream_t s)
+{ if (n > 0) { mc_samtext_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(t, n, emit); g_launches++; } }
 static void device_incmax_i64(int64_t* a, int64_t n, void* scratch, mc_stream_t s)
 { if (n > 0) { device_lookback_scan<int64_t, ScanMax, true>(a, a, n, scratch, nullptr, s); g_launches++; } }
 #include <cub/device/device_radix_sort.cuh>

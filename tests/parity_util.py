@@ -198,8 +198,8 @@ def _write_inputs(case, td):
     return fa, f1, (f2 if paired else None)
 
 
-def sam_lines_reference(case, td):
-    """SAM records (bytes, in file order, header lines dropped) of the unmodified reference CLI, -t 1."""
+def sam_lines_reference(case, td, all_best: bool = False):
+    """SAM records (bytes, in file order, header lines dropped) of the unmodified reference CLI, -t 1 (all_best: with -m)."""
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "MapCaller")
     fa, f1, f2 = _write_inputs(case, td)
     idx = os.path.join(td, "idx")
@@ -209,6 +209,8 @@ def sam_lines_reference(case, td):
     prm = case["params"]
     if prm.get("alg_ksw2"):
         cmd += ["-alg", "ksw2"]
+    if all_best:
+        cmd += ["-m"]
     assert prm.get("max_pos_diff", 30) == 30, "MaxPosDiff has no command-line switch"
     cmd += ["-dup", str(prm.get("max_dup", 5)), "-maxclip", str(prm.get("max_clip", 5)), "-maxmm", repr(float(prm.get("max_mismatch_rate", 0.05)))]
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=td)
@@ -240,6 +242,25 @@ def sam_lines_cuda(case, device: int = 0, batch_reads: int | None = None):
                 l = api.format_sam_line(recs[k], cigars[k], head, t[4 * i + 1], t[4 * i + 3], [x.encode() for x in names])
                 if l is not None:
                     lines.append(l)
+    return lines
+
+
+def sam_text_cuda(case, device: int = 0, batch_pairs: int | None = None, all_best: bool = False):
+    """The SAM lines assembled on the device (mc_sam_text) from FASTQ text ingested on the device, batch by batch."""
+    from mapcaller_b200 import api
+    paired = bool(case["params"]["paired"])
+    r1, r2 = case["r1"], case["r2"]
+    n = len(r1)
+    batch_pairs = batch_pairs or n
+    lines = []
+    with api.Context(build_index(case), want_alignments=0, update_profile=0, device=device, **case["params"]) as ctx:
+        for b in range(0, n, batch_pairs):
+            e = min(n, b + batch_pairs)
+            t1 = sim.fastq_text(r1[b:e], 1, "r", first=b)
+            t2 = sim.fastq_text(r2[b:e], 2, "r", first=b) if paired else None
+            ctx.ingest_fastq(t1, t2, slot=1, final=(e == n))
+            ctx.map_staged(1)
+            lines += [l for l in ctx.sam_text(1, all_best).split(b"\n") if l]
     return lines
 
 

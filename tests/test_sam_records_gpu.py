@@ -88,3 +88,46 @@ def test_sam_record_properties_at_ecoli_size(built):
     a, b = recs[0::2], recs[1::2]
     both = (a["has_mate"] == 1) & (b["has_mate"] == 1) & (a["mate_pos"] == b["pos"]) & (b["mate_pos"] == a["pos"])
     assert both.mean() > 0.8 and (a["tlen"][both] == -b["tlen"][both]).all()
+
+
+# ---- mc_sam_text: the whole SAM line assembled on the device from the FASTQ text mc_ingest_fastq left in HBM -------------
+@pytest.mark.parametrize("name", ("pe_nw", "pe_ksw2", "se_nw", "pe_multi"))
+def test_device_sam_text_equals_the_golden_fixture(built, name):
+    case = gu.with_mates(gu.load(name)[0])
+    mine = pu.sam_comparable(pu.sam_text_cuda(case), bool(case["params"]["paired"]))
+    assert mine == gu.load_sam(name)
+
+
+TEXT_CASES = dict(CASES, pe_lower_case_n=dict(seed=15, n_pairs=3000, genome_len=60000, lower_rate=0.3, n_rate=0.01),
+                  pe_all_best=dict(seed=9, n_pairs=4000, genome_len=60000, n_dup=40, tandem=10),
+                  se_all_best=dict(seed=10, n_pairs=4000, genome_len=60000, n_dup=40, tandem=10, paired=0))
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(TEXT_CASES))
+def test_device_sam_text_equals_the_reference_cli(built, tmp_path, name):
+    """QNAME / SEQ / QUAL come from the FASTQ text in the slot (reverse-complemented / reversed on the reverse strand, mate 2
+    folded as ReverseOrientation + GetComplementarySeq do); *_all_best = the reference's -m (one line per best candidate)."""
+    case = pu.make_case(**TEXT_CASES[name])
+    paired = bool(case["params"]["paired"]); all_best = name.endswith("all_best")
+    mine = pu.sam_comparable(pu.sam_text_cuda(case, batch_pairs=2000 if name == "pe_repeats" else None, all_best=all_best), paired)
+    ref = pu.sam_comparable(pu.sam_lines_reference(case, str(tmp_path), all_best=all_best), paired)
+    if all_best and not paired:
+        # single-end -m: SetSingledAlignmentFlag (src/SamReport.cpp:7-24) only initialises the flag of the first best candidate
+        # and the lines of the others print an uninitialised SamFlag - every column but FLAG is compared
+        strip = lambda ls: [b"\t".join(l.split(b"\t")[:1] + l.split(b"\t")[2:]) for l in ls]
+        mine, ref = strip(mine), strip(ref)
+    assert len(mine) == len(ref) > 1000
+    bad = [k for k, (a, b) in enumerate(zip(mine, ref)) if a != b]
+    assert not bad, "%d SAM lines differ, first:\n%r\n%r" % (len(bad), mine[bad[0]], ref[bad[0]])
+    if all_best:
+        assert len(ref) > (2 if paired else 1) * len(case["r1"])      # some reads have several best candidates
+
+
+def test_device_sam_text_needs_the_fastq_text(built):
+    from mapcaller_b200 import api
+    case = pu.make_case(seed=3, n_pairs=200, genome_len=20000)
+    with api.Context(pu.build_index(case), **case["params"]) as ctx:
+        ctx.stage_batch(case["seq"], case["off"], 0); ctx.map_staged(0)
+        with pytest.raises(api.McError):
+            ctx.sam_text(0)
