@@ -822,7 +822,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			if ((ovf >> 40) & 0xFF) { mc_set_error("mc_map_batch: internal error: candidate table overflow"); return MC_ERR_OVERFLOW; }
 			if (c->frag_factor > 4096 || c->aln_factor > 4096 || c->task_factor > 4096 || c->dpws_factor > 65536) { mc_set_error("mc_map_batch: arena overflow persists"); return MC_ERR_OVERFLOW; }
 			if (getenv("MC_DEBUG")) fprintf(stderr, "[mc] arena overflow %llx: now frag x%.0f aln x%.0f task x%.0f dpws x%.0f rescue %lld\n", (unsigned long long)ovf, c->frag_factor, c->aln_factor, c->task_factor, c->dpws_factor, (long long)c->rescue_cap);
-			bad |= dev_zero(&c->d_stats.as<DevStats>()->locate_blocks, sizeof(DevStats) - sizeof(mc_u64), s); // keep only the seeding counter
+			bad |= dev_zero(&c->d_stats.as<DevStats>()->locate_blocks, sizeof(DevStats) - 3 * sizeof(mc_u64), s); // keep only the seed kernel's counters
 			continue;
 		}
 		ev_record(&c->ev[EV_ALN1], s);
@@ -1008,7 +1008,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		c->stats.ms_profile += ev_ms(&c->ev[EV_PROF0], &c->ev[EV_PROF1]);
 		c->stats.ms_d2h += ev_ms(&c->ev[EV_PROF1], &c->ev[EV_D2H]);
 		c->stats.ms_total += ev_ms(&c->ev[EV_START], &c->ev[EV_D2H]);
-		c->stats.seed_blocks += hst->seed_blocks; c->stats.locate_blocks += hst->locate_blocks; c->stats.sa_reads += hst->sa_reads;
+		c->stats.seed_blocks += hst->seed_blocks; c->stats.locate_blocks += hst->locate_blocks + hst->seed_locate_blocks; c->stats.sa_reads += hst->sa_reads + hst->seed_sa_reads;
 		c->stats.dp_cells += hst->dp_cells; c->stats.dp_tasks += hst->dp_tasks; c->stats.profile_columns += hst->profile_columns; c->stats.profile_atomics += hst->profile_atomics;
 		c->dstats_last = *hst;
 

@@ -237,7 +237,8 @@ struct Cand { int32_t score; int32_t pbeg; int32_t pend; };              // clus
 struct DpTask { int32_t frag; int32_t m; int32_t n; int32_t pad; int64_t ws_off; };
 
 struct DevStats {
-	mc_u64 seed_blocks, locate_blocks, sa_reads, dp_cells, dp_tasks, profile_columns, profile_atomics;
+	mc_u64 seed_blocks, seed_locate_blocks, seed_sa_reads;   // written by the seed kernel only (kept when the later stages are repeated with larger arenas)
+	mc_u64 locate_blocks, sa_reads, dp_cells, dp_tasks, profile_columns, profile_atomics;
 	mc_u64 overflow;      // any arena ran out: the batch is re-run with larger arenas
 	mc_u64 odd_merge;     // defensive counter: IdentifyNormalPairs ordering assumption violated
 };

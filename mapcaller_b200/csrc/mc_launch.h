@@ -143,6 +143,7 @@ static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t
 	const int variant = forced ? forced : (a.ix.cbwt && a.ix.seq_len < (200ll << 20) ? 5 : 4);
 	const unsigned g = (unsigned)((n - first + MC_BLOCK - 1) / MC_BLOCK);
 	if (variant == 6) mc_seed_kernel<6><<<g, MC_BLOCK, 0, s>>>(a, first, n);
+	else if (variant == 3) mc_seed_kernel<3><<<g, MC_BLOCK, 0, s>>>(a, first, n);
 	else if (variant == 5) mc_seed_kernel<5><<<g, MC_BLOCK, 0, s>>>(a, first, n);
 	else mc_seed_kernel<4><<<g, MC_BLOCK, 0, s>>>(a, first, n);
 	g_launches++;

@@ -118,21 +118,61 @@ MC_HD void prep_body(int64_t r, int lane, int nl, const PipeArgs& a)
 // ------------------------------------------------------------------------------------------------
 // seeding: one thread walks one read left to right
 // ------------------------------------------------------------------------------------------------
-// read bases are fetched four at a time through an aligned 32-bit window (one load every fourth step instead of a byte
-// load per step: every load of this kernel costs a full L1TEX wavefront per lane)
-struct BaseWindow { const uint32_t* w; uint32_t cur; int have; int shift0; };
+// read bases are fetched eight at a time through an aligned 64-bit window, and the following eight are requested as soon as
+// a window is entered: the search only moves forward, so the next window is there when the walk reaches it (waiting for a
+// read's own bases was 13 % of the stall samples of this kernel)
+struct BaseWindow { const uint64_t* w; uint64_t cur, nxt; int have; int shift0; };
+MC_HD void base_window_init(BaseWindow& bw, const uint8_t* s)
+{
+	bw.shift0 = (int)((uintptr_t)s & 7); bw.w = (const uint64_t*)(s - bw.shift0); bw.have = 0;
+	bw.cur = mc_ldg(bw.w); bw.nxt = mc_ldg(bw.w + 1);     // the read arena is padded: a window past the last read stays inside it
+}
 MC_HD uint8_t base_at(const uint8_t* s, int p, BaseWindow& bw)
 {
 	const int q = p + bw.shift0;            // byte offset from the aligned base
-	const int word = q >> 2;
-	if (word != bw.have) { bw.cur = mc_ldg(bw.w + word); bw.have = word; }
-	return (uint8_t)(bw.cur >> ((q & 3) << 3));
+	const int word = q >> 3;
+	if (word != bw.have)
+	{
+		if (word == bw.have + 1) bw.cur = bw.nxt; else bw.cur = mc_ldg(bw.w + word);
+		bw.have = word; bw.nxt = mc_ldg(bw.w + word + 1);
+	}
+	return (uint8_t)(bw.cur >> ((q & 7) << 3));
+}
+// 2-bit codes of the text (forward strand then its reverse complement, mc_ref_code) through a 16-base window of the packed reference
+struct TextWindow { int64_t have; uint32_t cur; };
+MC_HD int text_code_at(const DevIndex& ix, int64_t j, TextWindow& tw)
+{
+	const bool fwd = j < ix.G;
+	const int64_t pp = fwd ? j : ix.twoG - 1 - j;
+	const int64_t wi = pp >> 4;
+	if (wi != tw.have) { tw.cur = mc_ldg((const uint32_t*)ix.pac + wi); tw.have = wi; }
+	const uint32_t byte = (tw.cur >> (((uint32_t)(pp >> 2) & 3u) << 3)) & 0xFFu;
+	const int c = (int)((byte >> ((~(uint32_t)pp & 3u) << 1)) & 3u);
+	return fwd ? c : 3 - c;
 }
 
 template <class Interval> struct SeedOps;
 template <> struct SeedOps<RcInterval> { static MC_HD RcInterval init(const DevIndex& ix, int c) { return mc_interval_init(ix, c); } };
 template <> struct SeedOps<RcInterval32> { static MC_HD RcInterval32 init(const DevIndex& ix, int c) { return mc_interval_init32(ix, c); } };
 
+#define MC_SEED_LOCATED (1ull << 63)   // Seed::x0 of a seed whose single occurrence is already known: the text position, not a BWT row
+#define MC_SEED_TEXT_STEP 8            // bases compared per trip once a seed is down to one occurrence
+
+// One thread walks one read left to right through the reference's greedy scheme (IdentifySimplePairs + BWT_Search,
+// src/ReadMapping.cpp:125-158, src/bwt_search.cpp:121-151): from `pos`, extend while the pattern occurs; record it when it is
+// >= 16 bases and occurs <= 50 times; continue one base behind where it stopped.
+// A seed goes through up to four phases, one load per trip of the flat loop each:
+//   start    the first k bases from the k-mer table (mc_fmindex.h), or a single base when the table cannot answer
+//   step     one backward-search step on the reverse-complement interval per base - while the pattern occurs more than once
+//   locate   the moment ONE occurrence is left (after ~15 bases in a 500 M-symbol text) its text position is looked up once:
+//            LF steps to the next sampled row (3 on average with the sample kept in HBM)
+//   compare  from then on extending the pattern is comparing the read with the packed reference text itself - sequential,
+//            cached, eight bases per trip - instead of one random index block per base.  The search stops exactly where
+//            the reference's does: a single row can only be extended by the base that precedes its suffix in the text.
+// A seed that ends in the compare phase already knows its position (Seed::x0 = MC_SEED_LOCATED | position), so the locate
+// kernel has nothing to walk for it.  The work counter `seed_blocks` stays the reference algorithm's: the table carries
+// the block count of the steps it replaces and every compared base is charged the one block its step reads in the
+// reference (an interval of one row straddles two blocks once in 128 steps: that 0.8 % is not counted).
 template <class Interval> MC_HD void seed_walk(int64_t r, const PipeArgs& a)
 {
 	const uint8_t* s = a.seq + a.roff[r];
@@ -140,17 +180,22 @@ template <class Interval> MC_HD void seed_walk(int64_t r, const PipeArgs& a)
 	const int64_t so = a.seed_off[r];
 	const int cap = (int)(a.seed_off[r + 1] - so);
 	const int stop = rlen - MC_MIN_SEED;
-	BaseWindow bw; bw.shift0 = (int)((uintptr_t)s & 3); bw.w = (const uint32_t*)(s - bw.shift0); bw.have = -1; bw.cur = 0;
+	BaseWindow bw; base_window_init(bw, s);
+	TextWindow tw; tw.have = -1; tw.cur = 0;
 	int ns = 0, pos = 0, p = 0;
 	uint32_t lower = 0;
-	bool in_seed = false;
-	uint32_t nblk = 0;
+	int mode = 0;                 // 0 between seeds, 1 stepping, 2 locating, 3 comparing
+	uint32_t nblk = 0, nloc = 0, nsa = 0;
 	Interval v; v.x1 = v.x2 = 0;
-	// One loop, one extension step per trip: lanes of a warp stay in lock step whatever their seed boundaries are
+	uint64_t lk = 0, lsteps = 0;  // locate phase: current row, steps taken
+	int64_t tq = 0;               // compare phase: where the reverse complement of read[pos, p) lies in the text
+	const bool direct = a.ix.sa_shift < 5;   // the denser suffix-array sample is there (mc_ctx_create)
+	// One loop, one load per trip: lanes of a warp stay in lock step whatever their seed boundaries and phases are
 	// (the nested search-inside-scan loops of the reference serialise lanes whose seeds end at different offsets).
 	for (;;)
 	{
-		if (!in_seed)
+		bool end = false;
+		if (mode == 0)
 		{
 			if (pos >= stop) break;
 			const uint8_t ch = base_at(s, pos, bw);
@@ -163,31 +208,55 @@ template <class Interval> MC_HD void seed_walk(int64_t r, const PipeArgs& a)
 				const int K = a.ix.ktab_k;
 				uint32_t m = (uint32_t)c, low = ch; bool clean = true;
 				for (int j = 1; j < K; j++) { const uint8_t cj = base_at(s, pos + j, bw); const int x = mc_nt4(cj); clean = clean && x <= 3; m = (m << 2) | (uint32_t)(x & 3); low |= cj; }
-				if (clean && KtabOps<Interval>::lookup(a.ix, m, v, &nblk)) { lower |= low; p = pos + K; in_seed = true; }
+				if (clean && KtabOps<Interval>::lookup(a.ix, m, v, &nblk)) { lower |= low; p = pos + K; mode = 1; }
 			}
-			if (!in_seed) { lower |= ch; v = SeedOps<Interval>::init(a.ix, c); p = pos + 1; in_seed = true; }
+			if (mode == 0) { lower |= ch; v = SeedOps<Interval>::init(a.ix, c); p = pos + 1; mode = 1; }
+			if (direct && v.x2 == 1) { mode = 2; lk = (uint64_t)v.x1; lsteps = 0; }
 		}
-		bool end = p >= rlen;
-		if (!end)
+		else if (mode == 1)
 		{
-			const uint8_t ch = base_at(s, p, bw);
-			const int cc = mc_nt4(ch);
-			end = cc > 3 || !mc_interval_extend(a.ix, v, cc, &nblk);
-			if (!end) { p++; lower |= ch; }
+			end = p >= rlen;
+			if (!end)
+			{
+				const uint8_t ch = base_at(s, p, bw);
+				const int cc = mc_nt4(ch);
+				end = cc > 3 || !mc_interval_extend(a.ix, v, cc, &nblk);
+				if (!end) { p++; lower |= ch; if (direct && v.x2 == 1 && p < rlen) { mode = 2; lk = (uint64_t)v.x1; lsteps = 0; } }
+			}
+		}
+		else if (mode == 2)
+		{
+			if (mc_sa_sampled(a.ix, lk)) { tq = (int64_t)mc_sa_value(a.ix, lk, lsteps); mode = 3; }
+			else { lk = mc_lf_step(a.ix, lk); lsteps++; nloc++; }
+		}
+		else
+		{
+			for (int t = 0; t < MC_SEED_TEXT_STEP; t++)
+			{
+				if (p >= rlen) { end = true; break; }
+				const uint8_t ch = base_at(s, p, bw);
+				const int cc = mc_nt4(ch);
+				if (cc > 3) { end = true; break; }
+				nblk++;                                            // the block this step reads in the reference
+				if (tq <= 0 || text_code_at(a.ix, tq - 1, tw) != 3 - cc) { end = true; break; }
+				p++; tq--; lower |= ch;
+			}
 		}
 		if (end)
 		{
 			const int len = p - pos;
 			if (len >= MC_MIN_SEED && v.x2 <= MC_MAX_OCC && ns < cap)
 			{
-				Seed sd; sd.x0 = v.x1; sd.read = (int32_t)r; sd.rpos = (int16_t)pos; sd.len = (int16_t)len;
+				Seed sd; sd.x0 = mode == 3 ? (MC_SEED_LOCATED | (uint64_t)tq) : (uint64_t)v.x1; sd.read = (int32_t)r; sd.rpos = (int16_t)pos; sd.len = (int16_t)len;
 				a.seeds[so + ns] = sd; a.slot_freq[so + ns] = (uint32_t)v.x2; ns++;
+				if (mode == 3) nsa++;
 			}
-			pos = p + 1; in_seed = false;
+			pos = p + 1; mode = 0;
 		}
 	}
 	a.rflag[r] = (uint8_t)((lower >> 5) & 1);
 	if (nblk) mc_stat_add(&a.st->seed_blocks, (uint32_t)(nblk));
+	if (direct) { mc_stat_add(&a.st->seed_locate_blocks, nloc); mc_stat_add(&a.st->seed_sa_reads, nsa); }
 }
 MC_HD void seed_body(int64_t r, const PipeArgs& a)
 {
@@ -319,21 +388,22 @@ MC_HD void locate_body(int64_t tid, int64_t nthreads, const PipeArgs& a)
 	bool live = true;
 	while (live)
 	{
-		const bool at = mc_sa_sampled(a.ix, k);
+		const bool known = (k & MC_SEED_LOCATED) != 0;   // the seed kernel already compared this seed against the text (seed_walk)
+		const bool at = known || mc_sa_sampled(a.ix, k);
 		if (at)
 		{
 			// the seed carries the rows of its reverse complement: an occurrence of that at q is the seed at 2G - q - len
-			const uint64_t q = mc_sa_value(a.ix, k, steps);
+			const uint64_t q = known ? (k & ~MC_SEED_LOCATED) : mc_sa_value(a.ix, k, steps);
 			const int64_t g = (int64_t)((uint64_t)a.ix.twoG - q - (uint64_t)p.len);
 			p.gpos = g;
 			if (g - (int64_t)p.rpos <= 0) p.len = 0;                    // PosDiff <= 0 is dropped (src/ReadMapping.cpp:145)
 			a.pairs[t] = p;
-			nsa++;
+			if (!known) nsa++;
 			t += nthreads;
 			live = t < a.n_locs;
 			if (live) { p = a.pairs[t]; k = (uint64_t)p.gpos; steps = 0; }
 		}
-		if (live && !mc_sa_sampled(a.ix, k)) { k = mc_lf_step(a.ix, k); steps++; nblk++; }
+		if (live && !(k & MC_SEED_LOCATED) && !mc_sa_sampled(a.ix, k)) { k = mc_lf_step(a.ix, k); steps++; nblk++; }
 	}
 	mc_stat_add(&a.st->locate_blocks, (uint32_t)(nblk));
 	mc_stat_add(&a.st->sa_reads, (uint32_t)(nsa));

@@ -50,10 +50,13 @@ def test_cuda_matches_oracle(built, name):
     mine = pu.cuda_results(case, ix)
     orc = pu.oracle_results(case, ix)
     pu.assert_same(mine, orc, paired=bool(case["params"]["paired"]))
-    # the work counter the seed-kernel roofline is computed from is the oracle's, exactly.  The locate kernel meets a sampled
-    # row after 3 LF steps on average (every 4th row is sampled in HBM) where the reference needs 31
-    for k in ("seed_blocks", "sa_reads"):
-        assert mine["stats"][k] == orc["work"][k], k
+    # the work counter the seed-kernel roofline is computed from is the oracle's: exactly while a seed is searched step by
+    # step or through the k-mer table, and one block per compared base once a seed is down to a single occurrence (the
+    # reference reads two when the row straddles a block boundary, once in 128 steps - that share is not counted).
+    # The locate kernel meets a sampled row after 3 LF steps on average (every 4th row is sampled in HBM) where
+    # the reference needs 31
+    assert mine["stats"]["sa_reads"] == orc["work"]["sa_reads"]
+    assert 0.985 * orc["work"]["seed_blocks"] <= mine["stats"]["seed_blocks"] <= orc["work"]["seed_blocks"]
     assert abs(mine["stats"]["locate_blocks"] - 3 * orc["work"]["sa_reads"]) <= 0.15 * 3 * orc["work"]["sa_reads"] + 2000
     assert mine["stats"]["locate_blocks"] < orc["work"]["locate_blocks"]
 
