@@ -28,7 +28,7 @@ static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t)
 }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
 static void launch_prep(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { for (int64_t r = first | 1; r < n; r += 2) prep_body(r, 0, 1, a); }
-static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { for (int64_t r = first; r < n; r++) seed_body(r, a); }
+static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { seed_body(0, 1, first, n, a); }
 static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin; for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
 static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump; for (int64_t i = 0; i < n; i++) a.st->profile_atomics += profpiece_body(i, 0, 1, a, q); }
@@ -132,20 +132,19 @@ static void launch_prep(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t
 	if (!a.pr.paired || p1 <= p0) return;
 	mc_prep_kernel<<<(unsigned)(((p1 - p0) * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, p0, p1); g_launches++;
 }
+// persistent lanes (seed_walk): a fixed grid of MINB resident blocks per SM
 template <int MINB> __global__ void __launch_bounds__(MC_BLOCK, MINB) mc_seed_kernel(const PipeArgs a, int64_t first, int64_t n)
-{ const int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) seed_body(i, a); }
+{ seed_body(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, first, n, a); }
 static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t s)
 {
 	if (n <= first) return;
-	// an index that fits L2 leaves the kernel latency / issue bound: five resident blocks (48 registers, a few spills) beat four
-	// (1.41 vs 1.56 ms on the bench); from HBM the kernel is bandwidth bound and the spills only add traffic
 	static const int forced = getenv("MC_SEED_MINB") ? atoi(getenv("MC_SEED_MINB")) : 0;
-	const int variant = forced ? forced : (a.ix.cbwt && a.ix.seq_len < (200ll << 20) ? 5 : 4);
-	const unsigned g = (unsigned)((n - first + MC_BLOCK - 1) / MC_BLOCK);
-	if (variant == 6) mc_seed_kernel<6><<<g, MC_BLOCK, 0, s>>>(a, first, n);
-	else if (variant == 3) mc_seed_kernel<3><<<g, MC_BLOCK, 0, s>>>(a, first, n);
-	else if (variant == 5) mc_seed_kernel<5><<<g, MC_BLOCK, 0, s>>>(a, first, n);
-	else mc_seed_kernel<4><<<g, MC_BLOCK, 0, s>>>(a, first, n);
+	const int variant = forced ? forced : 4;
+	int64_t g = (n - first + MC_BLOCK - 1) / MC_BLOCK; if (g > 148 * variant) g = 148 * variant;
+	if (variant == 6) mc_seed_kernel<6><<<(unsigned)g, MC_BLOCK, 0, s>>>(a, first, n);
+	else if (variant == 3) mc_seed_kernel<3><<<(unsigned)g, MC_BLOCK, 0, s>>>(a, first, n);
+	else if (variant == 5) mc_seed_kernel<5><<<(unsigned)g, MC_BLOCK, 0, s>>>(a, first, n);
+	else mc_seed_kernel<4><<<(unsigned)g, MC_BLOCK, 0, s>>>(a, first, n);
 	g_launches++;
 }
 // rescue (mc_stages_pair.h): enumerate the windows of the attempt's rescue pairs, search them with persistent thread blocks

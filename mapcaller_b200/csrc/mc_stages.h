@@ -173,31 +173,46 @@ template <> struct SeedOps<RcInterval32> { static MC_HD RcInterval32 init(const 
 // kernel has nothing to walk for it.  The work counter `seed_blocks` stays the reference algorithm's: the table carries
 // the block count of the steps it replaces and every compared base is charged the one block its step reads in the
 // reference (an interval of one row straddles two blocks once in 128 steps: that 0.8 % is not counted).
-template <class Interval> MC_HD void seed_walk(int64_t r, const PipeArgs& a)
+// Lanes are persistent: lane `tid` of `nthreads` takes reads first + tid, first + tid + nthreads, ... and starts its next read in
+// the trip after it finished one.  A read that lies in a repeat family keeps stepping through the index for all of its bases
+// while a unique read is done after ~25 cheap trips; with one read per thread every warp would wait for its slowest read
+// (practically every warp of 32 holds one), with ~26 reads per lane the difference averages out.
+template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, int64_t first, int64_t n_end, const PipeArgs& a)
 {
-	const uint8_t* s = a.seq + a.roff[r];
-	const int rlen = (int)(a.roff[r + 1] - a.roff[r]);
-	const int64_t so = a.seed_off[r];
-	const int cap = (int)(a.seed_off[r + 1] - so);
-	const int stop = rlen - MC_MIN_SEED;
-	BaseWindow bw; base_window_init(bw, s);
+	int64_t r = first + tid;
+	if (r >= n_end) return;
+	const uint8_t* s = nullptr; int rlen = 0, cap = 0, stop = 0; int64_t so = 0;
+	BaseWindow bw; bw.w = nullptr; bw.cur = bw.nxt = 0; bw.have = 0; bw.shift0 = 0;
 	TextWindow tw; tw.have = -1; tw.cur = 0;
 	int ns = 0, pos = 0, p = 0;
 	uint32_t lower = 0;
-	int mode = 0;                 // 0 between seeds, 1 stepping, 2 locating, 3 comparing
+	int mode = -1;                // -1 read not yet opened, 0 between seeds, 1 stepping, 2 locating, 3 comparing
 	uint32_t nblk = 0, nloc = 0, nsa = 0;
 	Interval v; v.x1 = v.x2 = 0;
 	uint64_t lk = 0, lsteps = 0;  // locate phase: current row, steps taken
 	int64_t tq = 0;               // compare phase: where the reverse complement of read[pos, p) lies in the text
 	const bool direct = a.ix.sa_shift < 5;   // the denser suffix-array sample is there (mc_ctx_create)
-	// One loop, one load per trip: lanes of a warp stay in lock step whatever their seed boundaries and phases are
+	// One loop, one load per trip: lanes of a warp stay in lock step whatever their reads, seed boundaries and phases are
 	// (the nested search-inside-scan loops of the reference serialise lanes whose seeds end at different offsets).
 	for (;;)
 	{
 		bool end = false;
+		if (mode < 0)
+		{
+			s = a.seq + a.roff[r]; rlen = (int)(a.roff[r + 1] - a.roff[r]);
+			so = a.seed_off[r]; cap = (int)(a.seed_off[r + 1] - so); stop = rlen - MC_MIN_SEED;
+			base_window_init(bw, s);
+			ns = 0; pos = 0; p = 0; lower = 0; mode = 0;
+		}
 		if (mode == 0)
 		{
-			if (pos >= stop) break;
+			if (pos >= stop)
+			{
+				a.rflag[r] = (uint8_t)((lower >> 5) & 1);
+				r += nthreads;
+				if (r >= n_end) break;
+				mode = -1; continue;
+			}
 			const uint8_t ch = base_at(s, pos, bw);
 			const int c = mc_nt4(ch);
 			if (c > 3) { pos++; continue; }
@@ -254,13 +269,12 @@ template <class Interval> MC_HD void seed_walk(int64_t r, const PipeArgs& a)
 			pos = p + 1; mode = 0;
 		}
 	}
-	a.rflag[r] = (uint8_t)((lower >> 5) & 1);
 	if (nblk) mc_stat_add(&a.st->seed_blocks, (uint32_t)(nblk));
 	if (direct) { mc_stat_add(&a.st->seed_locate_blocks, nloc); mc_stat_add(&a.st->seed_sa_reads, nsa); }
 }
-MC_HD void seed_body(int64_t r, const PipeArgs& a)
+MC_HD void seed_body(int64_t tid, int64_t nthreads, int64_t first, int64_t n_end, const PipeArgs& a)
 {
-	if (a.ix.cbwt) seed_walk<RcInterval32>(r, a); else seed_walk<RcInterval>(r, a);
+	if (a.ix.cbwt) seed_walk<RcInterval32>(tid, nthreads, first, n_end, a); else seed_walk<RcInterval>(tid, nthreads, first, n_end, a);
 }
 
 // BWT_Search as an operator (reference src/bwt_search.cpp:121-164) for independent (codes, start) queries: the search loop of
