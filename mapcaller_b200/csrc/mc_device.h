@@ -29,6 +29,7 @@ template <class T> static inline T mc_atomic_add(T* p, T v) { T o = *p; *p = (T)
 template <class T> static inline void mc_atomic_or(T* p, T v) { *p = (T)(*p | v); }
 static inline int mc_atomic_exch(int* p, int v) { int o = *p; *p = v; return o; }
 static inline int mc_popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int mc_ctz(uint32_t x) { return __builtin_ctz(x); }
 #define MC_WARP_SYNC() do { } while (0)
 static inline int64_t mc_bcast64(int64_t v) { return v; }
 static inline int mc_warp_sum(int v) { return v; }
@@ -62,6 +63,7 @@ static __device__ __forceinline__ void mc_atomic_or(unsigned long long* p, unsig
 static __device__ __forceinline__ void mc_atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 static __device__ __forceinline__ int mc_atomic_exch(int* p, int v) { return atomicExch(p, v); }
 static __device__ __forceinline__ int mc_popc(uint32_t x) { return __popc(x); }
+static __device__ __forceinline__ int mc_ctz(uint32_t x) { return __ffs((int)x) - 1; }
 #define MC_WARP_SYNC() __syncwarp()
 static __device__ __forceinline__ int64_t mc_bcast64(int64_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 static __device__ __forceinline__ int mc_warp_sum(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }

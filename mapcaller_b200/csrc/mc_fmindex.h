@@ -302,21 +302,21 @@ template <> struct KtabOps<RcInterval> {
 		return true;
 	}
 };
-// entry m of the table: the k bases of m, most significant pair first, searched step by step (ix.ktab_k is still 0 here)
+// entry m of the table: the k bases of m, first base in the low bits (the order mc_pack8 delivers), searched step by step
 MC_HD void mc_ktab_build_body(int64_t m, const DevIndex& ix, int k, uint32_t* out32, uint64_t* out64)
 {
 	uint32_t nblk = 0; bool ok = true;
 	if (out32)
 	{
-		RcInterval32 v = mc_interval_init32(ix, (int)((m >> (2 * (k - 1))) & 3));
-		for (int j = k - 2; j >= 0 && ok; j--) ok = mc_interval_extend(ix, v, (int)((m >> (2 * j)) & 3), &nblk);
+		RcInterval32 v = mc_interval_init32(ix, (int)(m & 3));
+		for (int j = 1; j < k && ok; j++) ok = mc_interval_extend(ix, v, (int)((m >> (2 * j)) & 3), &nblk);
 		ok = ok && v.x2 > 0 && v.x2 < (1u << MC_KTAB_BITS32);
 		out32[2 * m] = ok ? v.x1 : 0u; out32[2 * m + 1] = ok ? (v.x2 | (nblk << MC_KTAB_BITS32)) : 0u;
 	}
 	else
 	{
-		RcInterval v = mc_interval_init(ix, (int)((m >> (2 * (k - 1))) & 3));
-		for (int j = k - 2; j >= 0 && ok; j--) ok = mc_interval_extend(ix, v, (int)((m >> (2 * j)) & 3), &nblk);
+		RcInterval v = mc_interval_init(ix, (int)(m & 3));
+		for (int j = 1; j < k && ok; j++) ok = mc_interval_extend(ix, v, (int)((m >> (2 * j)) & 3), &nblk);
 		ok = ok && v.x2 > 0 && v.x2 < (1ull << MC_KTAB_BITS64);
 		out64[2 * m] = ok ? v.x1 : 0ull; out64[2 * m + 1] = ok ? (v.x2 | ((uint64_t)nblk << MC_KTAB_BITS64)) : 0ull;
 	}

@@ -138,17 +138,50 @@ MC_HD uint8_t base_at(const uint8_t* s, int p, BaseWindow& bw)
 	}
 	return (uint8_t)(bw.cur >> ((q & 7) << 3));
 }
-// 2-bit codes of the text (forward strand then its reverse complement, mc_ref_code) through a 16-base window of the packed reference
-struct TextWindow { int64_t have; uint32_t cur; };
-MC_HD int text_code_at(const DevIndex& ix, int64_t j, TextWindow& tw)
+// the eight bytes of the read that start at base p (p lies in the current window: call base_at(s, p, bw) first)
+MC_HD uint64_t bases8_at(int p, const BaseWindow& bw)
 {
-	const bool fwd = j < ix.G;
-	const int64_t pp = fwd ? j : ix.twoG - 1 - j;
-	const int64_t wi = pp >> 4;
-	if (wi != tw.have) { tw.cur = mc_ldg((const uint32_t*)ix.pac + wi); tw.have = wi; }
-	const uint32_t byte = (tw.cur >> (((uint32_t)(pp >> 2) & 3u) << 3)) & 0xFFu;
-	const int c = (int)((byte >> ((~(uint32_t)pp & 3u) << 1)) & 3u);
-	return fwd ? c : 3 - c;
+	const int off = ((p + bw.shift0) & 7) << 3;
+	return off ? (bw.cur >> off) | (bw.nxt << (64 - off)) : bw.cur;
+}
+// eight ASCII bases -> sixteen bits of 2-bit codes (base i in bits 2i, 2i + 1; nst_nt4_table for ACGT / acgt); bit i of *bad is
+// set when byte i is anything else.  All on the packed word: no per-base loop.
+MC_HD uint32_t mc_pack8(uint64_t w, uint32_t* bad)
+{
+	const uint64_t u = w & 0xDFDFDFDFDFDFDFDFull, L7 = 0x7F7F7F7F7F7F7F7Full, H = 0x8080808080808080ull;
+	const uint64_t a = u ^ 0x4141414141414141ull, c = u ^ 0x4343434343434343ull, g = u ^ 0x4747474747474747ull, t = u ^ 0x5454545454545454ull;
+	// bit 7 of a byte of ~(((x & 0x7F) + 0x7F) | x) is set iff the byte is zero, exactly (no carries between bytes)
+	const uint64_t ok = (~(((a & L7) + L7) | a) | ~(((c & L7) + L7) | c) | ~(((g & L7) + L7) | g) | ~(((t & L7) + L7) | t)) & H;
+	*bad = (uint32_t)(((((ok ^ H) >> 7) * 0x0102040810204080ull) >> 56) & 0xFFu);
+	uint64_t x = ((w >> 1) ^ (w >> 2)) & 0x0303030303030303ull;
+	x = (x | (x >> 6)) & 0x000F000F000F000Full;
+	x = (x | (x >> 12)) & 0x000000FF000000FFull;
+	return (uint32_t)((x | (x >> 24)) & 0xFFFFu);
+}
+// four bytes of the packed reference (16 bases, the first one in the top bits of byte 0) -> base t in bits 2t, 2t + 1
+MC_HD uint32_t mc_pac_norm(uint32_t x) { return ((x & 0x03030303u) << 6) | ((x & 0x0C0C0C0Cu) << 2) | ((x >> 2) & 0x0C0C0C0Cu) | ((x >> 6) & 0x03030303u); }
+// The codes the next eight read bases must have for the pattern to keep occurring: E[i] = 3 - T[tq - 1 - i] in bits 2i, 2i + 1,
+// T = forward strand followed by its reverse complement.  *avail = how many of them this call can vouch for (the text may end
+// or change halves first).  tq >= 1.
+MC_HD uint32_t text_expect8(const DevIndex& ix, int64_t tq, int* avail)
+{
+	const uint32_t* pac32 = (const uint32_t*)ix.pac;
+	if (tq - 1 >= ix.G)
+	{
+		// reverse-complement half: T[j] = 3 - F[2G - 1 - j], so E[i] = F[(2G - tq) + i]: the forward strand read forwards
+		const int64_t p0 = ix.twoG - tq, wi = p0 >> 4;
+		const uint64_t x = (uint64_t)mc_pac_norm(mc_ldg(pac32 + wi)) | (uint64_t)mc_pac_norm(mc_ldg(pac32 + wi + 1)) << 32;
+		const int64_t left = tq - ix.G; *avail = left < 8 ? (int)left : 8;
+		return (uint32_t)(x >> (((uint32_t)p0 & 15u) << 1)) & 0xFFFFu;
+	}
+	// forward half: E[i] = 3 - F[tq - 1 - i]: the forward strand read backwards, complemented
+	const int64_t p1 = tq - 1, a0 = p1 - 7, wi = a0 < 0 ? 0 : a0 >> 4;
+	const uint64_t x = (uint64_t)mc_pac_norm(mc_ldg(pac32 + wi)) | (uint64_t)mc_pac_norm(mc_ldg(pac32 + wi + 1)) << 32;
+	const int o = (int)(p1 - (wi << 4));                                       // 0..22: where F[p1] sits in x
+	uint32_t v = (uint32_t)((x << ((31 - o) << 1)) >> 48);                     // F[p1 - 7 + t] in bits 2t
+	v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u); v = ((v & 0x0F0Fu) << 4) | ((v >> 4) & 0x0F0Fu); v = ((v << 8) | (v >> 8)) & 0xFFFFu;   // F[p1 - i] in bits 2i
+	*avail = tq < 8 ? (int)tq : 8;
+	return v ^ 0xFFFFu;
 }
 
 template <class Interval> struct SeedOps;
@@ -156,7 +189,6 @@ template <> struct SeedOps<RcInterval> { static MC_HD RcInterval init(const DevI
 template <> struct SeedOps<RcInterval32> { static MC_HD RcInterval32 init(const DevIndex& ix, int c) { return mc_interval_init32(ix, c); } };
 
 #define MC_SEED_LOCATED (1ull << 63)   // Seed::x0 of a seed whose single occurrence is already known: the text position, not a BWT row
-#define MC_SEED_TEXT_STEP 8            // bases compared per trip once a seed is down to one occurrence
 
 // One thread walks one read left to right through the reference's greedy scheme (IdentifySimplePairs + BWT_Search,
 // src/ReadMapping.cpp:125-158, src/bwt_search.cpp:121-151): from `pos`, extend while the pattern occurs; record it when it is
@@ -167,7 +199,7 @@ template <> struct SeedOps<RcInterval32> { static MC_HD RcInterval32 init(const 
 //   locate   the moment ONE occurrence is left (after ~15 bases in a 500 M-symbol text) its text position is looked up once:
 //            LF steps to the next sampled row (3 on average with the sample kept in HBM)
 //   compare  from then on extending the pattern is comparing the read with the packed reference text itself - sequential,
-//            cached, eight bases per trip - instead of one random index block per base.  The search stops exactly where
+//            cached, eight bases per trip on packed words - instead of one random index block per base.  The search stops exactly where
 //            the reference's does: a single row can only be extended by the base that precedes its suffix in the text.
 // A seed that ends in the compare phase already knows its position (Seed::x0 = MC_SEED_LOCATED | position), so the locate
 // kernel has nothing to walk for it.  The work counter `seed_blocks` stays the reference algorithm's: the table carries
@@ -183,7 +215,6 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 	if (r >= n_end) return;
 	const uint8_t* s = nullptr; int rlen = 0, cap = 0, stop = 0; int64_t so = 0;
 	BaseWindow bw; bw.w = nullptr; bw.cur = bw.nxt = 0; bw.have = 0; bw.shift0 = 0;
-	TextWindow tw; tw.have = -1; tw.cur = 0;
 	int ns = 0, pos = 0, p = 0;
 	uint32_t lower = 0;
 	int mode = -1;                // -1 read not yet opened, 0 between seeds, 1 stepping, 2 locating, 3 comparing
@@ -213,19 +244,22 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 				if (r >= n_end) break;
 				mode = -1; continue;
 			}
-			const uint8_t ch = base_at(s, pos, bw);
-			const int c = mc_nt4(ch);
-			if (c > 3) { pos++; continue; }
+			base_at(s, pos, bw);
+			const uint64_t b0 = bases8_at(pos, bw);
+			uint32_t bad0; const uint32_t c0 = mc_pack8(b0, &bad0);
+			if (bad0 & 1u) { pos++; continue; }
 			// the k-mer start table answers the first k bases with one load (mc_fmindex.h); at an N, an absent or an over-frequent
 			// k-mer the search steps through them as the reference does
 			if (a.ix.ktab_k)
 			{
 				const int K = a.ix.ktab_k;
-				uint32_t m = (uint32_t)c, low = ch; bool clean = true;
-				for (int j = 1; j < K; j++) { const uint8_t cj = base_at(s, pos + j, bw); const int x = mc_nt4(cj); clean = clean && x <= 3; m = (m << 2) | (uint32_t)(x & 3); low |= cj; }
-				if (clean && KtabOps<Interval>::lookup(a.ix, m, v, &nblk)) { lower |= low; p = pos + K; mode = 1; }
+				uint32_t m = c0, bad = bad0; uint64_t low = b0;
+				if (K > 8) { base_at(s, pos + 8, bw); const uint64_t b1 = bases8_at(pos + 8, bw); uint32_t bad1; m |= mc_pack8(b1, &bad1) << 16; bad |= bad1 << 8; low |= b1 & ((1ull << ((K - 8) << 3)) - 1); }
+				else if (K < 8) low &= (1ull << (K << 3)) - 1;
+				if (!(bad & ((1u << K) - 1)) && KtabOps<Interval>::lookup(a.ix, m & (uint32_t)((1ull << (2 * K)) - 1), v, &nblk))
+				{ if (low & 0x2020202020202020ull) lower |= 0x20u; p = pos + K; mode = 1; }
 			}
-			if (mode == 0) { lower |= ch; v = SeedOps<Interval>::init(a.ix, c); p = pos + 1; mode = 1; }
+			if (mode == 0) { lower |= (uint32_t)(b0 & 0xFF); v = SeedOps<Interval>::init(a.ix, (int)(c0 & 3u)); p = pos + 1; mode = 1; }
 			if (direct && v.x2 == 1) { mode = 2; lk = (uint64_t)v.x1; lsteps = 0; }
 		}
 		else if (mode == 1)
@@ -246,15 +280,29 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 		}
 		else
 		{
-			for (int t = 0; t < MC_SEED_TEXT_STEP; t++)
+			if (p >= rlen) end = true;
+			else
 			{
-				if (p >= rlen) { end = true; break; }
-				const uint8_t ch = base_at(s, p, bw);
-				const int cc = mc_nt4(ch);
-				if (cc > 3) { end = true; break; }
-				nblk++;                                            // the block this step reads in the reference
-				if (tq <= 0 || text_code_at(a.ix, tq - 1, tw) != 3 - cc) { end = true; break; }
-				p++; tq--; lower |= ch;
+				base_at(s, p, bw);
+				const uint64_t b = bases8_at(p, bw);
+				uint32_t bad; const uint32_t rc = mc_pack8(b, &bad);
+				if (bad & 1u) end = true;                              // an N ends the seed before the reference reads anything
+				else if (tq <= 0) { nblk++; end = true; }              // the text starts here: the step reads its block and finds nothing
+				else
+				{
+					int avail; const uint32_t ex = text_expect8(a.ix, tq, &avail);
+					const int rem = rlen - p; int lim = rem < 8 ? rem : 8;
+					if (bad) { const int fb = mc_ctz(bad); if (fb < lim) lim = fb; }
+					uint32_t d = rc ^ ex; d = (d | (d >> 1)) & 0x5555u;
+					int n = d ? mc_ctz(d) >> 1 : 8;                    // bases that agree
+					const bool mismatch = n < lim && n < avail;
+					if (n > lim) n = lim;
+					if (n > avail) n = avail;
+					if (n > 0 && (b & 0x2020202020202020ull & (n == 8 ? ~0ull : (1ull << (n << 3)) - 1))) lower |= 0x20u;
+					p += n; tq -= n; nblk += (uint32_t)n;
+					if (mismatch) { nblk++; end = true; }              // the failing step reads its block in the reference as well
+					else if (n == lim && lim < 8) end = true;          // the read ends, or an N follows
+				}
 			}
 		}
 		if (end)
