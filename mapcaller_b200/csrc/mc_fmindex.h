@@ -245,6 +245,28 @@ MC_HD bool mc_interval_extend(const DevIndex& ix, RcInterval32& v, int c, uint32
 	return true;
 }
 
+// One backward-search step on the compact layout in the form the seed kernel uses for both of its index phases, so that lanes
+// extending a pattern and lanes walking towards a sampled row run the SAME instructions: extending {x1, x2} by the symbol
+// 3 - c, or - `walk` - by whatever symbol the BWT holds at row x1 (x2 == 1), which is the LF step of that row
+// (LF(k) = L2[s] + occ(s, k) = the first row of the extended interval).  false = empty child (never when walking).
+MC_HD bool mc_fm_step32(const DevIndex& ix, RcInterval32& v, int c, bool walk, uint32_t* nblk)
+{
+	const uint32_t prim = (uint32_t)ix.primary;
+	const uint32_t k = v.x1 - 1u, l = k + v.x2;
+	const uint32_t kk = k - (k >= prim), ll = l - (l >= prim);
+	if (!walk) *nblk += (kk >> 7) == (ll >> 7) ? 1u : 2u;              // blocks the reference algorithm touches (its layout)
+	CBlock bk, bl;
+	mc_load_cblock(ix, kk >> 6, bk);
+	bl = bk;
+	if ((kk >> 6) != (ll >> 6)) mc_load_cblock(ix, ll >> 6, bl);
+	const int i = walk ? mc_cblock_symbol(bl, ll & 63u) : 3 - c;
+	const uint32_t occ_k = mc_cblock_base(bk, i) + mc_count_in_cblock(bk, i, (int)(kk & 63) + 1);
+	const uint32_t occ_l = mc_cblock_base(bl, i) + mc_count_in_cblock(bl, i, (int)(ll & 63) + 1);
+	if (occ_l == occ_k) return false;
+	v.x1 = (uint32_t)ix.L2[i] + 1u + occ_k; v.x2 = occ_l - occ_k;
+	return true;
+}
+
 MC_HD uint64_t mc_lf_step(const DevIndex& ix, uint64_t k)
 {
 	if (k == ix.primary) return 0;

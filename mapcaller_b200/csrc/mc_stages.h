@@ -185,8 +185,23 @@ MC_HD uint32_t text_expect8(const DevIndex& ix, int64_t tq, int* avail)
 }
 
 template <class Interval> struct SeedOps;
-template <> struct SeedOps<RcInterval> { static MC_HD RcInterval init(const DevIndex& ix, int c) { return mc_interval_init(ix, c); } };
-template <> struct SeedOps<RcInterval32> { static MC_HD RcInterval32 init(const DevIndex& ix, int c) { return mc_interval_init32(ix, c); } };
+// step(): extend v by read base c, or - `walk` - move the single row v.x1 one LF step (mc_fm_step32)
+template <> struct SeedOps<RcInterval> {
+	static MC_HD RcInterval init(const DevIndex& ix, int c) { return mc_interval_init(ix, c); }
+	static MC_HD bool step(const DevIndex& ix, RcInterval& v, int c, bool walk, uint32_t* nblk)
+	{
+		if (!walk) return mc_interval_extend(ix, v, c, nblk);
+		v.x1 = mc_lf_step(ix, v.x1); return true;
+	}
+};
+template <> struct SeedOps<RcInterval32> {
+	static MC_HD RcInterval32 init(const DevIndex& ix, int c) { return mc_interval_init32(ix, c); }
+	static MC_HD bool step(const DevIndex& ix, RcInterval32& v, int c, bool walk, uint32_t* nblk)
+	{
+		if (walk && v.x1 == (uint32_t)ix.primary) { v.x1 = 0; return true; }      // bwt_invPsi of the row that holds the end marker
+		return mc_fm_step32(ix, v, c, walk, nblk);
+	}
+};
 
 #define MC_SEED_LOCATED (1ull << 63)   // Seed::x0 of a seed whose single occurrence is already known: the text position, not a BWT row
 
@@ -212,37 +227,53 @@ template <> struct SeedOps<RcInterval32> { static MC_HD RcInterval32 init(const 
 template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, int64_t first, int64_t n_end, const PipeArgs& a)
 {
 	int64_t r = first + tid;
-	if (r >= n_end) return;
 	const uint8_t* s = nullptr; int rlen = 0, cap = 0, stop = 0; int64_t so = 0;
 	BaseWindow bw; bw.w = nullptr; bw.cur = bw.nxt = 0; bw.have = 0; bw.shift0 = 0;
 	int ns = 0, pos = 0, p = 0;
 	uint32_t lower = 0;
-	int mode = -1;                // -1 read not yet opened, 0 between seeds, 1 stepping, 2 locating, 3 comparing
+	// phase of this lane: 4 = no reads left, -1 = read not yet opened, 0 between seeds, 1 stepping, 2 locating (v.x1 = the row
+	// being walked, v.x2 == 1), 3 comparing
+	int mode = r < n_end ? -1 : 4;
 	uint32_t nblk = 0, nloc = 0, nsa = 0;
 	Interval v; v.x1 = v.x2 = 0;
-	uint64_t lk = 0, lsteps = 0;  // locate phase: current row, steps taken
+	uint64_t lsteps = 0;          // locate phase: steps taken
 	int64_t tq = 0;               // compare phase: where the reverse complement of read[pos, p) lies in the text
 	const bool direct = a.ix.sa_shift < 5;   // the denser suffix-array sample is there (mc_ctx_create)
-	// One loop, one load per trip: lanes of a warp stay in lock step whatever their reads, seed boundaries and phases are
-	// (the nested search-inside-scan loops of the reference serialise lanes whose seeds end at different offsets).
+	// One loop, one load per trip.  The lanes of a warp are in different reads, seeds and phases; every trip the warp runs the
+	// ONE phase group most of its lanes are in - start (-1, 0), index step (1, 2) or compare (3) - and the others wait for
+	// their turn, so that an instruction is executed for many lanes instead of each group's code for a few (with every present
+	// group run in every trip 6 of 32 lanes were active per instruction).
 	for (;;)
 	{
-		bool end = false;
-		if (mode < 0)
+#if MC_DEV_ONLY
 		{
-			s = a.seq + a.roff[r]; rlen = (int)(a.roff[r + 1] - a.roff[r]);
-			so = a.seed_off[r]; cap = (int)(a.seed_off[r + 1] - so); stop = rlen - MC_MIN_SEED;
-			base_window_init(bw, s);
-			ns = 0; pos = 0; p = 0; lower = 0; mode = 0;
+			const unsigned full = 0xffffffffu;
+			const unsigned g0 = __ballot_sync(full, mode <= 0), g1 = __ballot_sync(full, mode == 1 || mode == 2), g3 = __ballot_sync(full, mode == 3);
+			if (!(g0 | g1 | g3)) break;                                 // every lane is out of reads
+			const int n0 = __popc(g0), n1 = __popc(g1), n3 = __popc(g3);
+			const int pick = (n1 >= n0 && n1 >= n3) ? 1 : (n3 >= n0 ? 3 : 0);
+			const int mine = mode <= 0 ? 0 : (mode == 3 ? 3 : (mode == 4 ? 4 : 1));
+			if (mine != pick) continue;
 		}
-		if (mode == 0)
+#else
+		if (mode == 4) break;
+#endif
+		bool end = false;
+		if (mode <= 0)
 		{
+			if (mode < 0)
+			{
+				s = a.seq + a.roff[r]; rlen = (int)(a.roff[r + 1] - a.roff[r]);
+				so = a.seed_off[r]; cap = (int)(a.seed_off[r + 1] - so); stop = rlen - MC_MIN_SEED;
+				base_window_init(bw, s);
+				ns = 0; pos = 0; p = 0; lower = 0; mode = 0;
+			}
 			if (pos >= stop)
 			{
 				a.rflag[r] = (uint8_t)((lower >> 5) & 1);
 				r += nthreads;
-				if (r >= n_end) break;
-				mode = -1; continue;
+				mode = r < n_end ? -1 : 4;
+				continue;
 			}
 			base_at(s, pos, bw);
 			const uint64_t b0 = bases8_at(pos, bw);
@@ -260,23 +291,29 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 				{ if (low & 0x2020202020202020ull) lower |= 0x20u; p = pos + K; mode = 1; }
 			}
 			if (mode == 0) { lower |= (uint32_t)(b0 & 0xFF); v = SeedOps<Interval>::init(a.ix, (int)(c0 & 3u)); p = pos + 1; mode = 1; }
-			if (direct && v.x2 == 1) { mode = 2; lk = (uint64_t)v.x1; lsteps = 0; }
+			if (direct && v.x2 == 1) { mode = 2; lsteps = 0; }
 		}
-		else if (mode == 1)
+		else if (mode <= 2)
 		{
-			end = p >= rlen;
-			if (!end)
+			// index step: extend by the next read base (1), or walk the single row towards a sampled one (2)
+			const bool walk = mode == 2;
+			if (walk && mc_sa_sampled(a.ix, (uint64_t)v.x1)) { tq = (int64_t)mc_sa_value(a.ix, (uint64_t)v.x1, lsteps); mode = 3; }
+			else
 			{
-				const uint8_t ch = base_at(s, p, bw);
-				const int cc = mc_nt4(ch);
-				end = cc > 3 || !mc_interval_extend(a.ix, v, cc, &nblk);
-				if (!end) { p++; lower |= ch; if (direct && v.x2 == 1 && p < rlen) { mode = 2; lk = (uint64_t)v.x1; lsteps = 0; } }
+				int cc = 0; uint8_t ch = 0;
+				if (!walk)
+				{
+					end = p >= rlen;
+					if (!end) { ch = base_at(s, p, bw); cc = mc_nt4(ch); end = cc > 3; }
+				}
+				if (!end)
+				{
+					const bool ok = SeedOps<Interval>::step(a.ix, v, cc, walk, &nblk);
+					if (walk) { lsteps++; nloc++; }
+					else if (!ok) end = true;
+					else { p++; lower |= ch; if (direct && v.x2 == 1 && p < rlen) { mode = 2; lsteps = 0; } }
+				}
 			}
-		}
-		else if (mode == 2)
-		{
-			if (mc_sa_sampled(a.ix, lk)) { tq = (int64_t)mc_sa_value(a.ix, lk, lsteps); mode = 3; }
-			else { lk = mc_lf_step(a.ix, lk); lsteps++; nloc++; }
 		}
 		else
 		{
