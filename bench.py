@@ -227,6 +227,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (default: sized for ~10-30 s)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM flavour of the end-to-end leg")
+    ap.add_argument("--trace-e2e", action="store_true", help="print a host-side timeline of one end-to-end step to stderr")
     ap.add_argument("--resident-only", action="store_true", help="profiling runs: only the resident leg (the JSON line then has no e2e)")
     args = ap.parse_args()
     args.pairs -= args.pairs % SIM_BLOCK
@@ -335,7 +336,9 @@ def main():
     def fastq_pass(sam: bool):
         # three device slots in flight: block b+1 on the wire (mc_ingest_prefetch, plain DMA), block b being parsed
         # (mc_ingest_fastq) by the feeder thread, block b-1 being mapped by this thread
-        ctx.reset()
+        T0 = time.perf_counter(); tl = []
+        mark = (lambda what, b: tl.append((1000 * (time.perf_counter() - T0), what, b))) if args.trace_e2e else (lambda what, b: None)
+        ctx.reset(); mark("reset done", -1)
         err = []
         ready = [threading.Semaphore(0) for _ in range(3)]; free = [threading.Semaphore(1) for _ in range(3)]
         slot = lambda b: S_IN0 + b % 3
@@ -346,7 +349,9 @@ def main():
                 for b in range(n_batches):
                     if b + 1 < n_batches:
                         free[(b + 1) % 3].acquire(); ctx.ingest_prefetch(ptext[b + 1][0], ptext[b + 1][1], slot=slot(b + 1))
+                    mark("ingest begin", b)
                     ctx.ingest_fastq(ptext[b][0], ptext[b][1], slot=slot(b), final=True)
+                    mark("ingest end", b)
                     ready[b % 3].release()
             except Exception as e:      # surfaces in the main thread
                 err.append(e)
@@ -358,16 +363,23 @@ def main():
             ready[b % 3].acquire()
             if err:
                 break
+            mark("map begin", b)
             ctx.map_staged(slot(b))
+            mark("map end", b)
             if sam:
-                sam_bytes += ctx.sam_text_raw(slot(b))
+                sam_bytes += ctx.sam_text_raw(slot(b)); mark("sam text end", b)
             free[b % 3].release()
         th.join()
         if err:
             raise err[0]
         if dist is not None:
             ctx.profile_allreduce()
+        mark("scan begin", -1)
         n_var, n_blk = ctx.variant_scan_raw()
+        mark("scan end", -1)
+        if args.trace_e2e and rank == 0:
+            for t, what, b in sorted(tl):
+                print("[e2e %s] %9.3f ms  %-14s batch %d" % ("sam" if sam else "vcf", t, what, b), file=sys.stderr)
         return n_var, sam_bytes
 
     def timed_fastq(sam: bool):

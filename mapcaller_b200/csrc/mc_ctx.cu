@@ -210,6 +210,7 @@ struct mc_ctx {
 	std::vector<mc_indel_rec> ind_out; std::vector<uint8_t> ind_seq_out; std::vector<mc_breakpoint_rec> bp_out;
 	std::vector<mc_variant_rec> vc_out; std::vector<int32_t> vc_depth;
 	DBuf d_vc[12];   // scratch of mc_variant_scan, kept between calls
+	DBuf d_ia[9]; HBuf h_ind_rec, h_ind_seq;   // scratch of mc_profile_indels
 	int64_t last_n = 0; const int64_t* last_roff = nullptr;   // the batch whose arenas are still on the device (mc_sam_records)
 	DBuf d_sam[5], d_chrom_names, d_chrom_name_off; HBuf h_sam_text; std::vector<mc_sam_rec> sam_out; std::vector<uint8_t> sam_cigar;
 	std::vector<std::string> chrom_names;
@@ -247,6 +248,8 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off, &c->d_scan2};
 	for (DBuf* b : bufs) b->release();
 	for (DBuf& b : c->d_vc) b.release();
+	for (DBuf& b : c->d_ia) b.release();
+	c->h_ind_rec.release(); c->h_ind_seq.release();
 	for (DBuf& b : c->d_sam) b.release();
 	c->d_chrom_names.release(); c->d_chrom_name_off.release(); c->h_sam_text.release();
 	std::vector<Staged*> st; st.push_back(&c->cur); for (int i = 0; i < MC_SLOTS; i++) st.push_back(&c->slots[i]);
@@ -288,9 +291,12 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 		delete c; return MC_ERR_CUDA;
 	}
 	if (cuda_fail(cudaSetDevice(params->device), "cudaSetDevice")) { delete c; return MC_ERR_CUDA; }
-	if (cuda_fail(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
-	if (cuda_fail(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
-	if (cuda_fail(cudaStreamCreateWithFlags(&c->dstream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
+	// the mapping stream outranks the staging streams: a batch being parsed for later must not hold up the kernels of the batch
+	// being mapped now
+	int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+	if (cuda_fail(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
+	if (cuda_fail(cudaStreamCreateWithPriority(&c->cstream, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
+	if (cuda_fail(cudaStreamCreateWithPriority(&c->dstream, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate")) { delete c; return MC_ERR_CUDA; }
 #else
 	c->stream = 0; c->cstream = 0; c->dstream = 0;
 #endif
@@ -1142,14 +1148,19 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	st.valid = false; st.pending = false; st.n_pieces = 0; st.h_roff.clear(); st.has_text = false;
 	const int nf = in->text2 ? 2 : 1;
 	st.n_files = nf;
+	const bool dbg = getenv("MC_DEBUG") != nullptr;
+	const auto t_in = std::chrono::steady_clock::now();
+	auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count(); };
+	double t_copy = 0, t_lines = 0;
 #ifndef MC_HOSTEMU
 	if (st.prefetched && cuda_fail(cudaStreamWaitEvent(s, c->ev_text[slot], 0), "cudaStreamWaitEvent")) return MC_ERR_CUDA;   // the copy queued by mc_ingest_prefetch
+	if (dbg && st.prefetched) { cudaEventSynchronize(c->ev_text[slot]); t_copy = since(); }
 #endif
 	const uint8_t* text[2] = {in->text1, in->text2}; const int64_t len[2] = {in->len1, in->text2 ? in->len2 : 0};
 	FastqArgs q; memset(&q, 0, sizeof(q));
 	DBuf* d_text = st.text; DBuf* d_cnt = c->fq_cnt; DBuf* d_off = c->fq_off; DBuf* d_lines = st.lines;
 	DBuf& d_scan = c->fq_scan; DBuf& d_rlen = c->fq_rlen; DBuf& d_rsrc = c->fq_rsrc;   // kept between calls: no allocation in the steady state
-	auto done = [&](int rc) { st.prefetched = false; return rc; };
+	auto done = [&](int rc) { if (dbg) fprintf(stderr, "[mc] ingest slot %d: %.1f MB, text on the device after %.3f ms, lines counted after %.3f ms, staged after %.3f ms\n", slot, (in->len1 + (in->text2 ? in->len2 : 0)) / 1e6, t_copy, t_lines, since()); st.prefetched = false; return rc; };
 	int bad = 0;
 	int64_t n_tiles[2] = {0, 0}, n_lines[2] = {0, 0}; bool open_end[2] = {false, false};
 	if (st.flag.reserve(16) || dev_zero(st.flag.p, 16, s)) return done(MC_ERR_CUDA);
@@ -1165,6 +1176,7 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 		bad |= dev_d2h(&n_lines[f], d_off[f].as<int64_t>() + n_tiles[f], 8, s);
 	}
 	if (bad || dev_sync(s)) return done(MC_ERR_CUDA);
+	t_lines = since();
 	// whole records only (four lines each); at the end of the file a last line without newline still counts
 	int64_t n_rec = -1;
 	for (int f = 0; f < nf; f++)
@@ -1376,33 +1388,56 @@ int mc_profile_indels(mc_ctx* c, const mc_indel_rec** recs, int64_t* n_recs, con
 #endif
 	if (!c || !recs || !n_recs || !seq_arena) { mc_set_error("mc_profile_indels: null argument"); return MC_ERR_ARG; }
 	PersistBumps pb;
-	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
-	std::vector<mc_indel_rec> raw((size_t)pb.ind); std::vector<uint8_t> seq((size_t)pb.ind_seq + 1);
-	if (dev_d2h(raw.data(), c->d_ind.p, raw.size() * sizeof(mc_indel_rec), c->stream) || dev_d2h(seq.data(), c->d_ind_seq.p, (size_t)pb.ind_seq, c->stream) || dev_sync(c->stream)) return MC_ERR_CUDA;
-	// aggregate like map<int64, map<string, uint16_t>>::operator[]++ (reference src/AlignmentProfile.cpp:123,129): sort the raw
-	// records by (kind, pos, sequence as std::string compares it) and count the runs - the order a walk over the maps gives
-	std::vector<uint32_t> order(raw.size());
-	for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
-	const uint8_t* sq = seq.data();
-	auto key_less = [&](uint32_t x, uint32_t y) {
-		const mc_indel_rec &a = raw[x], &b = raw[y];
-		if (a.kind != b.kind) return a.kind < b.kind;
-		if (a.pos != b.pos) return a.pos < b.pos;
-		const int m = memcmp(sq + a.seq_off, sq + b.seq_off, (size_t)std::min(a.len, b.len));
-		return m != 0 ? m < 0 : a.len < b.len;
-	};
-	std::sort(order.begin(), order.end(), key_less);
+	mc_stream_t s = c->stream;
+	if (dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s)) return MC_ERR_CUDA;
+	const int64_t n = (int64_t)pb.ind;
 	c->ind_out.clear(); c->ind_seq_out.clear();
-	for (size_t i = 0; i < order.size();)
+	if (n >= 0xffffffffll) { mc_set_error("mc_profile_indels: more than 2^32 raw records"); return MC_ERR_OVERFLOW; }
+	if (n > 0)
 	{
-		size_t j = i + 1;
-		while (j < order.size() && !key_less(order[i], order[j])) j++;   // sorted: not less = equal key
-		const mc_indel_rec& a = raw[order[i]];
-		mc_indel_rec r; r.pos = a.pos; r.kind = a.kind; r.len = a.len; r.count = (int32_t)((j - i) & 0xFFFF);
-		r.seq_off = (int32_t)c->ind_seq_out.size();
-		c->ind_seq_out.insert(c->ind_seq_out.end(), sq + a.seq_off, sq + a.seq_off + a.len);
-		c->ind_out.push_back(r);
-		i = j;
+		// the device sorts the raw records by (kind, position, hash of the sequence) and lays them and their sequences out in that
+		// order; what is left for the host is one sequential pass
+		DBuf &d_key = c->d_ia[0], &d_ktmp = c->d_ia[1], &d_idx = c->d_ia[2], &d_itmp = c->d_ia[3], &d_len = c->d_ia[4], &d_off = c->d_ia[5], &d_rec = c->d_ia[6], &d_seq = c->d_ia[7], &d_scr = c->d_ia[8];
+		int bad = d_key.reserve((size_t)n * 8) || d_ktmp.reserve((size_t)n * 8) || d_idx.reserve((size_t)n * 4) || d_itmp.reserve((size_t)n * 4) || d_len.reserve((size_t)(n + 1) * 4) || d_off.reserve((size_t)(n + 2) * 8);
+		bad = bad || d_rec.reserve((size_t)n * sizeof(mc_indel_rec)) || d_seq.reserve((size_t)pb.ind_seq + 16) || d_scr.reserve(device_sort_pairs_scratch_bytes(n)) || c->d_scan2.reserve(device_scan_scratch_bytes(n));
+		if (bad) return MC_ERR_CUDA;
+		launch_indkey(n, c->d_ind.as<mc_indel_rec>(), c->d_ind_seq.as<uint8_t>(), d_key.as<uint64_t>(), d_idx.as<uint32_t>(), s);
+		device_sort_pairs(d_key.as<uint64_t>(), d_ktmp.as<uint64_t>(), d_idx.as<uint32_t>(), d_itmp.as<uint32_t>(), n, d_scr.p, d_scr.cap, s);
+		launch_indlen(n, c->d_ind.as<mc_indel_rec>(), d_idx.as<uint32_t>(), d_len.as<uint32_t>(), s);
+		device_scan_u32(d_len.as<uint32_t>(), d_off.as<int64_t>(), n, c->d_scan2.as<int64_t>(), s);
+		launch_indgather(n, c->d_ind.as<mc_indel_rec>(), c->d_ind_seq.as<uint8_t>(), d_idx.as<uint32_t>(), d_off.as<int64_t>(), d_rec.as<mc_indel_rec>(), d_seq.as<uint8_t>(), s);
+		if (c->h_ind_rec.reserve((size_t)n * sizeof(mc_indel_rec)) || c->h_ind_seq.reserve((size_t)pb.ind_seq + 16)) return MC_ERR_CUDA;
+		if (dev_d2h(c->h_ind_rec.p, d_rec.p, (size_t)n * sizeof(mc_indel_rec), s) || dev_d2h(c->h_ind_seq.p, d_seq.p, (size_t)pb.ind_seq, s) || dev_sync(s)) return MC_ERR_CUDA;
+		const mc_indel_rec* raw = c->h_ind_rec.as<mc_indel_rec>(); const uint8_t* sq = c->h_ind_seq.as<uint8_t>();
+		// aggregate like map<int64, map<string, uint16_t>>::operator[]++ (reference src/AlignmentProfile.cpp:123,129): the records of
+		// one (kind, position) are adjacent; their distinct sequences come out in the order std::string compares them
+		auto seq_less = [&](const mc_indel_rec* a, const mc_indel_rec* b) {
+			const int m = memcmp(sq + a->seq_off, sq + b->seq_off, (size_t)std::min(a->len, b->len));
+			return m != 0 ? m < 0 : a->len < b->len;
+		};
+		std::vector<const mc_indel_rec*> grp;
+		c->ind_out.reserve((size_t)n / 4 + 16); c->ind_seq_out.reserve((size_t)pb.ind_seq / 4 + 16);
+		for (int64_t i = 0; i < n;)
+		{
+			int64_t j = i + 1;
+			while (j < n && raw[j].kind == raw[i].kind && raw[j].pos == raw[i].pos) j++;
+			grp.clear();
+			for (int64_t k = i; k < j; k++) grp.push_back(raw + k);
+			// equal sequences are already adjacent (same hash) except after a hash collision: a sort of the group's run heads would
+			// do, sorting the whole (small) group is simpler and exact either way
+			if (j - i > 1) std::sort(grp.begin(), grp.end(), seq_less);
+			for (size_t g = 0; g < grp.size();)
+			{
+				size_t h = g + 1;
+				while (h < grp.size() && !seq_less(grp[g], grp[h])) h++;
+				mc_indel_rec r; r.pos = grp[g]->pos; r.kind = grp[g]->kind; r.len = grp[g]->len; r.count = (int32_t)((h - g) & 0xFFFF);
+				r.seq_off = (int32_t)c->ind_seq_out.size();
+				c->ind_seq_out.insert(c->ind_seq_out.end(), sq + grp[g]->seq_off, sq + grp[g]->seq_off + grp[g]->len);
+				c->ind_out.push_back(r);
+				g = h;
+			}
+			i = j;
+		}
 	}
 	c->ind_seq_out.push_back(0);
 	*recs = c->ind_out.data(); *n_recs = (int64_t)c->ind_out.size(); *seq_arena = c->ind_seq_out.data();
@@ -1522,7 +1557,16 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	DevProfile p; p.base16 = c->d_base16.as<uint32_t>(); p.sdiff = c->d_sdiff.as<int32_t>(); p.cdiff = c->d_cdiff.as<int32_t>(); p.mdiff = c->d_mdiff.as<int32_t>();
 	p.rcount = c->d_rcount.as<uint8_t>();
 	const int64_t G = c->G, nb = (G + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK, nvb = (G + MC_VC_BLOCK - 1) / MC_VC_BLOCK;
-	const int64_t tile_cols = (int64_t)25600 * 640;   // a multiple of MC_PROF_BLOCK and of MC_VC_BLOCK
+	// The scan makes three passes over the packed profile (depths, counts, records).  When HBM has room for the whole
+	// MappingRecord_t image (16 bytes per column) it is packed once and kept; otherwise it is re-packed tile by tile per pass.
+	int64_t tile_cols = (int64_t)25600 * 640;           // a multiple of MC_PROF_BLOCK and of MC_VC_BLOCK
+#ifndef MC_HOSTEMU
+	{
+		size_t free_b = 0, total_b = 0;
+		const size_t whole = (size_t)((G + 25599) / 25600) * 25600 * 16;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (c->d_sort.cap >= whole || free_b > whole + ((size_t)8 << 30)) && !getenv("MC_VC_TILED")) tile_cols = (int64_t)(whole / 16);
+	}
+#endif
 	const int64_t n_tiles = (G + tile_cols - 1) / tile_cols;
 	DBuf &d_sums = c->d_vc[0], &d_depth = c->d_vc[1], &d_ng = c->d_vc[2], &d_nd = c->d_vc[3], &d_ln = c->d_vc[4], &d_le = c->d_vc[5], &d_lead = c->d_vc[6],
 	     &d_cnt = c->d_vc[7], &d_off = c->d_vc[8], &d_scan = c->d_vc[9], &d_cand = c->d_vc[10], &d_out = c->d_vc[11];

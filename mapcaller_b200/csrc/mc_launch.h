@@ -40,6 +40,9 @@ static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_
 static void launch_sa_dense(const DevIndex& ix, int64_t n, int shift, uint32_t* o32, uint64_t* o64, mc_stream_t) { for (int64_t j = 0; j < n; j++) mc_sa_dense_body(j, ix, shift, o32, o64); }
 static void launch_ktab_build(const DevIndex& ix, int k, uint32_t* o32, uint64_t* o64, mc_stream_t) { for (int64_t m = 0; m < (1ll << (2 * k)); m++) mc_ktab_build_body(m, ix, k, o32, o64); }
 static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) profstat_body(i, recs, acc); }
+static void launch_indkey(int64_t n, const mc_indel_rec* recs, const uint8_t* seq, uint64_t* keys, uint32_t* idx, mc_stream_t) { for (int64_t i = 0; i < n; i++) indkey_body(i, recs, seq, keys, idx); }
+static void launch_indlen(int64_t n, const mc_indel_rec* recs, const uint32_t* idx, uint32_t* len, mc_stream_t) { for (int64_t j = 0; j < n; j++) indlen_body(j, recs, idx, len); }
+static void launch_indgather(int64_t n, const mc_indel_rec* recs, const uint8_t* seq, const uint32_t* idx, const int64_t* off, mc_indel_rec* out, uint8_t* out_seq, mc_stream_t) { for (int64_t j = 0; j < n; j++) indgather_body(j, recs, seq, idx, off, out, out_seq); }
 static void launch_profhash(int64_t g0, int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t) { for (int64_t i = 0; i < n; i++) { const uint64_t h = profhash_of(g0 + i, recs, i); acc[0] += h; acc[1] ^= h; } }
 static void launch_gatecnt(const PipeArgs& a, const ProfArgs& q, int64_t n, uint64_t* list, mc_u64* bump, mc_stream_t) { for (int64_t i = 0; i < n; i++) gatecnt_body(i, a, q, list, bump); }
 static void launch_gateadd(const PipeArgs& a, int64_t n, const uint64_t* list, mc_stream_t) { for (int64_t i = 0; i < n; i++) gateadd_body(i, a, list); }
@@ -56,6 +59,7 @@ static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t) {
 static void launch_samtext(const SamTextArgs& t, int64_t n, bool emit, mc_stream_t) { for (int64_t r = 0; r < n; r++) samtext_body(r, t, emit); }
 static void device_incmax_i64(int64_t* a, int64_t n, void*, mc_stream_t) { for (int64_t i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, void*, mc_stream_t) { int64_t s = 0; for (int64_t i = 0; i < n; i++) { int64_t v = a[i]; a[i] = s; s += v; } *total = s; }
+#include <vector>
 static int64_t g_launches = 0;
 #define MC_SLOTS 8
 #else
@@ -187,6 +191,18 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_profstat_kernel(int64_t n, const 
 { for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (int64_t)gridDim.x * blockDim.x) if (i < n) profstat_body(i, recs, acc); }
 static void launch_profstat(int64_t n, const uint64_t* recs, mc_u64* acc, mc_stream_t s)
 { if (n > 0) { int64_t b = (n + MC_BLOCK - 1) / MC_BLOCK; if (b > 148 * 8) b = 148 * 8; mc_profstat_kernel<<<(unsigned)b, MC_BLOCK, 0, s>>>(n, recs, acc); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_indkey_kernel(int64_t n, const mc_indel_rec* recs, const uint8_t* seq, uint64_t* keys, uint32_t* idx)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) indkey_body(i, recs, seq, keys, idx); }
+__global__ void __launch_bounds__(MC_BLOCK) mc_indlen_kernel(int64_t n, const mc_indel_rec* recs, const uint32_t* idx, uint32_t* len)
+{ int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (j < n) indlen_body(j, recs, idx, len); }
+__global__ void __launch_bounds__(MC_BLOCK) mc_indgather_kernel(int64_t n, const mc_indel_rec* recs, const uint8_t* seq, const uint32_t* idx, const int64_t* off, mc_indel_rec* out, uint8_t* out_seq)
+{ int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (j < n) indgather_body(j, recs, seq, idx, off, out, out_seq); }
+static void launch_indkey(int64_t n, const mc_indel_rec* recs, const uint8_t* seq, uint64_t* keys, uint32_t* idx, mc_stream_t s)
+{ if (n > 0) { mc_indkey_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, recs, seq, keys, idx); g_launches++; } }
+static void launch_indlen(int64_t n, const mc_indel_rec* recs, const uint32_t* idx, uint32_t* len, mc_stream_t s)
+{ if (n > 0) { mc_indlen_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, recs, idx, len); g_launches++; } }
+static void launch_indgather(int64_t n, const mc_indel_rec* recs, const uint8_t* seq, const uint32_t* idx, const int64_t* off, mc_indel_rec* out, uint8_t* out_seq, mc_stream_t s)
+{ if (n > 0) { mc_indgather_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, recs, seq, idx, off, out, out_seq); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profhash_kernel(int64_t g0, int64_t n, const uint64_t* recs, mc_u64* acc)
 {
 	uint64_t sum = 0, x = 0;
@@ -296,6 +312,14 @@ static void device_scan_u32(const uint32_t* in, int64_t* out, int64_t n, int64_t
 { int64_t s = 0; for (int64_t i = 0; i < n; i++) { out[i] = s; s += in[i]; } out[n] = s; }
 static size_t device_scan_scratch_bytes(int64_t) { return 8; }
 static void device_sort_u64(uint64_t* keys, uint64_t*, int64_t n, void*, size_t, mc_stream_t) { std::sort(keys, keys + n); }
+static void device_sort_pairs(uint64_t* keys, uint64_t*, uint32_t* vals, uint32_t*, int64_t n, void*, size_t, mc_stream_t)
+{
+	std::vector<std::pair<uint64_t, uint32_t> > v((size_t)n);
+	for (int64_t i = 0; i < n; i++) v[(size_t)i] = std::make_pair(keys[i], vals[i]);
+	std::stable_sort(v.begin(), v.end(), [](const std::pair<uint64_t, uint32_t>& x, const std::pair<uint64_t, uint32_t>& y) { return x.first < y.first; });
+	for (int64_t i = 0; i < n; i++) { keys[i] = v[(size_t)i].first; vals[i] = v[(size_t)i].second; }
+}
+static size_t device_sort_pairs_scratch_bytes(int64_t) { return 8; }
 static size_t device_sort_scratch_bytes(int64_t) { return 8; }
 #else
 #include "mc_scan.cuh"
@@ -328,6 +352,19 @@ static size_t device_sort_scratch_bytes(int64_t n)
 {
 	size_t b = 0; cub::DeviceRadixSort::SortKeys(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, n);
 	return b + 256;
+}
+static size_t device_sort_pairs_scratch_bytes(int64_t n)
+{
+	size_t b = 0; cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+	return b + 256;
+}
+// sorts (key, value) pairs in place (the tmp arrays must hold n entries each); stable
+static void device_sort_pairs(uint64_t* keys, uint64_t* ktmp, uint32_t* vals, uint32_t* vtmp, int64_t n, void* scratch, size_t scratch_bytes, mc_stream_t s)
+{
+	if (n <= 1) return;
+	cub::DeviceRadixSort::SortPairs(scratch, scratch_bytes, (const uint64_t*)keys, ktmp, (const uint32_t*)vals, vtmp, n, 0, 64, s);
+	cudaMemcpyAsync(keys, ktmp, (size_t)n * 8, cudaMemcpyDeviceToDevice, s); cudaMemcpyAsync(vals, vtmp, (size_t)n * 4, cudaMemcpyDeviceToDevice, s);
+	g_launches += 4;
 }
 // sorts keys in place (tmp must hold n keys)
 static void device_sort_u64(uint64_t* keys, uint64_t* tmp, int64_t n, void* scratch, size_t scratch_bytes, mc_stream_t s)

@@ -316,6 +316,28 @@ MC_HD void profstat_body(int64_t i, const uint64_t* recs, mc_u64* acc)
 	mc_stat_add(acc + 2, rc ? 1u : 0u); mc_stat_add(acc + 3, rc);
 }
 
+// ---- aggregation of the raw indel records (mc_profile_indels): the device brings equal (kind, position, sequence) records
+// next to each other - sort key = kind | position | hash of the sequence - and lays the records and their sequences out in that
+// order, so that the host only counts runs (and orders the few distinct sequences of one position as std::string compares)
+MC_HD void indkey_body(int64_t i, const mc_indel_rec* recs, const uint8_t* seq, uint64_t* keys, uint32_t* idx)
+{
+	const mc_indel_rec r = recs[i];
+	uint32_t h = 2166136261u;                                        // FNV-1a over the sequence
+	for (int k = 0; k < r.len; k++) h = (h ^ seq[r.seq_off + k]) * 16777619u;
+	h = (h ^ (uint32_t)r.len) * 16777619u;
+	keys[i] = ((uint64_t)(r.kind & 1) << 63) | ((uint64_t)(uint32_t)(r.pos + 1) << 31) | (uint64_t)(h >> 1);   // positions start at -1
+	idx[i] = (uint32_t)i;
+}
+MC_HD void indlen_body(int64_t j, const mc_indel_rec* recs, const uint32_t* idx, uint32_t* len) { len[j] = (uint32_t)recs[idx[j]].len; }
+MC_HD void indgather_body(int64_t j, const mc_indel_rec* recs, const uint8_t* seq, const uint32_t* idx, const int64_t* off, mc_indel_rec* out, uint8_t* out_seq)
+{
+	mc_indel_rec r = recs[idx[j]];
+	const uint8_t* s = seq + r.seq_off;
+	r.seq_off = (int32_t)off[j];
+	for (int k = 0; k < r.len; k++) out_seq[off[j] + k] = s[k];
+	out[j] = r;
+}
+
 // fingerprint of the packed profile: every column's record mixed with its position (splitmix64 finaliser), summed into acc[0]
 // and xor-ed into acc[1] - independent of the order in which the columns are visited
 MC_HD uint64_t prof_mix(uint64_t x)
