@@ -189,7 +189,7 @@ struct mc_ctx {
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_rwin, d_rw_beg, d_bumps, d_stats, d_scan;
 	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off, d_scan2;
 	HBuf h_disc;
-	HBuf h_bounce[2];
+	HBuf h_bounce[2], h_push; size_t push_at = 0;
 	mc_stream_t cstream, dstream;   // copy + staging kernels; plain DMA of prefetched FASTQ blocks
 #ifndef MC_HOSTEMU
 	cudaEvent_t ev_bounce[2], ev_piece[8], ev_slot[MC_SLOTS], ev_text[MC_SLOTS];
@@ -263,7 +263,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	c->d_comm_small.release(); c->d_comm_buf.release(); c->d_glist.release(); c->d_glist_all.release(); c->h_comm_buf.release();
 #endif
 	for (int i = 0; i < EV_COUNT; i++) ev_destroy(&c->ev[i]);
-	c->h_bounce[0].release(); c->h_bounce[1].release();
+	c->h_bounce[0].release(); c->h_bounce[1].release(); c->h_push.release();
 #ifndef MC_HOSTEMU
 	cudaEventDestroy(c->ev_bounce[0]); cudaEventDestroy(c->ev_bounce[1]); for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev_piece[i]);
 	for (int i = 0; i < MC_SLOTS; i++) { cudaEventDestroy(c->ev_slot[i]); cudaEventDestroy(c->ev_text[i]); }
@@ -448,7 +448,15 @@ static int upload(mc_ctx* c, void* dst, const void* src, size_t bytes, mc_stream
 #ifndef MC_HOSTEMU
 	cudaPointerAttributes at;
 	if (cudaPointerGetAttributes(&at, src) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged))
-		return dev_h2d(dst, src, bytes, stream);
+	{
+		// in pieces of 4 MB: the copy engine takes its commands in order, and a batch being mapped sends a few kilobytes host ->
+		// device per attempt - behind one 600 MB transfer those would wait 10+ ms each (measured: mapping ran at 40 % of its speed
+		// while a prefetch was on the wire), behind a 4 MB piece they wait 0.1 ms
+		const size_t piece = (size_t)4 << 20;
+		for (size_t off = 0; off < bytes; off += piece)
+			if (dev_h2d((uint8_t*)dst + off, (const uint8_t*)src + off, std::min(piece, bytes - off), stream)) return -1;
+		return 0;
+	}
 	cudaGetLastError();
 	const size_t piece = 8u << 20;
 	if (c->h_bounce[0].reserve(piece) || c->h_bounce[1].reserve(piece)) return -1;
@@ -465,6 +473,33 @@ static int upload(mc_ctx* c, void* dst, const void* src, size_t bytes, mc_stream
 	return 0;
 #else
 	return dev_h2d(dst, src, bytes, stream);
+#endif
+}
+
+// Small host -> device transfers of the batch controller (a few kilobytes per attempt).  They do not go through the copy
+// engine: that engine takes its commands in submission order, so behind the FASTQ blocks mc_ingest_prefetch queued for the next
+// batches (1.3 GB each) they waited for tens of milliseconds and the mapping ran at 40 % of its speed.  The bytes are placed in
+// a page-locked ring and a one-block kernel reads them over PCIe itself.
+#ifndef MC_HOSTEMU
+__global__ void mc_push_kernel(uint8_t* dst, const uint8_t* src, size_t n)
+{ for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i]; }
+#endif
+static int dev_push(mc_ctx* c, void* dst, const void* src, size_t bytes, mc_stream_t s)
+{
+	if (!bytes) return 0;
+#ifdef MC_HOSTEMU
+	memcpy(dst, src, bytes); return 0;
+#else
+	const size_t ring = (size_t)8 << 20;
+	if (bytes > ring / 4) return dev_h2d(dst, src, bytes, s);
+	if (c->h_push.reserve(ring)) return -1;
+	size_t at = (c->push_at + 255) & ~(size_t)255;
+	if (at + bytes > ring) at = 0;      // a slot is reused 8 MB of pushes later: many batches, each of which ended with a synchronize
+	c->push_at = at + bytes;
+	memcpy(c->h_push.as<uint8_t>() + at, src, bytes);
+	g_h2d_bytes += (int64_t)bytes;
+	mc_push_kernel<<<(unsigned)std::min<size_t>((bytes + 255) / 256, 64), 256, 0, s>>>((uint8_t*)dst, c->h_push.as<uint8_t>() + at, bytes);
+	return cuda_fail(cudaGetLastError(), "push kernel");
 #endif
 }
 
@@ -738,7 +773,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		if (paired && c->tot.total_paired <= 1000)
 			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2 + 256; k < NG; k++) active[k] = 0;
 		Bumps hb; memset(&hb, 0, sizeof(hb)); hb.pair = (mc_u64)n_locs;
-		bad |= dev_h2d(db, &hb, sizeof(hb), s) || dev_zero(c->d_pair_flag.p, (n_pairs + 1) * 4, s);
+		bad |= dev_push(c, db, &hb, sizeof(hb), s) || dev_zero(c->d_pair_flag.p, (n_pairs + 1) * 4, s);
 		mc_totals run = c->tot;
 		c->chunks_final.assign(NG, mc_chunk_out());
 		int64_t first_open = 0;
@@ -753,7 +788,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			// one attempt: no host round trip inside it, the task lists are consumed from their device-side cursors
 			a.rtask_begin = (int64_t)hbp->rtask; a.task_begin = (int64_t)hbp->task; a.ptask_begin = (int64_t)hbp->ptask;
 			if (a.rtask_begin + n_pairs > rtask_cap) { mc_set_error("mc_map_batch: too many speculation replays in one batch"); return MC_ERR_OVERFLOW; }
-			bad |= dev_h2d(c->d_est.p, est.data() + g0, n_chunks * 4, s) || dev_h2d(c->d_active.p, active.data() + g0, n_chunks, s);
+			bad |= dev_push(c, c->d_est.p, est.data() + g0, n_chunks * 4, s) || dev_push(c, c->d_active.p, active.data() + g0, n_chunks, s);
 			if (paired) { bad |= dev_zero(&db->rwin, 8, s); launch_pair(a, n_pairs, s); launch_rescue(a, n_pairs, s); } else launch_single(a, n, s);
 			if (first_attempt) ev_record(&c->ev[EV_PAIR1], s);
 			first_attempt = false;
