@@ -45,9 +45,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GENOME_LEN = 248_956_422
-READ_LEN = 150
+READ_LEN = 150               # set from the chosen config in main()
 FULL_PAIRS = 10_000_000
 BATCH_PAIRS = 2_000_000
+# GRCh38 primary assembly, chr1..22, X, Y (configs[3] / configs[4]: "24 contigs with GRCh38 primary lengths")
+GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422, 135086622, 133275309,
+          114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+# BASELINE.json configs the bench can run.  2 is the default (the driver's BENCH / SCALE lines); 3 and 4 are the GRCh38-sized
+# runs (text of 6.2 G symbols: 64-bit rows, the wide index layout), committed as logs under profiles/.
+CONFIGS = {
+    2: dict(name="configs[2]: chr1-sized", genome=GENOME_LEN, contigs=None, read_len=150, ksw2=0, frag_mean=450, small_indel=100, large_indel=0, read_indel=0.0),
+    3: dict(name="configs[3]: GRCh38-sized", genome=sum(GRCH38), contigs=GRCH38, read_len=150, ksw2=0, frag_mean=450, small_indel=100, large_indel=0, read_indel=0.0),
+    4: dict(name="configs[4]: GRCh38-sized, ksw2 stress", genome=sum(GRCH38), contigs=GRCH38, read_len=250, ksw2=1, frag_mean=600, small_indel=2000, large_indel=500, read_indel=0.4),
+}
+CFG = CONFIGS[2]
 SIM_BLOCK = 250_000          # simulate_pairs_fast generates independent blocks of this many pairs
 CHECK_PAIRS = 500_000        # per rank, for the N-GPU == 1-GPU profile check
 
@@ -55,25 +66,38 @@ CHECK_PAIRS = 500_000        # per rank, for the N-GPU == 1-GPU profile check
 def make_genome(genome_len: int):
     from mapcaller_b200 import simulate as sim
     g = sim.genome(genome_len, 13, n_dup=2000 if genome_len > 50_000_000 else 200, repeat_frac=0.15)
-    mut, _ = sim.mutate(g, 14, snp_per_mb=1000, small_indel_per_mb=100, large_indel_per_mb=0, sv_per_mb=0)
+    if genome_len > 1_000_000_000 or CFG["ksw2"]:      # the vectorised variant of the same model (no per-event Python loop)
+        mut = sim.mutate_fast(g, 14, snp_per_mb=1000, small_indel_per_mb=CFG["small_indel"], large_indel_per_mb=CFG["large_indel"])
+    else:
+        mut, _ = sim.mutate(g, 14, snp_per_mb=1000, small_indel_per_mb=CFG["small_indel"], large_indel_per_mb=CFG["large_indel"], sv_per_mb=0)
     return g, mut
 
 
 def make_reads(mut, n_pairs: int, rank: int, first_block: int = 0):
     from mapcaller_b200 import simulate as sim
-    return sim.simulate_pairs_fast(mut, n_pairs, READ_LEN, seed=15 + 1000 * rank, frag_mean=450, frag_sd=50, sub_rate=0.003,
-                                   block=SIM_BLOCK, first_block=first_block)
+    return sim.simulate_pairs_fast(mut, n_pairs, READ_LEN, seed=15 + 1000 * rank, frag_mean=CFG["frag_mean"], frag_sd=50, sub_rate=0.003,
+                                   block=SIM_BLOCK, first_block=first_block, indel_read_frac=CFG["read_indel"])
+
+
+def contig_lengths(genome_len: int):
+    """The contig table of the chosen config, rescaled when --genome overrides the size (None = one contig)."""
+    if not CFG["contigs"]:
+        return None, None
+    lens = [int(x * genome_len / CFG["genome"]) for x in CFG["contigs"]]
+    lens[-1] += genome_len - sum(lens)
+    return lens, ["chr%s" % (i + 1 if i < 22 else "XY"[i - 22]) for i in range(len(lens))]
 
 
 def build_index(g, device):
     from mapcaller_b200 import api, simulate as sim
     codes = sim.encode(g)
+    lens, names = contig_lengths(len(g))
     if device is not None:
         try:
-            return api.Index.build(codes, gpu_device=device), "mc_index_build_gpu"
-        except api.McError:
-            pass
-    return api.Index.build(codes), "mc_index_build (host)"
+            return api.Index.build(codes, chrom_len=lens, chrom_name=names, gpu_device=device), "mc_index_build_gpu"
+        except api.McError as e:
+            print("[bench] GPU index build failed, host build instead: %s" % e, file=sys.stderr)
+    return api.Index.build(codes, chrom_len=lens, chrom_name=names), "mc_index_build (host)"
 
 
 class ClockSampler:
@@ -222,22 +246,26 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=FULL_PAIRS, help="library size per GPU (default: the config's 10 M pairs)")
-    ap.add_argument("--genome", type=int, default=GENOME_LEN, help="genome size in bp (default: the config's 248,956,422)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[] index (default 2: chr1-sized, 2x150, nw)")
+    ap.add_argument("--pairs", type=int, default=FULL_PAIRS, help="library size per GPU (default: 10 M pairs)")
+    ap.add_argument("--genome", type=int, default=0, help="genome size in bp (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (default: sized for ~10-30 s)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM flavour of the end-to-end leg")
     ap.add_argument("--trace-e2e", action="store_true", help="print a host-side timeline of one end-to-end step to stderr")
     ap.add_argument("--resident-only", action="store_true", help="profiling runs: only the resident leg (the JSON line then has no e2e)")
     args = ap.parse_args()
+    global CFG, READ_LEN
+    CFG = CONFIGS[args.config]; READ_LEN = CFG["read_len"]
+    args.genome = args.genome or CFG["genome"]
     args.pairs -= args.pairs % SIM_BLOCK
     assert args.pairs >= SIM_BLOCK, "--pairs must be at least %d" % SIM_BLOCK
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     n_batches = (args.pairs + BATCH_PAIRS - 1) // BATCH_PAIRS
-    config = {"workload": "configs[2]: chr1-sized %d bp synthetic reference (15 %% repeat families), 2x%d bp simulated PE reads, %d pairs per GPU in batches of %d, -alg nw, VCF profile on"
-                          % (args.genome, READ_LEN, args.pairs, min(BATCH_PAIRS, args.pairs)),
-              "genome_bp": args.genome, "read_len": READ_LEN, "pairs_per_gpu": args.pairs, "batch_pairs": min(BATCH_PAIRS, args.pairs), "alg": "nw",
+    config = {"workload": "%s %d bp synthetic reference (%s, 15 %% repeat families), 2x%d bp simulated PE reads, %d pairs per GPU in batches of %d, -alg %s, VCF profile on"
+                          % (CFG["name"], args.genome, "24 contigs" if CFG["contigs"] else "one contig", READ_LEN, args.pairs, min(BATCH_PAIRS, args.pairs), "ksw2" if CFG["ksw2"] else "nw"),
+              "genome_bp": args.genome, "read_len": READ_LEN, "pairs_per_gpu": args.pairs, "batch_pairs": min(BATCH_PAIRS, args.pairs), "alg": "ksw2" if CFG["ksw2"] else "nw",
               "parallelism": "reads sharded over %d GPU(s) in file order (one library: avgDist / dedup gate / discordant-pair state exchanged over NCCL inside every batch, profile reduced at the end of the pass), full index replica per GPU" % world
                              if world > 1 else "one GPU, one index replica",
               "l2_policy": "inputs larger than L2: index %.2f GB + %.1f GB of reads per batch stream from HBM" % (args.genome * 1.5 / 1e9, 2 * min(BATCH_PAIRS, args.pairs) * READ_LEN / 1e9)}
@@ -275,10 +303,14 @@ def main():
     t_setup = time.perf_counter()
     g, mut = make_genome(args.genome)
     ix, index_how = build_index(g, local)
+    del g
     t_index = time.perf_counter() - t_setup
     r1, r2 = make_reads(mut, args.pairs, rank)
     n_pairs = len(r1)
-    ctx = api.Context(ix, paired=1, alg_ksw2=0, update_profile=1, want_alignments=0, device=local, shard_rank=rank, shard_count=world)
+    big = args.genome > 1_000_000_000     # GRCh38-sized: a second context (102 GB of profile) does not fit beside the first
+    if big or world == 1:
+        del mut
+    ctx = api.Context(ix, paired=1, alg_ksw2=CFG["ksw2"], update_profile=1, want_alignments=0, device=local, shard_rank=rank, shard_count=world)
     if dist is not None:
         # the library's own NCCL communicator (NVLink / NVSwitch): ordered exchange inside the batches + profile reduction
         uid = [api.Context.comm_unique_id() if rank == 0 else None]
@@ -422,12 +454,14 @@ def main():
     # ---- N GPUs on one library == one GPU on the same reads (bit-exact profile and totals) ----
     check = {"mapped_fraction": totals["total_mapped"] / max(1, totals["total_reads"]), "avg_dist": totals["avg_dist"],
              "fastq_path_equals_resident": bool(e2e_fp == resident_fp and e2e_totals == totals), "variant_records": int(n_var)}
-    if dist is not None:
+    if dist is not None and big:
+        check["n_gpu_equals_1_gpu"] = "not run: the single-GPU control context does not fit beside a GRCh38-sized profile"
+    elif dist is not None:
         cseq, coff = sim.interleave(chk1, chk2)
         ctx.reset(); ctx.map_batch(cseq, coff, copy=False); ctx.profile_allreduce()
         multi_fp, multi_tot = ctx.profile_checksum(), ctx.totals()
         if rank == 0:
-            solo = api.Context(ix, paired=1, alg_ksw2=0, update_profile=1, want_alignments=0, device=local)
+            solo = api.Context(ix, paired=1, alg_ksw2=CFG["ksw2"], update_profile=1, want_alignments=0, device=local)
             for r in range(world):
                 a1, a2 = (chk1, chk2) if r == 0 else make_reads(mut, CHECK_PAIRS, r)
                 s_, o_ = sim.interleave(a1, a2)

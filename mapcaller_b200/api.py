@@ -228,6 +228,13 @@ class Index:
         _check(lib().mc_index_get(self._h, C.byref(v)), "mc_index_get")
         return v
 
+    def view_arrays(self) -> dict:
+        """The arrays of the image as numpy views (valid while the index lives): bwt words, sampled SA, pac bytes."""
+        v = self.view()
+        return dict(primary=int(v.primary), L2=[int(x) for x in v.L2], seq_len=int(v.seq_len),
+                    bwt=_view(v.bwt, int(v.bwt_size), np.dtype("<u4")), sa=_view(v.sa, int(v.n_sa), np.dtype("<u8")),
+                    pac=_view(v.pac, int(v.genome_size // 4 + 1), np.dtype("u1")))
+
     @property
     def genome_size(self) -> int:
         return self.view().genome_size

@@ -27,11 +27,12 @@
 #include <functional>
 #include <array>
 #include <vector>
+#include <chrono>
 
 void mc_set_error(const char* fmt, ...);
 #ifndef MC_HOSTEMU
-// index_gpu.cu: suffix array of the packed text by prefix doubling on the GPU
-extern "C" int mc_gpu_suffix_sort(const uint64_t* words, size_t n_words, int64_t n, int device, uint32_t* sa_out);
+// index_gpu.cu: BWT symbols by row, `primary` and the sampled suffix array of the packed text, sorted in chunks on the GPU
+extern "C" int mc_gpu_bwt_build(const uint64_t* words, size_t n_words, int64_t n, int device, uint64_t* rowsym_out, uint64_t* primary_out, uint64_t* samples_out);
 #endif
 
 struct mc_index {
@@ -145,6 +146,13 @@ template <class IdxT>
 int build_core(mc_index* ix, const uint8_t* fwd, int64_t G, int n_threads)
 {
 	const int64_t N = 2 * G;
+	const bool verbose = getenv("MC_DEBUG") != nullptr;
+	auto t_last = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		const auto now = std::chrono::steady_clock::now();
+		if (verbose) fprintf(stderr, "[mc] index build: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+		t_last = now;
+	};
 	PackedText t; t.n = N; t.w.assign((N + 31) / 32 + 2, 0);
 	if (n_threads < 1) n_threads = 1;
 	// every helper below cuts its index range into n_threads contiguous pieces
@@ -180,35 +188,43 @@ int build_core(mc_index* ix, const uint8_t* fwd, int64_t G, int n_threads)
 		for (auto& c : cnt) for (int k = 0; k < 4; k++) L2[k + 1] += c[k];
 	}
 	for (int c = 0; c < 4; c++) L2[c + 1] += L2[c];
+	lap("packed text");
 
+	// rows: 0 = empty suffix, r >= 1 = sa[r-1].  BWT symbol of row r = text[pos-1]; the row with pos == 0 is `primary`.
 	std::vector<IdxT> sa;
+	PackedText rowsym; rowsym.n = 0;                 // GPU path: symbol of row S + 1 at S, no suffix array on the host at all
+	uint64_t primary = 0;
+	const uint64_t n_sa = ((uint64_t)N + 32) / 32;
+	ix->sa_store.assign(n_sa, 0);
 #ifndef MC_HOSTEMU
-	if (g_sort_device >= 0 && sizeof(IdxT) == 4)
+	if (g_sort_device >= 0)
 	{
-		sa.resize(N);
-		int rc = mc_gpu_suffix_sort(t.w.data(), t.w.size(), N, g_sort_device, (uint32_t*)sa.data());
+		rowsym.n = N; rowsym.w.assign((N + 31) / 32, 0);
+		int rc = mc_gpu_bwt_build(t.w.data(), t.w.size(), N, g_sort_device, rowsym.w.data(), &primary, ix->sa_store.data());
 		if (rc != MC_OK) return rc;
 	}
 	else
 #endif
-	sort_suffixes<IdxT>(t, sa, n_threads);
+	{
+		sort_suffixes<IdxT>(t, sa, n_threads);
+		std::vector<uint64_t> found((size_t)n_threads, 0);
+		parallel(N, [&](int tid, int64_t r0, int64_t r1) { for (int64_t r = r0; r < r1; r++) if (sa[r] == 0) found[tid] = (uint64_t)r + 1; });
+		for (uint64_t f : found) if (f) primary = f;
+		ix->sa_store[0] = (uint64_t)-1;
+		for (uint64_t j = 1; j < n_sa; j++) ix->sa_store[j] = (uint64_t)sa[j * 32 - 1];
+	}
 
-	// rows: 0 = empty suffix, r >= 1 = sa[r-1].  BWT symbol of row r = text[pos-1]; the row with pos == 0 is `primary`.
+	lap(g_sort_device >= 0 ? "rows sorted (GPU)" : "suffixes sorted (host)");
 	const uint64_t n_occ = (uint64_t)(N + 127) / 128 + 1;
 	ix->bwt_store.assign(((uint64_t)(N + 15) >> 4) + n_occ * 8, 0);
 	uint32_t* out = ix->bwt_store.data();
 	// the row that holds the whole text ($ in its BWT column) is skipped: symbol k of the BWT string belongs to row k
 	// below it and to row k + 1 from it on
-	uint64_t primary = 0;
-	{
-		std::vector<uint64_t> found((size_t)n_threads, 0);
-		parallel(N, [&](int tid, int64_t r0, int64_t r1) { for (int64_t r = r0; r < r1; r++) if (sa[r] == 0) found[tid] = (uint64_t)r + 1; });
-		for (uint64_t f : found) if (f) primary = f;
-	}
+	const bool from_rows = rowsym.n > 0;
 	auto symbol = [&](uint64_t k) -> int {
 		if (k == 0) return t.base(N - 1);
 		const uint64_t r = k < primary ? k : k + 1;
-		return t.base((int64_t)sa[r - 1] - 1);
+		return from_rows ? rowsym.base((int64_t)r - 1) : t.base((int64_t)sa[r - 1] - 1);
 	};
 	// blocks of 128 symbols: 8 words of running counts, then 8 words of symbols; a last record of counts closes the string.
 	// Two passes over contiguous block ranges: symbol counts per range, then the ranges are written with their start counts.
@@ -246,13 +262,17 @@ int build_core(mc_index* ix, const uint8_t* fwd, int64_t G, int n_threads)
 		if (w + 8 != ix->bwt_store.size()) { mc_set_error("index build: inconsistent bwt size"); return MC_ERR_ARG; }
 	}
 
-	const uint64_t n_sa = ((uint64_t)N + 32) / 32;
-	ix->sa_store.assign(n_sa, 0);
-	ix->sa_store[0] = (uint64_t)-1;
-	for (uint64_t j = 1; j < n_sa; j++) ix->sa_store[j] = (uint64_t)sa[j * 32 - 1];
-
+	lap("bwt blocks");
 	ix->pac_store.assign((size_t)(G / 4 + 2), 0);
-	for (int64_t i = 0; i < G; i++) ix->pac_store[i >> 2] |= (uint8_t)((fwd[i] & 3) << ((~i & 3) << 1));
+	parallel((G + 3) / 4, [&](int, int64_t b0, int64_t b1) {
+		for (int64_t k = b0; k < b1; k++)
+		{
+			uint8_t v = 0;
+			for (int64_t i = 4 * k; i < std::min<int64_t>(G, 4 * k + 4); i++) v |= (uint8_t)((fwd[i] & 3) << ((~i & 3) << 1));
+			ix->pac_store[k] = v;
+		}
+	});
+	lap("pac");
 	finish_view(ix, primary, L2, (uint64_t)N, G);
 	return MC_OK;
 }
@@ -291,7 +311,7 @@ int mc_index_build_gpu(const uint8_t* fwd_codes, int64_t genome_size, int32_t n_
 #ifdef MC_HOSTEMU
 	mc_set_error("no GPU in the developer harness"); return MC_ERR_CUDA;
 #else
-	if (genome_size <= 0 || 2 * genome_size >= (1ll << 32) - 2) { mc_set_error("mc_index_build_gpu: texts of 2^32 symbols and more are sorted on the host (mc_index_build)"); return MC_ERR_ARG; }
+	if (genome_size <= 0 || 2 * genome_size >= (1ll << 34)) { mc_set_error("mc_index_build_gpu: texts of 2^34 symbols and more are sorted on the host (mc_index_build)"); return MC_ERR_ARG; }
 	if (device < 0) { mc_set_error("mc_index_build_gpu: bad device"); return MC_ERR_ARG; }
 	g_sort_device = device;
 	const int rc = mc_index_build(fwd_codes, genome_size, n_chrom, chrom_len, chrom_name, 0, out);   // host threads for packing and the BWT string

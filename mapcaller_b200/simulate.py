@@ -131,6 +131,35 @@ def mutate(g: np.ndarray, seed: int, snp_per_mb: float = 3000, small_indel_per_m
     return np.concatenate(pieces), truth
 
 
+def mutate_fast(g: np.ndarray, seed: int, snp_per_mb: float = 1000, small_indel_per_mb: float = 100, large_indel_per_mb: float = 0) -> np.ndarray:
+    """SNPs and indels at the rates of mutate(), vectorised for genomes of gigabases (no structural variants, no truth
+    list): complement-base SNPs in place, then every indel site either loses the `len` bases after it or gains `len`
+    random bases before it (small: 1 + geometric, capped at 10; large: 11-30); sites closer than 64 bases are thinned."""
+    rng = np.random.default_rng(seed)
+    n = len(g); mb = n / 1e6
+    out = g.copy()
+    snp = rng.integers(0, n, size=rng.poisson(snp_per_mb * mb))
+    out[snp] = _COMP[out[snp]]
+    n_small, n_large = rng.poisson(small_indel_per_mb * mb), rng.poisson(large_indel_per_mb * mb)
+    pos = rng.integers(100, n - 100, size=n_small + n_large)
+    ln = np.concatenate([np.minimum(10, rng.geometric(0.5, size=n_small)), rng.integers(11, 31, size=n_large)]).astype(np.int64)
+    order = np.argsort(pos, kind="stable"); pos, ln = pos[order], ln[order]
+    keep = np.concatenate([[True], np.diff(pos) > 64]); pos, ln = pos[keep], ln[keep]
+    is_del = rng.random(len(pos)) < 0.5
+    dpos, dlen = pos[is_del], ln[is_del]
+    mask = np.ones(n, dtype=bool)
+    if len(dpos):
+        idx = np.repeat(dpos, dlen) + (np.arange(int(dlen.sum())) - np.repeat(np.cumsum(dlen) - dlen, dlen))
+        mask[idx] = False
+    ipos, ilen = pos[~is_del], ln[~is_del]
+    if len(ipos):
+        ins_at = np.repeat(ipos, ilen)
+        bases = _ACGT[rng.integers(0, 4, size=len(ins_at), dtype=np.uint8)]
+        # np.insert works on the pre-deletion coordinates; flag the inserted bases as kept
+        out = np.insert(out, ins_at, bases); mask = np.insert(mask, ins_at, True)
+    return out[mask]
+
+
 def simulate_pairs(g: np.ndarray, n_pairs: int, read_len: int, seed: int, frag_mean: float = 400, frag_sd: float = 40,
                    sub_rate: float = 0.005, indel_rate: float = 0.0, n_rate: float = 0.0):
     """Returns (r1, r2): two uint8 arrays [n_pairs, read_len] of ASCII bases, mates as a sequencer
@@ -249,12 +278,15 @@ def fastq_text(reads: np.ndarray, mate: int, prefix: str = "r", first: int = 0) 
 
 
 def simulate_pairs_fast(g: np.ndarray, n_pairs: int, read_len: int, seed: int, frag_mean: float = 400, frag_sd: float = 40,
-                        sub_rate: float = 0.005, block: int = 250_000, first_block: int = 0):
-    """The same read model as simulate_pairs() without indel / N errors, for libraries of millions of pairs: generated in
+                        sub_rate: float = 0.005, block: int = 250_000, first_block: int = 0, indel_read_frac: float = 0.0):
+    """The same read model as simulate_pairs() without N errors, for libraries of millions of pairs: generated in
     independent blocks of `block` pairs (block b depends on (seed, b) only, so any prefix or slice of a library can be
-    regenerated), rows gathered through a strided window view, substitution sites drawn by count instead of a mask."""
+    regenerated), rows gathered through a strided window view, substitution sites drawn by count instead of a mask.
+    indel_read_frac: this fraction of the reads carries ONE sequencing indel (1-3 bases inserted or deleted at a random
+    offset; the vectorised stand-in for simulate_pairs()'s per-base indel errors)."""
     n = len(g)
-    win = np.lib.stride_tricks.sliding_window_view(g, read_len)
+    pad = 4 if indel_read_frac > 0 else 0
+    win = np.lib.stride_tricks.sliding_window_view(g, read_len + pad)
     r1 = np.empty((n_pairs, read_len), dtype=np.uint8); r2 = np.empty((n_pairs, read_len), dtype=np.uint8)
     for b0 in range(0, n_pairs, block):
         m = min(block, n_pairs - b0)
@@ -262,8 +294,12 @@ def simulate_pairs_fast(g: np.ndarray, n_pairs: int, read_len: int, seed: int, f
         flen = np.clip(np.rint(rng.normal(frag_mean, frag_sd, size=m)), read_len + 10, None).astype(np.int64)
         flen = np.minimum(flen, n - 1)
         start = (rng.random(m) * (n - flen)).astype(np.int64)
+        flen = np.minimum(flen, n - 1 - pad)
+        start = np.minimum(start, n - flen - pad)
         left = win[start]
-        right = _COMP[win[np.maximum(start + flen - read_len, 0)][:, ::-1]]
+        right = _COMP[win[np.maximum(start + flen - read_len - pad, 0)][:, ::-1]]
+        if pad:
+            left, right = _one_indel_per_read(left, read_len, indel_read_frac, rng), _one_indel_per_read(right, read_len, indel_read_frac, rng)
         flip = rng.random(m) < 0.5
         a = np.where(flip[:, None], right, left); c = np.where(flip[:, None], left, right)
         for r in (a, c):
@@ -274,6 +310,25 @@ def simulate_pairs_fast(g: np.ndarray, n_pairs: int, read_len: int, seed: int, f
                 flat[pos] = _ACGT[(_CODE[flat[pos]] + rng.integers(1, 4, size=k, dtype=np.uint8)) & 3]
         r1[b0:b0 + m] = a; r2[b0:b0 + m] = c
     return r1, r2
+
+
+def _one_indel_per_read(rows: np.ndarray, read_len: int, frac: float, rng) -> np.ndarray:
+    """rows [m, read_len + pad]: a fraction of the rows gets 1-3 bases deleted or inserted at a random offset (index
+    arithmetic on the padded window, no per-row loop); returns [m, read_len]."""
+    m = rows.shape[0]
+    hit = rng.random(m) < frac
+    at = rng.integers(10, read_len - 10, size=m); ln = rng.integers(1, 4, size=m); dele = rng.random(m) < 0.5
+    j = np.arange(read_len, dtype=np.int32)[None, :]
+    shift = np.where(hit & dele, ln, np.where(hit & ~dele, -ln, 0)).astype(np.int32)[:, None]
+    a = at.astype(np.int32)[:, None]
+    # deletion: columns from `at` on read ln bases further right; insertion: columns at..at+ln-1 are new bases, later ones shift left
+    src = np.where(j >= a, np.where(shift < 0, np.maximum(j + shift, a), j + shift), j)
+    out = np.take_along_axis(rows, src.astype(np.int64), axis=1)
+    new = (hit & ~dele)[:, None] & (j >= a) & (j < a + ln[:, None])
+    k = int(new.sum())
+    if k:
+        out[new] = _ACGT[rng.integers(0, 4, size=k, dtype=np.uint8)]
+    return out
 
 
 def write_fastq(path: str, reads: np.ndarray, mate: int, prefix: str = "r") -> None:

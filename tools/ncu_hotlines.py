@@ -1,8 +1,9 @@
 """Top source lines of a kernel by warp-stall samples from an .ncu-rep captured with --import-source on (-lineinfo build).
-usage: python tools/ncu_hotlines.py <file.ncu-rep> [N]"""
+usage: python tools/ncu_hotlines.py <file.ncu-rep> [N] [kernel regex] [launch index among the matches]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+sel = (["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []) + (["--launch-skip", sys.argv[4], "-c", "1"] if len(sys.argv) > 4 else [])
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 data = []; path = None; hdr = None
 for r in rows:
