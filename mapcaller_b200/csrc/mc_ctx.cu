@@ -778,6 +778,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		c->chunks_final.assign(NG, mc_chunk_out());
 		int64_t first_open = 0;
 		int replays = 0; bool overflow = false, first_attempt = true;
+		mc_u64 ovf_all = 0;                    // ordered exchange: OR of every rank's overflow word, so that all ranks leave together
 		Bumps* hbp = (Bumps*)(h_small + 64);   // pinned copy of the arena cursors, refreshed at the end of every attempt
 		memset(hbp, 0, sizeof(Bumps));
 		ev_record(&c->ev[EV_PAIR0], s);
@@ -810,7 +811,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 				mc_u64 any = 0;
 				if (ordered_chunks(c, od, g_hc, g_lo, g_hi, &any)) return MC_ERR_NCCL;
 				hc = g_hc.data(); lo = g_lo.data(); hi = g_hi.data();
-				if (any) { overflow = true; break; }      // every rank repeats the batch (each grows only what it ran out of)
+				if (any) { overflow = true; ovf_all = any; break; }      // every rank repeats the batch (each grows only what it ran out of)
 			}
 #endif
 			if (hst->overflow) { overflow = true; break; }
@@ -854,13 +855,14 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		if (overflow)
 		{
 			const mc_u64 ovf = ((DevStats*)(h_small + 8))->overflow;
+			const mc_u64 fatal = ovf | ovf_all;       // a fatal bit on ANY rank ends the collective call on every rank with the same code
 			if ((ovf >> 0) & 0xFF) c->rescue_cap *= 4;
 			if ((ovf >> 8) & 0xFF) c->frag_factor *= 2;
 			if ((ovf >> 16) & 0xFF) c->aln_factor *= 2;
 			if ((ovf >> 24) & 0xFF) c->task_factor *= 2;
 			if ((ovf >> 32) & 0xFF) c->dpws_factor *= 4;
-			if ((ovf >> 56) & 0xFF) { mc_set_error("mc_map_batch: a read is longer than %d bases (or the offsets decrease)", MC_MAX_RLEN); dev_zero(c->d_stats.p, sizeof(DevStats), s); return MC_ERR_ARG; }
-			if ((ovf >> 40) & 0xFF) { mc_set_error("mc_map_batch: internal error: candidate table overflow"); return MC_ERR_OVERFLOW; }
+			if ((fatal >> 56) & 0xFF) { mc_set_error("mc_map_batch: a read is longer than %d bases (or the offsets decrease)%s", MC_MAX_RLEN, ((ovf >> 56) & 0xFF) ? "" : " on another rank"); dev_zero(c->d_stats.p, sizeof(DevStats), s); return MC_ERR_ARG; }
+			if ((fatal >> 40) & 0xFF) { mc_set_error("mc_map_batch: internal error: candidate table overflow%s", ((ovf >> 40) & 0xFF) ? "" : " on another rank"); return MC_ERR_OVERFLOW; }
 			if (c->frag_factor > 4096 || c->aln_factor > 4096 || c->task_factor > 4096 || c->dpws_factor > 65536) { mc_set_error("mc_map_batch: arena overflow persists"); return MC_ERR_OVERFLOW; }
 			if (getenv("MC_DEBUG")) fprintf(stderr, "[mc] arena overflow %llx: now frag x%.0f aln x%.0f task x%.0f dpws x%.0f rescue %lld\n", (unsigned long long)ovf, c->frag_factor, c->aln_factor, c->task_factor, c->dpws_factor, (long long)c->rescue_cap);
 			bad |= dev_zero(&c->d_stats.as<DevStats>()->locate_blocks, sizeof(DevStats) - 3 * sizeof(mc_u64), s); // keep only the seed kernel's counters
@@ -1719,6 +1721,14 @@ int mc_comm_init(mc_ctx* c, const uint8_t* id_bytes, int32_t rank, int32_t n_ran
 
 __global__ void mc_seqoff_kernel(mc_indel_rec* r, int64_t n, int32_t add)
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) r[i].seq_off += add; }
+// independent shards: each 16-bit half clamped to the reference's MaxAlleleCount before the sum (n ranks x 4095 fits 16 bits for n <= 16)
+__global__ void mc_clamp_base16_kernel(uint32_t* p, int64_t n)
+{
+	int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t v = p[i], lo = v & 0xFFFFu, hi = v >> 16;
+	if (lo > 4095u || hi > 4095u) p[i] = (lo > 4095u ? 4095u : lo) | ((hi > 4095u ? 4095u : hi) << 16);
+}
 __global__ void mc_clamp_u8_kernel(uint8_t* p, int64_t n, int hi)
 { int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n && p[i] > hi) p[i] = (uint8_t)hi; }
 
@@ -1744,13 +1754,20 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	long long* d_tot = c->d_comm_small.as<long long>() + 6 * c->comm_size + 8;
 	long long t[5] = {c->tot.total_reads, c->tot.total_mapped, c->tot.total_paired, c->tot.total_distance, c->tot.read_length_sum};
 	if (dev_h2d(d_tot, t, sizeof(t), s)) return MC_ERR_CUDA;
+	const bool independent = !ordered_mode(c) || comm != c->comm;   // with the ordered exchange readCount and the totals already are the library's
+	if (independent)
+	{
+		// without the global dedup gate every shard may hold up to 15 x 4000 per column: the sum of the 16-bit halves could carry
+		// into the neighbouring base and the uint8 readCount sum could wrap; the read-out clamps at 4095 / max_dup anyway
+		if (c->comm_size > 16) { mc_set_error("mc_profile_allreduce: independent shards are limited to 16 ranks (packed 16-bit counters)"); return MC_ERR_ARG; }
+		mc_clamp_base16_kernel<<<(unsigned)((G * 2 + 255) / 256), 256, 0, s>>>(c->d_base16.as<uint32_t>(), (int64_t)(G * 2));
+	}
 	nccl_api()->GroupStart();
 	// packed 2 x uint16 counters are summed as uint32 words: no carry can cross the halves while every column stays below 65536
 	bad |= nccl_fail(ncclAllReduce(c->d_base16.p, c->d_base16.p, G * 2, ncclUint32, ncclSum, comm, s), "ncclAllReduce(base16)");
 	bad |= nccl_fail(ncclAllReduce(c->d_sdiff.p, c->d_sdiff.p, (G + 1) * 4, ncclInt32, ncclSum, comm, s), "ncclAllReduce(sdiff)");
 	bad |= nccl_fail(ncclAllReduce(c->d_cdiff.p, c->d_cdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(cdiff)");
 	bad |= nccl_fail(ncclAllReduce(c->d_mdiff.p, c->d_mdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(mdiff)");
-	const bool independent = !ordered_mode(c) || comm != c->comm;   // with the ordered exchange readCount and the totals already are the library's
 	if (independent)
 	{
 		bad |= nccl_fail(ncclAllReduce(c->d_rcount.p, c->d_rcount.p, G, ncclUint8, ncclSum, comm, s), "ncclAllReduce(rcount)");

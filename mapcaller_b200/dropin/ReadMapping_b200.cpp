@@ -7,9 +7,11 @@
 // symbols the kept objects import from the replaced ones: Mapping(), CompByDiscordPos(),
 // avgDist, avgReadLength, BreakPointMap, InsertSeqMap, DeleteSeqMap, InversionSiteVec, TranslocationSiteVec.
 //
-// What stays on the host, unchanged and in file order: FASTQ/FASTA reading (GetNextChunk), ReverseOrientation of mate 2
-// for the SAM text, SAM generation (GeneratePairedSamStream / GenerateSingleSamStream) and everything after Mapping().
-// With MC_B200_DEVICE_SAM=1 the SAM fields come from the device (mc_sam_records) and only print_sam_line() runs here.
+// Plain FASTQ files never pass through the reference's reader: raw file blocks go to the device, which finds the records,
+// maps them and - with -sam - assembles the SAM text (mc_ingest_fastq / mc_map_staged / mc_sam_text).  .gz and FASTA input
+// still comes through the reference's GetNextChunk / gzGetNextChunk; its SAM lines are then made by the reference's
+// SamReport.o from the downloaded candidates, or - MC_B200_DEVICE_SAM=1 - printed from the device's record fields
+// (mc_sam_records).  Everything after Mapping() is the reference's, except IdentifyVariants (mc_variant_scan, see below).
 #include "structure.h"
 #include "mapcaller_b200.h"
 
@@ -19,9 +21,18 @@ map<int64_t, map<string, uint16_t> > InsertSeqMap, DeleteSeqMap;
 map<int64_t, uint16_t> BreakPointMap;
 uint32_t avgCov, avgReadLength, avgDist = 1000;
 int64_t iTotalReadNum = 0, iTotalMappingNum = 0, iTotalPairedNum = 0, iAlignedBase = 0, iTotalCoverage = 0, TotalPairedDistance = 0, ReadLengthSum = 0;
-extern float MaxMisMatchRate;
+extern float MaxMisMatchRate, FrequencyThr;
 
 bool CompByDiscordPos(const DiscordPair_t& p1, const DiscordPair_t& p2) { return p1.gPos < p2.gPos; }
+
+// IdentifyVariants (src/VariantCalling.cpp:550-680) - the reference's forced-single-thread scan over every column of
+// MappingRecordArr - is answered by mc_variant_scan on the device-resident profile: Mapping() runs the scan while the context
+// still exists and parks the records here; the Makefile weakens the symbol in the kept VariantCalling.o (objcopy
+// --weaken-symbol), so the unchanged VariantCalling() calls THIS definition and finds VariantVec filled.  Everything after
+// it (RemoveConsecutiveGenomicVariant, structural variants, filters, the VCF text) is the reference's own code.
+extern vector<Variant_t> VariantVec;
+static vector<Variant_t> g_scanned_variants;
+void* IdentifyVariants(void*) { VariantVec.swap(g_scanned_variants); return (void*)(1); }
 
 namespace {
 
@@ -150,7 +161,9 @@ void Mapping()
 		if (mc_begin_library(ctx)) die("mc_begin_library");   // every -f library restarts the 200-read chunk grid; profile, totals and avgDist carry over
 		// No SAM wanted and plain FASTQ on disk: nothing of the reference's reader is needed - raw file blocks go to the GPU, which
 		// finds the records itself (mc_ingest_fastq = GetNextEntry / GetNextChunk, src/GetData.cpp:32-99) and maps them.
-		if (!bSAMoutput && !lib.gz && FastQFormat)
+		// With -sam the lines are assembled on the device as well (mc_sam_text: QNAME / SEQ / QUAL from the FASTQ text kept in the
+		// slot, -m included) and written with one fwrite per batch; MC_B200_HOST_SAM=1 keeps the reference's reader + SamReport.o.
+		if (!lib.gz && FastQFormat && (!bSAMoutput || getenv("MC_B200_HOST_SAM") == NULL))
 		{
 			// MC_B200_FASTQ_BLOCK (bytes) overrides the 64 MiB block size - the tests use it to cross many block boundaries with small files
 			const size_t BLK = getenv("MC_B200_FASTQ_BLOCK") ? (size_t)atoll(getenv("MC_B200_FASTQ_BLOCK")) : (size_t)64 << 20;
@@ -169,6 +182,12 @@ void Mapping()
 				{
 					mc_batch_out out;
 					if (mc_map_staged(ctx, 0, &out)) die("mc_map_staged");
+					if (bSAMoutput)
+					{
+						const uint8_t* text; int64_t n_bytes;
+						if (mc_sam_text(ctx, 0, !bUnique, &text, &n_bytes)) die("mc_sam_text");
+						if (n_bytes > 0 && fwrite(text, 1, (size_t)n_bytes, sam_out) != (size_t)n_bytes) { fprintf(stderr, "\nError! cannot write %s\n", SamFileName); exit(1); }
+					}
 					mc_totals t; mc_get_totals(ctx, &t);
 					fprintf(stderr, "\r%lld %s reads have been processed in %lld seconds...", (long long)t.total_reads, (bPairEnd ? "paired-end" : "singled-end"), (long long)(time(NULL) - StartProcessTime));
 				}
@@ -245,6 +264,20 @@ void Mapping()
 				vector<DiscordPair_t>& dst = kind == 0 ? InversionSiteVec : TranslocationSiteVec;
 				for (int64_t i = 0; i < ns; i++) { DiscordPair_t d; d.gPos = sr[i].gPos; d.dist = sr[i].dist; dst.push_back(d); }
 				sort(dst.begin(), dst.end(), CompByDiscordPos);   // the thread-end sort of the reference (src/ReadMapping.cpp:629-630)
+			}
+			// IdentifyVariants on the device, parked for the kept VariantCalling() (see the top of this file)
+			mc_vc_params vp; mc_vc_params_default(&vp);
+			vp.min_allele_depth = MinAlleleDepth; vp.frequency_thr = FrequencyThr; vp.somatic = bSomatic; vp.gvcf = bGVCF; vp.monomorphic = bMonomorphic;
+			vp.ploidy = iPloidy; vp.min_cnv_size = MinCNVsize; vp.min_unmapped_size = MinUnmappedSize;
+			const mc_variant_rec* vr; int64_t nv, nblk; const uint8_t* alt; const int32_t* depth;
+			if (mc_variant_scan(ctx, &vp, &vr, &nv, &alt, &depth, &nblk)) die("mc_variant_scan");
+			g_scanned_variants.resize((size_t)nv);
+			for (int64_t i = 0; i < nv; i++)
+			{
+				Variant_t& v = g_scanned_variants[i];
+				v.gPos = vr[i].gPos; v.DP = vr[i].DP; v.AD_ref = vr[i].AD_ref; v.AD_alt = vr[i].AD_alt; v.GenoType = vr[i].GenoType; v.qscore = vr[i].qscore; v.VarType = vr[i].VarType;
+				if (vr[i].VarType == MC_VAR_INS || vr[i].VarType == MC_VAR_DEL) v.ALTstr.assign((const char*)alt + vr[i].alt_off, vr[i].alt_len);
+				else if (vr[i].VarType == MC_VAR_SUB) v.ALTstr.assign(vr[i].alt, strnlen(vr[i].alt, 3));
 			}
 		}
 		mc_ctx_destroy(ctx);

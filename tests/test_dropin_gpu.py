@@ -37,7 +37,11 @@ def vcf_body(path):
     return [l for l in open(path) if not (l.startswith("##command_line") or l.startswith("##reference") or l.startswith("##fileDate"))]
 
 
-@pytest.mark.parametrize("mode", ["pe_nw", "pe_ksw2_monomorphic", "se_nw", "pe_nw_vcfonly", "se_nw_vcfonly"])
+# pe_nw / pe_ksw2_monomorphic / se_nw / pe_nw_m: plain FASTQ, SAM text assembled on the device (mc_sam_text; _m = the reference's -m,
+# one line per best candidate); *_hostsam: MC_B200_HOST_SAM=1, the reference's reader + SamReport.o over the downloaded candidates;
+# *_gz: gzip'ed FASTQ (the reference's gz reader feeds mc_map_batch); *_vcfonly: no SAM.  In every mode the VCF comes from the
+# unchanged VariantCalling() with IdentifyVariants answered by mc_variant_scan.
+@pytest.mark.parametrize("mode", ["pe_nw", "pe_ksw2_monomorphic", "se_nw", "pe_nw_vcfonly", "se_nw_vcfonly", "pe_nw_m", "pe_nw_hostsam", "pe_nw_gz"])
 def test_same_sam_and_vcf_as_the_reference_cli(tmp_path, mode):
     case = pu.make_case(seed=41, n_pairs=6000, genome_len=120000, contigs=2, sv=3.0)
     fa = str(tmp_path / "ref.fa")
@@ -51,6 +55,17 @@ def test_same_sam_and_vcf_as_the_reference_cli(tmp_path, mode):
         extra += ["-alg", "ksw2"]
     if "monomorphic" in mode:
         extra += ["-monomorphic"]
+    if mode.endswith("_m"):
+        extra += ["-m"]
+    if mode.endswith("_gz"):
+        import gzip
+        for f in (f1, f2):
+            with open(f, "rb") as src, gzip.open(f + ".gz", "wb", compresslevel=1) as dst:
+                dst.write(src.read())
+        f1, f2 = f1 + ".gz", f2 + ".gz"
+    env = dict(os.environ)
+    if mode.endswith("_hostsam"):
+        env["MC_B200_HOST_SAM"] = "1"
     reads = ["-f", f1] + ([] if mode.startswith("se") else ["-f2", f2])
     outs = {}
     for tag, exe in (("ref", REF_BIN), ("gpu", GPU_BIN)):
@@ -58,7 +73,7 @@ def test_same_sam_and_vcf_as_the_reference_cli(tmp_path, mode):
         # without -sam the drop-in hands raw FASTQ blocks to the device parser (mc_ingest_fastq) instead of the reference's reader
         want_sam = "vcfonly" not in mode
         subprocess.check_call([exe, "-i", idx, "-t", "1"] + reads + (["-sam", sam] if want_sam else []) + ["-vcf", vcf, "-log", str(tmp_path / (tag + ".log"))] + extra,
-                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=str(tmp_path))
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=str(tmp_path), env=env)
         outs[tag] = (sam_records(sam, mode.startswith("se")) if want_sam else [], vcf_body(vcf))
     assert outs["gpu"][0] == outs["ref"][0], "SAM differs"
     assert outs["gpu"][1] == outs["ref"][1], "VCF differs"
