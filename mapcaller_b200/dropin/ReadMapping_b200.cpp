@@ -163,16 +163,36 @@ void Mapping()
 		// finds the records itself (mc_ingest_fastq = GetNextEntry / GetNextChunk, src/GetData.cpp:32-99) and maps them.
 		// With -sam the lines are assembled on the device as well (mc_sam_text: QNAME / SEQ / QUAL from the FASTQ text kept in the
 		// slot, -m included) and written with one fwrite per batch; MC_B200_HOST_SAM=1 keeps the reference's reader + SamReport.o.
-		if (!lib.gz && FastQFormat && (!bSAMoutput || getenv("MC_B200_HOST_SAM") == NULL))
+		// .gz FASTQ takes the same road: the two mate files are inflated block-wise by zlib (gzread, one host thread per file)
+		// and the device parses the inflated text - no per-line gzgets, no per-read allocation (gzGetNextEntry,
+		// src/GetData.cpp:101-131; its 1024-byte line buffer is the one difference: longer lines are not cut here).
+		if (FastQFormat && (!bSAMoutput || getenv("MC_B200_HOST_SAM") == NULL))
 		{
+			if (lib.gz) { gzbuffer(lib.g1, 1 << 20); if (lib.g2) gzbuffer(lib.g2, 1 << 20); }
+			auto read_block = [&lib](int which, uint8_t* dst, size_t n) -> size_t {
+				if (!lib.gz) return fread(dst, 1, n, which ? lib.f2 : lib.f1);
+				size_t got = 0;
+				while (got < n) { const int g = gzread(which ? lib.g2 : lib.g1, dst + got, (unsigned)std::min<size_t>(n - got, 1u << 30)); if (g <= 0) break; got += (size_t)g; }
+				return got;
+			};
 			// MC_B200_FASTQ_BLOCK (bytes) overrides the 64 MiB block size - the tests use it to cross many block boundaries with small files
 			const size_t BLK = getenv("MC_B200_FASTQ_BLOCK") ? (size_t)atoll(getenv("MC_B200_FASTQ_BLOCK")) : (size_t)64 << 20;
 			vector<uint8_t> b1, b2; size_t have1 = 0, have2 = 0; bool eof1 = false, eof2 = !lib.sep, force_final = false;
 			for (;;)
 			{
 				// a file that reached its end just stops growing; its carried-over records are still consumed block by block
-				if (!eof1) { b1.resize(have1 + BLK); size_t g = fread(b1.data() + have1, 1, BLK, lib.f1); have1 += g; eof1 = g < BLK; }
-				if (!eof2) { b2.resize(have2 + BLK); size_t g = fread(b2.data() + have2, 1, BLK, lib.f2); have2 += g; eof2 = g < BLK; }
+				size_t g2 = 0; pthread_t th2; bool threaded = false;
+				struct Job { decltype(read_block)* rd; uint8_t* dst; size_t n, got; } job = {&read_block, NULL, BLK, 0};
+				if (!eof2)
+				{
+					b2.resize(have2 + BLK); job.dst = b2.data() + have2;
+					// the second mate file is read (inflated) by a thread of its own while this one reads the first
+					threaded = !eof1 && pthread_create(&th2, NULL, [](void* p) -> void* { Job* j = (Job*)p; j->got = (*j->rd)(1, j->dst, j->n); return NULL; }, &job) == 0;
+					if (!threaded) g2 = read_block(1, job.dst, BLK);
+				}
+				if (!eof1) { b1.resize(have1 + BLK); size_t g = read_block(0, b1.data() + have1, BLK); have1 += g; eof1 = g < BLK; }
+				if (threaded) { pthread_join(th2, NULL); g2 = job.got; }
+				if (!eof2) { have2 += g2; eof2 = g2 < BLK; }
 				const bool last = (eof1 && eof2) || force_final;   // only then may a ragged tail (not a multiple of 200 reads) be mapped
 				mc_fastq_in fi; memset(&fi, 0, sizeof(fi));
 				fi.text1 = b1.data(); fi.len1 = (int64_t)have1; fi.text2 = lib.sep ? b2.data() : NULL; fi.len2 = (int64_t)have2; fi.final_block = last;
@@ -202,7 +222,7 @@ void Mapping()
 					if (eof1 ? left2 > left1 : left1 > left2) force_final = true;
 				}
 			}
-			fclose(lib.f1); if (lib.f2) fclose(lib.f2);
+			if (lib.gz) { gzclose(lib.g1); if (lib.g2) gzclose(lib.g2); } else { fclose(lib.f1); if (lib.f2) fclose(lib.f2); }
 			continue;
 		}
 		vector<ReadItem_t> reads; vector<uint8_t> seq; vector<int64_t> off; vector<string> sam;

@@ -102,7 +102,7 @@ def _case_files(tmp_path, seed=43, n_pairs=9000):
     return case, idx
 
 
-@pytest.mark.parametrize("layout", ["two_files", "single_end", "interleaved", "unequal_mates"])
+@pytest.mark.parametrize("layout", ["two_files", "single_end", "interleaved", "unequal_mates", "two_files_gz"])
 def test_fastq_block_reader_crosses_block_boundaries(tmp_path, layout):
     """The raw-FASTQ path of the drop-in reads the files in blocks (64 MiB; 40 kB here, so that a 2 MB library crosses ~50
     block boundaries): every read of a single-file library has to be mapped, mate files whose byte sizes differ (trimmed
@@ -119,6 +119,12 @@ def test_fastq_block_reader_crosses_block_boundaries(tmp_path, layout):
         reads = ["-f", f1, "-p"]
     else:
         sim.write_fastq(f1, r1, 1); sim.write_fastq(f2, r2, 2)
+        if layout.endswith("_gz"):           # inflated block by block (gzread), parsed on the device like plain text
+            import gzip
+            for f in (f1, f2):
+                with open(f, "rb") as src, gzip.open(f + ".gz", "wb", compresslevel=1) as dst:
+                    dst.write(src.read())
+            f1, f2 = f1 + ".gz", f2 + ".gz"
         reads = ["-f", f1] if layout == "single_end" else ["-f", f1, "-f2", f2]
     out = _run_both(tmp_path, idx, reads, env={"MC_B200_FASTQ_BLOCK": "40000"})
     assert out["gpu"] == out["ref"], "VCF differs"
