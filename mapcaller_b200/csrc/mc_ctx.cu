@@ -208,8 +208,9 @@ struct mc_ctx {
 	std::vector<mc_site_rec> inv_sites, tnl_sites;
 	// finalize products
 	std::vector<mc_indel_rec> ind_out; std::vector<uint8_t> ind_seq_out; std::vector<mc_breakpoint_rec> bp_out;
-	std::vector<mc_variant_rec> vc_out; std::vector<int32_t> vc_depth;
-	DBuf d_vc[12];   // scratch of mc_variant_scan, kept between calls
+
+	DBuf d_vc[18];   // scratch of mc_variant_scan, kept between calls
+	HBuf h_vc_out, h_vc_depth; int64_t n_vc_out = 0;   // its result in page-locked memory
 	DBuf d_ia[9]; HBuf h_ind_rec, h_ind_seq;   // scratch of mc_profile_indels
 	int64_t last_n = 0; const int64_t* last_roff = nullptr;   // the batch whose arenas are still on the device (mc_sam_records)
 	DBuf d_sam[5], d_chrom_names, d_chrom_name_off; HBuf h_sam_text; std::vector<mc_sam_rec> sam_out; std::vector<uint8_t> sam_cigar;
@@ -249,7 +250,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	for (DBuf* b : bufs) b->release();
 	for (DBuf& b : c->d_vc) b.release();
 	for (DBuf& b : c->d_ia) b.release();
-	c->h_ind_rec.release(); c->h_ind_seq.release();
+	c->h_ind_rec.release(); c->h_ind_seq.release(); c->h_vc_out.release(); c->h_vc_depth.release();
 	for (DBuf& b : c->d_sam) b.release();
 	c->d_chrom_names.release(); c->d_chrom_name_off.release(); c->h_sam_text.release();
 	std::vector<Staged*> st; st.push_back(&c->cur); for (int i = 0; i < MC_SLOTS; i++) st.push_back(&c->slots[i]);
@@ -1654,42 +1655,34 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	if (d_out.reserve((size_t)(total + 1) * sizeof(mc_variant_rec))) return done(MC_ERR_CUDA);
 	a.out = d_out.as<mc_variant_rec>();
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), true, s); }
-	std::vector<mc_variant_rec> raw((size_t)total);
-	c->vc_depth.resize((size_t)nvb);
-	if (dev_d2h(raw.data(), d_out.p, (size_t)total * sizeof(mc_variant_rec), s) || dev_d2h(c->vc_depth.data(), d_depth.p, (size_t)nvb * 4, s) || dev_sync(s)) return done(MC_ERR_CUDA);
-	mark("emit+d2h");
-	// CompByVarPos (src/VariantCalling.cpp:51-55); (gPos, VarType) is unique within one scan.  The slots are in column order
-	// except for gap / dup records, which are pushed where their run ends but carry its start: two sorted streams, one merge.
-	auto by_pos = [](const mc_variant_rec& x, const mc_variant_rec& y) { return x.gPos != y.gPos ? x.gPos < y.gPos : x.VarType < y.VarType; };
-	std::vector<mc_variant_rec> runs;
-	c->vc_out.clear(); c->vc_out.reserve(raw.size());
-	size_t n_main = 0;
-	for (size_t i = 0; i < raw.size(); i++)
-	{
-		if (raw[i].VarType == MC_VAR_NIL) continue;
-		if (raw[i].VarType == MC_VAR_UMR || raw[i].VarType == MC_VAR_CNV) runs.push_back(raw[i]); else raw[n_main++] = raw[i];
-	}
-	for (size_t i = 0; i < n_main;)   // one column pushes INS, DEL, SUB in that order: VarType 1, 2, 0
-	{
-		size_t j = i + 1;
-		while (j < n_main && raw[j].gPos == raw[i].gPos) j++;
-		if (j - i > 1) std::sort(raw.begin() + i, raw.begin() + j, by_pos);
-		i = j;
-	}
-	if (!std::is_sorted(raw.begin(), raw.begin() + n_main, by_pos)) std::sort(raw.begin(), raw.begin() + n_main, by_pos);
-	if (!std::is_sorted(runs.begin(), runs.end(), by_pos)) std::sort(runs.begin(), runs.end(), by_pos);
-	c->vc_out.resize(n_main + runs.size());
-	std::merge(raw.begin(), raw.begin() + n_main, runs.begin(), runs.end(), c->vc_out.begin(), by_pos);
+	mark("emit");
+	// CompByVarPos order on the device (mc_stages_vc.h: vckey_body), then ONE copy of the valid records into page-locked memory
+	if (total >= (int64_t)0xFFFFFFFFll) { mc_set_error("mc_variant_scan: more than 2^32 record slots (a monomorphic / gVCF scan of a genome this large does not fit)"); return done(MC_ERR_OVERFLOW); }
+	DBuf &d_vkey = c->d_vc[12], &d_vkey2 = c->d_vc[13], &d_vidx = c->d_vc[14], &d_vidx2 = c->d_vc[15], &d_vsort = c->d_vc[16], &d_out2 = c->d_vc[17];
+	if (d_vkey.reserve((size_t)(total + 1) * 8) || d_vkey2.reserve((size_t)(total + 1) * 8) || d_vidx.reserve((size_t)(total + 1) * 4) || d_vidx2.reserve((size_t)(total + 1) * 4)
+	    || d_vsort.reserve(device_sort_pairs_scratch_bytes(total))) return done(MC_ERR_CUDA);
+	mc_u64* d_nvalid = (mc_u64*)d_off.as<int64_t>() + (nvb + 1);   // d_off has nvb + 2 entries; the last one is free
+	int64_t n_valid = 0;
+	if (dev_zero(d_nvalid, 8, s)) return done(MC_ERR_CUDA);
+	launch_vckey(total, a.out, d_vkey.as<uint64_t>(), d_vidx.as<uint32_t>(), d_nvalid, s);
+	device_sort_pairs(d_vkey.as<uint64_t>(), d_vkey2.as<uint64_t>(), d_vidx.as<uint32_t>(), d_vidx2.as<uint32_t>(), total, d_vsort.p, d_vsort.cap, s);
+	if (dev_d2h(&n_valid, d_nvalid, 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	if (d_out2.reserve((size_t)(n_valid + 1) * sizeof(mc_variant_rec)) || c->h_vc_out.reserve((size_t)(n_valid + 1) * sizeof(mc_variant_rec)) || c->h_vc_depth.reserve((size_t)(nvb + 1) * 4)) return done(MC_ERR_CUDA);
+	launch_vcgather(n_valid, a.out, d_vidx.as<uint32_t>(), d_out2.as<mc_variant_rec>(), s);
+	if (dev_d2h(c->h_vc_out.p, d_out2.p, (size_t)n_valid * sizeof(mc_variant_rec), s) || dev_d2h(c->h_vc_depth.p, d_depth.p, (size_t)nvb * 4, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	mark("order+d2h");
+	mc_variant_rec* vo = c->h_vc_out.as<mc_variant_rec>();
 	if (a.vp.gvcf)   // RemoveConsecutiveGenomicVariant (:682-694)
 	{
-		size_t w = 0;
-		for (size_t i = 0; i < c->vc_out.size(); i++)
-			if (!(w > 0 && c->vc_out[w - 1].VarType == MC_VAR_NOR && c->vc_out[i].VarType == MC_VAR_NOR)) c->vc_out[w++] = c->vc_out[i];
-		c->vc_out.resize(w);
+		int64_t w = 0;
+		for (int64_t i = 0; i < n_valid; i++)
+			if (!(w > 0 && vo[w - 1].VarType == MC_VAR_NOR && vo[i].VarType == MC_VAR_NOR)) vo[w++] = vo[i];
+		n_valid = w;
 	}
-	*recs = c->vc_out.data(); *n_recs = (int64_t)c->vc_out.size(); *alt_arena = c->ind_seq_out.data();
-	*block_depth = c->vc_depth.data(); *n_blocks = nvb;
-	mark("sort");
+	c->n_vc_out = n_valid;
+	*recs = vo; *n_recs = n_valid; *alt_arena = c->ind_seq_out.data();
+	*block_depth = c->h_vc_depth.as<int32_t>(); *n_blocks = nvb;
+	mark("gvcf");
 	return done(MC_OK);
 }
 

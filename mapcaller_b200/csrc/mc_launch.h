@@ -55,6 +55,8 @@ static void launch_fqcopy(const FastqArgs& q, int64_t n, mc_stream_t) { for (int
 static void launch_bwtsearch(const SearchArgs& a, int64_t n, mc_stream_t) { for (int64_t q = 0; q < n; q++) bwtsearch_body(q, a); }
 static void launch_vcdepth(const VcArgs& a, int64_t b0, int64_t b1, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcdepth_body(b, a); }
 static void launch_vcscan(const VcArgs& a, int64_t b0, int64_t b1, bool emit, mc_stream_t) { for (int64_t b = b0; b < b1; b++) vcscan_body(b, a, emit); }
+static void launch_vckey(int64_t n, const mc_variant_rec* recs, uint64_t* keys, uint32_t* idx, mc_u64* n_valid, mc_stream_t) { for (int64_t i = 0; i < n; i++) vckey_body(i, recs, keys, idx, n_valid); }
+static void launch_vcgather(int64_t n, const mc_variant_rec* in, const uint32_t* idx, mc_variant_rec* out, mc_stream_t) { for (int64_t j = 0; j < n; j++) vcgather_body(j, in, idx, out); }
 static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t) { for (int64_t r = 0; r < n; r++) samrec_body(r, a, emit); }
 static void launch_samtext(const SamTextArgs& t, int64_t n, bool emit, mc_stream_t) { for (int64_t r = 0; r < n; r++) samtext_body(r, t, emit); }
 static void device_incmax_i64(int64_t* a, int64_t n, void*, mc_stream_t) { for (int64_t i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
@@ -329,14 +331,60 @@ static void device_scan_u32(const uint32_t* in, int64_t* out, int64_t n, int64_t
 { device_lookback_scan<uint32_t, ScanSum, false>(in, out, n, scratch, out + n, s); g_launches++; }
 static void device_exscan_i64(int64_t* a, int64_t n, int64_t* total, void* scratch, mc_stream_t s)
 { device_lookback_scan<int64_t, ScanSum, false>(a, a, n, scratch, total, s); g_launches++; }
-__global__ void __launch_bounds__(MC_BLOCK) mc_vcdepth_kernel(const VcArgs a, int64_t b0, int64_t b1)
-{ int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < b1) vcdepth_body(b, a); }
+// The variant-scan walkers (one thread per block of 100 columns) read the packed profile through shared memory: the thread
+// block (128 walkers = 12800 columns) stages MC_VC_STAGE columns of every walker at a time with coalesced 16-byte loads
+// (runs of 320 contiguous bytes), so that every 32-byte sector of the 16 B/column image is fetched from DRAM exactly once
+// and whole; a row of 20 records is padded to 21 so that the walkers' own 16-byte reads spread over all banks.
+#define MC_VC_THREADS 128
+struct VcFetchShared {
+	const uint4* tile; int64_t col0, n_cols;     // packed tile, tile-relative column of walker 0 of this thread block, columns in the tile
+	uint4* sh;                                   // [MC_VC_THREADS][MC_VC_STAGE + 1]
+	__device__ __forceinline__ void sync(int j)
+	{
+		if (j % MC_VC_STAGE) return;
+		__syncthreads();                         // the previous stage has been consumed
+		for (int e = threadIdx.x; e < MC_VC_THREADS * MC_VC_STAGE; e += MC_VC_THREADS)
+		{
+			const int seg = e / MC_VC_STAGE, within = e % MC_VC_STAGE;
+			const int64_t col = col0 + (int64_t)seg * MC_VC_BLOCK + j + within;
+			uint4 v = make_uint4(0, 0, 0, 0);
+			if (col < n_cols) v = __ldg(tile + col);
+			sh[seg * (MC_VC_STAGE + 1) + within] = v;
+		}
+		__syncthreads();
+	}
+	__device__ __forceinline__ void get(int j, uint64_t& w0, uint64_t& w1) const
+	{
+		const uint4 v = sh[threadIdx.x * (MC_VC_STAGE + 1) + j % MC_VC_STAGE];
+		w0 = (uint64_t)v.y << 32 | v.x; w1 = (uint64_t)v.w << 32 | v.z;
+	}
+};
+__global__ void __launch_bounds__(MC_VC_THREADS) mc_vcdepth_kernel(const VcArgs a, int64_t b0, int64_t b1)
+{
+	__shared__ uint4 sh[MC_VC_THREADS * (MC_VC_STAGE + 1)];
+	const int64_t bb = b0 + blockIdx.x * (int64_t)MC_VC_THREADS, b = bb + threadIdx.x;
+	VcFetchShared f; f.tile = (const uint4*)a.recs; f.col0 = bb * MC_VC_BLOCK - a.tile_beg; f.n_cols = a.tile_end - a.tile_beg; f.sh = sh;
+	vcdepth_walk(b, b < b1, a, f);
+}
 static void launch_vcdepth(const VcArgs& a, int64_t b0, int64_t b1, mc_stream_t s)
-{ if (b1 > b0) { mc_vcdepth_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, b0, b1); g_launches++; } }
-__global__ void __launch_bounds__(MC_BLOCK) mc_vcscan_kernel(const VcArgs a, int64_t b0, int64_t b1, bool emit)
-{ int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (b < b1) vcscan_body(b, a, emit); }
+{ if (b1 > b0) { mc_vcdepth_kernel<<<(unsigned)((b1 - b0 + MC_VC_THREADS - 1) / MC_VC_THREADS), MC_VC_THREADS, 0, s>>>(a, b0, b1); g_launches++; } }
+__global__ void __launch_bounds__(MC_VC_THREADS) mc_vcscan_kernel(const VcArgs a, int64_t b0, int64_t b1, bool emit)
+{
+	__shared__ uint4 sh[MC_VC_THREADS * (MC_VC_STAGE + 1)];
+	const int64_t bb = b0 + blockIdx.x * (int64_t)MC_VC_THREADS, b = bb + threadIdx.x;
+	VcFetchShared f; f.tile = (const uint4*)a.recs; f.col0 = bb * MC_VC_BLOCK - a.tile_beg; f.n_cols = a.tile_end - a.tile_beg; f.sh = sh;
+	vcscan_walk(b, b < b1, a, emit, f);
+}
 static void launch_vcscan(const VcArgs& a, int64_t b0, int64_t b1, bool emit, mc_stream_t s)
-{ if (b1 > b0) { mc_vcscan_kernel<<<(unsigned)((b1 - b0 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(a, b0, b1, emit); g_launches++; } }
+{ if (b1 > b0) { mc_vcscan_kernel<<<(unsigned)((b1 - b0 + MC_VC_THREADS - 1) / MC_VC_THREADS), MC_VC_THREADS, 0, s>>>(a, b0, b1, emit); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_vckey_kernel(int64_t n, const mc_variant_rec* recs, uint64_t* keys, uint32_t* idx, mc_u64* n_valid)
+{ int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (i < n) vckey_body(i, recs, keys, idx, n_valid); }
+static void launch_vckey(int64_t n, const mc_variant_rec* recs, uint64_t* keys, uint32_t* idx, mc_u64* n_valid, mc_stream_t s)
+{ if (n > 0) { mc_vckey_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, recs, keys, idx, n_valid); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_vcgather_kernel(int64_t n, const mc_variant_rec* in, const uint32_t* idx, mc_variant_rec* out)
+{ int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (j < n) vcgather_body(j, in, idx, out); }
+static void launch_vcgather(int64_t n, const mc_variant_rec* in, const uint32_t* idx, mc_variant_rec* out, mc_stream_t s)
+{ if (n > 0) { mc_vcgather_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(n, in, idx, out); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_samrec_kernel(const SamArgs a, int64_t n, bool emit)
 { int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (r < n) samrec_body(r, a, emit); }
 static void launch_samrec(const SamArgs& a, int64_t n, bool emit, mc_stream_t s)

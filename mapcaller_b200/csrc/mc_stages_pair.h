@@ -211,6 +211,83 @@ MC_HD int rescue_scan_diag(const uint32_t* wkid0, const KmerEnt* km, int nk, int
 	return total;
 }
 
+#if MC_DEV_ONLY
+// The same walk with the 32 lanes of a warp side by side: lane l tests word c0 + l of the mate's list against diagonal d, two
+// ballots give the hit mask H and the mask C of hits that CONTINUE a run (previous word hit as well and labelled one lower);
+// runs are then read off the masks with bit scans - uniform code, a few instructions per run instead of a dozen per word of
+// the list on one lane while 31 wait.  Returns the score of the diagonal (every lane); Hs / Cs, if given, receive the masks.
+static __device__ __forceinline__ int rescue_diag_warp(const uint32_t* wkid0, const KmerEnt* km, int nk, int slen, int d, int l, uint32_t* Hs, uint32_t* Cs)
+{
+	const unsigned full = 0xffffffffu;
+	int total = 0, run = 0, carry_lab = -2, carry_hit = 0;
+	for (int c0 = 0, wi = 0; c0 < nk; c0 += 32, wi++)
+	{
+		const int i = c0 + l;
+		int lab = 0, hit = 0;
+		if (i < nk) { const KmerEnt e = km[i]; lab = e.label; const int g = lab + d; if (g >= 0 && g <= slen - 8) hit = wkid0[g] == e.wid; }
+		int plab = __shfl_up_sync(full, lab, 1), phit = __shfl_up_sync(full, hit, 1);
+		if (l == 0) { plab = carry_lab; phit = carry_hit; }
+		const int cont = hit && phit && lab == plab + 1;
+		const uint32_t H = __ballot_sync(full, hit), C = __ballot_sync(full, cont);
+		carry_lab = __shfl_sync(full, lab, 31); carry_hit = __shfl_sync(full, hit, 31);
+		if (Hs && l == 0) { Hs[wi] = H; Cs[wi] = C; }
+		int pos = 0;
+		if (run > 0)                                          // a run reaches over from the previous 32 words
+		{
+			const int k = C == full ? 32 : __ffs((int)~C) - 1;
+			run += k; pos = k;
+			if (k == 32) continue;
+			if (run >= 3) total += 7 + run;
+			run = 0;
+		}
+		while (pos < 32)
+		{
+			const uint32_t rest = H & (full << pos);
+			if (!rest) break;
+			const int s0 = __ffs((int)rest) - 1;
+			const int k = s0 < 31 ? __ffs((int)~(C >> (s0 + 1))) - 1 : 0;
+			run = 1 + k; pos = s0 + 1 + k;
+			if (pos >= 32) break;                             // may go on in the next 32 words
+			if (run >= 3) total += 7 + run;
+			run = 0;
+		}
+	}
+	if (run >= 3) total += 7 + run;
+	return total;
+}
+// the seeds of a diagonal from its masks (one lane): counts them, and writes them when `out` is given
+static __device__ __forceinline__ int rescue_seeds_from_masks(const uint32_t* Hs, const uint32_t* Cs, int nk, const KmerEnt* km, int64_t left, int d, SPair* out)
+{
+	int n = 0, run = 0, first = 0;
+	const int nw = (nk + 31) >> 5;
+	for (int wi = 0; wi <= nw; wi++)
+	{
+		const uint32_t H = wi < nw ? Hs[wi] : 0u, C = wi < nw ? Cs[wi] : 0u;
+		int pos = 0;
+		if (run > 0)
+		{
+			const int k = C == 0xffffffffu ? 32 : __ffs((int)~C) - 1;
+			run += k; pos = k;
+			if (k == 32) continue;
+			if (run >= 3) { if (out) { SPair sp; sp.rpos = km[first].label; sp.gpos = left + d + km[first].label; sp.len = 7 + run; out[n] = sp; } n++; }
+			run = 0;
+		}
+		while (pos < 32)
+		{
+			const uint32_t rest = H & (0xffffffffu << pos);
+			if (!rest) break;
+			const int s0 = __ffs((int)rest) - 1;
+			const int k = s0 < 31 ? __ffs((int)~(C >> (s0 + 1))) - 1 : 0;
+			run = 1 + k; first = wi * 32 + s0; pos = s0 + 1 + k;
+			if (pos >= 32) break;
+			if (run >= 3) { if (out) { SPair sp; sp.rpos = km[first].label; sp.gpos = left + d + km[first].label; sp.len = 7 + run; out[n] = sp; } n++; }
+			run = 0;
+		}
+	}
+	return n;
+}
+#endif
+
 #define MC_RESCUE_HASH 2048  // chain heads of the read's 8-mer table (low 11 bits of the 16-bit word id)
 #define MC_RESCUE_MARGIN 32   // how far beyond the moving window edge hits are looked for (validity interval of EstiDistance)
 
@@ -300,6 +377,39 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 	lanebuf[4 * nl + lane] = in_far; lanebuf[5 * nl + lane] = out_near;
 	MC_GROUP_SYNC();
 	int best = 0, bd = 0;
+#if MC_DEV_ONLY
+	{
+		// a WARP per diagonal with >= 3 hits: the warps take 32 diagonals at a time, the qualifying ones of a turn one after the
+		// other (ascending, so the first maximum wins inside a warp); every lane of a warp ends up with the warp's best
+		const int l = lane & 31, nwarp = nl >> 5;
+		for (int i0 = (lane >> 5) << 5; i0 < ndiag; i0 += nl)
+		{
+			const int i = i0 + l;
+			unsigned q = __ballot_sync(0xffffffffu, i < ndiag && hits[i] >= 3);
+			while (q)
+			{
+				const int dd = i0 + (__ffs((int)q) - 1) + dmin; q &= q - 1;
+				const int sc = rescue_diag_warp(wkid0, km, nk, slen, dd, l, nullptr, nullptr);
+				if (sc > best) { best = sc; bd = dd; }
+			}
+		}
+		// closest hits to the moving edge: reduced inside the warp, then over the warps
+		const unsigned fw = __reduce_min_sync(0xffffffffu, in_far < 0 ? 0xffffffffu : (unsigned)in_far), ow = __reduce_min_sync(0xffffffffu, (unsigned)out_near);
+		MC_GROUP_SYNC();                                    // lanebuf[4 nl ..] (per-lane in_far / out_near of the scan above) is no longer needed
+		if (l == 0) { int32_t* wb = lanebuf + 4 * (lane >> 5); wb[0] = best; wb[1] = bd; wb[2] = (int32_t)fw; wb[3] = (int32_t)ow; }
+		MC_GROUP_SYNC();
+		best = 0; bd = 0; in_far = -1; out_near = 1 << 30;
+		for (int w = 0; w < nwarp; w++)
+		{
+			const int sc = lanebuf[4 * w], dd = lanebuf[4 * w + 1];
+			if (sc > best || (sc == best && sc > 0 && dd < bd)) { best = sc; bd = dd; }
+			const unsigned f = (unsigned)lanebuf[4 * w + 2]; const int o = lanebuf[4 * w + 3];
+			if (f != 0xffffffffu && (in_far < 0 || (int)f < in_far)) in_far = (int)f;
+			if (o < out_near) out_near = o;
+		}
+		MC_GROUP_SYNC();
+	}
+#else
 	for (int i = lane; i < ndiag; i += nl)
 	{
 		if (hits[i] < 3) continue;
@@ -318,12 +428,31 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 		if (o < out_near) out_near = o;
 	}
 	MC_GROUP_SYNC();
+#endif
 	if (!clipped || dir == 1)
 	{
 		if (in_far >= 0 && est - in_far > *iv_lo) *iv_lo = est - in_far;
 		if (out_near < (1 << 30) && est + out_near - 1 < *iv_hi) *iv_hi = est + out_near - 1;
 	}
 	if (best == 0 || best <= floor_score) return false;
+#if MC_DEV_ONLY
+	if (lane < 32)
+	{
+		// the seeds of the winning diagonal: its masks once more (warp 0), then lane 0 reads the runs off them twice - count, reserve, write
+		uint32_t* Hs = (uint32_t*)lanebuf + 16; uint32_t* Cs = Hs + ((MC_MAX_RLEN + 31) >> 5);     // fits below lanebuf[4 nl]: 2 x 125 words
+		rescue_diag_warp(wkid0, km, nk, slen, bd, lane, Hs, Cs);
+		__syncwarp();
+		if (lane == 0)
+		{
+			int ok = 1;
+			const int n = rescue_seeds_from_masks(Hs, Cs, nk, km, left, bd, nullptr);
+			const int64_t pb = (int64_t)mc_atomic_add(a.pair_bump, (mc_u64)n);
+			if (pb + n > a.pair_cap) { mc_atomic_or(&a.st->overflow, (mc_u64)1 << 0); ok = 0; }
+			if (ok) { rescue_seeds_from_masks(Hs, Cs, nk, km, left, bd, a.pairs + pb); res->score = best; res->pbeg = (int32_t)pb; res->n = n; }
+			lanebuf[6 * nl] = ok;
+		}
+	}
+#else
 	if (lane == 0)
 	{
 		int n = 0, ok = 1;
@@ -333,6 +462,7 @@ MC_HD bool rescue_try(const PipeArgs& a, int lane, int nl, RWin* res, const Kmer
 		if (ok) { rescue_scan_diag(wkid0, km, nk, left, slen, bd, a.pairs + pb, &n); res->score = best; res->pbeg = (int32_t)pb; res->n = n; }
 		lanebuf[6 * nl] = ok;
 	}
+#endif
 	MC_GROUP_SYNC();
 	const int ok = lanebuf[6 * nl];
 	MC_GROUP_SYNC();

@@ -30,23 +30,44 @@ struct VcArgs {
 	mc_variant_rec* out;
 };
 
+// How a walker gets at the packed record of column j of its block.  On the device the 1600 bytes of a block are not read by
+// their thread 16 bytes at a time (every lane of a warp in a different line): the thread block stages MC_VC_STAGE columns of
+// all its walkers through shared memory with coalesced loads (mc_launch.h: VcFetchShared); sync(j) is called by EVERY thread
+// of the block at the top of EVERY one of the MC_VC_BLOCK iterations, whether the walker has a column there or not.
+#define MC_VC_STAGE 20
+struct VcFetchGlobal {
+	const uint64_t* recs;        // record of the walker's column 0
+	MC_HD void sync(int) {}
+	MC_HD void get(int j, uint64_t& w0, uint64_t& w1) const { w0 = recs[2 * j]; w1 = recs[2 * j + 1]; }
+};
+
 MC_HD int vc_cov(uint64_t w) { return (int)((w & 4095) + ((w >> 12) & 4095) + ((w >> 24) & 4095) + ((w >> 36) & 4095)); }
 
 // pass 1: BlockDepthArr and the run carriers
-MC_HD void vcdepth_body(int64_t b, const VcArgs& a)
+template <class Fetch> MC_HD void vcdepth_walk(int64_t b, bool live, const VcArgs& a, Fetch& f)
 {
 	const int64_t g0 = b * MC_VC_BLOCK; int64_t g1 = g0 + MC_VC_BLOCK; if (g1 > a.G) g1 = a.G;
+	if (!live) g1 = g0;
 	int sum = 0; int64_t ng = -1, nd = -1;
-	for (int64_t g = g0; g < g1; g++)
+	for (int j = 0; j < MC_VC_BLOCK; j++)
 	{
-		const uint64_t w = a.recs[2 * (g - a.tile_beg)];
+		f.sync(j);
+		const int64_t g = g0 + j;
+		if (g >= g1) continue;
+		uint64_t w, w1_unused; f.get(j, w, w1_unused);
 		const int cov = vc_cov(w); const int mh = (int)((w >> 48) & 4095);
 		sum += cov;
 		if (!(cov == 0 && mh == 0)) ng = g;
 		if (!(cov == 0 && mh > 0)) nd = g;
 	}
+	if (!live) return;
 	a.depth[b] = sum > 0 ? sum / MC_VC_BLOCK : 0;   // :117, always / BlockSize
 	a.last_nongap[b] = ng; a.last_nondup[b] = nd;
+}
+MC_HD void vcdepth_body(int64_t b, const VcArgs& a)
+{
+	VcFetchGlobal f; f.recs = a.recs + 2 * (b * MC_VC_BLOCK - a.tile_beg);
+	vcdepth_walk(b, true, a, f);
 }
 
 // DetermineGenotype, src/VariantCalling.cpp:523-548
@@ -67,9 +88,11 @@ MC_HD uint8_t vc_q8(double num, double den) { if (den == 0.0) return 0; return (
 MC_HD void vc_clear(mc_variant_rec& v) { v.gPos = 0; v.record[0] = v.record[1] = 0; v.alt_off = v.alt_len = 0; v.DP = v.AD_ref = v.AD_alt = 0; v.GenoType = v.qscore = 0; v.VarType = MC_VAR_NIL; v.alt[0] = v.alt[1] = v.alt[2] = 0; }
 
 // passes 2 (emit == false: counts and the gvcf carriers) and 3 (emit == true)
-MC_HD void vcscan_body(int64_t b, const VcArgs& a, bool emit)
+template <class Fetch> MC_HD void vcscan_walk(int64_t b, bool live, const VcArgs& a, bool emit, Fetch& f)
 {
+	if (!live) b = 0;            // a padding thread of the last block: takes part in the staging only
 	const int64_t g0 = b * MC_VC_BLOCK; int64_t g1 = g0 + MC_VC_BLOCK; if (g1 > a.G) g1 = a.G;
+	if (!live) g1 = g0;
 	const mc_vc_params& P = a.vp;
 	const int mad = P.min_allele_depth, depth = a.depth[b];
 	int cov_thr = depth >> 1; if (cov_thr < mad) cov_thr = mad;
@@ -81,6 +104,7 @@ MC_HD void vcscan_body(int64_t b, const VcArgs& a, bool emit)
 	if (b > 0) { gap = g0 - 1 - a.last_nongap[b - 1]; dup = g0 - 1 - a.last_nondup[b - 1]; }
 	// candidates of this block
 	int64_t ci; { int64_t lo = 0, hi = a.n_cand; while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a.cand[mid].pos < g0) lo = mid + 1; else hi = mid; } ci = lo; }
+	int64_t next_cand = ci < a.n_cand ? a.cand[ci].pos : -1;   // column of the next candidate: one register compare per column instead of a load
 	bool last_nor = false;
 	if (emit && P.gvcf && b > 0) { const int64_t ln = a.last_normal[b - 1], le = a.last_event[b - 1]; last_nor = ln >= 0 && ln >= le; }
 	int64_t slot = emit ? a.off[b] : 0; const int64_t slot_end = emit ? a.off[b] + a.cnt[b] : 0;
@@ -89,13 +113,16 @@ MC_HD void vcscan_body(int64_t b, const VcArgs& a, bool emit)
 	mc_variant_rec v;
 #define VC_PUSH() do { if (emit) a.out[slot++] = v; n++; } while (0)
 #define VC_EVENT(g) do { le_pos = (g); last_nor = false; if (emit && open_slot >= 0) { a.out[open_slot].AD_alt = (uint16_t)open_min; open_slot = -1; } } while (0)
-	for (int64_t g = g0; g < g1; g++)
+	for (int j = 0; j < MC_VC_BLOCK; j++)
 	{
-		const uint64_t w0 = a.recs[2 * (g - a.tile_beg)], w1 = a.recs[2 * (g - a.tile_beg) + 1];
+		f.sync(j);
+		const int64_t g = g0 + j;
+		if (g >= g1) continue;
+		uint64_t w0, w1; f.get(j, w0, w1);
 		int c[4] = {(int)(w0 & 4095), (int)((w0 >> 12) & 4095), (int)((w0 >> 24) & 4095), (int)((w0 >> 36) & 4095)};
 		const int mh = (int)((w0 >> 48) & 4095), cov = c[0] + c[1] + c[2] + c[3];
 		bool normal = true;
-		for (; ci < a.n_cand && a.cand[ci].pos == g; ci++)   // :571-592, insertion before deletion
+		for (; next_cand == g; ci++, next_cand = ci < a.n_cand ? a.cand[ci].pos : -1)   // :571-592, insertion before deletion
 		{
 			const VcCand k = a.cand[ci];
 			if (k.freq < (k.kind ? del_thr : ins_thr)) continue;
@@ -161,6 +188,7 @@ MC_HD void vcscan_body(int64_t b, const VcArgs& a, bool emit)
 	}
 #undef VC_PUSH
 #undef VC_EVENT
+	if (!live) return;
 	if (!emit) { a.cnt[b] = n; if (P.gvcf) { a.last_normal[b] = ln_pos; a.last_event[b] = le_pos; a.lead_min[b] = lead; } return; }
 	if (open_slot >= 0)   // the run is still open at the end of the block: it lasts until the next event
 	{
@@ -173,5 +201,23 @@ MC_HD void vcscan_body(int64_t b, const VcArgs& a, bool emit)
 	}
 	for (; slot < slot_end; slot++) { vc_clear(v); a.out[slot] = v; }
 }
+
+MC_HD void vcscan_body(int64_t b, const VcArgs& a, bool emit)
+{
+	VcFetchGlobal f; f.recs = a.recs + 2 * (b * MC_VC_BLOCK - a.tile_beg);
+	vcscan_walk(b, true, a, emit, f);
+}
+
+// The final order of the records (CompByVarPos, src/VariantCalling.cpp:51-55: gPos, then VarType - unique within one scan) is
+// made on the device: the slots are in column order except for gap / dup records, which sit where their run ends but carry its
+// start, and for the INS, DEL, SUB order of one column; unused slots sort to the end.
+MC_HD void vckey_body(int64_t i, const mc_variant_rec* recs, uint64_t* keys, uint32_t* idx, mc_u64* n_valid)
+{
+	const bool ok = recs[i].VarType != MC_VAR_NIL;
+	keys[i] = ok ? ((uint64_t)recs[i].gPos << 8 | (uint64_t)recs[i].VarType) : ~0ull;
+	idx[i] = (uint32_t)i;
+	mc_stat_add(n_valid, ok ? 1u : 0u);
+}
+MC_HD void vcgather_body(int64_t j, const mc_variant_rec* in, const uint32_t* idx, mc_variant_rec* out) { out[j] = in[idx[j]]; }
 
 #endif
