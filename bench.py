@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM flavour of the end-to-end leg")
     ap.add_argument("--cache-dir", default="", help="profiling runs: keep the mutant genome and the index files here (e.g. /dev/shm/mc) and reuse them, so that a run under ncu does not profile the index build")
+    ap.add_argument("--allreduce", action="store_true", help="N > 1: end the library with the whole-array all-reduce instead of the reduce-scatter")
     ap.add_argument("--trace-e2e", action="store_true", help="print a host-side timeline of one end-to-end step to stderr")
     ap.add_argument("--resident-only", action="store_true", help="profiling runs: only the resident leg (the JSON line then has no e2e)")
     args = ap.parse_args()
@@ -267,7 +268,8 @@ def main():
     config = {"workload": "%s %d bp synthetic reference (%s, 15 %% repeat families), 2x%d bp simulated PE reads, %d pairs per GPU in batches of %d, -alg %s, VCF profile on"
                           % (CFG["name"], args.genome, "24 contigs" if CFG["contigs"] else "one contig", READ_LEN, args.pairs, min(BATCH_PAIRS, args.pairs), "ksw2" if CFG["ksw2"] else "nw"),
               "genome_bp": args.genome, "read_len": READ_LEN, "pairs_per_gpu": args.pairs, "batch_pairs": min(BATCH_PAIRS, args.pairs), "alg": "ksw2" if CFG["ksw2"] else "nw",
-              "parallelism": "reads sharded over %d GPU(s) in file order (one library: avgDist / dedup gate / discordant-pair state exchanged over NCCL inside every batch, profile reduced at the end of the pass), full index replica per GPU" % world
+              "parallelism": "reads sharded over %d GPU(s) in file order (one library: avgDist / dedup gate / discordant-pair state exchanged over NCCL inside every batch; the pass ends with %s of the profile), full index replica per GPU"
+                             % (world, "ncclAllReduce" if args.allreduce else "ncclReduceScatter (every rank finishes one genome tile)")
                              if world > 1 else "one GPU, one index replica",
               "l2_policy": "inputs larger than L2: index %.2f GB + %.1f GB of reads per batch stream from HBM" % (args.genome * 1.5 / 1e9, 2 * min(BATCH_PAIRS, args.pairs) * READ_LEN / 1e9)}
     numa = bind_to_gpu_numa(local)
@@ -302,17 +304,31 @@ def main():
         dist = dist_mod
 
     t_setup = time.perf_counter()
+    # GRCh38-sized runs on several GPUs: rank 0 makes the mutant genome and the index once and the other ranks load them from
+    # /dev/shm (every rank generating 3.1 Gbp on its own costs a minute of box time and 15 GB of host memory per rank)
+    own_cache = world > 1 and args.genome > 1_000_000_000 and not args.cache_dir
+    if own_cache:
+        args.cache_dir = "/dev/shm/mc_bench_%s" % os.environ.get("MASTER_PORT", "0")
     cache = os.path.join(args.cache_dir, "c%d_%d" % (args.config, args.genome)) if args.cache_dir else ""
-    if cache and os.path.exists(cache + ".bwt") and os.path.exists(cache + ".mut.npy"):
-        mut = np.load(cache + ".mut.npy", mmap_mode="r")
-        ix, index_how = api.Index.load(cache), "mc_index_load (cached files of mc_index_build_gpu)"
-    else:
+    have = bool(cache) and os.path.exists(cache + ".bwt") and os.path.exists(cache + ".mut.npy") and not own_cache
+    if not have and (rank == 0 or not cache):
         g, mut = make_genome(args.genome)
         ix, index_how = build_index(g, local)
         del g
-        if cache and rank == 0:
+        if cache:
             os.makedirs(args.cache_dir, exist_ok=True)
             np.save(cache + ".mut.npy", mut); ix.save(cache)
+    if cache and dist is not None:
+        dist.barrier()
+    if have or (cache and rank != 0):
+        mut = np.load(cache + ".mut.npy", mmap_mode="r")
+        ix, index_how = api.Index.load(cache), "mc_index_load (files written by rank 0 / an earlier run with mc_index_build_gpu)"
+    if own_cache:
+        dist.barrier()
+        if rank == 0:
+            import shutil
+            mut = np.array(mut)          # rank 0 keeps its copy in memory; the files go away
+            shutil.rmtree(args.cache_dir, ignore_errors=True)
     t_index = time.perf_counter() - t_setup
     r1, r2 = make_reads(mut, args.pairs, rank)
     n_pairs = len(r1)
@@ -352,13 +368,17 @@ def main():
     S_IN0 = n_batches                            # first of the three device slots of the FASTQ feed
     assert n_batches + 3 <= 8
 
+    # The N ranks end a library with mc_profile_reduce_scatter (each keeps the sums of one genome tile; the variant scan and the
+    # checksums then run on the N tiles at once); --allreduce keeps the whole-array ncclAllReduce of round 1 for comparison.
+    end_of_library = ctx.profile_allreduce if args.allreduce else ctx.profile_reduce_scatter
+
     # ---- resident leg (value) ----
     def one_pass():
         ctx.reset()
         for b in range(n_batches):
             ctx.map_staged(b)
         if dist is not None:
-            ctx.profile_allreduce()      # every rank ends the pass with the whole-library profile
+            end_of_library()             # every rank ends the pass with the library's counters of its genome tile
 
     for _ in range(args.warmup):
         one_pass()
@@ -414,7 +434,7 @@ def main():
         if err:
             raise err[0]
         if dist is not None:
-            ctx.profile_allreduce()
+            end_of_library()
         mark("scan begin", -1)
         n_var, n_blk = ctx.variant_scan_raw()
         mark("scan end", -1)
@@ -440,7 +460,7 @@ def main():
         wall_e2e, h2d, d2h, n_var, _ = timed_fastq(False)
         e2e_fp = ctx.profile_checksum(); e2e_totals = ctx.totals()
     sam_leg = None
-    if not args.no_sam and not args.resident_only and hasattr(api.Context, "sam_text_raw"):
+    if not args.no_sam and not args.resident_only and world == 1:      # the SAM flavour is a single-GPU figure
         w, h, d, _, sam_bytes = timed_fastq(True)
         sam_leg = (w, h, d, sam_bytes)
 
@@ -467,7 +487,7 @@ def main():
         check["n_gpu_equals_1_gpu"] = "not run: the single-GPU control context does not fit beside a GRCh38-sized profile"
     elif dist is not None:
         cseq, coff = sim.interleave(chk1, chk2)
-        ctx.reset(); ctx.map_batch(cseq, coff, copy=False); ctx.profile_allreduce()
+        ctx.reset(); ctx.map_batch(cseq, coff, copy=False); end_of_library()
         multi_fp, multi_tot = ctx.profile_checksum(), ctx.totals()
         if rank == 0:
             solo = api.Context(ix, paired=1, alg_ksw2=CFG["ksw2"], update_profile=1, want_alignments=0, device=local)

@@ -265,6 +265,18 @@ int mc_variant_scan(mc_ctx *ctx, const mc_vc_params *vp, const mc_variant_rec **
 int mc_comm_unique_id(uint8_t *out128);
 int mc_comm_init(mc_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t n_ranks);
 int mc_profile_allreduce(mc_ctx *ctx, void *nccl_comm);
+/* The scalable variant for genomes of gigabases ("ncclReduceScatter ... so each GPU finalises 1/N of the
+ * genome"): every rank ends up with the library's counters of ONE tile of the genome (equal tiles of whole 25600-column
+ * units, rank r owns tile r; ncclReduceScatter in place - half the NVLink traffic of the all-reduce and no 33 B x G image
+ * per rank to finish) and the read-out calls that follow become collectives over the tiles, to be made by every rank:
+ *   mc_variant_scan       scans the own tile (run carriers of the earlier tiles come in through one small all-gather) and
+ *                         gathers the records and block depths of all ranks: every rank returns the whole genome's result
+ *                         (a gVCF scan needs mc_profile_allreduce: its runs look ahead across tiles)
+ *   mc_profile_summary, mc_profile_checksum   partial results of the tiles, combined
+ *   mc_profile_read       serves columns of the own tile only (mc_profile_owned tells which)
+ * Indel, break-point and SV-site records are gathered to every rank as by mc_profile_allreduce.  Ends the library run. */
+int mc_profile_reduce_scatter(mc_ctx *ctx);
+int mc_profile_owned(const mc_ctx *ctx, int64_t *beg, int64_t *end);   /* [0, genome) unless reduce-scattered */
 
 /* ---- read ingest (first "next" row) -----------------------------------------------------------
  * GetNextEntry / GetNextChunk, FASTQ branch (reference src/GetData.cpp:32-99), on the device: the caller hands over raw

@@ -155,6 +155,8 @@ def lib():
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.mc_sam_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
         L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
+        L.mc_profile_reduce_scatter.argtypes = [C.c_void_p]
+        L.mc_profile_owned.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.mc_comm_unique_id.argtypes = [C.c_void_p]
         L.mc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.mc_align_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 8
@@ -411,6 +413,16 @@ class Context:
 
     def profile_allreduce(self):
         _check(lib().mc_profile_allreduce(self._h, None), "mc_profile_allreduce")
+
+    def profile_reduce_scatter(self):
+        """Every rank keeps the library's counters of one genome tile; variant_scan / profile_summary / profile_checksum are
+        collectives afterwards (include/mapcaller_b200.h)."""
+        _check(lib().mc_profile_reduce_scatter(self._h), "mc_profile_reduce_scatter")
+
+    def profile_owned(self):
+        b, e = C.c_int64(), C.c_int64()
+        _check(lib().mc_profile_owned(self._h, C.byref(b), C.byref(e)), "mc_profile_owned")
+        return b.value, e.value
 
     def reset(self):
         _check(lib().mc_reset(self._h), "mc_reset")

@@ -81,6 +81,7 @@ struct NcclApi {
 	ncclResult_t (*CommDestroy)(ncclComm_t);
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
 	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
 	const char* (*GetErrorString)(ncclResult_t);
 	ncclResult_t (*GroupStart)();
@@ -100,9 +101,10 @@ static NcclApi* nccl_api()
 			*(void**)&api.GetUniqueId = dlsym(h, "ncclGetUniqueId"); *(void**)&api.CommInitRank = dlsym(h, "ncclCommInitRank");
 			*(void**)&api.CommDestroy = dlsym(h, "ncclCommDestroy"); *(void**)&api.AllReduce = dlsym(h, "ncclAllReduce");
 			*(void**)&api.AllGather = dlsym(h, "ncclAllGather"); *(void**)&api.Broadcast = dlsym(h, "ncclBroadcast");
+			*(void**)&api.ReduceScatter = dlsym(h, "ncclReduceScatter");
 			*(void**)&api.GetErrorString = dlsym(h, "ncclGetErrorString");
 			*(void**)&api.GroupStart = dlsym(h, "ncclGroupStart"); *(void**)&api.GroupEnd = dlsym(h, "ncclGroupEnd");
-			api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Broadcast && api.GetErrorString && api.GroupStart && api.GroupEnd;
+			api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.ReduceScatter && api.Broadcast && api.GetErrorString && api.GroupStart && api.GroupEnd;
 		}
 	}
 	if (!api.ok) { mc_set_error("libnccl.so.2 could not be loaded"); return nullptr; }
@@ -114,6 +116,7 @@ static void nccl_destroy(ncclComm_t comm) { nccl_api()->CommDestroy(comm); }
 #define ncclCommInitRank nccl_api()->CommInitRank
 #define ncclAllReduce nccl_api()->AllReduce
 #define ncclAllGather nccl_api()->AllGather
+#define ncclReduceScatter nccl_api()->ReduceScatter
 #define ncclBroadcast nccl_api()->Broadcast
 static int nccl_fail(ncclResult_t r, const char* what)
 {
@@ -177,7 +180,10 @@ struct mc_ctx {
 	DBuf d_bwt, d_cbwt, d_sa, d_sa_dense, d_ktab, d_pac, d_chrom_end, d_chrom_id;
 	DevIndex ix;
 	int64_t G;
-	// profile
+	// profile.  The arrays are padded to MC_TILE_PAD columns beyond G so that they divide into equal tiles for any number of ranks
+	// (mc_profile_reduce_scatter).  own_beg / own_end: the columns whose counters are the library's - everything, until a
+	// reduce-scatter leaves this rank with the sums of its tile only; own_carry = the difference-array sums of all columns before it.
+	int64_t own_beg = 0, own_end = 0, own_tile = 0; int64_t own_carry[6] = {0, 0, 0, 0, 0, 0}; bool scattered = false;
 	DBuf d_base16, d_sdiff, d_cdiff, d_mdiff, d_rcount, d_rflag;
 	DBuf d_bp, d_ind, d_ind_seq, d_pbump;
 	int64_t bp_cap = 0, ind_cap = 0, ind_seq_cap = 0;
@@ -225,6 +231,8 @@ struct mc_ctx {
 	DBuf fq_cnt[2], fq_off[2], fq_scan, fq_rlen, fq_rsrc;   // scratch of mc_ingest_fastq
 };
 
+#define MC_TILE_ALIGN 25600          /* a multiple of MC_PROF_BLOCK (1024) and of MC_VC_BLOCK (100) */
+#define MC_TILE_PAD (17 * MC_TILE_ALIGN) /* room for up to 16 equal tiles of whole MC_TILE_ALIGN units */
 static void zero_stats(mc_stats* s) { memset(s, 0, sizeof(*s)); }
 
 extern "C" {
@@ -329,10 +337,12 @@ int mc_ctx_create(const mc_index* idx, const mc_params* params, mc_ctx** out)
 	bad |= c->d_chrom_id.reserve(ids.size() * 4) || dev_h2d(c->d_chrom_id.p, ids.data(), ids.size() * 4, c->stream);
 	if (params->update_profile)
 	{
-		bad |= c->d_base16.reserve((size_t)G * 8) || c->d_sdiff.reserve((size_t)(G + 1) * 16) || c->d_cdiff.reserve((size_t)(G + 1) * 4);
-		bad |= c->d_mdiff.reserve((size_t)(G + 1) * 4) || c->d_rcount.reserve((size_t)G);
-		bad |= dev_zero(c->d_base16.p, (size_t)G * 8, c->stream) || dev_zero(c->d_sdiff.p, (size_t)(G + 1) * 16, c->stream) || dev_zero(c->d_cdiff.p, (size_t)(G + 1) * 4, c->stream);
-		bad |= dev_zero(c->d_mdiff.p, (size_t)(G + 1) * 4, c->stream) || dev_zero(c->d_rcount.p, (size_t)G, c->stream);
+		const size_t GP = (size_t)G + MC_TILE_PAD;
+		bad |= c->d_base16.reserve(GP * 8) || c->d_sdiff.reserve(GP * 16) || c->d_cdiff.reserve(GP * 4);
+		bad |= c->d_mdiff.reserve(GP * 4) || c->d_rcount.reserve(GP);
+		bad |= dev_zero(c->d_base16.p, GP * 8, c->stream) || dev_zero(c->d_sdiff.p, GP * 16, c->stream) || dev_zero(c->d_cdiff.p, GP * 4, c->stream);
+		bad |= dev_zero(c->d_mdiff.p, GP * 4, c->stream) || dev_zero(c->d_rcount.p, GP, c->stream);
+		c->own_beg = 0; c->own_end = G;
 	}
 	bad |= c->d_pbump.reserve(sizeof(PersistBumps)) || dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream);
 	bad |= c->d_bumps.reserve(sizeof(Bumps)) || c->d_stats.reserve(sizeof(DevStats)) || dev_zero(c->d_stats.p, sizeof(DevStats), c->stream);
@@ -403,9 +413,10 @@ int mc_reset(mc_ctx* c)
 	ev_record(&c->ev[EV_RST0], c->stream);
 	if (c->prm.update_profile)
 	{
-		const size_t G = (size_t)c->G;
-		bad |= dev_zero(c->d_base16.p, G * 8, c->stream) || dev_zero(c->d_sdiff.p, (G + 1) * 16, c->stream) || dev_zero(c->d_cdiff.p, (G + 1) * 4, c->stream);
-		bad |= dev_zero(c->d_mdiff.p, (G + 1) * 4, c->stream) || dev_zero(c->d_rcount.p, G, c->stream);
+		const size_t GP = (size_t)c->G + (c->scattered ? MC_TILE_PAD : 1);   // the padding only ever holds something after a reduce-scatter
+		bad |= dev_zero(c->d_base16.p, GP * 8, c->stream) || dev_zero(c->d_sdiff.p, GP * 16, c->stream) || dev_zero(c->d_cdiff.p, GP * 4, c->stream);
+		bad |= dev_zero(c->d_mdiff.p, GP * 4, c->stream) || dev_zero(c->d_rcount.p, GP, c->stream);
+		c->own_beg = 0; c->own_end = c->G; c->scattered = false; for (int k = 0; k < 6; k++) c->own_carry[k] = 0;
 	}
 	bad |= dev_zero(c->d_pbump.p, sizeof(PersistBumps), c->stream);
 	ev_record(&c->ev[EV_RST1], c->stream);
@@ -645,6 +656,19 @@ static int allgather_bytes(mc_ctx* c, ncclComm_t comm, const std::vector<uint8_t
 	if (dev_d2h(c->h_comm_buf.p, d_all, (size_t)mx * n, s) || dev_sync(s)) return -1;
 	all.assign(n, std::vector<uint8_t>());
 	for (int r = 0; r < n; r++) all[r].assign(c->h_comm_buf.as<uint8_t>() + (size_t)mx * r, c->h_comm_buf.as<uint8_t>() + (size_t)mx * r + sz[r]);
+	return 0;
+}
+
+// n 64-bit words of every rank, rank after rank, on the host of every rank (scalars of the distributed read-out)
+static int gather_words(mc_ctx* c, const mc_u64* mine, int n, std::vector<mc_u64>& all)
+{
+	const int N = c->comm_size; cudaStream_t s = c->stream;
+	if (c->d_comm_small.reserve(8 * (size_t)(n * (N + 1) + 8))) return -1;
+	mc_u64* d = c->d_comm_small.as<mc_u64>();
+	if (dev_h2d(d + (size_t)n * N, mine, 8 * (size_t)n, s)) return -1;
+	if (nccl_fail(ncclAllGather(d + (size_t)n * N, d, (size_t)n, ncclUint64, c->comm, s), "ncclAllGather(scalars)")) return -1;
+	all.assign((size_t)n * N, 0);
+	if (dev_d2h(all.data(), d, 8 * (size_t)n * N, s) || dev_sync(s)) return -1;
 	return 0;
 }
 
@@ -1345,6 +1369,20 @@ int mc_sam_text(mc_ctx* c, int32_t slot, int32_t all_best, const uint8_t** text,
 	return MC_OK;
 }
 
+// Block totals of the six difference-array lanes over the OWNED columns and their exclusive prefixes (pre[k * nb + b]).  After a
+// reduce-scatter the owned range starts in the middle of the genome: the sums of everything before it (own_carry) are planted
+// in the block just before the range and the scan starts there.
+static int profile_prefix(mc_ctx* c, const DevProfile& p, int64_t nb, int64_t* sums, mc_stream_t s)
+{
+	const int64_t ob0 = c->own_beg / MC_PROF_BLOCK, ob1 = (c->own_end + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK;
+	launch_profsum(p, c->G, nb, ob0, ob1, sums, s);
+	const int64_t s0 = ob0 > 0 ? ob0 - 1 : 0;
+	int bad = 0;
+	if (ob0 > 0) for (int k = 0; k < 6; k++) bad |= dev_h2d(sums + k * nb + s0, &c->own_carry[k], 8, s);
+	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb + s0, ob1 - s0, sums + 6 * nb + k, c->d_scan2.p, s);
+	return bad;
+}
+
 // packs the columns [beg, end) tile by tile; every tile is either copied to `outp` or reduced into the four counters `acc`
 static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64* d_acc, bool checksum = false)
 {
@@ -1355,8 +1393,9 @@ static int profile_walk(mc_ctx* c, int64_t beg, int64_t end, void* outp, mc_u64*
 	DBuf d_sums;
 	if (d_sums.reserve((size_t)(6 * nb + 8) * 8) || c->d_scan2.reserve(device_scan_scratch_bytes(nb))) return MC_ERR_CUDA;
 	int64_t* sums = d_sums.as<int64_t>();
-	launch_profsum(p, c->G, nb, sums, c->stream);
-	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, c->d_scan2.p, c->stream);
+	if (beg < c->own_beg) beg = c->own_beg;            // (mc_profile_read refuses such ranges; the reductions cover what this rank owns)
+	if (end > c->own_end) end = c->own_end;
+	if (profile_prefix(c, p, nb, sums, c->stream)) { d_sums.release(); return MC_ERR_CUDA; }
 	const int64_t tile_blocks = (1 << 24) / MC_PROF_BLOCK;
 	int rc = MC_OK;
 	if (c->d_sort.reserve((size_t)(tile_blocks * MC_PROF_BLOCK) * 16)) rc = MC_ERR_CUDA;
@@ -1379,6 +1418,7 @@ int mc_profile_read(mc_ctx* c, int64_t beg, int64_t end, void* outp)
 	if (!c || !outp || beg < 0 || end > c->G || beg > end) { mc_set_error("mc_profile_read: bad range"); return MC_ERR_ARG; }
 	if (!c->prm.update_profile) { mc_set_error("mc_profile_read: context was created without update_profile"); return MC_ERR_ARG; }
 	if (beg == end) return MC_OK;
+	if (beg < c->own_beg || end > c->own_end) { mc_set_error("mc_profile_read: after mc_profile_reduce_scatter this rank holds the columns [%lld, %lld) only", (long long)c->own_beg, (long long)c->own_end); return MC_ERR_ARG; }
 #ifndef MC_HOSTEMU
 	cudaSetDevice(c->prm.device);
 #endif
@@ -1398,6 +1438,14 @@ int mc_profile_summary(mc_ctx* c, mc_profile_stats* out)
 	mc_u64 h[4] = {0, 0, 0, 0};
 	if (rc == MC_OK && (dev_d2h(h, d_acc.p, 32, c->stream) || dev_sync(c->stream))) rc = MC_ERR_CUDA;
 	d_acc.release();
+#ifndef MC_HOSTEMU
+	if (rc == MC_OK && c->scattered)    // every rank reduced the tile it owns: the sums of all ranks are the library's
+	{
+		std::vector<mc_u64> all;
+		if (gather_words(c, h, 4, all)) return MC_ERR_NCCL;
+		for (int k = 0; k < 4; k++) { h[k] = 0; for (int r = 0; r < c->comm_size; r++) h[k] += all[(size_t)4 * r + k]; }
+	}
+#endif
 	out->aligned_bases = (int64_t)h[0]; out->coverage_sum = (int64_t)h[1]; out->dup_sites = (int64_t)h[2]; out->dup_reads = (int64_t)h[3];
 	return rc;
 }
@@ -1415,6 +1463,15 @@ int mc_profile_checksum(mc_ctx* c, uint64_t out[2])
 	mc_u64 h[2] = {0, 0};
 	if (rc == MC_OK && (dev_d2h(h, d_acc.p, 16, c->stream) || dev_sync(c->stream))) rc = MC_ERR_CUDA;
 	d_acc.release();
+#ifndef MC_HOSTEMU
+	if (rc == MC_OK && c->scattered)    // sum and xor of the per-column hashes combine over the tiles
+	{
+		std::vector<mc_u64> all;
+		if (gather_words(c, h, 2, all)) return MC_ERR_NCCL;
+		h[0] = h[1] = 0;
+		for (int r = 0; r < c->comm_size; r++) { h[0] += all[(size_t)2 * r]; h[1] ^= all[(size_t)2 * r + 1]; }
+	}
+#endif
 	out[0] = h[0]; out[1] = h[1];
 	return rc;
 }
@@ -1595,17 +1652,27 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	DevProfile p; p.base16 = c->d_base16.as<uint32_t>(); p.sdiff = c->d_sdiff.as<int32_t>(); p.cdiff = c->d_cdiff.as<int32_t>(); p.mdiff = c->d_mdiff.as<int32_t>();
 	p.rcount = c->d_rcount.as<uint8_t>();
 	const int64_t G = c->G, nb = (G + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK, nvb = (G + MC_VC_BLOCK - 1) / MC_VC_BLOCK;
+	// After mc_profile_reduce_scatter this rank scans the columns it owns, [R0, R1) (R0 a multiple of MC_TILE_ALIGN); the run
+	// carriers of the ranks before it come in through one small all-gather and the records of all ranks are gathered at the
+	// end, so every rank returns the scan of the whole genome.  Otherwise [R0, R1) = [0, G).
+	const int64_t R0 = c->own_beg, R1 = c->own_end;
+	const int64_t vbF = R0 / MC_VC_BLOCK, vbL = (R1 + MC_VC_BLOCK - 1) / MC_VC_BLOCK, nvo = vbL - vbF;   // blocks of 100 columns of the range
+	bool dist = false;
+#ifndef MC_HOSTEMU
+	dist = c->scattered;
+#endif
+	if (dist && vp->gvcf && !vp->monomorphic) { mc_set_error("mc_variant_scan: a gVCF scan needs the whole profile on one rank (mc_profile_allreduce instead of mc_profile_reduce_scatter)"); return MC_ERR_ARG; }
 	// The scan makes three passes over the packed profile (depths, counts, records).  When HBM has room for the whole
 	// MappingRecord_t image (16 bytes per column) it is packed once and kept; otherwise it is re-packed tile by tile per pass.
 	int64_t tile_cols = (int64_t)25600 * 640;           // a multiple of MC_PROF_BLOCK and of MC_VC_BLOCK
 #ifndef MC_HOSTEMU
 	{
 		size_t free_b = 0, total_b = 0;
-		const size_t whole = (size_t)((G + 25599) / 25600) * 25600 * 16;
+		const size_t whole = (size_t)((R1 - R0 + 25599) / 25600 + 1) * 25600 * 16;
 		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (c->d_sort.cap >= whole || free_b > whole + ((size_t)8 << 30)) && !getenv("MC_VC_TILED")) tile_cols = (int64_t)(whole / 16);
 	}
 #endif
-	const int64_t n_tiles = (G + tile_cols - 1) / tile_cols;
+	const int64_t n_tiles = (R1 - R0 + tile_cols - 1) / tile_cols;
 	DBuf &d_sums = c->d_vc[0], &d_depth = c->d_vc[1], &d_ng = c->d_vc[2], &d_nd = c->d_vc[3], &d_ln = c->d_vc[4], &d_le = c->d_vc[5], &d_lead = c->d_vc[6],
 	     &d_cnt = c->d_vc[7], &d_off = c->d_vc[8], &d_scan = c->d_vc[9], &d_cand = c->d_vc[10], &d_out = c->d_vc[11];
 	const bool trace = getenv("MC_VC_TRACE") != nullptr;   // stage timings on stderr (each stage ends with a stream sync then)
@@ -1619,56 +1686,106 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 	};
 	auto done = [&](int r) { dev_sync(s); return r; };
 	mark("indels");
-	int bad = d_sums.reserve((size_t)(6 * nb + 8) * 8) || d_depth.reserve((size_t)nvb * 4) || d_ng.reserve((size_t)nvb * 8) || d_nd.reserve((size_t)nvb * 8);
+	const int64_t nvb_pad = nvb + MC_TILE_PAD / MC_VC_BLOCK;      // room for the equal per-rank chunks of the depth all-gather
+	int bad = d_sums.reserve((size_t)(6 * nb + 8) * 8) || d_depth.reserve((size_t)nvb_pad * 4) || d_ng.reserve((size_t)nvb * 8) || d_nd.reserve((size_t)nvb * 8);
 	bad |= d_ln.reserve((size_t)nvb * 8) || d_le.reserve((size_t)nvb * 8) || d_lead.reserve((size_t)nvb * 4) || d_cnt.reserve((size_t)(nvb + 1) * 4);
 	bad |= d_off.reserve((size_t)(nvb + 2) * 8) || d_scan.reserve(device_scan_scratch_bytes(nvb)) || d_cand.reserve((cand.size() + 1) * sizeof(VcCand));
 	bad |= c->d_sort.reserve((size_t)std::min(tile_cols, nb * MC_PROF_BLOCK) * 16) || c->d_scan2.reserve(device_scan_scratch_bytes(std::max(nb, nvb)));
 	if (bad) return done(MC_ERR_CUDA);
 	if (dev_h2d(d_cand.p, cand.data(), cand.size() * sizeof(VcCand), s)) return done(MC_ERR_CUDA);
 	int64_t* sums = d_sums.as<int64_t>();
-	launch_profsum(p, G, nb, sums, s);
-	for (int k = 0; k < 6; k++) device_exscan_i64(sums + k * nb, nb, sums + 6 * nb + k, c->d_scan2.p, s);
+	if (profile_prefix(c, p, nb, sums, s)) return done(MC_ERR_CUDA);
 	VcArgs a; memset(&a, 0, sizeof(a));
 	a.vp = *vp; if (a.vp.gvcf && a.vp.monomorphic) a.vp.gvcf = 0;   // src/main.cpp:322
 	a.ix = c->ix; a.G = G; a.n_blocks = nvb; a.recs = c->d_sort.as<uint64_t>();
 	a.depth = d_depth.as<int32_t>(); a.last_nongap = d_ng.as<int64_t>(); a.last_nondup = d_nd.as<int64_t>(); a.last_normal = d_ln.as<int64_t>(); a.last_event = d_le.as<int64_t>();
 	a.lead_min = d_lead.as<int32_t>(); a.cnt = d_cnt.as<uint32_t>(); a.off = d_off.as<int64_t>(); a.cand = d_cand.as<VcCand>(); a.n_cand = (int64_t)cand.size();
 	int64_t packed = -1;
-	auto pack = [&](int64_t t) {   // MappingRecord_t image of tile t in d_sort (kept when the genome is a single tile)
-		a.tile_beg = t * tile_cols; a.tile_end = std::min(G, a.tile_beg + tile_cols);
+	auto pack = [&](int64_t t) {   // MappingRecord_t image of tile t in d_sort (kept when the range is a single tile)
+		a.tile_beg = R0 + t * tile_cols; a.tile_end = std::min(R1, a.tile_beg + tile_cols);
 		if (packed == t) return;
 		launch_profpack(c->ix, p, nb, sums, a.tile_beg / MC_PROF_BLOCK, (a.tile_end + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK, a.tile_beg, a.tile_end, c->d_sort.as<uint64_t>(), s);
 		packed = t;
 	};
-	auto vb0 = [&](int64_t t) { return t * (tile_cols / MC_VC_BLOCK); };
-	auto vb1 = [&](int64_t t) { return std::min(nvb, (t + 1) * (tile_cols / MC_VC_BLOCK)); };
+	auto vb0 = [&](int64_t t) { return vbF + t * (tile_cols / MC_VC_BLOCK); };
+	auto vb1 = [&](int64_t t) { return std::min(vbL, vbF + (t + 1) * (tile_cols / MC_VC_BLOCK)); };
 	mark("prefix");
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcdepth(a, vb0(t), vb1(t), s); }
 	mark("pack+depth");
-	device_incmax_i64(a.last_nongap, nvb, c->d_scan2.p, s); device_incmax_i64(a.last_nondup, nvb, c->d_scan2.p, s);
+	if (nvo > 0) { device_incmax_i64(a.last_nongap + vbF, nvo, c->d_scan2.p, s); device_incmax_i64(a.last_nondup + vbF, nvo, c->d_scan2.p, s); }
+#ifndef MC_HOSTEMU
+	if (dist)
+	{
+		// run carriers: the last non-gap / non-dup column of everything before this rank's range = the maximum over the earlier ranks
+		mc_u64 mine[2] = {(mc_u64)-1, (mc_u64)-1};       // -1 (none) as int64
+		if (nvo > 0 && (dev_d2h(&mine[0], a.last_nongap + vbL - 1, 8, s) || dev_d2h(&mine[1], a.last_nondup + vbL - 1, 8, s) || dev_sync(s))) return done(MC_ERR_CUDA);
+		std::vector<mc_u64> all;
+		if (gather_words(c, mine, 2, all)) return done(MC_ERR_NCCL);
+		int64_t carry[2] = {-1, -1};
+		for (int r = 0; r < c->comm_rank; r++) for (int k = 0; k < 2; k++) carry[k] = std::max(carry[k], (int64_t)all[(size_t)2 * r + k]);
+		if (vbF > 0)
+		{
+			if (dev_h2d(a.last_nongap + vbF - 1, &carry[0], 8, s) || dev_h2d(a.last_nondup + vbF - 1, &carry[1], 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+			if (nvo > 0) { device_incmax_i64(a.last_nongap + vbF - 1, nvo + 1, c->d_scan2.p, s); device_incmax_i64(a.last_nondup + vbF - 1, nvo + 1, c->d_scan2.p, s); }
+		}
+	}
+#endif
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), false, s); }
-	if (a.vp.gvcf) { device_incmax_i64(a.last_normal, nvb, c->d_scan2.p, s); device_incmax_i64(a.last_event, nvb, c->d_scan2.p, s); }
-	device_scan_u32(a.cnt, d_off.as<int64_t>(), nvb, d_scan.as<int64_t>(), s);
+	if (a.vp.gvcf && nvo > 0) { device_incmax_i64(a.last_normal + vbF, nvo, c->d_scan2.p, s); device_incmax_i64(a.last_event + vbF, nvo, c->d_scan2.p, s); }
 	int64_t total = 0;
-	if (dev_d2h(&total, d_off.as<int64_t>() + nvb, 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	if (nvo > 0)
+	{
+		device_scan_u32(a.cnt + vbF, d_off.as<int64_t>() + vbF, nvo, d_scan.as<int64_t>(), s);
+		if (dev_d2h(&total, d_off.as<int64_t>() + vbL, 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);
+	}
 	mark("count");
 	if (d_out.reserve((size_t)(total + 1) * sizeof(mc_variant_rec))) return done(MC_ERR_CUDA);
 	a.out = d_out.as<mc_variant_rec>();
 	for (int64_t t = 0; t < n_tiles; t++) { pack(t); launch_vcscan(a, vb0(t), vb1(t), true, s); }
 	mark("emit");
 	// CompByVarPos order on the device (mc_stages_vc.h: vckey_body), then ONE copy of the valid records into page-locked memory
-	if (total >= (int64_t)0xFFFFFFFFll) { mc_set_error("mc_variant_scan: more than 2^32 record slots (a monomorphic / gVCF scan of a genome this large does not fit)"); return done(MC_ERR_OVERFLOW); }
 	DBuf &d_vkey = c->d_vc[12], &d_vkey2 = c->d_vc[13], &d_vidx = c->d_vc[14], &d_vidx2 = c->d_vc[15], &d_vsort = c->d_vc[16], &d_out2 = c->d_vc[17];
-	if (d_vkey.reserve((size_t)(total + 1) * 8) || d_vkey2.reserve((size_t)(total + 1) * 8) || d_vidx.reserve((size_t)(total + 1) * 4) || d_vidx2.reserve((size_t)(total + 1) * 4)
-	    || d_vsort.reserve(device_sort_pairs_scratch_bytes(total))) return done(MC_ERR_CUDA);
 	mc_u64* d_nvalid = (mc_u64*)d_off.as<int64_t>() + (nvb + 1);   // d_off has nvb + 2 entries; the last one is free
+	// sorts `n` record slots of `src` by (gPos, VarType), unused slots last, and leaves the valid ones in d_out2
+	auto order = [&](const mc_variant_rec* src, int64_t n, int64_t* n_valid_out) -> int {
+		*n_valid_out = 0;
+		if (n >= (int64_t)0xFFFFFFFFll) { mc_set_error("mc_variant_scan: more than 2^32 record slots (a monomorphic / gVCF scan of a genome this large does not fit)"); return MC_ERR_OVERFLOW; }
+		if (d_vkey.reserve((size_t)(n + 1) * 8) || d_vkey2.reserve((size_t)(n + 1) * 8) || d_vidx.reserve((size_t)(n + 1) * 4) || d_vidx2.reserve((size_t)(n + 1) * 4)
+		    || d_vsort.reserve(device_sort_pairs_scratch_bytes(n))) return MC_ERR_CUDA;
+		if (dev_zero(d_nvalid, 8, s)) return MC_ERR_CUDA;
+		launch_vckey(n, src, d_vkey.as<uint64_t>(), d_vidx.as<uint32_t>(), d_nvalid, s);
+		device_sort_pairs(d_vkey.as<uint64_t>(), d_vkey2.as<uint64_t>(), d_vidx.as<uint32_t>(), d_vidx2.as<uint32_t>(), n, d_vsort.p, d_vsort.cap, s);
+		int64_t nv = 0;
+		if (dev_d2h(&nv, d_nvalid, 8, s) || dev_sync(s)) return MC_ERR_CUDA;
+		if (d_out2.reserve((size_t)(nv + 1) * sizeof(mc_variant_rec))) return MC_ERR_CUDA;
+		launch_vcgather(nv, src, d_vidx.as<uint32_t>(), d_out2.as<mc_variant_rec>(), s);
+		*n_valid_out = nv;
+		return MC_OK;
+	};
 	int64_t n_valid = 0;
-	if (dev_zero(d_nvalid, 8, s)) return done(MC_ERR_CUDA);
-	launch_vckey(total, a.out, d_vkey.as<uint64_t>(), d_vidx.as<uint32_t>(), d_nvalid, s);
-	device_sort_pairs(d_vkey.as<uint64_t>(), d_vkey2.as<uint64_t>(), d_vidx.as<uint32_t>(), d_vidx2.as<uint32_t>(), total, d_vsort.p, d_vsort.cap, s);
-	if (dev_d2h(&n_valid, d_nvalid, 8, s) || dev_sync(s)) return done(MC_ERR_CUDA);
-	if (d_out2.reserve((size_t)(n_valid + 1) * sizeof(mc_variant_rec)) || c->h_vc_out.reserve((size_t)(n_valid + 1) * sizeof(mc_variant_rec)) || c->h_vc_depth.reserve((size_t)(nvb + 1) * 4)) return done(MC_ERR_CUDA);
-	launch_vcgather(n_valid, a.out, d_vidx.as<uint32_t>(), d_out2.as<mc_variant_rec>(), s);
+	if ((rc = order(a.out, total, &n_valid)) != MC_OK) return done(rc);
+#ifndef MC_HOSTEMU
+	if (dist)
+	{
+		// records of all ranks, rank after rank (padded all-gather, compacted, ordered once more: a gap / dup run that ends in this
+		// rank's range may have started in an earlier one), and the block depths (equal chunks, in place)
+		const int N = c->comm_size;
+		mc_u64 mine = (mc_u64)n_valid; std::vector<mc_u64> cnts;
+		if (gather_words(c, &mine, 1, cnts)) return done(MC_ERR_NCCL);
+		int64_t mx = 1, sum = 0; for (int r = 0; r < N; r++) { mx = std::max(mx, (int64_t)cnts[r]); sum += (int64_t)cnts[r]; }
+		DBuf& d_all = d_out;                               // the slots are no longer needed
+		if (d_out2.grow_keep((size_t)(mx + 1) * sizeof(mc_variant_rec), (size_t)n_valid * sizeof(mc_variant_rec), s) || d_all.reserve((size_t)(mx + 1) * N * sizeof(mc_variant_rec))) return done(MC_ERR_CUDA);
+		if (nccl_fail(ncclAllGather(d_out2.p, d_all.p, (size_t)mx * sizeof(mc_variant_rec), ncclUint8, c->comm, s), "ncclAllGather(variant records)")) return done(MC_ERR_NCCL);
+		DBuf& d_cat = c->d_comm_buf;
+		if (d_cat.reserve((size_t)(sum + 1) * sizeof(mc_variant_rec))) return done(MC_ERR_CUDA);
+		int64_t o = 0;
+		for (int r = 0; r < N; r++) { if (cnts[r] && dev_d2d(d_cat.as<mc_variant_rec>() + o, d_all.as<uint8_t>() + (size_t)r * mx * sizeof(mc_variant_rec), (size_t)cnts[r] * sizeof(mc_variant_rec), s)) return done(MC_ERR_CUDA); o += (int64_t)cnts[r]; }
+		if ((rc = order(d_cat.as<mc_variant_rec>(), sum, &n_valid)) != MC_OK) return done(rc);
+		const int64_t chunk = (c->own_tile / MC_VC_BLOCK);
+		if (nccl_fail(ncclAllGather(d_depth.as<int32_t>() + (size_t)c->comm_rank * chunk, d_depth.p, (size_t)chunk, ncclInt32, c->comm, s), "ncclAllGather(block depths)")) return done(MC_ERR_NCCL);
+	}
+#endif
+	if (c->h_vc_out.reserve((size_t)(n_valid + 1) * sizeof(mc_variant_rec)) || c->h_vc_depth.reserve((size_t)(nvb + 1) * 4)) return done(MC_ERR_CUDA);
 	if (dev_d2h(c->h_vc_out.p, d_out2.p, (size_t)n_valid * sizeof(mc_variant_rec), s) || dev_d2h(c->h_vc_depth.p, d_depth.p, (size_t)nvb * 4, s) || dev_sync(s)) return done(MC_ERR_CUDA);
 	mark("order+d2h");
 	mc_variant_rec* vo = c->h_vc_out.as<mc_variant_rec>();
@@ -1691,6 +1808,7 @@ int mc_variant_scan(mc_ctx* c, const mc_vc_params* vp, const mc_variant_rec** re
 int mc_comm_unique_id(uint8_t*) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
 int mc_comm_init(mc_ctx*, const uint8_t*, int32_t, int32_t) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
 int mc_profile_allreduce(mc_ctx*, void*) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
+int mc_profile_reduce_scatter(mc_ctx*) { mc_set_error("no NCCL in the developer harness"); return MC_ERR_NCCL; }
 #else
 int mc_comm_unique_id(uint8_t* out)
 {
@@ -1728,9 +1846,10 @@ __global__ void mc_clamp_u8_kernel(uint8_t* p, int64_t n, int hi)
 // Sums what is additive across the shards (difference arrays, base counters, dedup counts, totals) with ncclAllReduce and
 // gathers the variable-length records (indels, break points, SV sites), so that afterwards every rank holds the profile
 // of the whole library.  `nccl_comm` may be an ncclComm_t created by the caller; NULL uses the one set up by mc_comm_init.
-int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
+static int profile_reduce(mc_ctx* c, void* nccl_comm, bool scatter)
 {
 	if (!c) { mc_set_error("mc_profile_allreduce: null context"); return MC_ERR_ARG; }
+	if (c->scattered) { mc_set_error("mc_profile_allreduce: the profile has already been reduced (mc_reset starts the next library)"); return MC_ERR_ARG; }
 	ncclComm_t comm = nccl_comm ? (ncclComm_t)nccl_comm : c->comm;
 	if (!comm) { mc_set_error("mc_profile_allreduce: no communicator (call mc_comm_init first)"); return MC_ERR_NCCL; }
 	if (!nccl_api()) return MC_ERR_NCCL;
@@ -1755,20 +1874,50 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 		if (c->comm_size > 16) { mc_set_error("mc_profile_allreduce: independent shards are limited to 16 ranks (packed 16-bit counters)"); return MC_ERR_ARG; }
 		mc_clamp_base16_kernel<<<(unsigned)((G * 2 + 255) / 256), 256, 0, s>>>(c->d_base16.as<uint32_t>(), (int64_t)(G * 2));
 	}
+	// equal tiles of whole MC_TILE_ALIGN units, one per rank (the arrays are padded for it, mc_ctx_create)
+	const size_t T = ((G + (size_t)c->comm_size - 1) / (size_t)c->comm_size + MC_TILE_ALIGN - 1) / MC_TILE_ALIGN * MC_TILE_ALIGN, me = (size_t)c->comm_rank;
+	if (scatter && (comm != c->comm || c->comm_size > 16)) { mc_set_error("mc_profile_reduce_scatter: needs the communicator of mc_comm_init and at most 16 ranks"); return MC_ERR_ARG; }
 	nccl_api()->GroupStart();
 	// packed 2 x uint16 counters are summed as uint32 words: no carry can cross the halves while every column stays below 65536
-	bad |= nccl_fail(ncclAllReduce(c->d_base16.p, c->d_base16.p, G * 2, ncclUint32, ncclSum, comm, s), "ncclAllReduce(base16)");
-	bad |= nccl_fail(ncclAllReduce(c->d_sdiff.p, c->d_sdiff.p, (G + 1) * 4, ncclInt32, ncclSum, comm, s), "ncclAllReduce(sdiff)");
-	bad |= nccl_fail(ncclAllReduce(c->d_cdiff.p, c->d_cdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(cdiff)");
-	bad |= nccl_fail(ncclAllReduce(c->d_mdiff.p, c->d_mdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(mdiff)");
-	if (independent)
+	if (!scatter)
 	{
-		bad |= nccl_fail(ncclAllReduce(c->d_rcount.p, c->d_rcount.p, G, ncclUint8, ncclSum, comm, s), "ncclAllReduce(rcount)");
-		bad |= nccl_fail(ncclAllReduce(d_tot, d_tot, 5, ncclInt64, ncclSum, comm, s), "ncclAllReduce(totals)");
+		bad |= nccl_fail(ncclAllReduce(c->d_base16.p, c->d_base16.p, G * 2, ncclUint32, ncclSum, comm, s), "ncclAllReduce(base16)");
+		bad |= nccl_fail(ncclAllReduce(c->d_sdiff.p, c->d_sdiff.p, (G + 1) * 4, ncclInt32, ncclSum, comm, s), "ncclAllReduce(sdiff)");
+		bad |= nccl_fail(ncclAllReduce(c->d_cdiff.p, c->d_cdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(cdiff)");
+		bad |= nccl_fail(ncclAllReduce(c->d_mdiff.p, c->d_mdiff.p, G + 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce(mdiff)");
+		if (independent) bad |= nccl_fail(ncclAllReduce(c->d_rcount.p, c->d_rcount.p, G, ncclUint8, ncclSum, comm, s), "ncclAllReduce(rcount)");
 	}
+	else
+	{
+		// in place: rank r receives the sums of tile r where they already lie; half the traffic of the all-reduce, and the
+		// read-out that follows (variant scan, summary) runs on N tiles at once
+		bad |= nccl_fail(ncclReduceScatter(c->d_base16.p, c->d_base16.as<uint32_t>() + me * T * 2, T * 2, ncclUint32, ncclSum, comm, s), "ncclReduceScatter(base16)");
+		bad |= nccl_fail(ncclReduceScatter(c->d_sdiff.p, c->d_sdiff.as<int32_t>() + me * T * 4, T * 4, ncclInt32, ncclSum, comm, s), "ncclReduceScatter(sdiff)");
+		bad |= nccl_fail(ncclReduceScatter(c->d_cdiff.p, c->d_cdiff.as<int32_t>() + me * T, T, ncclInt32, ncclSum, comm, s), "ncclReduceScatter(cdiff)");
+		bad |= nccl_fail(ncclReduceScatter(c->d_mdiff.p, c->d_mdiff.as<int32_t>() + me * T, T, ncclInt32, ncclSum, comm, s), "ncclReduceScatter(mdiff)");
+		if (independent) bad |= nccl_fail(ncclReduceScatter(c->d_rcount.p, c->d_rcount.as<uint8_t>() + me * T, T, ncclUint8, ncclSum, comm, s), "ncclReduceScatter(rcount)");
+	}
+	if (independent) bad |= nccl_fail(ncclAllReduce(d_tot, d_tot, 5, ncclInt64, ncclSum, comm, s), "ncclAllReduce(totals)");
 	bad |= nccl_fail(nccl_api()->GroupEnd(), "ncclGroupEnd");
 	if (bad) return MC_ERR_NCCL;
 	if (independent) mc_clamp_u8_kernel<<<(unsigned)((G + 255) / 256), 256, 0, s>>>(c->d_rcount.as<uint8_t>(), (int64_t)G, c->prm.max_dup);
+	if (scatter)
+	{
+		c->own_tile = (int64_t)T;
+		c->own_beg = (int64_t)std::min(G, me * T); c->own_end = (int64_t)std::min(G, (me + 1) * T);
+		for (int k = 0; k < 6; k++) c->own_carry[k] = 0;
+		// the difference arrays are read as prefix sums: this rank needs the sums of all columns before its tile = the tile totals of the ranks before it
+		DevProfile p; p.base16 = c->d_base16.as<uint32_t>(); p.sdiff = c->d_sdiff.as<int32_t>(); p.cdiff = c->d_cdiff.as<int32_t>(); p.mdiff = c->d_mdiff.as<int32_t>(); p.rcount = c->d_rcount.as<uint8_t>();
+		const int64_t nb = ((int64_t)G + MC_PROF_BLOCK - 1) / MC_PROF_BLOCK;
+		DBuf& d_sums = c->d_vc[0];
+		if (d_sums.reserve((size_t)(6 * nb + 8) * 8) || c->d_scan2.reserve(device_scan_scratch_bytes(nb)) || dev_zero(d_sums.as<int64_t>() + 6 * nb, 48, s)) return MC_ERR_CUDA;
+		mc_u64 mine[6] = {0, 0, 0, 0, 0, 0};
+		if (c->own_end > c->own_beg && (profile_prefix(c, p, nb, d_sums.as<int64_t>(), s) || dev_d2h(mine, d_sums.as<int64_t>() + 6 * nb, 48, s) || dev_sync(s))) return MC_ERR_CUDA;
+		std::vector<mc_u64> all;
+		if (gather_words(c, mine, 6, all)) return MC_ERR_NCCL;
+		for (int r = 0; r < c->comm_rank; r++) for (int k = 0; k < 6; k++) c->own_carry[k] += (int64_t)all[(size_t)6 * r + k];
+		c->scattered = true;
+	}
 	if (dev_d2h(t, d_tot, sizeof(t), s)) return MC_ERR_CUDA;   // completes with the next synchronize (record exchange below)
 	// variable-length records (break points, indels with their sequences, SV sites): every rank ends up with the records of
 	// all ranks in rank (= file) order.  The payload goes device to device; only the counts pass through the host.
@@ -1841,10 +1990,23 @@ int mc_profile_allreduce(mc_ctx* c, void* nccl_comm)
 	if (dev_sync(s)) return MC_ERR_CUDA;
 	c->stats.ms_reduce += ev_ms(&c->ev[EV_RED0], &c->ev[EV_RED1]);
 	const size_t mine_bytes = my_bp * 8 + my_ind * sizeof(mc_indel_rec) + my_seq;
-	if (dbg) fprintf(stderr, "[mc] rank %d allreduce: counters %.3f ms, records %.3f ms (%zu bytes mine)\n", c->comm_rank, t_reduced - t_begin, now() - t_reduced, mine_bytes);
+	if (dbg) fprintf(stderr, "[mc] rank %d %s: counters %.3f ms, records %.3f ms (%zu bytes mine)\n", c->comm_rank, scatter ? "reduce-scatter" : "allreduce", t_reduced - t_begin, now() - t_reduced, mine_bytes);
 	return MC_OK;
 }
+int mc_profile_allreduce(mc_ctx* c, void* nccl_comm) { return profile_reduce(c, nccl_comm, false); }
+// The scalable end of a library on N GPUs: every rank keeps the sums of ONE tile of the genome (ncclReduceScatter in place, half
+// the traffic of the all-reduce) and the read-out calls become collectives over the tiles - mc_variant_scan scans the tile
+// and gathers the records of all ranks, mc_profile_summary / mc_profile_checksum combine the tiles' partial results,
+// mc_profile_read serves the tile's columns (mc_profile_owned tells which).  Indel / break-point / SV-site records are
+// gathered to every rank as in mc_profile_allreduce.
+int mc_profile_reduce_scatter(mc_ctx* c) { return profile_reduce(c, nullptr, true); }
 #endif
+int mc_profile_owned(const mc_ctx* c, int64_t* beg, int64_t* end)
+{
+	if (!c || !beg || !end) { mc_set_error("mc_profile_owned: null argument"); return MC_ERR_ARG; }
+	*beg = c->own_beg; *end = c->own_end;
+	return MC_OK;
+}
 
 // Operator-level entry: seeding, locate and clustering of a batch (the front of run_batch), results back to the host.
 int mc_seed_cluster_batch(mc_ctx* c, const mc_batch_in* in, mc_seed_cluster_out* out)

@@ -33,7 +33,7 @@ static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
 static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump; for (int64_t i = 0; i < n; i++) a.st->profile_atomics += profpiece_body(i, 0, 1, a, q); }
 static void launch_disclist(const PipeArgs& a, int64_t n, DiscRec* out, mc_u64* bump, int64_t cap, mc_stream_t) { for (int64_t i = 0; i < n; i++) disclist_body(i, a, out, bump, cap); }
-static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t) { for (int64_t b = 0; b < nb; b++) profsum_body(b, 0, 1, p, G, nb, sums); }
+static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t b0, int64_t b1, int64_t* sums, mc_stream_t) { for (int64_t b = b0; b < b1; b++) profsum_body(b, 0, 1, p, G, nb, sums); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t)
 { for (int64_t b = b0; b < b1; b++) profpack_body(b, 0, 1, ix, p, nb, pre, beg, end, out); }
 static void launch_cbwt_build(int64_t n, const uint32_t* src, uint32_t* dst, mc_stream_t) { for (int64_t b = 0; b < n; b++) mc_cbwt_build_body(b, src, dst); }
@@ -262,10 +262,10 @@ __global__ void __launch_bounds__(MC_BLOCK) mc_ktab_build_kernel(const DevIndex 
 { int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (m < (1ll << (2 * k))) mc_ktab_build_body(m, ix, k, o32, o64); }
 static void launch_ktab_build(const DevIndex& ix, int k, uint32_t* o32, uint64_t* o64, mc_stream_t s)
 { const int64_t n = 1ll << (2 * k); mc_ktab_build_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(ix, k, o32, o64); g_launches++; }
-__global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t* sums)
-{ int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; if (b < nb) profsum_body(b, threadIdx.x & 31, 32, p, G, nb, sums); }   // whole warps leave together
-static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t* sums, mc_stream_t s)
-{ if (nb > 0) { mc_profsum_kernel<<<(unsigned)((nb * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(p, G, nb, sums); g_launches++; } }
+__global__ void __launch_bounds__(MC_BLOCK) mc_profsum_kernel(const DevProfile p, int64_t G, int64_t nb, int64_t b0, int64_t b1, int64_t* sums)
+{ int64_t b = b0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5); if (b < b1) profsum_body(b, threadIdx.x & 31, 32, p, G, nb, sums); }   // whole warps leave together
+static void launch_profsum(const DevProfile& p, int64_t G, int64_t nb, int64_t b0, int64_t b1, int64_t* sums, mc_stream_t s)
+{ if (b1 > b0) { mc_profsum_kernel<<<(unsigned)(((b1 - b0) * 32 + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, s>>>(p, G, nb, b0, b1, sums); g_launches++; } }
 __global__ void __launch_bounds__(MC_BLOCK) mc_profpack_kernel(const DevIndex ix, const DevProfile p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out)
 { int64_t b = b0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5); if (b < b1) profpack_body(b, threadIdx.x & 31, 32, ix, p, nb, pre, beg, end, out); }
 static void launch_profpack(const DevIndex& ix, const DevProfile& p, int64_t nb, const int64_t* pre, int64_t b0, int64_t b1, int64_t beg, int64_t end, uint64_t* out, mc_stream_t s)

@@ -165,3 +165,50 @@ def test_one_process_two_devices(built):
         pu.assert_same(got[k], want)
     for ctx in ctxs:
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("n_pairs,seed", [(20000, 64), (600, 65), (250, 66)])
+def test_reduce_scatter_read_out_equals_one_gpu(built, tmp_path, n_pairs, seed):
+    """mc_profile_reduce_scatter: every rank keeps the counters of one genome tile; the packed columns of the tiles, the variant
+    scan (default, monomorphic and low-threshold parameters; thin libraries put gap runs across the tile border), the summary
+    and the checksum must equal those of ONE context that mapped the whole library."""
+    code = textwrap.dedent("""
+        import os, sys
+        import numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import torch, torch.distributed as dist
+        import parity_util as pu
+        from mapcaller_b200 import api, shard
+        rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+        torch.cuda.set_device(rank); dist.init_process_group('nccl')
+        case = pu.make_case(seed=%d, n_pairs=%d, genome_len=120000, contigs=2, sv=2.0, n_dup=10)
+        ix = pu.build_index(case)
+        ctx = api.Context(ix, paired=1, device=rank, shard_rank=rank, shard_count=world)
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        seq, off = shard.take_shard(case['seq'], case['off'], world, rank)
+        ctx.map_batch(seq, off)
+        ctx.profile_reduce_scatter()
+        beg, end = ctx.profile_owned()
+        assert (beg, end) == ((0, 76800) if rank == 0 else (76800, 120000)), (beg, end)
+        solo = api.Context(ix, paired=1, device=rank)
+        solo.map_batch(case['seq'], case['off'])
+        assert np.array_equal(ctx.profile(beg, end), solo.profile(beg, end)), 'packed columns of the tile'
+        assert ctx.profile_summary() == solo.profile_summary(), 'summary'
+        assert ctx.profile_checksum() == solo.profile_checksum(), 'checksum'
+        for kw in (dict(), dict(monomorphic=1), dict(min_allele_depth=1, frequency_thr=0.05, min_cnv_size=5, min_unmapped_size=5), dict(somatic=1, ploidy=1)):
+            (ra, da), (rb, db) = ctx.variant_scan(**kw), solo.variant_scan(**kw)
+            assert len(ra) == len(rb) and ra == rb, ('records', kw, len(ra), len(rb), [x for x, y in zip(ra, rb) if x != y][:2])
+            assert np.array_equal(da, db), ('block depths', kw)
+            assert len(rb) > 10
+        try:
+            ctx.variant_scan(gvcf=1); raise SystemExit('a gVCF scan must be refused after a reduce-scatter')
+        except api.McError:
+            pass
+        dist.barrier(); dist.destroy_process_group()
+    """) % (ROOT, os.path.join(ROOT, "tests"), seed, n_pairs)
+    script = tmp_path / "w.py"
+    script.write_text(code)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)])

@@ -9,6 +9,11 @@ def ms(x):
     return v / 1e6 if u == 'ns' else v / 1e3 if u == 'us' else v
 idx = [i for i, x in enumerate(rows) if 'mc_seed_kernel' in x['Kernel Name']]
 start = idx[1] if len(idx) > 1 else idx[0]          # warm-up 1 + the timed resident step
+if "--skip-for" in sys.argv:      # how many launches matching the regex precede the timed pass (for ncu --launch-skip)
+    import re
+    rx = re.compile(sys.argv[sys.argv.index("--skip-for") + 1])
+    print(sum(1 for x in rows[:start] if rx.search(x['Kernel Name'])))
+    sys.exit(0)
 agg = collections.OrderedDict(); tot = 0
 for x in rows[start:]:
     if x['Kernel Name'].startswith(('mc_seedcap', 'mc_profsum')): break
