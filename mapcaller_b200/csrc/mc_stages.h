@@ -203,6 +203,7 @@ template <> struct SeedOps<RcInterval32> {
 	}
 };
 
+#define MC_SEED_CMP_REPS 4
 #define MC_SEED_LOCATED (1ull << 63)   // Seed::x0 of a seed whose single occurrence is already known: the text position, not a BWT row
 
 // One thread walks one read left to right through the reference's greedy scheme (IdentifySimplePairs + BWT_Search,
@@ -315,7 +316,7 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 				}
 			}
 		}
-		else
+		else for (int rep = 0; rep < MC_SEED_CMP_REPS && !end; rep++)   // several 8-base comparisons per turn of the compare group: fewer turns per read, less waiting for the other groups
 		{
 			if (p >= rlen) end = true;
 			else
