@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "slow: about a minute each (full-size parity against the unmodified reference); still part of `-m gpu`")
 
 
 @pytest.fixture(scope="session")
