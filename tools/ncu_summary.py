@@ -21,7 +21,7 @@ kn = hdr.index("Kernel Name")
 print("%-34s %9s %9s %9s %8s %7s %6s %6s %5s %7s %6s %7s %7s" % ("kernel", "ms", "DRAM rd GB", "wr GB", "TB/s", "IPC", "lanes", "occ%", "regs", "grid", "block", "L1hit%", "L2hit%"))
 best = {}
 for r in rows[2:]:
-    name = r[kn].split("(")[0].replace("void ", "")
+    name = r[kn].split("(")[0].replace("void ", "").split("<")[0]
     v = {k: val(r, m) for m, k in COLS}
     tb = ((v["rd"] or 0) + (v["wr"] or 0)) / (v["ms"] * 1e-3) / 1e12 if v["ms"] else 0
     print("%-34s %9.3f %9.3f %9.3f %8.2f %7.2f %6.1f %6.1f %5d %7d %6d %7.1f %7.1f" % (name[:34], v["ms"], (v["rd"] or 0) / 1e9, (v["wr"] or 0) / 1e9, tb, v["issue%"] or 0, v["lanes"] or 0,
