@@ -56,7 +56,9 @@ GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 1593
 CONFIGS = {
     2: dict(name="configs[2]: chr1-sized", genome=GENOME_LEN, contigs=None, read_len=150, ksw2=0, frag_mean=450, small_indel=100, large_indel=0, read_indel=0.0),
     3: dict(name="configs[3]: GRCh38-sized", genome=sum(GRCH38), contigs=GRCH38, read_len=150, ksw2=0, frag_mean=450, small_indel=100, large_indel=0, read_indel=0.0),
-    4: dict(name="configs[4]: GRCh38-sized, ksw2 stress", genome=sum(GRCH38), contigs=GRCH38, read_len=250, ksw2=1, frag_mean=600, small_indel=2000, large_indel=500, read_indel=0.4),
+    # 250-bp reads with alignment strings for nearly every read: 500 k pairs per batch keep the batch's arenas below 2^31 bytes
+    4: dict(name="configs[4]: GRCh38-sized, ksw2 stress", genome=sum(GRCH38), contigs=GRCH38, read_len=250, ksw2=1, frag_mean=600, small_indel=2000, large_indel=500, read_indel=0.4,
+            batch=500_000, pairs=2_500_000),
 }
 CFG = CONFIGS[2]
 SIM_BLOCK = 250_000          # simulate_pairs_fast generates independent blocks of this many pairs
@@ -247,7 +249,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[] index (default 2: chr1-sized, 2x150, nw)")
-    ap.add_argument("--pairs", type=int, default=FULL_PAIRS, help="library size per GPU (default: 10 M pairs)")
+    ap.add_argument("--pairs", type=int, default=0, help="library size per GPU (default: 10 M pairs; 2.5 M for configs[4])")
     ap.add_argument("--genome", type=int, default=0, help="genome size in bp (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (default: sized for ~10-30 s)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -257,8 +259,10 @@ def main():
     ap.add_argument("--trace-e2e", action="store_true", help="print a host-side timeline of one end-to-end step to stderr")
     ap.add_argument("--resident-only", action="store_true", help="profiling runs: only the resident leg (the JSON line then has no e2e)")
     args = ap.parse_args()
-    global CFG, READ_LEN
+    global CFG, READ_LEN, BATCH_PAIRS
     CFG = CONFIGS[args.config]; READ_LEN = CFG["read_len"]
+    BATCH_PAIRS = CFG.get("batch", BATCH_PAIRS)
+    args.pairs = args.pairs or CFG.get("pairs", FULL_PAIRS)
     args.genome = args.genome or CFG["genome"]
     args.pairs -= args.pairs % SIM_BLOCK
     assert args.pairs >= SIM_BLOCK, "--pairs must be at least %d" % SIM_BLOCK
