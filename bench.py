@@ -398,6 +398,17 @@ def main():
     resident_fp = ctx.profile_checksum()
 
     # ---- end-to-end leg: FASTQ text (host) -> variant records (host) ----
+    # The end-to-end feed cuts the library's FASTQ text into blocks of its own: the first one small (the pipeline starts mapping
+    # after 0.2 M pairs are on the device instead of 2 M), then the 2 M-pair batches; block boundaries are multiples of the
+    # reference's 200-read chunk, so the result is the resident path's (check.fastq_path_equals_resident).
+    FIRST = max(100, min(200_000, BATCH_PAIRS // 10) // 100 * 100)
+    blocks = []
+    for b, (p0, p1) in enumerate(bounds):
+        cuts = [0, min(FIRST, p1 - p0), p1 - p0] if b == 0 and p1 - p0 > FIRST else [0, p1 - p0]
+        for c0, c1 in zip(cuts[:-1], cuts[1:]):
+            blocks.append((ptext[b][0][c0 * rec_bytes:c1 * rec_bytes], ptext[b][1][c0 * rec_bytes:c1 * rec_bytes]))
+    n_blocks = len(blocks)
+
     def fastq_pass(sam: bool):
         # three device slots in flight: block b+1 on the wire (mc_ingest_prefetch, plain DMA), block b being parsed
         # (mc_ingest_fastq) by the feeder thread, block b-1 being mapped by this thread
@@ -410,12 +421,12 @@ def main():
 
         def feeder():
             try:
-                free[0].acquire(); ctx.ingest_prefetch(ptext[0][0], ptext[0][1], slot=slot(0))
-                for b in range(n_batches):
-                    if b + 1 < n_batches:
-                        free[(b + 1) % 3].acquire(); ctx.ingest_prefetch(ptext[b + 1][0], ptext[b + 1][1], slot=slot(b + 1))
+                free[0].acquire(); ctx.ingest_prefetch(blocks[0][0], blocks[0][1], slot=slot(0))
+                for b in range(n_blocks):
+                    if b + 1 < n_blocks:
+                        free[(b + 1) % 3].acquire(); ctx.ingest_prefetch(blocks[b + 1][0], blocks[b + 1][1], slot=slot(b + 1))
                     mark("ingest begin", b)
-                    ctx.ingest_fastq(ptext[b][0], ptext[b][1], slot=slot(b), final=True)
+                    ctx.ingest_fastq(blocks[b][0], blocks[b][1], slot=slot(b), final=True)
                     mark("ingest end", b)
                     ready[b % 3].release()
             except Exception as e:      # surfaces in the main thread
@@ -424,7 +435,7 @@ def main():
                     s_.release()
         th = threading.Thread(target=feeder); th.start()
         sam_bytes = 0
-        for b in range(n_batches):
+        for b in range(n_blocks):
             ready[b % 3].acquire()
             if err:
                 break

@@ -193,6 +193,7 @@ struct mc_ctx {
 	DBuf d_cands, d_ncand0, d_ncand, d_cscore, d_cpaired, d_corient, d_cfrag, d_cnfrag, d_ctmp;
 	DBuf d_est, d_active, d_pair_flag, d_est_lo, d_est_hi, d_pair_out, d_chunk_out, d_chunk_lo, d_chunk_hi;
 	DBuf d_rsum, d_frags, d_aln, d_tasks, d_dpws, d_rtask, d_rwin, d_rw_beg, d_bumps, d_stats, d_scan;
+	DBuf d_rnp;
 	DBuf d_keys, d_keys_tmp, d_accept, d_sort, d_read_redo, d_cap, d_ptask, d_disc, d_cand_off, d_scan2;
 	HBuf h_disc;
 	HBuf h_bounce[2], h_push; size_t push_at = 0;
@@ -254,7 +255,7 @@ void mc_ctx_destroy(mc_ctx* c)
 	                &c->d_ind_seq, &c->d_pbump, &c->d_slot_freq, &c->d_seeds, &c->d_slot_loc, &c->d_loc_slot, &c->d_pairs, &c->d_npair, &c->d_cands,
 	                &c->d_ncand0, &c->d_ncand, &c->d_cscore, &c->d_cpaired, &c->d_corient, &c->d_cfrag, &c->d_cnfrag, &c->d_ctmp, &c->d_est, &c->d_active,
 	                &c->d_pair_flag, &c->d_est_lo, &c->d_est_hi, &c->d_pair_out, &c->d_chunk_out, &c->d_chunk_lo, &c->d_chunk_hi, &c->d_rsum, &c->d_frags,
-	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off, &c->d_scan2};
+	                &c->d_aln, &c->d_tasks, &c->d_dpws, &c->d_rtask, &c->d_rwin, &c->d_rw_beg, &c->d_bumps, &c->d_stats, &c->d_scan, &c->d_keys, &c->d_keys_tmp, &c->d_accept, &c->d_rnp, &c->d_sort, &c->d_read_redo, &c->d_cap, &c->d_ptask, &c->d_disc, &c->d_cand_off, &c->d_scan2};
 	for (DBuf* b : bufs) b->release();
 	for (DBuf& b : c->d_vc) b.release();
 	for (DBuf& b : c->d_ia) b.release();
@@ -713,7 +714,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 	bad |= c->d_est.reserve(n_chunks * 4) || c->d_active.reserve(n_chunks) || c->d_chunk_out.reserve(mxc * sizeof(mc_chunk_out));
 	bad |= c->d_chunk_lo.reserve(mxc * 4) || c->d_chunk_hi.reserve(mxc * 4);
 	bad |= c->d_pair_flag.reserve((n_pairs + 1) * 4) || c->d_est_lo.reserve((n_pairs + 1) * 4) || c->d_est_hi.reserve((n_pairs + 1) * 4);
-	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4 * 4) || c->d_rw_beg.reserve((n_pairs + 1) * 4) || c->d_accept.reserve(n + 1) || c->d_read_redo.reserve(n + 1);
+	bad |= c->d_pair_out.reserve((n_pairs + 1) * sizeof(mc_pair_out)) || c->d_rtask.reserve((n_pairs + 1) * 4 * 4) || c->d_rw_beg.reserve((n_pairs + 1) * 4) || c->d_accept.reserve(n + 1) || c->d_rnp.reserve((n + 1) * 4) || c->d_read_redo.reserve(n + 1);
 	bad |= c->h_chunk.reserve(n_chunks * sizeof(mc_chunk_out)) || c->h_chunk_lo.reserve(n_chunks * 4) || c->h_chunk_hi.reserve(n_chunks * 4);
 	if (bad) return MC_ERR_CUDA;
 	a.slot_freq = c->d_slot_freq.as<uint32_t>(); a.seeds = c->d_seeds.as<Seed>(); a.slot_loc = c->d_slot_loc.as<int64_t>();
@@ -913,7 +914,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 			if (c->ind_seq_cap >= 0x7fffffffll) { mc_set_error("indel sequence arena exceeds 2 GiB; call mc_profile_indels() earlier"); return MC_ERR_OVERFLOW; }
 			PersistBumps* dpb = c->d_pbump.as<PersistBumps>();
 			ProfArgs q; memset(&q, 0, sizeof(q));
-			q.keys = c->d_keys.as<uint64_t>(); q.key_bump = &db->key; q.accept = c->d_accept.as<uint8_t>();
+			q.keys = c->d_keys.as<uint64_t>(); q.key_bump = &db->key; q.accept = c->d_accept.as<uint8_t>(); q.rnp = c->d_rnp.as<int32_t>();
 			q.bp_pos = c->d_bp.as<int64_t>(); q.bp_bump = &dpb->bp; q.bp_cap = c->bp_cap;
 			q.ind = c->d_ind.as<mc_indel_rec>(); q.ind_bump = &dpb->ind; q.ind_cap = c->ind_cap;
 			q.ind_seq = c->d_ind_seq.as<uint8_t>(); q.ind_seq_bump = &dpb->ind_seq; q.ind_seq_cap = c->ind_seq_cap;

@@ -14,6 +14,7 @@
 struct ProfArgs {
 	uint64_t* keys; mc_u64* key_bump;        // gate candidates of this batch
 	uint8_t* accept;                         // per read: 0 skip, 1 UpdateProfile, 2 UpdateMultiHitCount
+	int32_t* rnp;                            // per read with a gate key: its live candidate (<< 16) and how many of its pieces have aligned columns
 	int64_t n_keys;
 	int64_t* bp_pos; mc_u64* bp_bump; int64_t bp_cap;                  // BreakPointMap increments (persistent)
 	mc_indel_rec* ind; mc_u64* ind_bump; int64_t ind_cap;              // InsertSeqMap / DeleteSeqMap increments (persistent)
@@ -56,6 +57,10 @@ MC_HD uint64_t profkey_of(int64_t r, const PipeArgs& a, const ProfArgs& q)
 	}
 	const int64_t start = a.corient[co + ci] ? first.gPos : a.ix.twoG - (first.gPos + first.gLen);
 	if (start < 0 || start >= a.ix.G) return none; // the reference would index outside MappingRecordArr
+	// what scatter_body needs before its block-wide cursor bump, so that it does not have to walk read -> candidate -> fragments first
+	int np = 0;
+	for (int k = 0; k < nf; k++) if (!f[k].bSimple && f[k].gLen != 0 && f[k].rLen != 0) np++;
+	q.rnp[r] = (int32_t)(((uint32_t)ci << 16) | (uint32_t)(np > 0xFFFF ? 0xFFFF : np));
 	return ((uint64_t)start << MC_KEY_SHIFT) | (uint64_t)r;
 }
 MC_HD void profkey_body(int64_t r, bool live, const PipeArgs& a, const ProfArgs& q)
@@ -176,18 +181,20 @@ MC_HD void scatter_body(int64_t r, bool live, const PipeArgs& a, const ProfArgs&
 			if (g1 > g0) mc_stat_add(&a.st->profile_columns, (uint32_t)(g1 - g0));
 		}
 	}
-	int ci = 0;
-	const mc_frag_out* f = nullptr; int nf = 0, np = 0;
-	if (mode == 1)
-	{
-		while (ci < nc && a.cscore[co + ci] == 0) ci++;
-		f = a.frags + a.cfrag[co + ci]; nf = a.cnfrag[co + ci];
-		for (int k = 0; k < nf; k++) if (!f[k].bSimple && f[k].gLen != 0 && f[k].rLen != 0) np++;
-	}
 	// pieces with aligned columns are left to profpiece_body (a tile per piece): their queue slots come from one block-wide
-	// cursor bump, in which every thread of the block takes part
+	// cursor bump, in which every thread of the block takes part - with the count profkey_of left behind (one coalesced load), so
+	// that no thread waits at the barrier for another one's chain of dependent loads
+	const uint32_t hint = mode == 1 ? (uint32_t)q.rnp[r] : 0u;
+	int ci = (int)(hint >> 16), np = (int)(hint & 0xFFFFu);
+	const mc_frag_out* f = nullptr; int nf = 0;
+	if (mode == 1 && np == 0xFFFF)            // (more pieces than the hint can say: count them)
+	{
+		f = a.frags + a.cfrag[co + ci]; nf = a.cnfrag[co + ci];
+		np = 0; for (int k = 0; k < nf; k++) if (!f[k].bSimple && f[k].gLen != 0 && f[k].rLen != 0) np++;
+	}
 	int64_t pt = mc_block_bump(a.ptask_bump, (uint32_t)np);
 	if (mode != 1) return;
+	f = a.frags + a.cfrag[co + ci]; nf = a.cnfrag[co + ci];
 	const bool fwd = a.corient[co + ci] != 0;
 	const bool first_mate = a.pr.paired ? (((a.first_read + r) & 1) == 0) : true;
 	const int64_t start = fwd ? f[0].gPos : a.ix.twoG - (f[0].gPos + f[0].gLen);
