@@ -399,12 +399,16 @@ def main():
 
     # ---- end-to-end leg: FASTQ text (host) -> variant records (host) ----
     # The end-to-end feed cuts the library's FASTQ text into blocks of its own: the first one small (the pipeline starts mapping
-    # after 0.2 M pairs are on the device instead of 2 M), then the 2 M-pair batches; block boundaries are multiples of the
+    # after 0.2 M pairs are on the device instead of 2 M), then the 2 M-pair batches, and a small last one; block boundaries are multiples of the
     # reference's 200-read chunk, so the result is the resident path's (check.fastq_path_equals_resident).
     FIRST = max(100, min(200_000, BATCH_PAIRS // 10) // 100 * 100)
     blocks = []
     for b, (p0, p1) in enumerate(bounds):
-        cuts = [0, min(FIRST, p1 - p0), p1 - p0] if b == 0 and p1 - p0 > FIRST else [0, p1 - p0]
+        cuts = [0, p1 - p0]
+        if b == 0 and p1 - p0 > FIRST:
+            cuts.insert(1, FIRST)                      # a small first block: mapping starts early
+        if b == len(bounds) - 1 and cuts[-1] - cuts[-2] > FIRST:
+            cuts.insert(len(cuts) - 1, p1 - p0 - FIRST)  # and a small last one: little is left to map when the last byte has arrived
         for c0, c1 in zip(cuts[:-1], cuts[1:]):
             blocks.append((ptext[b][0][c0 * rec_bytes:c1 * rec_bytes], ptext[b][1][c0 * rec_bytes:c1 * rec_bytes]))
     n_blocks = len(blocks)

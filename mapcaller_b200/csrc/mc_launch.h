@@ -28,7 +28,7 @@ static void launch_rescue(const PipeArgs& a, int64_t n, mc_stream_t)
 }
 static void launch_locate(const PipeArgs& a, int64_t n, mc_stream_t) { if (n > 0) locate_body(0, 1, a); }
 static void launch_prep(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { for (int64_t r = first | 1; r < n; r += 2) prep_body(r, 0, 1, a); }
-static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { seed_body(0, 1, first, n, a); }
+static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t) { seed_body(0, 1, first, n, a, nullptr); }
 static void launch_piece(const PipeArgs& a, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump - a.ptask_begin; for (int64_t i = 0; i < n; i++) piece_body(i, 0, 1, a); }
 static void launch_chunkstat(const PipeArgs& a, int64_t n, mc_stream_t) { for (int64_t i = 0; i < n; i++) chunkstat_body(i, 0, 1, a); }
 static void launch_profpiece(const PipeArgs& a, const ProfArgs& q, int64_t, mc_stream_t) { const int64_t n = (int64_t)*a.ptask_bump; for (int64_t i = 0; i < n; i++) a.st->profile_atomics += profpiece_body(i, 0, 1, a, q); }
@@ -140,7 +140,10 @@ static void launch_prep(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t
 }
 // persistent lanes (seed_walk): a fixed grid of MINB resident blocks per SM
 template <int MINB> __global__ void __launch_bounds__(MC_BLOCK, MINB) mc_seed_kernel(const PipeArgs a, int64_t first, int64_t n)
-{ seed_body(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, first, n, a); }
+{
+	__shared__ uint64_t rows[MC_BLOCK * MC_SEED_ROW_WORDS];          // a row per lane for the read it is working on (mc_stages.h)
+	seed_body(blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, first, n, a, rows + threadIdx.x * MC_SEED_ROW_WORDS);
+}
 static void launch_seed(const PipeArgs& a, int64_t first, int64_t n, mc_stream_t s)
 {
 	if (n <= first) return;

@@ -121,11 +121,15 @@ MC_HD void prep_body(int64_t r, int lane, int nl, const PipeArgs& a)
 // read bases are fetched eight at a time through an aligned 64-bit window, and the following eight are requested as soon as
 // a window is entered: the search only moves forward, so the next window is there when the walk reaches it (waiting for a
 // read's own bases was 13 % of the stall samples of this kernel)
+// The window may lie in shared memory (seed_walk stages a read of up to MC_SEED_STAGE_BASES bases in its lane's row when it opens
+// it: the L2 round trip of every window refill was a quarter of the kernel's stall samples), hence plain loads, not __ldg.
 struct BaseWindow { const uint64_t* w; uint64_t cur, nxt; int have; int shift0; };
+#define MC_SEED_ROW_WORDS 23                                  /* 184 bytes per lane (an odd number of words: the lanes of a half-warp hit distinct banks), 46 KB per 256-thread block */
+#define MC_SEED_STAGE_BASES ((MC_SEED_ROW_WORDS - 2) * 8 - 7) /* the aligned words of the read plus the one the window prefetches */
 MC_HD void base_window_init(BaseWindow& bw, const uint8_t* s)
 {
 	bw.shift0 = (int)((uintptr_t)s & 7); bw.w = (const uint64_t*)(s - bw.shift0); bw.have = 0;
-	bw.cur = mc_ldg(bw.w); bw.nxt = mc_ldg(bw.w + 1);     // the read arena is padded: a window past the last read stays inside it
+	bw.cur = bw.w[0]; bw.nxt = bw.w[1];     // the read arena is padded: a window past the last read stays inside it
 }
 MC_HD uint8_t base_at(const uint8_t* s, int p, BaseWindow& bw)
 {
@@ -133,8 +137,8 @@ MC_HD uint8_t base_at(const uint8_t* s, int p, BaseWindow& bw)
 	const int word = q >> 3;
 	if (word != bw.have)
 	{
-		if (word == bw.have + 1) bw.cur = bw.nxt; else bw.cur = mc_ldg(bw.w + word);
-		bw.have = word; bw.nxt = mc_ldg(bw.w + word + 1);
+		if (word == bw.have + 1) bw.cur = bw.nxt; else bw.cur = bw.w[word];
+		bw.have = word; bw.nxt = bw.w[word + 1];
 	}
 	return (uint8_t)(bw.cur >> ((q & 7) << 3));
 }
@@ -225,7 +229,7 @@ template <> struct SeedOps<RcInterval32> {
 // the trip after it finished one.  A read that lies in a repeat family keeps stepping through the index for all of its bases
 // while a unique read is done after ~25 cheap trips; with one read per thread every warp would wait for its slowest read
 // (practically every warp of 32 holds one), with ~26 reads per lane the difference averages out.
-template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, int64_t first, int64_t n_end, const PipeArgs& a)
+template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, int64_t first, int64_t n_end, const PipeArgs& a, uint64_t* row)
 {
 	int64_t r = first + tid;
 	const uint8_t* s = nullptr; int rlen = 0, cap = 0, stop = 0; int64_t so = 0;
@@ -266,6 +270,14 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 			{
 				s = a.seq + a.roff[r]; rlen = (int)(a.roff[r + 1] - a.roff[r]);
 				so = a.seed_off[r]; cap = (int)(a.seed_off[r + 1] - so); stop = rlen - MC_MIN_SEED;
+				if (row && rlen <= MC_SEED_STAGE_BASES)
+				{
+					// the read into this lane's row of shared memory, as aligned 64-bit words (the row keeps the read's misalignment)
+					const int sh = (int)((uintptr_t)s & 7); const uint64_t* src = (const uint64_t*)(s - sh);
+					const int nw = ((sh + rlen + 7) >> 3) + 1;
+					for (int k = 0; k < nw; k++) row[k] = mc_ldg(src + k);
+					s = (const uint8_t*)row + sh;
+				}
 				base_window_init(bw, s);
 				ns = 0; pos = 0; p = 0; lower = 0; mode = 0;
 			}
@@ -358,9 +370,9 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 	if (nblk) mc_stat_add(&a.st->seed_blocks, (uint32_t)(nblk));
 	if (direct) { mc_stat_add(&a.st->seed_locate_blocks, nloc); mc_stat_add(&a.st->seed_sa_reads, nsa); }
 }
-MC_HD void seed_body(int64_t tid, int64_t nthreads, int64_t first, int64_t n_end, const PipeArgs& a)
+MC_HD void seed_body(int64_t tid, int64_t nthreads, int64_t first, int64_t n_end, const PipeArgs& a, uint64_t* row)
 {
-	if (a.ix.cbwt) seed_walk<RcInterval32>(tid, nthreads, first, n_end, a); else seed_walk<RcInterval>(tid, nthreads, first, n_end, a);
+	if (a.ix.cbwt) seed_walk<RcInterval32>(tid, nthreads, first, n_end, a, row); else seed_walk<RcInterval>(tid, nthreads, first, n_end, a, row);
 }
 
 // BWT_Search as an operator (reference src/bwt_search.cpp:121-164) for independent (codes, start) queries: the search loop of
