@@ -124,8 +124,7 @@ MC_HD void prep_body(int64_t r, int lane, int nl, const PipeArgs& a)
 // The window may lie in shared memory (seed_walk stages a read of up to MC_SEED_STAGE_BASES bases in its lane's row when it opens
 // it: the L2 round trip of every window refill was a quarter of the kernel's stall samples), hence plain loads, not __ldg.
 struct BaseWindow { const uint64_t* w; uint64_t cur, nxt; int have; int shift0; };
-#define MC_SEED_ROW_WORDS 23                                  /* 184 bytes per lane (an odd number of words: the lanes of a half-warp hit distinct banks), 46 KB per 256-thread block */
-#define MC_SEED_STAGE_BASES ((MC_SEED_ROW_WORDS - 2) * 8 - 7) /* the aligned words of the read plus the one the window prefetches */
+#define MC_SEED_ROW_WORDS 21                                  /* 168 bytes per lane (an odd number of words: the lanes of a half-warp hit distinct banks), 42 KB per 256-thread block: room for a 150-base read at any alignment its offset can have, plus the word the window prefetches */
 MC_HD void base_window_init(BaseWindow& bw, const uint8_t* s)
 {
 	bw.shift0 = (int)((uintptr_t)s & 7); bw.w = (const uint64_t*)(s - bw.shift0); bw.have = 0;
@@ -270,13 +269,15 @@ template <class Interval> MC_HD void seed_walk(int64_t tid, int64_t nthreads, in
 			{
 				s = a.seq + a.roff[r]; rlen = (int)(a.roff[r + 1] - a.roff[r]);
 				so = a.seed_off[r]; cap = (int)(a.seed_off[r + 1] - so); stop = rlen - MC_MIN_SEED;
-				if (row && rlen <= MC_SEED_STAGE_BASES)
 				{
 					// the read into this lane's row of shared memory, as aligned 64-bit words (the row keeps the read's misalignment)
 					const int sh = (int)((uintptr_t)s & 7); const uint64_t* src = (const uint64_t*)(s - sh);
 					const int nw = ((sh + rlen + 7) >> 3) + 1;
-					for (int k = 0; k < nw; k++) row[k] = mc_ldg(src + k);
-					s = (const uint8_t*)row + sh;
+					if (row && nw <= MC_SEED_ROW_WORDS)
+					{
+						for (int k = 0; k < nw; k++) row[k] = mc_ldg(src + k);
+						s = (const uint8_t*)row + sh;
+					}
 				}
 				base_window_init(bw, s);
 				ns = 0; pos = 0; p = 0; lower = 0; mode = 0;
