@@ -164,24 +164,40 @@ def recorded_traffic(genome_len: int):
 
 
 def bind_to_gpu_numa(device: int):
-    """Pin this process (threads and first-touch host memory) to the NUMA node of its GPU, when the box exposes it."""
+    """Pin this process (threads and the first-touch / page-locked host memory it allocates afterwards) to the CPUs next to its
+    GPU: the NUMA node sysfs names for the GPU's PCI device, else the CPU set NVML reports as ideal for it.  Without this,
+    eight ranks' FASTQ buffers land on whatever socket their process started on and half the GPUs pull their input across
+    the inter-socket link.  Returns a description for the JSON line (None when the box exposes nothing)."""
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(device)
+    except Exception:
+        return None
+    try:
         bus = pynvml.nvmlDeviceGetPciInfo(h).busId
         bus = bus.decode() if isinstance(bus, bytes) else bus
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]).read())
-        if node < 0:
-            return None
-        cpus = []
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus += list(range(int(a), int(b or a) + 1))
-        os.sched_setaffinity(0, cpus)
-        return node
+        if node >= 0:
+            cpus = []
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus += list(range(int(a), int(b or a) + 1))
+            os.sched_setaffinity(0, cpus)
+            return node
     except Exception:
-        return None
+        pass
+    try:
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed and len(allowed) < n_cpu:
+            os.sched_setaffinity(0, allowed)
+            return "nvml cpu set %d-%d (%d cpus)" % (allowed[0], allowed[-1], len(allowed))
+    except Exception:
+        pass
+    return None
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -311,6 +311,16 @@ int mc_ingest_prefetch(mc_ctx *ctx, const mc_fastq_in *in, int32_t slot);
  * codes: concatenated 0..4 codes, off[n+1]; start[n].  out_len/out_freq[n]; out_loc[n*MC_MAX_OCC]. */
 int mc_bwt_search_batch(mc_ctx *ctx, int64_t n, const uint8_t *codes, const int64_t *off, const int32_t *start,
                         int32_t *out_len, int32_t *out_freq, uint64_t *out_loc);
+/* ProduceReadAlignment in its setting (reference src/structure.h:242, src/ReadAlignment.cpp:306-430): SimplePairClustering ->
+ * RemoveRedundantAlnCan -> ProduceReadAlignment for n independent reads, the single-end branch of ReadMapping()
+ * (src/ReadMapping.cpp:575-585).  `out` as mc_map_batch with want_alignments (candidates, fragment lists, alignment strings,
+ * scores, AlnSummary); the context's totals, avgDist, chunk grid and profile are untouched.  Mates are not reversed. */
+int mc_read_alignment_batch(mc_ctx *ctx, const mc_batch_in *in, mc_batch_out *out);
+/* AlignmentRescue in its setting (reference src/structure.h:245, src/AlignmentRescue.cpp:28-111): the pairs of the batch through
+ * seeding, clustering, pairing / masking, AlignmentRescue(EstiDistance, read1, read2) and ProduceReadAlignment with
+ * EstiDistance = (int)(avg_dist * 1.5) for every pair (src/ReadMapping.cpp:462): no avgDist feedback between chunks, the
+ * context's sequential state is untouched, so a pair's records depend on the pair and avg_dist alone. */
+int mc_rescue_batch(mc_ctx *ctx, const mc_batch_in *in, uint32_t avg_dist, mc_batch_out *out);
 /* IdentifySimplePairs + SimplePairClustering (reference src/ReadMapping.cpp:125-226) for n independent reads, taken as they
  * are (no mate reversal): per read its simple pairs sorted by (PosDiff, rPos) - the sentinel left out - and its candidate
  * clusters as [pair_begin, pair_end) slices of that list (for a tandem-repeat cluster: the best equal-PosDiff run).

@@ -156,6 +156,8 @@ def lib():
         L.mc_sam_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
         L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
         L.mc_profile_reduce_scatter.argtypes = [C.c_void_p]
+        L.mc_read_alignment_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mc_rescue_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.mc_profile_owned.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.mc_comm_unique_id.argtypes = [C.c_void_p]
         L.mc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
@@ -293,6 +295,20 @@ class Context:
         out = BatchOut()
         _check(lib().mc_map_batch(self._h, C.byref(b), C.byref(out)), "mc_map_batch")
         return self._wrap(out, copy)
+
+    def read_alignment_batch(self, seq: np.ndarray, off: np.ndarray):
+        """mc_read_alignment_batch: SimplePairClustering .. ProduceReadAlignment for independent reads (the context's state is untouched)."""
+        b, keep = self._batch(seq, off)
+        out = BatchOut()
+        _check(lib().mc_read_alignment_batch(self._h, C.byref(b), C.byref(out)), "mc_read_alignment_batch")
+        return self._wrap(out, True)
+
+    def rescue_batch(self, seq: np.ndarray, off: np.ndarray, avg_dist: int):
+        """mc_rescue_batch: the pairs of the batch with EstiDistance = (int)(avg_dist * 1.5) for every pair, no feedback."""
+        b, keep = self._batch(seq, off)
+        out = BatchOut()
+        _check(lib().mc_rescue_batch(self._h, C.byref(b), C.c_uint32(int(avg_dist)), C.byref(out)), "mc_rescue_batch")
+        return self._wrap(out, True)
 
     def stage_batch(self, seq: np.ndarray, off: np.ndarray, slot: int = 0):
         b, keep = self._batch(seq, off)

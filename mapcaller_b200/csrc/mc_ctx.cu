@@ -211,6 +211,7 @@ struct mc_ctx {
 	// sequential state
 	mc_totals tot;
 	bool discord_init = false; int64_t discord_gpos = 0, discord_dist = 0;
+	bool freeze_avg_dist = false;  // operator entry mc_rescue_batch: every chunk sees the avgDist the caller gave, nothing feeds back
 	bool library_closed = false;   // a batch that was not a whole number of 200-read chunks has been mapped: only the last batch of a library may be
 	std::vector<mc_site_rec> inv_sites, tnl_sites;
 	// finalize products
@@ -796,7 +797,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		// avgDist stays at its initial value until more than 1000 pairs have been seen (src/ReadMapping.cpp:539) and then
 		// jumps: while warming up only the chunks that can still use the initial value are speculated on - plus a few hundred
 		// more, whose sums (nearly independent of the value) let the walk predict where the trajectory settles
-		if (paired && c->tot.total_paired <= 1000)
+		if (paired && c->tot.total_paired <= 1000 && !c->freeze_avg_dist)
 			for (int64_t k = (1000 - c->tot.total_paired) / (MC_CHUNK_READS / 2) + 2 + 256; k < NG; k++) active[k] = 0;
 		Bumps hb; memset(&hb, 0, sizeof(hb)); hb.pair = (mc_u64)n_locs;
 		bad |= dev_push(c, db, &hb, sizeof(hb), s) || dev_zero(c->d_pair_flag.p, (n_pairs + 1) * 4, s);
@@ -866,7 +867,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 						est[j] = (int32_t)(pred.avg_dist * 1.5); active[j] = 1; computed[j] = 0;
 						if (!ever[j]) continue;
 						pred.total_paired += hc[j].paired; pred.total_distance += hc[j].dist_sum;
-						if (paired && pred.total_paired > 1000) pred.avg_dist = (uint32_t)(int)(1. * pred.total_distance / pred.total_paired + .5);
+						if (paired && pred.total_paired > 1000 && !c->freeze_avg_dist) pred.avg_dist = (uint32_t)(int)(1. * pred.total_distance / pred.total_paired + .5);
 					}
 					break;
 				}
@@ -874,7 +875,7 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 				c->chunks_final[k] = ck;
 				run.total_reads += ck.n_reads; run.total_mapped += ck.mapped; run.total_paired += ck.paired;
 				run.total_distance += ck.dist_sum; run.read_length_sum += ck.len_sum;
-				if (paired && run.total_paired > 1000) run.avg_dist = (uint32_t)(int)(1. * run.total_distance / run.total_paired + .5);
+				if (paired && run.total_paired > 1000 && !c->freeze_avg_dist) run.avg_dist = (uint32_t)(int)(1. * run.total_distance / run.total_paired + .5);
 				first_open++;
 			}
 		}
@@ -1153,6 +1154,46 @@ int mc_map_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
 	int rc = stage_reads(c, in, c->cur, pieces > 1 ? c->cstream : c->stream, pieces);
 	if (rc) return rc;
 	return run_batch(c, c->cur, out, true);
+}
+
+// ---- operator-level entries for the steps that only show up inside a mapped batch otherwise ------------------------------------
+// Both run the pipeline of mc_map_batch on the caller's reads with the context's sequential state (totals, avgDist, SV-site
+// bookkeeping, chunk grid, profile) set aside and put back afterwards: what comes out depends on the reads alone.
+struct SavedState {
+	mc_params prm; mc_totals tot; bool closed, discord_init; int64_t dg, dd; std::vector<mc_site_rec> inv, tnl;
+	explicit SavedState(mc_ctx* c) : prm(c->prm), tot(c->tot), closed(c->library_closed), discord_init(c->discord_init), dg(c->discord_gpos), dd(c->discord_dist), inv(c->inv_sites), tnl(c->tnl_sites) {}
+	void restore(mc_ctx* c) { c->prm = prm; c->tot = tot; c->library_closed = closed; c->discord_init = discord_init; c->discord_gpos = dg; c->discord_dist = dd; c->inv_sites = inv; c->tnl_sites = tnl; c->freeze_avg_dist = false; }
+};
+
+// SimplePairClustering -> RemoveRedundantAlnCan -> ProduceReadAlignment for n independent reads, i.e. the single-end branch of
+// ReadMapping() (reference src/ReadMapping.cpp:575-585; ProduceReadAlignment src/ReadAlignment.cpp:306-430): candidates with their
+// fragment lists, alignment strings and scores, AlnSummary per read.  Works on a paired context as well (mates are NOT reversed).
+int mc_read_alignment_batch(mc_ctx* c, const mc_batch_in* in, mc_batch_out* out)
+{
+	if (!c || !in || !out) { mc_set_error("mc_read_alignment_batch: null argument"); return MC_ERR_ARG; }
+	SavedState keep(c);
+	c->prm.paired = 0; c->prm.update_profile = 0; c->prm.want_alignments = 1; c->prm.reserved[2] = 1; c->library_closed = false;
+	memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = 1000;
+	const int rc = mc_map_batch(c, in, out);
+	keep.restore(c);
+	return rc;
+}
+
+// AlignmentRescue in its setting (reference src/AlignmentRescue.cpp:28-111, called from src/ReadMapping.cpp:466): every pair of the
+// batch goes through IdentifySimplePairs, SimplePairClustering, the pairing / masking of ReadMapping(), AlignmentRescue(EstiDistance,
+// read1, read2) and ProduceReadAlignment with EstiDistance = (int)(avg_dist * 1.5) for ALL pairs (src/ReadMapping.cpp:462) - no
+// feedback from one 200-read chunk to the next, so a pair's records depend on the pair and on avg_dist alone.  Rescued candidates
+// are the ones whose paired_idx points at a partner the FM-index seeds alone did not produce.
+int mc_rescue_batch(mc_ctx* c, const mc_batch_in* in, uint32_t avg_dist, mc_batch_out* out)
+{
+	if (!c || !in || !out) { mc_set_error("mc_rescue_batch: null argument"); return MC_ERR_ARG; }
+	if (!c->prm.paired) { mc_set_error("mc_rescue_batch: the context was created for single-end reads"); return MC_ERR_ARG; }
+	SavedState keep(c);
+	c->prm.update_profile = 0; c->prm.want_alignments = 1; c->prm.reserved[2] = 1; c->library_closed = false;
+	memset(&c->tot, 0, sizeof(c->tot)); c->tot.avg_dist = avg_dist; c->freeze_avg_dist = true;
+	const int rc = mc_map_batch(c, in, out);
+	keep.restore(c);
+	return rc;
 }
 
 int mc_stage_batch_async(mc_ctx* c, const mc_batch_in* in, int32_t slot)

@@ -210,6 +210,9 @@ void mcref_reset_state()
 	avgDist = 1000; avgReadLength = 0; g_discord_init = false;
 }
 
+// operator-level tests (AlignmentRescue with a given EstiDistance): the value the next chunk computes EstiDistance from
+void mcref_set_avg_dist(uint32_t v) { avgDist = v; }
+
 // Processes `n_reads` reads (mates adjacent when paired) in chunks of ReadChunkSize exactly as one
 // reference thread would (src/ReadMapping.cpp:432-624), mutating the reference's global state.
 // seq: concatenated ASCII reads, off[n_reads+1].  Returns a malloc'd blob: for every read the record

@@ -154,6 +154,11 @@ def map_reads(seq: np.ndarray, off: np.ndarray, paired: bool, update_profile: bo
     return parse_reads(blob, len(off) - 1, paired)
 
 
+def set_avg_dist(v: int) -> None:
+    """The value the next chunk derives its EstiDistance from (operator-level test of AlignmentRescue)."""
+    lib().mcref_set_avg_dist(C.c_uint32(int(v)))
+
+
 def counters():
     a = (C.c_int64 * 8)()
     lib().mcref_counters(a)
