@@ -321,6 +321,13 @@ int mc_read_alignment_batch(mc_ctx *ctx, const mc_batch_in *in, mc_batch_out *ou
  * EstiDistance = (int)(avg_dist * 1.5) for every pair (src/ReadMapping.cpp:462): no avgDist feedback between chunks, the
  * context's sequential state is untouched, so a pair's records depend on the pair and avg_dist alone. */
 int mc_rescue_batch(mc_ctx *ctx, const mc_batch_in *in, uint32_t avg_dist, mc_batch_out *out);
+/* UpdateProfile / UpdateMultiHitCount as a step of its own (reference src/structure.h:248-249, src/AlignmentProfile.cpp:41-271,
+ * call site src/ReadMapping.cpp:559-568).  After mc_defer_profile(ctx, 1) a mapped batch leaves the profile untouched and its
+ * candidates, fragment lists and alignment strings in the device arenas; mc_update_profile_last(ctx) applies the update to
+ * exactly those reads (dedup gate, strand / base / multi-hit counters, indel and break-point records), once, before the
+ * next batch is mapped.  Not with the ordered multi-GPU exchange. */
+int mc_defer_profile(mc_ctx *ctx, int32_t on);
+int mc_update_profile_last(mc_ctx *ctx);
 /* IdentifySimplePairs + SimplePairClustering (reference src/ReadMapping.cpp:125-226) for n independent reads, taken as they
  * are (no mate reversal): per read its simple pairs sorted by (PosDiff, rPos) - the sentinel left out - and its candidate
  * clusters as [pair_begin, pair_end) slices of that list (for a tandem-repeat cluster: the best equal-PosDiff run).

@@ -157,6 +157,8 @@ def lib():
         L.mc_profile_allreduce.argtypes = [C.c_void_p, C.c_void_p]
         L.mc_profile_reduce_scatter.argtypes = [C.c_void_p]
         L.mc_read_alignment_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mc_defer_profile.argtypes = [C.c_void_p, C.c_int32]
+        L.mc_update_profile_last.argtypes = [C.c_void_p]
         L.mc_rescue_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.mc_profile_owned.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.mc_comm_unique_id.argtypes = [C.c_void_p]
@@ -309,6 +311,13 @@ class Context:
         out = BatchOut()
         _check(lib().mc_rescue_batch(self._h, C.byref(b), C.c_uint32(int(avg_dist)), C.byref(out)), "mc_rescue_batch")
         return self._wrap(out, True)
+
+    def defer_profile(self, on: bool = True):
+        _check(lib().mc_defer_profile(self._h, int(on)), "mc_defer_profile")
+
+    def update_profile_last(self):
+        """UpdateProfile / UpdateMultiHitCount for the reads of the batch just mapped (after defer_profile())."""
+        _check(lib().mc_update_profile_last(self._h), "mc_update_profile_last")
 
     def stage_batch(self, seq: np.ndarray, off: np.ndarray, slot: int = 0):
         b, keep = self._batch(seq, off)

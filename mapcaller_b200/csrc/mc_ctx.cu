@@ -211,6 +211,7 @@ struct mc_ctx {
 	// sequential state
 	mc_totals tot;
 	bool discord_init = false; int64_t discord_gpos = 0, discord_dist = 0;
+	PipeArgs last_a; int64_t last_frag_cap = 0; Bumps last_hb; bool last_profiled = true, defer_profile = false;   // the batch whose arenas are still on the device
 	bool freeze_avg_dist = false;  // operator entry mc_rescue_batch: every chunk sees the avgDist the caller gave, nothing feeds back
 	bool library_closed = false;   // a batch that was not a whole number of 200-read chunks has been mapped: only the last batch of a library may be
 	std::vector<mc_site_rec> inv_sites, tnl_sites;
@@ -678,6 +679,92 @@ static int gather_words(mc_ctx* c, const mc_u64* mine, int n, std::vector<mc_u64
 static bool ordered_mode(const mc_ctx*) { return false; }
 #endif
 
+// ---- the profile stage of a batch: UpdateProfile / UpdateMultiHitCount (reference src/AlignmentProfile.cpp:41-271) for the reads
+// whose candidates, fragments and alignment strings lie in the batch's device arenas (`a`).  Runs at the end of run_batch, or
+// later through mc_update_profile_last when the context defers it (mc_defer_profile).
+static int profile_stage(mc_ctx* c, PipeArgs& a, int64_t n, const Ordered& od, int64_t frag_cap, const Bumps& hb)
+{
+	const mc_stream_t s = c->stream;
+	Bumps* db = c->d_bumps.as<Bumps>();
+	int64_t* h_small = c->h_small.as<int64_t>();
+	int bad = dev_zero(&db->key, 8, s);      // the gate-key cursor (a deferred call finds the discordant-pair list's count in it)
+	{
+		PersistBumps pb;
+		bad |= dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s);
+		const int64_t need_bp = (int64_t)pb.bp + 2 * n, need_ind = (int64_t)pb.ind + (int64_t)hb.frag + 16, need_seq = (int64_t)pb.ind_seq + (int64_t)hb.aln + 16;
+		bad |= c->d_bp.grow_keep(need_bp * 8, pb.bp * 8, s) || c->d_ind.grow_keep(need_ind * sizeof(mc_indel_rec), pb.ind * sizeof(mc_indel_rec), s);
+		bad |= c->d_ind_seq.grow_keep(need_seq, pb.ind_seq, s);
+		bad |= c->d_keys.reserve((n + 1) * 8) || c->d_keys_tmp.reserve((n + 1) * 8) || c->d_sort.reserve(device_sort_scratch_bytes(n));
+		if (bad) return MC_ERR_CUDA;
+		c->bp_cap = c->d_bp.cap / 8; c->ind_cap = c->d_ind.cap / sizeof(mc_indel_rec); c->ind_seq_cap = c->d_ind_seq.cap;
+		if (c->ind_seq_cap >= 0x7fffffffll) { mc_set_error("indel sequence arena exceeds 2 GiB; call mc_profile_indels() earlier"); return MC_ERR_OVERFLOW; }
+		PersistBumps* dpb = c->d_pbump.as<PersistBumps>();
+		ProfArgs q; memset(&q, 0, sizeof(q));
+		q.keys = c->d_keys.as<uint64_t>(); q.key_bump = &db->key; q.accept = c->d_accept.as<uint8_t>(); q.rnp = c->d_rnp.as<int32_t>();
+		q.bp_pos = c->d_bp.as<int64_t>(); q.bp_bump = &dpb->bp; q.bp_cap = c->bp_cap;
+		q.ind = c->d_ind.as<mc_indel_rec>(); q.ind_bump = &dpb->ind; q.ind_cap = c->ind_cap;
+		q.ind_seq = c->d_ind_seq.as<uint8_t>(); q.ind_seq_bump = &dpb->ind_seq; q.ind_seq_cap = c->ind_seq_cap;
+		launch_profkey(a, q, n, s);
+		bad |= dev_d2h(h_small, &db->key, 8, s) || dev_sync(s);
+		if (bad) return MC_ERR_CUDA;
+		q.n_keys = h_small[0];
+		device_sort_u64(q.keys, c->d_keys_tmp.as<uint64_t>(), q.n_keys, c->d_sort.p, c->d_sort.cap, s);
+#ifndef MC_HOSTEMU
+		std::vector<long long> gl_n; long long gl_mx = 0; const uint64_t* gl_all = nullptr;
+		const uint8_t* gd_all = nullptr; size_t gd_pitch = 0;
+		if (od.on)
+		{
+			// per-start candidate counts of every rank (heads of the sorted key runs, capped at 15).  Small genomes: one byte
+			// per column, all-gathered and applied by streaming kernels; large ones: (start, count) lists, all-gathered and
+			// applied list by list.  The choice depends only on sizes every rank knows (G and the key counts).
+			long long* d_sz = c->d_comm_small.as<long long>();
+			long long my_keys = q.n_keys;
+			if (dev_h2d(d_sz + od.n, &my_keys, 8, s)) return MC_ERR_CUDA;
+			if (nccl_fail(ncclAllGather(d_sz + od.n, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(key counts)")) return MC_ERR_NCCL;
+			gl_n.resize(od.n);
+			if (dev_d2h(gl_n.data(), d_sz, 8 * od.n, s) || dev_sync(s)) return MC_ERR_CUDA;
+			long long keys_mx = 0; for (int r = 0; r < od.n; r++) keys_mx = std::max(keys_mx, gl_n[r]);
+			if (keys_mx == 0) {}
+			else if ((long long)c->G <= 8 * keys_mx)
+			{
+				gd_pitch = ((size_t)c->G + 255) & ~(size_t)255;
+				if (c->d_glist.reserve(gd_pitch) || c->d_glist_all.reserve(gd_pitch * od.n) || dev_zero(c->d_glist.p, gd_pitch, s)) return MC_ERR_CUDA;
+				launch_gatedense_fill(a, q, q.n_keys, c->d_glist.as<uint8_t>(), s);
+				if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, gd_pitch, ncclUint8, c->comm, s), "ncclAllGather(gate counts)")) return MC_ERR_NCCL;
+				gd_all = c->d_glist_all.as<uint8_t>();
+				launch_gatedense_apply(a, c->G, gd_all, gd_pitch, 0, od.me, s);
+			}
+			else
+			{
+				if (c->d_glist.reserve((size_t)(q.n_keys + 2) * 8) || dev_zero(&db->rwin, 8, s)) return MC_ERR_CUDA;   // the window cursor is free: reuse it
+				launch_gatecnt(a, q, q.n_keys, c->d_glist.as<uint64_t>(), &db->rwin, s);
+				if (nccl_fail(ncclAllGather(&db->rwin, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(gate list sizes)")) return MC_ERR_NCCL;
+				if (dev_d2h(gl_n.data(), d_sz, 8 * od.n, s) || dev_sync(s)) return MC_ERR_CUDA;
+				for (int r = 0; r < od.n; r++) gl_mx = std::max(gl_mx, gl_n[r]);
+				gl_mx = (gl_mx + 1) & ~1ll;
+				if (gl_mx)
+				{
+					if (c->d_glist.grow_keep((size_t)gl_mx * 8, (size_t)gl_n[od.me] * 8, s) || c->d_glist_all.reserve((size_t)gl_mx * 8 * od.n)) return MC_ERR_CUDA;
+					if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, (size_t)gl_mx * 8, ncclUint8, c->comm, s), "ncclAllGather(gate lists)")) return MC_ERR_NCCL;
+					gl_all = c->d_glist_all.as<uint64_t>();
+					for (int r = 0; r < od.me; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
+				}
+			}
+		}
+#endif
+		launch_gate(a, q, q.n_keys, s);
+		launch_gateupd(a, q, q.n_keys, s);
+#ifndef MC_HOSTEMU
+		if (od.on && gl_all) for (int r = od.me + 1; r < od.n; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
+		if (od.on && gd_all) launch_gatedense_apply(a, c->G, gd_all, gd_pitch, od.me + 1, od.n, s);
+#endif
+		bad |= dev_zero(&db->ptask, 8, s);            // the piece list of the alignment stage is free again: reuse it
+		launch_scatter(a, q, n, s);
+		launch_profpiece(a, q, frag_cap, s);
+		}
+	return bad ? MC_ERR_CUDA : MC_OK;
+}
+
 // ---- the batch controller -----------------------------------------------------------------------------
 static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 {
@@ -902,80 +989,11 @@ static int run_batch(mc_ctx* c, Staged& st, mc_batch_out* out, bool prep_needed)
 		bad |= dev_d2h(&hb, db, sizeof(hb), s) || dev_sync(s);
 		if (bad) return MC_ERR_CUDA;
 		ev_record(&c->ev[EV_PROF0], s);
-		if (c->prm.update_profile)
+		c->last_a = a; c->last_frag_cap = frag_cap; c->last_hb = hb; c->last_profiled = false;
+		if (c->prm.update_profile && !c->defer_profile)
 		{
-			PersistBumps pb;
-			bad |= dev_d2h(&pb, c->d_pbump.p, sizeof(pb), s) || dev_sync(s);
-			const int64_t need_bp = (int64_t)pb.bp + 2 * n, need_ind = (int64_t)pb.ind + (int64_t)hb.frag + 16, need_seq = (int64_t)pb.ind_seq + (int64_t)hb.aln + 16;
-			bad |= c->d_bp.grow_keep(need_bp * 8, pb.bp * 8, s) || c->d_ind.grow_keep(need_ind * sizeof(mc_indel_rec), pb.ind * sizeof(mc_indel_rec), s);
-			bad |= c->d_ind_seq.grow_keep(need_seq, pb.ind_seq, s);
-			bad |= c->d_keys.reserve((n + 1) * 8) || c->d_keys_tmp.reserve((n + 1) * 8) || c->d_sort.reserve(device_sort_scratch_bytes(n));
-			if (bad) return MC_ERR_CUDA;
-			c->bp_cap = c->d_bp.cap / 8; c->ind_cap = c->d_ind.cap / sizeof(mc_indel_rec); c->ind_seq_cap = c->d_ind_seq.cap;
-			if (c->ind_seq_cap >= 0x7fffffffll) { mc_set_error("indel sequence arena exceeds 2 GiB; call mc_profile_indels() earlier"); return MC_ERR_OVERFLOW; }
-			PersistBumps* dpb = c->d_pbump.as<PersistBumps>();
-			ProfArgs q; memset(&q, 0, sizeof(q));
-			q.keys = c->d_keys.as<uint64_t>(); q.key_bump = &db->key; q.accept = c->d_accept.as<uint8_t>(); q.rnp = c->d_rnp.as<int32_t>();
-			q.bp_pos = c->d_bp.as<int64_t>(); q.bp_bump = &dpb->bp; q.bp_cap = c->bp_cap;
-			q.ind = c->d_ind.as<mc_indel_rec>(); q.ind_bump = &dpb->ind; q.ind_cap = c->ind_cap;
-			q.ind_seq = c->d_ind_seq.as<uint8_t>(); q.ind_seq_bump = &dpb->ind_seq; q.ind_seq_cap = c->ind_seq_cap;
-			launch_profkey(a, q, n, s);
-			bad |= dev_d2h(h_small, &db->key, 8, s) || dev_sync(s);
-			if (bad) return MC_ERR_CUDA;
-			q.n_keys = h_small[0];
-			device_sort_u64(q.keys, c->d_keys_tmp.as<uint64_t>(), q.n_keys, c->d_sort.p, c->d_sort.cap, s);
-#ifndef MC_HOSTEMU
-			std::vector<long long> gl_n; long long gl_mx = 0; const uint64_t* gl_all = nullptr;
-			const uint8_t* gd_all = nullptr; size_t gd_pitch = 0;
-			if (od.on)
-			{
-				// per-start candidate counts of every rank (heads of the sorted key runs, capped at 15).  Small genomes: one byte
-				// per column, all-gathered and applied by streaming kernels; large ones: (start, count) lists, all-gathered and
-				// applied list by list.  The choice depends only on sizes every rank knows (G and the key counts).
-				long long* d_sz = c->d_comm_small.as<long long>();
-				long long my_keys = q.n_keys;
-				if (dev_h2d(d_sz + od.n, &my_keys, 8, s)) return MC_ERR_CUDA;
-				if (nccl_fail(ncclAllGather(d_sz + od.n, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(key counts)")) return MC_ERR_NCCL;
-				gl_n.resize(od.n);
-				if (dev_d2h(gl_n.data(), d_sz, 8 * od.n, s) || dev_sync(s)) return MC_ERR_CUDA;
-				long long keys_mx = 0; for (int r = 0; r < od.n; r++) keys_mx = std::max(keys_mx, gl_n[r]);
-				if (keys_mx == 0) {}
-				else if ((long long)c->G <= 8 * keys_mx)
-				{
-					gd_pitch = ((size_t)c->G + 255) & ~(size_t)255;
-					if (c->d_glist.reserve(gd_pitch) || c->d_glist_all.reserve(gd_pitch * od.n) || dev_zero(c->d_glist.p, gd_pitch, s)) return MC_ERR_CUDA;
-					launch_gatedense_fill(a, q, q.n_keys, c->d_glist.as<uint8_t>(), s);
-					if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, gd_pitch, ncclUint8, c->comm, s), "ncclAllGather(gate counts)")) return MC_ERR_NCCL;
-					gd_all = c->d_glist_all.as<uint8_t>();
-					launch_gatedense_apply(a, c->G, gd_all, gd_pitch, 0, od.me, s);
-				}
-				else
-				{
-					if (c->d_glist.reserve((size_t)(q.n_keys + 2) * 8) || dev_zero(&db->rwin, 8, s)) return MC_ERR_CUDA;   // the window cursor is free: reuse it
-					launch_gatecnt(a, q, q.n_keys, c->d_glist.as<uint64_t>(), &db->rwin, s);
-					if (nccl_fail(ncclAllGather(&db->rwin, d_sz, 1, ncclInt64, c->comm, s), "ncclAllGather(gate list sizes)")) return MC_ERR_NCCL;
-					if (dev_d2h(gl_n.data(), d_sz, 8 * od.n, s) || dev_sync(s)) return MC_ERR_CUDA;
-					for (int r = 0; r < od.n; r++) gl_mx = std::max(gl_mx, gl_n[r]);
-					gl_mx = (gl_mx + 1) & ~1ll;
-					if (gl_mx)
-					{
-						if (c->d_glist.grow_keep((size_t)gl_mx * 8, (size_t)gl_n[od.me] * 8, s) || c->d_glist_all.reserve((size_t)gl_mx * 8 * od.n)) return MC_ERR_CUDA;
-						if (nccl_fail(ncclAllGather(c->d_glist.p, c->d_glist_all.p, (size_t)gl_mx * 8, ncclUint8, c->comm, s), "ncclAllGather(gate lists)")) return MC_ERR_NCCL;
-						gl_all = c->d_glist_all.as<uint64_t>();
-						for (int r = 0; r < od.me; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
-					}
-				}
-			}
-#endif
-			launch_gate(a, q, q.n_keys, s);
-			launch_gateupd(a, q, q.n_keys, s);
-#ifndef MC_HOSTEMU
-			if (od.on && gl_all) for (int r = od.me + 1; r < od.n; r++) launch_gateadd(a, gl_n[r], gl_all + (size_t)gl_mx * r, s);
-			if (od.on && gd_all) launch_gatedense_apply(a, c->G, gd_all, gd_pitch, od.me + 1, od.n, s);
-#endif
-			bad |= dev_zero(&db->ptask, 8, s);            // the piece list of the alignment stage is free again: reuse it
-			launch_scatter(a, q, n, s);
-			launch_profpiece(a, q, frag_cap, s);
+			if (int prc = profile_stage(c, a, n, od, frag_cap, hb)) return prc;
+			c->last_profiled = true;
 		}
 		ev_record(&c->ev[EV_PROF1], s);
 
@@ -1194,6 +1212,36 @@ int mc_rescue_batch(mc_ctx* c, const mc_batch_in* in, uint32_t avg_dist, mc_batc
 	const int rc = mc_map_batch(c, in, out);
 	keep.restore(c);
 	return rc;
+}
+
+// UpdateProfile / UpdateMultiHitCount as a step of its own (reference src/structure.h:248-249, src/AlignmentProfile.cpp:41-271;
+// call site src/ReadMapping.cpp:559-568): with mc_defer_profile(ctx, 1) a mapped batch leaves its candidates, fragment lists and
+// alignment strings in the device arenas and the profile untouched; mc_update_profile_last applies the reference's update to
+// exactly those reads - dedup gate, strand / base / multi-hit counters, indel and break-point records - once.
+int mc_defer_profile(mc_ctx* c, int32_t on)
+{
+	if (!c) { mc_set_error("mc_defer_profile: null context"); return MC_ERR_ARG; }
+	c->defer_profile = on != 0;
+	return MC_OK;
+}
+int mc_update_profile_last(mc_ctx* c)
+{
+	if (!c) { mc_set_error("mc_update_profile_last: null context"); return MC_ERR_ARG; }
+	if (!c->prm.update_profile) { mc_set_error("mc_update_profile_last: context was created without update_profile"); return MC_ERR_ARG; }
+	if (c->last_n <= 0 || c->last_profiled) { mc_set_error("mc_update_profile_last: no mapped batch on the device whose profile update is still due (mc_defer_profile, then mc_map_batch / mc_map_staged)"); return MC_ERR_ARG; }
+	if (ordered_mode(c)) { mc_set_error("mc_update_profile_last: not with the ordered multi-GPU exchange (the dedup gate is exchanged inside mc_map_batch)"); return MC_ERR_ARG; }
+#ifndef MC_HOSTEMU
+	cudaSetDevice(c->prm.device);
+#endif
+	Ordered od;
+	ev_record(&c->ev[EV_PROF0], c->stream);
+	const int rc = profile_stage(c, c->last_a, c->last_n, od, c->last_frag_cap, c->last_hb);
+	ev_record(&c->ev[EV_PROF1], c->stream);
+	if (rc != MC_OK) return rc;
+	if (dev_sync(c->stream)) return MC_ERR_CUDA;
+	{ const double ms = ev_ms(&c->ev[EV_PROF0], &c->ev[EV_PROF1]); c->stats.ms_profile += ms; c->stats.ms_total += ms; }
+	c->last_profiled = true;
+	return MC_OK;
 }
 
 int mc_stage_batch_async(mc_ctx* c, const mc_batch_in* in, int32_t slot)

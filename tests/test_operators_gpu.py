@@ -83,3 +83,34 @@ def test_rescue_operator_matches_the_reference(built, tmp_path, avg_dist):
     assert d is None, "read %d differs:\n mine %r\n ref  %r" % d
     assert (ctx.totals(), ctx.profile_checksum(), sorted(ctx.sites(0)), sorted(ctx.sites(1))) == before
     ctx.close()
+
+
+@pytest.mark.parametrize("paired", [1, 0])
+def test_deferred_profile_update_equals_the_inline_one_and_the_reference(built, paired):
+    """mc_defer_profile + mc_update_profile_last: UpdateProfile / UpdateMultiHitCount applied as a step of its own to the reads of the
+    batch just mapped - batch after batch the same profile, indel maps and break points as the inline update, which the
+    reference's own UpdateProfile leaves behind (pu.ref_results)."""
+    case = pu.make_case(seed=73, n_pairs=4000, genome_len=90000, contigs=2, sv=3.0, n_dup=15, tandem=6, indel_rate=0.003, lower_rate=0.05, paired=paired, max_dup=3)
+    ix = pu.build_index(case)
+    seq, off = case["seq"], case["off"]
+    n = len(off) - 1
+    cut = (n // 600) * 200
+    inline, later = api.Context(ix, update_profile=1, **case["params"]), api.Context(ix, update_profile=1, **case["params"])
+    later.defer_profile(True)
+    empty = later.profile_checksum()
+    for b, e in ((0, cut), (cut, n)):
+        inline.map_batch(seq[off[b]:off[e]], off[b:e + 1] - off[b])
+        before = later.profile_checksum()
+        later.map_batch(seq[off[b]:off[e]], off[b:e + 1] - off[b])
+        assert later.profile_checksum() == before                    # mapping alone leaves the profile alone
+        later.update_profile_last()
+        assert later.profile_checksum() == inline.profile_checksum()
+        with pytest.raises(api.McError):
+            later.update_profile_last()                              # once per batch
+    assert empty != inline.profile_checksum()
+    assert later.indels() == inline.indels() and later.breakpoints() == inline.breakpoints() and later.profile_summary() == inline.profile_summary()
+    ref = pu.ref_results(case, ix, want_reads=False)
+    assert np.array_equal(later.profile_columns(), ref["profile"])
+    ins, dele = later.indels()
+    assert ins == ref["ins"] and dele == ref["dele"] and later.breakpoints() == ref["bp"]
+    inline.close(); later.close()
