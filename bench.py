@@ -43,6 +43,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+ALL_CPUS = os.sched_getaffinity(0)      # before any NUMA pinning: the reference arm gets every host core it was given
 
 GENOME_LEN = 248_956_422
 READ_LEN = 150               # set from the chosen config in main()
@@ -218,7 +219,7 @@ for i in range(%(runs)d):
 def time_reference(ix, text1, text2, n_sample: int, rec_bytes: int, runs: int):
     """Seconds per run of the reference's own CPU implementation on the first n_sample pairs, all host threads.
     Returns (list of seconds, kind, cores, description)."""
-    cores = os.cpu_count() or 1
+    cores = len(ALL_CPUS) or 1
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libmcref.so")
     td = tempfile.mkdtemp(prefix="mcbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     prefix = os.path.join(td, "idx")
@@ -228,7 +229,7 @@ def time_reference(ix, text1, text2, n_sample: int, rec_bytes: int, runs: int):
             f1, f2 = os.path.join(td, "r1.fq"), os.path.join(td, "r2.fq")
             text1[:n_sample * rec_bytes].tofile(f1); text2[:n_sample * rec_bytes].tofile(f2)
             code = _REF_CODE % dict(tests=os.path.join(ROOT, "tests"), prefix=prefix, cores=cores, runs=runs, f1=f1, f2=f2)
-            out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+            out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, preexec_fn=lambda: os.sched_setaffinity(0, ALL_CPUS))
             secs = [float(l.split()[1]) for l in out.stdout.splitlines() if l.startswith("SECONDS")]
             if len(secs) != runs:
                 raise RuntimeError("reference run failed: " + out.stderr[-500:])
@@ -292,7 +293,7 @@ def main():
                              % (world, "ncclAllReduce" if args.allreduce else "ncclReduceScatter (every rank finishes one genome tile)")
                              if world > 1 else "one GPU, one index replica",
               "l2_policy": "inputs larger than L2: index %.2f GB + %.1f GB of reads per batch stream from HBM" % (args.genome * 1.5 / 1e9, 2 * min(BATCH_PAIRS, args.pairs) * READ_LEN / 1e9)}
-    numa = bind_to_gpu_numa(local)
+    numa = bind_to_gpu_numa(local) if args.impl == "ours" else None
 
     if args.impl == "reference":
         if rank != 0:
