@@ -291,7 +291,9 @@ typedef struct {
     const uint8_t *text2; int64_t len2;   /* block of the second mate file, or NULL */
     int64_t max_reads;                    /* 0 = as many as the blocks hold */
     int32_t final_block;                  /* the blocks reach the end of the file(s) */
-    int32_t pad;
+    int32_t format;                       /* 0 = FASTQ (four lines per record); 1 = FASTA reads with the sequence on ONE line (two
+                                             lines per record: '>' header, bases - the FASTA branch of GetNextEntry, src/GetData.cpp:54-76,
+                                             for records that are not wrapped; a wrapped record makes the call fail with MC_ERR_ARG) */
 } mc_fastq_in;
 typedef struct { int64_t n_reads, consumed1, consumed2, n_bases;
                  int64_t records1, records2;   /* whole records the blocks held (before the cut to n_reads) */ } mc_fastq_out;

@@ -330,21 +330,22 @@ class Context:
         self._staging = getattr(self, "_staging", {}); self._staging[slot] = keep
         _check(lib().mc_stage_batch_async(self._h, C.byref(b), slot), "mc_stage_batch_async")
 
-    def ingest_fastq(self, text1, text2=None, slot: int = 0, max_reads: int = 0, final: bool = True, keep_text: bool = False) -> dict:
+    def ingest_fastq(self, text1, text2=None, slot: int = 0, max_reads: int = 0, final: bool = True, keep_text: bool = False, fasta: bool = False) -> dict:
         """Parses blocks of FASTQ text (bytes / uint8 arrays; one per mate file, or one with adjacent mates) on the device into
-        slot `slot`; returns n_reads, consumed1, consumed2, n_bases.  map_staged(slot) maps the batch."""
+        slot `slot`; returns n_reads, consumed1, consumed2, n_bases.  map_staged(slot) maps the batch.  fasta: the text is FASTA
+        with one line of bases per record."""
         t1 = np.frombuffer(text1, dtype=np.uint8) if isinstance(text1, (bytes, bytearray)) else np.ascontiguousarray(text1, dtype=np.uint8)
         t2 = None if text2 is None else (np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else np.ascontiguousarray(text2, dtype=np.uint8))
-        arg = (C.c_int64 * 6)(t1.ctypes.data, len(t1), t2.ctypes.data if t2 is not None else 0, len(t2) if t2 is not None else 0, max_reads, int(bool(final)))
+        arg = (C.c_int64 * 6)(t1.ctypes.data, len(t1), t2.ctypes.data if t2 is not None else 0, len(t2) if t2 is not None else 0, max_reads, int(bool(final)) | (int(bool(fasta)) << 32))   # final_block, format
         out = (C.c_int64 * 6)()
         _check(lib().mc_ingest_fastq(self._h, arg, slot, out), "mc_ingest_fastq")
         return dict(n_reads=int(out[0]), consumed1=int(out[1]), consumed2=int(out[2]), n_bases=int(out[3]), records1=int(out[4]), records2=int(out[5]))
 
     @staticmethod
-    def _fastq_arg(text1, text2, max_reads, final):
+    def _fastq_arg(text1, text2, max_reads, final, fasta=False):
         t1 = np.frombuffer(text1, dtype=np.uint8) if isinstance(text1, (bytes, bytearray)) else np.ascontiguousarray(text1, dtype=np.uint8)
         t2 = None if text2 is None else (np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else np.ascontiguousarray(text2, dtype=np.uint8))
-        arg = (C.c_int64 * 6)(t1.ctypes.data, len(t1), t2.ctypes.data if t2 is not None else 0, len(t2) if t2 is not None else 0, max_reads, int(bool(final)))
+        arg = (C.c_int64 * 6)(t1.ctypes.data, len(t1), t2.ctypes.data if t2 is not None else 0, len(t2) if t2 is not None else 0, max_reads, int(bool(final)) | (int(bool(fasta)) << 32))   # final_block, format
         return arg, (t1, t2)
 
     def ingest_prefetch(self, text1, text2=None, slot: int = 0):

@@ -168,7 +168,7 @@ struct PersistBumps { mc_u64 bp, ind, ind_seq, pad; };
 
 struct Staged { DBuf seq, roff, seed_off, cap, scan, flag; int64_t n_reads = 0, n_bytes = 0, n_slots = 0, base = 0; std::vector<int64_t> h_roff; bool valid = false;
 	// a slot filled by mc_ingest_fastq keeps the FASTQ text and its newline table in HBM (mc_sam_text prints names, bases and qualities from them)
-	DBuf text[2], lines[2]; int n_files = 0; bool has_text = false;
+	DBuf text[2], lines[2]; int n_files = 0; bool has_text = false; int lpr = 4;
 	const void* pre_src[2] = {nullptr, nullptr}; int64_t pre_len[2] = {0, 0}; bool prefetched = false;   // mc_ingest_prefetch
 	int n_pieces = 0; int64_t piece_end[8];
 	bool pending = false; };   // staged asynchronously: the consumer has to wait for ev_slot[] first   // read ranges [piece_end[p-1], piece_end[p]) whose bases arrive one after the other (events ev_piece[])
@@ -1309,7 +1309,10 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	if (dbg && st.prefetched) { cudaEventSynchronize(c->ev_text[slot]); t_copy = since(); }
 #endif
 	const uint8_t* text[2] = {in->text1, in->text2}; const int64_t len[2] = {in->len1, in->text2 ? in->len2 : 0};
-	FastqArgs q; memset(&q, 0, sizeof(q));
+	if (in->format != 0 && in->format != 1) { mc_set_error("mc_ingest_fastq: unknown format %d", in->format); return MC_ERR_ARG; }
+	const int lpr = in->format == 1 ? 2 : 4;      // lines per record
+	st.lpr = lpr;
+	FastqArgs q; memset(&q, 0, sizeof(q)); q.lpr = lpr;
 	DBuf* d_text = st.text; DBuf* d_cnt = c->fq_cnt; DBuf* d_off = c->fq_off; DBuf* d_lines = st.lines;
 	DBuf& d_scan = c->fq_scan; DBuf& d_rlen = c->fq_rlen; DBuf& d_rsrc = c->fq_rsrc;   // kept between calls: no allocation in the steady state
 	auto done = [&](int rc) { if (dbg) fprintf(stderr, "[mc] ingest slot %d: %.1f MB, text on the device after %.3f ms, lines counted after %.3f ms, staged after %.3f ms\n", slot, (in->len1 + (in->text2 ? in->len2 : 0)) / 1e6, t_copy, t_lines, since()); st.prefetched = false; return rc; };
@@ -1334,7 +1337,7 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	for (int f = 0; f < nf; f++)
 	{
 		open_end[f] = in->final_block && len[f] > 0 && text[f][len[f] - 1] != '\n';
-		const int64_t rec = (n_lines[f] + (open_end[f] ? 1 : 0)) / 4;
+		const int64_t rec = (n_lines[f] + (open_end[f] ? 1 : 0)) / lpr;
 		(f == 0 ? out->records1 : out->records2) = rec;
 		n_rec = n_rec < 0 ? rec : std::min(n_rec, rec);
 	}
@@ -1365,7 +1368,7 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	int64_t cons[2] = {0, 0};
 	for (int f = 0; f < nf; f++)
 	{
-		const int64_t last_line = 4 * n_rec - 1;                           // index of the last consumed line
+		const int64_t last_line = lpr * n_rec - 1;                         // index of the last consumed line
 		if (last_line < n_lines[f]) bad |= dev_d2h(&cons[f], q.line_end[f] + last_line, 8, s); else cons[f] = len[f] - 1;
 	}
 	bad |= d_rlen.reserve((size_t)(n + 1) * 4) || d_rsrc.reserve((size_t)n * 8) || st.roff.reserve((size_t)(n + 1) * 8) || d_scan.reserve(device_scan_scratch_bytes(n + 1));
@@ -1392,6 +1395,7 @@ int mc_ingest_fastq(mc_ctx* c, const mc_fastq_in* in, int32_t slot, mc_fastq_out
 	mc_u64 flag = 0;
 	bad |= dev_d2h(&flag, st.flag.p, 8, s);
 	if (bad || dev_sync(s)) return done(MC_ERR_CUDA);
+	if (flag >> 57) { mc_set_error("mc_ingest_fastq: FASTA records with the sequence on several lines (or text that is not FASTA): only one line of bases per record is parsed on the device"); return done(MC_ERR_ARG); }
 	if (flag) { mc_set_error("mc_ingest_fastq: a record has an empty read or one longer than %d bases", MC_MAX_RLEN); return done(MC_ERR_ARG); }
 	st.valid = true; st.has_text = true;
 	return done(MC_OK);
@@ -1444,7 +1448,7 @@ int mc_sam_text(mc_ctx* c, int32_t slot, int32_t all_best, const uint8_t** text,
 	SamTextArgs t; memset(&t, 0, sizeof(t));
 	sam_args_of(c, t.s, n, d_tab);
 	for (int f = 0; f < st.n_files; f++) { t.text[f] = st.text[f].as<uint8_t>(); t.line_end[f] = st.lines[f].as<int64_t>() + 1; }
-	t.two_files = st.n_files == 2; t.unique = all_best ? 0 : 1;
+	t.two_files = st.n_files == 2; t.unique = all_best ? 0 : 1; t.lpr = st.lpr;
 	t.chrom_names = c->d_chrom_names.as<uint8_t>(); t.chrom_name_off = c->d_chrom_name_off.as<int32_t>();
 	t.tlen = d_len.as<uint32_t>(); t.toff = d_off.as<int64_t>();
 	launch_samtext(t, n, false, s);

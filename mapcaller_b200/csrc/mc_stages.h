@@ -412,6 +412,7 @@ struct FastqArgs {
 	const uint8_t* text[2]; int64_t len[2];       // one text per mate file; text[1] == 0: mates are adjacent records of text[0]
 	uint32_t* tile_cnt[2]; const int64_t* tile_off[2]; int64_t* line_end[2]; int64_t n_lines[2];   // newline positions
 	int64_t n_reads; uint32_t* rlen; int64_t* rsrc; const int64_t* roff; uint8_t* seq; mc_u64* flag;
+	int lpr;                                      // lines per record: 4 (FASTQ) or 2 (FASTA with one sequence line per record)
 };
 // A tile is 64 bytes = four 128-bit loads per thread (the text buffer is padded to a multiple of 64); the newline bytes
 // of a 32-bit word are found with the zero-byte trick on word ^ 0x0A0A0A0A.
@@ -463,9 +464,11 @@ MC_HD void fqread_body(int64_t r, const FastqArgs& q)
 {
 	const int f = q.text[1] ? (int)(r & 1) : 0;
 	const int64_t rec = q.text[1] ? (r >> 1) : r;
-	const int64_t beg = q.line_end[f][4 * rec] + 1, end = q.line_end[f][4 * rec + 1];
+	const int64_t beg = q.line_end[f][q.lpr * rec] + 1, end = q.line_end[f][q.lpr * rec + 1];
 	int64_t n = end - beg;
 	if (n <= 0 || n > MC_MAX_RLEN) { mc_atomic_or(q.flag, (mc_u64)1 << 56); n = 1; }
+	// FASTA: every record is a '>' line and ONE line of bases; a wrapped record shifts a line of bases to where a header should be
+	if (q.lpr == 2 && (q.text[f][q.line_end[f][2 * rec - 1] + 1] != '>' || q.text[f][beg] == '>')) mc_atomic_or(q.flag, (mc_u64)1 << 57);
 	q.rlen[r] = (uint32_t)n; q.rsrc[r] = beg;
 }
 MC_HD void fqcopy_body(int64_t r, int lane, int nl, const FastqArgs& q)

@@ -171,7 +171,7 @@ MC_HD void samrec_body(int64_t r, const SamArgs& a, bool emit)
 struct SamTextArgs {
 	SamArgs s;
 	const uint8_t* text[2]; const int64_t* line_end[2];   // FASTQ text of the batch and its newline table (line_end[-1] = -1)
-	int32_t two_files, unique;
+	int32_t two_files, unique, lpr;              // lpr: lines per record of the text (4 FASTQ, 2 FASTA: no qualities, QUAL is "*")
 	const uint8_t* chrom_names; const int32_t* chrom_name_off;   // names back to back, n_chrom + 1 offsets
 	uint32_t* tlen; const int64_t* toff; uint8_t* out;
 };
@@ -204,6 +204,7 @@ MC_HD void sam_put_seq(SamWriter& w, const uint8_t* seq, int n, bool reverse, bo
 }
 MC_HD void sam_put_qual(SamWriter& w, const uint8_t* q, int n, bool reverse)
 {
+	if (!q) { w.ch('*'); return; }            // FASTA reads: no qualities (src/SamReport.cpp:332,351)
 	if (!reverse) { w.bytes(q, n); return; }
 	if (w.p) for (int i = 0; i < n; i++) w.p[w.at + i] = q[n - 1 - i];
 	w.at += n;
@@ -216,10 +217,10 @@ MC_HD void samtext_body(int64_t r, const SamTextArgs& t, bool emit)
 	// the read's record in the FASTQ text: header line, bases, '+' line, qualities
 	const int f = t.two_files ? (int)(r & 1) : 0;
 	const int64_t rec = t.two_files ? (r >> 1) : r;
-	const int64_t* le = t.line_end[f] + 4 * rec;
+	const int64_t* le = t.line_end[f] + t.lpr * rec;
 	const uint8_t* hdr = t.text[f] + le[-1] + 1; const int hlen = (int)(le[0] - le[-1]);   // including the newline, as getline() counts
 	const uint8_t* seq = t.text[f] + le[0] + 1; const int rlen = (int)(le[1] - le[0] - 1);
-	const uint8_t* qual = t.text[f] + le[2] + 1;
+	const uint8_t* qual = t.lpr == 4 ? t.text[f] + le[2] + 1 : nullptr;
 	int p1 = hlen - 1, p2 = (hlen > 100 ? 100 : hlen) - 1;
 	for (int i = 1; i < hlen; i++) if (hdr[i] != '>' && hdr[i] != '@') { p1 = i; break; }
 	for (int i = 1; i < (hlen > 100 ? 100 : hlen); i++) if (hdr[i] == ' ' || hdr[i] == '/' || hdr[i] < 0x20 || hdr[i] > 0x7E) { p2 = i; break; }

@@ -166,7 +166,10 @@ void Mapping()
 		// .gz FASTQ takes the same road: the two mate files are inflated block-wise by zlib (gzread, one host thread per file)
 		// and the device parses the inflated text - no per-line gzgets, no per-read allocation (gzGetNextEntry,
 		// src/GetData.cpp:101-131; its 1024-byte line buffer is the one difference: longer lines are not cut here).
-		if (FastQFormat && (!bSAMoutput || getenv("MC_B200_HOST_SAM") == NULL))
+		// FASTA reads take it as well when every record keeps its bases on one line (mc_fastq_in.format = 1); the device checks that,
+		// and a file with wrapped records is handed back to the reference's reader before anything has been mapped from it.
+		bool device_reader = !bSAMoutput || getenv("MC_B200_HOST_SAM") == NULL;
+		if (device_reader)
 		{
 			if (lib.gz) { gzbuffer(lib.g1, 1 << 20); if (lib.g2) gzbuffer(lib.g2, 1 << 20); }
 			auto read_block = [&lib](int which, uint8_t* dst, size_t n) -> size_t {
@@ -177,7 +180,7 @@ void Mapping()
 			};
 			// MC_B200_FASTQ_BLOCK (bytes) overrides the 64 MiB block size - the tests use it to cross many block boundaries with small files
 			const size_t BLK = getenv("MC_B200_FASTQ_BLOCK") ? (size_t)atoll(getenv("MC_B200_FASTQ_BLOCK")) : (size_t)64 << 20;
-			vector<uint8_t> b1, b2; size_t have1 = 0, have2 = 0; bool eof1 = false, eof2 = !lib.sep, force_final = false;
+			vector<uint8_t> b1, b2; size_t have1 = 0, have2 = 0; bool eof1 = false, eof2 = !lib.sep, force_final = false, first_block = true;
 			for (;;)
 			{
 				// a file that reached its end just stops growing; its carried-over records are still consumed block by block
@@ -196,8 +199,15 @@ void Mapping()
 				const bool last = (eof1 && eof2) || force_final;   // only then may a ragged tail (not a multiple of 200 reads) be mapped
 				mc_fastq_in fi; memset(&fi, 0, sizeof(fi));
 				fi.text1 = b1.data(); fi.len1 = (int64_t)have1; fi.text2 = lib.sep ? b2.data() : NULL; fi.len2 = (int64_t)have2; fi.final_block = last;
+				fi.format = FastQFormat ? 0 : 1;
 				mc_fastq_out fo;
-				if (mc_ingest_fastq(ctx, &fi, 0, &fo)) die("mc_ingest_fastq");
+				if (mc_ingest_fastq(ctx, &fi, 0, &fo))
+				{
+					if (FastQFormat || !first_block) die("mc_ingest_fastq");
+					device_reader = false;          // wrapped FASTA records: back to the start, the reference's reader takes the library
+					break;
+				}
+				first_block = false;
 				if (fo.n_reads > 0)
 				{
 					mc_batch_out out;
@@ -222,8 +232,12 @@ void Mapping()
 					if (eof1 ? left2 > left1 : left1 > left2) force_final = true;
 				}
 			}
-			if (lib.gz) { gzclose(lib.g1); if (lib.g2) gzclose(lib.g2); } else { fclose(lib.f1); if (lib.f2) fclose(lib.f2); }
-			continue;
+			if (device_reader)
+			{
+				if (lib.gz) { gzclose(lib.g1); if (lib.g2) gzclose(lib.g2); } else { fclose(lib.f1); if (lib.f2) fclose(lib.f2); }
+				continue;
+			}
+			if (lib.gz) { gzrewind(lib.g1); if (lib.g2) gzrewind(lib.g2); } else { rewind(lib.f1); if (lib.f2) rewind(lib.f2); }
 		}
 		vector<ReadItem_t> reads; vector<uint8_t> seq; vector<int64_t> off; vector<string> sam;
 		while (pull_batch(lib, reads) > 0)

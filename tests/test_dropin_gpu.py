@@ -41,7 +41,9 @@ def vcf_body(path):
 # one line per best candidate); *_hostsam: MC_B200_HOST_SAM=1, the reference's reader + SamReport.o over the downloaded candidates;
 # *_gz: gzip'ed FASTQ (the reference's gz reader feeds mc_map_batch); *_vcfonly: no SAM.  In every mode the VCF comes from the
 # unchanged VariantCalling() with IdentifyVariants answered by mc_variant_scan.
-@pytest.mark.parametrize("mode", ["pe_nw", "pe_ksw2_monomorphic", "se_nw", "pe_nw_vcfonly", "se_nw_vcfonly", "pe_nw_m", "pe_nw_hostsam", "pe_nw_gz"])
+# *_fasta: FASTA reads, one line of bases per record - parsed on the device like FASTQ (QUAL is "*"); *_fasta_wrapped: bases on
+# several lines - the device refuses the first block and the reference's reader takes the library.
+@pytest.mark.parametrize("mode", ["pe_nw", "pe_ksw2_monomorphic", "se_nw", "pe_nw_vcfonly", "se_nw_vcfonly", "pe_nw_m", "pe_nw_hostsam", "pe_nw_gz", "pe_nw_fasta", "pe_nw_fasta_wrapped"])
 def test_same_sam_and_vcf_as_the_reference_cli(tmp_path, mode):
     case = pu.make_case(seed=41, n_pairs=6000, genome_len=120000, contigs=2, sv=3.0)
     fa = str(tmp_path / "ref.fa")
@@ -63,6 +65,15 @@ def test_same_sam_and_vcf_as_the_reference_cli(tmp_path, mode):
             with open(f, "rb") as src, gzip.open(f + ".gz", "wb", compresslevel=1) as dst:
                 dst.write(src.read())
         f1, f2 = f1 + ".gz", f2 + ".gz"
+    if "_fasta" in mode:
+        width = 60 if mode.endswith("_wrapped") else 0
+        for f, r, mate in ((f1, case["r1"], 1), (f2, case["r2"], 2)):
+            with open(f[:-3] + ".fa", "wb") as fh:
+                for i, row in enumerate(r):
+                    b = row.tobytes()
+                    fh.write(b">r%09d/%d\n" % (i, mate))
+                    fh.write(b"\n".join(b[k:k + width] for k in range(0, len(b), width)) + b"\n" if width else b + b"\n")
+        f1, f2 = f1[:-3] + ".fa", f2[:-3] + ".fa"
     env = dict(os.environ)
     if mode.endswith("_hostsam"):
         env["MC_B200_HOST_SAM"] = "1"
