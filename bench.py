@@ -422,9 +422,11 @@ def main():
     blocks = []
     for b, (p0, p1) in enumerate(bounds):
         cuts = [0, p1 - p0]
-        if b == 0 and p1 - p0 > FIRST:
+        if world > 1:
+            pass   # N ranks on one library: file order = rank after rank inside every batch, so both legs must cut the library alike
+        elif b == 0 and p1 - p0 > FIRST:
             cuts.insert(1, FIRST)                      # a small first block: mapping starts early
-        if b == len(bounds) - 1 and cuts[-1] - cuts[-2] > FIRST:
+        if world == 1 and b == len(bounds) - 1 and cuts[-1] - cuts[-2] > FIRST:
             cuts.insert(len(cuts) - 1, p1 - p0 - FIRST)  # and a small last one: little is left to map when the last byte has arrived
         for c0, c1 in zip(cuts[:-1], cuts[1:]):
             blocks.append((ptext[b][0][c0 * rec_bytes:c1 * rec_bytes], ptext[b][1][c0 * rec_bytes:c1 * rec_bytes]))
