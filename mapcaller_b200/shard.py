@@ -34,3 +34,31 @@ def merge_totals(parts):
     out = {k: int(sum(p[k] for p in parts)) for k in keys}
     out["avg_dist"] = int(1.0 * out["total_distance"] / out["total_paired"] + 0.5) if out["total_paired"] > 1000 else 1000
     return out
+
+
+# ---- genome tiles of mc_profile_reduce_scatter (csrc/mc_ctx.cu: profile_reduce) ----------------------------------------------
+TILE_ALIGN = 25600   # columns: a multiple of the 1024-column prefix blocks and of the 100-column variant-scan blocks
+
+
+def tile_size(genome: int, world: int) -> int:
+    """Columns per rank: equal tiles of whole TILE_ALIGN units that cover the genome."""
+    per = (genome + world - 1) // world
+    return (per + TILE_ALIGN - 1) // TILE_ALIGN * TILE_ALIGN
+
+
+def tile_bounds(genome: int, world: int, rank: int):
+    """[begin, end) columns whose counters `rank` holds after the reduce-scatter (possibly empty for the last ranks of a tiny genome)."""
+    t = tile_size(genome, world)
+    return min(genome, rank * t), min(genome, (rank + 1) * t)
+
+
+def prefix_with_carry(tile_diff: np.ndarray, totals_of_all_ranks, rank: int) -> np.ndarray:
+    """Coverage of the tile's columns from its difference-array entries: the running sum inside the tile plus the sums of all
+    entries before it = the tile totals of the earlier ranks (what profile_prefix plants in front of the tile)."""
+    carry = sum(totals_of_all_ranks[:rank])
+    return np.cumsum(tile_diff, axis=0) + carry
+
+
+def run_carry(last_seen_of_all_ranks, rank: int) -> int:
+    """Last non-gap (non-dup) column before the tile: the maximum over the earlier ranks, -1 if none (mc_variant_scan)."""
+    return max([-1] + [int(x) for x in last_seen_of_all_ranks[:rank]])
