@@ -1970,7 +1970,7 @@ static int profile_reduce(mc_ctx* c, void* nccl_comm, bool scatter)
 	}
 	// equal tiles of whole MC_TILE_ALIGN units, one per rank (the arrays are padded for it, mc_ctx_create)
 	const size_t T = ((G + (size_t)c->comm_size - 1) / (size_t)c->comm_size + MC_TILE_ALIGN - 1) / MC_TILE_ALIGN * MC_TILE_ALIGN, me = (size_t)c->comm_rank;
-	if (scatter && (comm != c->comm || c->comm_size > 16)) { mc_set_error("mc_profile_reduce_scatter: needs the communicator of mc_comm_init and at most 16 ranks"); return MC_ERR_ARG; }
+	if (scatter && (comm != c->comm || c->comm_size > 16 || independent)) { mc_set_error("mc_profile_reduce_scatter: needs the communicator of mc_comm_init with the ordered exchange on (independent shards end with mc_profile_allreduce) and at most 16 ranks"); return MC_ERR_ARG; }
 	nccl_api()->GroupStart();
 	// packed 2 x uint16 counters are summed as uint32 words: no carry can cross the halves while every column stays below 65536
 	if (!scatter)
